@@ -1,0 +1,142 @@
+/*
+ * salun.h -- C ABI of libsalun.so, the B200-native (sm_100a) SalUn engine.
+ *
+ * The reference (OPTML-Group/Unlearn-Saliency) has no FFI: its hot path is Python calling
+ * ATen.  This header is the boundary a maintainer binds instead (ctypes stub in
+ * INTEGRATION.md): every entry point names the reference lines it replaces.  Citations
+ * are relative to the reference checkout.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only, no torch types.  `stream` is a cudaStream_t passed as
+ *     void* (0 = legacy default stream).  Every call only ENQUEUES work on `stream` unless
+ *     stated otherwise; buffers are owned by the caller (PyTorch) and must stay alive until
+ *     the stream reaches the enqueued work.
+ *   - pointers are DEVICE pointers unless the parameter name ends in `_host`.
+ *   - return 0 on success, negative salun_status otherwise; salun_last_error() returns a
+ *     thread-local message for the last failure on the calling thread.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point returns
+ *     SALUN_ERR_CUDA.
+ *   - mask_bits: packed 1-bit mask, element i is bit (i & 31) of word (i >> 5); the buffer
+ *     holds (n + 31) / 32 words and padding bits are zero.  The on-disk format stays the
+ *     reference's dict{name: int64 0/1 tensor} (Classification/generate_mask.py:76-82).
+ */
+#ifndef SALUN_H_
+#define SALUN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum salun_status {
+  SALUN_OK = 0,
+  SALUN_ERR_INVALID = -1, /* bad argument (null pointer, negative size, misaligned buffer) */
+  SALUN_ERR_CUDA = -2,    /* a CUDA runtime / driver call failed, see salun_last_error() */
+  SALUN_ERR_STATE = -3,   /* object used in the wrong state (e.g. backward before forward) */
+  SALUN_ERR_UNSUPPORTED = -4
+} salun_status;
+
+typedef struct salun_ctx salun_ctx;
+
+/* ABI version: major*1000 + minor */
+int salun_version(void);
+const char *salun_last_error(void);
+
+/* One context per (thread, device).  Owns the small device workspaces (radix-select
+ * histograms, reduction partials) and a pinned host mailbox.  Not thread-safe: use one
+ * context per thread/stream. */
+int salun_ctx_create(int device, salun_ctx **out);
+int salun_ctx_destroy(salun_ctx *ctx);
+
+/* ---------------------------------------------------------------------------------------
+ * (i) saliency mask generation tail
+ * ------------------------------------------------------------------------------------- */
+
+/* accum_flat[off_t + j] += scale * grads[t][j]   for every tensor t, j < numels[t]
+ * replaces  gradients[name] += param.grad.data        Classification/generate_mask.py:41-44
+ *                                                      DDPM/runners/diffusion.py:992-996 (no .cpu() round trip)
+ *                                                      SD/train-scripts/generate_mask.py:66-69
+ * grads_host / numels_host: HOST arrays of n_tensors device pointers / element counts, laid
+ * out back to back in accum_flat in the given order (= model.named_parameters() order).
+ * scale_dev: optional device scalar (e.g. the clip coefficient of runners/diffusion.py:985-990);
+ * NULL means 1. */
+int salun_saliency_accumulate(salun_ctx *ctx, const float *const *grads_host,
+                              const int64_t *numels_host, int n_tensors, float *accum_flat,
+                              const float *scale_dev, void *stream);
+
+/* accum[i] += scale * grad[i] on one flat arena (the engine's own gradient layout). */
+int salun_saliency_accumulate_flat(salun_ctx *ctx, const float *grad, float *accum, int64_t n,
+                                   const float *scale_dev, void *stream);
+
+/* a[i] = |a[i]|       replaces torch.abs_  generate_mask.py:46-48 */
+int salun_abs_inplace(salun_ctx *ctx, float *a, int64_t n, void *stream);
+
+typedef struct salun_topk_info {
+  uint32_t thr_key;  /* key(|g|) of the k-th largest element; key = bits(|g|)+1, NaN -> 0 */
+  float thr_value;   /* |g| of the k-th largest element */
+  int64_t n_greater; /* elements strictly above the threshold */
+  int64_t n_equal;   /* elements equal to the threshold (ties); k - n_greater of them are selected */
+} salun_topk_info;
+
+/* Global top-k saliency mask: element i gets 1 iff its rank in descending |accum| is < k.
+ * replaces  all_elements = -cat(...); argsort; argsort; ranks < k   generate_mask.py:57-80
+ *           DDPM/runners/diffusion.py:1006-1037, SD/train-scripts/generate_mask.py:78-106
+ * with a 3-pass radix select (no sort).  `accum` may be signed: |.| is applied on the fly.
+ * Ties at the threshold are resolved in flat order (stable-argsort semantics); NaN ranks last.
+ * k is computed by the caller as int(n * ratio) in double arithmetic (generate_mask.py:60).
+ * mask_i64 / mask_bits: either may be NULL.  info_host: optional HOST struct; when non-NULL
+ * the call synchronises `stream` before returning. */
+int salun_topk_mask(salun_ctx *ctx, const float *accum, int64_t n, int64_t k, int64_t *mask_i64,
+                    uint32_t *mask_bits, salun_topk_info *info_host, void *stream);
+
+/* int64 {0,1} <-> packed bits (loading / saving the reference's on-disk mask) */
+int salun_pack_mask(salun_ctx *ctx, const int64_t *mask_i64, int64_t n, uint32_t *mask_bits,
+                    void *stream);
+int salun_unpack_mask(salun_ctx *ctx, const uint32_t *mask_bits, int64_t n, int64_t *mask_i64,
+                      void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (ii) masked unlearning step tail
+ * ------------------------------------------------------------------------------------- */
+
+/* g[i] *= m[i]     replaces _apply_mask_to_grads  Classification/unlearn/RL.py:11-14
+ *                  DDPM/runners/diffusion.py:589-592 (incl. its 309 MB per-step H2D), SD/train-scripts/train-esd.py:318-321 */
+int salun_apply_mask(salun_ctx *ctx, float *g, const uint32_t *mask_bits, int64_t n,
+                     void *stream);
+
+/* Fused  mask(.)grad -> SGD(momentum, weight decay) -> restore  on a flat arena:
+ *   m=1: g' = g + wd*p ; v = momentum*v + g' ; p = p - lr*v        m=0: p untouched, v = 0
+ * replaces  _apply_mask_to_grads + optimizer.step() + _restore_masked_params
+ *           Classification/unlearn/RL.py:134-140 (same in GA.py:119-125, FT.py:137-142)
+ *           with torch.optim.SGD built at Classification/unlearn/impl.py:68-73.
+ * v must be zero-initialised before the first step (torch's "buf = clone(g')" first step is
+ * then reproduced exactly).  mask_bits == NULL: plain SGD on every coordinate. */
+int salun_masked_sgd_step(salun_ctx *ctx, float *p, const float *g, float *v,
+                          const uint32_t *mask_bits, int64_t n, float lr, float momentum,
+                          float wd, void *stream);
+
+/* sumsq_dev[0] = sum_i g[i]^2 in double (deterministic two-stage reduction).
+ * replaces the norm inside clip_grad_norm_   DDPM/runners/diffusion.py:582-587,985-990 */
+int salun_grad_sumsq(salun_ctx *ctx, const float *g, int64_t n, double *sumsq_dev, void *stream);
+
+/* coef_dev[0] = min(1, max_norm / (sqrt(sumsq_dev[0]) + 1e-6))   (torch clip_grad_norm_) */
+int salun_clip_coef(salun_ctx *ctx, const double *sumsq_dev, float max_norm, float *coef_dev,
+                    void *stream);
+
+/* Fused  clip -> mask(.)grad -> Adam  on a flat arena (torch.optim.Adam arithmetic, amsgrad off):
+ *   g = coef*g*m ; m1 += (g-m1)(1-b1) ; m2 = b2*m2 + (1-b2) g^2 ;
+ *   p -= lr/(1-b1^t) * m1 / (sqrt(m2)/sqrt(1-b2^t) + eps)
+ * replaces  clip_grad_norm_ + mask multiply + optimizer.step()
+ *           DDPM/runners/diffusion.py:582-593 with Adam from DDPM/functions/__init__.py:9-18;
+ *           SD/train-scripts/train-esd.py:318-323, random_label.py:132-139 (coef_dev = NULL: no clip).
+ * step is 1-based.  mask_bits == NULL: no mask. */
+int salun_masked_adam_step(salun_ctx *ctx, float *p, const float *g, float *m1, float *m2,
+                           const uint32_t *mask_bits, int64_t n, float lr, float beta1,
+                           float beta2, float eps, float wd, int64_t step,
+                           const float *coef_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SALUN_H_ */

@@ -1,0 +1,93 @@
+"""ctypes binding of libsalun.so (the C ABI declared in include/salun.h).
+
+There is no fallback: if the shared library is missing or a call fails, a RuntimeError is
+raised.  Nothing here (or anywhere in this package) imports ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libsalun.so")
+
+_lib = None
+
+
+class salun_topk_info(C.Structure):
+    _fields_ = [
+        ("thr_key", C.c_uint32),
+        ("thr_value", C.c_float),
+        ("n_greater", C.c_int64),
+        ("n_equal", C.c_int64),
+    ]
+
+
+_P = C.c_void_p
+_I64 = C.c_int64
+_F = C.c_float
+
+# name -> argtypes (restype is always int unless listed in _RESTYPES)
+_SIGNATURES = {
+    "salun_version": [],
+    "salun_last_error": [],
+    "salun_ctx_create": [C.c_int, C.POINTER(_P)],
+    "salun_ctx_destroy": [_P],
+    "salun_saliency_accumulate": [_P, C.POINTER(_P), C.POINTER(_I64), C.c_int, _P, _P, _P],
+    "salun_saliency_accumulate_flat": [_P, _P, _P, _I64, _P, _P],
+    "salun_abs_inplace": [_P, _P, _I64, _P],
+    "salun_topk_mask": [_P, _P, _I64, _I64, _P, _P, C.POINTER(salun_topk_info), _P],
+    "salun_pack_mask": [_P, _P, _I64, _P, _P],
+    "salun_unpack_mask": [_P, _P, _I64, _P, _P],
+    "salun_apply_mask": [_P, _P, _P, _I64, _P],
+    "salun_masked_sgd_step": [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _P],
+    "salun_grad_sumsq": [_P, _P, _I64, _P, _P],
+    "salun_clip_coef": [_P, _P, _F, _P, _P],
+    "salun_masked_adam_step": [_P, _P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I64, _P, _P],
+}
+_RESTYPES = {"salun_last_error": C.c_char_p}
+
+
+def exported_symbols():
+    """Every symbol include/salun.h declares (used by the CPU-side ABI test)."""
+    return sorted(set(_SIGNATURES) | set(_EXTRA_SIGNATURES))
+
+
+_EXTRA_SIGNATURES: dict = {}
+
+
+def register_signatures(sigs: dict, restypes: dict | None = None):
+    """Other modules of the package (gemm / resnet engine) register their entry points here."""
+    _EXTRA_SIGNATURES.update(sigs)
+    if restypes:
+        _RESTYPES.update(restypes)
+    if _lib is not None:
+        _bind(_lib, sigs)
+
+
+def _bind(lib, sigs):
+    for name, argtypes in sigs.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export it: fail loudly
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, C.c_int)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"libsalun.so not found at {LIB_PATH}: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C unlearn_saliency_b200/csrc`). There is no CPU / PyTorch fallback."
+            )
+        l = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        _bind(l, _SIGNATURES)
+        _bind(l, _EXTRA_SIGNATURES)
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().salun_last_error()
+        raise RuntimeError(f"libsalun {what} failed (status {rc}): {msg.decode() if msg else '?'}")

@@ -1,0 +1,731 @@
+// salun_tail.cu -- HBM-bound tail of the SalUn hot path for sm_100a.
+//
+//   (i)  saliency accumulate, |.|, global top-k mask by 3-pass radix select   (include/salun.h)
+//   (ii) mask (.) grad, fused masked SGD+restore, grad-norm clip, fused masked Adam
+//
+// All kernels are streaming kernels bounded by HBM bandwidth: 16-byte vector loads/stores,
+// persistent grids of (#SMs x 8) CTAs x 256 threads, no shared-memory staging (no reuse).
+// Floating point uses explicit __fmul_rn/__fadd_rn so the sequence of roundings equals
+// oracle/salun_oracle.c (built with -ffp-contract=off) and results compare bit-exactly.
+#include <math.h>
+#include <stdarg.h>
+
+#include "salun_common.cuh"
+
+namespace salun {
+
+static thread_local char g_err[512] = "";
+char *err_buf() { return g_err; }
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+constexpr int kThreads = 256;
+
+static inline int grid_for(const salun_ctx *ctx, int64_t n_vec) {
+  int64_t want = (n_vec + kThreads - 1) / kThreads;
+  int64_t cap = (int64_t)ctx->num_sms * 8;
+  if (cap > kMaxPartials) cap = kMaxPartials;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+__device__ __forceinline__ uint32_t sal_key(float a) {
+  uint32_t b = __float_as_uint(a) & 0x7fffffffu;
+  return b > 0x7f800000u ? 0u : b + 1u;  // NaN ranks last (torch.argsort semantics), else monotone
+}
+
+// guarded 4-wide load: elements past n read as `pad`
+__device__ __forceinline__ float4 load4(const float *__restrict__ a, int64_t i, int64_t n, float pad) {
+  if (i + 3 < n) return *reinterpret_cast<const float4 *>(a + i);
+  float4 r = make_float4(pad, pad, pad, pad);
+  if (i < n) r.x = a[i];
+  if (i + 1 < n) r.y = a[i + 1];
+  if (i + 2 < n) r.z = a[i + 2];
+  return r;
+}
+__device__ __forceinline__ void store4(float *__restrict__ a, int64_t i, int64_t n, float4 v) {
+  if (i + 3 < n) {
+    *reinterpret_cast<float4 *>(a + i) = v;
+    return;
+  }
+  if (i < n) a[i] = v.x;
+  if (i + 1 < n) a[i + 1] = v.y;
+  if (i + 2 < n) a[i + 2] = v.z;
+}
+__device__ __forceinline__ uint32_t mask_nibble(const uint32_t *__restrict__ bits, int64_t i) {
+  // i is a multiple of 4: the 4 mask bits of elements i..i+3 sit in one word
+  return bits ? (__ldg(bits + (i >> 5)) >> (i & 31)) & 0xFu : 0xFu;
+}
+
+// ------------------------------------------------------------------------------------------
+// accumulate / abs
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_accum_flat(const float *__restrict__ g, float *__restrict__ acc,
+                                                         int64_t n, const float *__restrict__ scale) {
+  const float s = scale ? *scale : 1.0f;
+  const bool scaled = scale != nullptr;
+  int64_t stride = (int64_t)gridDim.x * kThreads * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4; i < n; i += stride) {
+    float4 a = load4(acc, i, n, 0.f), b = load4(g, i, n, 0.f);
+    if (scaled) {
+      b.x = __fmul_rn(b.x, s); b.y = __fmul_rn(b.y, s); b.z = __fmul_rn(b.z, s); b.w = __fmul_rn(b.w, s);
+    }
+    a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
+    store4(acc, i, n, a);
+  }
+}
+
+constexpr int kTabMax = 96;
+struct TensorTable {
+  const float *src[kTabMax];
+  long long dst_off[kTabMax];
+  long long numel[kTabMax];
+};
+// one grid row per tensor (blockIdx.y); tensors are separately allocated (param.grad), the
+// destination offsets are arbitrary, so accesses are 4-byte coalesced rather than 16-byte.
+__global__ void __launch_bounds__(kThreads) k_accum_multi(TensorTable tab, float *__restrict__ acc,
+                                                          const float *__restrict__ scale) {
+  const float s = scale ? *scale : 1.0f;
+  const bool scaled = scale != nullptr;
+  const float *__restrict__ src = tab.src[blockIdx.y];
+  float *__restrict__ dst = acc + tab.dst_off[blockIdx.y];
+  const long long n = tab.numel[blockIdx.y];
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+    float b = src[i];
+    if (scaled) b = __fmul_rn(b, s);
+    dst[i] = __fadd_rn(dst[i], b);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_abs(float *__restrict__ a, int64_t n) {
+  int64_t stride = (int64_t)gridDim.x * kThreads * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4; i < n; i += stride) {
+    float4 v = load4(a, i, n, 0.f);
+    v.x = fabsf(v.x); v.y = fabsf(v.y); v.z = fabsf(v.z); v.w = fabsf(v.w);
+    store4(a, i, n, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// radix select: key = 32 bits split 11 | 11 | 10 (most significant first)
+// sel[0]=prefix sel[1]=prefix_mask sel[2]=remaining sel[3]=thr sel[4]=n_gt sel[5]=n_eq
+// sel[6]=need sel[7]=ordered_ties
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pass_shift(int pass) { return pass == 0 ? 21 : (pass == 1 ? 10 : 0); }
+__device__ __forceinline__ int pass_bins(int pass) { return pass == 2 ? 1024 : 2048; }
+
+__global__ void __launch_bounds__(kThreads) k_radix_hist(const float *__restrict__ a, int64_t n,
+                                                         const unsigned long long *__restrict__ sel,
+                                                         unsigned int *__restrict__ hist, int pass) {
+  __shared__ unsigned int sh[kRadixBins];
+  for (int i = threadIdx.x; i < kRadixBins; i += kThreads) sh[i] = 0;
+  __syncthreads();
+  const uint32_t prefix = (uint32_t)sel[0], pmask = (uint32_t)sel[1];
+  const int shift = pass_shift(pass);
+  const uint32_t dmask = pass_bins(pass) - 1;
+  int64_t stride = (int64_t)gridDim.x * kThreads * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4; i < n; i += stride) {
+    float4 v = load4(a, i, n, 0.f);
+    uint32_t k0 = sal_key(v.x), k1 = sal_key(v.y), k2 = sal_key(v.z), k3 = sal_key(v.w);
+    if ((k0 & pmask) == prefix) atomicAdd(&sh[(k0 >> shift) & dmask], 1u);
+    if (i + 1 < n && (k1 & pmask) == prefix) atomicAdd(&sh[(k1 >> shift) & dmask], 1u);
+    if (i + 2 < n && (k2 & pmask) == prefix) atomicAdd(&sh[(k2 >> shift) & dmask], 1u);
+    if (i + 3 < n && (k3 & pmask) == prefix) atomicAdd(&sh[(k3 >> shift) & dmask], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kRadixBins; i += kThreads)
+    if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+// one warp: walk the histogram from the top digit, pick the digit holding rank `remaining`
+__global__ void k_radix_pick(unsigned int *__restrict__ hist, unsigned long long *__restrict__ sel, int pass,
+                             long long k) {
+  const int lane = threadIdx.x;
+  const int bins = pass_bins(pass);
+  const int per = bins / 32;
+  const unsigned long long remaining = sel[2], prefix_in = sel[0], pmask_in = sel[1];  // read before any lane writes
+  // lane 0 owns the TOP `per` digits
+  const int top = bins - 1 - lane * per;
+  unsigned long long mine = 0;
+  for (int j = 0; j < per; ++j) mine += hist[top - j];
+  unsigned long long incl = mine;
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  unsigned long long excl = incl - mine;
+  const bool owner = remaining > excl && remaining <= incl;
+  if (owner) {
+    unsigned long long r = remaining - excl;
+    int d = top;
+    for (int j = 0; j < per; ++j, --d) {
+      unsigned long long h = hist[d];
+      if (r <= h) break;
+      r -= h;
+    }
+    const int shift = pass_shift(pass);
+    unsigned long long prefix = prefix_in | ((unsigned long long)d << shift);
+    sel[0] = prefix;
+    sel[1] = pmask_in | ((unsigned long long)(bins - 1) << shift);
+    sel[2] = r;
+    if (pass == 2) {
+      unsigned long long n_eq = hist[d];
+      sel[3] = prefix;           // threshold key
+      sel[4] = (unsigned long long)k - r;  // n_gt
+      sel[5] = n_eq;
+      sel[6] = r;                // ties to take
+      sel[7] = r < n_eq ? 1ull : 0ull;  // flat-order tie resolution needed
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < kRadixBins; i += 32) hist[i] = 0;  // ready for the next pass
+}
+
+__global__ void k_sel_init(unsigned long long *sel, unsigned int *hist, long long k) {
+  int t = threadIdx.x + blockIdx.x * blockDim.x;
+  if (t < 8) sel[t] = t == 2 ? (unsigned long long)k : 0ull;
+  if (t < kRadixBins) hist[t] = 0;
+}
+
+// contiguous chunk of block b: [b*chunk, min(n, (b+1)*chunk)), chunk a multiple of 1024
+__global__ void __launch_bounds__(kThreads) k_tie_count(const float *__restrict__ a, int64_t n, int64_t chunk,
+                                                        const unsigned long long *__restrict__ sel,
+                                                        unsigned int *__restrict__ block_ties) {
+  __shared__ unsigned int warp_cnt[kThreads / 32];
+  if (sel[7] == 0) return;  // all ties taken: no ordering needed (uniform across the grid)
+  const uint32_t thr = (uint32_t)sel[3];
+  const int64_t lo = (int64_t)blockIdx.x * chunk;
+  const int64_t hi = min(n, lo + chunk);
+  unsigned int c = 0;
+  for (int64_t i = lo + (int64_t)threadIdx.x * 4; i < hi; i += kThreads * 4) {
+    float4 v = load4(a, i, n, 0.f);
+    c += (sal_key(v.x) == thr) + (i + 1 < n && sal_key(v.y) == thr) + (i + 2 < n && sal_key(v.z) == thr) +
+         (i + 3 < n && sal_key(v.w) == thr);
+  }
+  for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = 0;
+    for (int w = 0; w < kThreads / 32; ++w) t += warp_cnt[w];
+    block_ties[blockIdx.x] = t;
+  }
+}
+
+__global__ void k_tie_scan(unsigned int *__restrict__ block_ties, int nblocks,
+                           const unsigned long long *__restrict__ sel) {
+  if (sel[7] == 0) return;
+  // single thread: nblocks <= kMaxPartials (1184) -- negligible next to the N-element passes
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    unsigned int run = 0;
+    for (int b = 0; b < nblocks; ++b) {
+      unsigned int t = block_ties[b];
+      block_ties[b] = run;
+      run += t;
+    }
+  }
+}
+
+template <bool kVecI64>
+__global__ void __launch_bounds__(kThreads) k_write_mask(const float *__restrict__ a, int64_t n, int64_t chunk,
+                                                         const unsigned long long *__restrict__ sel,
+                                                         const unsigned int *__restrict__ block_ties,
+                                                         long long *__restrict__ mask_i64,
+                                                         uint32_t *__restrict__ mask_bits, int all_ones) {
+  __shared__ unsigned int warp_tot[kThreads / 32];
+  __shared__ unsigned int iter_base;
+  const uint32_t thr = all_ones ? 0u : (uint32_t)sel[3];
+  const bool ordered = !all_ones && sel[7] != 0;
+  const unsigned long long need = all_ones ? 0ull : sel[6];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) iter_base = ordered ? block_ties[blockIdx.x] : 0u;
+  __syncthreads();
+  const int64_t lo = (int64_t)blockIdx.x * chunk;
+  const int64_t hi = min(n, lo + chunk);
+  for (int64_t base = lo; base < hi; base += kThreads * 4) {  // uniform trip count per block
+    const int64_t i = base + (int64_t)threadIdx.x * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < hi) v = load4(a, i, n, 0.f);
+    uint32_t key[4] = {sal_key(v.x), sal_key(v.y), sal_key(v.z), sal_key(v.w)};
+    uint32_t gt = 0, eq = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool valid = i + j < n && i < hi;
+      if (all_ones) {
+        gt |= (valid ? 1u : 0u) << j;
+      } else {
+        gt |= ((valid && key[j] > thr) ? 1u : 0u) << j;
+        eq |= ((valid && key[j] == thr) ? 1u : 0u) << j;
+      }
+    }
+    uint32_t sel_bits = gt;
+    if (!ordered) {
+      sel_bits |= eq;  // need == n_eq: every tie is selected
+    } else {
+      // block-wide exclusive prefix of tie counts in flat order
+      unsigned int c = __popc(eq), incl = c;
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) warp_tot[warp] = incl;
+      __syncthreads();
+      unsigned int wbase = 0, total = 0;
+      for (int w = 0; w < kThreads / 32; ++w) {
+        unsigned int t = warp_tot[w];
+        if (w < warp) wbase += t;
+        total += t;
+      }
+      unsigned long long rank = (unsigned long long)iter_base + wbase + (incl - c);  // ties before my first element
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (eq & (1u << j)) {
+          if (rank < need) sel_bits |= 1u << j;
+          ++rank;
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) iter_base += total;
+      // next iteration's readers are separated from this write by the __syncthreads above in that iteration
+    }
+    if (mask_i64 && i < hi) {
+      long long m0 = sel_bits & 1u, m1 = (sel_bits >> 1) & 1u, m2 = (sel_bits >> 2) & 1u, m3 = (sel_bits >> 3) & 1u;
+      if (kVecI64 && i + 3 < n) {
+        reinterpret_cast<longlong2 *>(mask_i64 + i)[0] = make_longlong2(m0, m1);
+        reinterpret_cast<longlong2 *>(mask_i64 + i)[1] = make_longlong2(m2, m3);
+      } else {
+        if (i < n) mask_i64[i] = m0;
+        if (i + 1 < n) mask_i64[i + 1] = m1;
+        if (i + 2 < n) mask_i64[i + 2] = m2;
+        if (i + 3 < n) mask_i64[i + 3] = m3;
+      }
+    }
+    if (mask_bits) {
+      // 8 lanes x 4 bits -> one 32-bit word
+      uint32_t w = sel_bits << (4 * (lane & 7));
+      w |= __shfl_xor_sync(0xffffffffu, w, 1);
+      w |= __shfl_xor_sync(0xffffffffu, w, 2);
+      w |= __shfl_xor_sync(0xffffffffu, w, 4);
+      if ((lane & 7) == 0 && i < hi && i < n) mask_bits[i >> 5] = w;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// mask pack / unpack / apply
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_pack_mask(const long long *__restrict__ m, int64_t n,
+                                                        uint32_t *__restrict__ bits) {
+  const int lane = threadIdx.x & 31;
+  int64_t nw = (n + 31) / 32;
+  int64_t warp_id = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
+  int64_t nwarps = ((int64_t)gridDim.x * kThreads) >> 5;
+  for (int64_t w = warp_id; w < nw; w += nwarps) {
+    int64_t i = w * 32 + lane;
+    bool on = i < n && m[i] != 0;
+    uint32_t word = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) bits[w] = word;
+  }
+}
+__global__ void __launch_bounds__(kThreads) k_unpack_mask(const uint32_t *__restrict__ bits, int64_t n,
+                                                          long long *__restrict__ m) {
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+    m[i] = (bits[i >> 5] >> (i & 31)) & 1u;
+}
+__global__ void __launch_bounds__(kThreads) k_apply_mask(float *__restrict__ g, const uint32_t *__restrict__ bits,
+                                                         int64_t n) {
+  int64_t stride = (int64_t)gridDim.x * kThreads * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4; i < n; i += stride) {
+    uint32_t nib = mask_nibble(bits, i);
+    if (nib == 0xFu) continue;
+    float4 v = load4(g, i, n, 0.f);
+    if (!(nib & 1u)) v.x = __fmul_rn(v.x, 0.f);
+    if (!(nib & 2u)) v.y = __fmul_rn(v.y, 0.f);
+    if (!(nib & 4u)) v.z = __fmul_rn(v.z, 0.f);
+    if (!(nib & 8u)) v.w = __fmul_rn(v.w, 0.f);
+    store4(g, i, n, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused masked SGD + restore          (oracle_masked_sgd_step)
+// bytes/param: read p,g,v (12) + 1/8 mask + write p,v (8) = 20.125
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sgd1(float &p, float g, float &v, bool m, float lr, float mu, float wd) {
+  if (m) {
+    float gp = __fadd_rn(g, __fmul_rn(wd, p));
+    float vn = __fadd_rn(__fmul_rn(mu, v), gp);
+    v = vn;
+    p = __fadd_rn(p, -__fmul_rn(lr, vn));
+  } else {
+    v = 0.f;
+  }
+}
+__global__ void __launch_bounds__(kThreads) k_masked_sgd(float *__restrict__ p, const float *__restrict__ g,
+                                                         float *__restrict__ v, const uint32_t *__restrict__ bits,
+                                                         int64_t n, float lr, float mu, float wd) {
+  int64_t stride = (int64_t)gridDim.x * kThreads * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4; i < n; i += stride) {
+    uint32_t nib = mask_nibble(bits, i);
+    float4 vv = load4(v, i, n, 0.f);
+    if (nib == 0u) {  // whole vector masked out: p untouched, only v forced to 0
+      store4(v, i, n, make_float4(0.f, 0.f, 0.f, 0.f));
+      continue;
+    }
+    float4 pp = load4(p, i, n, 0.f), gg = load4(g, i, n, 0.f);
+    sgd1(pp.x, gg.x, vv.x, nib & 1u, lr, mu, wd);
+    sgd1(pp.y, gg.y, vv.y, nib & 2u, lr, mu, wd);
+    sgd1(pp.z, gg.z, vv.z, nib & 4u, lr, mu, wd);
+    sgd1(pp.w, gg.w, vv.w, nib & 8u, lr, mu, wd);
+    store4(p, i, n, pp);
+    store4(v, i, n, vv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// grad norm (double partials, fixed reduction tree -> deterministic), clip coefficient
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_sumsq_partial(const float *__restrict__ g, int64_t n,
+                                                            double *__restrict__ partials) {
+  __shared__ double sh[kThreads / 32];
+  double s = 0.0;
+  int64_t stride = (int64_t)gridDim.x * kThreads * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4; i < n; i += stride) {
+    float4 v = load4(g, i, n, 0.f);
+    s += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+  }
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) t += sh[w];
+    partials[blockIdx.x] = t;
+  }
+}
+__global__ void k_sumsq_final(const double *__restrict__ partials, int nparts, double *__restrict__ out) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += partials[i];
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+    *out = t;
+  }
+}
+__global__ void k_clip_coef(const double *__restrict__ sumsq, float max_norm, float *__restrict__ coef) {
+  float total = (float)sqrt(*sumsq);
+  float c = __fdiv_rn(max_norm, __fadd_rn(total, 1e-6f));
+  *coef = c > 1.0f ? 1.0f : c;
+}
+
+// ------------------------------------------------------------------------------------------
+// fused clip + mask + Adam            (oracle_masked_adam_step)
+// bytes/param: read p,g,m1,m2 (16) + 1/8 + write p,m1,m2 (12) = 28.125 (+4 for the norm pass)
+// ------------------------------------------------------------------------------------------
+struct AdamK {
+  float lr_step, bc2_sqrt, b2, one_m_b1, one_m_b2, eps, wd;
+};
+__device__ __forceinline__ void adam1(float &p, float g, float &m1, float &m2, bool m, float coef, const AdamK &k) {
+  float gi = __fmul_rn(g, coef);
+  if (!m) gi = __fmul_rn(0.f, gi);
+  if (k.wd != 0.f) gi = __fadd_rn(gi, __fmul_rn(k.wd, p));
+  float a = __fadd_rn(m1, __fmul_rn(__fadd_rn(gi, -m1), k.one_m_b1));
+  float b = __fadd_rn(__fmul_rn(m2, k.b2), __fmul_rn(k.one_m_b2, __fmul_rn(gi, gi)));
+  m1 = a;
+  m2 = b;
+  float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(b), k.bc2_sqrt), k.eps);
+  p = __fadd_rn(p, __fmul_rn(-k.lr_step, __fdiv_rn(a, denom)));
+}
+__global__ void __launch_bounds__(kThreads) k_masked_adam(float *__restrict__ p, const float *__restrict__ g,
+                                                          float *__restrict__ m1, float *__restrict__ m2,
+                                                          const uint32_t *__restrict__ bits, int64_t n, AdamK k,
+                                                          const float *__restrict__ coef_dev) {
+  const float coef = coef_dev ? *coef_dev : 1.0f;
+  int64_t stride = (int64_t)gridDim.x * kThreads * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4; i < n; i += stride) {
+    uint32_t nib = mask_nibble(bits, i);
+    float4 pp = load4(p, i, n, 0.f), gg = load4(g, i, n, 0.f), aa = load4(m1, i, n, 0.f), bb = load4(m2, i, n, 0.f);
+    adam1(pp.x, gg.x, aa.x, bb.x, nib & 1u, coef, k);
+    adam1(pp.y, gg.y, aa.y, bb.y, nib & 2u, coef, k);
+    adam1(pp.z, gg.z, aa.z, bb.z, nib & 4u, coef, k);
+    adam1(pp.w, gg.w, aa.w, bb.w, nib & 8u, coef, k);
+    store4(p, i, n, pp);
+    store4(m1, i, n, aa);
+    store4(m2, i, n, bb);
+  }
+}
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace salun
+
+using namespace salun;
+
+// ============================================================================================
+// C ABI
+// ============================================================================================
+extern "C" {
+
+int salun_version(void) { return 1000; }
+const char *salun_last_error(void) { return err_buf(); }
+
+int salun_ctx_create(int device, salun_ctx **out) {
+  SALUN_REQUIRE(out != nullptr, "out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  SALUN_CUDA_OK(cudaGetDeviceCount(&ndev));
+  SALUN_REQUIRE(device >= 0 && device < ndev, "device index out of range");
+  SALUN_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SALUN_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("libsalun is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+    return SALUN_ERR_UNSUPPORTED;
+  }
+  salun_ctx *c = new salun_ctx();
+  memset(c, 0, sizeof *c);
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  SALUN_CUDA_OK(cudaMalloc(&c->hist, kRadixBins * sizeof(unsigned int)));
+  SALUN_CUDA_OK(cudaMalloc(&c->sel, 8 * sizeof(unsigned long long)));
+  SALUN_CUDA_OK(cudaMalloc(&c->block_ties, (kMaxPartials + 1) * sizeof(unsigned int)));
+  SALUN_CUDA_OK(cudaMalloc(&c->partials, kMaxPartials * sizeof(double)));
+  SALUN_CUDA_OK(cudaMallocHost(&c->mailbox_host, 8 * sizeof(unsigned long long)));
+  *out = c;
+  return SALUN_OK;
+}
+
+int salun_ctx_destroy(salun_ctx *c) {
+  if (!c) return SALUN_OK;
+  cudaSetDevice(c->device);
+  cudaFree(c->hist);
+  cudaFree(c->sel);
+  cudaFree(c->block_ties);
+  cudaFree(c->partials);
+  cudaFreeHost(c->mailbox_host);
+  delete c;
+  return SALUN_OK;
+}
+
+#define SALUN_ENTER(ctx)                        \
+  SALUN_REQUIRE((ctx) != nullptr, "ctx is NULL"); \
+  SALUN_CUDA_OK(cudaSetDevice((ctx)->device));  \
+  cudaStream_t st = (cudaStream_t)stream
+
+int salun_saliency_accumulate_flat(salun_ctx *ctx, const float *grad, float *accum, int64_t n,
+                                   const float *scale_dev, void *stream) {
+  SALUN_ENTER(ctx);
+  SALUN_REQUIRE(n >= 0, "n < 0");
+  if (n == 0) return SALUN_OK;
+  SALUN_REQUIRE(grad && accum, "NULL buffer");
+  SALUN_REQUIRE(aligned16(grad) && aligned16(accum), "buffers must be 16-byte aligned");
+  k_accum_flat<<<grid_for(ctx, (n + 3) / 4), kThreads, 0, st>>>(grad, accum, n, scale_dev);
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+
+int salun_saliency_accumulate(salun_ctx *ctx, const float *const *grads_host, const int64_t *numels_host,
+                              int n_tensors, float *accum_flat, const float *scale_dev, void *stream) {
+  SALUN_ENTER(ctx);
+  SALUN_REQUIRE(n_tensors >= 0, "n_tensors < 0");
+  if (n_tensors == 0) return SALUN_OK;
+  SALUN_REQUIRE(grads_host && numels_host && accum_flat, "NULL buffer");
+  long long off = 0;
+  int t = 0;
+  while (t < n_tensors) {
+    TensorTable tab;
+    int cnt = 0;
+    long long maxn = 0;
+    while (t < n_tensors && cnt < kTabMax) {
+      SALUN_REQUIRE(numels_host[t] >= 0, "negative numel");
+      if (numels_host[t] > 0) {
+        SALUN_REQUIRE(grads_host[t] != nullptr, "NULL grad pointer");
+        tab.src[cnt] = grads_host[t];
+        tab.dst_off[cnt] = off;
+        tab.numel[cnt] = numels_host[t];
+        if (numels_host[t] > maxn) maxn = numels_host[t];
+        ++cnt;
+      }
+      off += numels_host[t];
+      ++t;
+    }
+    if (cnt == 0) continue;
+    long long gx = (maxn + kThreads * 8 - 1) / (kThreads * 8);
+    if (gx > 128) gx = 128;
+    if (gx < 1) gx = 1;
+    dim3 grid((unsigned)gx, (unsigned)cnt);
+    k_accum_multi<<<grid, kThreads, 0, st>>>(tab, accum_flat, scale_dev);
+    SALUN_CUDA_OK(cudaGetLastError());
+  }
+  return SALUN_OK;
+}
+
+int salun_abs_inplace(salun_ctx *ctx, float *a, int64_t n, void *stream) {
+  SALUN_ENTER(ctx);
+  SALUN_REQUIRE(n >= 0, "n < 0");
+  if (n == 0) return SALUN_OK;
+  SALUN_REQUIRE(a && aligned16(a), "buffer must be non-NULL and 16-byte aligned");
+  k_abs<<<grid_for(ctx, (n + 3) / 4), kThreads, 0, st>>>(a, n);
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+
+int salun_topk_mask(salun_ctx *ctx, const float *accum, int64_t n, int64_t k, int64_t *mask_i64,
+                    uint32_t *mask_bits, salun_topk_info *info_host, void *stream) {
+  SALUN_ENTER(ctx);
+  SALUN_REQUIRE(n >= 0 && k >= 0, "n or k negative");
+  if (info_host) memset(info_host, 0, sizeof *info_host);
+  if (n == 0) return SALUN_OK;
+  SALUN_REQUIRE(accum && aligned16(accum), "accum must be non-NULL and 16-byte aligned");
+  SALUN_REQUIRE(mask_i64 || mask_bits, "no output requested");
+  const int grid = grid_for(ctx, (n + 3) / 4);
+  // contiguous chunk per block, multiple of 1024 so that warps own whole mask words
+  int64_t chunk = (n + grid - 1) / grid;
+  chunk = (chunk + 1023) / 1024 * 1024;
+  const int wgrid = (int)((n + chunk - 1) / chunk);
+  const bool vec64 = mask_i64 && aligned16(mask_i64);
+  if (k == 0) {
+    if (mask_i64) SALUN_CUDA_OK(cudaMemsetAsync(mask_i64, 0, (size_t)n * 8, st));
+    if (mask_bits) SALUN_CUDA_OK(cudaMemsetAsync(mask_bits, 0, (size_t)((n + 31) / 32) * 4, st));
+    if (info_host) {
+      SALUN_CUDA_OK(cudaStreamSynchronize(st));
+      info_host->thr_key = 0xffffffffu;
+      info_host->thr_value = INFINITY;
+    }
+    return SALUN_OK;
+  }
+  const int all_ones = k >= n;
+  if (!all_ones) {
+    k_sel_init<<<(kRadixBins + 255) / 256, 256, 0, st>>>(ctx->sel, ctx->hist, (long long)k);
+    for (int pass = 0; pass < 3; ++pass) {
+      k_radix_hist<<<grid, kThreads, 0, st>>>(accum, n, ctx->sel, ctx->hist, pass);
+      k_radix_pick<<<1, 32, 0, st>>>(ctx->hist, ctx->sel, pass, (long long)k);
+    }
+    k_tie_count<<<wgrid, kThreads, 0, st>>>(accum, n, chunk, ctx->sel, ctx->block_ties);
+    k_tie_scan<<<1, 32, 0, st>>>(ctx->block_ties, wgrid, ctx->sel);
+  }
+  if (vec64)
+    k_write_mask<true><<<wgrid, kThreads, 0, st>>>(accum, n, chunk, ctx->sel, ctx->block_ties,
+                                                   (long long *)mask_i64, mask_bits, all_ones);
+  else
+    k_write_mask<false><<<wgrid, kThreads, 0, st>>>(accum, n, chunk, ctx->sel, ctx->block_ties,
+                                                    (long long *)mask_i64, mask_bits, all_ones);
+  SALUN_CUDA_OK(cudaGetLastError());
+  if (info_host) {
+    if (all_ones) {
+      SALUN_CUDA_OK(cudaStreamSynchronize(st));
+      info_host->thr_key = 0;
+      info_host->thr_value = 0.f;
+      info_host->n_greater = n;
+      info_host->n_equal = 0;
+    } else {
+      SALUN_CUDA_OK(cudaMemcpyAsync(ctx->mailbox_host, ctx->sel, 8 * sizeof(unsigned long long),
+                                    cudaMemcpyDeviceToHost, st));
+      SALUN_CUDA_OK(cudaStreamSynchronize(st));
+      info_host->thr_key = (uint32_t)ctx->mailbox_host[3];
+      uint32_t vb = info_host->thr_key ? info_host->thr_key - 1u : 0x7fc00000u;
+      memcpy(&info_host->thr_value, &vb, 4);
+      info_host->n_greater = (int64_t)ctx->mailbox_host[4];
+      info_host->n_equal = (int64_t)ctx->mailbox_host[5];
+    }
+  }
+  return SALUN_OK;
+}
+
+int salun_pack_mask(salun_ctx *ctx, const int64_t *mask_i64, int64_t n, uint32_t *mask_bits, void *stream) {
+  SALUN_ENTER(ctx);
+  SALUN_REQUIRE(n >= 0, "n < 0");
+  if (n == 0) return SALUN_OK;
+  SALUN_REQUIRE(mask_i64 && mask_bits, "NULL buffer");
+  k_pack_mask<<<grid_for(ctx, n), kThreads, 0, st>>>((const long long *)mask_i64, n, mask_bits);
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+
+int salun_unpack_mask(salun_ctx *ctx, const uint32_t *mask_bits, int64_t n, int64_t *mask_i64, void *stream) {
+  SALUN_ENTER(ctx);
+  SALUN_REQUIRE(n >= 0, "n < 0");
+  if (n == 0) return SALUN_OK;
+  SALUN_REQUIRE(mask_i64 && mask_bits, "NULL buffer");
+  k_unpack_mask<<<grid_for(ctx, n), kThreads, 0, st>>>(mask_bits, n, (long long *)mask_i64);
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+
+int salun_apply_mask(salun_ctx *ctx, float *g, const uint32_t *mask_bits, int64_t n, void *stream) {
+  SALUN_ENTER(ctx);
+  SALUN_REQUIRE(n >= 0, "n < 0");
+  if (n == 0) return SALUN_OK;
+  SALUN_REQUIRE(g && mask_bits && aligned16(g), "g must be non-NULL, 16-byte aligned; mask_bits non-NULL");
+  k_apply_mask<<<grid_for(ctx, (n + 3) / 4), kThreads, 0, st>>>(g, mask_bits, n);
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+
+int salun_masked_sgd_step(salun_ctx *ctx, float *p, const float *g, float *v, const uint32_t *mask_bits,
+                          int64_t n, float lr, float momentum, float wd, void *stream) {
+  SALUN_ENTER(ctx);
+  SALUN_REQUIRE(n >= 0, "n < 0");
+  if (n == 0) return SALUN_OK;
+  SALUN_REQUIRE(p && g && v, "NULL buffer");
+  SALUN_REQUIRE(aligned16(p) && aligned16(g) && aligned16(v), "p, g, v must be 16-byte aligned");
+  k_masked_sgd<<<grid_for(ctx, (n + 3) / 4), kThreads, 0, st>>>(p, g, v, mask_bits, n, lr, momentum, wd);
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+
+int salun_grad_sumsq(salun_ctx *ctx, const float *g, int64_t n, double *sumsq_dev, void *stream) {
+  SALUN_ENTER(ctx);
+  SALUN_REQUIRE(n >= 0 && sumsq_dev, "n < 0 or NULL output");
+  if (n == 0) {
+    SALUN_CUDA_OK(cudaMemsetAsync(sumsq_dev, 0, sizeof(double), st));
+    return SALUN_OK;
+  }
+  SALUN_REQUIRE(g && aligned16(g), "g must be non-NULL and 16-byte aligned");
+  const int grid = grid_for(ctx, (n + 3) / 4);
+  k_sumsq_partial<<<grid, kThreads, 0, st>>>(g, n, ctx->partials);
+  k_sumsq_final<<<1, 256, 0, st>>>(ctx->partials, grid, sumsq_dev);
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+
+int salun_clip_coef(salun_ctx *ctx, const double *sumsq_dev, float max_norm, float *coef_dev, void *stream) {
+  SALUN_ENTER(ctx);
+  SALUN_REQUIRE(sumsq_dev && coef_dev, "NULL buffer");
+  k_clip_coef<<<1, 1, 0, st>>>(sumsq_dev, max_norm, coef_dev);
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+
+int salun_masked_adam_step(salun_ctx *ctx, float *p, const float *g, float *m1, float *m2,
+                           const uint32_t *mask_bits, int64_t n, float lr, float beta1, float beta2, float eps,
+                           float wd, int64_t step, const float *coef_dev, void *stream) {
+  SALUN_ENTER(ctx);
+  SALUN_REQUIRE(n >= 0 && step >= 1, "n < 0 or step < 1");
+  if (n == 0) return SALUN_OK;
+  SALUN_REQUIRE(p && g && m1 && m2, "NULL buffer");
+  SALUN_REQUIRE(aligned16(p) && aligned16(g) && aligned16(m1) && aligned16(m2), "buffers must be 16-byte aligned");
+  AdamK k;
+  double bc1 = 1.0 - pow((double)beta1, (double)step);
+  double bc2 = 1.0 - pow((double)beta2, (double)step);
+  k.lr_step = (float)((double)lr / bc1);
+  k.bc2_sqrt = (float)sqrt(bc2);
+  k.b2 = beta2;
+  k.one_m_b1 = (float)(1.0 - (double)beta1);
+  k.one_m_b2 = (float)(1.0 - (double)beta2);
+  k.eps = eps;
+  k.wd = wd;
+  k_masked_adam<<<grid_for(ctx, (n + 3) / 4), kThreads, 0, st>>>(p, g, m1, m2, mask_bits, n, k, coef_dev);
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+
+}  // extern "C"
