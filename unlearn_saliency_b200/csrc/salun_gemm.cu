@@ -1,0 +1,551 @@
+// salun_gemm.cu -- tcgen05 / TMEM / TMA GEMM kernels for the convolution forward, dgrad and wgrad
+// of the SalUn ResNet path (replaces the cuDNN calls behind Classification/models/ResNet.py:58-74,
+// 108-124 forward and loss.backward() at Classification/unlearn/RL.py:128-132).
+//
+// k_conv_gemm : D[M][N] = A[M][K] . B[N][K]^T, both operands K-major bf16 in 128B-swizzled smem tiles
+//               written by TMA; accumulators in TMEM; warp-specialised:
+//                 warp 0      TMA producer (one elected lane)
+//                 warp 1      TMEM allocator + tcgen05.mma issuer (one elected lane)
+//                 warps 2..5  epilogue: tcgen05.ld -> registers -> bf16/fp32 global stores (+ per-column
+//                             sum / sum-of-squares partials for the BatchNorm batch statistics)
+//               For stride-1 convolutions A is never materialised: k-block kb = (tap, 64 input channels) is
+//               fetched straight from the halo-padded NHWC activation by a 4-D TMA box whose (x, y) origin is
+//               shifted by the tap -- TMA does the im2col.
+// k_wgrad     : dW[co][kc] += sum_pixels dY[p][co] * X[p][kc]; the pixel dimension is the MMA K dimension, so both
+//               operands are MN-major tiles ([pixels][64 channels], the same TMA boxes as above); split-K over
+//               pixel ranges with fp32 red.global.add.
+#include "salun_gemm.cuh"
+#include "salun_sm100.cuh"
+
+namespace salun {
+using namespace sm100;
+
+constexpr int kGemmThreads = 192;
+constexpr int kBM = 128;
+constexpr int kBK = 64;  // bf16 elements per k-block = one 128-byte swizzle row
+
+// Transposing reduction: every lane holds v[0..31] (32 columns of its own row); afterwards lane j holds the
+// sum over the 32 lanes (rows) of column j.  31 shuffles instead of 160.
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const bool up = lane & 16;
+    float send = up ? v[i] : v[i + 16];
+    float keep = up ? v[i + 16] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool up = lane & 8;
+    float send = up ? v[i] : v[i + 8];
+    float keep = up ? v[i + 8] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool up = lane & 4;
+    float send = up ? v[i] : v[i + 4];
+    float keep = up ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool up = lane & 2;
+    float send = up ? v[i] : v[i + 2];
+    float keep = up ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  {
+    const bool up = lane & 1;
+    float send = up ? v[0] : v[1];
+    float keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
+  return v[0];
+}
+
+// =================================================================================================
+// conv / plain GEMM, K-major operands
+// =================================================================================================
+template <int BN, int kStages>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+k_conv_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvGemmArgs a) {
+  constexpr uint32_t kABytes = kBM * kBK * 2;  // 16 KB
+  constexpr uint32_t kBBytes = BN * kBK * 2;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 1);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kStages, tfull = empty0 + 8 * kStages;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tile = blockIdx.x, n_tile = blockIdx.y;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ TMA producer
+      int n0 = 0, y0 = 0;
+      if (a.mode_a == 1) {
+        const int pix0 = m_tile * kBM;
+        n0 = pix0 / (a.H * a.W);
+        y0 = (pix0 % (a.H * a.W)) / a.W;
+      }
+      for (int kb = 0; kb < a.num_k_blocks; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        const uint32_t sa = smem_base + s * kStageBytes, sb = sa + kABytes;
+        mbar_arrive_expect_tx(full0 + 8 * s, kStageBytes);
+        if (a.mode_a == 1) {
+          const int tap = kb / a.cin_blocks, cb = kb - tap * a.cin_blocks;
+          const int ky = tap / a.kw, kx = tap - ky * a.kw;
+          tma_load_4d(sa, &tmA, full0 + 8 * s, cb * kBK, a.tap_x0 + kx, a.tap_y0 + y0 + ky, n0);
+        } else {
+          tma_load_2d(sa, &tmA, full0 + 8 * s, kb * kBK, m_tile * kBM);
+        }
+        tma_load_2d(sb, &tmB, full0 + 8 * s, kb * kBK, n_tile * BN);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
+      for (int kb = 0; kb < a.num_k_blocks; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(full0 + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * kStageBytes, sb = sa + kABytes;
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          const uint64_t ad = umma_desc_sw128(sa + k * 32, 16, 1024);
+          const uint64_t bd = umma_desc_sw128(sb + k * 32, 16, 1024);
+          tc_mma_f16(tmem_base, ad, bd, idesc, (kb | k) != 0);
+        }
+        tc_commit(empty0 + 8 * s);  // frees the smem stage when the MMAs above retire
+      }
+      tc_commit(tfull);
+    }
+  } else {
+    // -------------------------------------------------------------------- epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    const int row = m_tile * kBM + q * 32 + lane;
+    const bool row_ok = row < a.M;
+    const int stat_row = (m_tile * 4 + q);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, r);
+      tc_wait_ld();
+      const int col0 = n_tile * BN + c * 32;
+      if (col0 >= a.N) break;
+      if (row_ok) {
+        if (a.out_bf16) {
+          uint4 *dst = reinterpret_cast<uint4 *>(a.out_bf16 + (size_t)row * a.ld_out + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]));
+            v.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+            v.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+            v.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+            dst[j] = v;
+          }
+        }
+        if (a.out_f32) {
+          uint4 *dst = reinterpret_cast<uint4 *>(a.out_f32 + (size_t)row * a.ld_out + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        }
+      }
+      if (a.stat_sum) {
+        float v[32], w[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = row_ok ? __uint_as_float(r[j]) : 0.f;
+          v[j] = x;
+          w[j] = x * x;
+        }
+        float s1 = warp_transpose_reduce(v, lane);
+        float s2 = warp_transpose_reduce(w, lane);
+        if (col0 + lane < a.N) {
+          a.stat_sum[(size_t)stat_row * a.N + col0 + lane] = s1;
+          a.stat_sq[(size_t)stat_row * a.N + col0 + lane] = s2;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
+// =================================================================================================
+// wgrad: MN-major operands (pixel dimension is K)
+// =================================================================================================
+constexpr int kWgStages = 4;
+constexpr int kWgPix = 64;                         // pixels per k-block
+constexpr uint32_t kWgBlockBytes = kWgPix * 128;   // one [64 px][64 ch] bf16 slab = 8 KB
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+k_wgrad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t stage_bytes = (2 + a.n_blocks) * kWgBlockBytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kWgStages * 6 * kWgBlockBytes);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kWgStages + 1);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kWgStages, tfull = empty0 + 8 * kWgStages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int co_tile = blockIdx.x, grp = blockIdx.y, split = blockIdx.z;
+  const int kb_begin = split * a.kb_per_split;
+  const int kb_end = min(a.kb_total, kb_begin + a.kb_per_split);
+  const int nkb = kb_end - kb_begin;
+  const int a_blocks = (a.Cout - co_tile * 128) >= 128 ? 2 : 1;  // valid 64-row slabs of dY in this tile
+  const uint32_t tmem_cols = a.n_blocks <= 1 ? 64 : (a.n_blocks == 2 ? 128 : 256);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kWgStages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (nkb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int i = 0; i < nkb; ++i) {
+          const int kb = kb_begin + i;
+          const int s = i % kWgStages;
+          const uint32_t ph = (i / kWgStages) & 1;
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          const uint32_t sa = smem_base + s * stage_bytes, sb = sa + 2 * kWgBlockBytes;
+          mbar_arrive_expect_tx(full0 + 8 * s, (a_blocks + a.n_blocks) * kWgBlockBytes);
+          const int pix0 = kb * kWgPix;
+          for (int j = 0; j < a_blocks; ++j)
+            tma_load_2d(sa + j * kWgBlockBytes, &tmA, full0 + 8 * s, co_tile * 128 + j * 64, pix0);
+          int n0 = 0, y0 = 0;
+          if (a.mode_b == 1) {
+            n0 = pix0 / (a.H * a.W);
+            y0 = (pix0 % (a.H * a.W)) / a.W;
+          }
+          for (int j = 0; j < a.n_blocks; ++j) {
+            const int b = grp * a.n_blocks + j;
+            if (a.mode_b == 1) {
+              const int tap = b / a.cin_blocks, cb = b - tap * a.cin_blocks;
+              const int ky = tap / a.kw, kx = tap - ky * a.kw;
+              tma_load_4d(sb + j * kWgBlockBytes, &tmB, full0 + 8 * s, cb * 64, a.tap_x0 + kx, a.tap_y0 + y0 + ky, n0);
+            } else {
+              tma_load_2d(sb + j * kWgBlockBytes, &tmB, full0 + 8 * s, b * 64, pix0);
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = umma_idesc_bf16(128, 64 * a.n_blocks, 1, 1);
+        // MN-major, 128B swizzle: 64-element (128 B) rows, 8 pixel rows per 1024-byte atom (SBO),
+        // next 64-channel slab kWgBlockBytes further (LBO)
+        const uint32_t lbo = a.swap_lbo_sbo ? 1024u : kWgBlockBytes;
+        const uint32_t sbo = a.swap_lbo_sbo ? kWgBlockBytes : 1024u;
+        for (int i = 0; i < nkb; ++i) {
+          const int s = i % kWgStages;
+          const uint32_t ph = (i / kWgStages) & 1;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * stage_bytes, sb = sa + 2 * kWgBlockBytes;
+#pragma unroll
+          for (int k = 0; k < kWgPix / 16; ++k) {
+            const uint64_t ad = umma_desc_sw128(sa + k * 2048, lbo, sbo);
+            const uint64_t bd = umma_desc_sw128(sb + k * 2048, lbo, sbo);
+            tc_mma_f16(tmem_base, ad, bd, idesc, (i | k) != 0);
+          }
+          tc_commit(empty0 + 8 * s);
+        }
+        tc_commit(tfull);
+      }
+    } else {
+      const int q = warp & 3;
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+      const int co = co_tile * 128 + q * 32 + lane;
+      const bool row_ok = co < a.Cout;
+      for (int c = 0; c < a.n_blocks * 2; ++c) {
+        uint32_t r[32];
+        tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, r);
+        tc_wait_ld();
+        const int col0 = (grp * a.n_blocks) * 64 + c * 32;
+        float *dst = a.dw + (size_t)co * a.ldw + col0;
+        if (!row_ok) {
+          // junk rows of a half-empty co tile: nothing to store
+        } else if (col0 + 32 <= a.kvalid && (a.ldw & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j),
+                         "f"(__uint_as_float(r[4 * j])), "f"(__uint_as_float(r[4 * j + 1])),
+                         "f"(__uint_as_float(r[4 * j + 2])), "f"(__uint_as_float(r[4 * j + 3]))
+                         : "memory");
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < a.kvalid) atomicAdd(dst + j, __uint_as_float(r[j]));
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+int make_tmap_2d_bf16(CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                      uint32_t box_cols) {
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {cols * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = cuTensorMapEncodeTiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstr, box,
+                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(2d rows=%llu cols=%llu box=%ux%u) failed: %d", (unsigned long long)rows,
+              (unsigned long long)cols, box_rows, box_cols, (int)r);
+    return SALUN_ERR_CUDA;
+  }
+  return SALUN_OK;
+}
+
+int make_tmap_4d_bf16(CUtensorMap *m, const void *base, uint64_t C, uint64_t Wp, uint64_t Hp, uint64_t N,
+                      TmapBox4 bx) {
+  cuuint64_t gdim[4] = {C, Wp, Hp, N};
+  cuuint64_t gstr[3] = {C * 2, Wp * C * 2, Hp * Wp * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)bx.c, (cuuint32_t)bx.w, (cuuint32_t)bx.h, (cuuint32_t)bx.n};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = cuTensorMapEncodeTiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), gdim, gstr, box,
+                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(4d C=%llu Wp=%llu Hp=%llu N=%llu box=%d,%d,%d,%d) failed: %d",
+              (unsigned long long)C, (unsigned long long)Wp, (unsigned long long)Hp, (unsigned long long)N, bx.c, bx.w,
+              bx.h, bx.n, (int)r);
+    return SALUN_ERR_CUDA;
+  }
+  return SALUN_OK;
+}
+
+int conv_box(int H, int W, int pixels, TmapBox4 *box) {
+  // `pixels` consecutive output pixels in (n, y, x) order must form a (w=W, h, n) box
+  if (W <= 0 || H <= 0 || pixels % W != 0) {
+    set_error("conv_box: W=%d does not divide the %d-pixel tile", W, pixels);
+    return SALUN_ERR_UNSUPPORTED;
+  }
+  int rows = pixels / W;
+  int h = rows < H ? rows : H;
+  if (rows % h != 0 || H % h != 0) {
+    set_error("conv_box: H=%d W=%d cannot tile %d pixels", H, W, pixels);
+    return SALUN_ERR_UNSUPPORTED;
+  }
+  box->c = 64;
+  box->w = W;
+  box->h = h;
+  box->n = rows / h;
+  return SALUN_OK;
+}
+
+template <int BN, int S>
+static int launch_conv_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvGemmArgs &a, cudaStream_t st) {
+  constexpr size_t smem = (size_t)S * (kBM * kBK * 2 + BN * kBK * 2) + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SALUN_CUDA_OK(cudaFuncSetAttribute(k_conv_gemm<BN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid((a.M + kBM - 1) / kBM, (a.N + BN - 1) / BN);
+  k_conv_gemm<BN, S><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, a);
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+
+int launch_conv_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvGemmArgs &a, int bn, cudaStream_t st) {
+  switch (bn) {
+    case 64: return launch_conv_gemm_t<64, 4>(tmA, tmB, a, st);
+    case 128: return launch_conv_gemm_t<128, 3>(tmA, tmB, a, st);
+    case 256: return launch_conv_gemm_t<256, 4>(tmA, tmB, a, st);
+    default: set_error("launch_conv_gemm: unsupported BN=%d", bn); return SALUN_ERR_INVALID;
+  }
+}
+
+int wgrad_pick_blocks(int total_blocks) {
+  if (total_blocks % 4 == 0) return 4;
+  if (total_blocks % 3 == 0) return 3;
+  if (total_blocks % 2 == 0) return 2;
+  return 1;
+}
+
+int launch_wgrad(const CUtensorMap &tmA, const CUtensorMap &tmB, const WgradArgs &a, int co_tiles, int col_groups,
+                 int splits, cudaStream_t st) {
+  constexpr size_t smem = (size_t)kWgStages * 6 * kWgBlockBytes + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SALUN_CUDA_OK(cudaFuncSetAttribute(k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid(co_tiles, col_groups, splits);
+  k_wgrad<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, a);
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+
+}  // namespace salun
+
+// =================================================================================================
+// C ABI: stand-alone entry points (used by the parity tests and by integrators who want one conv)
+// =================================================================================================
+using namespace salun;
+
+extern "C" {
+
+// D[M][N] (fp32 and/or bf16) = A[M][K] . B[N][K]^T, bf16 row-major operands, K % 64 == 0, N % 64 == 0
+int salun_gemm_bf16_tn(salun_ctx *ctx, const void *A, const void *B, float *out_f32, void *out_bf16, int64_t M,
+                       int64_t N, int64_t K, void *stream) {
+  SALUN_REQUIRE(ctx && A && B && (out_f32 || out_bf16), "NULL argument");
+  SALUN_REQUIRE(M > 0 && N > 0 && K > 0 && K % 64 == 0 && N % 64 == 0, "need K % 64 == 0 and N % 64 == 0");
+  SALUN_CUDA_OK(cudaSetDevice(ctx->device));
+  const int bn = (N % 256 == 0 && M * N >= 148ll * 128 * 256) ? 256 : (N % 128 == 0 ? 128 : 64);
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_tmap_2d_bf16(&tmA, A, M, K, kBM, kBK))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmB, B, N, K, bn, kBK))) return rc;
+  ConvGemmArgs a{};
+  a.mode_a = 0;
+  a.num_k_blocks = (int)(K / 64);
+  a.M = (int)M;
+  a.N = (int)N;
+  a.out_bf16 = (__nv_bfloat16 *)out_bf16;
+  a.out_f32 = out_f32;
+  a.ld_out = (int)N;
+  return launch_conv_gemm(tmA, tmB, a, bn, (cudaStream_t)stream);
+}
+
+// Y[batch*H*W][Cout] = conv(X, Wk) for a stride-1 kh x kw convolution (3x3/pad 1 or 1x1/pad 0).
+//   xpad : bf16 [batch][H+2][W+2][Cin]  halo-padded NHWC, halo = 0        (Cin % 64 == 0)
+//   wk   : bf16 [Cout][kh*kw*Cin]       (tap-major, then input channel)   (Cout % 64 == 0)
+//   y    : bf16 [batch*H*W][Cout]  ;  stat_sum / stat_sq: optional fp32 [(batch*H*W/128)*4][Cout] partials
+// replaces F.conv2d forward (cuDNN) behind Classification/models/ResNet.py:111-119.
+int salun_conv_fwd_bf16(salun_ctx *ctx, const void *xpad, const void *wk, void *y_bf16, float *y_f32, float *stat_sum,
+                        float *stat_sq, int batch, int H, int W, int Cin, int Cout, int ksize, void *stream) {
+  SALUN_REQUIRE(ctx && xpad && wk && (y_bf16 || y_f32), "NULL argument");
+  SALUN_REQUIRE(ksize == 3 || ksize == 1, "ksize must be 1 or 3");
+  SALUN_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "Cin and Cout must be multiples of 64");
+  SALUN_REQUIRE(((int64_t)batch * H * W) % 128 == 0, "batch*H*W must be a multiple of 128");
+  SALUN_CUDA_OK(cudaSetDevice(ctx->device));
+  const int bn = Cout % 128 == 0 ? 128 : 64;
+  TmapBox4 bx;
+  int rc;
+  if ((rc = conv_box(H, W, kBM, &bx))) return rc;
+  CUtensorMap tmA, tmB;
+  if ((rc = make_tmap_4d_bf16(&tmA, xpad, Cin, W + 2, H + 2, batch, bx))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmB, wk, Cout, (uint64_t)ksize * ksize * Cin, bn, kBK))) return rc;
+  ConvGemmArgs a{};
+  a.mode_a = 1;
+  a.cin_blocks = Cin / 64;
+  a.num_k_blocks = ksize * ksize * a.cin_blocks;
+  a.kw = ksize;
+  a.tap_y0 = a.tap_x0 = ksize == 3 ? 0 : 1;
+  a.H = H;
+  a.W = W;
+  a.M = batch * H * W;
+  a.N = Cout;
+  a.out_bf16 = (__nv_bfloat16 *)y_bf16;
+  a.out_f32 = y_f32;
+  a.ld_out = Cout;
+  a.stat_sum = stat_sum;
+  a.stat_sq = stat_sq;
+  return launch_conv_gemm(tmA, tmB, a, bn, (cudaStream_t)stream);
+}
+
+// dW[Cout][kh*kw*Cin] (fp32, tap-major) += sum over pixels dY[p][Cout]^T . X_tap[p][Cin]
+//   dy : bf16 [batch*H*W][Cout] ; xpad : bf16 halo-padded NHWC ; dw must be zeroed by the caller.
+// replaces the cuDNN wgrad inside loss.backward() (Classification/unlearn/RL.py:132).
+int salun_conv_wgrad_bf16(salun_ctx *ctx, const void *dy, const void *xpad, float *dw, int batch, int H, int W, int Cin,
+                          int Cout, int ksize, int splits, int swap_lbo_sbo, void *stream) {
+  SALUN_REQUIRE(ctx && dy && xpad && dw, "NULL argument");
+  SALUN_REQUIRE(ksize == 3 || ksize == 1, "ksize must be 1 or 3");
+  SALUN_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "Cin and Cout must be multiples of 64");
+  const int64_t M = (int64_t)batch * H * W;
+  SALUN_REQUIRE(M % 64 == 0, "batch*H*W must be a multiple of 64");
+  SALUN_CUDA_OK(cudaSetDevice(ctx->device));
+  TmapBox4 bx;
+  int rc;
+  if ((rc = conv_box(H, W, kWgPix, &bx))) return rc;
+  CUtensorMap tmA, tmB;
+  if ((rc = make_tmap_2d_bf16(&tmA, dy, M, Cout, kWgPix, 64))) return rc;
+  if ((rc = make_tmap_4d_bf16(&tmB, xpad, Cin, W + 2, H + 2, batch, bx))) return rc;
+  WgradArgs a{};
+  a.mode_b = 1;
+  a.kb_total = (int)(M / kWgPix);
+  a.cin_blocks = Cin / 64;
+  a.kw = ksize;
+  a.tap_y0 = a.tap_x0 = ksize == 3 ? 0 : 1;
+  a.H = H;
+  a.W = W;
+  a.total_blocks = ksize * ksize * a.cin_blocks;
+  a.n_blocks = wgrad_pick_blocks(a.total_blocks);
+  a.Cout = Cout;
+  a.ldw = ksize * ksize * Cin;
+  a.kvalid = a.ldw;
+  a.dw = dw;
+  a.swap_lbo_sbo = swap_lbo_sbo;
+  const int co_tiles = (Cout + 127) / 128, groups = a.total_blocks / a.n_blocks;
+  if (splits <= 0) {
+    splits = (2 * ctx->num_sms + co_tiles * groups - 1) / (co_tiles * groups);
+    if (splits < 1) splits = 1;
+  }
+  if (splits > a.kb_total) splits = a.kb_total;
+  a.kb_per_split = (a.kb_total + splits - 1) / splits;
+  splits = (a.kb_total + a.kb_per_split - 1) / a.kb_per_split;
+  return launch_wgrad(tmA, tmB, a, co_tiles, groups, splits, (cudaStream_t)stream);
+}
+
+}  // extern "C"

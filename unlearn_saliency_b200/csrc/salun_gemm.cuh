@@ -1,0 +1,61 @@
+// salun_gemm.cuh -- host-side interface of the tcgen05 GEMM kernels (salun_gemm.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "salun_common.cuh"
+
+namespace salun {
+
+// D[M][N] = sum_k A[m][k] * B[n][k]   (bf16 x bf16 -> fp32 accumulate in TMEM)
+// A comes either from a plain 2-D matrix or, for stride-1 convolutions, directly from the
+// halo-padded NHWC activation through a 4-D tensor map (implicit GEMM: k-block = (tap, 64 channels)).
+struct ConvGemmArgs {
+  int mode_a;        // 0: A is [M][K] row-major; 1: A is padded NHWC [batch][H+2][W+2][C], taps walk it
+  int num_k_blocks;  // K / 64
+  int cin_blocks;    // mode 1: 64-channel blocks per tap
+  int kw;            // mode 1: taps per kernel row (3 for 3x3, 1 for 1x1)
+  int tap_y0, tap_x0;  // mode 1: padded coordinate of tap (0,0) for output pixel (0,0): 0 for 3x3/pad1, 1 for 1x1/pad0
+  int H, W;          // mode 1: output spatial size (== input spatial size, stride 1)
+  int M, N;          // valid rows / columns of D
+  __nv_bfloat16 *out_bf16;  // [M][ld_out] or nullptr
+  float *out_f32;           // [M][ld_out] or nullptr
+  int ld_out;
+  float *stat_sum, *stat_sq;  // per-(m tile, warp) column partial sums [gridDim.x * 4][N], or nullptr
+};
+
+// dW[co][b*64 + j] += sum_p dY[p][co] * X_b[p][j]   (both operands MN-major: pixels are the K dimension)
+// X_b is either a 64-column slab of a 2-D matrix Col[M][Kc] or the (tap, 64-channel) slab of the padded
+// NHWC activation.  Split-K over pixel ranges, fp32 red.global.add into dW.
+struct WgradArgs {
+  int mode_b;         // 0: 2-D Col[M][Kc]; 1: 4-D padded NHWC taps
+  int kb_total;       // M / 64 (k-blocks of 64 pixels)
+  int kb_per_split;
+  int cin_blocks, kw, tap_y0, tap_x0, H, W;
+  int n_blocks;       // 64-wide column blocks per CTA (1..4)
+  int total_blocks;   // column blocks overall (= Kc / 64)
+  int Cout;           // valid rows of dW
+  int ldw;            // row stride of dW in floats
+  int kvalid;         // valid columns of dW (<= total_blocks * 64)
+  float *dw;
+  int swap_lbo_sbo;   // debug knob for descriptor bring-up (0 in production)
+};
+
+struct TmapBox4 {
+  int c, w, h, n;
+};
+
+int make_tmap_2d_bf16(CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                      uint32_t box_cols);
+int make_tmap_4d_bf16(CUtensorMap *m, const void *base, uint64_t C, uint64_t Wp, uint64_t Hp, uint64_t N,
+                      TmapBox4 box);
+
+// box decomposition of `pixels` consecutive output pixels of an H x W image batch (power-of-two sizes)
+int conv_box(int H, int W, int pixels, TmapBox4 *box);
+
+int launch_conv_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvGemmArgs &a, int bn, cudaStream_t st);
+int launch_wgrad(const CUtensorMap &tmA, const CUtensorMap &tmB, const WgradArgs &a, int co_tiles, int col_groups,
+                 int splits, cudaStream_t st);
+int wgrad_pick_blocks(int total_blocks);
+
+}  // namespace salun
