@@ -136,6 +136,36 @@ int salun_masked_adam_step(salun_ctx *ctx, float *p, const float *g, float *m1, 
                            float beta2, float eps, float wd, int64_t step,
                            const float *coef_dev, void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * tcgen05 tensor-core building blocks (bf16 operands, fp32 accumulation in TMEM, TMA-fed).
+ * These replace the cuDNN/cuBLAS calls behind Classification/models/ResNet.py:58-74,108-124
+ * (conv forward) and behind loss.backward() (Classification/unlearn/RL.py:132: dgrad, wgrad).
+ * Activation layout: halo-padded NHWC bf16 [batch][H+2][W+2][C] with a zero halo -- the
+ * convolution reads its taps straight out of it with shifted 4-D TMA boxes (no im2col buffer).
+ * Weight layout: bf16 [Cout][kh*kw*Cin], tap-major then input channel.
+ * ------------------------------------------------------------------------------------- */
+
+/* D[M][N] = A[M][K] . B[N][K]^T ; A, B bf16 row-major ; out_f32 and/or out_bf16 [M][N].
+ * Requires K % 64 == 0 and N % 64 == 0. */
+int salun_gemm_bf16_tn(salun_ctx *ctx, const void *A, const void *B, float *out_f32, void *out_bf16,
+                       int64_t M, int64_t N, int64_t K, void *stream);
+
+/* Stride-1 convolution forward, ksize 3 (pad 1) or 1 (pad 0):
+ *   y[batch*H*W][Cout] = conv(xpad, wk)        (y_bf16 and/or y_f32; either may be NULL, not both)
+ *   stat_sum / stat_sq: optional fp32 [(batch*H*W/128)*4][Cout] per-tile column sums of y and y^2
+ *   (the BatchNorm batch statistics, reduced by the caller).  Cin, Cout multiples of 64,
+ *   batch*H*W a multiple of 128, H and W powers of two. */
+int salun_conv_fwd_bf16(salun_ctx *ctx, const void *xpad, const void *wk, void *y_bf16, float *y_f32,
+                        float *stat_sum, float *stat_sq, int batch, int H, int W, int Cin, int Cout,
+                        int ksize, void *stream);
+
+/* Stride-1 convolution weight gradient: dw[Cout][ksize*ksize*Cin] (fp32, tap-major) +=
+ *   sum over pixels of dy[p][Cout]^T . x_tap[p][Cin].  dw must be zeroed by the caller (split-K
+ *   accumulates with fp32 red.global.add).  splits <= 0 picks a split count that fills the GPU.
+ *   swap_lbo_sbo is a bring-up knob and must be 0. */
+int salun_conv_wgrad_bf16(salun_ctx *ctx, const void *dy, const void *xpad, float *dw, int batch, int H,
+                          int W, int Cin, int Cout, int ksize, int splits, int swap_lbo_sbo, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,215 @@
+"""oracle/classification.py -- CPU restatement (torch fp32) of the Classification hot path.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Restates, functionally and without nn.Module
+classes, what the reference computes; citations are relative to /root/reference/Classification.
+Pinned against outputs of the unmodified reference by tests/golden/make_golden.py ->
+tests/golden/*.npz -> tests/test_oracle_golden.py.
+
+  resnet_forward          models/ResNet.py:303-322 (+ BasicBlock.forward :108-124, NormalizeByChannelMeanStd :23-28)
+  save_gradient_ratio     generate_mask.py:14-82
+  rl_epoch / ga / ft      unlearn/RL.py:109-176, unlearn/GA.py:107-128, unlearn/FT.py:116-144 with
+                          _apply_mask_to_grads (RL.py:11-14), torch.optim.SGD (impl.py:68-73),
+                          _restore_masked_params (RL.py:17-34)
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from typing import Dict, Iterable, List, Tuple
+
+import torch
+import torch.nn.functional as F
+
+CIFAR_MEAN = (0.4914, 0.4822, 0.4465)  # models/ResNet.py:214-216
+CIFAR_STD = (0.2470, 0.2435, 0.2616)
+
+# ---------------------------------------------------------------------------------------------
+# architecture table of resnet18 with the CIFAR stem (models/ResNet.py:217-223, 232-243, 336)
+# ---------------------------------------------------------------------------------------------
+STAGES = [(64, 1), (128, 2), (256, 2), (512, 2)]  # (planes, stride of the first block); 2 BasicBlocks each
+
+
+def resnet18_param_shapes(num_classes: int = 10) -> "OrderedDict[str, Tuple[int, ...]]":
+    """named_parameters() order of the reference's resnet18 (62 tensors, 11 173 962 elements for 10 classes)."""
+    s: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    s["conv1.weight"] = (64, 3, 3, 3)
+    s["bn1.weight"] = (64,)
+    s["bn1.bias"] = (64,)
+    inpl = 64
+    for li, (planes, stride) in enumerate(STAGES, start=1):
+        for b in range(2):
+            pre = f"layer{li}.{b}."
+            st = stride if b == 0 else 1
+            s[pre + "conv1.weight"] = (planes, inpl, 3, 3)
+            s[pre + "bn1.weight"] = (planes,)
+            s[pre + "bn1.bias"] = (planes,)
+            s[pre + "conv2.weight"] = (planes, planes, 3, 3)
+            s[pre + "bn2.weight"] = (planes,)
+            s[pre + "bn2.bias"] = (planes,)
+            if b == 0 and (st != 1 or inpl != planes):
+                s[pre + "downsample.0.weight"] = (planes, inpl, 1, 1)
+                s[pre + "downsample.1.weight"] = (planes,)
+                s[pre + "downsample.1.bias"] = (planes,)
+            inpl = planes
+    s["fc.weight"] = (num_classes, 512)
+    s["fc.bias"] = (num_classes,)
+    return s
+
+
+def bn_names(shapes) -> List[str]:
+    """prefixes of every BatchNorm (they carry running_mean / running_var / num_batches_tracked buffers)"""
+    return [k[: -len(".weight")] for k in shapes if (".bn" in k or k.startswith("bn") or "downsample.1" in k) and k.endswith(".weight")]
+
+
+def synth_state(num_classes: int = 10, seed: int = 0, bn_stats: bool = True):
+    """Deterministic synthetic weights (formula shared by make_golden.py and the tests; no checkpoint exists offline).
+
+    conv: N(0, 2/fan_out) (the reference's kaiming_normal_(fan_out), ResNet.py:247-249), BN gamma 1+0.1 N, beta 0.1 N,
+    running_mean 0.1 N, running_var 1+0.1|N|, fc: N(0, 1/512)."""
+    g = torch.Generator().manual_seed(seed)
+    shapes = resnet18_param_shapes(num_classes)
+    params: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for name, shp in shapes.items():
+        if len(shp) == 4:
+            fan_out = shp[0] * shp[2] * shp[3]
+            params[name] = torch.randn(shp, generator=g) * math.sqrt(2.0 / fan_out)
+        elif name == "fc.weight":
+            params[name] = torch.randn(shp, generator=g) * math.sqrt(1.0 / shp[1])
+        elif name.endswith(".weight"):
+            params[name] = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        else:
+            params[name] = 0.1 * torch.randn(shp, generator=g)
+    buffers: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for bn in bn_names(shapes):
+        c = shapes[bn + ".weight"][0]
+        if bn_stats:
+            buffers[bn + ".running_mean"] = 0.1 * torch.randn(c, generator=g)
+            buffers[bn + ".running_var"] = 1.0 + 0.1 * torch.randn(c, generator=g).abs()
+        else:
+            buffers[bn + ".running_mean"] = torch.zeros(c)
+            buffers[bn + ".running_var"] = torch.ones(c)
+        buffers[bn + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+    return params, buffers
+
+
+def state_dict_of(params, buffers, mean=CIFAR_MEAN, std=CIFAR_STD):
+    """state_dict in the reference's key layout (incl. normalize.mean/std buffers)."""
+    sd = OrderedDict()
+    sd["normalize.mean"] = torch.tensor(mean)
+    sd["normalize.std"] = torch.tensor(std)
+    sd.update(params)
+    sd.update(buffers)
+    return sd
+
+
+# ---------------------------------------------------------------------------------------------
+# forward (autograd supplies the backward -- this is the fp32 CPU reference of the op chain)
+# ---------------------------------------------------------------------------------------------
+def _bn(x, p, b, name, train: bool, momentum: float = 0.1, eps: float = 1e-5):
+    rm, rv = b[name + ".running_mean"], b[name + ".running_var"]
+    if train:
+        b[name + ".num_batches_tracked"] += 1  # nn.BatchNorm2d bookkeeping (buffers are not masked, Appendix B.1)
+    return F.batch_norm(x, rm, rv, p[name + ".weight"], p[name + ".bias"], train, momentum, eps)
+
+
+def resnet_forward(p: Dict[str, torch.Tensor], b: Dict[str, torch.Tensor], x: torch.Tensor, train: bool,
+                   mean=CIFAR_MEAN, std=CIFAR_STD) -> torch.Tensor:
+    m = torch.tensor(mean, dtype=x.dtype)[None, :, None, None]
+    s = torch.tensor(std, dtype=x.dtype)[None, :, None, None]
+    x = x.sub(m).div(s)  # ResNet.py:23-28
+    x = F.relu(_bn(F.conv2d(x, p["conv1.weight"], padding=1), p, b, "bn1", train))  # :307-310 (maxpool = Identity)
+    inpl = 64
+    for li, (planes, stride) in enumerate(STAGES, start=1):
+        for blk in range(2):
+            pre = f"layer{li}.{blk}."
+            st = stride if blk == 0 else 1
+            identity = x
+            out = F.relu(_bn(F.conv2d(x, p[pre + "conv1.weight"], stride=st, padding=1), p, b, pre + "bn1", train))
+            out = _bn(F.conv2d(out, p[pre + "conv2.weight"], padding=1), p, b, pre + "bn2", train)
+            if pre + "downsample.0.weight" in p:
+                identity = _bn(F.conv2d(x, p[pre + "downsample.0.weight"], stride=st), p, b, pre + "downsample.1", train)
+            x = F.relu(out + identity)  # :121-122
+            inpl = planes
+    x = F.adaptive_avg_pool2d(x, 1).flatten(1)  # :317-318
+    return F.linear(x, p["fc.weight"], p["fc.bias"])  # :320
+
+
+def loss_and_grads(p, b, x, y, train: bool, sign: float = 1.0):
+    """sign * mean CE and its gradient w.r.t. every parameter (zero_grad + backward of the reference loops)."""
+    leaves = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in p.items())
+    out = resnet_forward(leaves, b, x, train)
+    loss = sign * F.cross_entropy(out, y)
+    grads = torch.autograd.grad(loss, list(leaves.values()))
+    return loss.detach(), out.detach(), OrderedDict(zip(leaves.keys(), grads))
+
+
+# ---------------------------------------------------------------------------------------------
+# (i) generate_mask.py:14-82
+# ---------------------------------------------------------------------------------------------
+THRESHOLDS = [0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0]  # generate_mask.py:50
+
+
+def accumulate_saliency(p, b, batches: Iterable[Tuple[torch.Tensor, torch.Tensor]]):
+    """generate_mask.py:25-48: eval mode, loss = -CE, gradients[name] += grad, abs_ at the end. Returns flat |G|."""
+    acc = None
+    for x, y in batches:
+        _, _, g = loss_and_grads(p, b, x, y, train=False, sign=-1.0)
+        flat = torch.cat([t.flatten() for t in g.values()])
+        acc = flat if acc is None else acc + flat
+    return acc.abs_()
+
+
+def masks_from_saliency(absg: torch.Tensor, ratios=THRESHOLDS):
+    """generate_mask.py:57-80 with stable sorts (see oracle/salun_oracle.c on ties). Returns {ratio: int64 flat mask}."""
+    out = {}
+    neg = -absg
+    positions = torch.argsort(neg, stable=True)
+    ranks = torch.argsort(positions, stable=True)
+    for r in ratios:
+        k = int(len(neg) * r)
+        m = torch.zeros_like(ranks)
+        m[ranks < k] = 1
+        out[r] = m
+    return out
+
+
+def split_mask(flat_mask: torch.Tensor, shapes) -> "OrderedDict[str, torch.Tensor]":
+    out, off = OrderedDict(), 0
+    for name, shp in shapes.items():
+        n = math.prod(shp)
+        out[name] = flat_mask[off: off + n].reshape(shp)
+        off += n
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# (ii) masked SGD steps: RL.py:123-176, GA.py:107-128, FT.py:116-144
+# ---------------------------------------------------------------------------------------------
+class MaskedSGD:
+    """torch.optim.SGD(momentum, wd) + mask multiply + restore, restated per coordinate."""
+
+    def __init__(self, p, mask=None, lr=0.013, momentum=0.9, wd=5e-4):
+        self.p, self.mask, self.lr, self.mu, self.wd = p, mask, lr, momentum, wd
+        self.v = OrderedDict((k, torch.zeros_like(t)) for k, t in p.items())
+
+    def step(self, grads):
+        for k, t in self.p.items():
+            g = grads[k]
+            m = None if self.mask is None else self.mask[k].to(t.dtype)
+            if m is not None:
+                g = g * m  # RL.py:11-14
+            gp = g + self.wd * t
+            v = self.mu * self.v[k] + gp
+            newp = t - self.lr * v
+            if m is not None:  # RL.py:17-34 (theta0 == current value on masked-out coordinates)
+                newp = torch.where(m != 0, newp, t)
+                v = v * m
+            self.v[k] = v
+            self.p[k] = newp
+
+
+def unlearn_step(p, b, opt: MaskedSGD, x, y, sign: float = 1.0):
+    """one loop body of RL/GA/FT: train-mode forward, backward, mask, SGD, restore. Returns (loss, logits)."""
+    loss, out, g = loss_and_grads(p, b, x, y, train=True, sign=sign)
+    opt.step(g)
+    return loss, out

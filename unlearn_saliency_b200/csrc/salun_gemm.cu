@@ -339,13 +339,36 @@ k_wgrad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
 // =================================================================================================
 // host side
 // =================================================================================================
+// cuTensorMapEncodeTiled is resolved through the runtime (no link-time dependency on libcuda.so.1, so the
+// library still loads -- and reports a clean error -- on a machine without a driver).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+#define SALUN_ENCODE_OR_FAIL()                                                   \
+  EncodeTiledFn enc = encode_tiled();                                            \
+  if (!enc) {                                                                    \
+    set_error("cuTensorMapEncodeTiled not available (no CUDA driver?)");         \
+    return SALUN_ERR_CUDA;                                                       \
+  }
 int make_tmap_2d_bf16(CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows,
                       uint32_t box_cols) {
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstr[1] = {cols * 2};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = cuTensorMapEncodeTiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstr, box,
+  SALUN_ENCODE_OR_FAIL();
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstr, box,
                                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -362,7 +385,8 @@ int make_tmap_4d_bf16(CUtensorMap *m, const void *base, uint64_t C, uint64_t Wp,
   cuuint64_t gstr[3] = {C * 2, Wp * C * 2, Hp * Wp * C * 2};
   cuuint32_t box[4] = {(cuuint32_t)bx.c, (cuuint32_t)bx.w, (cuuint32_t)bx.h, (cuuint32_t)bx.n};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = cuTensorMapEncodeTiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), gdim, gstr, box,
+  SALUN_ENCODE_OR_FAIL();
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), gdim, gstr, box,
                                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
