@@ -204,6 +204,21 @@ def main():
         rm_bn1=bufs["bn1.running_mean"].numpy(), rv_l4=bufs["layer4.1.bn2.running_var"].numpy(),
         nbt=np.int64(bufs["bn1.num_batches_tracked"].item()),
     )
+    # a single forget step (tight tolerance: no chaotic amplification of rounding differences yet)
+    model = model_dict["resnet18"](num_classes=10)
+    model.load_state_dict(sd)
+    f1 = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x[:16], y[:16]), batch_size=16, shuffle=False)
+    r0 = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x[:0], y[:0]), batch_size=16, shuffle=False)
+    drawn1 = []
+    drawn, keep = drawn1, drawn
+    torch.manual_seed(321)
+    torch.randint = lambda *a, **k: (drawn1.append(orig_randint(*a, **k)), drawn1[-1])[1]
+    try:
+        unlearn.RL({"forget": f1, "retain": r0}, model, crit, ref_args("/tmp"), mask05)
+    finally:
+        torch.randint = orig_randint
+    res["rand_labels_1"] = drawn1[0].numpy()
+    res["psample_1"] = np.concatenate([p.detach().flatten()[sample_idx(p.numel())].numpy() for p in model.parameters()])
     np.savez_compressed(os.path.join(HERE, "resnet18_rl.npz"), **res)
     print("resnet18_rl.npz labels", res["rand_labels"].shape, "nbt", res["nbt"])
 
