@@ -166,6 +166,52 @@ int salun_conv_fwd_bf16(salun_ctx *ctx, const void *xpad, const void *wk, void *
 int salun_conv_wgrad_bf16(salun_ctx *ctx, const void *dy, const void *xpad, float *dw, int batch, int H,
                           int W, int Cin, int Cout, int ksize, int splits, int swap_lbo_sbo, void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * ResNet (BasicBlock, CIFAR stem) forward + backward engine.
+ * replaces  output = model(image); loss = +/-criterion(output, target); loss.backward()
+ *           Classification/generate_mask.py:35-39  (model.eval(): BN uses running statistics, loss_sign = -1)
+ *           Classification/unlearn/RL.py:128-132, GA.py:113-117, FT.py:128-135  (model.train())
+ * for the architecture of Classification/models/ResNet.py:180-322 with imagenet=False
+ * (resnet18: ResNet.py:336, resnet34: :347).  bf16 tensor-core operands, fp32 accumulation,
+ * fp32 master weights / gradients / BatchNorm statistics.
+ *
+ * Arena layout (caller-owned device buffers, fp32):
+ *   params / grads : tensors back to back in model.named_parameters() order; every conv weight
+ *                    is stored [Cout][kh][kw][Cin] (the reference's [Cout][Cin][kh][kw] permuted
+ *                    (0,2,3,1)); BN weight/bias and fc weight/bias as in PyTorch.
+ *   running_mean / running_var : BatchNorm buffers back to back in module order
+ *                    (bn1, layer1.0.bn1, layer1.0.bn2, [layer*.0.downsample.1], ...).
+ * ------------------------------------------------------------------------------------- */
+typedef struct salun_resnet salun_resnet;
+typedef struct salun_resnet_cfg {
+  int depth;       /* 18 or 34 */
+  int num_classes; /* arg_parser.py --num_classes */
+  int image_size;  /* 32 (CIFAR/SVHN) or 64 */
+  int max_batch;   /* largest batch a call will pass */
+  float mean[3];   /* NormalizeByChannelMeanStd, ResNet.py:7-28, values replaced per dataset in utils.py:115-117 */
+  float std[3];
+  float bn_eps;      /* 1e-5 */
+  float bn_momentum; /* 0.1 */
+} salun_resnet_cfg;
+
+int64_t salun_resnet_param_count(const salun_resnet_cfg *cfg); /* elements of params / grads */
+int64_t salun_resnet_bn_channels(const salun_resnet_cfg *cfg); /* elements of running_mean / running_var */
+int salun_resnet_create(salun_ctx *ctx, const salun_resnet_cfg *cfg, float *params, float *grads,
+                        float *running_mean, float *running_var, salun_resnet **out);
+int salun_resnet_destroy(salun_resnet *net);
+
+/* One mini-batch: logits = net(x); loss = loss_sign * mean CE(logits, labels); grads = dloss/dparams
+ * (grads is overwritten: the zero_grad() of the reference loops is implied).
+ *   x      : fp32 NCHW [n][3][S][S] in [0,1] (what image.cuda() hands the reference model)
+ *   labels : int64 [n]
+ *   train  : 1 = batch statistics + running-stat update (model.train()), 0 = running statistics (model.eval())
+ *   loss_dev (1 float) / logits_dev ([n][num_classes] fp32): optional device outputs. */
+int salun_resnet_forward_backward(salun_resnet *net, const float *x, const int64_t *labels, int n,
+                                  int train, float loss_sign, float *loss_dev, float *logits_dev,
+                                  void *stream);
+/* eval-mode inference (trainer/val.py:6-72 validate): logits only */
+int salun_resnet_forward(salun_resnet *net, const float *x, int n, float *logits_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,13 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libsalun.so")
 _lib = None
 
 
+class salun_resnet_cfg(C.Structure):
+    _fields_ = [
+        ("depth", C.c_int), ("num_classes", C.c_int), ("image_size", C.c_int), ("max_batch", C.c_int),
+        ("mean", C.c_float * 3), ("std", C.c_float * 3), ("bn_eps", C.c_float), ("bn_momentum", C.c_float),
+    ]
+
+
 class salun_topk_info(C.Structure):
     _fields_ = [
         ("thr_key", C.c_uint32),
@@ -48,8 +55,16 @@ _SIGNATURES = {
     "salun_gemm_bf16_tn": [_P, _P, _P, _P, _P, _I64, _I64, _I64, _P],
     "salun_conv_fwd_bf16": [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P],
     "salun_conv_wgrad_bf16": [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P],
+    # ResNet engine (salun_resnet.cu)
+    "salun_resnet_param_count": [_P],
+    "salun_resnet_bn_channels": [_P],
+    "salun_resnet_create": [_P, _P, _P, _P, _P, _P, C.POINTER(_P)],
+    "salun_resnet_destroy": [_P],
+    "salun_resnet_forward_backward": [_P, _P, _P, C.c_int, C.c_int, _F, _P, _P, _P],
+    "salun_resnet_forward": [_P, _P, C.c_int, _P, _P],
 }
-_RESTYPES = {"salun_last_error": C.c_char_p}
+_RESTYPES = {"salun_last_error": C.c_char_p, "salun_resnet_param_count": C.c_int64,
+             "salun_resnet_bn_channels": C.c_int64}
 
 
 def exported_symbols():

@@ -1,0 +1,557 @@
+// salun_elem.cu -- HBM-bound kernels of the ResNet path (see salun_elem.cuh).  All activations are NHWC bf16,
+// 8 channels (16 bytes) per thread, fp32 math.  Replaces the ATen/cuDNN elementwise chain of
+// Classification/models/ResNet.py:108-124 (BatchNorm2d train/eval, ReLU, residual add), :303-322
+// (normalize, avgpool, fc) and their autograd backward.
+#include "salun_elem.cuh"
+
+#include <math.h>
+
+namespace salun {
+
+constexpr int kET = 256;
+
+__device__ __forceinline__ void ld8(const __nv_bfloat16 *p, float (&f)[8]) {
+  uint4 v = *reinterpret_cast<const uint4 *>(p);
+  const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void st8(__nv_bfloat16 *p, const float (&f)[8]) {
+  uint4 v;
+  __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<uint4 *>(p) = v;
+}
+__device__ __forceinline__ size_t pad_off(int m, int H, int W, int C) {
+  const int hw = H * W;
+  const int n = m / hw, r = m - n * hw;
+  const int y = r / W, x = r - y * W;
+  return ((size_t)(n * (H + 2) + y + 1) * (W + 2) + x + 1) * C;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward BN statistics: [rows][C] fp32 partials (GEMM epilogue) -> [kStatSlices][2][C] doubles
+// ------------------------------------------------------------------------------------------------
+__global__ void k_bn_stats_reduce(const float *__restrict__ ssum, const float *__restrict__ ssq, int rows, int C,
+                                  double *__restrict__ slices) {
+  __shared__ double sh[2][8][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int s = blockIdx.y;
+  const int lo = (int)((long long)rows * s / kStatSlices), hi = (int)((long long)rows * (s + 1) / kStatSlices);
+  double a = 0.0, b = 0.0;
+  if (c < C)
+    for (int r = lo + threadIdx.y; r < hi; r += 8) {
+      a += (double)ssum[(size_t)r * C + c];
+      b += (double)ssq[(size_t)r * C + c];
+    }
+  sh[0][threadIdx.y][threadIdx.x] = a;
+  sh[1][threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int j = 1; j < 8; ++j) {
+      a += sh[0][j][threadIdx.x];
+      b += sh[1][j][threadIdx.x];
+    }
+    slices[((size_t)s * 2 + 0) * C + c] = a;
+    slices[((size_t)s * 2 + 1) * C + c] = b;
+  }
+}
+void launch_bn_stats_reduce(const float *stat_sum, const float *stat_sq, int rows, int C, double *slices,
+                            cudaStream_t st) {
+  dim3 grid((C + 31) / 32, kStatSlices), block(32, 8);
+  k_bn_stats_reduce<<<grid, block, 0, st>>>(stat_sum, stat_sq, rows, C, slices);
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN apply (+ second BN branch, + residual, + ReLU) -> padded NHWC
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bn_prologue(const BnFwd &p, float *sc, float *sh, int C, int train, double count,
+                                            float eps, float momentum) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, invstd;
+    if (train) {
+      double s = 0.0, q = 0.0;
+      for (int i = 0; i < kStatSlices; ++i) {
+        s += p.slices[((size_t)i * 2 + 0) * C + c];
+        q += p.slices[((size_t)i * 2 + 1) * C + c];
+      }
+      const double m = s / count;
+      double var = q / count - m * m;
+      if (var < 0.0) var = 0.0;
+      mean = (float)m;
+      invstd = (float)(1.0 / sqrt(var + (double)eps));
+      if (blockIdx.x == 0) {  // nn.BatchNorm2d buffers: momentum update with the unbiased variance
+        const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+        p.running_mean[c] = (1.f - momentum) * p.running_mean[c] + momentum * mean;
+        p.running_var[c] = (1.f - momentum) * p.running_var[c] + momentum * (float)unb;
+      }
+    } else {
+      mean = p.running_mean[c];
+      invstd = (float)(1.0 / sqrt((double)p.running_var[c] + (double)eps));
+    }
+    if (blockIdx.x == 0) {
+      p.saved_mean[c] = mean;
+      p.saved_invstd[c] = invstd;
+    }
+    const float scale = p.gamma[c] * invstd;
+    sc[c] = scale;
+    sh[c] = p.beta[c] - mean * scale;
+  }
+}
+
+__global__ void __launch_bounds__(kET) k_bn_apply(BnFwd a, BnFwd b, int has_b, const __nv_bfloat16 *__restrict__ resid,
+                                                  __nv_bfloat16 *__restrict__ out, int M, int H, int W, int C, int relu,
+                                                  int train, float eps, float momentum) {
+  extern __shared__ float smf[];
+  float *sc_a = smf, *sh_a = smf + C, *sc_b = smf + 2 * C, *sh_b = smf + 3 * C;
+  bn_prologue(a, sc_a, sh_a, C, train, (double)M, eps, momentum);
+  if (has_b) bn_prologue(b, sc_b, sh_b, C, train, (double)M, eps, momentum);
+  __syncthreads();
+  const int tpr = C >> 3, rpb = kET / tpr;
+  const int rl = threadIdx.x / tpr, c0 = (threadIdx.x - rl * tpr) * 8;
+  for (int m = blockIdx.x * rpb + rl; m < M; m += gridDim.x * rpb) {
+    float v[8], t[8];
+    ld8(a.y + (size_t)m * C + c0, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], sc_a[c0 + i], sh_a[c0 + i]);
+    if (has_b) {
+      ld8(b.y + (size_t)m * C + c0, t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += fmaf(t[i], sc_b[c0 + i], sh_b[c0 + i]);
+    }
+    const size_t po = pad_off(m, H, W, C) + c0;
+    if (resid) {
+      ld8(resid + po, t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += t[i];
+    }
+    if (relu) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    st8(out + po, v);
+  }
+}
+static inline int elem_grid(int M, int C) {
+  const int rpb = kET / (C >> 3);
+  long long g = ((long long)M + rpb - 1) / rpb;
+  if (g > 148 * 8) g = 148 * 8;
+  return (int)(g < 1 ? 1 : g);
+}
+void launch_bn_apply(const BnFwd &a, const BnFwd *b, const __nv_bfloat16 *resid_padded, __nv_bfloat16 *out_padded,
+                     int n_img, int H, int W, int C, int relu, int train, float eps, float momentum, cudaStream_t st) {
+  const int M = n_img * H * W;
+  BnFwd bb = b ? *b : a;
+  k_bn_apply<<<elem_grid(M, C), kET, 4 * C * sizeof(float), st>>>(a, bb, b != nullptr, resid_padded, out_padded, M, H,
+                                                                  W, C, relu, train, eps, momentum);
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN backward
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kET) k_bn_bwd_reduce(const __nv_bfloat16 *__restrict__ dout,
+                                                       const __nv_bfloat16 *__restrict__ outp,
+                                                       const __nv_bfloat16 *__restrict__ y,
+                                                       const float *__restrict__ mean, const float *__restrict__ invstd,
+                                                       float *__restrict__ partials, int M, int H, int W, int C) {
+  extern __shared__ float smf[];  // [2][rpb][C]
+  const int tpr = C >> 3, rpb = kET / tpr;
+  const int rl = threadIdx.x / tpr, c0 = (threadIdx.x - rl * tpr) * 8;
+  float s1[8], s2[8], mu[8], is[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    s1[i] = s2[i] = 0.f;
+    mu[i] = mean[c0 + i];
+    is[i] = invstd[c0 + i];
+  }
+  for (int m = blockIdx.x * rpb + rl; m < M; m += gridDim.x * rpb) {
+    float d[8], o[8], yy[8];
+    ld8(dout + (size_t)m * C + c0, d);
+    ld8(y + (size_t)m * C + c0, yy);
+    if (outp) {
+      ld8(outp + pad_off(m, H, W, C) + c0, o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] = o[i] > 0.f ? d[i] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s1[i] += d[i];
+      s2[i] += d[i] * ((yy[i] - mu[i]) * is[i]);
+    }
+  }
+  float *b1 = smf, *b2 = smf + rpb * C;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    b1[rl * C + c0 + i] = s1[i];
+    b2[rl * C + c0 + i] = s2[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kET) {
+    float a = 0.f, b = 0.f;
+    for (int r = 0; r < rpb; ++r) {
+      a += b1[r * C + c];
+      b += b2[r * C + c];
+    }
+    partials[((size_t)blockIdx.x * 2 + 0) * C + c] = a;
+    partials[((size_t)blockIdx.x * 2 + 1) * C + c] = b;
+  }
+}
+static inline int bwd_rows(int M, int C) {
+  const int rpb = kET / (C >> 3);
+  int g = (M + rpb - 1) / rpb;
+  return g < kBwdPartialRows ? (g < 1 ? 1 : g) : kBwdPartialRows;
+}
+void launch_bn_bwd_reduce(const __nv_bfloat16 *dout, const __nv_bfloat16 *out_padded, const __nv_bfloat16 *y,
+                          const float *saved_mean, const float *saved_invstd, float *partials, int n_img, int H, int W,
+                          int C, cudaStream_t st) {
+  const int M = n_img * H * W;
+  const int rpb = kET / (C >> 3);
+  k_bn_bwd_reduce<<<bwd_rows(M, C), kET, 2 * rpb * C * sizeof(float), st>>>(dout, out_padded, y, saved_mean,
+                                                                           saved_invstd, partials, M, H, W, C);
+}
+
+__global__ void k_bn_bwd_finalize(const float *__restrict__ partials, int rows, int C, const float *__restrict__ gamma,
+                                  const float *__restrict__ invstd, float count, int train, float *__restrict__ dgamma,
+                                  float *__restrict__ dbeta, float *__restrict__ coef) {
+  __shared__ double sh[2][8][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double a = 0.0, b = 0.0;
+  if (c < C)
+    for (int r = threadIdx.y; r < rows; r += 8) {
+      a += (double)partials[((size_t)r * 2 + 0) * C + c];
+      b += (double)partials[((size_t)r * 2 + 1) * C + c];
+    }
+  sh[0][threadIdx.y][threadIdx.x] = a;
+  sh[1][threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int j = 1; j < 8; ++j) {
+      a += sh[0][j][threadIdx.x];
+      b += sh[1][j][threadIdx.x];
+    }
+    dbeta[c] = (float)a;
+    dgamma[c] = (float)b;
+    coef[c] = gamma[c] * invstd[c];
+    coef[C + c] = train ? (float)(a / (double)count) : 0.f;
+    coef[2 * C + c] = train ? (float)(b / (double)count) : 0.f;
+  }
+}
+void launch_bn_bwd_finalize(const float *partials, int C, const float *gamma, const float *saved_invstd, float count,
+                            int train, float *dgamma, float *dbeta, float *coef, cudaStream_t st) {
+  const int M = (int)count;
+  dim3 grid((C + 31) / 32), block(32, 8);
+  k_bn_bwd_finalize<<<grid, block, 0, st>>>(partials, bwd_rows(M, C), C, gamma, saved_invstd, count, train, dgamma,
+                                            dbeta, coef);
+}
+
+__global__ void __launch_bounds__(kET) k_bn_bwd_apply(const __nv_bfloat16 *__restrict__ dout,
+                                                      const __nv_bfloat16 *__restrict__ outp,
+                                                      const __nv_bfloat16 *__restrict__ y,
+                                                      const float *__restrict__ mean, const float *__restrict__ invstd,
+                                                      const float *__restrict__ coef, __nv_bfloat16 *__restrict__ dy,
+                                                      int dy_padded, __nv_bfloat16 *__restrict__ dz_flat, int M, int H,
+                                                      int W, int C) {
+  const int tpr = C >> 3, rpb = kET / tpr;
+  const int rl = threadIdx.x / tpr, c0 = (threadIdx.x - rl * tpr) * 8;
+  float mu[8], is[8], k1[8], m1[8], m2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    mu[i] = mean[c0 + i];
+    is[i] = invstd[c0 + i];
+    k1[i] = coef[c0 + i];
+    m1[i] = coef[C + c0 + i];
+    m2[i] = coef[2 * C + c0 + i];
+  }
+  for (int m = blockIdx.x * rpb + rl; m < M; m += gridDim.x * rpb) {
+    float d[8], o[8], yy[8];
+    ld8(dout + (size_t)m * C + c0, d);
+    ld8(y + (size_t)m * C + c0, yy);
+    const size_t po = pad_off(m, H, W, C) + c0;
+    if (outp) {
+      ld8(outp + po, o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] = o[i] > 0.f ? d[i] : 0.f;
+    }
+    if (dz_flat) st8(dz_flat + (size_t)m * C + c0, d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) yy[i] = k1[i] * (d[i] - m1[i] - (yy[i] - mu[i]) * is[i] * m2[i]);
+    st8(dy_padded ? dy + po : dy + (size_t)m * C + c0, yy);
+  }
+}
+void launch_bn_bwd_apply(const __nv_bfloat16 *dout, const __nv_bfloat16 *out_padded, const __nv_bfloat16 *y,
+                         const float *saved_mean, const float *saved_invstd, const float *coef, __nv_bfloat16 *dy,
+                         int dy_padded, __nv_bfloat16 *dz_flat, int n_img, int H, int W, int C, cudaStream_t st) {
+  const int M = n_img * H * W;
+  k_bn_bwd_apply<<<elem_grid(M, C), kET, 0, st>>>(dout, out_padded, y, saved_mean, saved_invstd, coef, dy, dy_padded,
+                                                  dz_flat, M, H, W, C);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stem / stride-2 patch kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kET) k_stem_im2col(const float *__restrict__ x, __nv_bfloat16 *__restrict__ col, int M,
+                                                     int H, int W, float m0, float m1, float m2, float i0, float i1,
+                                                     float i2) {
+  const int m = blockIdx.x * kET + threadIdx.x;
+  if (m >= M) return;
+  const int hw = H * W;
+  const int n = m / hw, r = m - n * hw, y = r / W, xx = r - y * W;
+  const float mean[3] = {m0, m1, m2}, inv[3] = {i0, i1, i2};
+  float v[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) v[i] = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int yy = y + ky - 1, xs = xx + kx - 1;
+      const bool ok = yy >= 0 && yy < H && xs >= 0 && xs < W;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float t = 0.f;  // zero padding is applied AFTER normalisation (conv pads the normalised tensor)
+        if (ok) t = (x[((size_t)(n * 3 + c) * H + yy) * W + xs] - mean[c]) * inv[c];
+        v[(ky * 3 + kx) * 3 + c] = t;
+      }
+    }
+  __nv_bfloat16 *dst = col + (size_t)m * 64;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = v[8 * j + i];
+    st8(dst + 8 * j, f);
+  }
+}
+void launch_stem_im2col(const float *x, __nv_bfloat16 *col, int n_img, int H, int W, const float *mean3,
+                        const float *inv_std3, cudaStream_t st) {
+  const int M = n_img * H * W;
+  k_stem_im2col<<<(M + kET - 1) / kET, kET, 0, st>>>(x, col, M, H, W, mean3[0], mean3[1], mean3[2], inv_std3[0],
+                                                     inv_std3[1], inv_std3[2]);
+}
+
+__global__ void __launch_bounds__(kET) k_im2col_s2(const __nv_bfloat16 *__restrict__ in, __nv_bfloat16 *__restrict__ col,
+                                                   long long total, int Hin, int Win, int C, int ks) {
+  const int Ho = Hin / 2, Wo = Win / 2, cgs = C >> 3, taps = ks * ks;
+  for (long long i = (long long)blockIdx.x * kET + threadIdx.x; i < total; i += (long long)gridDim.x * kET) {
+    const int cg = (int)(i % cgs);
+    long long t = i / cgs;
+    const int tap = (int)(t % taps);
+    const int mo = (int)(t / taps);
+    const int n = mo / (Ho * Wo), r = mo - n * Ho * Wo, oy = r / Wo, ox = r - oy * Wo;
+    const int ky = tap / ks, kx = tap - ky * ks;
+    const int off = ks == 3 ? 0 : 1;  // padded coordinates of input pixel (2oy+ky-pad, 2ox+kx-pad)
+    const int py = 2 * oy + ky + off, px = 2 * ox + kx + off;
+    const uint4 v =
+        *reinterpret_cast<const uint4 *>(in + ((size_t)(n * (Hin + 2) + py) * (Win + 2) + px) * C + cg * 8);
+    *reinterpret_cast<uint4 *>(col + ((size_t)mo * taps + tap) * C + cg * 8) = v;
+  }
+}
+void launch_im2col_s2(const __nv_bfloat16 *in_padded, __nv_bfloat16 *col, int n_img, int Hin, int Win, int C, int ks,
+                      cudaStream_t st) {
+  const long long total = (long long)n_img * (Hin / 2) * (Win / 2) * ks * ks * (C >> 3);
+  long long g = (total + kET - 1) / kET;
+  if (g > 148 * 16) g = 148 * 16;
+  k_im2col_s2<<<(int)g, kET, 0, st>>>(in_padded, col, total, Hin, Win, C, ks);
+}
+
+__global__ void __launch_bounds__(kET) k_col2im_s2(const __nv_bfloat16 *__restrict__ dcol3,
+                                                   const __nv_bfloat16 *__restrict__ dcol1,
+                                                   __nv_bfloat16 *__restrict__ dx, long long total, int Hin, int Win,
+                                                   int C) {
+  const int Ho = Hin / 2, Wo = Win / 2, cgs = C >> 3;
+  for (long long i = (long long)blockIdx.x * kET + threadIdx.x; i < total; i += (long long)gridDim.x * kET) {
+    const int cg = (int)(i % cgs);
+    const int m = (int)(i / cgs);
+    const int n = m / (Hin * Win), r = m - n * Hin * Win, y = r / Win, x = r - y * Win;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int ty = y + 1 - ky;
+      if (ty < 0 || (ty & 1) || (ty >> 1) >= Ho) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int tx = x + 1 - kx;
+        if (tx < 0 || (tx & 1) || (tx >> 1) >= Wo) continue;
+        const int mo = (n * Ho + (ty >> 1)) * Wo + (tx >> 1);
+        float t[8];
+        ld8(dcol3 + ((size_t)mo * 9 + ky * 3 + kx) * C + cg * 8, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += t[j];
+      }
+    }
+    if (dcol1 && !(y & 1) && !(x & 1)) {
+      const int mo = (n * Ho + (y >> 1)) * Wo + (x >> 1);
+      float t[8];
+      ld8(dcol1 + (size_t)mo * C + cg * 8, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += t[j];
+    }
+    st8(dx + (size_t)m * C + cg * 8, acc);
+  }
+}
+void launch_col2im_s2(const __nv_bfloat16 *dcol3, const __nv_bfloat16 *dcol1, __nv_bfloat16 *dx, int n_img, int Hin,
+                      int Win, int C, cudaStream_t st) {
+  const long long total = (long long)n_img * Hin * Win * (C >> 3);
+  long long g = (total + kET - 1) / kET;
+  if (g > 148 * 16) g = 148 * 16;
+  k_col2im_s2<<<(int)g, kET, 0, st>>>(dcol3, dcol1, dx, total, Hin, Win, C);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight re-layout (fp32 master, native [Cout][tap][Cin]) -> bf16 GEMM operands
+// ------------------------------------------------------------------------------------------------
+__global__ void k_prep_w_fwd(const float *__restrict__ w, __nv_bfloat16 *__restrict__ out, int Cout, int kc, int kcp) {
+  const long long total = (long long)Cout * kcp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i / kcp), j = (int)(i - (long long)co * kcp);
+    out[i] = __float2bfloat16(j < kc ? w[(size_t)co * kc + j] : 0.f);
+  }
+}
+__global__ void k_prep_w_dgrad_s1(const float *__restrict__ w, __nv_bfloat16 *__restrict__ out, int Cout, int Cin,
+                                  int taps) {
+  // out[ci][(taps-1-t)*Cout + co] = w[(co*taps + t)*Cin + ci]; threads walk the OUTPUT (coalesced writes)
+  const long long total = (long long)Cout * Cin * taps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    long long r = i / Cout;
+    const int tf = (int)(r % taps);
+    const int ci = (int)(r / taps);
+    const int t = taps - 1 - tf;
+    out[i] = __float2bfloat16(w[((size_t)co * taps + t) * Cin + ci]);
+  }
+}
+__global__ void k_prep_w_transpose(const float *__restrict__ w, __nv_bfloat16 *__restrict__ out, int Cout, int kc) {
+  // out[j][co] = w[co][j]
+  const long long total = (long long)Cout * kc;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    const int j = (int)(i / Cout);
+    out[i] = __float2bfloat16(w[(size_t)co * kc + j]);
+  }
+}
+static inline int flat_grid(long long total) {
+  long long g = (total + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  return (int)(g < 1 ? 1 : g);
+}
+void launch_prep_w_fwd(const float *w, __nv_bfloat16 *out, int Cout, int kc, int kc_padded, cudaStream_t st) {
+  k_prep_w_fwd<<<flat_grid((long long)Cout * kc_padded), 256, 0, st>>>(w, out, Cout, kc, kc_padded);
+}
+void launch_prep_w_dgrad_s1(const float *w, __nv_bfloat16 *out, int Cout, int Cin, int taps, cudaStream_t st) {
+  k_prep_w_dgrad_s1<<<flat_grid((long long)Cout * Cin * taps), 256, 0, st>>>(w, out, Cout, Cin, taps);
+}
+void launch_prep_w_transpose(const float *w, __nv_bfloat16 *out, int Cout, int kc, cudaStream_t st) {
+  k_prep_w_transpose<<<flat_grid((long long)Cout * kc), 256, 0, st>>>(w, out, Cout, kc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// head: global average pool, FC, cross-entropy (mean over the batch), and their backward
+// ------------------------------------------------------------------------------------------------
+__global__ void k_avgpool(const __nv_bfloat16 *__restrict__ act, float *__restrict__ pooled, int n_img, int H, int W,
+                          int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_img * C) return;
+  const int n = i / C, c = i - n * C;
+  float s = 0.f;
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) s += __bfloat162float(act[((size_t)(n * (H + 2) + y + 1) * (W + 2) + x + 1) * C + c]);
+  pooled[i] = s / (float)(H * W);
+}
+void launch_avgpool(const __nv_bfloat16 *act_padded, float *pooled, int n_img, int H, int W, int C, cudaStream_t st) {
+  k_avgpool<<<(n_img * C + 255) / 256, 256, 0, st>>>(act_padded, pooled, n_img, H, W, C);
+}
+
+__global__ void __launch_bounds__(128) k_fc_ce(const float *__restrict__ pooled, const float *__restrict__ w,
+                                               const float *__restrict__ bias, const int64_t *__restrict__ labels,
+                                               float *__restrict__ logits, float *__restrict__ dlogits,
+                                               float *__restrict__ loss_ps, int n_img, int C, int K, float sign) {
+  extern __shared__ float lg[];  // [K]
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float *x = pooled + (size_t)b * C;
+  for (int k = warp; k < K; k += 4) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += x[c] * w[(size_t)k * C + c];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) lg[k] = s + bias[k];
+  }
+  __syncthreads();
+  if (logits)
+    for (int k = threadIdx.x; k < K; k += 128) logits[(size_t)b * K + k] = lg[k];
+  if (!labels) return;
+  __shared__ float red[2];
+  if (threadIdx.x == 0) {
+    float mx = -INFINITY;
+    for (int k = 0; k < K; ++k) mx = fmaxf(mx, lg[k]);
+    float se = 0.f;
+    for (int k = 0; k < K; ++k) se += expf(lg[k] - mx);
+    red[0] = mx;
+    red[1] = se;
+    const int y = (int)labels[b];
+    loss_ps[b] = (logf(se) + mx) - lg[y];
+  }
+  __syncthreads();
+  const float mx = red[0], inv = 1.f / red[1];
+  const int y = (int)labels[b];
+  for (int k = threadIdx.x; k < K; k += 128)
+    dlogits[(size_t)b * K + k] = sign * (expf(lg[k] - mx) * inv - (k == y ? 1.f : 0.f)) / (float)n_img;
+}
+void launch_fc_ce(const float *pooled, const float *w, const float *b, const int64_t *labels, float *logits,
+                  float *dlogits, float *loss_per_sample, int n_img, int C, int K, float sign, cudaStream_t st) {
+  k_fc_ce<<<n_img, 128, K * sizeof(float), st>>>(pooled, w, b, labels, logits, dlogits, loss_per_sample, n_img, C, K,
+                                                  sign);
+}
+__global__ void k_loss_sum(const float *__restrict__ l, int n, float sign, float *__restrict__ out) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += l[i];
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+    *out = sign * t / (float)n;
+  }
+}
+void launch_loss_sum(const float *loss_per_sample, int n_img, float sign, float *loss_out, cudaStream_t st) {
+  k_loss_sum<<<1, 256, 0, st>>>(loss_per_sample, n_img, sign, loss_out);
+}
+
+__global__ void k_fc_bwd_w(const float *__restrict__ pooled, const float *__restrict__ dl, float *__restrict__ dw,
+                           float *__restrict__ db, int n_img, int C, int K) {
+  const int k = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < n_img; ++b) s += dl[(size_t)b * K + k] * pooled[(size_t)b * C + c];
+    dw[(size_t)k * C + c] = s;
+  }
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int b = 0; b < n_img; ++b) s += dl[(size_t)b * K + k];
+    db[k] = s;
+  }
+}
+__global__ void k_fc_bwd_x(const float *__restrict__ dl, const float *__restrict__ w, __nv_bfloat16 *__restrict__ dact,
+                           int n_img, int C, int K, int pix) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_img * C) return;
+  const int b = i / C, c = i - b * C;
+  float s = 0.f;
+  for (int k = 0; k < K; ++k) s += dl[(size_t)b * K + k] * w[(size_t)k * C + c];
+  const __nv_bfloat16 v = __float2bfloat16(s / (float)pix);
+  for (int p = 0; p < pix; ++p) dact[((size_t)b * pix + p) * C + c] = v;
+}
+void launch_fc_bwd(const float *pooled, const float *dlogits, const float *w, float *dw, float *db,
+                   __nv_bfloat16 *dact_flat, int n_img, int C, int K, int pix, cudaStream_t st) {
+  k_fc_bwd_w<<<K, 256, 0, st>>>(pooled, dlogits, dw, db, n_img, C, K);
+  k_fc_bwd_x<<<(n_img * C + 255) / 256, 256, 0, st>>>(dlogits, w, dact_flat, n_img, C, K, pix);
+}
+
+}  // namespace salun

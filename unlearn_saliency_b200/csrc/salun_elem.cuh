@@ -1,0 +1,65 @@
+// salun_elem.cuh -- launchers of the HBM-bound elementwise / reduction kernels of the ResNet path
+// (BatchNorm forward/backward around the tcgen05 GEMMs, ReLU, residual add, stride-2 im2col/col2im,
+// stem input normalisation, average pool + FC + cross-entropy head, weight re-layout).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace salun {
+
+constexpr int kStatSlices = 8;      // row slices of the forward BN statistics reduction
+constexpr int kBwdPartialRows = 296;  // CTAs (= partial rows) of the backward BN reduction
+
+struct BnFwd {            // one BatchNorm applied to a raw conv output y[M][C]
+  const __nv_bfloat16 *y;
+  const double *slices;   // [kStatSlices][2][C] (sum, sumsq), train mode
+  const float *gamma, *beta;
+  float *running_mean, *running_var;  // updated in train mode (momentum, unbiased var)
+  float *saved_mean, *saved_invstd;   // written for the backward pass
+};
+
+// partial column sums written by the GEMM epilogue -> kStatSlices double slices
+void launch_bn_stats_reduce(const float *stat_sum, const float *stat_sq, int rows, int C, double *slices,
+                            cudaStream_t st);
+
+// out = relu?( bn_a(y_a) [+ bn_b(y_b)] [+ resid] ), written into the halo-padded NHWC activation
+void launch_bn_apply(const BnFwd &a, const BnFwd *b, const __nv_bfloat16 *resid_padded, __nv_bfloat16 *out_padded,
+                     int n_img, int H, int W, int C, int relu, int train, float eps, float momentum, cudaStream_t st);
+
+// sums over pixels of dZ and dZ*xhat, dZ = dout * (out > 0)  [out_padded == nullptr: no ReLU in front]
+void launch_bn_bwd_reduce(const __nv_bfloat16 *dout, const __nv_bfloat16 *out_padded, const __nv_bfloat16 *y,
+                          const float *saved_mean, const float *saved_invstd, float *partials, int n_img, int H, int W,
+                          int C, cudaStream_t st);
+// partials -> dgamma, dbeta (into the grad arena) and the per-channel coefficients k1, m1, m2 of the apply pass
+void launch_bn_bwd_finalize(const float *partials, int C, const float *gamma, const float *saved_invstd, float count,
+                            int train, float *dgamma, float *dbeta, float *coef, cudaStream_t st);
+// dY = k1 * (dZ - m1 - xhat * m2); written padded (for the 4-D TMA consumers) or flat [M][C]; optionally dZ too
+void launch_bn_bwd_apply(const __nv_bfloat16 *dout, const __nv_bfloat16 *out_padded, const __nv_bfloat16 *y,
+                         const float *saved_mean, const float *saved_invstd, const float *coef, __nv_bfloat16 *dy,
+                         int dy_padded, __nv_bfloat16 *dz_flat, int n_img, int H, int W, int C, cudaStream_t st);
+
+// stem: x fp32 NCHW [n][3][H][W] -> ((x-mean)/std) -> 3x3/pad-1 patches, col[M][64] bf16 (27 valid, tap-major)
+void launch_stem_im2col(const float *x, __nv_bfloat16 *col, int n_img, int H, int W, const float *mean3,
+                        const float *inv_std3, cudaStream_t st);
+// stride-2 patches of the padded NHWC activation: col[Mout][ks*ks*C]
+void launch_im2col_s2(const __nv_bfloat16 *in_padded, __nv_bfloat16 *col, int n_img, int Hin, int Win, int C, int ks,
+                      cudaStream_t st);
+// dX[Min][C] = col2im(dcol3 [Mout][9C]) (+ dcol1 [Mout][C] at even pixels) (+ addend)
+void launch_col2im_s2(const __nv_bfloat16 *dcol3, const __nv_bfloat16 *dcol1, __nv_bfloat16 *dx, int n_img, int Hin,
+                      int Win, int C, cudaStream_t st);
+
+// weights: fp32 native [Cout][taps][Cin] -> bf16 operands
+void launch_prep_w_fwd(const float *w, __nv_bfloat16 *out, int Cout, int kc, int kc_padded, cudaStream_t st);
+void launch_prep_w_dgrad_s1(const float *w, __nv_bfloat16 *out, int Cout, int Cin, int taps, cudaStream_t st);
+void launch_prep_w_transpose(const float *w, __nv_bfloat16 *out, int Cout, int kc, cudaStream_t st);
+
+// head
+void launch_avgpool(const __nv_bfloat16 *act_padded, float *pooled, int n_img, int H, int W, int C, cudaStream_t st);
+void launch_fc_ce(const float *pooled, const float *w, const float *b, const int64_t *labels, float *logits,
+                  float *dlogits, float *loss_per_sample, int n_img, int C, int K, float sign, cudaStream_t st);
+void launch_loss_sum(const float *loss_per_sample, int n_img, float sign, float *loss_out, cudaStream_t st);
+void launch_fc_bwd(const float *pooled, const float *dlogits, const float *w, float *dw, float *db,
+                   __nv_bfloat16 *dact_flat, int n_img, int C, int K, int pix, cudaStream_t st);
+
+}  // namespace salun

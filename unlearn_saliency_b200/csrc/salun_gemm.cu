@@ -162,6 +162,20 @@ k_conv_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc_wait_ld();
       const int col0 = n_tile * BN + c * 32;
       if (col0 >= a.N) break;
+      if (row_ok && a.addend) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.addend + (size_t)row * a.ld_out + col0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 v = src[j];
+          const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 t = __bfloat1622float2(h[i]);
+            r[8 * j + 2 * i] = __float_as_uint(__uint_as_float(r[8 * j + 2 * i]) + t.x);
+            r[8 * j + 2 * i + 1] = __float_as_uint(__uint_as_float(r[8 * j + 2 * i + 1]) + t.y);
+          }
+        }
+      }
       if (row_ok) {
         if (a.out_bf16) {
           uint4 *dst = reinterpret_cast<uint4 *>(a.out_bf16 + (size_t)row * a.ld_out + col0);
@@ -258,12 +272,16 @@ k_wgrad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
           const uint32_t sa = smem_base + s * stage_bytes, sb = sa + 2 * kWgBlockBytes;
           mbar_arrive_expect_tx(full0 + 8 * s, (a_blocks + a.n_blocks) * kWgBlockBytes);
           const int pix0 = kb * kWgPix;
-          for (int j = 0; j < a_blocks; ++j)
-            tma_load_2d(sa + j * kWgBlockBytes, &tmA, full0 + 8 * s, co_tile * 128 + j * 64, pix0);
           int n0 = 0, y0 = 0;
-          if (a.mode_b == 1) {
+          if (a.mode_b == 1 || a.mode_a == 1) {
             n0 = pix0 / (a.H * a.W);
             y0 = (pix0 % (a.H * a.W)) / a.W;
+          }
+          for (int j = 0; j < a_blocks; ++j) {
+            if (a.mode_a == 1)
+              tma_load_4d(sa + j * kWgBlockBytes, &tmA, full0 + 8 * s, co_tile * 128 + j * 64, 1, 1 + y0, n0);
+            else
+              tma_load_2d(sa + j * kWgBlockBytes, &tmA, full0 + 8 * s, co_tile * 128 + j * 64, pix0);
           }
           for (int j = 0; j < a.n_blocks; ++j) {
             const int b = grp * a.n_blocks + j;

@@ -22,12 +22,14 @@ struct ConvGemmArgs {
   float *out_f32;           // [M][ld_out] or nullptr
   int ld_out;
   float *stat_sum, *stat_sq;  // per-(m tile, warp) column partial sums [gridDim.x * 4][N], or nullptr
+  const __nv_bfloat16 *addend;  // optional [M][ld_out]: D += addend before the store (residual-gradient merge)
 };
 
 // dW[co][b*64 + j] += sum_p dY[p][co] * X_b[p][j]   (both operands MN-major: pixels are the K dimension)
 // X_b is either a 64-column slab of a 2-D matrix Col[M][Kc] or the (tap, 64-channel) slab of the padded
 // NHWC activation.  Split-K over pixel ranges, fp32 red.global.add into dW.
 struct WgradArgs {
+  int mode_a;         // 0: dY is [M][Cout] row-major; 1: dY is halo-padded NHWC (interior is read)
   int mode_b;         // 0: 2-D Col[M][Kc]; 1: 4-D padded NHWC taps
   int kb_total;       // M / 64 (k-blocks of 64 pixels)
   int kb_per_split;

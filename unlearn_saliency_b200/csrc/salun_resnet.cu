@@ -1,0 +1,553 @@
+// salun_resnet.cu -- runtime of the BasicBlock ResNet (CIFAR stem) forward + backward on sm_100a.
+//
+// Replaces, for the SalUn hot path, model(image) and loss.backward() of
+//   Classification/generate_mask.py:35-39   (eval-mode BN, loss = -CE)        and
+//   Classification/unlearn/RL.py:128-132    (train-mode BN, CE)  (same in GA.py:113-117, FT.py:128-135)
+// on the architecture of Classification/models/ResNet.py:180-322 (resnet18/34, imagenet=False stem).
+//
+// Data layout in HBM
+//   parameters / gradients : one flat fp32 arena each, tensors in named_parameters() order; conv weights are kept
+//                            "native" = [Cout][kh][kw][Cin] (OHWI) so that the bf16 GEMM operand is a plain cast and
+//                            the wgrad kernel's red.add rows are contiguous.  The host mirror permutes at the boundary.
+//   activations            : bf16 NHWC with a zero halo, [n][H+2][W+2][C]; the tcgen05 conv kernels read their 3x3 taps
+//                            out of it with shifted 4-D TMA boxes (no im2col buffer for stride-1 convs).
+//   raw conv outputs       : bf16 [n*H*W][C]; BatchNorm batch statistics come out of the GEMM epilogue (fp32
+//                            accumulators) as per-tile partials and are reduced in double.
+// Every kernel launch below is enqueued on the caller's stream; nothing synchronises.
+#include <map>
+#include <vector>
+
+#include "salun_elem.cuh"
+#include "salun_gemm.cuh"
+
+namespace salun {
+
+typedef __nv_bfloat16 bf16;
+
+struct ConvL {
+  int cin, cout, ks, stride, hin, hout;
+  bool stem;
+  int kc, kcp;           // valid / padded reduction length (ks*ks*cin)
+  int64_t w_off, g_off, b_off;  // arena offsets: weight, BN gamma, BN beta
+  int rs_off;            // offset into the running-stat arenas
+  int in_act;            // index of the padded input activation (-1: network input)
+  bf16 *w_fwd, *w_dgrad, *col, *y, *dy, *dcol;
+  float *stat_sum, *stat_sq, *saved_mean, *saved_invstd, *coef, *bwd_partials;
+  double *slices;
+  bool dy_padded;
+};
+struct Act {
+  int C, H;
+  bf16 *p;       // padded [n][H+2][H+2][C]
+  bf16 *dout;    // gradient w.r.t. this activation, flat [n*H*H][C]
+  bf16 *dz;      // dout * (act > 0), flat (identity-shortcut blocks only)
+};
+struct Block {
+  int c1, c2, cd;          // conv indices (cd = -1: identity shortcut)
+  int in_act, mid_act, out_act;
+};
+struct ConvMaps {
+  CUtensorMap fwdA, fwdB, dgA, dgB, wgA, wgB, dgA1;
+};
+
+}  // namespace salun
+
+using namespace salun;
+
+struct salun_resnet {
+  salun_ctx *ctx;
+  salun_resnet_cfg cfg;
+  float *params, *grads, *rmean, *rvar;
+  int64_t n_params;
+  int n_bn_channels;
+  std::vector<ConvL> convs;
+  std::vector<Act> acts;
+  std::vector<Block> blocks;
+  int64_t fc_w_off, fc_b_off;
+  int feat;  // channels of the last stage
+  float *pooled, *logits, *dlogits, *loss_ps;
+  std::vector<void *> allocs;
+  std::map<int, std::vector<ConvMaps>> plans;
+  int last_n, last_train;
+  bool fwd_done;
+};
+
+namespace salun {
+
+static int stage_blocks(int depth, int s) {
+  static const int r18[4] = {2, 2, 2, 2}, r34[4] = {3, 4, 6, 3};
+  return depth == 34 ? r34[s] : r18[s];
+}
+
+// shared by create / param_count: walks the architecture in named_parameters() order
+static int build_arch(const salun_resnet_cfg &c, std::vector<ConvL> *convs, std::vector<Act> *acts,
+                      std::vector<Block> *blocks, int64_t *n_params, int *n_bn, int64_t *fcw, int64_t *fcb, int *feat) {
+  if (!(c.depth == 18 || c.depth == 34)) {
+    set_error("salun_resnet: depth %d not supported (BasicBlock nets 18/34)", c.depth);
+    return SALUN_ERR_UNSUPPORTED;
+  }
+  if (c.image_size != 32 && c.image_size != 64) {
+    set_error("salun_resnet: image_size %d not supported (power-of-two CIFAR-style stem: 32 or 64)", c.image_size);
+    return SALUN_ERR_UNSUPPORTED;
+  }
+  int64_t off = 0;
+  int rs = 0;
+  auto add_conv = [&](int cin, int cout, int ks, int stride, int hin, bool stem, int in_act) {
+    ConvL L{};
+    L.cin = cin; L.cout = cout; L.ks = ks; L.stride = stride; L.hin = hin; L.hout = hin / stride; L.stem = stem;
+    L.kc = ks * ks * cin;
+    L.kcp = (L.kc + 63) / 64 * 64;
+    L.w_off = off; off += (int64_t)cout * L.kc;
+    L.g_off = off; off += cout;
+    L.b_off = off; off += cout;
+    L.rs_off = rs; rs += cout;
+    L.in_act = in_act;
+    L.dy_padded = (!stem && stride == 1);
+    convs->push_back(L);
+    return (int)convs->size() - 1;
+  };
+  auto add_act = [&](int C, int H) {
+    Act a{};
+    a.C = C; a.H = H;
+    acts->push_back(a);
+    return (int)acts->size() - 1;
+  };
+  int H = c.image_size;
+  add_conv(3, 64, 3, 1, H, true, -1);
+  int cur = add_act(64, H);
+  int inpl = 64;
+  const int planes[4] = {64, 128, 256, 512};
+  for (int s = 0; s < 4; ++s) {
+    for (int b = 0; b < stage_blocks(c.depth, s); ++b) {
+      const int stride = (b == 0 && s > 0) ? 2 : 1;
+      Block B{};
+      B.in_act = cur;
+      // named_parameters order inside a BasicBlock: conv1, bn1, conv2, bn2, downsample.0, downsample.1
+      B.c1 = add_conv(inpl, planes[s], 3, stride, H, false, cur);
+      const int Ho = H / stride;
+      B.mid_act = add_act(planes[s], Ho);
+      B.c2 = add_conv(planes[s], planes[s], 3, 1, Ho, false, B.mid_act);
+      B.cd = -1;
+      if (stride != 1 || inpl != planes[s]) B.cd = add_conv(inpl, planes[s], 1, stride, H, false, cur);
+      B.out_act = add_act(planes[s], Ho);
+      blocks->push_back(B);
+      cur = B.out_act;
+      inpl = planes[s];
+      H = Ho;
+    }
+  }
+  *feat = inpl;
+  *fcw = off; off += (int64_t)c.num_classes * inpl;
+  *fcb = off; off += c.num_classes;
+  *n_params = off;
+  *n_bn = rs;
+  return SALUN_OK;
+}
+
+template <typename T>
+static int dmalloc(salun_resnet *net, T **p, size_t count, bool zero) {
+  void *q = nullptr;
+  SALUN_CUDA_OK(cudaMalloc(&q, count * sizeof(T)));
+  if (zero) SALUN_CUDA_OK(cudaMemset(q, 0, count * sizeof(T)));
+  net->allocs.push_back(q);
+  *p = (T *)q;
+  return SALUN_OK;
+}
+#define TRY(expr)              \
+  do {                         \
+    int _rc = (expr);          \
+    if (_rc) return _rc;       \
+  } while (0)
+
+static int build_plan(salun_resnet *net, int n, std::vector<ConvMaps> **out) {
+  auto it = net->plans.find(n);
+  if (it != net->plans.end()) {
+    *out = &it->second;
+    return SALUN_OK;
+  }
+  std::vector<ConvMaps> maps(net->convs.size());
+  for (size_t i = 0; i < net->convs.size(); ++i) {
+    const ConvL &L = net->convs[i];
+    ConvMaps &m = maps[i];
+    const int64_t Mout = (int64_t)n * L.hout * L.hout;
+    const int bn = L.cout % 128 == 0 ? 128 : 64;
+    TRY(make_tmap_2d_bf16(&m.fwdB, L.w_fwd, L.cout, L.kcp, bn, 64));
+    TmapBox4 bx128, bx64;
+    if (L.dy_padded) {
+      // stride-1 3x3: forward A and wgrad B read the padded input activation, dgrad A / wgrad A the padded dY
+      const Act &in = net->acts[L.in_act];
+      TRY(conv_box(L.hin, L.hin, 128, &bx128));
+      TRY(conv_box(L.hin, L.hin, 64, &bx64));
+      TRY(make_tmap_4d_bf16(&m.fwdA, in.p, L.cin, L.hin + 2, L.hin + 2, n, bx128));
+      TRY(make_tmap_4d_bf16(&m.dgA, L.dy, L.cout, L.hout + 2, L.hout + 2, n, bx128));
+      const int bnd = L.cin % 128 == 0 ? 128 : 64;
+      TRY(make_tmap_2d_bf16(&m.dgB, L.w_dgrad, L.cin, (uint64_t)L.ks * L.ks * L.cout, bnd, 64));
+      TRY(make_tmap_4d_bf16(&m.wgA, L.dy, L.cout, L.hout + 2, L.hout + 2, n, bx64));
+      TRY(make_tmap_4d_bf16(&m.wgB, in.p, L.cin, L.hin + 2, L.hin + 2, n, bx64));
+    } else {
+      // stem / stride-2: explicit patch matrix col[Mout][kcp]
+      TRY(make_tmap_2d_bf16(&m.fwdA, L.col, Mout, L.kcp, 128, 64));
+      TRY(make_tmap_2d_bf16(&m.wgA, L.dy, Mout, L.cout, 64, 64));
+      TRY(make_tmap_2d_bf16(&m.wgB, L.col, Mout, L.kcp, 64, 64));
+      if (!L.stem) {
+        // dgrad: dcol[Mout][kc] = dY[Mout][Cout] . Wt[kc][Cout]^T
+        TRY(make_tmap_2d_bf16(&m.dgA, L.dy, Mout, L.cout, 128, 64));
+        const int bnd = L.kc % 128 == 0 ? 128 : 64;
+        TRY(make_tmap_2d_bf16(&m.dgB, L.w_dgrad, L.kc, L.cout, bnd, 64));
+      }
+    }
+  }
+  auto res = net->plans.emplace(n, std::move(maps));
+  *out = &res.first->second;
+  return SALUN_OK;
+}
+
+static int conv_forward(salun_resnet *net, const ConvL &L, const ConvMaps &m, int n, int train, cudaStream_t st) {
+  const int M = n * L.hout * L.hout;
+  ConvGemmArgs a{};
+  a.M = M;
+  a.N = L.cout;
+  a.out_bf16 = L.y;
+  a.ld_out = L.cout;
+  if (train) {
+    a.stat_sum = L.stat_sum;
+    a.stat_sq = L.stat_sq;
+  }
+  const int bn = L.cout % 128 == 0 ? 128 : 64;
+  if (L.dy_padded) {
+    a.mode_a = 1;
+    a.cin_blocks = L.cin / 64;
+    a.num_k_blocks = L.ks * L.ks * a.cin_blocks;
+    a.kw = L.ks;
+    a.tap_y0 = a.tap_x0 = L.ks == 3 ? 0 : 1;
+    a.H = a.W = L.hout;
+  } else {
+    a.mode_a = 0;
+    a.num_k_blocks = L.kcp / 64;
+  }
+  TRY(launch_conv_gemm(m.fwdA, m.fwdB, a, bn, st));
+  if (train) launch_bn_stats_reduce(L.stat_sum, L.stat_sq, (M + 127) / 128 * 4, L.cout, L.slices, st);
+  return SALUN_OK;
+}
+
+static BnFwd bn_of(salun_resnet *net, const ConvL &L) {
+  BnFwd b;
+  b.y = L.y;
+  b.slices = L.slices;
+  b.gamma = net->params + L.g_off;
+  b.beta = net->params + L.b_off;
+  b.running_mean = net->rmean + L.rs_off;
+  b.running_var = net->rvar + L.rs_off;
+  b.saved_mean = L.saved_mean;
+  b.saved_invstd = L.saved_invstd;
+  return b;
+}
+
+static int wgrad_conv(salun_resnet *net, const ConvL &L, const ConvMaps &m, int n, cudaStream_t st) {
+  const int64_t M = (int64_t)n * L.hout * L.hout;
+  WgradArgs a{};
+  a.mode_a = L.dy_padded ? 1 : 0;
+  a.mode_b = L.dy_padded ? 1 : 0;
+  a.kb_total = (int)((M + 63) / 64);
+  a.cin_blocks = L.cin >= 64 ? L.cin / 64 : 1;
+  a.kw = L.ks;
+  a.tap_y0 = a.tap_x0 = L.ks == 3 ? 0 : 1;
+  a.H = a.W = L.hout;
+  a.total_blocks = L.kcp / 64;
+  a.n_blocks = wgrad_pick_blocks(a.total_blocks);
+  a.Cout = L.cout;
+  a.ldw = L.kc;
+  a.kvalid = L.kc;
+  a.dw = net->grads + L.w_off;
+  const int co_tiles = (L.cout + 127) / 128, groups = a.total_blocks / a.n_blocks;
+  int splits = (2 * net->ctx->num_sms + co_tiles * groups - 1) / (co_tiles * groups);
+  if (splits < 1) splits = 1;
+  if (splits > a.kb_total) splits = a.kb_total;
+  a.kb_per_split = (a.kb_total + splits - 1) / splits;
+  splits = (a.kb_total + a.kb_per_split - 1) / a.kb_per_split;
+  return launch_wgrad(m.wgA, m.wgB, a, co_tiles, groups, splits, st);
+}
+
+// BN backward of one conv's BatchNorm: dout (flat) [* relu mask of out_act] -> L.dy (+ dz)
+static void bn_backward(salun_resnet *net, const ConvL &L, const bf16 *dout, const bf16 *relu_act, bf16 *dz, int n,
+                        int train, cudaStream_t st) {
+  const int H = L.hout;
+  launch_bn_bwd_reduce(dout, relu_act, L.y, L.saved_mean, L.saved_invstd, L.bwd_partials, n, H, H, L.cout, st);
+  launch_bn_bwd_finalize(L.bwd_partials, L.cout, net->params + L.g_off, L.saved_invstd, (float)(n * H * H), train,
+                         net->grads + L.g_off, net->grads + L.b_off, L.coef, st);
+  launch_bn_bwd_apply(dout, relu_act, L.y, L.saved_mean, L.saved_invstd, L.coef, L.dy, L.dy_padded ? 1 : 0, dz, n, H, H,
+                      L.cout, st);
+}
+
+static int prep_weights(salun_resnet *net, bool need_dgrad, cudaStream_t st) {
+  for (const ConvL &L : net->convs) {
+    const float *w = net->params + L.w_off;
+    launch_prep_w_fwd(w, L.w_fwd, L.cout, L.kc, L.kcp, st);
+    if (need_dgrad && !L.stem) {
+      if (L.dy_padded)
+        launch_prep_w_dgrad_s1(w, L.w_dgrad, L.cout, L.cin, L.ks * L.ks, st);
+      else
+        launch_prep_w_transpose(w, L.w_dgrad, L.cout, L.kc, st);
+    }
+  }
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+
+static int forward_impl(salun_resnet *net, const float *x, const int64_t *labels, int n, int train, float sign,
+                        float *loss_dev, float *logits_out, bool need_bwd, cudaStream_t st) {
+  std::vector<ConvMaps> *plan;
+  TRY(build_plan(net, n, &plan));
+  TRY(prep_weights(net, need_bwd, st));
+  const salun_resnet_cfg &c = net->cfg;
+  const float inv_std[3] = {1.f / c.std[0], 1.f / c.std[1], 1.f / c.std[2]};
+  // stem
+  {
+    const ConvL &L = net->convs[0];
+    launch_stem_im2col(x, L.col, n, L.hin, L.hin, c.mean, inv_std, st);
+    TRY(conv_forward(net, L, (*plan)[0], n, train, st));
+    BnFwd b = bn_of(net, L);
+    launch_bn_apply(b, nullptr, nullptr, net->acts[0].p, n, L.hout, L.hout, L.cout, 1, train, c.bn_eps, c.bn_momentum,
+                    st);
+  }
+  for (const Block &B : net->blocks) {
+    const ConvL &L1 = net->convs[B.c1], &L2 = net->convs[B.c2];
+    const Act &in = net->acts[B.in_act], &mid = net->acts[B.mid_act], &out = net->acts[B.out_act];
+    if (!L1.dy_padded) launch_im2col_s2(in.p, L1.col, n, L1.hin, L1.hin, L1.cin, 3, st);
+    TRY(conv_forward(net, L1, (*plan)[B.c1], n, train, st));
+    BnFwd b1 = bn_of(net, L1);
+    launch_bn_apply(b1, nullptr, nullptr, mid.p, n, L1.hout, L1.hout, L1.cout, 1, train, c.bn_eps, c.bn_momentum, st);
+    TRY(conv_forward(net, L2, (*plan)[B.c2], n, train, st));
+    BnFwd b2 = bn_of(net, L2);
+    if (B.cd >= 0) {
+      const ConvL &Ld = net->convs[B.cd];
+      launch_im2col_s2(in.p, Ld.col, n, Ld.hin, Ld.hin, Ld.cin, 1, st);
+      TRY(conv_forward(net, Ld, (*plan)[B.cd], n, train, st));
+      BnFwd bd = bn_of(net, Ld);
+      launch_bn_apply(b2, &bd, nullptr, out.p, n, L2.hout, L2.hout, L2.cout, 1, train, c.bn_eps, c.bn_momentum, st);
+    } else {
+      launch_bn_apply(b2, nullptr, in.p, out.p, n, L2.hout, L2.hout, L2.cout, 1, train, c.bn_eps, c.bn_momentum, st);
+    }
+  }
+  const Act &last = net->acts[net->blocks.back().out_act];
+  launch_avgpool(last.p, net->pooled, n, last.H, last.H, last.C, st);
+  launch_fc_ce(net->pooled, net->params + net->fc_w_off, net->params + net->fc_b_off, labels,
+               logits_out ? logits_out : net->logits, net->dlogits, net->loss_ps, n, net->feat, c.num_classes, sign, st);
+  if (labels && loss_dev) launch_loss_sum(net->loss_ps, n, sign, loss_dev, st);
+  SALUN_CUDA_OK(cudaGetLastError());
+  net->last_n = n;
+  net->last_train = train;
+  net->fwd_done = true;
+  return SALUN_OK;
+}
+
+static int backward_impl(salun_resnet *net, cudaStream_t st) {
+  if (!net->fwd_done) {
+    set_error("salun_resnet backward called before forward");
+    return SALUN_ERR_STATE;
+  }
+  const int n = net->last_n, train = net->last_train;
+  std::vector<ConvMaps> *plan;
+  TRY(build_plan(net, n, &plan));
+  SALUN_CUDA_OK(cudaMemsetAsync(net->grads, 0, (size_t)net->n_params * sizeof(float), st));
+  const Act &last = net->acts[net->blocks.back().out_act];
+  launch_fc_bwd(net->pooled, net->dlogits, net->params + net->fc_w_off, net->grads + net->fc_w_off,
+                net->grads + net->fc_b_off, last.dout, n, net->feat, net->cfg.num_classes, last.H * last.H, st);
+  for (int bi = (int)net->blocks.size() - 1; bi >= 0; --bi) {
+    const Block &B = net->blocks[bi];
+    const ConvL &L1 = net->convs[B.c1], &L2 = net->convs[B.c2];
+    const Act &in = net->acts[B.in_act], &mid = net->acts[B.mid_act], &out = net->acts[B.out_act];
+    const bool identity = B.cd < 0;
+    // out = relu(bn2(y2) + shortcut):  dZ = dOut * (out > 0)
+    bn_backward(net, L2, out.dout, out.p, identity ? out.dz : nullptr, n, train, st);
+    if (!identity) bn_backward(net, net->convs[B.cd], out.dout, out.p, nullptr, n, train, st);
+    // conv2: dgrad -> d(mid), wgrad
+    {
+      ConvGemmArgs a{};
+      a.mode_a = 1;
+      a.cin_blocks = L2.cout / 64;
+      a.num_k_blocks = 9 * a.cin_blocks;
+      a.kw = 3;
+      a.H = a.W = L2.hout;
+      a.M = n * L2.hout * L2.hout;
+      a.N = L2.cin;
+      a.out_bf16 = mid.dout;
+      a.ld_out = L2.cin;
+      TRY(launch_conv_gemm((*plan)[B.c2].dgA, (*plan)[B.c2].dgB, a, L2.cin % 128 == 0 ? 128 : 64, st));
+      TRY(wgrad_conv(net, L2, (*plan)[B.c2], n, st));
+    }
+    // mid = relu(bn1(y1))
+    bn_backward(net, L1, mid.dout, mid.p, nullptr, n, train, st);
+    if (L1.dy_padded) {
+      ConvGemmArgs a{};
+      a.mode_a = 1;
+      a.cin_blocks = L1.cout / 64;
+      a.num_k_blocks = 9 * a.cin_blocks;
+      a.kw = 3;
+      a.H = a.W = L1.hout;
+      a.M = n * L1.hout * L1.hout;
+      a.N = L1.cin;
+      a.out_bf16 = in.dout;
+      a.ld_out = L1.cin;
+      a.addend = identity ? out.dz : nullptr;  // gradient of the identity shortcut
+      TRY(launch_conv_gemm((*plan)[B.c1].dgA, (*plan)[B.c1].dgB, a, L1.cin % 128 == 0 ? 128 : 64, st));
+      if (!identity) {
+        set_error("salun_resnet: stride-1 block with projection shortcut is not supported");
+        return SALUN_ERR_UNSUPPORTED;
+      }
+    } else {
+      // stride 2: dcol = dY . W ; then col2im gathers the 3x3 taps and the 1x1 projection shortcut
+      const ConvL &Ld = net->convs[B.cd];
+      const int Mo = n * L1.hout * L1.hout;
+      ConvGemmArgs a{};
+      a.mode_a = 0;
+      a.num_k_blocks = L1.cout / 64;
+      a.M = Mo;
+      a.N = L1.kc;
+      a.out_bf16 = L1.dcol;
+      a.ld_out = L1.kc;
+      TRY(launch_conv_gemm((*plan)[B.c1].dgA, (*plan)[B.c1].dgB, a, L1.kc % 128 == 0 ? 128 : 64, st));
+      ConvGemmArgs d{};
+      d.mode_a = 0;
+      d.num_k_blocks = Ld.cout / 64;
+      d.M = Mo;
+      d.N = Ld.kc;
+      d.out_bf16 = Ld.dcol;
+      d.ld_out = Ld.kc;
+      TRY(launch_conv_gemm((*plan)[B.cd].dgA, (*plan)[B.cd].dgB, d, Ld.kc % 128 == 0 ? 128 : 64, st));
+      launch_col2im_s2(L1.dcol, Ld.dcol, in.dout, n, L1.hin, L1.hin, L1.cin, st);
+      TRY(wgrad_conv(net, Ld, (*plan)[B.cd], n, st));
+    }
+    TRY(wgrad_conv(net, L1, (*plan)[B.c1], n, st));
+  }
+  // stem: act0 = relu(bn(y0)); no dgrad (the input needs no gradient)
+  {
+    const ConvL &L = net->convs[0];
+    bn_backward(net, L, net->acts[0].dout, net->acts[0].p, nullptr, n, train, st);
+    TRY(wgrad_conv(net, L, (*plan)[0], n, st));
+  }
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+
+}  // namespace salun
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int64_t salun_resnet_param_count(const salun_resnet_cfg *cfg) {
+  if (!cfg) return -1;
+  std::vector<ConvL> c;
+  std::vector<Act> a;
+  std::vector<Block> b;
+  int64_t n, fw, fb;
+  int nb, feat;
+  if (build_arch(*cfg, &c, &a, &b, &n, &nb, &fw, &fb, &feat)) return -1;
+  return n;
+}
+
+int64_t salun_resnet_bn_channels(const salun_resnet_cfg *cfg) {
+  if (!cfg) return -1;
+  std::vector<ConvL> c;
+  std::vector<Act> a;
+  std::vector<Block> b;
+  int64_t n, fw, fb;
+  int nb, feat;
+  if (build_arch(*cfg, &c, &a, &b, &n, &nb, &fw, &fb, &feat)) return -1;
+  return nb;
+}
+
+int salun_resnet_create(salun_ctx *ctx, const salun_resnet_cfg *cfg, float *params, float *grads, float *running_mean,
+                        float *running_var, salun_resnet **out) {
+  SALUN_REQUIRE(ctx && cfg && params && grads && running_mean && running_var && out, "NULL argument");
+  SALUN_REQUIRE(cfg->max_batch > 0 && cfg->num_classes > 0, "max_batch and num_classes must be positive");
+  SALUN_CUDA_OK(cudaSetDevice(ctx->device));
+  salun_resnet *net = new salun_resnet();
+  net->ctx = ctx;
+  net->cfg = *cfg;
+  net->params = params;
+  net->grads = grads;
+  net->rmean = running_mean;
+  net->rvar = running_var;
+  net->fwd_done = false;
+  int rc = build_arch(*cfg, &net->convs, &net->acts, &net->blocks, &net->n_params, &net->n_bn_channels, &net->fc_w_off,
+                      &net->fc_b_off, &net->feat);
+  if (rc) {
+    delete net;
+    return rc;
+  }
+  const int64_t nb = (cfg->max_batch + 7) / 8 * 8;  // TMA boxes cover up to 8 images of the 4x4 stage
+#define A(expr)                     \
+  do {                              \
+    int _rc = (expr);               \
+    if (_rc) {                      \
+      salun_resnet_destroy(net);    \
+      return _rc;                   \
+    }                               \
+  } while (0)
+  for (Act &a : net->acts) {
+    const size_t padded = (size_t)nb * (a.H + 2) * (a.H + 2) * a.C;
+    A(dmalloc(net, &a.p, padded, true));
+    A(dmalloc(net, &a.dout, (size_t)nb * a.H * a.H * a.C, false));
+    A(dmalloc(net, &a.dz, (size_t)nb * a.H * a.H * a.C, false));
+  }
+  for (ConvL &L : net->convs) {
+    const size_t Mo = (size_t)nb * L.hout * L.hout;
+    A(dmalloc(net, &L.w_fwd, (size_t)L.cout * L.kcp, true));
+    if (!L.stem) A(dmalloc(net, &L.w_dgrad, (size_t)L.cout * L.kc, true));
+    A(dmalloc(net, &L.y, Mo * L.cout, false));
+    if (L.dy_padded) {
+      A(dmalloc(net, &L.dy, (size_t)nb * (L.hout + 2) * (L.hout + 2) * L.cout, true));
+    } else {
+      A(dmalloc(net, &L.dy, Mo * L.cout, false));
+      A(dmalloc(net, &L.col, Mo * L.kcp, true));
+      if (!L.stem) A(dmalloc(net, &L.dcol, Mo * L.kc, false));
+    }
+    const size_t rows = (Mo + 127) / 128 * 4;
+    A(dmalloc(net, &L.stat_sum, rows * L.cout, true));
+    A(dmalloc(net, &L.stat_sq, rows * L.cout, true));
+    A(dmalloc(net, &L.slices, (size_t)kStatSlices * 2 * L.cout, true));
+    A(dmalloc(net, &L.saved_mean, (size_t)L.cout, true));
+    A(dmalloc(net, &L.saved_invstd, (size_t)L.cout, true));
+    A(dmalloc(net, &L.coef, (size_t)3 * L.cout, true));
+    A(dmalloc(net, &L.bwd_partials, (size_t)kBwdPartialRows * 2 * L.cout, true));
+  }
+  A(dmalloc(net, &net->pooled, (size_t)nb * net->feat, true));
+  A(dmalloc(net, &net->logits, (size_t)nb * cfg->num_classes, true));
+  A(dmalloc(net, &net->dlogits, (size_t)nb * cfg->num_classes, true));
+  A(dmalloc(net, &net->loss_ps, (size_t)nb, true));
+#undef A
+  *out = net;
+  return SALUN_OK;
+}
+
+int salun_resnet_destroy(salun_resnet *net) {
+  if (!net) return SALUN_OK;
+  cudaSetDevice(net->ctx->device);
+  for (void *p : net->allocs) cudaFree(p);
+  delete net;
+  return SALUN_OK;
+}
+
+int salun_resnet_forward_backward(salun_resnet *net, const float *x, const int64_t *labels, int n, int train,
+                                  float loss_sign, float *loss_dev, float *logits_dev, void *stream) {
+  SALUN_REQUIRE(net && x && labels, "NULL argument");
+  SALUN_REQUIRE(n > 0 && n <= net->cfg.max_batch, "batch size out of range");
+  SALUN_CUDA_OK(cudaSetDevice(net->ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  TRY(forward_impl(net, x, labels, n, train, loss_sign, loss_dev, logits_dev, true, st));
+  return backward_impl(net, st);
+}
+
+int salun_resnet_forward(salun_resnet *net, const float *x, int n, float *logits_dev, void *stream) {
+  SALUN_REQUIRE(net && x && logits_dev, "NULL argument");
+  SALUN_REQUIRE(n > 0 && n <= net->cfg.max_batch, "batch size out of range");
+  SALUN_CUDA_OK(cudaSetDevice(net->ctx->device));
+  int rc = forward_impl(net, x, nullptr, n, 0, 1.f, nullptr, logits_dev, false, (cudaStream_t)stream);
+  net->fwd_done = false;
+  return rc;
+}
+
+}  // extern "C"
