@@ -41,6 +41,13 @@ typedef struct salun_ctx salun_ctx;
 
 /* ABI version: major*1000 + minor */
 int salun_version(void);
+/* number of kernels this library has launched since it was loaded (bench.py: gpu_launches) */
+long long salun_launch_count(void);
+/* Per-launch CUDA-event timing of the two tensor-core kernels (category 0 = conv forward/dgrad GEMM,
+ * 1 = wgrad GEMM).  begin() arms it; end() synchronises the device and returns, per category, summed
+ * milliseconds, launch count and algorithmic FLOPs.  Arrays of 2; any may be NULL. */
+int salun_profile_begin(void);
+int salun_profile_end(double *ms_by_cat, int64_t *launches_by_cat, double *flops_by_cat);
 const char *salun_last_error(void);
 
 /* One context per (thread, device).  Owns the small device workspaces (radix-select

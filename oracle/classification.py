@@ -112,32 +112,68 @@ def _bn(x, p, b, name, train: bool, momentum: float = 0.1, eps: float = 1e-5):
     return F.batch_norm(x, rm, rv, p[name + ".weight"], p[name + ".bias"], train, momentum, eps)
 
 
+class _RoundFwd(torch.autograd.Function):
+    """value stored in bf16 by the engine (conv operand); its gradient stays fp32"""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _RoundBoth(torch.autograd.Function):
+    """tensor whose value AND whose gradient the engine stores in bf16 (raw conv outputs, activations)"""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
 def resnet_forward(p: Dict[str, torch.Tensor], b: Dict[str, torch.Tensor], x: torch.Tensor, train: bool,
-                   mean=CIFAR_MEAN, std=CIFAR_STD) -> torch.Tensor:
+                   mean=CIFAR_MEAN, std=CIFAR_STD, emulate_bf16: bool = False) -> torch.Tensor:
+    """emulate_bf16=False: the reference's fp32 op chain.
+    emulate_bf16=True : the SAME chain in fp32 arithmetic, with a bf16 rounding at every point where the sm_100a engine
+    stores a tensor in bf16 (DESIGN.md "precision"): conv operands (normalised input, weights), raw conv outputs and
+    activations, and -- on the way back -- the gradients of those outputs / activations.  This is the plain-PyTorch
+    reference of the op the kernels actually implement; the fp32 chain measures what bf16 storage costs."""
+    rf = _RoundFwd.apply if emulate_bf16 else (lambda t: t)
+    rb = _RoundBoth.apply if emulate_bf16 else (lambda t: t)
     m = torch.tensor(mean, dtype=x.dtype)[None, :, None, None]
     s = torch.tensor(std, dtype=x.dtype)[None, :, None, None]
-    x = x.sub(m).div(s)  # ResNet.py:23-28
-    x = F.relu(_bn(F.conv2d(x, p["conv1.weight"], padding=1), p, b, "bn1", train))  # :307-310 (maxpool = Identity)
+    if emulate_bf16:
+        x = (x - m) * (1.0 / s)  # the engine multiplies by 1/std
+    else:
+        x = x.sub(m).div(s)  # ResNet.py:23-28
+    x = rf(x)
+    w = lambda k: rf(p[k])
+    x = rb(F.relu(_bn(rb(F.conv2d(x, w("conv1.weight"), padding=1)), p, b, "bn1", train)))  # :307-310 (maxpool = Identity)
     inpl = 64
     for li, (planes, stride) in enumerate(STAGES, start=1):
         for blk in range(2):
             pre = f"layer{li}.{blk}."
             st = stride if blk == 0 else 1
             identity = x
-            out = F.relu(_bn(F.conv2d(x, p[pre + "conv1.weight"], stride=st, padding=1), p, b, pre + "bn1", train))
-            out = _bn(F.conv2d(out, p[pre + "conv2.weight"], padding=1), p, b, pre + "bn2", train)
+            out = rb(F.relu(_bn(rb(F.conv2d(x, w(pre + "conv1.weight"), stride=st, padding=1)), p, b, pre + "bn1", train)))
+            out = _bn(rb(F.conv2d(out, w(pre + "conv2.weight"), padding=1)), p, b, pre + "bn2", train)
             if pre + "downsample.0.weight" in p:
-                identity = _bn(F.conv2d(x, p[pre + "downsample.0.weight"], stride=st), p, b, pre + "downsample.1", train)
-            x = F.relu(out + identity)  # :121-122
+                identity = _bn(rb(F.conv2d(x, w(pre + "downsample.0.weight"), stride=st)), p, b, pre + "downsample.1", train)
+            x = rb(F.relu(out + identity))  # :121-122
             inpl = planes
     x = F.adaptive_avg_pool2d(x, 1).flatten(1)  # :317-318
     return F.linear(x, p["fc.weight"], p["fc.bias"])  # :320
 
 
-def loss_and_grads(p, b, x, y, train: bool, sign: float = 1.0):
+def loss_and_grads(p, b, x, y, train: bool, sign: float = 1.0, emulate_bf16: bool = False):
     """sign * mean CE and its gradient w.r.t. every parameter (zero_grad + backward of the reference loops)."""
     leaves = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in p.items())
-    out = resnet_forward(leaves, b, x, train)
+    out = resnet_forward(leaves, b, x, train, emulate_bf16=emulate_bf16)
     loss = sign * F.cross_entropy(out, y)
     grads = torch.autograd.grad(loss, list(leaves.values()))
     return loss.detach(), out.detach(), OrderedDict(zip(leaves.keys(), grads))
@@ -149,11 +185,11 @@ def loss_and_grads(p, b, x, y, train: bool, sign: float = 1.0):
 THRESHOLDS = [0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0]  # generate_mask.py:50
 
 
-def accumulate_saliency(p, b, batches: Iterable[Tuple[torch.Tensor, torch.Tensor]]):
+def accumulate_saliency(p, b, batches: Iterable[Tuple[torch.Tensor, torch.Tensor]], emulate_bf16: bool = False):
     """generate_mask.py:25-48: eval mode, loss = -CE, gradients[name] += grad, abs_ at the end. Returns flat |G|."""
     acc = None
     for x, y in batches:
-        _, _, g = loss_and_grads(p, b, x, y, train=False, sign=-1.0)
+        _, _, g = loss_and_grads(p, b, x, y, train=False, sign=-1.0, emulate_bf16=emulate_bf16)
         flat = torch.cat([t.flatten() for t in g.values()])
         acc = flat if acc is None else acc + flat
     return acc.abs_()
@@ -208,8 +244,8 @@ class MaskedSGD:
             self.p[k] = newp
 
 
-def unlearn_step(p, b, opt: MaskedSGD, x, y, sign: float = 1.0):
+def unlearn_step(p, b, opt: MaskedSGD, x, y, sign: float = 1.0, emulate_bf16: bool = False):
     """one loop body of RL/GA/FT: train-mode forward, backward, mask, SGD, restore. Returns (loss, logits)."""
-    loss, out, g = loss_and_grads(p, b, x, y, train=True, sign=sign)
+    loss, out, g = loss_and_grads(p, b, x, y, train=True, sign=sign, emulate_bf16=emulate_bf16)
     opt.step(g)
     return loss, out

@@ -13,7 +13,7 @@ g = torch.Generator().manual_seed(11)
 x = torch.rand(32, 3, 32, 32, generator=g); y = torch.randint(0, 10, (32,), generator=g)
 for train, sign in ((False, -1.0), (True, 1.0)):
     b = {k: v.clone() for k, v in buffers.items()}
-    lr, lg, gr = OC.loss_and_grads(params, b, x, y, train=train, sign=sign)
+    lr, lg, gr = OC.loss_and_grads(params, b, x, y, train=train, sign=sign, emulate_bf16=True)
     eng.train(train)
     loss, logits = eng.forward_backward(x.cuda(), y.cuda(), loss_sign=sign, want_logits=True)
     torch.cuda.synchronize()
@@ -22,7 +22,7 @@ for train, sign in ((False, -1.0), (True, 1.0)):
     for k, r in gr.items():
         e = gd[k].cpu()
         rel = float((e - r).norm() / (r.norm() + 1e-12)); cos = float(torch.dot(e.flatten(), r.flatten()) / (e.norm() * r.norm() + 1e-20))
-        if rel > 0.02 or cos < 0.9995 or k in ("conv1.weight", "fc.weight", "layer2.0.downsample.0.weight", "layer4.1.conv2.weight", "bn1.weight"):
+        if rel > 0.01 or cos < 0.9995 or k in ("conv1.weight", "fc.weight", "layer2.0.downsample.0.weight", "layer4.1.conv2.weight", "bn1.weight"):
             print(f"   {k:34s} rel {rel:.4f} cos {cos:.6f} |ref| {r.norm().item():.4e}", flush=True)
 
 # timing at the benchmark shape

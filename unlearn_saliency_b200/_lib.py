@@ -37,6 +37,9 @@ _F = C.c_float
 # name -> argtypes (restype is always int unless listed in _RESTYPES)
 _SIGNATURES = {
     "salun_version": [],
+    "salun_launch_count": [],
+    "salun_profile_begin": [],
+    "salun_profile_end": [_P, _P, _P],
     "salun_last_error": [],
     "salun_ctx_create": [C.c_int, C.POINTER(_P)],
     "salun_ctx_destroy": [_P],
@@ -63,7 +66,7 @@ _SIGNATURES = {
     "salun_resnet_forward_backward": [_P, _P, _P, C.c_int, C.c_int, _F, _P, _P, _P],
     "salun_resnet_forward": [_P, _P, C.c_int, _P, _P],
 }
-_RESTYPES = {"salun_last_error": C.c_char_p, "salun_resnet_param_count": C.c_int64,
+_RESTYPES = {"salun_last_error": C.c_char_p, "salun_launch_count": C.c_longlong, "salun_resnet_param_count": C.c_int64,
              "salun_resnet_bn_channels": C.c_int64}
 
 

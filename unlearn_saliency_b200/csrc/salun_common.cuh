@@ -31,6 +31,8 @@ void set_error(const char *fmt, ...);
     }                                                                                        \
   } while (0)
 
+extern long long g_launch_count;  // kernels launched by this library (bench.py reports it as gpu_launches)
+
 constexpr int kRadixBins = 2048;      // 11-bit digits: 3 passes over a 32-bit key
 constexpr int kMaxPartials = 148 * 8; // one partial per CTA of the persistent reduction grids
 

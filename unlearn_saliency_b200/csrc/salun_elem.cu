@@ -6,6 +6,8 @@
 
 #include <math.h>
 
+#include "salun_common.cuh"
+
 namespace salun {
 
 constexpr int kET = 256;
@@ -64,7 +66,7 @@ __global__ void k_bn_stats_reduce(const float *__restrict__ ssum, const float *_
 void launch_bn_stats_reduce(const float *stat_sum, const float *stat_sq, int rows, int C, double *slices,
                             cudaStream_t st) {
   dim3 grid((C + 31) / 32, kStatSlices), block(32, 8);
-  k_bn_stats_reduce<<<grid, block, 0, st>>>(stat_sum, stat_sq, rows, C, slices);
+  { k_bn_stats_reduce<<<grid, block, 0, st>>>(stat_sum, stat_sq, rows, C, slices); ++::salun::g_launch_count; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -147,8 +149,8 @@ void launch_bn_apply(const BnFwd &a, const BnFwd *b, const __nv_bfloat16 *resid_
                      int n_img, int H, int W, int C, int relu, int train, float eps, float momentum, cudaStream_t st) {
   const int M = n_img * H * W;
   BnFwd bb = b ? *b : a;
-  k_bn_apply<<<elem_grid(M, C), kET, 4 * C * sizeof(float), st>>>(a, bb, b != nullptr, resid_padded, out_padded, M, H,
-                                                                  W, C, relu, train, eps, momentum);
+  { k_bn_apply<<<elem_grid(M, C), kET, 4 * C * sizeof(float), st>>>(a, bb, b != nullptr, resid_padded, out_padded, M, H,
+                                                                  W, C, relu, train, eps, momentum); ++::salun::g_launch_count; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -211,8 +213,8 @@ void launch_bn_bwd_reduce(const __nv_bfloat16 *dout, const __nv_bfloat16 *out_pa
                           int C, cudaStream_t st) {
   const int M = n_img * H * W;
   const int rpb = kET / (C >> 3);
-  k_bn_bwd_reduce<<<bwd_rows(M, C), kET, 2 * rpb * C * sizeof(float), st>>>(dout, out_padded, y, saved_mean,
-                                                                           saved_invstd, partials, M, H, W, C);
+  { k_bn_bwd_reduce<<<bwd_rows(M, C), kET, 2 * rpb * C * sizeof(float), st>>>(dout, out_padded, y, saved_mean,
+                                                                           saved_invstd, partials, M, H, W, C); ++::salun::g_launch_count; }
 }
 
 __global__ void k_bn_bwd_finalize(const float *__restrict__ partials, int rows, int C, const float *__restrict__ gamma,
@@ -245,8 +247,8 @@ void launch_bn_bwd_finalize(const float *partials, int C, const float *gamma, co
                             int train, float *dgamma, float *dbeta, float *coef, cudaStream_t st) {
   const int M = (int)count;
   dim3 grid((C + 31) / 32), block(32, 8);
-  k_bn_bwd_finalize<<<grid, block, 0, st>>>(partials, bwd_rows(M, C), C, gamma, saved_invstd, count, train, dgamma,
-                                            dbeta, coef);
+  { k_bn_bwd_finalize<<<grid, block, 0, st>>>(partials, bwd_rows(M, C), C, gamma, saved_invstd, count, train, dgamma,
+                                            dbeta, coef); ++::salun::g_launch_count; }
 }
 
 __global__ void __launch_bounds__(kET) k_bn_bwd_apply(const __nv_bfloat16 *__restrict__ dout,
@@ -287,8 +289,8 @@ void launch_bn_bwd_apply(const __nv_bfloat16 *dout, const __nv_bfloat16 *out_pad
                          const float *saved_mean, const float *saved_invstd, const float *coef, __nv_bfloat16 *dy,
                          int dy_padded, __nv_bfloat16 *dz_flat, int n_img, int H, int W, int C, cudaStream_t st) {
   const int M = n_img * H * W;
-  k_bn_bwd_apply<<<elem_grid(M, C), kET, 0, st>>>(dout, out_padded, y, saved_mean, saved_invstd, coef, dy, dy_padded,
-                                                  dz_flat, M, H, W, C);
+  { k_bn_bwd_apply<<<elem_grid(M, C), kET, 0, st>>>(dout, out_padded, y, saved_mean, saved_invstd, coef, dy, dy_padded,
+                                                  dz_flat, M, H, W, C); ++::salun::g_launch_count; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -330,8 +332,8 @@ __global__ void __launch_bounds__(kET) k_stem_im2col(const float *__restrict__ x
 void launch_stem_im2col(const float *x, __nv_bfloat16 *col, int n_img, int H, int W, const float *mean3,
                         const float *inv_std3, cudaStream_t st) {
   const int M = n_img * H * W;
-  k_stem_im2col<<<(M + kET - 1) / kET, kET, 0, st>>>(x, col, M, H, W, mean3[0], mean3[1], mean3[2], inv_std3[0],
-                                                     inv_std3[1], inv_std3[2]);
+  { k_stem_im2col<<<(M + kET - 1) / kET, kET, 0, st>>>(x, col, M, H, W, mean3[0], mean3[1], mean3[2], inv_std3[0],
+                                                     inv_std3[1], inv_std3[2]); ++::salun::g_launch_count; }
 }
 
 __global__ void __launch_bounds__(kET) k_im2col_s2(const __nv_bfloat16 *__restrict__ in, __nv_bfloat16 *__restrict__ col,
@@ -356,7 +358,7 @@ void launch_im2col_s2(const __nv_bfloat16 *in_padded, __nv_bfloat16 *col, int n_
   const long long total = (long long)n_img * (Hin / 2) * (Win / 2) * ks * ks * (C >> 3);
   long long g = (total + kET - 1) / kET;
   if (g > 148 * 16) g = 148 * 16;
-  k_im2col_s2<<<(int)g, kET, 0, st>>>(in_padded, col, total, Hin, Win, C, ks);
+  { k_im2col_s2<<<(int)g, kET, 0, st>>>(in_padded, col, total, Hin, Win, C, ks); ++::salun::g_launch_count; }
 }
 
 __global__ void __launch_bounds__(kET) k_col2im_s2(const __nv_bfloat16 *__restrict__ dcol3,
@@ -401,7 +403,7 @@ void launch_col2im_s2(const __nv_bfloat16 *dcol3, const __nv_bfloat16 *dcol1, __
   const long long total = (long long)n_img * Hin * Win * (C >> 3);
   long long g = (total + kET - 1) / kET;
   if (g > 148 * 16) g = 148 * 16;
-  k_col2im_s2<<<(int)g, kET, 0, st>>>(dcol3, dcol1, dx, total, Hin, Win, C);
+  { k_col2im_s2<<<(int)g, kET, 0, st>>>(dcol3, dcol1, dx, total, Hin, Win, C); ++::salun::g_launch_count; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -442,13 +444,13 @@ static inline int flat_grid(long long total) {
   return (int)(g < 1 ? 1 : g);
 }
 void launch_prep_w_fwd(const float *w, __nv_bfloat16 *out, int Cout, int kc, int kc_padded, cudaStream_t st) {
-  k_prep_w_fwd<<<flat_grid((long long)Cout * kc_padded), 256, 0, st>>>(w, out, Cout, kc, kc_padded);
+  { k_prep_w_fwd<<<flat_grid((long long)Cout * kc_padded), 256, 0, st>>>(w, out, Cout, kc, kc_padded); ++::salun::g_launch_count; }
 }
 void launch_prep_w_dgrad_s1(const float *w, __nv_bfloat16 *out, int Cout, int Cin, int taps, cudaStream_t st) {
-  k_prep_w_dgrad_s1<<<flat_grid((long long)Cout * Cin * taps), 256, 0, st>>>(w, out, Cout, Cin, taps);
+  { k_prep_w_dgrad_s1<<<flat_grid((long long)Cout * Cin * taps), 256, 0, st>>>(w, out, Cout, Cin, taps); ++::salun::g_launch_count; }
 }
 void launch_prep_w_transpose(const float *w, __nv_bfloat16 *out, int Cout, int kc, cudaStream_t st) {
-  k_prep_w_transpose<<<flat_grid((long long)Cout * kc), 256, 0, st>>>(w, out, Cout, kc);
+  { k_prep_w_transpose<<<flat_grid((long long)Cout * kc), 256, 0, st>>>(w, out, Cout, kc); ++::salun::g_launch_count; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -465,7 +467,7 @@ __global__ void k_avgpool(const __nv_bfloat16 *__restrict__ act, float *__restri
   pooled[i] = s / (float)(H * W);
 }
 void launch_avgpool(const __nv_bfloat16 *act_padded, float *pooled, int n_img, int H, int W, int C, cudaStream_t st) {
-  k_avgpool<<<(n_img * C + 255) / 256, 256, 0, st>>>(act_padded, pooled, n_img, H, W, C);
+  { k_avgpool<<<(n_img * C + 255) / 256, 256, 0, st>>>(act_padded, pooled, n_img, H, W, C); ++::salun::g_launch_count; }
 }
 
 __global__ void __launch_bounds__(128) k_fc_ce(const float *__restrict__ pooled, const float *__restrict__ w,
@@ -504,8 +506,8 @@ __global__ void __launch_bounds__(128) k_fc_ce(const float *__restrict__ pooled,
 }
 void launch_fc_ce(const float *pooled, const float *w, const float *b, const int64_t *labels, float *logits,
                   float *dlogits, float *loss_per_sample, int n_img, int C, int K, float sign, cudaStream_t st) {
-  k_fc_ce<<<n_img, 128, K * sizeof(float), st>>>(pooled, w, b, labels, logits, dlogits, loss_per_sample, n_img, C, K,
-                                                  sign);
+  { k_fc_ce<<<n_img, 128, K * sizeof(float), st>>>(pooled, w, b, labels, logits, dlogits, loss_per_sample, n_img, C, K,
+                                                  sign); ++::salun::g_launch_count; }
 }
 __global__ void k_loss_sum(const float *__restrict__ l, int n, float sign, float *__restrict__ out) {
   __shared__ float sh[32];
@@ -521,7 +523,7 @@ __global__ void k_loss_sum(const float *__restrict__ l, int n, float sign, float
   }
 }
 void launch_loss_sum(const float *loss_per_sample, int n_img, float sign, float *loss_out, cudaStream_t st) {
-  k_loss_sum<<<1, 256, 0, st>>>(loss_per_sample, n_img, sign, loss_out);
+  { k_loss_sum<<<1, 256, 0, st>>>(loss_per_sample, n_img, sign, loss_out); ++::salun::g_launch_count; }
 }
 
 __global__ void k_fc_bwd_w(const float *__restrict__ pooled, const float *__restrict__ dl, float *__restrict__ dw,
@@ -550,8 +552,8 @@ __global__ void k_fc_bwd_x(const float *__restrict__ dl, const float *__restrict
 }
 void launch_fc_bwd(const float *pooled, const float *dlogits, const float *w, float *dw, float *db,
                    __nv_bfloat16 *dact_flat, int n_img, int C, int K, int pix, cudaStream_t st) {
-  k_fc_bwd_w<<<K, 256, 0, st>>>(pooled, dlogits, dw, db, n_img, C, K);
-  k_fc_bwd_x<<<(n_img * C + 255) / 256, 256, 0, st>>>(dlogits, w, dact_flat, n_img, C, K, pix);
+  { k_fc_bwd_w<<<K, 256, 0, st>>>(pooled, dlogits, dw, db, n_img, C, K); ++::salun::g_launch_count; }
+  { k_fc_bwd_x<<<(n_img * C + 255) / 256, 256, 0, st>>>(dlogits, w, dact_flat, n_img, C, K, pix); ++::salun::g_launch_count; }
 }
 
 }  // namespace salun

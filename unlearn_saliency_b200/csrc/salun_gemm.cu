@@ -14,6 +14,8 @@
 // k_wgrad     : dW[co][kc] += sum_pixels dY[p][co] * X[p][kc]; the pixel dimension is the MMA K dimension, so both
 //               operands are MN-major tiles ([pixels][64 channels], the same TMA boxes as above); split-K over
 //               pixel ranges with fp32 red.global.add.
+#include <vector>
+
 #include "salun_gemm.cuh"
 #include "salun_sm100.cuh"
 
@@ -435,6 +437,29 @@ int conv_box(int H, int W, int pixels, TmapBox4 *box) {
   return SALUN_OK;
 }
 
+// optional per-launch timing of the two tensor-core kernels (bench.py roofline): CUDA events on the launch stream
+struct ProfRec {
+  cudaEvent_t a, b;
+  int cat;
+  double flops;
+};
+static bool g_prof = false;
+static std::vector<ProfRec> g_recs;
+static void prof_open(int cat, double flops, cudaStream_t st) {
+  if (!g_prof) return;
+  ProfRec r;
+  r.cat = cat;
+  r.flops = flops;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, st);
+  g_recs.push_back(r);
+}
+static void prof_close(cudaStream_t st) {
+  if (!g_prof) return;
+  cudaEventRecord(g_recs.back().b, st);
+}
+
 template <int BN, int S>
 static int launch_conv_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvGemmArgs &a, cudaStream_t st) {
   constexpr size_t smem = (size_t)S * (kBM * kBK * 2 + BN * kBK * 2) + 1024 + 256;
@@ -444,18 +469,22 @@ static int launch_conv_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, co
     attr_set = true;
   }
   dim3 grid((a.M + kBM - 1) / kBM, (a.N + BN - 1) / BN);
-  k_conv_gemm<BN, S><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, a);
+  { k_conv_gemm<BN, S><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, a); ++::salun::g_launch_count; }
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;
 }
 
 int launch_conv_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvGemmArgs &a, int bn, cudaStream_t st) {
+  prof_open(0, 2.0 * a.M * a.N * (double)a.num_k_blocks * 64.0, st);
+  int rc;
   switch (bn) {
-    case 64: return launch_conv_gemm_t<64, 4>(tmA, tmB, a, st);
-    case 128: return launch_conv_gemm_t<128, 3>(tmA, tmB, a, st);
-    case 256: return launch_conv_gemm_t<256, 4>(tmA, tmB, a, st);
-    default: set_error("launch_conv_gemm: unsupported BN=%d", bn); return SALUN_ERR_INVALID;
+    case 64: rc = launch_conv_gemm_t<64, 4>(tmA, tmB, a, st); break;
+    case 128: rc = launch_conv_gemm_t<128, 3>(tmA, tmB, a, st); break;
+    case 256: rc = launch_conv_gemm_t<256, 4>(tmA, tmB, a, st); break;
+    default: set_error("launch_conv_gemm: unsupported BN=%d", bn); rc = SALUN_ERR_INVALID;
   }
+  prof_close(st);
+  return rc;
 }
 
 int wgrad_pick_blocks(int total_blocks) {
@@ -474,7 +503,9 @@ int launch_wgrad(const CUtensorMap &tmA, const CUtensorMap &tmB, const WgradArgs
     attr_set = true;
   }
   dim3 grid(co_tiles, col_groups, splits);
-  k_wgrad<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, a);
+  prof_open(1, 2.0 * (double)a.kb_total * 64.0 * a.Cout * (double)a.kvalid, st);
+  { k_wgrad<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, a); ++::salun::g_launch_count; }
+  prof_close(st);
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;
 }
@@ -487,6 +518,35 @@ int launch_wgrad(const CUtensorMap &tmA, const CUtensorMap &tmB, const WgradArgs
 using namespace salun;
 
 extern "C" {
+
+// per-launch CUDA-event timing of the tensor-core kernels: category 0 = k_conv_gemm (forward + dgrad),
+// 1 = k_wgrad.  begin() arms it, end() synchronises the device and returns summed milliseconds, launch counts and
+// algorithmic FLOPs per category.
+int salun_profile_begin(void) {
+  g_recs.clear();
+  g_prof = true;
+  return SALUN_OK;
+}
+int salun_profile_end(double *ms_by_cat, int64_t *launches_by_cat, double *flops_by_cat) {
+  g_prof = false;
+  SALUN_CUDA_OK(cudaDeviceSynchronize());
+  for (int c = 0; c < 2; ++c) {
+    if (ms_by_cat) ms_by_cat[c] = 0.0;
+    if (launches_by_cat) launches_by_cat[c] = 0;
+    if (flops_by_cat) flops_by_cat[c] = 0.0;
+  }
+  for (ProfRec &r : g_recs) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    if (ms_by_cat) ms_by_cat[r.cat] += ms;
+    if (launches_by_cat) launches_by_cat[r.cat] += 1;
+    if (flops_by_cat) flops_by_cat[r.cat] += r.flops;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_recs.clear();
+  return SALUN_OK;
+}
 
 // D[M][N] (fp32 and/or bf16) = A[M][K] . B[N][K]^T, bf16 row-major operands, K % 64 == 0, N % 64 == 0
 int salun_gemm_bf16_tn(salun_ctx *ctx, const void *A, const void *B, float *out_f32, void *out_bf16, int64_t M,

@@ -14,6 +14,7 @@
 
 namespace salun {
 
+long long g_launch_count = 0;
 static thread_local char g_err[512] = "";
 char *err_buf() { return g_err; }
 void set_error(const char *fmt, ...) {
@@ -475,6 +476,7 @@ using namespace salun;
 extern "C" {
 
 int salun_version(void) { return 1000; }
+long long salun_launch_count(void) { return ::salun::g_launch_count; }
 const char *salun_last_error(void) { return err_buf(); }
 
 int salun_ctx_create(int device, salun_ctx **out) {
@@ -527,7 +529,7 @@ int salun_saliency_accumulate_flat(salun_ctx *ctx, const float *grad, float *acc
   if (n == 0) return SALUN_OK;
   SALUN_REQUIRE(grad && accum, "NULL buffer");
   SALUN_REQUIRE(aligned16(grad) && aligned16(accum), "buffers must be 16-byte aligned");
-  k_accum_flat<<<grid_for(ctx, (n + 3) / 4), kThreads, 0, st>>>(grad, accum, n, scale_dev);
+  { k_accum_flat<<<grid_for(ctx, (n + 3) / 4), kThreads, 0, st>>>(grad, accum, n, scale_dev); ++::salun::g_launch_count; }
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;
 }
@@ -562,7 +564,7 @@ int salun_saliency_accumulate(salun_ctx *ctx, const float *const *grads_host, co
     if (gx > 128) gx = 128;
     if (gx < 1) gx = 1;
     dim3 grid((unsigned)gx, (unsigned)cnt);
-    k_accum_multi<<<grid, kThreads, 0, st>>>(tab, accum_flat, scale_dev);
+    { k_accum_multi<<<grid, kThreads, 0, st>>>(tab, accum_flat, scale_dev); ++::salun::g_launch_count; }
     SALUN_CUDA_OK(cudaGetLastError());
   }
   return SALUN_OK;
@@ -573,7 +575,7 @@ int salun_abs_inplace(salun_ctx *ctx, float *a, int64_t n, void *stream) {
   SALUN_REQUIRE(n >= 0, "n < 0");
   if (n == 0) return SALUN_OK;
   SALUN_REQUIRE(a && aligned16(a), "buffer must be non-NULL and 16-byte aligned");
-  k_abs<<<grid_for(ctx, (n + 3) / 4), kThreads, 0, st>>>(a, n);
+  { k_abs<<<grid_for(ctx, (n + 3) / 4), kThreads, 0, st>>>(a, n); ++::salun::g_launch_count; }
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;
 }
@@ -604,20 +606,20 @@ int salun_topk_mask(salun_ctx *ctx, const float *accum, int64_t n, int64_t k, in
   }
   const int all_ones = k >= n;
   if (!all_ones) {
-    k_sel_init<<<(kRadixBins + 255) / 256, 256, 0, st>>>(ctx->sel, ctx->hist, (long long)k);
+    { k_sel_init<<<(kRadixBins + 255) / 256, 256, 0, st>>>(ctx->sel, ctx->hist, (long long)k); ++::salun::g_launch_count; }
     for (int pass = 0; pass < 3; ++pass) {
-      k_radix_hist<<<grid, kThreads, 0, st>>>(accum, n, ctx->sel, ctx->hist, pass);
-      k_radix_pick<<<1, 32, 0, st>>>(ctx->hist, ctx->sel, pass, (long long)k);
+      { k_radix_hist<<<grid, kThreads, 0, st>>>(accum, n, ctx->sel, ctx->hist, pass); ++::salun::g_launch_count; }
+      { k_radix_pick<<<1, 32, 0, st>>>(ctx->hist, ctx->sel, pass, (long long)k); ++::salun::g_launch_count; }
     }
-    k_tie_count<<<wgrid, kThreads, 0, st>>>(accum, n, chunk, ctx->sel, ctx->block_ties);
-    k_tie_scan<<<1, 32, 0, st>>>(ctx->block_ties, wgrid, ctx->sel);
+    { k_tie_count<<<wgrid, kThreads, 0, st>>>(accum, n, chunk, ctx->sel, ctx->block_ties); ++::salun::g_launch_count; }
+    { k_tie_scan<<<1, 32, 0, st>>>(ctx->block_ties, wgrid, ctx->sel); ++::salun::g_launch_count; }
   }
   if (vec64)
-    k_write_mask<true><<<wgrid, kThreads, 0, st>>>(accum, n, chunk, ctx->sel, ctx->block_ties,
-                                                   (long long *)mask_i64, mask_bits, all_ones);
+    { k_write_mask<true><<<wgrid, kThreads, 0, st>>>(accum, n, chunk, ctx->sel, ctx->block_ties,
+                                                   (long long *)mask_i64, mask_bits, all_ones); ++::salun::g_launch_count; }
   else
-    k_write_mask<false><<<wgrid, kThreads, 0, st>>>(accum, n, chunk, ctx->sel, ctx->block_ties,
-                                                    (long long *)mask_i64, mask_bits, all_ones);
+    { k_write_mask<false><<<wgrid, kThreads, 0, st>>>(accum, n, chunk, ctx->sel, ctx->block_ties,
+                                                    (long long *)mask_i64, mask_bits, all_ones); ++::salun::g_launch_count; }
   SALUN_CUDA_OK(cudaGetLastError());
   if (info_host) {
     if (all_ones) {
@@ -645,7 +647,7 @@ int salun_pack_mask(salun_ctx *ctx, const int64_t *mask_i64, int64_t n, uint32_t
   SALUN_REQUIRE(n >= 0, "n < 0");
   if (n == 0) return SALUN_OK;
   SALUN_REQUIRE(mask_i64 && mask_bits, "NULL buffer");
-  k_pack_mask<<<grid_for(ctx, n), kThreads, 0, st>>>((const long long *)mask_i64, n, mask_bits);
+  { k_pack_mask<<<grid_for(ctx, n), kThreads, 0, st>>>((const long long *)mask_i64, n, mask_bits); ++::salun::g_launch_count; }
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;
 }
@@ -655,7 +657,7 @@ int salun_unpack_mask(salun_ctx *ctx, const uint32_t *mask_bits, int64_t n, int6
   SALUN_REQUIRE(n >= 0, "n < 0");
   if (n == 0) return SALUN_OK;
   SALUN_REQUIRE(mask_i64 && mask_bits, "NULL buffer");
-  k_unpack_mask<<<grid_for(ctx, n), kThreads, 0, st>>>(mask_bits, n, (long long *)mask_i64);
+  { k_unpack_mask<<<grid_for(ctx, n), kThreads, 0, st>>>(mask_bits, n, (long long *)mask_i64); ++::salun::g_launch_count; }
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;
 }
@@ -665,7 +667,7 @@ int salun_apply_mask(salun_ctx *ctx, float *g, const uint32_t *mask_bits, int64_
   SALUN_REQUIRE(n >= 0, "n < 0");
   if (n == 0) return SALUN_OK;
   SALUN_REQUIRE(g && mask_bits && aligned16(g), "g must be non-NULL, 16-byte aligned; mask_bits non-NULL");
-  k_apply_mask<<<grid_for(ctx, (n + 3) / 4), kThreads, 0, st>>>(g, mask_bits, n);
+  { k_apply_mask<<<grid_for(ctx, (n + 3) / 4), kThreads, 0, st>>>(g, mask_bits, n); ++::salun::g_launch_count; }
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;
 }
@@ -677,7 +679,7 @@ int salun_masked_sgd_step(salun_ctx *ctx, float *p, const float *g, float *v, co
   if (n == 0) return SALUN_OK;
   SALUN_REQUIRE(p && g && v, "NULL buffer");
   SALUN_REQUIRE(aligned16(p) && aligned16(g) && aligned16(v), "p, g, v must be 16-byte aligned");
-  k_masked_sgd<<<grid_for(ctx, (n + 3) / 4), kThreads, 0, st>>>(p, g, v, mask_bits, n, lr, momentum, wd);
+  { k_masked_sgd<<<grid_for(ctx, (n + 3) / 4), kThreads, 0, st>>>(p, g, v, mask_bits, n, lr, momentum, wd); ++::salun::g_launch_count; }
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;
 }
@@ -691,8 +693,8 @@ int salun_grad_sumsq(salun_ctx *ctx, const float *g, int64_t n, double *sumsq_de
   }
   SALUN_REQUIRE(g && aligned16(g), "g must be non-NULL and 16-byte aligned");
   const int grid = grid_for(ctx, (n + 3) / 4);
-  k_sumsq_partial<<<grid, kThreads, 0, st>>>(g, n, ctx->partials);
-  k_sumsq_final<<<1, 256, 0, st>>>(ctx->partials, grid, sumsq_dev);
+  { k_sumsq_partial<<<grid, kThreads, 0, st>>>(g, n, ctx->partials); ++::salun::g_launch_count; }
+  { k_sumsq_final<<<1, 256, 0, st>>>(ctx->partials, grid, sumsq_dev); ++::salun::g_launch_count; }
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;
 }
@@ -700,7 +702,7 @@ int salun_grad_sumsq(salun_ctx *ctx, const float *g, int64_t n, double *sumsq_de
 int salun_clip_coef(salun_ctx *ctx, const double *sumsq_dev, float max_norm, float *coef_dev, void *stream) {
   SALUN_ENTER(ctx);
   SALUN_REQUIRE(sumsq_dev && coef_dev, "NULL buffer");
-  k_clip_coef<<<1, 1, 0, st>>>(sumsq_dev, max_norm, coef_dev);
+  { k_clip_coef<<<1, 1, 0, st>>>(sumsq_dev, max_norm, coef_dev); ++::salun::g_launch_count; }
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;
 }
@@ -723,7 +725,7 @@ int salun_masked_adam_step(salun_ctx *ctx, float *p, const float *g, float *m1, 
   k.one_m_b2 = (float)(1.0 - (double)beta2);
   k.eps = eps;
   k.wd = wd;
-  k_masked_adam<<<grid_for(ctx, (n + 3) / 4), kThreads, 0, st>>>(p, g, m1, m2, mask_bits, n, k, coef_dev);
+  { k_masked_adam<<<grid_for(ctx, (n + 3) / 4), kThreads, 0, st>>>(p, g, m1, m2, mask_bits, n, k, coef_dev); ++::salun::g_launch_count; }
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;
 }
