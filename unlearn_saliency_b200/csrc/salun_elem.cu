@@ -11,6 +11,7 @@
 namespace salun {
 
 constexpr int kET = 256;
+constexpr int kRedY = 32;  // row lanes of the (32 x kRedY)-thread column-reduction blocks
 
 __device__ __forceinline__ void ld8(const __nv_bfloat16 *p, float (&f)[8]) {
   uint4 v = *reinterpret_cast<const uint4 *>(p);
@@ -41,21 +42,33 @@ __device__ __forceinline__ size_t pad_off(int m, int H, int W, int C) {
 // ------------------------------------------------------------------------------------------------
 __global__ void k_bn_stats_reduce(const float *__restrict__ ssum, const float *__restrict__ ssq, int rows, int C,
                                   double *__restrict__ slices) {
-  __shared__ double sh[2][8][32];
+  __shared__ double sh[2][kRedY][32];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int s = blockIdx.y;
   const int lo = (int)((long long)rows * s / kStatSlices), hi = (int)((long long)rows * (s + 1) / kStatSlices);
   double a = 0.0, b = 0.0;
-  if (c < C)
-    for (int r = lo + threadIdx.y; r < hi; r += 8) {
+  if (c < C) {
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;  // <= 4 fp32 adds per accumulator before widening
+    int r = lo + threadIdx.y;
+    for (; r + kRedY < hi; r += 2 * kRedY) {
+      a0 += ssum[(size_t)r * C + c];
+      b0 += ssq[(size_t)r * C + c];
+      a1 += ssum[(size_t)(r + kRedY) * C + c];
+      b1 += ssq[(size_t)(r + kRedY) * C + c];
+      a += (double)a0 + (double)a1;
+      b += (double)b0 + (double)b1;
+      a0 = a1 = b0 = b1 = 0.f;
+    }
+    if (r < hi) {
       a += (double)ssum[(size_t)r * C + c];
       b += (double)ssq[(size_t)r * C + c];
     }
+  }
   sh[0][threadIdx.y][threadIdx.x] = a;
   sh[1][threadIdx.y][threadIdx.x] = b;
   __syncthreads();
   if (threadIdx.y == 0 && c < C) {
-    for (int j = 1; j < 8; ++j) {
+    for (int j = 1; j < kRedY; ++j) {
       a += sh[0][j][threadIdx.x];
       b += sh[1][j][threadIdx.x];
     }
@@ -65,7 +78,7 @@ __global__ void k_bn_stats_reduce(const float *__restrict__ ssum, const float *_
 }
 void launch_bn_stats_reduce(const float *stat_sum, const float *stat_sq, int rows, int C, double *slices,
                             cudaStream_t st) {
-  dim3 grid((C + 31) / 32, kStatSlices), block(32, 8);
+  dim3 grid((C + 31) / 32, kStatSlices), block(32, kRedY);
   { k_bn_stats_reduce<<<grid, block, 0, st>>>(stat_sum, stat_sq, rows, C, slices); ++::salun::g_launch_count; }
 }
 
@@ -220,19 +233,27 @@ void launch_bn_bwd_reduce(const __nv_bfloat16 *dout, const __nv_bfloat16 *out_pa
 __global__ void k_bn_bwd_finalize(const float *__restrict__ partials, int rows, int C, const float *__restrict__ gamma,
                                   const float *__restrict__ invstd, float count, int train, float *__restrict__ dgamma,
                                   float *__restrict__ dbeta, float *__restrict__ coef) {
-  __shared__ double sh[2][8][32];
+  __shared__ double sh[2][kRedY][32];
   const int c = blockIdx.x * 32 + threadIdx.x;
   double a = 0.0, b = 0.0;
-  if (c < C)
-    for (int r = threadIdx.y; r < rows; r += 8) {
+  if (c < C) {
+    int r = threadIdx.y;
+    for (; r + kRedY < rows; r += 2 * kRedY) {
+      const float a0 = partials[((size_t)r * 2 + 0) * C + c], b0 = partials[((size_t)r * 2 + 1) * C + c];
+      const float a1 = partials[((size_t)(r + kRedY) * 2 + 0) * C + c], b1 = partials[((size_t)(r + kRedY) * 2 + 1) * C + c];
+      a += (double)a0 + (double)a1;
+      b += (double)b0 + (double)b1;
+    }
+    if (r < rows) {
       a += (double)partials[((size_t)r * 2 + 0) * C + c];
       b += (double)partials[((size_t)r * 2 + 1) * C + c];
     }
+  }
   sh[0][threadIdx.y][threadIdx.x] = a;
   sh[1][threadIdx.y][threadIdx.x] = b;
   __syncthreads();
   if (threadIdx.y == 0 && c < C) {
-    for (int j = 1; j < 8; ++j) {
+    for (int j = 1; j < kRedY; ++j) {
       a += sh[0][j][threadIdx.x];
       b += sh[1][j][threadIdx.x];
     }
@@ -246,7 +267,7 @@ __global__ void k_bn_bwd_finalize(const float *__restrict__ partials, int rows, 
 void launch_bn_bwd_finalize(const float *partials, int C, const float *gamma, const float *saved_invstd, float count,
                             int train, float *dgamma, float *dbeta, float *coef, cudaStream_t st) {
   const int M = (int)count;
-  dim3 grid((C + 31) / 32), block(32, 8);
+  dim3 grid((C + 31) / 32), block(32, kRedY);
   { k_bn_bwd_finalize<<<grid, block, 0, st>>>(partials, bwd_rows(M, C), C, gamma, saved_invstd, count, train, dgamma,
                                             dbeta, coef); ++::salun::g_launch_count; }
 }
@@ -438,6 +459,37 @@ __global__ void k_prep_w_transpose(const float *__restrict__ w, __nv_bfloat16 *_
     out[i] = __float2bfloat16(w[(size_t)co * kc + j]);
   }
 }
+// all convolutions of the network in ONE launch: blockIdx.y walks the table
+__global__ void k_prep_w_all(const WPrepEntry *__restrict__ tab, const float *__restrict__ params, int need_dgrad) {
+  const WPrepEntry e = tab[blockIdx.y];
+  const float *__restrict__ w = params + e.w_off;
+  const long long nthreads = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long tf = (long long)e.cout * e.kcp;
+  for (long long i = t0; i < tf; i += nthreads) {
+    const int co = (int)(i / e.kcp), j = (int)(i - (long long)co * e.kcp);
+    e.w_fwd[i] = __float2bfloat16(j < e.kc ? w[(size_t)co * e.kc + j] : 0.f);
+  }
+  if (!need_dgrad || e.dgrad_mode == 0) return;
+  const long long td = (long long)e.cout * e.kc;
+  if (e.dgrad_mode == 1) {  // stride-1: [ci][flipped tap][co]
+    const int taps = e.kc / e.cin;
+    for (long long i = t0; i < td; i += nthreads) {
+      const int co = (int)(i % e.cout);
+      long long r = i / e.cout;
+      const int tfp = (int)(r % taps), ci = (int)(r / taps);
+      e.w_dgrad[i] = __float2bfloat16(w[((size_t)co * taps + (taps - 1 - tfp)) * e.cin + ci]);
+    }
+  } else {  // stride-2: plain transpose [kc][co]
+    for (long long i = t0; i < td; i += nthreads) {
+      const int co = (int)(i % e.cout), j = (int)(i / e.cout);
+      e.w_dgrad[i] = __float2bfloat16(w[(size_t)co * e.kc + j]);
+    }
+  }
+}
+void launch_prep_w_all(const WPrepEntry *table_dev, int n_convs, const float *params, int need_dgrad, cudaStream_t st) {
+  { k_prep_w_all<<<dim3(64, n_convs), 256, 0, st>>>(table_dev, params, need_dgrad); ++::salun::g_launch_count; }
+}
+
 static inline int flat_grid(long long total) {
   long long g = (total + 255) / 256;
   if (g > 148 * 8) g = 148 * 8;
@@ -528,16 +580,30 @@ void launch_loss_sum(const float *loss_per_sample, int n_img, float sign, float 
 
 __global__ void k_fc_bwd_w(const float *__restrict__ pooled, const float *__restrict__ dl, float *__restrict__ dw,
                            float *__restrict__ db, int n_img, int C, int K) {
-  const int k = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f;
-    for (int b = 0; b < n_img; ++b) s += dl[(size_t)b * K + k] * pooled[(size_t)b * C + c];
+  // grid (K, C/64), block (64 channels, 8 batch lanes): fixed summation order -> deterministic
+  __shared__ float sh[8][64];
+  const int k = blockIdx.x, c = blockIdx.y * 64 + threadIdx.x;
+  float s = 0.f, sb = 0.f;
+  for (int b = threadIdx.y; b < n_img; b += 8) {
+    const float d = dl[(size_t)b * K + k];
+    if (c < C) s += d * pooled[(size_t)b * C + c];
+    sb += d;
+  }
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int j = 1; j < 8; ++j) s += sh[j][threadIdx.x];
     dw[(size_t)k * C + c] = s;
   }
-  if (threadIdx.x == 0) {
-    float s = 0.f;
-    for (int b = 0; b < n_img; ++b) s += dl[(size_t)b * K + k];
-    db[k] = s;
+  __syncthreads();
+  if (blockIdx.y == 0 && threadIdx.x == 0) {
+    sh[threadIdx.y][0] = sb;
+  }
+  __syncthreads();
+  if (blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) {
+    float t = 0.f;
+    for (int j = 0; j < 8; ++j) t += sh[j][0];
+    db[k] = t;
   }
 }
 __global__ void k_fc_bwd_x(const float *__restrict__ dl, const float *__restrict__ w, __nv_bfloat16 *__restrict__ dact,
@@ -552,7 +618,7 @@ __global__ void k_fc_bwd_x(const float *__restrict__ dl, const float *__restrict
 }
 void launch_fc_bwd(const float *pooled, const float *dlogits, const float *w, float *dw, float *db,
                    __nv_bfloat16 *dact_flat, int n_img, int C, int K, int pix, cudaStream_t st) {
-  { k_fc_bwd_w<<<K, 256, 0, st>>>(pooled, dlogits, dw, db, n_img, C, K); ++::salun::g_launch_count; }
+  { k_fc_bwd_w<<<dim3(K, (C + 63) / 64), dim3(64, 8), 0, st>>>(pooled, dlogits, dw, db, n_img, C, K); ++::salun::g_launch_count; }
   { k_fc_bwd_x<<<(n_img * C + 255) / 256, 256, 0, st>>>(dlogits, w, dact_flat, n_img, C, K, pix); ++::salun::g_launch_count; }
 }
 

@@ -49,7 +49,16 @@ void launch_im2col_s2(const __nv_bfloat16 *in_padded, __nv_bfloat16 *col, int n_
 void launch_col2im_s2(const __nv_bfloat16 *dcol3, const __nv_bfloat16 *dcol1, __nv_bfloat16 *dx, int n_img, int Hin,
                       int Win, int C, cudaStream_t st);
 
-// weights: fp32 native [Cout][taps][Cin] -> bf16 operands
+// weights: fp32 native [Cout][taps][Cin] -> bf16 operands; one launch for the whole network
+struct WPrepEntry {
+  long long w_off;         // offset of the fp32 master weight in the parameter arena
+  __nv_bfloat16 *w_fwd;    // [cout][kcp]  (zero padded beyond kc)
+  __nv_bfloat16 *w_dgrad;  // dgrad operand or nullptr
+  int cout, cin, kc, kcp;
+  int dgrad_mode;          // 0: none, 1: stride-1 flipped [ci][tap'][co], 2: transposed [kc][co]
+};
+void launch_prep_w_all(const WPrepEntry *table_dev, int n_convs, const float *params, int need_dgrad, cudaStream_t st);
+
 void launch_prep_w_fwd(const float *w, __nv_bfloat16 *out, int Cout, int kc, int kc_padded, cudaStream_t st);
 void launch_prep_w_dgrad_s1(const float *w, __nv_bfloat16 *out, int Cout, int Cin, int taps, cudaStream_t st);
 void launch_prep_w_transpose(const float *w, __nv_bfloat16 *out, int Cout, int kc, cudaStream_t st);

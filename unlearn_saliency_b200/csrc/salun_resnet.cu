@@ -66,6 +66,7 @@ struct salun_resnet {
   int64_t fc_w_off, fc_b_off;
   int feat;  // channels of the last stage
   float *pooled, *logits, *dlogits, *loss_ps;
+  WPrepEntry *wprep_table;
   std::vector<void *> allocs;
   std::map<int, std::vector<ConvMaps>> plans;
   int last_n, last_train;
@@ -280,16 +281,7 @@ static void bn_backward(salun_resnet *net, const ConvL &L, const bf16 *dout, con
 }
 
 static int prep_weights(salun_resnet *net, bool need_dgrad, cudaStream_t st) {
-  for (const ConvL &L : net->convs) {
-    const float *w = net->params + L.w_off;
-    launch_prep_w_fwd(w, L.w_fwd, L.cout, L.kc, L.kcp, st);
-    if (need_dgrad && !L.stem) {
-      if (L.dy_padded)
-        launch_prep_w_dgrad_s1(w, L.w_dgrad, L.cout, L.cin, L.ks * L.ks, st);
-      else
-        launch_prep_w_transpose(w, L.w_dgrad, L.cout, L.kc, st);
-    }
-  }
+  launch_prep_w_all(net->wprep_table, (int)net->convs.size(), net->params, need_dgrad ? 1 : 0, st);
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;
 }
@@ -513,6 +505,28 @@ int salun_resnet_create(salun_ctx *ctx, const salun_resnet_cfg *cfg, float *para
     A(dmalloc(net, &L.saved_invstd, (size_t)L.cout, true));
     A(dmalloc(net, &L.coef, (size_t)3 * L.cout, true));
     A(dmalloc(net, &L.bwd_partials, (size_t)kBwdPartialRows * 2 * L.cout, true));
+  }
+  {
+    std::vector<WPrepEntry> tab;
+    for (const ConvL &L : net->convs) {
+      WPrepEntry e{};
+      e.w_off = L.w_off;
+      e.w_fwd = L.w_fwd;
+      e.w_dgrad = L.stem ? nullptr : L.w_dgrad;
+      e.cout = L.cout;
+      e.cin = L.cin;
+      e.kc = L.kc;
+      e.kcp = L.kcp;
+      e.dgrad_mode = L.stem ? 0 : (L.dy_padded ? 1 : 2);
+      tab.push_back(e);
+    }
+    A(dmalloc(net, &net->wprep_table, tab.size(), false));
+    cudaError_t ce = cudaMemcpy(net->wprep_table, tab.data(), tab.size() * sizeof(WPrepEntry), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) {
+      set_error("cudaMemcpy(wprep_table) failed: %s", cudaGetErrorString(ce));
+      salun_resnet_destroy(net);
+      return SALUN_ERR_CUDA;
+    }
   }
   A(dmalloc(net, &net->pooled, (size_t)nb * net->feat, true));
   A(dmalloc(net, &net->logits, (size_t)nb * cfg->num_classes, true));
