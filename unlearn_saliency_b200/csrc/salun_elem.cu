@@ -459,8 +459,14 @@ __global__ void k_prep_w_transpose(const float *__restrict__ w, __nv_bfloat16 *_
     out[i] = __float2bfloat16(w[(size_t)co * kc + j]);
   }
 }
-// all convolutions of the network in ONE launch: blockIdx.y walks the table
-__global__ void k_prep_w_all(const WPrepEntry *__restrict__ tab, const float *__restrict__ params, int need_dgrad) {
+// all convolutions of the network in ONE launch: blockIdx.y walks the table.
+//   forward operand : plain cast (+ zero padding of the stem's 27 -> 64 columns), coalesced both ways
+//   dgrad operand   : out[ci][taps-1-t][co] = w[co][t][ci]  (stride-1: flipped taps)   or   out[j][co] = w[co][j]
+//                     (stride-2: taps == 1, "ci" walks all kc columns) -- a batched matrix transpose, done through
+//                     32x33 shared-memory tiles so that both the fp32 reads and the bf16 writes are coalesced.
+__global__ void __launch_bounds__(256) k_prep_w_all(const WPrepEntry *__restrict__ tab, const float *__restrict__ params,
+                                                    int need_dgrad) {
+  __shared__ float tile[32][33];
   const WPrepEntry e = tab[blockIdx.y];
   const float *__restrict__ w = params + e.w_off;
   const long long nthreads = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -470,24 +476,32 @@ __global__ void k_prep_w_all(const WPrepEntry *__restrict__ tab, const float *__
     e.w_fwd[i] = __float2bfloat16(j < e.kc ? w[(size_t)co * e.kc + j] : 0.f);
   }
   if (!need_dgrad || e.dgrad_mode == 0) return;
-  const long long td = (long long)e.cout * e.kc;
-  if (e.dgrad_mode == 1) {  // stride-1: [ci][flipped tap][co]
-    const int taps = e.kc / e.cin;
-    for (long long i = t0; i < td; i += nthreads) {
-      const int co = (int)(i % e.cout);
-      long long r = i / e.cout;
-      const int tfp = (int)(r % taps), ci = (int)(r / taps);
-      e.w_dgrad[i] = __float2bfloat16(w[((size_t)co * taps + (taps - 1 - tfp)) * e.cin + ci]);
+  const int taps = e.dgrad_mode == 1 ? e.kc / e.cin : 1;
+  const int cin = e.dgrad_mode == 1 ? e.cin : e.kc;
+  const int tiles_ci = (cin + 31) / 32, tiles_co = (e.cout + 31) / 32;
+  const int ntiles = taps * tiles_ci * tiles_co;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int tIdx = blockIdx.x; tIdx < ntiles; tIdx += gridDim.x) {
+    const int t = tIdx / (tiles_ci * tiles_co);
+    const int r = tIdx - t * tiles_ci * tiles_co;
+    const int ci0 = (r % tiles_ci) * 32, co0 = (r / tiles_ci) * 32;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // read w[co][t][ci]: ci contiguous
+      const int co = co0 + ty + 8 * j, ci = ci0 + tx;
+      tile[ty + 8 * j][tx] = (co < e.cout && ci < cin) ? w[((size_t)co * taps + t) * cin + ci] : 0.f;
     }
-  } else {  // stride-2: plain transpose [kc][co]
-    for (long long i = t0; i < td; i += nthreads) {
-      const int co = (int)(i % e.cout), j = (int)(i / e.cout);
-      e.w_dgrad[i] = __float2bfloat16(w[(size_t)co * e.kc + j]);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // write out[ci][taps-1-t][co]: co contiguous
+      const int ci = ci0 + ty + 8 * j, co = co0 + tx;
+      if (ci < cin && co < e.cout)
+        e.w_dgrad[((size_t)ci * taps + (taps - 1 - t)) * e.cout + co] = __float2bfloat16(tile[tx][ty + 8 * j]);
     }
+    __syncthreads();
   }
 }
 void launch_prep_w_all(const WPrepEntry *table_dev, int n_convs, const float *params, int need_dgrad, cudaStream_t st) {
-  { k_prep_w_all<<<dim3(64, n_convs), 256, 0, st>>>(table_dev, params, need_dgrad); ++::salun::g_launch_count; }
+  { k_prep_w_all<<<dim3(96, n_convs), 256, 0, st>>>(table_dev, params, need_dgrad); ++::salun::g_launch_count; }
 }
 
 static inline int flat_grid(long long total) {

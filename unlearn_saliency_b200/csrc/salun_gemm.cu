@@ -221,6 +221,179 @@ k_conv_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 // =================================================================================================
+// k_conv_rw: persistent stride-1 3x3 convolution with the weight slice RESIDENT in shared memory.
+//
+// The large-image layers (layer1: 64 ch @32x32, layer2: 128 ch @16x16) are bound by L2->smem operand traffic in
+// k_conv_gemm (every one of the 9 taps re-fetches a 16 KB activation tile and an 8-16 KB weight tile).  Here
+//   * one CTA per SM keeps its [64 out-ch][9*Cin] weight slice in smem for its whole life (72 / 144 KB),
+//   * an activation box of (rows+2) image rows is fetched once per (kx, 64-channel slab) and serves the three
+//     ky taps: tap ky starts ky*W*128 bytes into the box, a multiple of the 1024-byte swizzle atom, so the UMMA
+//     descriptor simply moves its start address,
+//   * two TMEM accumulators let the epilogue of tile i overlap the MMAs of tile i+1.
+// Operand traffic per 128x64 output tile drops from 9*(16+8) = 216 KB to 3*24 = 72 KB (Cin = 64).
+// =================================================================================================
+template <int kW, int kCinBlocks>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+k_conv_rw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvRwArgs a) {
+  constexpr int kRows = 128 / kW;                         // image rows per 128-pixel tile
+  constexpr uint32_t kABytes = (kRows + 2) * kW * 128;    // activation box incl. the two halo rows
+  constexpr int kStages = kCinBlocks == 1 ? 4 : 3;
+  constexpr uint32_t kSlab = 64 * 128;                    // one [64 out-ch][64 in-ch] weight slab
+  constexpr uint32_t kWBytes = 9 * kCinBlocks * kSlab;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t w_base = smem_u32(smem);
+  const uint32_t a_base = w_base + kWBytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kWBytes + kStages * kABytes);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 5);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kStages, wfull = empty0 + 8 * kStages;
+  const uint32_t tfull0 = wfull + 8, tempty0 = tfull0 + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.y;
+  constexpr int kSteps = 3 * kCinBlocks;  // (kx, channel slab) load steps per tile
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(wfull, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull0 + 8 * i, 1);
+      mbar_init(tempty0 + 8 * i, 4);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 128);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // resident weights: 9*cin_blocks slabs, slab (tap, cb) = columns [(tap*cin_blocks + cb)*64, +64) of rows n_tile*64..
+      mbar_arrive_expect_tx(wfull, kWBytes);
+      for (int j = 0; j < 9 * kCinBlocks; ++j) tma_load_2d(w_base + j * kSlab, &tmB, wfull, j * 64, n_tile * 64);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        const int pix0 = tile * 128;
+        const int n0 = pix0 / (a.H * a.W), y0 = (pix0 % (a.H * a.W)) / a.W;
+        for (int st = 0; st < kSteps; ++st, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          const int kx = st / kCinBlocks, cb = st - kx * kCinBlocks;
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          mbar_arrive_expect_tx(full0 + 8 * s, kABytes);
+          tma_load_4d(a_base + s * kABytes, &tmA, full0 + 8 * s, cb * 64, kx, y0, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+      mbar_wait(wfull, 0);
+      uint32_t it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++ti) {
+        const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
+        mbar_wait(tempty0 + 8 * acc, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 64;
+        for (int st = 0; st < kSteps; ++st, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          const int kx = st / kCinBlocks, cb = st - kx * kCinBlocks;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sa = a_base + s * kABytes;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const uint32_t sb = w_base + ((ky * 3 + kx) * kCinBlocks + cb) * kSlab;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = umma_desc_sw128(sa + ky * (kW * 128) + k * 32, 16, 1024);
+              const uint64_t bd = umma_desc_sw128(sb + k * 32, 16, 1024);
+              tc_mma_f16(d_tmem, ad, bd, idesc, (st | ky | k) != 0);
+            }
+          }
+          tc_commit(empty0 + 8 * s);
+        }
+        tc_commit(tfull0 + 8 * acc);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
+      mbar_wait(tfull0 + 8 * acc, aph);
+      tc_fence_after();
+      const int row = tile * 128 + q * 32 + lane;
+      const bool row_ok = row < a.M;
+      const int stat_row = tile * 4 + q;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 64 + c * 32, r);
+        tc_wait_ld();
+        const int col0 = n_tile * 64 + c * 32;
+        if (a.stat_sum) {  // BatchNorm batch statistics from the unrounded fp32 accumulators
+          float v[32], w[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = row_ok ? __uint_as_float(r[j]) : 0.f;
+            v[j] = x;
+            w[j] = x * x;
+          }
+          float s1 = warp_transpose_reduce(v, lane);
+          float s2 = warp_transpose_reduce(w, lane);
+          a.stat_sum[(size_t)stat_row * a.N + col0 + lane] = s1;
+          a.stat_sq[(size_t)stat_row * a.N + col0 + lane] = s2;
+        }
+        if (row_ok) {
+          if (a.addend) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.addend + (size_t)row * a.ld_out + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 v = src[j];
+              const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 t = __bfloat1622float2(h[i]);
+                r[8 * j + 2 * i] = __float_as_uint(__uint_as_float(r[8 * j + 2 * i]) + t.x);
+                r[8 * j + 2 * i + 1] = __float_as_uint(__uint_as_float(r[8 * j + 2 * i + 1]) + t.y);
+              }
+            }
+          }
+          uint4 *dst = reinterpret_cast<uint4 *>(a.out_bf16 + (size_t)row * a.ld_out + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]));
+            v.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+            v.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+            v.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+            dst[j] = v;
+          }
+        }
+        __syncwarp();
+      }
+      // this warp has drained its quarter of the accumulator: hand it back to the MMA issuer
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 128);
+}
+
+// =================================================================================================
 // wgrad: MN-major operands (pixel dimension is K)
 // =================================================================================================
 constexpr int kWgStages = 4;
@@ -485,6 +658,42 @@ int launch_conv_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvG
   }
   prof_close(st);
   return rc;
+}
+
+template <int kW, int kCB>
+static int launch_conv_rw_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvRwArgs &a, int num_sms,
+                            cudaStream_t st) {
+  constexpr int kRows = 128 / kW;
+  constexpr int kStages = kCB == 1 ? 4 : 3;
+  constexpr size_t smem = (size_t)9 * kCB * 8192 + (size_t)kStages * (kRows + 2) * kW * 128 + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SALUN_CUDA_OK(cudaFuncSetAttribute(k_conv_rw<kW, kCB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int n_tiles = a.N / 64;
+  int gx = num_sms / n_tiles;
+  if (gx > a.num_tiles) gx = a.num_tiles;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, n_tiles);
+  prof_open(0, 2.0 * a.M * a.N * 9.0 * kCB * 64.0, st);
+  { k_conv_rw<kW, kCB><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, a); ++::salun::g_launch_count; }
+  prof_close(st);
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+
+bool conv_rw_supported(int W, int cin, int cout) {
+  return (W == 32 || W == 16) && (cin == 64 || cin == 128) && cout % 64 == 0;
+}
+
+int launch_conv_rw(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvRwArgs &a, int num_sms, cudaStream_t st) {
+  if (a.W == 32 && a.cin_blocks == 1) return launch_conv_rw_t<32, 1>(tmA, tmB, a, num_sms, st);
+  if (a.W == 32 && a.cin_blocks == 2) return launch_conv_rw_t<32, 2>(tmA, tmB, a, num_sms, st);
+  if (a.W == 16 && a.cin_blocks == 1) return launch_conv_rw_t<16, 1>(tmA, tmB, a, num_sms, st);
+  if (a.W == 16 && a.cin_blocks == 2) return launch_conv_rw_t<16, 2>(tmA, tmB, a, num_sms, st);
+  set_error("launch_conv_rw: unsupported W=%d cin_blocks=%d", a.W, a.cin_blocks);
+  return SALUN_ERR_UNSUPPORTED;
 }
 
 int wgrad_pick_blocks(int total_blocks) {

@@ -43,6 +43,18 @@ struct WgradArgs {
   int swap_lbo_sbo;   // debug knob for descriptor bring-up (0 in production)
 };
 
+// persistent stride-1 3x3 convolution with smem-resident weights (k_conv_rw): layer1 / layer2 shapes
+struct ConvRwArgs {
+  int H, W;             // image size (stride 1: in == out)
+  int cin_blocks;       // Cin / 64
+  int num_tiles;        // ceil(M / 128)
+  int M, N;             // valid rows / columns (N = Cout)
+  __nv_bfloat16 *out_bf16;
+  int ld_out;
+  float *stat_sum, *stat_sq;
+  const __nv_bfloat16 *addend;
+};
+
 struct TmapBox4 {
   int c, w, h, n;
 };
@@ -59,5 +71,8 @@ int launch_conv_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvG
 int launch_wgrad(const CUtensorMap &tmA, const CUtensorMap &tmB, const WgradArgs &a, int co_tiles, int col_groups,
                  int splits, cudaStream_t st);
 int wgrad_pick_blocks(int total_blocks);
+bool conv_rw_supported(int W, int cin, int cout);
+// tmA: 4-D map of the padded activation with box {64, W, 128/W + 2, 1}; tmB: 2-D weight map with box {64, 64}
+int launch_conv_rw(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvRwArgs &a, int num_sms, cudaStream_t st);
 
 }  // namespace salun

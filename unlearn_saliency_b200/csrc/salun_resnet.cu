@@ -14,6 +14,8 @@
 //   raw conv outputs       : bf16 [n*H*W][C]; BatchNorm batch statistics come out of the GEMM epilogue (fp32
 //                            accumulators) as per-tile partials and are reduced in double.
 // Every kernel launch below is enqueued on the caller's stream; nothing synchronises.
+#include <stdlib.h>
+
 #include <map>
 #include <vector>
 
@@ -47,7 +49,9 @@ struct Block {
   int in_act, mid_act, out_act;
 };
 struct ConvMaps {
-  CUtensorMap fwdA, fwdB, dgA, dgB, wgA, wgB, dgA1;
+  CUtensorMap fwdA, fwdB, dgA, dgB, wgA, wgB;
+  CUtensorMap rwA, rwB, rwdA, rwdB;  // k_conv_rw (resident weights) forward / dgrad maps
+  bool rw_fwd, rw_dgrad;
 };
 
 }  // namespace salun
@@ -67,6 +71,7 @@ struct salun_resnet {
   int feat;  // channels of the last stage
   float *pooled, *logits, *dlogits, *loss_ps;
   WPrepEntry *wprep_table;
+  bool use_conv_rw;  // SALUN_CONV_RW=0 falls back to k_conv_gemm everywhere (A/B measurements)
   std::vector<void *> allocs;
   std::map<int, std::vector<ConvMaps>> plans;
   int last_n, last_train;
@@ -170,6 +175,7 @@ static int build_plan(salun_resnet *net, int n, std::vector<ConvMaps> **out) {
   for (size_t i = 0; i < net->convs.size(); ++i) {
     const ConvL &L = net->convs[i];
     ConvMaps &m = maps[i];
+    m.rw_fwd = m.rw_dgrad = false;
     const int64_t Mout = (int64_t)n * L.hout * L.hout;
     const int bn = L.cout % 128 == 0 ? 128 : 64;
     TRY(make_tmap_2d_bf16(&m.fwdB, L.w_fwd, L.cout, L.kcp, bn, 64));
@@ -185,6 +191,17 @@ static int build_plan(salun_resnet *net, int n, std::vector<ConvMaps> **out) {
       TRY(make_tmap_2d_bf16(&m.dgB, L.w_dgrad, L.cin, (uint64_t)L.ks * L.ks * L.cout, bnd, 64));
       TRY(make_tmap_4d_bf16(&m.wgA, L.dy, L.cout, L.hout + 2, L.hout + 2, n, bx64));
       TRY(make_tmap_4d_bf16(&m.wgB, in.p, L.cin, L.hin + 2, L.hin + 2, n, bx64));
+      m.rw_fwd = net->use_conv_rw && L.ks == 3 && conv_rw_supported(L.hin, L.cin, L.cout);
+      m.rw_dgrad = net->use_conv_rw && L.ks == 3 && conv_rw_supported(L.hout, L.cout, L.cin);
+      TmapBox4 bxr{64, L.hin, 128 / L.hin + 2, 1};
+      if (m.rw_fwd) {
+        TRY(make_tmap_4d_bf16(&m.rwA, in.p, L.cin, L.hin + 2, L.hin + 2, n, bxr));
+        TRY(make_tmap_2d_bf16(&m.rwB, L.w_fwd, L.cout, L.kcp, 64, 64));
+      }
+      if (m.rw_dgrad) {
+        TRY(make_tmap_4d_bf16(&m.rwdA, L.dy, L.cout, L.hout + 2, L.hout + 2, n, bxr));
+        TRY(make_tmap_2d_bf16(&m.rwdB, L.w_dgrad, L.cin, (uint64_t)9 * L.cout, 64, 64));
+      }
     } else {
       // stem / stride-2: explicit patch matrix col[Mout][kcp]
       TRY(make_tmap_2d_bf16(&m.fwdA, L.col, Mout, L.kcp, 128, 64));
@@ -215,6 +232,21 @@ static int conv_forward(salun_resnet *net, const ConvL &L, const ConvMaps &m, in
     a.stat_sq = L.stat_sq;
   }
   const int bn = L.cout % 128 == 0 ? 128 : 64;
+  if (m.rw_fwd) {
+    ConvRwArgs r{};
+    r.H = r.W = L.hout;
+    r.cin_blocks = L.cin / 64;
+    r.num_tiles = (M + 127) / 128;
+    r.M = M;
+    r.N = L.cout;
+    r.out_bf16 = L.y;
+    r.ld_out = L.cout;
+    r.stat_sum = a.stat_sum;
+    r.stat_sq = a.stat_sq;
+    TRY(launch_conv_rw(m.rwA, m.rwB, r, net->ctx->num_sms, st));
+    if (train) launch_bn_stats_reduce(L.stat_sum, L.stat_sq, (M + 127) / 128 * 4, L.cout, L.slices, st);
+    return SALUN_OK;
+  }
   if (L.dy_padded) {
     a.mode_a = 1;
     a.cin_blocks = L.cin / 64;
@@ -354,7 +386,18 @@ static int backward_impl(salun_resnet *net, cudaStream_t st) {
     bn_backward(net, L2, out.dout, out.p, identity ? out.dz : nullptr, n, train, st);
     if (!identity) bn_backward(net, net->convs[B.cd], out.dout, out.p, nullptr, n, train, st);
     // conv2: dgrad -> d(mid), wgrad
-    {
+    if ((*plan)[B.c2].rw_dgrad) {
+      ConvRwArgs r{};
+      r.H = r.W = L2.hout;
+      r.cin_blocks = L2.cout / 64;
+      r.M = n * L2.hout * L2.hout;
+      r.num_tiles = (r.M + 127) / 128;
+      r.N = L2.cin;
+      r.out_bf16 = mid.dout;
+      r.ld_out = L2.cin;
+      TRY(launch_conv_rw((*plan)[B.c2].rwdA, (*plan)[B.c2].rwdB, r, net->ctx->num_sms, st));
+      TRY(wgrad_conv(net, L2, (*plan)[B.c2], n, st));
+    } else {
       ConvGemmArgs a{};
       a.mode_a = 1;
       a.cin_blocks = L2.cout / 64;
@@ -370,7 +413,22 @@ static int backward_impl(salun_resnet *net, cudaStream_t st) {
     }
     // mid = relu(bn1(y1))
     bn_backward(net, L1, mid.dout, mid.p, nullptr, n, train, st);
-    if (L1.dy_padded) {
+    if (L1.dy_padded && (*plan)[B.c1].rw_dgrad) {
+      ConvRwArgs r{};
+      r.H = r.W = L1.hout;
+      r.cin_blocks = L1.cout / 64;
+      r.M = n * L1.hout * L1.hout;
+      r.num_tiles = (r.M + 127) / 128;
+      r.N = L1.cin;
+      r.out_bf16 = in.dout;
+      r.ld_out = L1.cin;
+      r.addend = identity ? out.dz : nullptr;
+      TRY(launch_conv_rw((*plan)[B.c1].rwdA, (*plan)[B.c1].rwdB, r, net->ctx->num_sms, st));
+      if (!identity) {
+        set_error("salun_resnet: stride-1 block with projection shortcut is not supported");
+        return SALUN_ERR_UNSUPPORTED;
+      }
+    } else if (L1.dy_padded) {
       ConvGemmArgs a{};
       a.mode_a = 1;
       a.cin_blocks = L1.cout / 64;
@@ -464,6 +522,10 @@ int salun_resnet_create(salun_ctx *ctx, const salun_resnet_cfg *cfg, float *para
   net->rmean = running_mean;
   net->rvar = running_var;
   net->fwd_done = false;
+  {
+    const char *e = getenv("SALUN_CONV_RW");
+    net->use_conv_rw = !(e && e[0] == '0');
+  }
   int rc = build_arch(*cfg, &net->convs, &net->acts, &net->blocks, &net->n_params, &net->n_bn_channels, &net->fc_w_off,
                       &net->fc_b_off, &net->feat);
   if (rc) {
