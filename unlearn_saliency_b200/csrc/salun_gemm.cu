@@ -14,6 +14,8 @@
 // k_wgrad     : dW[co][kc] += sum_pixels dY[p][co] * X[p][kc]; the pixel dimension is the MMA K dimension, so both
 //               operands are MN-major tiles ([pixels][64 channels], the same TMA boxes as above); split-K over
 //               pixel ranges with fp32 red.global.add.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "salun_gemm.cuh"
@@ -221,6 +223,184 @@ k_conv_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 // =================================================================================================
+// k_conv_gemm_p: PERSISTENT variant of k_conv_gemm.  One CTA per SM walks output tiles (n fastest, so that CTAs
+// running concurrently share the A tile in L2); two TMEM accumulators let the epilogue of tile i run under the MMAs of
+// tile i+1; barriers / TMEM / descriptors are set up once per CTA instead of once per tile (the short-K GEMMs of the
+// stem and of the stride-2 dgrad spent most of their time in that setup).
+// =================================================================================================
+template <int BN, int kStages>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvGemmArgs a,
+              int m_tiles, int n_tiles) {
+  constexpr uint32_t kABytes = kBM * kBK * 2;
+  constexpr uint32_t kBBytes = BN * kBK * 2;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kStages;
+  const uint32_t tfull0 = empty0 + 8 * kStages, tempty0 = tfull0 + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = m_tiles * n_tiles;
+  constexpr uint32_t kTmemCols = 2 * BN;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull0 + 8 * i, 1);
+      mbar_init(tempty0 + 8 * i, 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
+        int n0 = 0, y0 = 0;
+        if (a.mode_a == 1) {
+          const int pix0 = m_tile * kBM;
+          n0 = pix0 / (a.H * a.W);
+          y0 = (pix0 % (a.H * a.W)) / a.W;
+        }
+        for (int kb = 0; kb < a.num_k_blocks; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          const uint32_t sa = smem_base + s * kStageBytes, sb = sa + kABytes;
+          mbar_arrive_expect_tx(full0 + 8 * s, kStageBytes);
+          if (a.mode_a == 1) {
+            const int tap = kb / a.cin_blocks, cb = kb - tap * a.cin_blocks;
+            const int ky = tap / a.kw, kx = tap - ky * a.kw;
+            tma_load_4d(sa, &tmA, full0 + 8 * s, cb * kBK, a.tap_x0 + kx, a.tap_y0 + y0 + ky, n0);
+          } else {
+            tma_load_2d(sa, &tmA, full0 + 8 * s, kb * kBK, m_tile * kBM);
+          }
+          tma_load_2d(sb, &tmB, full0 + 8 * s, kb * kBK, n_tile * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
+      uint32_t it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+        const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
+        mbar_wait(tempty0 + 8 * acc, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < a.num_k_blocks; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * kStageBytes, sb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t ad = umma_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t bd = umma_desc_sw128(sb + k * 32, 16, 1024);
+            tc_mma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+          }
+          tc_commit(empty0 + 8 * s);
+        }
+        tc_commit(tfull0 + 8 * acc);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
+      const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
+      mbar_wait(tfull0 + 8 * acc, aph);
+      tc_fence_after();
+      const int row = m_tile * kBM + q * 32 + lane;
+      const bool row_ok = row < a.M;
+      const int stat_row = (m_tile * 4 + q);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, r);
+        tc_wait_ld();
+        const int col0 = n_tile * BN + c * 32;
+        if (col0 < a.N) {
+          if (a.stat_sum) {
+            float v[32], w[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = row_ok ? __uint_as_float(r[j]) : 0.f;
+              v[j] = x;
+              w[j] = x * x;
+            }
+            float s1 = warp_transpose_reduce(v, lane);
+            float s2 = warp_transpose_reduce(w, lane);
+            if (col0 + lane < a.N) {
+              a.stat_sum[(size_t)stat_row * a.N + col0 + lane] = s1;
+              a.stat_sq[(size_t)stat_row * a.N + col0 + lane] = s2;
+            }
+          }
+          if (row_ok && a.addend) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.addend + (size_t)row * a.ld_out + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 v = src[j];
+              const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 t = __bfloat1622float2(h[i]);
+                r[8 * j + 2 * i] = __float_as_uint(__uint_as_float(r[8 * j + 2 * i]) + t.x);
+                r[8 * j + 2 * i + 1] = __float_as_uint(__uint_as_float(r[8 * j + 2 * i + 1]) + t.y);
+              }
+            }
+          }
+          if (row_ok) {
+            if (a.out_bf16) {
+              uint4 *dst = reinterpret_cast<uint4 *>(a.out_bf16 + (size_t)row * a.ld_out + col0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 v;
+                v.x = pack_bf16x2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]));
+                v.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+                v.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+                v.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+                dst[j] = v;
+              }
+            }
+            if (a.out_f32) {
+              uint4 *dst = reinterpret_cast<uint4 *>(a.out_f32 + (size_t)row * a.ld_out + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dst[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// =================================================================================================
 // k_conv_rw: persistent stride-1 3x3 convolution with the weight slice RESIDENT in shared memory.
 //
 // The large-image layers (layer1: 64 ch @32x32, layer2: 128 ch @16x16) are bound by L2->smem operand traffic in
@@ -237,7 +417,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 k_conv_rw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvRwArgs a) {
   constexpr int kRows = 128 / kW;                         // image rows per 128-pixel tile
   constexpr uint32_t kABytes = (kRows + 2) * kW * 128;    // activation box incl. the two halo rows
-  constexpr int kStages = kCinBlocks == 1 ? 4 : 3;
+  constexpr int kStages = kCinBlocks == 1 ? 6 : 3;
   constexpr uint32_t kSlab = 64 * 128;                    // one [64 out-ch][64 in-ch] weight slab
   constexpr uint32_t kWBytes = 9 * kCinBlocks * kSlab;
   extern __shared__ uint8_t smem_raw[];
@@ -647,9 +827,48 @@ static int launch_conv_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, co
   return SALUN_OK;
 }
 
+template <int BN, int S>
+static int launch_conv_gemm_p_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvGemmArgs &a, cudaStream_t st) {
+  constexpr size_t smem = (size_t)S * (kBM * kBK * 2 + BN * kBK * 2) + 1024 + 256;
+  static bool attr_set = false;
+  static int num_sms = 0;
+  if (!attr_set) {
+    SALUN_CUDA_OK(cudaFuncSetAttribute(k_conv_gemm_p<BN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0;
+    SALUN_CUDA_OK(cudaGetDevice(&dev));
+    SALUN_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    attr_set = true;
+  }
+  const int m_tiles = (a.M + kBM - 1) / kBM, n_tiles = (a.N + BN - 1) / BN;
+  int grid = m_tiles * n_tiles;
+  if (grid > num_sms) grid = num_sms;
+  { k_conv_gemm_p<BN, S><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, a, m_tiles, n_tiles); ++::salun::g_launch_count; }
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+
+static bool gemm_persistent() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SALUN_GEMM_PERSIST");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int launch_conv_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvGemmArgs &a, int bn, cudaStream_t st) {
   prof_open(0, 2.0 * a.M * a.N * (double)a.num_k_blocks * 64.0, st);
   int rc;
+  if (gemm_persistent()) {
+    switch (bn) {
+      case 64: rc = launch_conv_gemm_p_t<64, 8>(tmA, tmB, a, st); break;
+      case 128: rc = launch_conv_gemm_p_t<128, 6>(tmA, tmB, a, st); break;
+      case 256: rc = launch_conv_gemm_p_t<256, 4>(tmA, tmB, a, st); break;
+      default: set_error("launch_conv_gemm: unsupported BN=%d", bn); rc = SALUN_ERR_INVALID;
+    }
+    prof_close(st);
+    return rc;
+  }
   switch (bn) {
     case 64: rc = launch_conv_gemm_t<64, 4>(tmA, tmB, a, st); break;
     case 128: rc = launch_conv_gemm_t<128, 3>(tmA, tmB, a, st); break;
@@ -664,7 +883,7 @@ template <int kW, int kCB>
 static int launch_conv_rw_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvRwArgs &a, int num_sms,
                             cudaStream_t st) {
   constexpr int kRows = 128 / kW;
-  constexpr int kStages = kCB == 1 ? 4 : 3;
+  constexpr int kStages = kCB == 1 ? 6 : 3;
   constexpr size_t smem = (size_t)9 * kCB * 8192 + (size_t)kStages * (kRows + 2) * kW * 128 + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {

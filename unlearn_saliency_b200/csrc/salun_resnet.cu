@@ -71,7 +71,7 @@ struct salun_resnet {
   int feat;  // channels of the last stage
   float *pooled, *logits, *dlogits, *loss_ps;
   WPrepEntry *wprep_table;
-  bool use_conv_rw;  // SALUN_CONV_RW=0 falls back to k_conv_gemm everywhere (A/B measurements)
+  int use_conv_rw;  // SALUN_CONV_RW: 0 = k_conv_gemm everywhere, 1 = k_conv_rw where supported, 2 = only 32x32 layers
   std::vector<void *> allocs;
   std::map<int, std::vector<ConvMaps>> plans;
   int last_n, last_train;
@@ -191,8 +191,8 @@ static int build_plan(salun_resnet *net, int n, std::vector<ConvMaps> **out) {
       TRY(make_tmap_2d_bf16(&m.dgB, L.w_dgrad, L.cin, (uint64_t)L.ks * L.ks * L.cout, bnd, 64));
       TRY(make_tmap_4d_bf16(&m.wgA, L.dy, L.cout, L.hout + 2, L.hout + 2, n, bx64));
       TRY(make_tmap_4d_bf16(&m.wgB, in.p, L.cin, L.hin + 2, L.hin + 2, n, bx64));
-      m.rw_fwd = net->use_conv_rw && L.ks == 3 && conv_rw_supported(L.hin, L.cin, L.cout);
-      m.rw_dgrad = net->use_conv_rw && L.ks == 3 && conv_rw_supported(L.hout, L.cout, L.cin);
+      m.rw_fwd = net->use_conv_rw && (net->use_conv_rw == 1 || L.hin == 32) && L.ks == 3 && conv_rw_supported(L.hin, L.cin, L.cout);
+      m.rw_dgrad = net->use_conv_rw && (net->use_conv_rw == 1 || L.hout == 32) && L.ks == 3 && conv_rw_supported(L.hout, L.cout, L.cin);
       TmapBox4 bxr{64, L.hin, 128 / L.hin + 2, 1};
       if (m.rw_fwd) {
         TRY(make_tmap_4d_bf16(&m.rwA, in.p, L.cin, L.hin + 2, L.hin + 2, n, bxr));
@@ -524,7 +524,7 @@ int salun_resnet_create(salun_ctx *ctx, const salun_resnet_cfg *cfg, float *para
   net->fwd_done = false;
   {
     const char *e = getenv("SALUN_CONV_RW");
-    net->use_conv_rw = !(e && e[0] == '0');
+    net->use_conv_rw = e ? atoi(e) : 1;
   }
   int rc = build_arch(*cfg, &net->convs, &net->acts, &net->blocks, &net->n_params, &net->n_bn_channels, &net->fc_w_off,
                       &net->fc_b_off, &net->feat);
