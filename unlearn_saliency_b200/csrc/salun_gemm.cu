@@ -684,9 +684,20 @@ k_wgrad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
         tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, r);
         tc_wait_ld();
         const int col0 = (grp * a.n_blocks) * 64 + c * 32;
-        float *dst = a.dw + (size_t)co * a.ldw + col0;
+        float *dst = a.dw + (size_t)split * a.split_stride + (size_t)co * a.ldw + col0;
         if (!row_ok) {
           // junk rows of a half-empty co tile: nothing to store
+        } else if (a.split_stride > 0) {
+          // workspace mode: plain stores of this split's partial tile
+          if (col0 + 32 <= a.kvalid && (a.ldw & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              reinterpret_cast<uint4 *>(dst)[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < a.kvalid) dst[j] = __uint_as_float(r[j]);
+          }
         } else if (col0 + 32 <= a.kvalid && (a.ldw & 3) == 0) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -913,6 +924,29 @@ int launch_conv_rw(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvRwA
   if (a.W == 16 && a.cin_blocks == 2) return launch_conv_rw_t<16, 2>(tmA, tmB, a, num_sms, st);
   set_error("launch_conv_rw: unsupported W=%d cin_blocks=%d", a.W, a.cin_blocks);
   return SALUN_ERR_UNSUPPORTED;
+}
+
+__global__ void __launch_bounds__(256) k_wgrad_reduce(const WgReduceEntry *__restrict__ tab, float *__restrict__ grads) {
+  const WgReduceEntry e = tab[blockIdx.y];
+  float *__restrict__ dst = grads + e.dst_off;
+  const long long n4 = e.count >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 acc = reinterpret_cast<const float4 *>(e.ws)[i];
+    for (int s = 1; s < e.splits; ++s) {
+      const float4 v = reinterpret_cast<const float4 *>(e.ws + (size_t)s * e.count)[i];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4 *>(dst)[i] = acc;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (e.count & 3)) {  // tail (the 64x27 stem weight is not a multiple of 4... it is; kept general)
+    const long long i = (n4 << 2) + threadIdx.x;
+    float acc = 0.f;
+    for (int s = 0; s < e.splits; ++s) acc += e.ws[(size_t)s * e.count + i];
+    dst[i] = acc;
+  }
+}
+void launch_wgrad_reduce(const WgReduceEntry *table_dev, int n_entries, float *grads, cudaStream_t st) {
+  { k_wgrad_reduce<<<dim3(64, n_entries), 256, 0, st>>>(table_dev, grads); ++::salun::g_launch_count; }
 }
 
 int wgrad_pick_blocks(int total_blocks) {

@@ -40,6 +40,9 @@ struct WgradArgs {
   int ldw;            // row stride of dW in floats
   int kvalid;         // valid columns of dW (<= total_blocks * 64)
   float *dw;
+  long long split_stride;  // 0: every split red.add's into dw (caller zeroes dw).  > 0: split s STORES its partial
+                           // tile into dw + s*split_stride (a workspace slab of [Cout][ldw]); a deterministic
+                           // reduction over the slabs follows (launch_wgrad_reduce) -- no atomics, no zero-fill
   int swap_lbo_sbo;   // debug knob for descriptor bring-up (0 in production)
 };
 
@@ -71,6 +74,14 @@ int launch_conv_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvG
 int launch_wgrad(const CUtensorMap &tmA, const CUtensorMap &tmB, const WgradArgs &a, int co_tiles, int col_groups,
                  int splits, cudaStream_t st);
 int wgrad_pick_blocks(int total_blocks);
+// dst[off + i] = sum_s ws[s*count + i], one table entry per convolution, ONE launch for the whole network
+struct WgReduceEntry {
+  const float *ws;
+  long long dst_off;
+  long long count;
+  int splits;
+};
+void launch_wgrad_reduce(const WgReduceEntry *table_dev, int n_entries, float *grads, cudaStream_t st);
 bool conv_rw_supported(int W, int cin, int cout);
 // tmA: 4-D map of the padded activation with box {64, W, 128/W + 2, 1}; tmB: 2-D weight map with box {64, 64}
 int launch_conv_rw(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvRwArgs &a, int num_sms, cudaStream_t st);

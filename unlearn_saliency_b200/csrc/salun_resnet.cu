@@ -35,6 +35,8 @@ struct ConvL {
   int in_act;            // index of the padded input activation (-1: network input)
   bf16 *w_fwd, *w_dgrad, *col, *y, *dy, *dcol;
   float *stat_sum, *stat_sq, *saved_mean, *saved_invstd, *coef, *bwd_partials;
+  float *wg_ws;          // split-K workspace of the weight gradient: [wg_splits_max][cout][kc]
+  int wg_splits_max;
   double *slices;
   bool dy_padded;
 };
@@ -71,6 +73,9 @@ struct salun_resnet {
   int feat;  // channels of the last stage
   float *pooled, *logits, *dlogits, *loss_ps;
   WPrepEntry *wprep_table;
+  WgReduceEntry *wgred_table;          // device copy, refreshed per backward (split counts depend on the batch size)
+  WgReduceEntry *wgred_host;           // pinned staging
+  std::vector<int> wg_splits_host;
   int use_conv_rw;  // SALUN_CONV_RW: 0 = k_conv_gemm everywhere, 1 = k_conv_rw where supported, 2 = only 32x32 layers
   std::vector<void *> allocs;
   std::map<int, std::vector<ConvMaps>> plans;
@@ -291,13 +296,17 @@ static int wgrad_conv(salun_resnet *net, const ConvL &L, const ConvMaps &m, int 
   a.Cout = L.cout;
   a.ldw = L.kc;
   a.kvalid = L.kc;
-  a.dw = net->grads + L.w_off;
   const int co_tiles = (L.cout + 127) / 128, groups = a.total_blocks / a.n_blocks;
-  int splits = (2 * net->ctx->num_sms + co_tiles * groups - 1) / (co_tiles * groups);
+  // one wave: as many pixel splits as fit on the SMs next to the (co tile, tap group) decomposition
+  int splits = net->ctx->num_sms / (co_tiles * groups);
   if (splits < 1) splits = 1;
+  if (splits > L.wg_splits_max) splits = L.wg_splits_max;
   if (splits > a.kb_total) splits = a.kb_total;
   a.kb_per_split = (a.kb_total + splits - 1) / splits;
   splits = (a.kb_total + a.kb_per_split - 1) / a.kb_per_split;
+  a.dw = L.wg_ws;                                   // split s stores its partial into slab s ...
+  a.split_stride = (long long)L.cout * L.kc;
+  net->wg_splits_host[&L - net->convs.data()] = splits;  // ... and launch_wgrad_reduce sums the slabs into the grad arena
   return launch_wgrad(m.wgA, m.wgB, a, co_tiles, groups, splits, st);
 }
 
@@ -373,7 +382,7 @@ static int backward_impl(salun_resnet *net, cudaStream_t st) {
   const int n = net->last_n, train = net->last_train;
   std::vector<ConvMaps> *plan;
   TRY(build_plan(net, n, &plan));
-  SALUN_CUDA_OK(cudaMemsetAsync(net->grads, 0, (size_t)net->n_params * sizeof(float), st));
+  // every gradient element has exactly one writer (BN finalize, FC backward, wgrad reduce): no zero-fill needed
   const Act &last = net->acts[net->blocks.back().out_act];
   launch_fc_bwd(net->pooled, net->dlogits, net->params + net->fc_w_off, net->grads + net->fc_w_off,
                 net->grads + net->fc_b_off, last.dout, n, net->feat, net->cfg.num_classes, last.H * last.H, st);
@@ -476,6 +485,18 @@ static int backward_impl(salun_resnet *net, cudaStream_t st) {
     bn_backward(net, L, net->acts[0].dout, net->acts[0].p, nullptr, n, train, st);
     TRY(wgrad_conv(net, L, (*plan)[0], n, st));
   }
+  // deterministic split-K reduction of every conv weight gradient into the flat gradient arena (one launch)
+  for (size_t i = 0; i < net->convs.size(); ++i) {
+    const ConvL &L = net->convs[i];
+    WgReduceEntry &e = net->wgred_host[i];
+    e.ws = L.wg_ws;
+    e.dst_off = L.w_off;
+    e.count = (long long)L.cout * L.kc;
+    e.splits = net->wg_splits_host[i];
+  }
+  SALUN_CUDA_OK(cudaMemcpyAsync(net->wgred_table, net->wgred_host, net->convs.size() * sizeof(WgReduceEntry),
+                                cudaMemcpyHostToDevice, st));
+  launch_wgrad_reduce(net->wgred_table, (int)net->convs.size(), net->grads, st);
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;
 }
@@ -522,6 +543,7 @@ int salun_resnet_create(salun_ctx *ctx, const salun_resnet_cfg *cfg, float *para
   net->rmean = running_mean;
   net->rvar = running_var;
   net->fwd_done = false;
+  net->wgred_host = nullptr;
   {
     const char *e = getenv("SALUN_CONV_RW");
     net->use_conv_rw = e ? atoi(e) : 1;
@@ -567,6 +589,20 @@ int salun_resnet_create(salun_ctx *ctx, const salun_resnet_cfg *cfg, float *para
     A(dmalloc(net, &L.saved_invstd, (size_t)L.cout, true));
     A(dmalloc(net, &L.coef, (size_t)3 * L.cout, true));
     A(dmalloc(net, &L.bwd_partials, (size_t)kBwdPartialRows * 2 * L.cout, true));
+    {
+      const int total_blocks = L.kcp / 64, nb_ = wgrad_pick_blocks(total_blocks);
+      const int tiles = ((L.cout + 127) / 128) * (total_blocks / nb_);
+      L.wg_splits_max = ctx->num_sms / tiles;
+      if (L.wg_splits_max < 1) L.wg_splits_max = 1;
+      A(dmalloc(net, &L.wg_ws, (size_t)L.wg_splits_max * L.cout * L.kc, false));
+    }
+  }
+  net->wg_splits_host.assign(net->convs.size(), 1);
+  A(dmalloc(net, &net->wgred_table, net->convs.size(), false));
+  if (cudaMallocHost(&net->wgred_host, net->convs.size() * sizeof(WgReduceEntry)) != cudaSuccess) {
+    set_error("cudaMallocHost(wgred_host) failed");
+    salun_resnet_destroy(net);
+    return SALUN_ERR_CUDA;
   }
   {
     std::vector<WPrepEntry> tab;
@@ -603,6 +639,7 @@ int salun_resnet_destroy(salun_resnet *net) {
   if (!net) return SALUN_OK;
   cudaSetDevice(net->ctx->device);
   for (void *p : net->allocs) cudaFree(p);
+  if (net->wgred_host) cudaFreeHost(net->wgred_host);
   delete net;
   return SALUN_OK;
 }
