@@ -47,6 +47,10 @@ long long salun_launch_count(void);
  * 1 = wgrad GEMM).  begin() arms it; end() synchronises the device and returns, per category, summed
  * milliseconds, launch count and algorithmic FLOPs.  Arrays of 2; any may be NULL. */
 int salun_profile_begin(void);
+/* bring-up aid: attach a device buffer of >= 8 * 1024 int64; every tensor-core launch then records per-CTA role
+ * timings (cycles) into it: [cta][0] producer wait-empty, [1] producer total, [2] MMA wait-full, [3] MMA wait-tmem-empty,
+ * [4] MMA total, [5] epilogue wait-tmem-full, [6] epilogue total.  NULL detaches. */
+int salun_debug_role_timing(long long *buf_dev);
 int salun_profile_end(double *ms_by_cat, int64_t *launches_by_cat, double *flops_by_cat);
 const char *salun_last_error(void);
 
@@ -165,6 +169,11 @@ int salun_gemm_bf16_tn(salun_ctx *ctx, const void *A, const void *B, float *out_
 int salun_conv_fwd_bf16(salun_ctx *ctx, const void *xpad, const void *wk, void *y_bf16, float *y_f32,
                         float *stat_sum, float *stat_sq, int batch, int H, int W, int Cin, int Cout,
                         int ksize, void *stream);
+
+/* salun_conv_fwd_bf16 for 3x3 convolutions on 32x32 / 16x16 images with Cin in {64,128}, through the persistent
+ * kernel that keeps its weight slice resident in shared memory (k_conv_rw). */
+int salun_conv_rw_fwd_bf16(salun_ctx *ctx, const void *xpad, const void *wk, void *y_bf16, float *stat_sum,
+                           float *stat_sq, int batch, int H, int W, int Cin, int Cout, void *stream);
 
 /* Stride-1 convolution weight gradient: dw[Cout][ksize*ksize*Cin] (fp32, tap-major) +=
  *   sum over pixels of dy[p][Cout]^T . x_tap[p][Cin].  dw must be zeroed by the caller (split-K

@@ -39,6 +39,7 @@ _SIGNATURES = {
     "salun_version": [],
     "salun_launch_count": [],
     "salun_profile_begin": [],
+    "salun_debug_role_timing": [_P],
     "salun_profile_end": [_P, _P, _P],
     "salun_last_error": [],
     "salun_ctx_create": [C.c_int, C.POINTER(_P)],
@@ -57,6 +58,7 @@ _SIGNATURES = {
     # tcgen05 GEMM / convolution entry points (salun_gemm.cu)
     "salun_gemm_bf16_tn": [_P, _P, _P, _P, _P, _I64, _I64, _I64, _P],
     "salun_conv_fwd_bf16": [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P],
+    "salun_conv_rw_fwd_bf16": [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P],
     "salun_conv_wgrad_bf16": [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P],
     # ResNet engine (salun_resnet.cu)
     "salun_resnet_param_count": [_P],

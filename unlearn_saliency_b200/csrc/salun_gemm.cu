@@ -268,67 +268,90 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  const bool dbg_on = a.dbg != nullptr;
+  const long long t_begin = dbg_on ? clock64() : 0;
   if (warp == 0) {
-    if (lane == 0) {
+    if (lane < 2) {
+      // lane 0 fetches the A tile, lane 1 the B tile (the issuing threads are instruction-latency bound: two lanes
+      // halve the per-stage issue time; no integer division inside the k loop)
+      long long w_empty = 0;
       uint32_t it = 0;
+      const int hw = a.H * a.W;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
         int n0 = 0, y0 = 0;
         if (a.mode_a == 1) {
           const int pix0 = m_tile * kBM;
-          n0 = pix0 / (a.H * a.W);
-          y0 = (pix0 % (a.H * a.W)) / a.W;
+          n0 = pix0 / hw;
+          y0 = (pix0 - n0 * hw) / a.W;
         }
+        int cb = 0, kx = 0, ky = 0;
         for (int kb = 0; kb < a.num_k_blocks; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
-          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          mbar_wait_t(empty0 + 8 * s, ph ^ 1, w_empty, dbg_on);
           const uint32_t sa = smem_base + s * kStageBytes, sb = sa + kABytes;
-          mbar_arrive_expect_tx(full0 + 8 * s, kStageBytes);
-          if (a.mode_a == 1) {
-            const int tap = kb / a.cin_blocks, cb = kb - tap * a.cin_blocks;
-            const int ky = tap / a.kw, kx = tap - ky * a.kw;
-            tma_load_4d(sa, &tmA, full0 + 8 * s, cb * kBK, a.tap_x0 + kx, a.tap_y0 + y0 + ky, n0);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(full0 + 8 * s, kStageBytes);
+            if (a.mode_a == 1)
+              tma_load_4d(sa, &tmA, full0 + 8 * s, cb * kBK, a.tap_x0 + kx, a.tap_y0 + y0 + ky, n0);
+            else
+              tma_load_2d(sa, &tmA, full0 + 8 * s, kb * kBK, m_tile * kBM);
           } else {
-            tma_load_2d(sa, &tmA, full0 + 8 * s, kb * kBK, m_tile * kBM);
+            tma_load_2d(sb, &tmB, full0 + 8 * s, kb * kBK, n_tile * BN);
           }
-          tma_load_2d(sb, &tmB, full0 + 8 * s, kb * kBK, n_tile * BN);
+          if (++cb == a.cin_blocks) {
+            cb = 0;
+            if (++kx == a.kw) {
+              kx = 0;
+              ++ky;
+            }
+          }
         }
+      }
+      if (dbg_on && lane == 0) {
+        a.dbg[blockIdx.x * 8 + 0] = w_empty;
+        a.dbg[blockIdx.x * 8 + 1] = clock64() - t_begin;
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
+      const uint32_t dhi = umma_desc_hi_sw128(1024), a_lo0 = umma_desc_lo(smem_base, 16);
+      long long w_full = 0, w_tempty = 0;
       uint32_t it = 0, ti = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
         const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
-        mbar_wait(tempty0 + 8 * acc, aph ^ 1);
+        mbar_wait_t(tempty0 + 8 * acc, aph ^ 1, w_tempty, dbg_on);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < a.num_k_blocks; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
-          mbar_wait(full0 + 8 * s, ph);
+          mbar_wait_t(full0 + 8 * s, ph, w_full, dbg_on);
           tc_fence_after();
-          const uint32_t sa = smem_base + s * kStageBytes, sb = sa + kABytes;
+          const uint32_t alo = a_lo0 + s * (kStageBytes >> 4), blo = alo + (kABytes >> 4);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            const uint64_t ad = umma_desc_sw128(sa + k * 32, 16, 1024);
-            const uint64_t bd = umma_desc_sw128(sb + k * 32, 16, 1024);
-            tc_mma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0);
-          }
+          for (int k = 0; k < kBK / 16; ++k)
+            tc_mma_f16(d_tmem, umma_desc_pack(alo + 2 * k, dhi), umma_desc_pack(blo + 2 * k, dhi), idesc, (kb | k) != 0);
           tc_commit(empty0 + 8 * s);
         }
         tc_commit(tfull0 + 8 * acc);
       }
+      if (dbg_on) {
+        a.dbg[blockIdx.x * 8 + 2] = w_full;
+        a.dbg[blockIdx.x * 8 + 3] = w_tempty;
+        a.dbg[blockIdx.x * 8 + 4] = clock64() - t_begin;
+      }
     }
   } else {
     const int q = warp & 3;
+    long long w_tfull = 0;
     uint32_t ti = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
       const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
-      mbar_wait(tfull0 + 8 * acc, aph);
+      mbar_wait_t(tfull0 + 8 * acc, aph, w_tfull, dbg_on);
       tc_fence_after();
       const int row = m_tile * kBM + q * 32 + lane;
       const bool row_ok = row < a.M;
@@ -394,6 +417,10 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       tc_fence_before();
       if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
     }
+    if (dbg_on && q == 0 && lane == 0) {
+      a.dbg[blockIdx.x * 8 + 5] = w_tfull;
+      a.dbg[blockIdx.x * 8 + 6] = clock64() - t_begin;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -455,8 +482,12 @@ k_conv_rw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  const bool dbg_on = a.dbg != nullptr;
+  const long long t_begin = dbg_on ? clock64() : 0;
+  const int cta = blockIdx.y * gridDim.x + blockIdx.x;
   if (warp == 0) {
     if (lane == 0) {
+      long long w_empty = 0;
       // resident weights: 9*cin_blocks slabs, slab (tap, cb) = columns [(tap*cin_blocks + cb)*64, +64) of rows n_tile*64..
       mbar_arrive_expect_tx(wfull, kWBytes);
       for (int j = 0; j < 9 * kCinBlocks; ++j) tma_load_2d(w_base + j * kSlab, &tmB, wfull, j * 64, n_tile * 64);
@@ -468,50 +499,61 @@ k_conv_rw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           const int kx = st / kCinBlocks, cb = st - kx * kCinBlocks;
-          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          mbar_wait_t(empty0 + 8 * s, ph ^ 1, w_empty, dbg_on);
           mbar_arrive_expect_tx(full0 + 8 * s, kABytes);
           tma_load_4d(a_base + s * kABytes, &tmA, full0 + 8 * s, cb * 64, kx, y0, n0);
         }
+      }
+      if (dbg_on) {
+        a.dbg[cta * 8 + 0] = w_empty;
+        a.dbg[cta * 8 + 1] = clock64() - t_begin;
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
-      mbar_wait(wfull, 0);
+      long long w_full = 0, w_tempty = 0;
+      const uint32_t dhi = umma_desc_hi_sw128(1024), a_lo0 = umma_desc_lo(a_base, 16), w_lo0 = umma_desc_lo(w_base, 16);
+      mbar_wait_t(wfull, 0, w_full, dbg_on);
       uint32_t it = 0, ti = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++ti) {
         const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
-        mbar_wait(tempty0 + 8 * acc, aph ^ 1);
+        mbar_wait_t(tempty0 + 8 * acc, aph ^ 1, w_tempty, dbg_on);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 64;
         for (int st = 0; st < kSteps; ++st, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           const int kx = st / kCinBlocks, cb = st - kx * kCinBlocks;
-          mbar_wait(full0 + 8 * s, ph);
+          mbar_wait_t(full0 + 8 * s, ph, w_full, dbg_on);
           tc_fence_after();
-          const uint32_t sa = a_base + s * kABytes;
+          const uint32_t alo = a_lo0 + s * (kABytes >> 4);
+          const uint32_t blo = w_lo0 + (kx * kCinBlocks + cb) * (kSlab >> 4);
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky) {
-            const uint32_t sb = w_base + ((ky * 3 + kx) * kCinBlocks + cb) * kSlab;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t ad = umma_desc_sw128(sa + ky * (kW * 128) + k * 32, 16, 1024);
-              const uint64_t bd = umma_desc_sw128(sb + k * 32, 16, 1024);
-              tc_mma_f16(d_tmem, ad, bd, idesc, (st | ky | k) != 0);
-            }
+            for (int k = 0; k < 4; ++k)
+              tc_mma_f16(d_tmem, umma_desc_pack(alo + ky * ((kW * 128) >> 4) + 2 * k, dhi),
+                         umma_desc_pack(blo + ky * (3 * kCinBlocks * (kSlab >> 4)) + 2 * k, dhi), idesc,
+                         (st | ky | k) != 0);
           }
           tc_commit(empty0 + 8 * s);
         }
         tc_commit(tfull0 + 8 * acc);
       }
+      if (dbg_on) {
+        a.dbg[cta * 8 + 2] = w_full;
+        a.dbg[cta * 8 + 3] = w_tempty;
+        a.dbg[cta * 8 + 4] = clock64() - t_begin;
+      }
     }
   } else {
     const int q = warp & 3;
+    long long w_tfull = 0;
     uint32_t ti = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++ti) {
       const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
-      mbar_wait(tfull0 + 8 * acc, aph);
+      mbar_wait_t(tfull0 + 8 * acc, aph, w_tfull, dbg_on);
       tc_fence_after();
       const int row = tile * 128 + q * 32 + lane;
       const bool row_ok = row < a.M;
@@ -567,6 +609,10 @@ k_conv_rw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       tc_fence_before();
       if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
     }
+    if (dbg_on && q == 0 && lane == 0) {
+      a.dbg[cta * 8 + 5] = w_tfull;
+      a.dbg[cta * 8 + 6] = clock64() - t_begin;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -616,38 +662,54 @@ k_wgrad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  const bool dbg_on = a.dbg != nullptr;
+  const long long t_begin = dbg_on ? clock64() : 0;
+  const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
   if (nkb > 0) {
     if (warp == 0) {
-      if (lane == 0) {
+      const int nbox = a_blocks + a.n_blocks;
+      if (lane < nbox) {
+        // one lane per TMA box (2 dY slabs + up to 4 X slabs): address math and issue run SIMT-parallel
+        long long w_empty = 0;
+        const bool is_a = lane < a_blocks;
+        const int j = is_a ? lane : lane - a_blocks;
+        const uint32_t dst_off = is_a ? j * kWgBlockBytes : (2 + j) * kWgBlockBytes;
+        const int hw = a.H * a.W;
+        int c0, dx = 1, dy = 1;   // channel offset and padded-coordinate shift of this lane's box
+        if (is_a) {
+          c0 = co_tile * 128 + j * 64;
+        } else {
+          const int b = grp * a.n_blocks + j;
+          if (a.mode_b == 1) {
+            const int tap = b / a.cin_blocks, cb = b - tap * a.cin_blocks;
+            const int ky = tap / a.kw, kx = tap - ky * a.kw;
+            c0 = cb * 64;
+            dx = a.tap_x0 + kx;
+            dy = a.tap_y0 + ky;
+          } else {
+            c0 = b * 64;
+          }
+        }
+        const bool four_d = is_a ? (a.mode_a == 1) : (a.mode_b == 1);
+        const CUtensorMap *tm = is_a ? &tmA : &tmB;
         for (int i = 0; i < nkb; ++i) {
-          const int kb = kb_begin + i;
           const int s = i % kWgStages;
           const uint32_t ph = (i / kWgStages) & 1;
-          mbar_wait(empty0 + 8 * s, ph ^ 1);
-          const uint32_t sa = smem_base + s * stage_bytes, sb = sa + 2 * kWgBlockBytes;
-          mbar_arrive_expect_tx(full0 + 8 * s, (a_blocks + a.n_blocks) * kWgBlockBytes);
-          const int pix0 = kb * kWgPix;
-          int n0 = 0, y0 = 0;
-          if (a.mode_b == 1 || a.mode_a == 1) {
-            n0 = pix0 / (a.H * a.W);
-            y0 = (pix0 % (a.H * a.W)) / a.W;
+          mbar_wait_t(empty0 + 8 * s, ph ^ 1, w_empty, dbg_on);
+          const uint32_t dst = smem_base + s * stage_bytes + dst_off;
+          if (lane == 0) mbar_arrive_expect_tx(full0 + 8 * s, nbox * kWgBlockBytes);
+          const int pix0 = (kb_begin + i) * kWgPix;
+          if (four_d) {
+            const int n0 = pix0 / hw;   // hw is a power of two on every supported shape: compiles to a shift-free
+            const int y0 = (pix0 - n0 * hw) / a.W;  // udiv, but only two per k-block per lane, in parallel lanes
+            tma_load_4d(dst, tm, full0 + 8 * s, c0, dx, dy + y0, n0);
+          } else {
+            tma_load_2d(dst, tm, full0 + 8 * s, c0, pix0);
           }
-          for (int j = 0; j < a_blocks; ++j) {
-            if (a.mode_a == 1)
-              tma_load_4d(sa + j * kWgBlockBytes, &tmA, full0 + 8 * s, co_tile * 128 + j * 64, 1, 1 + y0, n0);
-            else
-              tma_load_2d(sa + j * kWgBlockBytes, &tmA, full0 + 8 * s, co_tile * 128 + j * 64, pix0);
-          }
-          for (int j = 0; j < a.n_blocks; ++j) {
-            const int b = grp * a.n_blocks + j;
-            if (a.mode_b == 1) {
-              const int tap = b / a.cin_blocks, cb = b - tap * a.cin_blocks;
-              const int ky = tap / a.kw, kx = tap - ky * a.kw;
-              tma_load_4d(sb + j * kWgBlockBytes, &tmB, full0 + 8 * s, cb * 64, a.tap_x0 + kx, a.tap_y0 + y0 + ky, n0);
-            } else {
-              tma_load_2d(sb + j * kWgBlockBytes, &tmB, full0 + 8 * s, b * 64, pix0);
-            }
-          }
+        }
+        if (dbg_on && lane == 0) {
+          a.dbg[cta * 8 + 0] = w_empty;
+          a.dbg[cta * 8 + 1] = clock64() - t_begin;
         }
       }
     } else if (warp == 1) {
@@ -657,25 +719,30 @@ k_wgrad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
         // next 64-channel slab kWgBlockBytes further (LBO)
         const uint32_t lbo = a.swap_lbo_sbo ? 1024u : kWgBlockBytes;
         const uint32_t sbo = a.swap_lbo_sbo ? kWgBlockBytes : 1024u;
+        const uint32_t dhi = umma_desc_hi_sw128(sbo), a_lo0 = umma_desc_lo(smem_base, lbo);
+        long long w_full = 0;
         for (int i = 0; i < nkb; ++i) {
           const int s = i % kWgStages;
           const uint32_t ph = (i / kWgStages) & 1;
-          mbar_wait(full0 + 8 * s, ph);
+          mbar_wait_t(full0 + 8 * s, ph, w_full, dbg_on);
           tc_fence_after();
-          const uint32_t sa = smem_base + s * stage_bytes, sb = sa + 2 * kWgBlockBytes;
+          const uint32_t alo = a_lo0 + s * (stage_bytes >> 4), blo = alo + ((2 * kWgBlockBytes) >> 4);
 #pragma unroll
-          for (int k = 0; k < kWgPix / 16; ++k) {
-            const uint64_t ad = umma_desc_sw128(sa + k * 2048, lbo, sbo);
-            const uint64_t bd = umma_desc_sw128(sb + k * 2048, lbo, sbo);
-            tc_mma_f16(tmem_base, ad, bd, idesc, (i | k) != 0);
-          }
+          for (int k = 0; k < kWgPix / 16; ++k)
+            tc_mma_f16(tmem_base, umma_desc_pack(alo + k * (2048 >> 4), dhi), umma_desc_pack(blo + k * (2048 >> 4), dhi),
+                       idesc, (i | k) != 0);
           tc_commit(empty0 + 8 * s);
         }
         tc_commit(tfull);
+        if (dbg_on) {
+          a.dbg[cta * 8 + 2] = w_full;
+          a.dbg[cta * 8 + 4] = clock64() - t_begin;
+        }
       }
     } else {
       const int q = warp & 3;
-      mbar_wait(tfull, 0);
+      long long w_tfull = 0;
+      mbar_wait_t(tfull, 0, w_tfull, dbg_on);
       tc_fence_after();
       const int co = co_tile * 128 + q * 32 + lane;
       const bool row_ok = co < a.Cout;
@@ -712,6 +779,10 @@ k_wgrad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
             if (col0 + j < a.kvalid) atomicAdd(dst + j, __uint_as_float(r[j]));
         }
         __syncwarp();
+      }
+      if (dbg_on && q == 0 && lane == 0) {
+        a.dbg[cta * 8 + 5] = w_tfull;
+        a.dbg[cta * 8 + 6] = clock64() - t_begin;
       }
     }
   }
@@ -807,6 +878,7 @@ struct ProfRec {
   int cat;
   double flops;
 };
+static long long *g_dbg = nullptr;  // role-timing buffer attached to every GEMM launch while set (salun_debug_role_timing)
 static bool g_prof = false;
 static std::vector<ProfRec> g_recs;
 static void prof_open(int cat, double flops, cudaStream_t st) {
@@ -853,7 +925,9 @@ static int launch_conv_gemm_p_t(const CUtensorMap &tmA, const CUtensorMap &tmB, 
   const int m_tiles = (a.M + kBM - 1) / kBM, n_tiles = (a.N + BN - 1) / BN;
   int grid = m_tiles * n_tiles;
   if (grid > num_sms) grid = num_sms;
-  { k_conv_gemm_p<BN, S><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, a, m_tiles, n_tiles); ++::salun::g_launch_count; }
+  ConvGemmArgs aa = a;
+  aa.dbg = g_dbg;
+  { k_conv_gemm_p<BN, S><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, aa, m_tiles, n_tiles); ++::salun::g_launch_count; }
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;
 }
@@ -907,7 +981,9 @@ static int launch_conv_rw_t(const CUtensorMap &tmA, const CUtensorMap &tmB, cons
   if (gx < 1) gx = 1;
   dim3 grid(gx, n_tiles);
   prof_open(0, 2.0 * a.M * a.N * 9.0 * kCB * 64.0, st);
-  { k_conv_rw<kW, kCB><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, a); ++::salun::g_launch_count; }
+  ConvRwArgs aa = a;
+  aa.dbg = g_dbg;
+  { k_conv_rw<kW, kCB><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, aa); ++::salun::g_launch_count; }
   prof_close(st);
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;
@@ -966,7 +1042,9 @@ int launch_wgrad(const CUtensorMap &tmA, const CUtensorMap &tmB, const WgradArgs
   }
   dim3 grid(co_tiles, col_groups, splits);
   prof_open(1, 2.0 * (double)a.kb_total * 64.0 * a.Cout * (double)a.kvalid, st);
-  { k_wgrad<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, a); ++::salun::g_launch_count; }
+  WgradArgs aa = a;
+  aa.dbg = g_dbg;
+  { k_wgrad<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, aa); ++::salun::g_launch_count; }
   prof_close(st);
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;
@@ -984,6 +1062,13 @@ extern "C" {
 // per-launch CUDA-event timing of the tensor-core kernels: category 0 = k_conv_gemm (forward + dgrad),
 // 1 = k_wgrad.  begin() arms it, end() synchronises the device and returns summed milliseconds, launch counts and
 // algorithmic FLOPs per category.
+// bring-up aid: while a buffer is attached, every GEMM launch writes per-CTA role timings into it
+// ([cta][8] cycles: 0 producer wait-empty, 1 producer total, 2 MMA wait-full, 3 MMA wait-tmem-empty, 4 MMA total,
+//  5 epilogue wait-tmem-full, 6 epilogue total).  Pass NULL to detach.
+int salun_debug_role_timing(long long *buf_dev) {
+  g_dbg = buf_dev;
+  return SALUN_OK;
+}
 int salun_profile_begin(void) {
   g_recs.clear();
   g_prof = true;
@@ -1067,6 +1152,32 @@ int salun_conv_fwd_bf16(salun_ctx *ctx, const void *xpad, const void *wk, void *
   a.stat_sum = stat_sum;
   a.stat_sq = stat_sq;
   return launch_conv_gemm(tmA, tmB, a, bn, (cudaStream_t)stream);
+}
+
+// Same contract as salun_conv_fwd_bf16 (3x3 only) through the persistent resident-weight kernel k_conv_rw;
+// W (= H) in {16, 32}, Cin in {64, 128}.
+int salun_conv_rw_fwd_bf16(salun_ctx *ctx, const void *xpad, const void *wk, void *y_bf16, float *stat_sum,
+                           float *stat_sq, int batch, int H, int W, int Cin, int Cout, void *stream) {
+  SALUN_REQUIRE(ctx && xpad && wk && y_bf16, "NULL argument");
+  SALUN_REQUIRE(H == W && conv_rw_supported(W, Cin, Cout), "shape not served by k_conv_rw");
+  SALUN_CUDA_OK(cudaSetDevice(ctx->device));
+  CUtensorMap tmA, tmB;
+  int rc;
+  TmapBox4 bx{64, W, 128 / W + 2, 1};
+  if ((rc = make_tmap_4d_bf16(&tmA, xpad, Cin, W + 2, H + 2, batch, bx))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmB, wk, Cout, (uint64_t)9 * Cin, 64, 64))) return rc;
+  ConvRwArgs r{};
+  r.H = H;
+  r.W = W;
+  r.cin_blocks = Cin / 64;
+  r.M = batch * H * W;
+  r.num_tiles = (r.M + 127) / 128;
+  r.N = Cout;
+  r.out_bf16 = (__nv_bfloat16 *)y_bf16;
+  r.ld_out = Cout;
+  r.stat_sum = stat_sum;
+  r.stat_sq = stat_sq;
+  return launch_conv_rw(tmA, tmB, r, ctx->num_sms, (cudaStream_t)stream);
 }
 
 // dW[Cout][kh*kw*Cin] (fp32, tap-major) += sum over pixels dY[p][Cout]^T . X_tap[p][Cin]

@@ -23,6 +23,7 @@ struct ConvGemmArgs {
   int ld_out;
   float *stat_sum, *stat_sq;  // per-(m tile, warp) column partial sums [gridDim.x * 4][N], or nullptr
   const __nv_bfloat16 *addend;  // optional [M][ld_out]: D += addend before the store (residual-gradient merge)
+  long long *dbg;               // optional per-CTA role timing [gridDim][8] (bring-up / profiling only)
 };
 
 // dW[co][b*64 + j] += sum_p dY[p][co] * X_b[p][j]   (both operands MN-major: pixels are the K dimension)
@@ -44,6 +45,7 @@ struct WgradArgs {
                            // tile into dw + s*split_stride (a workspace slab of [Cout][ldw]); a deterministic
                            // reduction over the slabs follows (launch_wgrad_reduce) -- no atomics, no zero-fill
   int swap_lbo_sbo;   // debug knob for descriptor bring-up (0 in production)
+  long long *dbg;     // optional per-CTA role timing [gridDim][8]
 };
 
 // persistent stride-1 3x3 convolution with smem-resident weights (k_conv_rw): layer1 / layer2 shapes
@@ -56,6 +58,7 @@ struct ConvRwArgs {
   int ld_out;
   float *stat_sum, *stat_sq;
   const __nv_bfloat16 *addend;
+  long long *dbg;
 };
 
 struct TmapBox4 {

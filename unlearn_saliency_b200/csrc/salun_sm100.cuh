@@ -44,6 +44,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// timed wait: adds the cycles spent blocked to *acc (role-timing instrumentation of the GEMM kernels)
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long &acc, bool on) {
+  if (!on) {
+    mbar_wait(bar, parity);
+    return;
+  }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
@@ -115,6 +126,20 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   d |= 2ull << 61;
   return d;
 }
+// Split form for hot loops: the single MMA-issuing thread is instruction-latency bound, so descriptors are built once
+// (hi word, lo word of the tile base) and advanced with ONE 32-bit add per operand per MMA.
+__device__ __forceinline__ uint32_t umma_desc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint64_t umma_desc_pack(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+
 // Instruction descriptor, kind::f16, BF16 x BF16 -> F32, dense:
 //  [4,6) D format (1 = f32) | [7,10) A format (1 = bf16) | [10,13) B format | [15] A major (1 = MN)
 //  [16] B major | [17,23) N >> 3 | [24,29) M >> 4
