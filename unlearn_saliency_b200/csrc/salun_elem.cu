@@ -469,11 +469,11 @@ __global__ void __launch_bounds__(256) k_prep_w_all(const WPrepEntry *__restrict
   __shared__ float tile[32][33];
   const WPrepEntry e = tab[blockIdx.y];
   const float *__restrict__ w = params + e.w_off;
-  const long long nthreads = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long tf = (long long)e.cout * e.kcp;
-  for (long long i = t0; i < tf; i += nthreads) {
-    const int co = (int)(i / e.kcp), j = (int)(i - (long long)co * e.kcp);
-    e.w_fwd[i] = __float2bfloat16(j < e.kc ? w[(size_t)co * e.kc + j] : 0.f);
+  // forward operand: one output row per block iteration, threads along the row (no integer division per element)
+  for (int co = blockIdx.x; co < e.cout; co += gridDim.x) {
+    const float *__restrict__ src = w + (size_t)co * e.kc;
+    __nv_bfloat16 *__restrict__ dst = e.w_fwd + (size_t)co * e.kcp;
+    for (int j = threadIdx.x; j < e.kcp; j += blockDim.x) dst[j] = __float2bfloat16(j < e.kc ? src[j] : 0.f);
   }
   if (!need_dgrad || e.dgrad_mode == 0) return;
   const int taps = e.dgrad_mode == 1 ? e.kc / e.cin : 1;

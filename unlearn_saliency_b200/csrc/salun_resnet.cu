@@ -75,6 +75,11 @@ struct salun_resnet {
   WPrepEntry *wprep_table;
   WgReduceEntry *wgred_table;          // device copy, refreshed per backward (split counts depend on the batch size)
   WgReduceEntry *wgred_host;           // pinned staging
+  // weight-gradient GEMMs only feed the final gradient: they run on a side stream, under the HBM-bound BatchNorm
+  // backward kernels of the main chain (tensor-bound + memory-bound work co-resident on the SMs)
+  cudaStream_t side;
+  cudaEvent_t ev_fork, ev_join;
+  int use_side;
   std::vector<int> wg_splits_host;
   int use_conv_rw;  // SALUN_CONV_RW: 0 = k_conv_gemm everywhere, 1 = k_conv_rw where supported, 2 = only 32x32 layers
   std::vector<void *> allocs;
@@ -281,7 +286,13 @@ static BnFwd bn_of(salun_resnet *net, const ConvL &L) {
   return b;
 }
 
-static int wgrad_conv(salun_resnet *net, const ConvL &L, const ConvMaps &m, int n, cudaStream_t st) {
+static int wgrad_conv(salun_resnet *net, const ConvL &L, const ConvMaps &m, int n, cudaStream_t main_st) {
+  cudaStream_t st = main_st;
+  if (net->use_side) {  // fork: everything enqueued on the main stream so far (dY, activations) precedes this wgrad
+    SALUN_CUDA_OK(cudaEventRecord(net->ev_fork, main_st));
+    SALUN_CUDA_OK(cudaStreamWaitEvent(net->side, net->ev_fork, 0));
+    st = net->side;
+  }
   const int64_t M = (int64_t)n * L.hout * L.hout;
   WgradArgs a{};
   a.mode_a = L.dy_padded ? 1 : 0;
@@ -485,6 +496,10 @@ static int backward_impl(salun_resnet *net, cudaStream_t st) {
     bn_backward(net, L, net->acts[0].dout, net->acts[0].p, nullptr, n, train, st);
     TRY(wgrad_conv(net, L, (*plan)[0], n, st));
   }
+  if (net->use_side) {  // join: the reduction below consumes every wgrad workspace
+    SALUN_CUDA_OK(cudaEventRecord(net->ev_join, net->side));
+    SALUN_CUDA_OK(cudaStreamWaitEvent(st, net->ev_join, 0));
+  }
   // deterministic split-K reduction of every conv weight gradient into the flat gradient arena (one launch)
   for (size_t i = 0; i < net->convs.size(); ++i) {
     const ConvL &L = net->convs[i];
@@ -544,6 +559,21 @@ int salun_resnet_create(salun_ctx *ctx, const salun_resnet_cfg *cfg, float *para
   net->rvar = running_var;
   net->fwd_done = false;
   net->wgred_host = nullptr;
+  net->side = nullptr;
+  net->ev_fork = net->ev_join = nullptr;
+  {
+    const char *e = getenv("SALUN_WGRAD_SIDE_STREAM");
+    net->use_side = e ? atoi(e) : 1;
+    if (net->use_side) {
+      if (cudaStreamCreateWithFlags(&net->side, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&net->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&net->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        set_error("salun_resnet: could not create the side stream / events");
+        delete net;
+        return SALUN_ERR_CUDA;
+      }
+    }
+  }
   {
     const char *e = getenv("SALUN_CONV_RW");
     net->use_conv_rw = e ? atoi(e) : 1;
@@ -640,6 +670,9 @@ int salun_resnet_destroy(salun_resnet *net) {
   cudaSetDevice(net->ctx->device);
   for (void *p : net->allocs) cudaFree(p);
   if (net->wgred_host) cudaFreeHost(net->wgred_host);
+  if (net->side) cudaStreamDestroy(net->side);
+  if (net->ev_fork) cudaEventDestroy(net->ev_fork);
+  if (net->ev_join) cudaEventDestroy(net->ev_join);
   delete net;
   return SALUN_OK;
 }
