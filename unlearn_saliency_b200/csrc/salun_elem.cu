@@ -264,11 +264,11 @@ __global__ void k_bn_bwd_finalize(const float *__restrict__ partials, int rows, 
     coef[2 * C + c] = train ? (float)(b / (double)count) : 0.f;
   }
 }
-void launch_bn_bwd_finalize(const float *partials, int C, const float *gamma, const float *saved_invstd, float count,
-                            int train, float *dgamma, float *dbeta, float *coef, cudaStream_t st) {
+void launch_bn_bwd_finalize(const float *partials, int rows, int C, const float *gamma, const float *saved_invstd,
+                            float count, int train, float *dgamma, float *dbeta, float *coef, cudaStream_t st) {
   const int M = (int)count;
   dim3 grid((C + 31) / 32), block(32, kRedY);
-  { k_bn_bwd_finalize<<<grid, block, 0, st>>>(partials, bwd_rows(M, C), C, gamma, saved_invstd, count, train, dgamma,
+  { k_bn_bwd_finalize<<<grid, block, 0, st>>>(partials, rows > 0 ? rows : bwd_rows(M, C), C, gamma, saved_invstd, count, train, dgamma,
                                             dbeta, coef); ++::salun::g_launch_count; }
 }
 

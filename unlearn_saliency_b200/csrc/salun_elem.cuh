@@ -32,8 +32,9 @@ void launch_bn_bwd_reduce(const __nv_bfloat16 *dout, const __nv_bfloat16 *out_pa
                           const float *saved_mean, const float *saved_invstd, float *partials, int n_img, int H, int W,
                           int C, cudaStream_t st);
 // partials -> dgamma, dbeta (into the grad arena) and the per-channel coefficients k1, m1, m2 of the apply pass
-void launch_bn_bwd_finalize(const float *partials, int C, const float *gamma, const float *saved_invstd, float count,
-                            int train, float *dgamma, float *dbeta, float *coef, cudaStream_t st);
+// rows > 0: number of partial rows (fused dgrad-epilogue partials); rows == 0: the rows launch_bn_bwd_reduce wrote
+void launch_bn_bwd_finalize(const float *partials, int rows, int C, const float *gamma, const float *saved_invstd,
+                            float count, int train, float *dgamma, float *dbeta, float *coef, cudaStream_t st);
 // dY = k1 * (dZ - m1 - xhat * m2); written padded (for the 4-D TMA consumers) or flat [M][C]; optionally dZ too
 void launch_bn_bwd_apply(const __nv_bfloat16 *dout, const __nv_bfloat16 *out_padded, const __nv_bfloat16 *y,
                          const float *saved_mean, const float *saved_invstd, const float *coef, __nv_bfloat16 *dy,

@@ -68,6 +68,54 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
   return v[0];
 }
 
+// BN-backward partial sums of one 32-column chunk held in r[] (fp32 dX of row `row`): see BnBwdFuse.
+__device__ __forceinline__ void bn_bwd_fuse_chunk(const BnBwdFuse &f, const uint32_t (&r)[32], bool row_ok,
+                                                  size_t pad_off_elems, size_t flat_off_elems, int col0, int N,
+                                                  int stat_row, int lane) {
+  uint32_t maskbits = 0;
+  uint4 yv[4];
+  if (row_ok) {
+    const uint4 *ap = reinterpret_cast<const uint4 *>(f.act + pad_off_elems + col0);
+    const uint4 *yp = reinterpret_cast<const uint4 *>(f.y + flat_off_elems + col0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 av = ap[j];
+      yv[j] = yp[j];
+      const uint32_t w[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        // bf16 > 0  <=>  sign bit clear and magnitude non-zero (activations are post-ReLU: never negative, no NaN)
+        maskbits |= ((w[i] & 0x7fffu) != 0 ? 1u : 0u) << (8 * j + 2 * i);
+        maskbits |= ((w[i] & 0x7fff0000u) != 0 ? 1u : 0u) << (8 * j + 2 * i + 1);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) yv[j] = make_uint4(0, 0, 0, 0);
+  }
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = (maskbits >> j) & 1u ? __uint_as_float(r[j]) : 0.f;
+  const float s1 = warp_transpose_reduce(v, lane);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const uint32_t *yw = reinterpret_cast<const uint32_t *>(&yv[j >> 3]);
+    const uint32_t pair = yw[(j & 7) >> 1];
+    const float yy = __uint_as_float((j & 1) ? (pair & 0xffff0000u) : (pair << 16));
+    const float xh = (yy - __ldg(f.mean + col0 + j)) * __ldg(f.invstd + col0 + j);
+    v[j] = (maskbits >> j) & 1u ? __uint_as_float(r[j]) * xh : 0.f;
+  }
+  const float s2 = warp_transpose_reduce(v, lane);
+  f.partials[((size_t)stat_row * 2 + 0) * N + col0 + lane] = s1;
+  f.partials[((size_t)stat_row * 2 + 1) * N + col0 + lane] = s2;
+}
+__device__ __forceinline__ size_t pad_row_off(int m, int H, int W, int C) {
+  const int hw = H * W;
+  const int n = m / hw, rr = m - n * hw;
+  const int y = rr / W, x = rr - y * W;
+  return ((size_t)(n * (H + 2) + y + 1) * (W + 2) + x + 1) * C;
+}
+
 // =================================================================================================
 // conv / plain GEMM, K-major operands
 // =================================================================================================
@@ -356,6 +404,7 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const int row = m_tile * kBM + q * 32 + lane;
       const bool row_ok = row < a.M;
       const int stat_row = (m_tile * 4 + q);
+      const size_t fuse_pad = (a.f1.act && row_ok) ? pad_row_off(row, a.fH, a.fW, a.N) : 0;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
@@ -391,6 +440,10 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 r[8 * j + 2 * i + 1] = __float_as_uint(__uint_as_float(r[8 * j + 2 * i + 1]) + t.y);
               }
             }
+          }
+          if (a.f1.act) {
+            bn_bwd_fuse_chunk(a.f1, r, row_ok, fuse_pad, (size_t)row * a.N, col0, a.N, stat_row, lane);
+            if (a.f2.act) bn_bwd_fuse_chunk(a.f2, r, row_ok, fuse_pad, (size_t)row * a.N, col0, a.N, stat_row, lane);
           }
           if (row_ok) {
             if (a.out_bf16) {
@@ -558,6 +611,7 @@ k_conv_rw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const int row = tile * 128 + q * 32 + lane;
       const bool row_ok = row < a.M;
       const int stat_row = tile * 4 + q;
+      const size_t fuse_pad = (a.f1.act && row_ok) ? pad_row_off(row, a.H, a.W, a.N) : 0;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
@@ -602,6 +656,10 @@ k_conv_rw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             v.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
             dst[j] = v;
           }
+        }
+        if (a.f1.act) {
+          bn_bwd_fuse_chunk(a.f1, r, row_ok, fuse_pad, (size_t)row * a.N, col0, a.N, stat_row, lane);
+          if (a.f2.act) bn_bwd_fuse_chunk(a.f2, r, row_ok, fuse_pad, (size_t)row * a.N, col0, a.N, stat_row, lane);
         }
         __syncwarp();
       }

@@ -7,6 +7,17 @@
 
 namespace salun {
 
+// Optional epilogue fusion for the dgrad GEMMs: the tile just computed is dX, the gradient w.r.t. an activation
+// act = relu(BN(y) [+ ...]).  The BatchNorm backward of that BN needs  sum_pixels dZ  and  sum_pixels dZ * xhat  with
+// dZ = dX * (act > 0), xhat = (y - mean) * invstd : they are reduced here from the fp32 accumulators (per (tile, warp)
+// column partials, same layout as the forward statistics) instead of in a separate pass over dX, act and y.
+struct BnBwdFuse {
+  const __nv_bfloat16 *act;   // halo-padded activation (ReLU mask), nullptr = fusion off
+  const __nv_bfloat16 *y;     // raw conv output [M][N] feeding that BN
+  const float *mean, *invstd; // saved statistics of that BN
+  float *partials;            // [tiles*4][2][N]
+};
+
 // D[M][N] = sum_k A[m][k] * B[n][k]   (bf16 x bf16 -> fp32 accumulate in TMEM)
 // A comes either from a plain 2-D matrix or, for stride-1 convolutions, directly from the
 // halo-padded NHWC activation through a 4-D tensor map (implicit GEMM: k-block = (tap, 64 channels)).
@@ -24,6 +35,8 @@ struct ConvGemmArgs {
   float *stat_sum, *stat_sq;  // per-(m tile, warp) column partial sums [gridDim.x * 4][N], or nullptr
   const __nv_bfloat16 *addend;  // optional [M][ld_out]: D += addend before the store (residual-gradient merge)
   long long *dbg;               // optional per-CTA role timing [gridDim][8] (bring-up / profiling only)
+  BnBwdFuse f1, f2;             // up to two consumer BatchNorms of the produced gradient (bn2 + projection-shortcut BN)
+  int fH, fW;                   // image size of the output pixels (padded-offset arithmetic of f1/f2.act)
 };
 
 // dW[co][b*64 + j] += sum_p dY[p][co] * X_b[p][j]   (both operands MN-major: pixels are the K dimension)
@@ -59,6 +72,7 @@ struct ConvRwArgs {
   float *stat_sum, *stat_sq;
   const __nv_bfloat16 *addend;
   long long *dbg;
+  BnBwdFuse f1, f2;
 };
 
 struct TmapBox4 {

@@ -81,6 +81,8 @@ struct salun_resnet {
   cudaEvent_t ev_fork, ev_join;
   int use_side;
   std::vector<int> wg_splits_host;
+  std::vector<int> bwd_fused_rows;     // per conv: partial rows written by a fused dgrad epilogue in this backward (0 = none)
+  int use_bwd_fuse;
   int use_conv_rw;  // SALUN_CONV_RW: 0 = k_conv_gemm everywhere, 1 = k_conv_rw where supported, 2 = only 32x32 layers
   std::vector<void *> allocs;
   std::map<int, std::vector<ConvMaps>> plans;
@@ -325,9 +327,12 @@ static int wgrad_conv(salun_resnet *net, const ConvL &L, const ConvMaps &m, int 
 static void bn_backward(salun_resnet *net, const ConvL &L, const bf16 *dout, const bf16 *relu_act, bf16 *dz, int n,
                         int train, cudaStream_t st) {
   const int H = L.hout;
-  launch_bn_bwd_reduce(dout, relu_act, L.y, L.saved_mean, L.saved_invstd, L.bwd_partials, n, H, H, L.cout, st);
-  launch_bn_bwd_finalize(L.bwd_partials, L.cout, net->params + L.g_off, L.saved_invstd, (float)(n * H * H), train,
-                         net->grads + L.g_off, net->grads + L.b_off, L.coef, st);
+  const int ci = (int)(&L - net->convs.data());
+  const int fused_rows = net->bwd_fused_rows[ci];  // > 0: the dgrad GEMM that produced `dout` already reduced dZ, dZ*xhat
+  if (fused_rows == 0)
+    launch_bn_bwd_reduce(dout, relu_act, L.y, L.saved_mean, L.saved_invstd, L.bwd_partials, n, H, H, L.cout, st);
+  launch_bn_bwd_finalize(L.bwd_partials, fused_rows, L.cout, net->params + L.g_off, L.saved_invstd, (float)(n * H * H),
+                         train, net->grads + L.g_off, net->grads + L.b_off, L.coef, st);
   launch_bn_bwd_apply(dout, relu_act, L.y, L.saved_mean, L.saved_invstd, L.coef, L.dy, L.dy_padded ? 1 : 0, dz, n, H, H,
                       L.cout, st);
 }
@@ -393,6 +398,18 @@ static int backward_impl(salun_resnet *net, cudaStream_t st) {
   const int n = net->last_n, train = net->last_train;
   std::vector<ConvMaps> *plan;
   TRY(build_plan(net, n, &plan));
+  net->bwd_fused_rows.assign(net->convs.size(), 0);
+  // consumer BatchNorm(s) of the gradient a dgrad GEMM produces: fills f1/f2 and marks them as reduced
+  auto fuse_for = [&](int conv_idx, const Act &act, BnBwdFuse *f, int rows) {
+    if (!net->use_bwd_fuse) return;
+    ConvL &C = net->convs[conv_idx];
+    f->act = act.p;
+    f->y = C.y;
+    f->mean = C.saved_mean;
+    f->invstd = C.saved_invstd;
+    f->partials = C.bwd_partials;
+    net->bwd_fused_rows[conv_idx] = rows;
+  };
   // every gradient element has exactly one writer (BN finalize, FC backward, wgrad reduce): no zero-fill needed
   const Act &last = net->acts[net->blocks.back().out_act];
   launch_fc_bwd(net->pooled, net->dlogits, net->params + net->fc_w_off, net->grads + net->fc_w_off,
@@ -415,6 +432,7 @@ static int backward_impl(salun_resnet *net, cudaStream_t st) {
       r.N = L2.cin;
       r.out_bf16 = mid.dout;
       r.ld_out = L2.cin;
+      fuse_for(B.c1, mid, &r.f1, r.num_tiles * 4);  // mid = relu(bn1(y1))
       TRY(launch_conv_rw((*plan)[B.c2].rwdA, (*plan)[B.c2].rwdB, r, net->ctx->num_sms, st));
       TRY(wgrad_conv(net, L2, (*plan)[B.c2], n, st));
     } else {
@@ -428,6 +446,8 @@ static int backward_impl(salun_resnet *net, cudaStream_t st) {
       a.N = L2.cin;
       a.out_bf16 = mid.dout;
       a.ld_out = L2.cin;
+      a.fH = a.fW = L2.hout;
+      fuse_for(B.c1, mid, &a.f1, (a.M + 127) / 128 * 4);
       TRY(launch_conv_gemm((*plan)[B.c2].dgA, (*plan)[B.c2].dgB, a, L2.cin % 128 == 0 ? 128 : 64, st));
       TRY(wgrad_conv(net, L2, (*plan)[B.c2], n, st));
     }
@@ -443,6 +463,13 @@ static int backward_impl(salun_resnet *net, cudaStream_t st) {
       r.out_bf16 = in.dout;
       r.ld_out = L1.cin;
       r.addend = identity ? out.dz : nullptr;
+      if (bi > 0) {  // in = relu(bn2(y2) + shortcut) of the previous block
+        const Block &P = net->blocks[bi - 1];
+        fuse_for(P.c2, in, &r.f1, r.num_tiles * 4);
+        if (P.cd >= 0) fuse_for(P.cd, in, &r.f2, r.num_tiles * 4);
+      } else {
+        fuse_for(0, in, &r.f1, r.num_tiles * 4);  // acts[0] = relu(bn(stem conv))
+      }
       TRY(launch_conv_rw((*plan)[B.c1].rwdA, (*plan)[B.c1].rwdB, r, net->ctx->num_sms, st));
       if (!identity) {
         set_error("salun_resnet: stride-1 block with projection shortcut is not supported");
@@ -460,6 +487,17 @@ static int backward_impl(salun_resnet *net, cudaStream_t st) {
       a.out_bf16 = in.dout;
       a.ld_out = L1.cin;
       a.addend = identity ? out.dz : nullptr;  // gradient of the identity shortcut
+      a.fH = a.fW = L1.hout;
+      {
+        const int rows = (a.M + 127) / 128 * 4;
+        if (bi > 0) {
+          const Block &P = net->blocks[bi - 1];
+          fuse_for(P.c2, in, &a.f1, rows);
+          if (P.cd >= 0) fuse_for(P.cd, in, &a.f2, rows);
+        } else {
+          fuse_for(0, in, &a.f1, rows);
+        }
+      }
       TRY(launch_conv_gemm((*plan)[B.c1].dgA, (*plan)[B.c1].dgB, a, L1.cin % 128 == 0 ? 128 : 64, st));
       if (!identity) {
         set_error("salun_resnet: stride-1 block with projection shortcut is not supported");
@@ -575,6 +613,12 @@ int salun_resnet_create(salun_ctx *ctx, const salun_resnet_cfg *cfg, float *para
     }
   }
   {
+    // measured on B200 (profiles/README.md): the dgrad epilogues are already the slower side of their kernels, so
+    // moving the BatchNorm-backward reduction into them costs more (-6% steps/s) than the 16 reduce launches it saves
+    const char *e = getenv("SALUN_BN_BWD_FUSE");
+    net->use_bwd_fuse = e ? atoi(e) : 0;
+  }
+  {
     const char *e = getenv("SALUN_CONV_RW");
     net->use_conv_rw = e ? atoi(e) : 1;
   }
@@ -618,7 +662,11 @@ int salun_resnet_create(salun_ctx *ctx, const salun_resnet_cfg *cfg, float *para
     A(dmalloc(net, &L.saved_mean, (size_t)L.cout, true));
     A(dmalloc(net, &L.saved_invstd, (size_t)L.cout, true));
     A(dmalloc(net, &L.coef, (size_t)3 * L.cout, true));
-    A(dmalloc(net, &L.bwd_partials, (size_t)kBwdPartialRows * 2 * L.cout, true));
+    {
+      size_t prow = (Mo + 127) / 128 * 4;  // fused dgrad epilogues write one partial row per (tile, warp)
+      if (prow < (size_t)kBwdPartialRows) prow = kBwdPartialRows;
+      A(dmalloc(net, &L.bwd_partials, prow * 2 * L.cout, true));
+    }
     {
       const int total_blocks = L.kcp / 64, nb_ = wgrad_pick_blocks(total_blocks);
       const int tiles = ((L.cout + 127) / 128) * (total_blocks / nb_);
