@@ -26,18 +26,20 @@ CIFAR_STD = (0.2470, 0.2435, 0.2616)
 # ---------------------------------------------------------------------------------------------
 # architecture table of resnet18 with the CIFAR stem (models/ResNet.py:217-223, 232-243, 336)
 # ---------------------------------------------------------------------------------------------
-STAGES = [(64, 1), (128, 2), (256, 2), (512, 2)]  # (planes, stride of the first block); 2 BasicBlocks each
+STAGES = [(64, 1), (128, 2), (256, 2), (512, 2)]  # (planes, stride of the first block)
+BLOCKS = {18: (2, 2, 2, 2), 34: (3, 4, 6, 3)}      # BasicBlocks per stage: resnet18 (ResNet.py:336), resnet34 (:347)
 
 
-def resnet18_param_shapes(num_classes: int = 10) -> "OrderedDict[str, Tuple[int, ...]]":
-    """named_parameters() order of the reference's resnet18 (62 tensors, 11 173 962 elements for 10 classes)."""
+def resnet18_param_shapes(num_classes: int = 10, depth: int = 18) -> "OrderedDict[str, Tuple[int, ...]]":
+    """named_parameters() order of the reference's resnet18 (62 tensors, 11 173 962 elements for 10 classes);
+    depth=34 gives resnet34 (BasicBlock [3,4,6,3])."""
     s: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
     s["conv1.weight"] = (64, 3, 3, 3)
     s["bn1.weight"] = (64,)
     s["bn1.bias"] = (64,)
     inpl = 64
     for li, (planes, stride) in enumerate(STAGES, start=1):
-        for b in range(2):
+        for b in range(BLOCKS[depth][li - 1]):
             pre = f"layer{li}.{b}."
             st = stride if b == 0 else 1
             s[pre + "conv1.weight"] = (planes, inpl, 3, 3)
@@ -61,13 +63,13 @@ def bn_names(shapes) -> List[str]:
     return [k[: -len(".weight")] for k in shapes if (".bn" in k or k.startswith("bn") or "downsample.1" in k) and k.endswith(".weight")]
 
 
-def synth_state(num_classes: int = 10, seed: int = 0, bn_stats: bool = True):
+def synth_state(num_classes: int = 10, seed: int = 0, bn_stats: bool = True, depth: int = 18):
     """Deterministic synthetic weights (formula shared by make_golden.py and the tests; no checkpoint exists offline).
 
     conv: N(0, 2/fan_out) (the reference's kaiming_normal_(fan_out), ResNet.py:247-249), BN gamma 1+0.1 N, beta 0.1 N,
     running_mean 0.1 N, running_var 1+0.1|N|, fc: N(0, 1/512)."""
     g = torch.Generator().manual_seed(seed)
-    shapes = resnet18_param_shapes(num_classes)
+    shapes = resnet18_param_shapes(num_classes, depth)
     params: "OrderedDict[str, torch.Tensor]" = OrderedDict()
     for name, shp in shapes.items():
         if len(shp) == 4:
@@ -156,7 +158,7 @@ def resnet_forward(p: Dict[str, torch.Tensor], b: Dict[str, torch.Tensor], x: to
     x = rb(F.relu(_bn(rb(F.conv2d(x, w("conv1.weight"), padding=1)), p, b, "bn1", train)))  # :307-310 (maxpool = Identity)
     inpl = 64
     for li, (planes, stride) in enumerate(STAGES, start=1):
-        for blk in range(2):
+        for blk in range(sum(1 for k in p if k.startswith(f"layer{li}.") and k.endswith(".conv1.weight"))):
             pre = f"layer{li}.{blk}."
             st = stride if blk == 0 else 1
             identity = x

@@ -178,3 +178,27 @@ def test_saliency_mask_end_to_end(engine, salun_ctx):
     # whose |G| sits within the rounding noise of the threshold
     assert jac_emu >= 0.95
     assert jac >= jac_oo - 0.02
+
+
+def test_resnet34_forward_backward(salun_ctx):
+    """resnet34 (ResNet.py:347, BasicBlock [3,4,6,3]) through the same engine: same tolerance model, batch 8."""
+    from unlearn_saliency_b200.engine import ResNetEngine
+    eng = ResNetEngine("resnet34", 10, 32, max_batch=8, ctx=salun_ctx)
+    params, buffers = OC.synth_state(10, seed=1, depth=34)
+    assert list(params.keys()) == list(eng.table.keys())
+    eng.load_state_dict(OC.state_dict_of(params, buffers))
+    x, y = _data(8, seed=4)
+    for train, sign in ((False, -1.0), (True, 1.0)):
+        b = {k: v.clone() for k, v in buffers.items()}
+        _, logits_ref, g_ref = OC.loss_and_grads(params, b, x, y, train=train, sign=sign)
+        b2 = {k: v.clone() for k, v in buffers.items()}
+        _, _, g_emu = OC.loss_and_grads(params, b2, x, y, train=train, sign=sign, emulate_bf16=True)
+        eng.train(train)
+        _, logits = eng.forward_backward(x.cuda(), y.cuda(), loss_sign=sign, want_logits=True)
+        assert (logits.cpu() - logits_ref).abs().max().item() <= 0.08 + 0.03 * logits_ref.abs().max().item()
+        gd = eng.grad_dict()
+        for k in ("fc.weight", "layer4.2.conv2.weight", "layer3.5.bn2.weight", "layer1.0.conv1.weight"):
+            rel_e, cos_e = _rel_cos(gd[k].cpu(), g_ref[k])
+            rel_m, cos_m = _rel_cos(g_emu[k], g_ref[k])
+            assert rel_e <= 1.4 * rel_m + 0.03 and cos_e >= cos_m - 0.05, (k, rel_e, rel_m)
+    eng.close()

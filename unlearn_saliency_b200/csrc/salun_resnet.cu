@@ -162,6 +162,18 @@ static int build_arch(const salun_resnet_cfg &c, std::vector<ConvL> *convs, std:
   return SALUN_OK;
 }
 
+// N-tile of the conv GEMMs: the L2->SM port (64 B/clk) bounds the 128-wide tiles at ~50% of the tensor pipe; 256-wide
+// tiles move 25% fewer operand bytes per MMA cycle and are used whenever they still give ~100+ CTAs
+static int pick_bn(int N, int64_t M) {
+  static int allow256 = -1;
+  if (allow256 < 0) {
+    const char *e = getenv("SALUN_BN256");
+    allow256 = e ? atoi(e) : 1;
+  }
+  if (allow256 && N % 256 == 0 && ((M + 127) / 128) * (N / 256) >= 96) return 256;
+  return N % 128 == 0 ? 128 : 64;
+}
+
 template <typename T>
 static int dmalloc(salun_resnet *net, T **p, size_t count, bool zero) {
   void *q = nullptr;
@@ -189,7 +201,7 @@ static int build_plan(salun_resnet *net, int n, std::vector<ConvMaps> **out) {
     ConvMaps &m = maps[i];
     m.rw_fwd = m.rw_dgrad = false;
     const int64_t Mout = (int64_t)n * L.hout * L.hout;
-    const int bn = L.cout % 128 == 0 ? 128 : 64;
+    const int bn = pick_bn(L.cout, Mout);
     TRY(make_tmap_2d_bf16(&m.fwdB, L.w_fwd, L.cout, L.kcp, bn, 64));
     TmapBox4 bx128, bx64;
     if (L.dy_padded) {
@@ -199,7 +211,7 @@ static int build_plan(salun_resnet *net, int n, std::vector<ConvMaps> **out) {
       TRY(conv_box(L.hin, L.hin, 64, &bx64));
       TRY(make_tmap_4d_bf16(&m.fwdA, in.p, L.cin, L.hin + 2, L.hin + 2, n, bx128));
       TRY(make_tmap_4d_bf16(&m.dgA, L.dy, L.cout, L.hout + 2, L.hout + 2, n, bx128));
-      const int bnd = L.cin % 128 == 0 ? 128 : 64;
+      const int bnd = pick_bn(L.cin, Mout);
       TRY(make_tmap_2d_bf16(&m.dgB, L.w_dgrad, L.cin, (uint64_t)L.ks * L.ks * L.cout, bnd, 64));
       TRY(make_tmap_4d_bf16(&m.wgA, L.dy, L.cout, L.hout + 2, L.hout + 2, n, bx64));
       TRY(make_tmap_4d_bf16(&m.wgB, in.p, L.cin, L.hin + 2, L.hin + 2, n, bx64));
@@ -222,7 +234,7 @@ static int build_plan(salun_resnet *net, int n, std::vector<ConvMaps> **out) {
       if (!L.stem) {
         // dgrad: dcol[Mout][kc] = dY[Mout][Cout] . Wt[kc][Cout]^T
         TRY(make_tmap_2d_bf16(&m.dgA, L.dy, Mout, L.cout, 128, 64));
-        const int bnd = L.kc % 128 == 0 ? 128 : 64;
+        const int bnd = pick_bn(L.kc, Mout);
         TRY(make_tmap_2d_bf16(&m.dgB, L.w_dgrad, L.kc, L.cout, bnd, 64));
       }
     }
@@ -243,7 +255,7 @@ static int conv_forward(salun_resnet *net, const ConvL &L, const ConvMaps &m, in
     a.stat_sum = L.stat_sum;
     a.stat_sq = L.stat_sq;
   }
-  const int bn = L.cout % 128 == 0 ? 128 : 64;
+  const int bn = pick_bn(L.cout, M);
   if (m.rw_fwd) {
     ConvRwArgs r{};
     r.H = r.W = L.hout;
@@ -448,7 +460,7 @@ static int backward_impl(salun_resnet *net, cudaStream_t st) {
       a.ld_out = L2.cin;
       a.fH = a.fW = L2.hout;
       fuse_for(B.c1, mid, &a.f1, (a.M + 127) / 128 * 4);
-      TRY(launch_conv_gemm((*plan)[B.c2].dgA, (*plan)[B.c2].dgB, a, L2.cin % 128 == 0 ? 128 : 64, st));
+      TRY(launch_conv_gemm((*plan)[B.c2].dgA, (*plan)[B.c2].dgB, a, pick_bn(L2.cin, a.M), st));
       TRY(wgrad_conv(net, L2, (*plan)[B.c2], n, st));
     }
     // mid = relu(bn1(y1))
@@ -498,7 +510,7 @@ static int backward_impl(salun_resnet *net, cudaStream_t st) {
           fuse_for(0, in, &a.f1, rows);
         }
       }
-      TRY(launch_conv_gemm((*plan)[B.c1].dgA, (*plan)[B.c1].dgB, a, L1.cin % 128 == 0 ? 128 : 64, st));
+      TRY(launch_conv_gemm((*plan)[B.c1].dgA, (*plan)[B.c1].dgB, a, pick_bn(L1.cin, a.M), st));
       if (!identity) {
         set_error("salun_resnet: stride-1 block with projection shortcut is not supported");
         return SALUN_ERR_UNSUPPORTED;
@@ -514,7 +526,7 @@ static int backward_impl(salun_resnet *net, cudaStream_t st) {
       a.N = L1.kc;
       a.out_bf16 = L1.dcol;
       a.ld_out = L1.kc;
-      TRY(launch_conv_gemm((*plan)[B.c1].dgA, (*plan)[B.c1].dgB, a, L1.kc % 128 == 0 ? 128 : 64, st));
+      TRY(launch_conv_gemm((*plan)[B.c1].dgA, (*plan)[B.c1].dgB, a, pick_bn(L1.kc, a.M), st));
       ConvGemmArgs d{};
       d.mode_a = 0;
       d.num_k_blocks = Ld.cout / 64;
@@ -522,7 +534,7 @@ static int backward_impl(salun_resnet *net, cudaStream_t st) {
       d.N = Ld.kc;
       d.out_bf16 = Ld.dcol;
       d.ld_out = Ld.kc;
-      TRY(launch_conv_gemm((*plan)[B.cd].dgA, (*plan)[B.cd].dgB, d, Ld.kc % 128 == 0 ? 128 : 64, st));
+      TRY(launch_conv_gemm((*plan)[B.cd].dgA, (*plan)[B.cd].dgB, d, pick_bn(Ld.kc, d.M), st));
       launch_col2im_s2(L1.dcol, Ld.dcol, in.dout, n, L1.hin, L1.hin, L1.cin, st);
       TRY(wgrad_conv(net, Ld, (*plan)[B.cd], n, st));
     }
