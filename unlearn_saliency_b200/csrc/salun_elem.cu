@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(256) k_prep_w_all(const WPrepEntry *__restrict
   }
 }
 void launch_prep_w_all(const WPrepEntry *table_dev, int n_convs, const float *params, int need_dgrad, cudaStream_t st) {
-  { k_prep_w_all<<<dim3(96, n_convs), 256, 0, st>>>(table_dev, params, need_dgrad); ++::salun::g_launch_count; }
+  { k_prep_w_all<<<dim3(592, n_convs), 256, 0, st>>>(table_dev, params, need_dgrad); ++::salun::g_launch_count; }
 }
 
 static inline int flat_grid(long long total) {
