@@ -120,8 +120,8 @@ __device__ __forceinline__ void bn_prologue(const BnFwd &p, float *sc, float *sh
 }
 
 __global__ void __launch_bounds__(kET) k_bn_apply(BnFwd a, BnFwd b, int has_b, const __nv_bfloat16 *__restrict__ resid,
-                                                  __nv_bfloat16 *__restrict__ out, int M, int H, int W, int C, int relu,
-                                                  int train, float eps, float momentum) {
+                                                  __nv_bfloat16 *__restrict__ out, uint8_t *__restrict__ rmask, int M,
+                                                  int H, int W, int C, int relu, int train, float eps, float momentum) {
   extern __shared__ float smf[];
   float *sc_a = smf, *sh_a = smf + C, *sc_b = smf + 2 * C, *sh_b = smf + 3 * C;
   bn_prologue(a, sc_a, sh_a, C, train, (double)M, eps, momentum);
@@ -150,6 +150,12 @@ __global__ void __launch_bounds__(kET) k_bn_apply(BnFwd a, BnFwd b, int has_b, c
       for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
     }
     st8(out + po, v);
+    if (rmask) {  // the stored bf16 value decides (a positive fp32 that rounds to +0 cannot occur: bf16 keeps the exponent)
+      uint32_t bits = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << i;
+      rmask[(size_t)m * (C >> 3) + (c0 >> 3)] = (uint8_t)bits;
+    }
   }
 }
 static inline int elem_grid(int M, int C) {
@@ -159,10 +165,12 @@ static inline int elem_grid(int M, int C) {
   return (int)(g < 1 ? 1 : g);
 }
 void launch_bn_apply(const BnFwd &a, const BnFwd *b, const __nv_bfloat16 *resid_padded, __nv_bfloat16 *out_padded,
-                     int n_img, int H, int W, int C, int relu, int train, float eps, float momentum, cudaStream_t st) {
+                     uint8_t *relu_mask_out, int n_img, int H, int W, int C, int relu, int train, float eps,
+                     float momentum, cudaStream_t st) {
   const int M = n_img * H * W;
   BnFwd bb = b ? *b : a;
-  { k_bn_apply<<<elem_grid(M, C), kET, 4 * C * sizeof(float), st>>>(a, bb, b != nullptr, resid_padded, out_padded, M, H,
+  { k_bn_apply<<<elem_grid(M, C), kET, 4 * C * sizeof(float), st>>>(a, bb, b != nullptr, resid_padded, out_padded,
+                                                                  relu_mask_out, M, H,
                                                                   W, C, relu, train, eps, momentum); ++::salun::g_launch_count; }
 }
 
@@ -170,7 +178,7 @@ void launch_bn_apply(const BnFwd &a, const BnFwd *b, const __nv_bfloat16 *resid_
 // BN backward
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kET) k_bn_bwd_reduce(const __nv_bfloat16 *__restrict__ dout,
-                                                       const __nv_bfloat16 *__restrict__ outp,
+                                                       const uint8_t *__restrict__ rmask,
                                                        const __nv_bfloat16 *__restrict__ y,
                                                        const float *__restrict__ mean, const float *__restrict__ invstd,
                                                        float *__restrict__ partials, int M, int H, int W, int C) {
@@ -185,13 +193,13 @@ __global__ void __launch_bounds__(kET) k_bn_bwd_reduce(const __nv_bfloat16 *__re
     is[i] = invstd[c0 + i];
   }
   for (int m = blockIdx.x * rpb + rl; m < M; m += gridDim.x * rpb) {
-    float d[8], o[8], yy[8];
+    float d[8], yy[8];
     ld8(dout + (size_t)m * C + c0, d);
     ld8(y + (size_t)m * C + c0, yy);
-    if (outp) {
-      ld8(outp + pad_off(m, H, W, C) + c0, o);
+    if (rmask) {
+      const uint32_t bits = rmask[(size_t)m * (C >> 3) + (c0 >> 3)];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = o[i] > 0.f ? d[i] : 0.f;
+      for (int i = 0; i < 8; ++i) d[i] = (bits >> i) & 1u ? d[i] : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -221,12 +229,12 @@ static inline int bwd_rows(int M, int C) {
   int g = (M + rpb - 1) / rpb;
   return g < kBwdPartialRows ? (g < 1 ? 1 : g) : kBwdPartialRows;
 }
-void launch_bn_bwd_reduce(const __nv_bfloat16 *dout, const __nv_bfloat16 *out_padded, const __nv_bfloat16 *y,
+void launch_bn_bwd_reduce(const __nv_bfloat16 *dout, const uint8_t *relu_mask, const __nv_bfloat16 *y,
                           const float *saved_mean, const float *saved_invstd, float *partials, int n_img, int H, int W,
                           int C, cudaStream_t st) {
   const int M = n_img * H * W;
   const int rpb = kET / (C >> 3);
-  { k_bn_bwd_reduce<<<bwd_rows(M, C), kET, 2 * rpb * C * sizeof(float), st>>>(dout, out_padded, y, saved_mean,
+  { k_bn_bwd_reduce<<<bwd_rows(M, C), kET, 2 * rpb * C * sizeof(float), st>>>(dout, relu_mask, y, saved_mean,
                                                                            saved_invstd, partials, M, H, W, C); ++::salun::g_launch_count; }
 }
 
@@ -273,7 +281,7 @@ void launch_bn_bwd_finalize(const float *partials, int rows, int C, const float 
 }
 
 __global__ void __launch_bounds__(kET) k_bn_bwd_apply(const __nv_bfloat16 *__restrict__ dout,
-                                                      const __nv_bfloat16 *__restrict__ outp,
+                                                      const uint8_t *__restrict__ rmask,
                                                       const __nv_bfloat16 *__restrict__ y,
                                                       const float *__restrict__ mean, const float *__restrict__ invstd,
                                                       const float *__restrict__ coef, __nv_bfloat16 *__restrict__ dy,
@@ -291,26 +299,25 @@ __global__ void __launch_bounds__(kET) k_bn_bwd_apply(const __nv_bfloat16 *__res
     m2[i] = coef[2 * C + c0 + i];
   }
   for (int m = blockIdx.x * rpb + rl; m < M; m += gridDim.x * rpb) {
-    float d[8], o[8], yy[8];
+    float d[8], yy[8];
     ld8(dout + (size_t)m * C + c0, d);
     ld8(y + (size_t)m * C + c0, yy);
-    const size_t po = pad_off(m, H, W, C) + c0;
-    if (outp) {
-      ld8(outp + po, o);
+    if (rmask) {
+      const uint32_t bits = rmask[(size_t)m * (C >> 3) + (c0 >> 3)];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = o[i] > 0.f ? d[i] : 0.f;
+      for (int i = 0; i < 8; ++i) d[i] = (bits >> i) & 1u ? d[i] : 0.f;
     }
     if (dz_flat) st8(dz_flat + (size_t)m * C + c0, d);
 #pragma unroll
     for (int i = 0; i < 8; ++i) yy[i] = k1[i] * (d[i] - m1[i] - (yy[i] - mu[i]) * is[i] * m2[i]);
-    st8(dy_padded ? dy + po : dy + (size_t)m * C + c0, yy);
+    st8(dy_padded ? dy + pad_off(m, H, W, C) + c0 : dy + (size_t)m * C + c0, yy);
   }
 }
-void launch_bn_bwd_apply(const __nv_bfloat16 *dout, const __nv_bfloat16 *out_padded, const __nv_bfloat16 *y,
+void launch_bn_bwd_apply(const __nv_bfloat16 *dout, const uint8_t *relu_mask, const __nv_bfloat16 *y,
                          const float *saved_mean, const float *saved_invstd, const float *coef, __nv_bfloat16 *dy,
                          int dy_padded, __nv_bfloat16 *dz_flat, int n_img, int H, int W, int C, cudaStream_t st) {
   const int M = n_img * H * W;
-  { k_bn_bwd_apply<<<elem_grid(M, C), kET, 0, st>>>(dout, out_padded, y, saved_mean, saved_invstd, coef, dy, dy_padded,
+  { k_bn_bwd_apply<<<elem_grid(M, C), kET, 0, st>>>(dout, relu_mask, y, saved_mean, saved_invstd, coef, dy, dy_padded,
                                                   dz_flat, M, H, W, C); ++::salun::g_launch_count; }
 }
 

@@ -24,11 +24,14 @@ void launch_bn_stats_reduce(const float *stat_sum, const float *stat_sq, int row
                             cudaStream_t st);
 
 // out = relu?( bn_a(y_a) [+ bn_b(y_b)] [+ resid] ), written into the halo-padded NHWC activation
+// relu_mask_out (optional): 1 bit per output element, [M][C/8] bytes, bit i of byte (m, c/8) = out[m][c + i] > 0 --
+// the backward kernels read it instead of the 16x larger activation
 void launch_bn_apply(const BnFwd &a, const BnFwd *b, const __nv_bfloat16 *resid_padded, __nv_bfloat16 *out_padded,
-                     int n_img, int H, int W, int C, int relu, int train, float eps, float momentum, cudaStream_t st);
+                     uint8_t *relu_mask_out, int n_img, int H, int W, int C, int relu, int train, float eps,
+                     float momentum, cudaStream_t st);
 
-// sums over pixels of dZ and dZ*xhat, dZ = dout * (out > 0)  [out_padded == nullptr: no ReLU in front]
-void launch_bn_bwd_reduce(const __nv_bfloat16 *dout, const __nv_bfloat16 *out_padded, const __nv_bfloat16 *y,
+// sums over pixels of dZ and dZ*xhat, dZ = dout * (out > 0)  [relu_mask == nullptr: no ReLU in front]
+void launch_bn_bwd_reduce(const __nv_bfloat16 *dout, const uint8_t *relu_mask, const __nv_bfloat16 *y,
                           const float *saved_mean, const float *saved_invstd, float *partials, int n_img, int H, int W,
                           int C, cudaStream_t st);
 // partials -> dgamma, dbeta (into the grad arena) and the per-channel coefficients k1, m1, m2 of the apply pass
@@ -36,7 +39,7 @@ void launch_bn_bwd_reduce(const __nv_bfloat16 *dout, const __nv_bfloat16 *out_pa
 void launch_bn_bwd_finalize(const float *partials, int rows, int C, const float *gamma, const float *saved_invstd,
                             float count, int train, float *dgamma, float *dbeta, float *coef, cudaStream_t st);
 // dY = k1 * (dZ - m1 - xhat * m2); written padded (for the 4-D TMA consumers) or flat [M][C]; optionally dZ too
-void launch_bn_bwd_apply(const __nv_bfloat16 *dout, const __nv_bfloat16 *out_padded, const __nv_bfloat16 *y,
+void launch_bn_bwd_apply(const __nv_bfloat16 *dout, const uint8_t *relu_mask, const __nv_bfloat16 *y,
                          const float *saved_mean, const float *saved_invstd, const float *coef, __nv_bfloat16 *dy,
                          int dy_padded, __nv_bfloat16 *dz_flat, int n_img, int H, int W, int C, cudaStream_t st);
 

@@ -45,6 +45,7 @@ struct Act {
   bf16 *p;       // padded [n][H+2][H+2][C]
   bf16 *dout;    // gradient w.r.t. this activation, flat [n*H*H][C]
   bf16 *dz;      // dout * (act > 0), flat (identity-shortcut blocks only)
+  uint8_t *rmask;  // 1-bit ReLU mask of this activation, [n*H*H][C/8] (read by the BatchNorm backward instead of p)
 };
 struct Block {
   int c1, c2, cd;          // conv indices (cd = -1: identity shortcut)
@@ -336,7 +337,7 @@ static int wgrad_conv(salun_resnet *net, const ConvL &L, const ConvMaps &m, int 
 }
 
 // BN backward of one conv's BatchNorm: dout (flat) [* relu mask of out_act] -> L.dy (+ dz)
-static void bn_backward(salun_resnet *net, const ConvL &L, const bf16 *dout, const bf16 *relu_act, bf16 *dz, int n,
+static void bn_backward(salun_resnet *net, const ConvL &L, const bf16 *dout, const uint8_t *relu_act, bf16 *dz, int n,
                         int train, cudaStream_t st) {
   const int H = L.hout;
   const int ci = (int)(&L - net->convs.data());
@@ -368,7 +369,7 @@ static int forward_impl(salun_resnet *net, const float *x, const int64_t *labels
     launch_stem_im2col(x, L.col, n, L.hin, L.hin, c.mean, inv_std, st);
     TRY(conv_forward(net, L, (*plan)[0], n, train, st));
     BnFwd b = bn_of(net, L);
-    launch_bn_apply(b, nullptr, nullptr, net->acts[0].p, n, L.hout, L.hout, L.cout, 1, train, c.bn_eps, c.bn_momentum,
+    launch_bn_apply(b, nullptr, nullptr, net->acts[0].p, need_bwd ? net->acts[0].rmask : nullptr, n, L.hout, L.hout, L.cout, 1, train, c.bn_eps, c.bn_momentum,
                     st);
   }
   for (const Block &B : net->blocks) {
@@ -377,7 +378,7 @@ static int forward_impl(salun_resnet *net, const float *x, const int64_t *labels
     if (!L1.dy_padded) launch_im2col_s2(in.p, L1.col, n, L1.hin, L1.hin, L1.cin, 3, st);
     TRY(conv_forward(net, L1, (*plan)[B.c1], n, train, st));
     BnFwd b1 = bn_of(net, L1);
-    launch_bn_apply(b1, nullptr, nullptr, mid.p, n, L1.hout, L1.hout, L1.cout, 1, train, c.bn_eps, c.bn_momentum, st);
+    launch_bn_apply(b1, nullptr, nullptr, mid.p, need_bwd ? mid.rmask : nullptr, n, L1.hout, L1.hout, L1.cout, 1, train, c.bn_eps, c.bn_momentum, st);
     TRY(conv_forward(net, L2, (*plan)[B.c2], n, train, st));
     BnFwd b2 = bn_of(net, L2);
     if (B.cd >= 0) {
@@ -385,9 +386,9 @@ static int forward_impl(salun_resnet *net, const float *x, const int64_t *labels
       launch_im2col_s2(in.p, Ld.col, n, Ld.hin, Ld.hin, Ld.cin, 1, st);
       TRY(conv_forward(net, Ld, (*plan)[B.cd], n, train, st));
       BnFwd bd = bn_of(net, Ld);
-      launch_bn_apply(b2, &bd, nullptr, out.p, n, L2.hout, L2.hout, L2.cout, 1, train, c.bn_eps, c.bn_momentum, st);
+      launch_bn_apply(b2, &bd, nullptr, out.p, need_bwd ? out.rmask : nullptr, n, L2.hout, L2.hout, L2.cout, 1, train, c.bn_eps, c.bn_momentum, st);
     } else {
-      launch_bn_apply(b2, nullptr, in.p, out.p, n, L2.hout, L2.hout, L2.cout, 1, train, c.bn_eps, c.bn_momentum, st);
+      launch_bn_apply(b2, nullptr, in.p, out.p, need_bwd ? out.rmask : nullptr, n, L2.hout, L2.hout, L2.cout, 1, train, c.bn_eps, c.bn_momentum, st);
     }
   }
   const Act &last = net->acts[net->blocks.back().out_act];
@@ -432,8 +433,8 @@ static int backward_impl(salun_resnet *net, cudaStream_t st) {
     const Act &in = net->acts[B.in_act], &mid = net->acts[B.mid_act], &out = net->acts[B.out_act];
     const bool identity = B.cd < 0;
     // out = relu(bn2(y2) + shortcut):  dZ = dOut * (out > 0)
-    bn_backward(net, L2, out.dout, out.p, identity ? out.dz : nullptr, n, train, st);
-    if (!identity) bn_backward(net, net->convs[B.cd], out.dout, out.p, nullptr, n, train, st);
+    bn_backward(net, L2, out.dout, out.rmask, identity ? out.dz : nullptr, n, train, st);
+    if (!identity) bn_backward(net, net->convs[B.cd], out.dout, out.rmask, nullptr, n, train, st);
     // conv2: dgrad -> d(mid), wgrad
     if ((*plan)[B.c2].rw_dgrad) {
       ConvRwArgs r{};
@@ -464,7 +465,7 @@ static int backward_impl(salun_resnet *net, cudaStream_t st) {
       TRY(wgrad_conv(net, L2, (*plan)[B.c2], n, st));
     }
     // mid = relu(bn1(y1))
-    bn_backward(net, L1, mid.dout, mid.p, nullptr, n, train, st);
+    bn_backward(net, L1, mid.dout, mid.rmask, nullptr, n, train, st);
     if (L1.dy_padded && (*plan)[B.c1].rw_dgrad) {
       ConvRwArgs r{};
       r.H = r.W = L1.hout;
@@ -543,7 +544,7 @@ static int backward_impl(salun_resnet *net, cudaStream_t st) {
   // stem: act0 = relu(bn(y0)); no dgrad (the input needs no gradient)
   {
     const ConvL &L = net->convs[0];
-    bn_backward(net, L, net->acts[0].dout, net->acts[0].p, nullptr, n, train, st);
+    bn_backward(net, L, net->acts[0].dout, net->acts[0].rmask, nullptr, n, train, st);
     TRY(wgrad_conv(net, L, (*plan)[0], n, st));
   }
   if (net->use_side) {  // join: the reduction below consumes every wgrad workspace
@@ -654,6 +655,7 @@ int salun_resnet_create(salun_ctx *ctx, const salun_resnet_cfg *cfg, float *para
     A(dmalloc(net, &a.p, padded, true));
     A(dmalloc(net, &a.dout, (size_t)nb * a.H * a.H * a.C, false));
     A(dmalloc(net, &a.dz, (size_t)nb * a.H * a.H * a.C, false));
+    A(dmalloc(net, &a.rmask, (size_t)nb * a.H * a.H * a.C / 8, true));
   }
   for (ConvL &L : net->convs) {
     const size_t Mo = (size_t)nb * L.hout * L.hout;
