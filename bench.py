@@ -149,7 +149,13 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
 
-    eng = ResNetEngine("resnet18", 10, 32, max_batch=BATCH, device=dev)
+    fused_dp = world > 1 and os.environ.get("SALUN_FUSED_DP", "1") != "0"
+    try:
+        eng = ResNetEngine("resnet18", 10, 32, max_batch=BATCH, device=dev, symmetric=fused_dp)
+    except Exception as e:  # symmetric memory unavailable on this box: NCCL all-reduce + local step (same arithmetic)
+        print(f"[bench] symmetric memory unavailable ({e!r}); using NCCL all-reduce", file=sys.stderr)
+        fused_dp = False
+        eng = ResNetEngine("resnet18", 10, 32, max_batch=BATCH, device=dev)
     # random-init weights of the reference architecture (kaiming-normal fan_out convs, unit BN), same on every rank
     g = torch.Generator(device="cpu").manual_seed(0)
     sd = {}
@@ -164,7 +170,16 @@ def main():
             sd[k] = torch.zeros(shp)
     eng.load_state_dict(sd)
     mask_native = (torch.rand(eng.n_params, generator=g) < 0.5).to(torch.int64).to(dev)
-    opt = MaskedSGD(eng, 0.013, 0.9, 5e-4, mask_bits=eng.ctx.pack_mask(mask_native))
+    bits = eng.ctx.pack_mask(mask_native)
+    if fused_dp:
+        from unlearn_saliency_b200.engine import DistMaskedSGD
+        try:
+            opt = DistMaskedSGD(eng, 0.013, 0.9, 5e-4, mask_bits=bits)
+        except Exception as e:
+            print(f"[bench] fused DP step unavailable ({e!r}); using NCCL all-reduce", file=sys.stderr)
+            fused_dp = False
+    if not fused_dp:
+        opt = MaskedSGD(eng, 0.013, 0.9, 5e-4, mask_bits=bits)
     eng.train(True)
 
     # synthetic CIFAR-shaped inputs: a pool larger than L2 is not needed for the images (3 MB/step); the step itself
@@ -178,16 +193,16 @@ def main():
 
     def step_resident(i):
         eng.forward_backward(dev_x[i % n_pool], dev_y[i % n_pool])
-        if world > 1:
+        if world > 1 and not fused_dp:
             dist.all_reduce(eng.grads)
             eng.grads.div_(world)
-        opt.step()
+        opt.step()  # fused_dp: reduce-scatter + masked SGD + all-gather in one kernel over NVLink peer memory
 
     def step_e2e(i):
         x = host_x[i % n_pool].to(dev, non_blocking=True)
         y = host_y[i % n_pool].to(dev, non_blocking=True)
         loss, _ = eng.forward_backward(x, y)
-        if world > 1:
+        if world > 1 and not fused_dp:
             dist.all_reduce(eng.grads)
             eng.grads.div_(world)
         opt.step()
@@ -270,7 +285,10 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "ResNet-18/CIFAR-10 SalUn RL masked unlearn step (RL.py:123-140), mask ratio 0.5",
                        "global_batch": BATCH * world, "per_gpu_batch": BATCH, "image": "3x32x32",
-                       "parallelism": f"dp{world}", "optimizer": "SGD lr 0.013 momentum 0.9 wd 5e-4 (fused masked step)",
+                       "parallelism": f"dp{world}",
+                       "collective": ("fused reduce-scatter + masked SGD + all-gather kernel over NVLink peer memory"
+                                      if fused_dp else ("NCCL all-reduce of the flat gradient" if world > 1 else "none")),
+                       "optimizer": "SGD lr 0.013 momentum 0.9 wd 5e-4 (fused masked step)",
                        "l2": "step working set (~2 GB activations + 134 MB optimizer state) exceeds the 126 MB L2"},
             "tflops_per_gpu": STEP_GFLOP / ms_step, "gpu_launches": int(launches), "launches_per_step": launches / args.steps,
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

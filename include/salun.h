@@ -127,6 +127,21 @@ int salun_masked_sgd_step(salun_ctx *ctx, float *p, const float *g, float *v,
                           const uint32_t *mask_bits, int64_t n, float lr, float momentum,
                           float wd, void *stream);
 
+/* Data-parallel form of the step above, ONE kernel over NVLink peer memory instead of
+ * all-reduce + scale + salun_masked_sgd_step:
+ *   shard [lo, hi) = salun_dp_shard(n, rank, world) of the flat arena is owned by `rank`;
+ *   g = (sum over ranks r = 0..world-1 of grad_peers[r][i]) / world   (peer loads, fixed order -> identical replicas)
+ *   masked SGD on p[i], v_shard[i - lo] exactly as salun_masked_sgd_step
+ *   p written to param_peers[r][i] for every r                          (peer stores)
+ * param_peers_host / grad_peers_host: HOST arrays of `world` device pointers, entry r = rank r's arena mapped into
+ * this process (e.g. torch symmetric memory buffer_ptrs); world <= 8.  v_shard: hi - lo floats, zero-initialised.
+ * The caller orders the ranks: a cross-rank barrier on `stream` before (all gradients written) and after (all weights
+ * delivered) the call.  Semantics are those of DDP-averaged gradients followed by RL.py:134-140. */
+int salun_dp_shard(int64_t n, int rank, int world, int64_t *lo, int64_t *hi);
+int salun_dp_masked_sgd_step(salun_ctx *ctx, float *const *param_peers_host, const float *const *grad_peers_host,
+                             float *v_shard, const uint32_t *mask_bits, int64_t n, int rank, int world, float lr,
+                             float momentum, float wd, void *stream);
+
 /* sumsq_dev[0] = sum_i g[i]^2 in double (deterministic two-stage reduction).
  * replaces the norm inside clip_grad_norm_   DDPM/runners/diffusion.py:582-587,985-990 */
 int salun_grad_sumsq(salun_ctx *ctx, const float *g, int64_t n, double *sumsq_dev, void *stream);

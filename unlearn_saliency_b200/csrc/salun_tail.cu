@@ -388,6 +388,48 @@ __global__ void __launch_bounds__(kThreads) k_masked_sgd(float *__restrict__ p, 
 }
 
 // ------------------------------------------------------------------------------------------
+// data-parallel fused step: reduce-scatter(grad) over NVLink peer memory -> masked SGD on the owned shard ->
+// all-gather(param) by peer stores.  Replaces  all_reduce(grad); grad /= W; masked SGD  (3 passes over the arena + NCCL)
+// with ONE kernel: every rank reads its 1/W shard of every peer's gradient arena (fixed rank order: bit-identical
+// replicas), updates that shard of the weights with the same arithmetic as k_masked_sgd, and writes the new weights into
+// every peer's parameter arena.  The momentum buffer exists only for the owned shard (ZeRO-1 style).
+// Cross-rank ordering (gradients complete before, weights visible after) is the caller's job: a symmetric-memory
+// barrier on the stream on both sides.
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 8;
+struct PeerPtrs {
+  float *p[kMaxPeers];
+  const float *g[kMaxPeers];
+};
+__global__ void __launch_bounds__(kThreads) k_dp_masked_sgd(PeerPtrs peers, int world, float *__restrict__ v_shard,
+                                                            const uint32_t *__restrict__ bits, int64_t lo, int64_t hi,
+                                                            float lr, float mu, float wd, float inv_world) {
+  int64_t stride = (int64_t)gridDim.x * kThreads * 4;
+  for (int64_t i = lo + ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4; i < hi; i += stride) {
+    const uint32_t nib = mask_nibble(bits, i);
+    float4 vv = load4(v_shard, i - lo, hi - lo, 0.f);
+    if (nib == 0u) {
+      store4(v_shard, i - lo, hi - lo, make_float4(0.f, 0.f, 0.f, 0.f));
+      continue;  // masked-out: weights untouched on every replica
+    }
+    float4 gg = load4(peers.g[0], i, hi, 0.f);
+    for (int r = 1; r < world; ++r) {
+      const float4 t = load4(peers.g[r], i, hi, 0.f);
+      gg.x = __fadd_rn(gg.x, t.x); gg.y = __fadd_rn(gg.y, t.y); gg.z = __fadd_rn(gg.z, t.z); gg.w = __fadd_rn(gg.w, t.w);
+    }
+    gg.x = __fmul_rn(gg.x, inv_world); gg.y = __fmul_rn(gg.y, inv_world);
+    gg.z = __fmul_rn(gg.z, inv_world); gg.w = __fmul_rn(gg.w, inv_world);
+    float4 pp = load4(peers.p[0], i, hi, 0.f);  // all replicas hold the same weights; read the first pointer (= local)
+    sgd1(pp.x, gg.x, vv.x, nib & 1u, lr, mu, wd);
+    sgd1(pp.y, gg.y, vv.y, nib & 2u, lr, mu, wd);
+    sgd1(pp.z, gg.z, vv.z, nib & 4u, lr, mu, wd);
+    sgd1(pp.w, gg.w, vv.w, nib & 8u, lr, mu, wd);
+    store4(v_shard, i - lo, hi - lo, vv);
+    for (int r = 0; r < world; ++r) store4(peers.p[r], i, hi, pp);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // grad norm (double partials, fixed reduction tree -> deterministic), clip coefficient
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) k_sumsq_partial(const float *__restrict__ g, int64_t n,
@@ -680,6 +722,41 @@ int salun_masked_sgd_step(salun_ctx *ctx, float *p, const float *g, float *v, co
   SALUN_REQUIRE(p && g && v, "NULL buffer");
   SALUN_REQUIRE(aligned16(p) && aligned16(g) && aligned16(v), "p, g, v must be 16-byte aligned");
   { k_masked_sgd<<<grid_for(ctx, (n + 3) / 4), kThreads, 0, st>>>(p, g, v, mask_bits, n, lr, momentum, wd); ++::salun::g_launch_count; }
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+
+int salun_dp_shard(int64_t n, int rank, int world, int64_t *lo, int64_t *hi) {
+  SALUN_REQUIRE(n >= 0 && world >= 1 && rank >= 0 && rank < world && lo && hi, "bad shard arguments");
+  int64_t per = (n + world - 1) / world;
+  per = (per + 127) / 128 * 128;  // whole mask words and 16-byte vectors per shard
+  *lo = per * rank < n ? per * rank : n;
+  *hi = per * (rank + 1) < n ? per * (rank + 1) : n;
+  return SALUN_OK;
+}
+
+int salun_dp_masked_sgd_step(salun_ctx *ctx, float *const *param_peers_host, const float *const *grad_peers_host,
+                             float *v_shard, const uint32_t *mask_bits, int64_t n, int rank, int world, float lr,
+                             float momentum, float wd, void *stream) {
+  SALUN_ENTER(ctx);
+  SALUN_REQUIRE(param_peers_host && grad_peers_host && v_shard, "NULL argument");
+  SALUN_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "world must be 1..8");
+  int64_t lo, hi;
+  salun_dp_shard(n, rank, world, &lo, &hi);
+  if (hi <= lo) return SALUN_OK;
+  PeerPtrs pp;
+  // local replica first: it is the one whose weights are read
+  for (int r = 0; r < world; ++r) {
+    const int src = (rank + r) % world;
+    SALUN_REQUIRE(param_peers_host[src] && grad_peers_host[src], "NULL peer pointer");
+    SALUN_REQUIRE(aligned16(param_peers_host[src]) && aligned16(grad_peers_host[src]), "peer arenas must be 16-byte aligned");
+    pp.p[r] = param_peers_host[src];
+  }
+  for (int r = 0; r < world; ++r) pp.g[r] = grad_peers_host[r];  // gradients summed in rank order on every rank
+  SALUN_REQUIRE(aligned16(v_shard), "v_shard must be 16-byte aligned");
+  k_dp_masked_sgd<<<grid_for(ctx, (hi - lo + 3) / 4), kThreads, 0, st>>>(pp, world, v_shard, mask_bits, lo, hi, lr,
+                                                                          momentum, wd, 1.0f / (float)world);
+  ++::salun::g_launch_count;
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;
 }

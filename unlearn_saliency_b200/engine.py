@@ -63,7 +63,10 @@ class ResNetEngine:
     """The reference's ``model`` for the hot path: parameters live in one flat fp32 arena on the GPU."""
 
     def __init__(self, arch: str = "resnet18", num_classes: int = 10, image_size: int = 32, max_batch: int = 256,
-                 mean=CIFAR_MEAN, std=CIFAR_STD, device=None, ctx: Optional[SalunContext] = None):
+                 mean=CIFAR_MEAN, std=CIFAR_STD, device=None, ctx: Optional[SalunContext] = None,
+                 symmetric: bool = False):
+        """symmetric=True allocates the parameter / gradient arenas as torch symmetric memory (NVLink peer-mapped), which
+        DistMaskedSGD needs for its fused reduce-scatter + update + all-gather kernel."""
         if arch not in _ARCH_DEPTH:
             raise ValueError(f"arch {arch!r} is not served by the sm_100a engine (supported: {sorted(_ARCH_DEPTH)})")
         self.arch, self.depth = arch, _ARCH_DEPTH[arch]
@@ -80,8 +83,16 @@ class ResNetEngine:
         if self.n_params != sum(math.prod(s) for s in self.table.values()):
             raise RuntimeError("parameter table of the host mirror and libsalun disagree")
         dev = self.device
-        self.params = torch.zeros(self.n_params, device=dev)
-        self.grads = torch.zeros(self.n_params, device=dev)
+        self.symmetric = symmetric
+        if symmetric:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.params = symm_mem.empty(self.n_params, dtype=torch.float32, device=dev)
+            self.grads = symm_mem.empty(self.n_params, dtype=torch.float32, device=dev)
+            self.params.zero_()
+            self.grads.zero_()
+        else:
+            self.params = torch.zeros(self.n_params, device=dev)
+            self.grads = torch.zeros(self.n_params, device=dev)
         self.running_mean = torch.zeros(n_bn, device=dev)
         self.running_var = torch.ones(n_bn, device=dev)
         self.num_batches_tracked = 0
@@ -273,3 +284,42 @@ class MaskedSGD:
         g = self.param_groups[0]
         self.ctx.masked_sgd_step(self.engine.params, self.engine.grads, self.momentum_buffer, self.mask_bits,
                                  g["lr"], g["momentum"], g["weight_decay"])
+
+
+class DistMaskedSGD:
+    """Data-parallel MaskedSGD: all_reduce(grad)/W + mask + SGD + restore as ONE kernel over NVLink peer memory
+    (salun_dp_masked_sgd_step): each rank reduces its 1/W shard of every peer's gradient arena, updates that shard of the
+    weights (momentum exists only for the shard) and stores the new weights into every peer's parameter arena.
+    The engine must have been created with symmetric=True and torch.distributed (NCCL) must be initialised."""
+
+    def __init__(self, engine: ResNetEngine, lr: float, momentum: float = 0.9, weight_decay: float = 5e-4,
+                 mask_bits: Optional[torch.Tensor] = None, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        if not engine.symmetric:
+            raise ValueError("DistMaskedSGD needs ResNetEngine(symmetric=True)")
+        self.engine, self.ctx = engine, engine.ctx
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.param_groups = [{"lr": lr, "momentum": momentum, "weight_decay": weight_decay}]
+        self.mask_bits = mask_bits
+        self._hp = symm_mem.rendezvous(engine.params, self.group)
+        self._hg = symm_mem.rendezvous(engine.grads, self.group)
+        lo, hi = C.c_int64(), C.c_int64()
+        check(engine._lib.salun_dp_shard(engine.n_params, self.rank, self.world, C.byref(lo), C.byref(hi)), "salun_dp_shard")
+        self.lo, self.hi = lo.value, hi.value
+        self.momentum_shard = torch.zeros(max(4, self.hi - self.lo), device=engine.device)
+        self._pp = (C.c_void_p * self.world)(*[int(p) for p in self._hp.buffer_ptrs])
+        self._gp = (C.c_void_p * self.world)(*[int(p) for p in self._hg.buffer_ptrs])
+
+    def zero_grad(self):
+        pass
+
+    def step(self):
+        g = self.param_groups[0]
+        self._hg.barrier(channel=0)  # every rank's backward has written its gradient arena
+        check(self.engine._lib.salun_dp_masked_sgd_step(
+            self.ctx.handle, self._pp, self._gp, _ptr(self.momentum_shard), _ptr(self.mask_bits), self.engine.n_params,
+            self.rank, self.world, float(g["lr"]), float(g["momentum"]), float(g["weight_decay"]),
+            _stream(self.engine.device)), "salun_dp_masked_sgd_step")
+        self._hp.barrier(channel=1)  # every rank's shard of the new weights has landed in every replica
