@@ -25,7 +25,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-os.environ["NCCL_DEBUG"] = os.environ.get("SALUN_NCCL_DEBUG", "WARN")  # keep stdout to the ONE JSON line
+# keep stdout to the ONE JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION/WARN/INFO
+os.environ.pop("NCCL_DEBUG", None)
+if os.environ.get("SALUN_NCCL_DEBUG"):
+    os.environ["NCCL_DEBUG"] = os.environ["SALUN_NCCL_DEBUG"]
 
 BATCH = 256
 FWD_GFLOP_PER_IMG = 1.1108  # SURVEY.md section 6 (torch.utils.flop_counter on the reference model)
