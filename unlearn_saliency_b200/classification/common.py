@@ -14,8 +14,9 @@ def check_criterion(criterion):
         raise ValueError("the sm_100a engine implements nn.CrossEntropyLoss() (mean reduction, no weights) only")
 
 
-def as_engine(model, args=None, max_batch=None) -> ResNetEngine:
-    """Accept the reference's nn.Module (models/ResNet.py) and move it onto the engine, or pass an engine through."""
+def as_engine(model, args=None, max_batch=None, symmetric: bool = False) -> ResNetEngine:
+    """Accept the reference's nn.Module (models/ResNet.py) and move it onto the engine, or pass an engine through.
+    symmetric=True: allocate the arenas as NVLink peer-mapped symmetric memory (fused data-parallel step)."""
     if isinstance(model, ResNetEngine):
         return model
     if not isinstance(model, torch.nn.Module):
@@ -27,7 +28,7 @@ def as_engine(model, args=None, max_batch=None) -> ResNetEngine:
     std = tuple(float(v) for v in sd.get("normalize.std", torch.tensor(CIFAR_STD)).flatten())
     image = int(getattr(args, "input_size", 32) or 32)
     mb = int(max_batch or getattr(args, "batch_size", 256) or 256)
-    eng = ResNetEngine(arch, num_classes, image, max_batch=mb, mean=mean, std=std)
+    eng = ResNetEngine(arch, num_classes, image, max_batch=mb, mean=mean, std=std, symmetric=symmetric)
     eng.load_state_dict(sd)
     eng.train(model.training)
     eng._source_module = model  # written back by sync_to_module()

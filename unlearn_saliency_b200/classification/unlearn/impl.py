@@ -3,8 +3,8 @@ from __future__ import annotations
 
 import time
 
-from ...engine import MaskedSGD
-from ..common import as_engine, check_criterion, sync_to_module
+from ...engine import DistMaskedSGD, MaskedSGD
+from ..common import as_engine, check_criterion, dist_info, sync_to_module
 
 
 def _lr_at(base_lr, epoch, milestones, gamma=0.1):
@@ -20,10 +20,16 @@ def _iterative_unlearn_impl(unlearn_iter_func):
         if getattr(args, "imagenet_arch", False):
             raise NotImplementedError("imagenet_arch branches are not served by the CIFAR-stem engine")
         decreasing_lr = list(map(int, args.decreasing_lr.split(",")))
-        engine = as_engine(model, args)
+        _, world = dist_info()
+        engine = as_engine(model, args, symmetric=world > 1)
         bits = engine.mask_bits_from_dict(mask) if mask else None  # `if mask:` RL.py:134
-        optimizer = MaskedSGD(engine, args.unlearn_lr, momentum=args.momentum, weight_decay=args.weight_decay,
-                              mask_bits=bits)  # impl.py:68-73 + RL.py:11-34
+        if world > 1 and engine.symmetric:
+            # data parallel: gradient reduce-scatter + masked SGD + weight all-gather in ONE kernel over NVLink peer memory
+            optimizer = DistMaskedSGD(engine, args.unlearn_lr, momentum=args.momentum, weight_decay=args.weight_decay,
+                                      mask_bits=bits)
+        else:
+            optimizer = MaskedSGD(engine, args.unlearn_lr, momentum=args.momentum, weight_decay=args.weight_decay,
+                                  mask_bits=bits)  # impl.py:68-73 + RL.py:11-34
         train_acc = None
         for epoch in range(0, args.unlearn_epochs):
             start_time = time.time()

@@ -46,8 +46,10 @@ def masked_step(engine, optimizer, image, target, loss_sign=1.0, want_logits=Fal
         w = image.shape[0] * world / float(n)
         if w != 1.0:
             engine.grads.mul_(w)
-        torch.distributed.all_reduce(engine.grads)
-        engine.grads.div_(world)
+        if not hasattr(optimizer, "momentum_shard"):  # plain MaskedSGD: NCCL all-reduce, then the local fused step
+            torch.distributed.all_reduce(engine.grads)
+            engine.grads.div_(world)
+        # DistMaskedSGD averages the peers' gradients inside its kernel
     optimizer.step()
     return loss, logits, target
 
