@@ -182,3 +182,47 @@ def test_apply_mask(salun_ctx):
     salun_ctx.apply_mask(dg, _dev(bits.view(np.int32)))
     O.apply_mask(g, bits)
     assert np.array_equal(dg.cpu().numpy(), g)
+
+
+def test_empty_inputs_are_noops(salun_ctx):
+    e = torch.zeros(0, device="cuda")
+    salun_ctx.saliency_accumulate_flat(e, e)
+    salun_ctx.abs_(e)
+    salun_ctx.masked_sgd_step(e, e, e, None, 0.1, 0.9, 0.0)
+    m64, bits, info = salun_ctx.topk_mask(e, 0, want_info=True)
+    assert m64.numel() == 0 and bits.numel() == 0
+    assert float(salun_ctx.grad_sumsq(e).item()) == 0.0
+
+
+def test_topk_at_sd_unet_scale_properties(salun_ctx):
+    """N = 859 520 964 (SD v1.4 U-Net): too large for the scalar oracle, so size-independent properties:
+    exactly k ones, every selected |g| >= every unselected |g|, packed bits == int64 mask, nested in the ratio."""
+    n = 859520964
+    g = torch.Generator(device="cuda").manual_seed(0)
+    a = torch.randn(n, device="cuda", generator=g)
+    a[::97] = 0.0
+    prev = None
+    for ratio in (0.3, 0.5):
+        k = int(n * ratio)
+        m64, bits, info = salun_ctx.topk_mask(a, k, want_info=True)
+        assert int(m64.sum()) == k
+        sel = m64.bool()
+        absa = a.abs()
+        assert float(absa[sel].min()) >= float(absa[~sel].max())
+        assert float(absa[sel].min()) == info.thr_value
+        assert torch.equal(salun_ctx.pack_mask(m64), bits)
+        if prev is not None:
+            assert bool((m64 >= prev).all())
+        prev = m64
+        del sel, absa
+    # fused clip + masked Adam at the same scale: masked-out coordinates bit-identical, others moved
+    p = torch.randn(n, device="cuda", generator=g)
+    p0 = p.clone()
+    m1, m2 = torch.zeros_like(p), torch.zeros_like(p)
+    ss = salun_ctx.grad_sumsq(a)
+    assert abs(float(ss.item()) - float(a.double().square().sum().item())) <= 1e-9 * float(ss.item())
+    coef = salun_ctx.clip_coef(ss, 1.0)
+    salun_ctx.masked_adam_step(p, a, m1, m2, bits, 1e-5, 0.9, 0.999, 1e-8, 0.0, 1, coef)
+    sel = prev.bool()
+    assert torch.equal(p[~sel], p0[~sel])
+    assert float((p[sel] != p0[sel]).float().mean()) > 0.99
