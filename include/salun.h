@@ -202,8 +202,9 @@ int salun_conv_wgrad_bf16(salun_ctx *ctx, const void *dy, const void *xpad, floa
  * replaces  output = model(image); loss = +/-criterion(output, target); loss.backward()
  *           Classification/generate_mask.py:35-39  (model.eval(): BN uses running statistics, loss_sign = -1)
  *           Classification/unlearn/RL.py:128-132, GA.py:113-117, FT.py:128-135  (model.train())
- * for the architecture of Classification/models/ResNet.py:180-322 with imagenet=False
- * (resnet18: ResNet.py:336, resnet34: :347).  bf16 tensor-core operands, fp32 accumulation,
+ * for the architectures of Classification/models/ResNet.py:180-322: resnet18 / resnet34 (BasicBlock :77-124, CIFAR
+ * stem, power-of-two images: implicit-GEMM path on halo-padded activations) and resnet50 / 101 / 152 (Bottleneck
+ * :127-177, CIFAR or ImageNet stem, any image size: BASELINE config 4).  bf16 tensor-core operands, fp32 accumulation,
  * fp32 master weights / gradients / BatchNorm statistics.
  *
  * Arena layout (caller-owned device buffers, fp32):
@@ -215,14 +216,15 @@ int salun_conv_wgrad_bf16(salun_ctx *ctx, const void *dy, const void *xpad, floa
  * ------------------------------------------------------------------------------------- */
 typedef struct salun_resnet salun_resnet;
 typedef struct salun_resnet_cfg {
-  int depth;       /* 18 or 34 */
+  int depth;       /* 18 / 34 (BasicBlock, CIFAR stem) ; 50 / 101 / 152 (Bottleneck, either stem) */
   int num_classes; /* arg_parser.py --num_classes */
-  int image_size;  /* 32 (CIFAR/SVHN) or 64 */
+  int image_size;  /* BasicBlock nets: 32 or 64 ; Bottleneck nets: any (e.g. 224) */
   int max_batch;   /* largest batch a call will pass */
   float mean[3];   /* NormalizeByChannelMeanStd, ResNet.py:7-28, values replaced per dataset in utils.py:115-117 */
   float std[3];
   float bn_eps;      /* 1e-5 */
   float bn_momentum; /* 0.1 */
+  int imagenet_stem; /* Bottleneck nets: 1 = 7x7/2 conv + 3x3/2 max pool (ResNet.py:224-230, imagenet=True), 0 = 3x3/1 */
 } salun_resnet_cfg;
 
 int64_t salun_resnet_param_count(const salun_resnet_cfg *cfg); /* elements of params / grads */

@@ -251,3 +251,102 @@ def unlearn_step(p, b, opt: MaskedSGD, x, y, sign: float = 1.0, emulate_bf16: bo
     loss, out, g = loss_and_grads(p, b, x, y, train=True, sign=sign, emulate_bf16=emulate_bf16)
     opt.step(g)
     return loss, out
+
+
+# ---------------------------------------------------------------------------------------------
+# Bottleneck nets (resnet50/101/152: models/ResNet.py:127-177, 358-390) with either stem (:217-230)
+# ---------------------------------------------------------------------------------------------
+BOTTLENECK_BLOCKS = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3), 152: (3, 8, 36, 3)}
+
+
+def bottleneck_param_shapes(num_classes: int = 1000, depth: int = 50, imagenet: bool = True):
+    """named_parameters() order of the reference's Bottleneck ResNets (resnet50: 161 tensors, 25 557 032 for 1000 classes)."""
+    s: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    s["conv1.weight"] = (64, 3, 7, 7) if imagenet else (64, 3, 3, 3)
+    s["bn1.weight"] = (64,)
+    s["bn1.bias"] = (64,)
+    inpl = 64
+    for li, ((planes, stride), nblk) in enumerate(zip(STAGES, BOTTLENECK_BLOCKS[depth]), start=1):
+        for b in range(nblk):
+            pre = f"layer{li}.{b}."
+            st = stride if b == 0 else 1
+            s[pre + "conv1.weight"] = (planes, inpl, 1, 1)
+            s[pre + "bn1.weight"] = (planes,)
+            s[pre + "bn1.bias"] = (planes,)
+            s[pre + "conv2.weight"] = (planes, planes, 3, 3)
+            s[pre + "bn2.weight"] = (planes,)
+            s[pre + "bn2.bias"] = (planes,)
+            s[pre + "conv3.weight"] = (planes * 4, planes, 1, 1)
+            s[pre + "bn3.weight"] = (planes * 4,)
+            s[pre + "bn3.bias"] = (planes * 4,)
+            if st != 1 or inpl != planes * 4:
+                s[pre + "downsample.0.weight"] = (planes * 4, inpl, 1, 1)
+                s[pre + "downsample.1.weight"] = (planes * 4,)
+                s[pre + "downsample.1.bias"] = (planes * 4,)
+            inpl = planes * 4
+    s["fc.weight"] = (num_classes, 2048)
+    s["fc.bias"] = (num_classes,)
+    return s
+
+
+def synth_state_bottleneck(num_classes: int = 10, seed: int = 0, depth: int = 50, imagenet: bool = True):
+    """same weight formula as synth_state, for the Bottleneck tables"""
+    g = torch.Generator().manual_seed(seed)
+    shapes = bottleneck_param_shapes(num_classes, depth, imagenet)
+    params: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for name, shp in shapes.items():
+        if len(shp) == 4:
+            params[name] = torch.randn(shp, generator=g) * math.sqrt(2.0 / (shp[0] * shp[2] * shp[3]))
+        elif name == "fc.weight":
+            params[name] = torch.randn(shp, generator=g) * math.sqrt(1.0 / shp[1])
+        elif name.endswith(".weight"):
+            params[name] = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        else:
+            params[name] = 0.1 * torch.randn(shp, generator=g)
+    buffers: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for name, shp in shapes.items():
+        if len(shp) == 1 and name.endswith(".weight"):
+            bn = name[: -len(".weight")]
+            buffers[bn + ".running_mean"] = 0.1 * torch.randn(shp[0], generator=g)
+            buffers[bn + ".running_var"] = 1.0 + 0.1 * torch.randn(shp[0], generator=g).abs()
+            buffers[bn + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+    return params, buffers
+
+
+def bottleneck_forward(p, b, x, train: bool, imagenet: bool = True, mean=CIFAR_MEAN, std=CIFAR_STD,
+                       emulate_bf16: bool = False):
+    """ResNet._forward_impl (ResNet.py:303-322) with Bottleneck.forward (:157-177); emulate_bf16 as in resnet_forward."""
+    rf = _RoundFwd.apply if emulate_bf16 else (lambda t: t)
+    rb = _RoundBoth.apply if emulate_bf16 else (lambda t: t)
+    m = torch.tensor(mean, dtype=x.dtype)[None, :, None, None]
+    s = torch.tensor(std, dtype=x.dtype)[None, :, None, None]
+    x = (x - m) * (1.0 / s) if emulate_bf16 else x.sub(m).div(s)
+    x = rf(x)
+    w = lambda k: rf(p[k])
+    if imagenet:
+        x = rb(F.relu(_bn(rb(F.conv2d(x, w("conv1.weight"), stride=2, padding=3)), p, b, "bn1", train)))
+        x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    else:
+        x = rb(F.relu(_bn(rb(F.conv2d(x, w("conv1.weight"), padding=1)), p, b, "bn1", train)))
+    for li, (planes, stride) in enumerate(STAGES, start=1):
+        nblk = sum(1 for k in p if k.startswith(f"layer{li}.") and k.endswith(".conv1.weight"))
+        for blk in range(nblk):
+            pre = f"layer{li}.{blk}."
+            st = stride if blk == 0 else 1
+            identity = x
+            out = rb(F.relu(_bn(rb(F.conv2d(x, w(pre + "conv1.weight"))), p, b, pre + "bn1", train)))
+            out = rb(F.relu(_bn(rb(F.conv2d(out, w(pre + "conv2.weight"), stride=st, padding=1)), p, b, pre + "bn2", train)))
+            out = _bn(rb(F.conv2d(out, w(pre + "conv3.weight"))), p, b, pre + "bn3", train)
+            if pre + "downsample.0.weight" in p:
+                identity = _bn(rb(F.conv2d(x, w(pre + "downsample.0.weight"), stride=st)), p, b, pre + "downsample.1", train)
+            x = rb(F.relu(out + identity))
+    x = F.adaptive_avg_pool2d(x, 1).flatten(1)
+    return F.linear(x, p["fc.weight"], p["fc.bias"])
+
+
+def bottleneck_loss_and_grads(p, b, x, y, train: bool, sign: float = 1.0, imagenet: bool = True, emulate_bf16: bool = False):
+    leaves = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in p.items())
+    out = bottleneck_forward(leaves, b, x, train, imagenet=imagenet, emulate_bf16=emulate_bf16)
+    loss = sign * F.cross_entropy(out, y)
+    grads = torch.autograd.grad(loss, list(leaves.values()))
+    return loss.detach(), out.detach(), OrderedDict(zip(leaves.keys(), grads))

@@ -173,6 +173,31 @@ def main():
     np.savez_compressed(os.path.join(HERE, "resnet18_mask.npz"), **res)
     print("resnet18_mask.npz", {k: int(v) for k, v in res.items() if k.startswith("ones")})
 
+    # ------------------------------------------------------------------ resnet50, ImageNet stem (BASELINE config 4 shape, 64x64 here)
+    p50, b50 = OC.synth_state_bottleneck(10, seed=0, depth=50, imagenet=True)
+    m50 = model_dict["resnet50"](num_classes=10, imagenet=True)
+    assert [n for n, _ in m50.named_parameters()] == list(p50.keys())
+    sd50 = OC.state_dict_of(p50, b50)
+    m50.load_state_dict(sd50)
+    g = torch.Generator().manual_seed(21)
+    x50 = torch.rand(4, 3, 64, 64, generator=g)
+    y50 = torch.randint(0, 10, (4,), generator=g)
+    out50 = {}
+    for tag, train, sign in (("eval", False, -1.0), ("train", True, 1.0)):
+        mm = model_dict["resnet50"](num_classes=10, imagenet=True)
+        mm.load_state_dict(sd50)
+        mm.train(train)
+        logits = mm(x50)
+        loss = sign * crit(logits, y50)
+        loss.backward()
+        out50[f"{tag}_logits"] = logits.detach().numpy()
+        out50[f"{tag}_loss"] = np.float32(loss.item())
+        out50[f"{tag}_gnorm"] = np.array([p.grad.norm().item() for p in mm.parameters()], dtype=np.float64)
+    out50["n_params"] = np.int64(sum(p.numel() for p in m50.parameters()))
+    out50["n_params_1000"] = np.int64(sum(p.numel() for p in model_dict["resnet50"](num_classes=1000, imagenet=True).parameters()))
+    np.savez_compressed(os.path.join(HERE, "resnet50_grad.npz"), **out50)
+    print("resnet50_grad.npz", out50["eval_loss"], out50["train_loss"], out50["n_params_1000"])
+
     # ------------------------------------------------------------------ RL epoch with the 0.5 mask
     model = model_dict["resnet18"](num_classes=10)
     model.load_state_dict(sd)

@@ -202,3 +202,42 @@ def test_resnet34_forward_backward(salun_ctx):
             rel_m, cos_m = _rel_cos(g_emu[k], g_ref[k])
             assert rel_e <= 1.4 * rel_m + 0.03 and cos_e >= cos_m - 0.05, (k, rel_e, rel_m)
     eng.close()
+
+
+@pytest.mark.parametrize("imagenet,size,n", [(True, 64, 6), (False, 32, 5)])
+def test_resnet50_forward_backward(salun_ctx, imagenet, size, n):
+    """resnet50 (Bottleneck, ResNet.py:358) with the ImageNet stem (7x7/2 + max pool, BASELINE config 4 architecture) and
+    with the CIFAR stem: flat-activation runtime (csrc/salun_resnetb.cu), same tolerance model as resnet18."""
+    from unlearn_saliency_b200.engine import ResNetEngine
+    eng = ResNetEngine("resnet50", 10, size, max_batch=8, ctx=salun_ctx, imagenet=imagenet)
+    params, buffers = OC.synth_state_bottleneck(10, seed=0, depth=50, imagenet=imagenet)
+    assert list(params.keys()) == list(eng.table.keys()) and eng.n_params == sum(v.numel() for v in params.values())
+    eng.load_state_dict(OC.state_dict_of(params, buffers))
+    g = torch.Generator().manual_seed(21)
+    x = torch.rand(n, 3, size, size, generator=g)
+    y = torch.randint(0, 10, (n,), generator=g)
+    for train, sign in ((True, 1.0), (False, -1.0)):
+        b = {k: v.clone() for k, v in buffers.items()}
+        loss_ref, logits_ref, g_ref = OC.bottleneck_loss_and_grads(params, b, x, y, train=train, sign=sign, imagenet=imagenet)
+        b2 = {k: v.clone() for k, v in buffers.items()}
+        _, logits_emu, g_emu = OC.bottleneck_loss_and_grads(params, b2, x, y, train=train, sign=sign, imagenet=imagenet,
+                                                             emulate_bf16=True)
+        eng.train(train)
+        loss, logits = eng.forward_backward(x.cuda(), y.cuda(), loss_sign=sign, want_logits=True)
+        torch.cuda.synchronize()
+        scale = logits_ref.abs().max().item()
+        err, err_emu = (logits.cpu() - logits_ref).abs().max().item(), (logits_emu - logits_ref).abs().max().item()
+        assert err <= 1.5 * err_emu + 0.02 * scale + 0.05, (train, err, err_emu, scale)
+        gd = eng.grad_dict()
+        worst = (0.0, None, 0.0)
+        for k, r in g_ref.items():
+            rel_e, cos_e = _rel_cos(gd[k].cpu(), r)
+            rel_m, cos_m = _rel_cos(g_emu[k], r)
+            if rel_e > worst[0]:
+                worst = (rel_e, k, rel_m)
+            assert rel_e <= 1.4 * rel_m + 0.03, (train, k, rel_e, rel_m)
+            assert cos_e >= cos_m - 0.05, (train, k, cos_e, cos_m)
+        print("resnet50", "imagenet" if imagenet else "cifar", "train" if train else "eval", "worst", worst, "logit err", err, err_emu)
+    sd = eng.state_dict()
+    assert set(sd.keys()) == set(OC.state_dict_of(params, buffers).keys())
+    eng.close()

@@ -18,6 +18,7 @@ class salun_resnet_cfg(C.Structure):
     _fields_ = [
         ("depth", C.c_int), ("num_classes", C.c_int), ("image_size", C.c_int), ("max_batch", C.c_int),
         ("mean", C.c_float * 3), ("std", C.c_float * 3), ("bn_eps", C.c_float), ("bn_momentum", C.c_float),
+        ("imagenet_stem", C.c_int),
     ]
 
 

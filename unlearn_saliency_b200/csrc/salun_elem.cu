@@ -435,6 +435,261 @@ void launch_col2im_s2(const __nv_bfloat16 *dcol3, const __nv_bfloat16 *dcol1, __
 }
 
 // ------------------------------------------------------------------------------------------------
+// generic flat-activation kernels (Bottleneck / ImageNet-stem nets: any H, W, stride, padding)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kET) k_im2col_flat(const __nv_bfloat16 *__restrict__ in, __nv_bfloat16 *__restrict__ col,
+                                                     long long total, int Hin, int Win, int C, int ks, int stride, int pad,
+                                                     int Hout, int Wout) {
+  const int cgs = C >> 3, taps = ks * ks;
+  for (long long i = (long long)blockIdx.x * kET + threadIdx.x; i < total; i += (long long)gridDim.x * kET) {
+    const int cg = (int)(i % cgs);
+    long long t = i / cgs;
+    const int tap = (int)(t % taps);
+    const int mo = (int)(t / taps);
+    const int n = mo / (Hout * Wout), r = mo - n * Hout * Wout, oy = r / Wout, ox = r - oy * Wout;
+    const int ky = tap / ks, kx = tap - ky * ks;
+    const int y = oy * stride + ky - pad, x = ox * stride + kx - pad;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (y >= 0 && y < Hin && x >= 0 && x < Win)
+      v = *reinterpret_cast<const uint4 *>(in + ((size_t)(n * Hin + y) * Win + x) * C + cg * 8);
+    *reinterpret_cast<uint4 *>(col + ((size_t)mo * taps + tap) * C + cg * 8) = v;
+  }
+}
+void launch_im2col_flat(const __nv_bfloat16 *in_flat, __nv_bfloat16 *col, int n_img, int Hin, int Win, int C, int ks,
+                        int stride, int pad, int Hout, int Wout, cudaStream_t st) {
+  const long long total = (long long)n_img * Hout * Wout * ks * ks * (C >> 3);
+  long long g = (total + kET - 1) / kET;
+  if (g > 148 * 16) g = 148 * 16;
+  { k_im2col_flat<<<(int)g, kET, 0, st>>>(in_flat, col, total, Hin, Win, C, ks, stride, pad, Hout, Wout); ++::salun::g_launch_count; }
+}
+
+__global__ void __launch_bounds__(kET) k_stem_im2col_generic(const float *__restrict__ x, __nv_bfloat16 *__restrict__ col,
+                                                             long long total, int Hin, int Win, int ks, int stride,
+                                                             int pad, int Hout, int Wout, int kcp, float m0, float m1,
+                                                             float m2, float i0, float i1, float i2) {
+  // one thread per (output pixel, 8-column group of the patch row): columns j = tap*3 + c
+  const int groups = kcp >> 3, kc = ks * ks * 3;
+  for (long long i = (long long)blockIdx.x * kET + threadIdx.x; i < total; i += (long long)gridDim.x * kET) {
+    const int gidx = (int)(i % groups);
+    const int mo = (int)(i / groups);
+    const int n = mo / (Hout * Wout), r = mo - n * Hout * Wout, oy = r / Wout, ox = r - oy * Wout;
+    float f[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int j = gidx * 8 + q;
+      float v = 0.f;
+      if (j < kc) {
+        const int tap = j / 3, c = j - tap * 3;
+        const int ky = tap / ks, kx = tap - ky * ks;
+        const int y = oy * stride + ky - pad, xx = ox * stride + kx - pad;
+        if (y >= 0 && y < Hin && xx >= 0 && xx < Win) {
+          const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), inv = c == 0 ? i0 : (c == 1 ? i1 : i2);
+          v = (x[((size_t)(n * 3 + c) * Hin + y) * Win + xx] - mean) * inv;
+        }
+      }
+      f[q] = v;
+    }
+    st8(col + (size_t)mo * kcp + gidx * 8, f);
+  }
+}
+void launch_stem_im2col_generic(const float *x, __nv_bfloat16 *col, int n_img, int Hin, int Win, int ks, int stride,
+                                int pad, int Hout, int Wout, int kcp, const float *mean3, const float *inv_std3,
+                                cudaStream_t st) {
+  const long long total = (long long)n_img * Hout * Wout * (kcp >> 3);
+  long long g = (total + kET - 1) / kET;
+  if (g > 148 * 16) g = 148 * 16;
+  { k_stem_im2col_generic<<<(int)g, kET, 0, st>>>(x, col, total, Hin, Win, ks, stride, pad, Hout, Wout, kcp, mean3[0],
+                                                  mean3[1], mean3[2], inv_std3[0], inv_std3[1], inv_std3[2]); ++::salun::g_launch_count; }
+}
+
+__global__ void __launch_bounds__(kET) k_col2im_flat(const __nv_bfloat16 *__restrict__ dcol,
+                                                     const __nv_bfloat16 *__restrict__ addend,
+                                                     __nv_bfloat16 *__restrict__ dx, long long total, int Hin, int Win,
+                                                     int C, int ks, int stride, int pad, int Hout, int Wout) {
+  const int cgs = C >> 3, taps = ks * ks;
+  for (long long i = (long long)blockIdx.x * kET + threadIdx.x; i < total; i += (long long)gridDim.x * kET) {
+    const int cg = (int)(i % cgs);
+    const int m = (int)(i / cgs);
+    const int n = m / (Hin * Win), r = m - n * Hin * Win, y = r / Win, x = r - y * Win;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (addend) ld8(addend + (size_t)m * C + cg * 8, acc);
+    for (int ky = 0; ky < ks; ++ky) {
+      const int ty = y + pad - ky;
+      if (ty < 0 || ty % stride != 0) continue;
+      const int oy = ty / stride;
+      if (oy >= Hout) continue;
+      for (int kx = 0; kx < ks; ++kx) {
+        const int tx = x + pad - kx;
+        if (tx < 0 || tx % stride != 0) continue;
+        const int ox = tx / stride;
+        if (ox >= Wout) continue;
+        const int mo = (n * Hout + oy) * Wout + ox;
+        float t[8];
+        ld8(dcol + ((size_t)mo * taps + ky * ks + kx) * C + cg * 8, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += t[j];
+      }
+    }
+    st8(dx + (size_t)m * C + cg * 8, acc);
+  }
+}
+void launch_col2im_flat(const __nv_bfloat16 *dcol, const __nv_bfloat16 *addend, __nv_bfloat16 *dx, int n_img, int Hin,
+                        int Win, int C, int ks, int stride, int pad, int Hout, int Wout, cudaStream_t st) {
+  const long long total = (long long)n_img * Hin * Win * (C >> 3);
+  long long g = (total + kET - 1) / kET;
+  if (g > 148 * 16) g = 148 * 16;
+  { k_col2im_flat<<<(int)g, kET, 0, st>>>(dcol, addend, dx, total, Hin, Win, C, ks, stride, pad, Hout, Wout); ++::salun::g_launch_count; }
+}
+
+__global__ void __launch_bounds__(kET) k_bn_apply_flat(BnFwd a, BnFwd b, int has_b, const __nv_bfloat16 *__restrict__ resid,
+                                                       __nv_bfloat16 *__restrict__ out, uint8_t *__restrict__ rmask, int M,
+                                                       int C, int relu, int train, float eps, float momentum) {
+  extern __shared__ float smf[];
+  float *sc_a = smf, *sh_a = smf + C, *sc_b = smf + 2 * C, *sh_b = smf + 3 * C;
+  bn_prologue(a, sc_a, sh_a, C, train, (double)M, eps, momentum);
+  if (has_b) bn_prologue(b, sc_b, sh_b, C, train, (double)M, eps, momentum);
+  __syncthreads();
+  const int tpr = C >> 3;
+  // C up to 2048 (tpr 256): one row per pass when tpr == kET, several rows otherwise
+  const int rpb = kET / tpr;
+  const int rl = threadIdx.x / tpr, c0 = (threadIdx.x - rl * tpr) * 8;
+  for (int m = blockIdx.x * rpb + rl; m < M; m += gridDim.x * rpb) {
+    float v[8], t[8];
+    const size_t o = (size_t)m * C + c0;
+    ld8(a.y + o, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], sc_a[c0 + i], sh_a[c0 + i]);
+    if (has_b) {
+      ld8(b.y + o, t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += fmaf(t[i], sc_b[c0 + i], sh_b[c0 + i]);
+    }
+    if (resid) {
+      ld8(resid + o, t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += t[i];
+    }
+    if (relu) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    st8(out + o, v);
+    if (rmask) {
+      uint32_t bits = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << i;
+      rmask[(size_t)m * (C >> 3) + (c0 >> 3)] = (uint8_t)bits;
+    }
+  }
+}
+void launch_bn_apply_flat(const BnFwd &a, const BnFwd *b, const __nv_bfloat16 *resid_flat, __nv_bfloat16 *out_flat,
+                          uint8_t *relu_mask_out, int M, int C, int relu, int train, float eps, float momentum,
+                          cudaStream_t st) {
+  BnFwd bb = b ? *b : a;
+  { k_bn_apply_flat<<<elem_grid(M, C), kET, 4 * C * sizeof(float), st>>>(a, bb, b != nullptr, resid_flat, out_flat,
+                                                                       relu_mask_out, M, C, relu, train, eps, momentum); ++::salun::g_launch_count; }
+}
+
+__global__ void __launch_bounds__(kET) k_maxpool_fwd(const __nv_bfloat16 *__restrict__ in, __nv_bfloat16 *__restrict__ out,
+                                                     uint8_t *__restrict__ argmax, long long total, int Hin, int Win,
+                                                     int C) {
+  const int Ho = (Hin + 2 - 3) / 2 + 1, Wo = (Win + 2 - 3) / 2 + 1, cgs = C >> 3;
+  for (long long i = (long long)blockIdx.x * kET + threadIdx.x; i < total; i += (long long)gridDim.x * kET) {
+    const int cg = (int)(i % cgs);
+    const int mo = (int)(i / cgs);
+    const int n = mo / (Ho * Wo), r = mo - n * Ho * Wo, oy = r / Wo, ox = r - oy * Wo;
+    float best[8];
+    int arg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      best[j] = -INFINITY;
+      arg[j] = 0;
+    }
+    for (int ky = 0; ky < 3; ++ky) {
+      const int y = oy * 2 + ky - 1;
+      if (y < 0 || y >= Hin) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int x = ox * 2 + kx - 1;
+        if (x < 0 || x >= Win) continue;
+        float t[8];
+        ld8(in + ((size_t)(n * Hin + y) * Win + x) * C + cg * 8, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (t[j] > best[j]) {  // first maximum in scan order wins, like torch's max_pool2d
+            best[j] = t[j];
+            arg[j] = ky * 3 + kx;
+          }
+      }
+    }
+    st8(out + (size_t)mo * C + cg * 8, best);
+    uint2 packed;
+    packed.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+    packed.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+    *reinterpret_cast<uint2 *>(argmax + (size_t)mo * C + cg * 8) = packed;
+  }
+}
+void launch_maxpool_fwd(const __nv_bfloat16 *in_flat, __nv_bfloat16 *out_flat, uint8_t *argmax, int n_img, int Hin,
+                        int Win, int C, cudaStream_t st) {
+  const int Ho = (Hin + 2 - 3) / 2 + 1, Wo = (Win + 2 - 3) / 2 + 1;
+  const long long total = (long long)n_img * Ho * Wo * (C >> 3);
+  long long g = (total + kET - 1) / kET;
+  if (g > 148 * 16) g = 148 * 16;
+  { k_maxpool_fwd<<<(int)g, kET, 0, st>>>(in_flat, out_flat, argmax, total, Hin, Win, C); ++::salun::g_launch_count; }
+}
+__global__ void __launch_bounds__(kET) k_maxpool_bwd(const __nv_bfloat16 *__restrict__ dout,
+                                                     const uint8_t *__restrict__ argmax, __nv_bfloat16 *__restrict__ dx,
+                                                     long long total, int Hin, int Win, int C) {
+  const int Ho = (Hin + 2 - 3) / 2 + 1, Wo = (Win + 2 - 3) / 2 + 1, cgs = C >> 3;
+  for (long long i = (long long)blockIdx.x * kET + threadIdx.x; i < total; i += (long long)gridDim.x * kET) {
+    const int cg = (int)(i % cgs);
+    const int m = (int)(i / cgs);
+    const int n = m / (Hin * Win), r = m - n * Hin * Win, y = r / Win, x = r - y * Win;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int ky = 0; ky < 3; ++ky) {
+      const int ty = y + 1 - ky;
+      if (ty < 0 || (ty & 1) || (ty >> 1) >= Ho) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int tx = x + 1 - kx;
+        if (tx < 0 || (tx & 1) || (tx >> 1) >= Wo) continue;
+        const int mo = (n * Ho + (ty >> 1)) * Wo + (tx >> 1);
+        const uint2 a = *reinterpret_cast<const uint2 *>(argmax + (size_t)mo * C + cg * 8);
+        float t[8];
+        ld8(dout + (size_t)mo * C + cg * 8, t);
+        const int want = ky * 3 + kx;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t w = j < 4 ? a.x : a.y;
+          if ((int)((w >> (8 * (j & 3))) & 0xffu) == want) acc[j] += t[j];
+        }
+      }
+    }
+    st8(dx + (size_t)m * C + cg * 8, acc);
+  }
+}
+void launch_maxpool_bwd(const __nv_bfloat16 *dout_flat, const uint8_t *argmax, __nv_bfloat16 *dx_flat, int n_img, int Hin,
+                        int Win, int C, cudaStream_t st) {
+  const long long total = (long long)n_img * Hin * Win * (C >> 3);
+  long long g = (total + kET - 1) / kET;
+  if (g > 148 * 16) g = 148 * 16;
+  { k_maxpool_bwd<<<(int)g, kET, 0, st>>>(dout_flat, argmax, dx_flat, total, Hin, Win, C); ++::salun::g_launch_count; }
+}
+__global__ void k_avgpool_flat(const __nv_bfloat16 *__restrict__ act, float *__restrict__ pooled, int n_img, int pix, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_img * C) return;
+  const int n = i / C, c = i - n * C;
+  float s = 0.f;
+  for (int p = 0; p < pix; ++p) s += __bfloat162float(act[((size_t)n * pix + p) * C + c]);
+  pooled[i] = s / (float)pix;
+}
+void launch_avgpool_flat(const __nv_bfloat16 *act_flat, float *pooled, int n_img, int pix, int C, cudaStream_t st) {
+  { k_avgpool_flat<<<(n_img * C + 255) / 256, 256, 0, st>>>(act_flat, pooled, n_img, pix, C); ++::salun::g_launch_count; }
+}
+
+// ------------------------------------------------------------------------------------------------
 // weight re-layout (fp32 master, native [Cout][tap][Cin]) -> bf16 GEMM operands
 // ------------------------------------------------------------------------------------------------
 __global__ void k_prep_w_fwd(const float *__restrict__ w, __nv_bfloat16 *__restrict__ out, int Cout, int kc, int kcp) {

@@ -67,6 +67,28 @@ void launch_prep_w_fwd(const float *w, __nv_bfloat16 *out, int Cout, int kc, int
 void launch_prep_w_dgrad_s1(const float *w, __nv_bfloat16 *out, int Cout, int Cin, int taps, cudaStream_t st);
 void launch_prep_w_transpose(const float *w, __nv_bfloat16 *out, int Cout, int kc, cudaStream_t st);
 
+// ---- generic (any spatial size / stride / padding) kernels on FLAT NHWC activations [n*H*W][C]: Bottleneck nets ----
+// col[Mout][ks*ks*C] (tap-major) from a flat activation; out-of-image taps are zero
+void launch_im2col_flat(const __nv_bfloat16 *in_flat, __nv_bfloat16 *col, int n_img, int Hin, int Win, int C, int ks,
+                        int stride, int pad, int Hout, int Wout, cudaStream_t st);
+// stem of any geometry: x fp32 NCHW -> normalise -> col[Mout][kcp] (kc = ks*ks*3 valid, tap-major then channel)
+void launch_stem_im2col_generic(const float *x, __nv_bfloat16 *col, int n_img, int Hin, int Win, int ks, int stride,
+                                int pad, int Hout, int Wout, int kcp, const float *mean3, const float *inv_std3,
+                                cudaStream_t st);
+// dx[Min][C] = col2im(dcol[Mout][ks*ks*C]) (+ addend[Min][C]); gather form, deterministic
+void launch_col2im_flat(const __nv_bfloat16 *dcol, const __nv_bfloat16 *addend, __nv_bfloat16 *dx, int n_img, int Hin,
+                        int Win, int C, int ks, int stride, int pad, int Hout, int Wout, cudaStream_t st);
+// out = relu?(bn_a(y_a) [+ bn_b(y_b)] [+ resid_flat]) written FLAT
+void launch_bn_apply_flat(const BnFwd &a, const BnFwd *b, const __nv_bfloat16 *resid_flat, __nv_bfloat16 *out_flat,
+                          uint8_t *relu_mask_out, int M, int C, int relu, int train, float eps, float momentum,
+                          cudaStream_t st);
+// 3x3 / stride 2 / pad 1 max pooling (nn.MaxPool2d(3, 2, 1), ResNet.py:229) and its backward (argmax offsets kept)
+void launch_maxpool_fwd(const __nv_bfloat16 *in_flat, __nv_bfloat16 *out_flat, uint8_t *argmax, int n_img, int Hin,
+                        int Win, int C, cudaStream_t st);
+void launch_maxpool_bwd(const __nv_bfloat16 *dout_flat, const uint8_t *argmax, __nv_bfloat16 *dx_flat, int n_img, int Hin,
+                        int Win, int C, cudaStream_t st);
+void launch_avgpool_flat(const __nv_bfloat16 *act_flat, float *pooled, int n_img, int pix, int C, cudaStream_t st);
+
 // head
 void launch_avgpool(const __nv_bfloat16 *act_padded, float *pooled, int n_img, int H, int W, int C, cudaStream_t st);
 void launch_fc_ce(const float *pooled, const float *w, const float *b, const int64_t *labels, float *logits,

@@ -21,6 +21,7 @@
 
 #include "salun_elem.cuh"
 #include "salun_gemm.cuh"
+#include "salun_resnetb.cuh"
 
 namespace salun {
 
@@ -62,6 +63,7 @@ struct ConvMaps {
 using namespace salun;
 
 struct salun_resnet {
+  salun::FlatNet *flat;  // non-null: Bottleneck runtime (salun_resnetb.cu); everything below is unused then
   salun_ctx *ctx;
   salun_resnet_cfg cfg;
   float *params, *grads, *rmean, *rvar;
@@ -576,6 +578,7 @@ extern "C" {
 
 int64_t salun_resnet_param_count(const salun_resnet_cfg *cfg) {
   if (!cfg) return -1;
+  if (cfg->depth >= 50) return flatnet_param_count(cfg, nullptr);
   std::vector<ConvL> c;
   std::vector<Act> a;
   std::vector<Block> b;
@@ -587,6 +590,10 @@ int64_t salun_resnet_param_count(const salun_resnet_cfg *cfg) {
 
 int64_t salun_resnet_bn_channels(const salun_resnet_cfg *cfg) {
   if (!cfg) return -1;
+  if (cfg->depth >= 50) {
+    int64_t nbn = -1;
+    return flatnet_param_count(cfg, &nbn) < 0 ? -1 : nbn;
+  }
   std::vector<ConvL> c;
   std::vector<Act> a;
   std::vector<Block> b;
@@ -602,6 +609,23 @@ int salun_resnet_create(salun_ctx *ctx, const salun_resnet_cfg *cfg, float *para
   SALUN_REQUIRE(cfg->max_batch > 0 && cfg->num_classes > 0, "max_batch and num_classes must be positive");
   SALUN_CUDA_OK(cudaSetDevice(ctx->device));
   salun_resnet *net = new salun_resnet();
+  net->flat = nullptr;
+  if (cfg->depth >= 50) {
+    if (!(cfg->depth == 50 || cfg->depth == 101 || cfg->depth == 152)) {
+      delete net;
+      set_error("salun_resnet: depth %d not supported", cfg->depth);
+      return SALUN_ERR_UNSUPPORTED;
+    }
+    net->ctx = ctx;
+    net->cfg = *cfg;
+    int rcf = flatnet_create(ctx, cfg, params, grads, running_mean, running_var, &net->flat);
+    if (rcf) {
+      delete net;
+      return rcf;
+    }
+    *out = net;
+    return SALUN_OK;
+  }
   net->ctx = ctx;
   net->cfg = *cfg;
   net->params = params;
@@ -729,6 +753,11 @@ int salun_resnet_create(salun_ctx *ctx, const salun_resnet_cfg *cfg, float *para
 
 int salun_resnet_destroy(salun_resnet *net) {
   if (!net) return SALUN_OK;
+  if (net->flat) {
+    flatnet_destroy(net->flat);
+    delete net;
+    return SALUN_OK;
+  }
   cudaSetDevice(net->ctx->device);
   for (void *p : net->allocs) cudaFree(p);
   if (net->wgred_host) cudaFreeHost(net->wgred_host);
@@ -745,6 +774,7 @@ int salun_resnet_forward_backward(salun_resnet *net, const float *x, const int64
   SALUN_REQUIRE(n > 0 && n <= net->cfg.max_batch, "batch size out of range");
   SALUN_CUDA_OK(cudaSetDevice(net->ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
+  if (net->flat) return flatnet_forward_backward(net->flat, x, labels, n, train, loss_sign, loss_dev, logits_dev, st);
   TRY(forward_impl(net, x, labels, n, train, loss_sign, loss_dev, logits_dev, true, st));
   return backward_impl(net, st);
 }
@@ -753,6 +783,7 @@ int salun_resnet_forward(salun_resnet *net, const float *x, int n, float *logits
   SALUN_REQUIRE(net && x && logits_dev, "NULL argument");
   SALUN_REQUIRE(n > 0 && n <= net->cfg.max_batch, "batch size out of range");
   SALUN_CUDA_OK(cudaSetDevice(net->ctx->device));
+  if (net->flat) return flatnet_forward(net->flat, x, n, logits_dev, (cudaStream_t)stream);
   int rc = forward_impl(net, x, nullptr, n, 0, 1.f, nullptr, logits_dev, false, (cudaStream_t)stream);
   net->fwd_done = false;
   return rc;

@@ -23,12 +23,40 @@ from .tail import SalunContext, _ptr, _stream, mask_words
 
 CIFAR_MEAN = (0.4914, 0.4822, 0.4465)  # Classification/models/ResNet.py:214-216
 CIFAR_STD = (0.2470, 0.2435, 0.2616)
-_STAGE_BLOCKS = {18: (2, 2, 2, 2), 34: (3, 4, 6, 3)}
-_ARCH_DEPTH = {"resnet18": 18, "resnet34": 34}
+_STAGE_BLOCKS = {18: (2, 2, 2, 2), 34: (3, 4, 6, 3), 50: (3, 4, 6, 3), 101: (3, 4, 23, 3), 152: (3, 8, 36, 3)}
+_ARCH_DEPTH = {"resnet18": 18, "resnet34": 34, "resnet50": 50, "resnet101": 101, "resnet152": 152}
 
 
-def resnet_param_table(depth: int, num_classes: int) -> "OrderedDict[str, Tuple[int, ...]]":
-    """named_parameters() order and PyTorch shapes of the reference's BasicBlock ResNets (ResNet.py:180-260)."""
+def _bottleneck_param_table(depth: int, num_classes: int, imagenet: bool) -> "OrderedDict[str, Tuple[int, ...]]":
+    """Bottleneck ResNets (ResNet.py:127-177): conv1 1x1, conv2 3x3 (carries the stride), conv3 1x1 x4, projection shortcut."""
+    s: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    s["conv1.weight"] = (64, 3, 7, 7) if imagenet else (64, 3, 3, 3)
+    s["bn1.weight"] = (64,)
+    s["bn1.bias"] = (64,)
+    inpl = 64
+    for li, (planes, nblk) in enumerate(zip((64, 128, 256, 512), _STAGE_BLOCKS[depth]), start=1):
+        for b in range(nblk):
+            pre = f"layer{li}.{b}."
+            stride = 2 if (b == 0 and li > 1) else 1
+            for nm, shp in (("conv1", (planes, inpl, 1, 1)), ("conv2", (planes, planes, 3, 3)), ("conv3", (planes * 4, planes, 1, 1))):
+                s[pre + nm + ".weight"] = shp
+                bn = "bn" + nm[-1]
+                s[pre + bn + ".weight"] = (shp[0],)
+                s[pre + bn + ".bias"] = (shp[0],)
+            if stride != 1 or inpl != planes * 4:
+                s[pre + "downsample.0.weight"] = (planes * 4, inpl, 1, 1)
+                s[pre + "downsample.1.weight"] = (planes * 4,)
+                s[pre + "downsample.1.bias"] = (planes * 4,)
+            inpl = planes * 4
+    s["fc.weight"] = (num_classes, 2048)
+    s["fc.bias"] = (num_classes,)
+    return s
+
+
+def resnet_param_table(depth: int, num_classes: int, imagenet: bool = False) -> "OrderedDict[str, Tuple[int, ...]]":
+    """named_parameters() order and PyTorch shapes of the reference's ResNets (ResNet.py:180-260)."""
+    if depth >= 50:
+        return _bottleneck_param_table(depth, num_classes, imagenet)
     s: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
     s["conv1.weight"] = (64, 3, 3, 3)
     s["bn1.weight"] = (64,)
@@ -64,20 +92,23 @@ class ResNetEngine:
 
     def __init__(self, arch: str = "resnet18", num_classes: int = 10, image_size: int = 32, max_batch: int = 256,
                  mean=CIFAR_MEAN, std=CIFAR_STD, device=None, ctx: Optional[SalunContext] = None,
-                 symmetric: bool = False):
+                 symmetric: bool = False, imagenet: bool = False):
         """symmetric=True allocates the parameter / gradient arenas as torch symmetric memory (NVLink peer-mapped), which
         DistMaskedSGD needs for its fused reduce-scatter + update + all-gather kernel."""
         if arch not in _ARCH_DEPTH:
             raise ValueError(f"arch {arch!r} is not served by the sm_100a engine (supported: {sorted(_ARCH_DEPTH)})")
         self.arch, self.depth = arch, _ARCH_DEPTH[arch]
+        if imagenet and self.depth < 50:
+            raise ValueError("the ImageNet stem (imagenet=True, ResNet.py:224-230) is served for resnet50/101/152")
+        self.imagenet = bool(imagenet)
         self.num_classes, self.image_size, self.max_batch = num_classes, image_size, max_batch
         self.ctx = ctx if ctx is not None else SalunContext(device)
         self.device = self.ctx.device
         self._lib = _lib.lib()
         self.mean, self.std = tuple(float(v) for v in mean), tuple(float(v) for v in std)
         self.cfg = _lib.salun_resnet_cfg(self.depth, num_classes, image_size, max_batch, (C.c_float * 3)(*self.mean),
-                                         (C.c_float * 3)(*self.std), 1e-5, 0.1)
-        self.table = resnet_param_table(self.depth, num_classes)
+                                         (C.c_float * 3)(*self.std), 1e-5, 0.1, 1 if imagenet else 0)
+        self.table = resnet_param_table(self.depth, num_classes, self.imagenet)
         self.n_params = int(self._lib.salun_resnet_param_count(C.byref(self.cfg)))
         n_bn = int(self._lib.salun_resnet_bn_channels(C.byref(self.cfg)))
         if self.n_params != sum(math.prod(s) for s in self.table.values()):
