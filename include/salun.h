@@ -176,6 +176,11 @@ int salun_masked_adam_step(salun_ctx *ctx, float *p, const float *g, float *m1, 
 int salun_gemm_bf16_tn(salun_ctx *ctx, const void *A, const void *B, float *out_f32, void *out_bf16,
                        int64_t M, int64_t N, int64_t K, void *stream);
 
+/* Same contract through the CTA-pair kernel (tcgen05 cta_group::2, 256 x {128,256} tiles shared by two SMs);
+ * N % 128 == 0. */
+int salun_gemm2_bf16_tn(salun_ctx *ctx, const void *A, const void *B, float *out_f32, void *out_bf16,
+                        int64_t M, int64_t N, int64_t K, void *stream);
+
 /* Stride-1 convolution forward, ksize 3 (pad 1) or 1 (pad 0):
  *   y[batch*H*W][Cout] = conv(xpad, wk)        (y_bf16 and/or y_f32; either may be NULL, not both)
  *   stat_sum / stat_sq: optional fp32 [(batch*H*W/128)*4][Cout] per-tile column sums of y and y^2

@@ -38,6 +38,22 @@ def test_gemm_tn(salun_ctx, M, N, K):
     torch.testing.assert_close(outb.float(), ref, rtol=8e-3, atol=2e-2 * K ** 0.5 / 8)
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 128, 64), (256, 256, 128), (512, 128, 576), (4096, 512, 4608),
+                                    (200, 128, 64), (8192, 256, 1152), (16384, 1024, 1024), (300, 384, 192)])
+def test_gemm2_tn(salun_ctx, M, N, K):
+    """CTA-pair kernel (tcgen05 cta_group::2): same contract, including ragged M and an odd number of 128-row tiles."""
+    torch.manual_seed(M + N + K + 1)
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = torch.randn(N, K, device="cuda").bfloat16()
+    out = torch.full((M, N), float("nan"), device="cuda")
+    outb = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    check(_lib.lib().salun_gemm2_bf16_tn(salun_ctx.handle, _p(A), _p(B), _p(out), _p(outb), M, N, K, _st()), "gemm2")
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().t()
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-3 * K ** 0.5 / 8)
+    torch.testing.assert_close(outb.float(), ref, rtol=8e-3, atol=2e-2 * K ** 0.5 / 8)
+
+
 def _pad_nhwc(x_nchw):
     """fp32 NCHW -> bf16 halo-padded NHWC [N][H+2][W+2][C]"""
     return F.pad(x_nchw.permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1)).contiguous().bfloat16()

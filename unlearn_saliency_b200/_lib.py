@@ -60,6 +60,7 @@ _SIGNATURES = {
     "salun_masked_adam_step": [_P, _P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I64, _P, _P],
     # tcgen05 GEMM / convolution entry points (salun_gemm.cu)
     "salun_gemm_bf16_tn": [_P, _P, _P, _P, _P, _I64, _I64, _I64, _P],
+    "salun_gemm2_bf16_tn": [_P, _P, _P, _P, _P, _I64, _I64, _I64, _P],
     "salun_conv_fwd_bf16": [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P],
     "salun_conv_rw_fwd_bf16": [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P],
     "salun_conv_wgrad_bf16": [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P],

@@ -481,6 +481,198 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 }
 
 // =================================================================================================
+// k_gemm2: CTA-PAIR variant of k_conv_gemm_p (cta_group::2).  A cluster of two CTAs (two SMs of one TPC) computes a
+// 256 x BN tile: CTA r holds rows [r*128, +128) of A and rows [r*BN/2, +BN/2) of B in its own shared memory, the leader
+// (rank 0) issues tcgen05.mma.cta_group::2 (M = 256) into both CTAs' tensor memory.  Per CTA a k-block moves
+// 16 KB (A) + BN/2 * 128 B (half of B) through the L2->SM port for 128 x BN x 64 MACs: half the B bytes of the 1-CTA
+// kernel, which that port bounds (profiles/README.md section 3).
+//   full[s]   : leader's barrier; both CTAs' TMA loads signal it (peer-bit-masked address), leader arrives with expect_tx
+//   empty[s]  : one per CTA; the leader's tcgen05.commit multicasts the arrive to both
+//   tfull[a]  : one per CTA (multicast commit); tempty[a]: leader's, 8 arrivals (4 epilogue warps x 2 CTAs)
+// =================================================================================================
+template <int BN, int kStages>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+k_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvGemmArgs a,
+        int m_pairs, int n_tiles) {
+  constexpr uint32_t kABytes = kBM * kBK * 2;
+  constexpr uint32_t kBBytes = (BN / 2) * kBK * 2;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kStages;
+  const uint32_t tfull0 = empty0 + 8 * kStages, tempty0 = tfull0 + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int total_tiles = m_pairs * n_tiles;
+  constexpr uint32_t kTmemCols = 2 * BN;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull0 + 8 * i, 1);
+      mbar_init(tempty0 + 8 * i, 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem2_alloc(smem_u32(tmem_slot), kTmemCols);
+    tmem2_relinquish();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs' barriers initialised and tensor memory allocated before anyone signals a peer
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane < 2) {
+      uint32_t it = 0;
+      const int hw = a.H * a.W;
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
+        const int m_pair = tile / n_tiles, n_tile = tile - m_pair * n_tiles;
+        const int m0 = m_pair * 256 + (int)rank * 128;
+        int n0 = 0, y0 = 0;
+        if (a.mode_a == 1) {
+          n0 = m0 / hw;
+          y0 = (m0 - n0 * hw) / a.W;
+        }
+        int cb = 0, kx = 0, ky = 0;
+        for (int kb = 0; kb < a.num_k_blocks; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          const uint32_t sa = smem_base + s * kStageBytes, sb = sa + kABytes;
+          if (lane == 0) {
+            if (leader) mbar_arrive_expect_tx(full0 + 8 * s, 2 * kStageBytes);  // both CTAs' bytes land on this barrier
+            if (a.mode_a == 1)
+              tma2_load_4d(sa, &tmA, full0 + 8 * s, cb * kBK, a.tap_x0 + kx, a.tap_y0 + y0 + ky, n0);
+            else
+              tma2_load_2d(sa, &tmA, full0 + 8 * s, kb * kBK, m0);
+          } else {
+            tma2_load_2d(sb, &tmB, full0 + 8 * s, kb * kBK, n_tile * BN + (int)rank * (BN / 2));
+          }
+          if (++cb == a.cin_blocks) {
+            cb = 0;
+            if (++kx == a.kw) {
+              kx = 0;
+              ++ky;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
+      const uint32_t dhi = umma_desc_hi_sw128(1024), a_lo0 = umma_desc_lo(smem_base, 16);
+      uint32_t it = 0, ti = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs, ++ti) {
+        const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
+        mbar_wait(tempty0 + 8 * acc, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < a.num_k_blocks; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t alo = a_lo0 + s * (kStageBytes >> 4), blo = alo + (kABytes >> 4);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            tc2_mma_f16(d_tmem, umma_desc_pack(alo + 2 * k, dhi), umma_desc_pack(blo + 2 * k, dhi), idesc, (kb | k) != 0);
+          tc2_commit_mc(empty0 + 8 * s, 3);  // frees this stage in BOTH CTAs
+        }
+        tc2_commit_mc(tfull0 + 8 * acc, 3);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    uint32_t ti = 0;
+    for (int tile = pair; tile < total_tiles; tile += npairs, ++ti) {
+      const int m_pair = tile / n_tiles, n_tile = tile - m_pair * n_tiles;
+      const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
+      mbar_wait(tfull0 + 8 * acc, aph);
+      tc_fence_after();
+      const int row = m_pair * 256 + (int)rank * 128 + q * 32 + lane;
+      const bool row_ok = row < a.M;
+      const int stat_row = (m_pair * 2 + (int)rank) * 4 + q;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, r);
+        tc_wait_ld();
+        const int col0 = n_tile * BN + c * 32;
+        if (col0 < a.N) {
+          if (a.stat_sum) {
+            float v[32], w[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = row_ok ? __uint_as_float(r[j]) : 0.f;
+              v[j] = x;
+              w[j] = x * x;
+            }
+            float s1 = warp_transpose_reduce(v, lane);
+            float s2 = warp_transpose_reduce(w, lane);
+            if (col0 + lane < a.N) {
+              a.stat_sum[(size_t)stat_row * a.N + col0 + lane] = s1;
+              a.stat_sq[(size_t)stat_row * a.N + col0 + lane] = s2;
+            }
+          }
+          if (row_ok && a.addend) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.addend + (size_t)row * a.ld_out + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 v = src[j];
+              const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 t = __bfloat1622float2(h[i]);
+                r[8 * j + 2 * i] = __float_as_uint(__uint_as_float(r[8 * j + 2 * i]) + t.x);
+                r[8 * j + 2 * i + 1] = __float_as_uint(__uint_as_float(r[8 * j + 2 * i + 1]) + t.y);
+              }
+            }
+          }
+          if (row_ok) {
+            if (a.out_bf16) {
+              uint4 *dst = reinterpret_cast<uint4 *>(a.out_bf16 + (size_t)row * a.ld_out + col0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 v;
+                v.x = pack_bf16x2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]));
+                v.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+                v.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+                v.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+                dst[j] = v;
+              }
+            }
+            if (a.out_f32) {
+              uint4 *dst = reinterpret_cast<uint4 *>(a.out_f32 + (size_t)row * a.ld_out + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dst[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      if (lane == 0) mbar_arrive_remote(tempty0 + 8 * acc, 0);  // the leader's MMA thread owns the accumulator hand-back
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();  // no CTA may exit (or free tensor memory) while its peer can still signal it
+  if (warp == 1) tmem2_dealloc(tmem_base, kTmemCols);
+}
+
+// =================================================================================================
 // k_conv_rw: persistent stride-1 3x3 convolution with the weight slice RESIDENT in shared memory.
 //
 // The large-image layers (layer1: 64 ch @32x32, layer2: 128 ch @16x16) are bound by L2->smem operand traffic in
@@ -990,6 +1182,53 @@ static int launch_conv_gemm_p_t(const CUtensorMap &tmA, const CUtensorMap &tmB, 
   return SALUN_OK;
 }
 
+template <int BN, int S>
+static int launch_gemm2_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvGemmArgs &a, cudaStream_t st) {
+  constexpr size_t smem = (size_t)S * (kBM * kBK * 2 + (BN / 2) * kBK * 2) + 1024 + 256;
+  static bool attr_set = false;
+  static int num_sms = 0;
+  if (!attr_set) {
+    SALUN_CUDA_OK(cudaFuncSetAttribute(k_gemm2<BN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0;
+    SALUN_CUDA_OK(cudaGetDevice(&dev));
+    SALUN_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    attr_set = true;
+  }
+  const int m_pairs = (a.M + 255) / 256, n_tiles = (a.N + BN - 1) / BN;
+  int pairs = m_pairs * n_tiles;
+  if (pairs > num_sms / 2) pairs = num_sms / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ConvGemmArgs aa = a;
+  aa.dbg = nullptr;
+  SALUN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gemm2<BN, S>, tmA, tmB, aa, m_pairs, n_tiles));
+  ++::salun::g_launch_count;
+  return SALUN_OK;
+}
+
+// CTA-pair GEMM: B tensor map must have box rows BN/2.  bn in {128, 256}.
+int launch_gemm2(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvGemmArgs &a, int bn, cudaStream_t st) {
+  prof_open(0, 2.0 * a.M * a.N * (double)a.num_k_blocks * 64.0, st);
+  int rc;
+  switch (bn) {
+    case 128: rc = launch_gemm2_t<128, 8>(tmA, tmB, a, st); break;
+    case 256: rc = launch_gemm2_t<256, 6>(tmA, tmB, a, st); break;
+    default: set_error("launch_gemm2: unsupported BN=%d", bn); rc = SALUN_ERR_INVALID;
+  }
+  prof_close(st);
+  return rc;
+}
+
 static bool gemm_persistent() {
   static int v = -1;
   if (v < 0) {
@@ -1173,6 +1412,29 @@ int salun_gemm_bf16_tn(salun_ctx *ctx, const void *A, const void *B, float *out_
   a.out_f32 = out_f32;
   a.ld_out = (int)N;
   return launch_conv_gemm(tmA, tmB, a, bn, (cudaStream_t)stream);
+}
+
+// CTA-pair (cta_group::2) variant of salun_gemm_bf16_tn: N % 128 == 0.
+int salun_gemm2_bf16_tn(salun_ctx *ctx, const void *A, const void *B, float *out_f32, void *out_bf16, int64_t M,
+                        int64_t N, int64_t K, void *stream) {
+  SALUN_REQUIRE(ctx && A && B && (out_f32 || out_bf16), "NULL argument");
+  SALUN_REQUIRE(M > 0 && N > 0 && K > 0 && K % 64 == 0 && N % 128 == 0, "need K % 64 == 0 and N % 128 == 0");
+  SALUN_CUDA_OK(cudaSetDevice(ctx->device));
+  const int bn = N % 256 == 0 ? 256 : 128;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_tmap_2d_bf16(&tmA, A, M, K, kBM, kBK))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmB, B, N, K, bn / 2, kBK))) return rc;
+  ConvGemmArgs a{};
+  a.mode_a = 0;
+  a.num_k_blocks = (int)(K / 64);
+  a.cin_blocks = 1 << 30;
+  a.M = (int)M;
+  a.N = (int)N;
+  a.out_bf16 = (__nv_bfloat16 *)out_bf16;
+  a.out_f32 = out_f32;
+  a.ld_out = (int)N;
+  return launch_gemm2(tmA, tmB, a, bn, (cudaStream_t)stream);
 }
 
 // Y[batch*H*W][Cout] = conv(X, Wk) for a stride-1 kh x kw convolution (3x3/pad 1 or 1x1/pad 0).

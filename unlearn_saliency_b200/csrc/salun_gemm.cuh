@@ -90,6 +90,8 @@ int conv_box(int H, int W, int pixels, TmapBox4 *box);
 int launch_conv_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvGemmArgs &a, int bn, cudaStream_t st);
 int launch_wgrad(const CUtensorMap &tmA, const CUtensorMap &tmB, const WgradArgs &a, int co_tiles, int col_groups,
                  int splits, cudaStream_t st);
+// CTA-pair (cta_group::2) GEMM, 256 x bn tiles; tmB must be encoded with bn/2 box rows
+int launch_gemm2(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvGemmArgs &a, int bn, cudaStream_t st);
 int wgrad_pick_blocks(int total_blocks);
 // dst[off + i] = sum_s ws[s*count + i], one table entry per convolution, ONE launch for the whole network
 struct WgReduceEntry {
