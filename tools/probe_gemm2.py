@@ -1,5 +1,7 @@
 """Time the 1-CTA persistent GEMM against the CTA-pair (cta_group::2) GEMM on the step's GEMM shapes."""
 import ctypes as C
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from unlearn_saliency_b200 import _lib
 from unlearn_saliency_b200._lib import check

@@ -2,6 +2,7 @@
 // 8 channels (16 bytes) per thread, fp32 math.  Replaces the ATen/cuDNN elementwise chain of
 // Classification/models/ResNet.py:108-124 (BatchNorm2d train/eval, ReLU, residual add), :303-322
 // (normalize, avgpool, fc) and their autograd backward.
+#include <cstdlib>
 #include "salun_elem.cuh"
 
 #include <math.h>
@@ -15,6 +16,16 @@ constexpr int kRedY = 32;  // row lanes of the (32 x kRedY)-thread column-reduct
 
 __device__ __forceinline__ void ld8(const __nv_bfloat16 *p, float (&f)[8]) {
   uint4 v = *reinterpret_cast<const uint4 *>(p);
+  const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 ldraw(const __nv_bfloat16 *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+__device__ __forceinline__ void cvt8(const uint4 &v, float (&f)[8]) {
   const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -119,7 +130,8 @@ __device__ __forceinline__ void bn_prologue(const BnFwd &p, float *sc, float *sh
   }
 }
 
-__global__ void __launch_bounds__(kET) k_bn_apply(BnFwd a, BnFwd b, int has_b, const __nv_bfloat16 *__restrict__ resid,
+template <int kU, int kMinB>
+__global__ void __launch_bounds__(kET, kMinB) k_bn_apply(BnFwd a, BnFwd b, int has_b, const __nv_bfloat16 *__restrict__ resid,
                                                   __nv_bfloat16 *__restrict__ out, uint8_t *__restrict__ rmask, int M,
                                                   int H, int W, int C, int relu, int train, float eps, float momentum) {
   extern __shared__ float smf[];
@@ -129,39 +141,68 @@ __global__ void __launch_bounds__(kET) k_bn_apply(BnFwd a, BnFwd b, int has_b, c
   __syncthreads();
   const int tpr = C >> 3, rpb = kET / tpr;
   const int rl = threadIdx.x / tpr, c0 = (threadIdx.x - rl * tpr) * 8;
-  for (int m = blockIdx.x * rpb + rl; m < M; m += gridDim.x * rpb) {
-    float v[8], t[8];
-    ld8(a.y + (size_t)m * C + c0, v);
+  // kU rows per thread per trip, all loads issued before the first use: one 16-byte load per thread and trip leaves the
+  // SM with ~32 KB in flight, below what HBM3e latency x bandwidth needs (profiles/README.md section 3)
+  const int stride = gridDim.x * rpb;
+  for (int m0 = blockIdx.x * rpb + rl; m0 < M; m0 += kU * stride) {
+    uint4 ra[kU], rb[kU], rr[kU];
+    size_t po[kU];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], sc_a[c0 + i], sh_a[c0 + i]);
-    if (has_b) {
-      ld8(b.y + (size_t)m * C + c0, t);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] += fmaf(t[i], sc_b[c0 + i], sh_b[c0 + i]);
+    for (int u = 0; u < kU; ++u) {
+      const int m = m0 + u * stride;
+      if (m < M) {
+        ra[u] = ldraw(a.y + (size_t)m * C + c0);
+        if (has_b) rb[u] = ldraw(b.y + (size_t)m * C + c0);
+        po[u] = pad_off(m, H, W, C) + c0;
+        if (resid) rr[u] = ldraw(resid + po[u]);
+      }
     }
-    const size_t po = pad_off(m, H, W, C) + c0;
-    if (resid) {
-      ld8(resid + po, t);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] += t[i];
-    }
-    if (relu) {
+    for (int u = 0; u < kU; ++u) {
+      const int m = m0 + u * stride;
+      if (m >= M) break;
+      float v[8], t[8];
+      cvt8(ra[u], v);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-    }
-    st8(out + po, v);
-    if (rmask) {  // the stored bf16 value decides (a positive fp32 that rounds to +0 cannot occur: bf16 keeps the exponent)
-      uint32_t bits = 0;
+      for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], sc_a[c0 + i], sh_a[c0 + i]);
+      if (has_b) {
+        cvt8(rb[u], t);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << i;
-      rmask[(size_t)m * (C >> 3) + (c0 >> 3)] = (uint8_t)bits;
+        for (int i = 0; i < 8; ++i) v[i] += fmaf(t[i], sc_b[c0 + i], sh_b[c0 + i]);
+      }
+      if (resid) {
+        cvt8(rr[u], t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += t[i];
+      }
+      if (relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+      st8(out + po[u], v);
+      if (rmask) {  // the stored bf16 value decides (a positive fp32 that rounds to +0 cannot occur: bf16 keeps the exponent)
+        uint32_t bits = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << i;
+        rmask[(size_t)m * (C >> 3) + (c0 >> 3)] = (uint8_t)bits;
+      }
     }
   }
 }
-static inline int elem_grid(int M, int C) {
+// (rows per trip, resident blocks per SM) of the BN elementwise kernels; SALUN_ELEM_VARIANT picks another one for tuning
+static int elem_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SALUN_ELEM_VARIANT");
+    v = e ? atoi(e) : 3;
+    if (v < 0 || v > 6) v = 3;
+  }
+  return v;
+}
+static inline int elem_grid(int M, int C, int blocks_per_sm = 8) {
   const int rpb = kET / (C >> 3);
   long long g = ((long long)M + rpb - 1) / rpb;
-  if (g > 148 * 8) g = 148 * 8;
+  if (g > 148 * blocks_per_sm) g = 148 * blocks_per_sm;  // = resident blocks: one full wave, no ragged second wave
   return (int)(g < 1 ? 1 : g);
 }
 void launch_bn_apply(const BnFwd &a, const BnFwd *b, const __nv_bfloat16 *resid_padded, __nv_bfloat16 *out_padded,
@@ -169,15 +210,28 @@ void launch_bn_apply(const BnFwd &a, const BnFwd *b, const __nv_bfloat16 *resid_
                      float momentum, cudaStream_t st) {
   const int M = n_img * H * W;
   BnFwd bb = b ? *b : a;
-  { k_bn_apply<<<elem_grid(M, C), kET, 4 * C * sizeof(float), st>>>(a, bb, b != nullptr, resid_padded, out_padded,
-                                                                  relu_mask_out, M, H,
-                                                                  W, C, relu, train, eps, momentum); ++::salun::g_launch_count; }
+#define SALUN_BN_APPLY(U, B)                                                                                          \
+  k_bn_apply<U, B><<<elem_grid(M, C, B), kET, 4 * C * sizeof(float), st>>>(a, bb, b != nullptr, resid_padded, out_padded, \
+                                                                            relu_mask_out, M, H, W, C, relu, train, eps, \
+                                                                            momentum)
+  switch (elem_variant()) {
+    case 0: SALUN_BN_APPLY(1, 8); break;
+    case 1: SALUN_BN_APPLY(2, 4); break;
+    case 2: SALUN_BN_APPLY(4, 3); break;
+    case 4: SALUN_BN_APPLY(8, 1); break;
+    case 5: SALUN_BN_APPLY(2, 2); break;
+    case 6: SALUN_BN_APPLY(4, 1); break;
+    default: SALUN_BN_APPLY(4, 2); break;
+  }
+#undef SALUN_BN_APPLY
+  ++::salun::g_launch_count;
 }
 
 // ------------------------------------------------------------------------------------------------
 // BN backward
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kET) k_bn_bwd_reduce(const __nv_bfloat16 *__restrict__ dout,
+template <int kU>
+__global__ void __launch_bounds__(kET, 2) k_bn_bwd_reduce(const __nv_bfloat16 *__restrict__ dout,
                                                        const uint8_t *__restrict__ rmask,
                                                        const __nv_bfloat16 *__restrict__ y,
                                                        const float *__restrict__ mean, const float *__restrict__ invstd,
@@ -192,19 +246,33 @@ __global__ void __launch_bounds__(kET) k_bn_bwd_reduce(const __nv_bfloat16 *__re
     mu[i] = mean[c0 + i];
     is[i] = invstd[c0 + i];
   }
-  for (int m = blockIdx.x * rpb + rl; m < M; m += gridDim.x * rpb) {
-    float d[8], yy[8];
-    ld8(dout + (size_t)m * C + c0, d);
-    ld8(y + (size_t)m * C + c0, yy);
-    if (rmask) {
-      const uint32_t bits = rmask[(size_t)m * (C >> 3) + (c0 >> 3)];
+  // kU independent loads per trip; rows are still accumulated in ascending order (same sums as kU = 1)
+  const int stride = gridDim.x * rpb;
+  for (int m0 = blockIdx.x * rpb + rl; m0 < M; m0 += kU * stride) {
+    uint4 rd[kU], ry[kU];
+    uint32_t rbits[kU];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = (bits >> i) & 1u ? d[i] : 0.f;
+    for (int u = 0; u < kU; ++u) {
+      const int m = m0 + u * stride;
+      if (m < M) {
+        rd[u] = ldraw(dout + (size_t)m * C + c0);
+        ry[u] = ldraw(y + (size_t)m * C + c0);
+        rbits[u] = rmask ? (uint32_t)__ldg(rmask + (size_t)m * (C >> 3) + (c0 >> 3)) : 0xffu;
+      }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      s1[i] += d[i];
-      s2[i] += d[i] * ((yy[i] - mu[i]) * is[i]);
+    for (int u = 0; u < kU; ++u) {
+      if (m0 + u * stride >= M) break;
+      float d[8], yy[8];
+      cvt8(rd[u], d);
+      cvt8(ry[u], yy);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] = (rbits[u] >> i) & 1u ? d[i] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s1[i] += d[i];
+        s2[i] += d[i] * ((yy[i] - mu[i]) * is[i]);
+      }
     }
   }
   float *b1 = smf, *b2 = smf + rpb * C;
@@ -234,8 +302,19 @@ void launch_bn_bwd_reduce(const __nv_bfloat16 *dout, const uint8_t *relu_mask, c
                           int C, cudaStream_t st) {
   const int M = n_img * H * W;
   const int rpb = kET / (C >> 3);
-  { k_bn_bwd_reduce<<<bwd_rows(M, C), kET, 2 * rpb * C * sizeof(float), st>>>(dout, relu_mask, y, saved_mean,
-                                                                           saved_invstd, partials, M, H, W, C); ++::salun::g_launch_count; }
+#define SALUN_BN_BWD_REDUCE(U)                                                                                  \
+  k_bn_bwd_reduce<U><<<bwd_rows(M, C), kET, 2 * rpb * C * sizeof(float), st>>>(dout, relu_mask, y, saved_mean, \
+                                                                               saved_invstd, partials, M, H, W, C)
+  switch (elem_variant()) {
+    case 0: SALUN_BN_BWD_REDUCE(1); break;
+    case 1: SALUN_BN_BWD_REDUCE(2); break;
+    case 2: SALUN_BN_BWD_REDUCE(4); break;
+    case 5: SALUN_BN_BWD_REDUCE(2); break;
+    case 6: SALUN_BN_BWD_REDUCE(4); break;
+    default: SALUN_BN_BWD_REDUCE(8); break;
+  }
+#undef SALUN_BN_BWD_REDUCE
+  ++::salun::g_launch_count;
 }
 
 __global__ void k_bn_bwd_finalize(const float *__restrict__ partials, int rows, int C, const float *__restrict__ gamma,
@@ -280,7 +359,8 @@ void launch_bn_bwd_finalize(const float *partials, int rows, int C, const float 
                                             dbeta, coef); ++::salun::g_launch_count; }
 }
 
-__global__ void __launch_bounds__(kET) k_bn_bwd_apply(const __nv_bfloat16 *__restrict__ dout,
+template <int kU, int kMinB>
+__global__ void __launch_bounds__(kET, kMinB) k_bn_bwd_apply(const __nv_bfloat16 *__restrict__ dout,
                                                       const uint8_t *__restrict__ rmask,
                                                       const __nv_bfloat16 *__restrict__ y,
                                                       const float *__restrict__ mean, const float *__restrict__ invstd,
@@ -298,27 +378,53 @@ __global__ void __launch_bounds__(kET) k_bn_bwd_apply(const __nv_bfloat16 *__res
     m1[i] = coef[C + c0 + i];
     m2[i] = coef[2 * C + c0 + i];
   }
-  for (int m = blockIdx.x * rpb + rl; m < M; m += gridDim.x * rpb) {
-    float d[8], yy[8];
-    ld8(dout + (size_t)m * C + c0, d);
-    ld8(y + (size_t)m * C + c0, yy);
-    if (rmask) {
-      const uint32_t bits = rmask[(size_t)m * (C >> 3) + (c0 >> 3)];
+  const int stride = gridDim.x * rpb;
+  for (int m0 = blockIdx.x * rpb + rl; m0 < M; m0 += kU * stride) {
+    uint4 rd[kU], ry[kU];
+    uint32_t rbits[kU];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = (bits >> i) & 1u ? d[i] : 0.f;
+    for (int u = 0; u < kU; ++u) {
+      const int m = m0 + u * stride;
+      if (m < M) {
+        rd[u] = ldraw(dout + (size_t)m * C + c0);
+        ry[u] = ldraw(y + (size_t)m * C + c0);
+        rbits[u] = rmask ? (uint32_t)__ldg(rmask + (size_t)m * (C >> 3) + (c0 >> 3)) : 0xffu;
+      }
     }
-    if (dz_flat) st8(dz_flat + (size_t)m * C + c0, d);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) yy[i] = k1[i] * (d[i] - m1[i] - (yy[i] - mu[i]) * is[i] * m2[i]);
-    st8(dy_padded ? dy + pad_off(m, H, W, C) + c0 : dy + (size_t)m * C + c0, yy);
+    for (int u = 0; u < kU; ++u) {
+      const int m = m0 + u * stride;
+      if (m >= M) break;
+      float d[8], yy[8];
+      cvt8(rd[u], d);
+      cvt8(ry[u], yy);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] = (rbits[u] >> i) & 1u ? d[i] : 0.f;
+      if (dz_flat) st8(dz_flat + (size_t)m * C + c0, d);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) yy[i] = k1[i] * (d[i] - m1[i] - (yy[i] - mu[i]) * is[i] * m2[i]);
+      st8(dy_padded ? dy + pad_off(m, H, W, C) + c0 : dy + (size_t)m * C + c0, yy);
+    }
   }
 }
 void launch_bn_bwd_apply(const __nv_bfloat16 *dout, const uint8_t *relu_mask, const __nv_bfloat16 *y,
                          const float *saved_mean, const float *saved_invstd, const float *coef, __nv_bfloat16 *dy,
                          int dy_padded, __nv_bfloat16 *dz_flat, int n_img, int H, int W, int C, cudaStream_t st) {
   const int M = n_img * H * W;
-  { k_bn_bwd_apply<<<elem_grid(M, C), kET, 0, st>>>(dout, relu_mask, y, saved_mean, saved_invstd, coef, dy, dy_padded,
-                                                  dz_flat, M, H, W, C); ++::salun::g_launch_count; }
+#define SALUN_BN_BWD_APPLY(U, B)                                                                              \
+  k_bn_bwd_apply<U, B><<<elem_grid(M, C, B), kET, 0, st>>>(dout, relu_mask, y, saved_mean, saved_invstd, coef, dy, \
+                                                           dy_padded, dz_flat, M, H, W, C)
+  switch (elem_variant()) {
+    case 0: SALUN_BN_BWD_APPLY(1, 6); break;
+    case 1: SALUN_BN_BWD_APPLY(2, 4); break;
+    case 2: SALUN_BN_BWD_APPLY(4, 3); break;
+    case 4: SALUN_BN_BWD_APPLY(8, 1); break;
+    case 5: SALUN_BN_BWD_APPLY(2, 2); break;
+    case 6: SALUN_BN_BWD_APPLY(4, 1); break;
+    default: SALUN_BN_BWD_APPLY(4, 2); break;
+  }
+#undef SALUN_BN_BWD_APPLY
+  ++::salun::g_launch_count;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -768,7 +874,7 @@ void launch_prep_w_all(const WPrepEntry *table_dev, int n_convs, const float *pa
 
 static inline int flat_grid(long long total) {
   long long g = (total + 255) / 256;
-  if (g > 148 * 8) g = 148 * 8;
+  if (g > 148 * 4) g = 148 * 4;  // = resident blocks (launch bounds (kET, 4)): one full wave, no ragged second wave
   return (int)(g < 1 ? 1 : g);
 }
 void launch_prep_w_fwd(const float *w, __nv_bfloat16 *out, int Cout, int kc, int kc_padded, cudaStream_t st) {
