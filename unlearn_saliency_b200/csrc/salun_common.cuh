@@ -31,6 +31,34 @@ void set_error(const char *fmt, ...);
     }                                                                                        \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------------
+// A step is ~170 dependent launches of 3-35 us kernels; the drain -> launch -> prologue bubble between two of them is
+// 1.5-2 us.  Kernels of the step path start with pdl_trigger() (the NEXT kernel of the stream may begin launching: its
+// CTAs become resident as this kernel's CTAs retire and run their global-memory-free prologue) and call pdl_wait()
+// before their first global-memory access (returns once the PREVIOUS kernel has completed and its writes are visible).
+// launch_pdl() must only be used for kernels that call pdl_wait(); both instructions are no-ops under a plain launch.
+// SALUN_PDL=0 turns the launch attribute off.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+bool pdl_enabled();
+template <typename... Exp, typename... Act>
+inline cudaError_t launch_pdl(void (*kernel)(Exp...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Act &&...args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<Exp>(args)...);
+}
+
 extern long long g_launch_count;  // kernels launched by this library (bench.py reports it as gpu_launches)
 
 constexpr int kRadixBins = 2048;      // 11-bit digits: 3 passes over a 32-bit key

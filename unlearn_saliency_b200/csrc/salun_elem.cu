@@ -53,6 +53,8 @@ __device__ __forceinline__ size_t pad_off(int m, int H, int W, int C) {
 // ------------------------------------------------------------------------------------------------
 __global__ void k_bn_stats_reduce(const float *__restrict__ ssum, const float *__restrict__ ssq, int rows, int C,
                                   double *__restrict__ slices) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double sh[2][kRedY][32];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int s = blockIdx.y;
@@ -90,7 +92,7 @@ __global__ void k_bn_stats_reduce(const float *__restrict__ ssum, const float *_
 void launch_bn_stats_reduce(const float *stat_sum, const float *stat_sq, int rows, int C, double *slices,
                             cudaStream_t st) {
   dim3 grid((C + 31) / 32, kStatSlices), block(32, kRedY);
-  { k_bn_stats_reduce<<<grid, block, 0, st>>>(stat_sum, stat_sq, rows, C, slices); ++::salun::g_launch_count; }
+  { ::salun::launch_pdl(k_bn_stats_reduce, dim3(grid), dim3(block), 0, st, stat_sum, stat_sq, rows, C, slices); ++::salun::g_launch_count; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -134,6 +136,8 @@ template <int kU, int kMinB>
 __global__ void __launch_bounds__(kET, kMinB) k_bn_apply(BnFwd a, BnFwd b, int has_b, const __nv_bfloat16 *__restrict__ resid,
                                                   __nv_bfloat16 *__restrict__ out, uint8_t *__restrict__ rmask, int M,
                                                   int H, int W, int C, int relu, int train, float eps, float momentum) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float smf[];
   float *sc_a = smf, *sh_a = smf + C, *sc_b = smf + 2 * C, *sh_b = smf + 3 * C;
   bn_prologue(a, sc_a, sh_a, C, train, (double)M, eps, momentum);
@@ -211,7 +215,7 @@ void launch_bn_apply(const BnFwd &a, const BnFwd *b, const __nv_bfloat16 *resid_
   const int M = n_img * H * W;
   BnFwd bb = b ? *b : a;
 #define SALUN_BN_APPLY(U, B)                                                                                          \
-  k_bn_apply<U, B><<<elem_grid(M, C, B), kET, 4 * C * sizeof(float), st>>>(a, bb, b != nullptr, resid_padded, out_padded, \
+  ::salun::launch_pdl(k_bn_apply<U, B>, dim3(elem_grid(M, C, B)), dim3(kET), 4 * C * sizeof(float), st, a, bb, b != nullptr, resid_padded, out_padded, \
                                                                             relu_mask_out, M, H, W, C, relu, train, eps, \
                                                                             momentum)
   switch (elem_variant()) {
@@ -236,6 +240,8 @@ __global__ void __launch_bounds__(kET, 2) k_bn_bwd_reduce(const __nv_bfloat16 *_
                                                        const __nv_bfloat16 *__restrict__ y,
                                                        const float *__restrict__ mean, const float *__restrict__ invstd,
                                                        float *__restrict__ partials, int M, int H, int W, int C) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float smf[];  // [2][rpb][C]
   const int tpr = C >> 3, rpb = kET / tpr;
   const int rl = threadIdx.x / tpr, c0 = (threadIdx.x - rl * tpr) * 8;
@@ -303,7 +309,7 @@ void launch_bn_bwd_reduce(const __nv_bfloat16 *dout, const uint8_t *relu_mask, c
   const int M = n_img * H * W;
   const int rpb = kET / (C >> 3);
 #define SALUN_BN_BWD_REDUCE(U)                                                                                  \
-  k_bn_bwd_reduce<U><<<bwd_rows(M, C), kET, 2 * rpb * C * sizeof(float), st>>>(dout, relu_mask, y, saved_mean, \
+  ::salun::launch_pdl(k_bn_bwd_reduce<U>, dim3(bwd_rows(M, C)), dim3(kET), 2 * rpb * C * sizeof(float), st, dout, relu_mask, y, saved_mean, \
                                                                                saved_invstd, partials, M, H, W, C)
   switch (elem_variant()) {
     case 0: SALUN_BN_BWD_REDUCE(1); break;
@@ -320,6 +326,8 @@ void launch_bn_bwd_reduce(const __nv_bfloat16 *dout, const uint8_t *relu_mask, c
 __global__ void k_bn_bwd_finalize(const float *__restrict__ partials, int rows, int C, const float *__restrict__ gamma,
                                   const float *__restrict__ invstd, float count, int train, float *__restrict__ dgamma,
                                   float *__restrict__ dbeta, float *__restrict__ coef) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double sh[2][kRedY][32];
   const int c = blockIdx.x * 32 + threadIdx.x;
   double a = 0.0, b = 0.0;
@@ -355,7 +363,7 @@ void launch_bn_bwd_finalize(const float *partials, int rows, int C, const float 
                             float count, int train, float *dgamma, float *dbeta, float *coef, cudaStream_t st) {
   const int M = (int)count;
   dim3 grid((C + 31) / 32), block(32, kRedY);
-  { k_bn_bwd_finalize<<<grid, block, 0, st>>>(partials, rows > 0 ? rows : bwd_rows(M, C), C, gamma, saved_invstd, count, train, dgamma,
+  { ::salun::launch_pdl(k_bn_bwd_finalize, dim3(grid), dim3(block), 0, st, partials, rows > 0 ? rows : bwd_rows(M, C), C, gamma, saved_invstd, count, train, dgamma,
                                             dbeta, coef); ++::salun::g_launch_count; }
 }
 
@@ -367,6 +375,8 @@ __global__ void __launch_bounds__(kET, kMinB) k_bn_bwd_apply(const __nv_bfloat16
                                                       const float *__restrict__ coef, __nv_bfloat16 *__restrict__ dy,
                                                       int dy_padded, __nv_bfloat16 *__restrict__ dz_flat, int M, int H,
                                                       int W, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int tpr = C >> 3, rpb = kET / tpr;
   const int rl = threadIdx.x / tpr, c0 = (threadIdx.x - rl * tpr) * 8;
   float mu[8], is[8], k1[8], m1[8], m2[8];
@@ -412,7 +422,7 @@ void launch_bn_bwd_apply(const __nv_bfloat16 *dout, const uint8_t *relu_mask, co
                          int dy_padded, __nv_bfloat16 *dz_flat, int n_img, int H, int W, int C, cudaStream_t st) {
   const int M = n_img * H * W;
 #define SALUN_BN_BWD_APPLY(U, B)                                                                              \
-  k_bn_bwd_apply<U, B><<<elem_grid(M, C, B), kET, 0, st>>>(dout, relu_mask, y, saved_mean, saved_invstd, coef, dy, \
+  ::salun::launch_pdl(k_bn_bwd_apply<U, B>, dim3(elem_grid(M, C, B)), dim3(kET), 0, st, dout, relu_mask, y, saved_mean, saved_invstd, coef, dy, \
                                                            dy_padded, dz_flat, M, H, W, C)
   switch (elem_variant()) {
     case 0: SALUN_BN_BWD_APPLY(1, 6); break;
@@ -433,6 +443,8 @@ void launch_bn_bwd_apply(const __nv_bfloat16 *dout, const uint8_t *relu_mask, co
 __global__ void __launch_bounds__(kET) k_stem_im2col(const float *__restrict__ x, __nv_bfloat16 *__restrict__ col, int M,
                                                      int H, int W, float m0, float m1, float m2, float i0, float i1,
                                                      float i2) {
+  pdl_trigger();
+  pdl_wait();
   const int m = blockIdx.x * kET + threadIdx.x;
   if (m >= M) return;
   const int hw = H * W;
@@ -466,12 +478,14 @@ __global__ void __launch_bounds__(kET) k_stem_im2col(const float *__restrict__ x
 void launch_stem_im2col(const float *x, __nv_bfloat16 *col, int n_img, int H, int W, const float *mean3,
                         const float *inv_std3, cudaStream_t st) {
   const int M = n_img * H * W;
-  { k_stem_im2col<<<(M + kET - 1) / kET, kET, 0, st>>>(x, col, M, H, W, mean3[0], mean3[1], mean3[2], inv_std3[0],
+  { ::salun::launch_pdl(k_stem_im2col, dim3((M + kET - 1) / kET), dim3(kET), 0, st, x, col, M, H, W, mean3[0], mean3[1], mean3[2], inv_std3[0],
                                                      inv_std3[1], inv_std3[2]); ++::salun::g_launch_count; }
 }
 
 __global__ void __launch_bounds__(kET) k_im2col_s2(const __nv_bfloat16 *__restrict__ in, __nv_bfloat16 *__restrict__ col,
                                                    long long total, int Hin, int Win, int C, int ks) {
+  pdl_trigger();
+  pdl_wait();
   const int Ho = Hin / 2, Wo = Win / 2, cgs = C >> 3, taps = ks * ks;
   for (long long i = (long long)blockIdx.x * kET + threadIdx.x; i < total; i += (long long)gridDim.x * kET) {
     const int cg = (int)(i % cgs);
@@ -492,13 +506,15 @@ void launch_im2col_s2(const __nv_bfloat16 *in_padded, __nv_bfloat16 *col, int n_
   const long long total = (long long)n_img * (Hin / 2) * (Win / 2) * ks * ks * (C >> 3);
   long long g = (total + kET - 1) / kET;
   if (g > 148 * 16) g = 148 * 16;
-  { k_im2col_s2<<<(int)g, kET, 0, st>>>(in_padded, col, total, Hin, Win, C, ks); ++::salun::g_launch_count; }
+  { ::salun::launch_pdl(k_im2col_s2, dim3((int)g), dim3(kET), 0, st, in_padded, col, total, Hin, Win, C, ks); ++::salun::g_launch_count; }
 }
 
 __global__ void __launch_bounds__(kET) k_col2im_s2(const __nv_bfloat16 *__restrict__ dcol3,
                                                    const __nv_bfloat16 *__restrict__ dcol1,
                                                    __nv_bfloat16 *__restrict__ dx, long long total, int Hin, int Win,
                                                    int C) {
+  pdl_trigger();
+  pdl_wait();
   const int Ho = Hin / 2, Wo = Win / 2, cgs = C >> 3;
   for (long long i = (long long)blockIdx.x * kET + threadIdx.x; i < total; i += (long long)gridDim.x * kET) {
     const int cg = (int)(i % cgs);
@@ -537,7 +553,7 @@ void launch_col2im_s2(const __nv_bfloat16 *dcol3, const __nv_bfloat16 *dcol1, __
   const long long total = (long long)n_img * Hin * Win * (C >> 3);
   long long g = (total + kET - 1) / kET;
   if (g > 148 * 16) g = 148 * 16;
-  { k_col2im_s2<<<(int)g, kET, 0, st>>>(dcol3, dcol1, dx, total, Hin, Win, C); ++::salun::g_launch_count; }
+  { ::salun::launch_pdl(k_col2im_s2, dim3((int)g), dim3(kET), 0, st, dcol3, dcol1, dx, total, Hin, Win, C); ++::salun::g_launch_count; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -834,6 +850,8 @@ __global__ void k_prep_w_transpose(const float *__restrict__ w, __nv_bfloat16 *_
 //                     32x33 shared-memory tiles so that both the fp32 reads and the bf16 writes are coalesced.
 __global__ void __launch_bounds__(256) k_prep_w_all(const WPrepEntry *__restrict__ tab, const float *__restrict__ params,
                                                     int need_dgrad) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tile[32][33];
   const WPrepEntry e = tab[blockIdx.y];
   const float *__restrict__ w = params + e.w_off;
@@ -869,7 +887,7 @@ __global__ void __launch_bounds__(256) k_prep_w_all(const WPrepEntry *__restrict
   }
 }
 void launch_prep_w_all(const WPrepEntry *table_dev, int n_convs, const float *params, int need_dgrad, cudaStream_t st) {
-  { k_prep_w_all<<<dim3(592, n_convs), 256, 0, st>>>(table_dev, params, need_dgrad); ++::salun::g_launch_count; }
+  { ::salun::launch_pdl(k_prep_w_all, dim3(dim3(592, n_convs)), dim3(256), 0, st, table_dev, params, need_dgrad); ++::salun::g_launch_count; }
 }
 
 static inline int flat_grid(long long total) {
@@ -892,6 +910,8 @@ void launch_prep_w_transpose(const float *w, __nv_bfloat16 *out, int Cout, int k
 // ------------------------------------------------------------------------------------------------
 __global__ void k_avgpool(const __nv_bfloat16 *__restrict__ act, float *__restrict__ pooled, int n_img, int H, int W,
                           int C) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_img * C) return;
   const int n = i / C, c = i - n * C;
@@ -901,13 +921,15 @@ __global__ void k_avgpool(const __nv_bfloat16 *__restrict__ act, float *__restri
   pooled[i] = s / (float)(H * W);
 }
 void launch_avgpool(const __nv_bfloat16 *act_padded, float *pooled, int n_img, int H, int W, int C, cudaStream_t st) {
-  { k_avgpool<<<(n_img * C + 255) / 256, 256, 0, st>>>(act_padded, pooled, n_img, H, W, C); ++::salun::g_launch_count; }
+  { ::salun::launch_pdl(k_avgpool, dim3((n_img * C + 255) / 256), dim3(256), 0, st, act_padded, pooled, n_img, H, W, C); ++::salun::g_launch_count; }
 }
 
 __global__ void __launch_bounds__(128) k_fc_ce(const float *__restrict__ pooled, const float *__restrict__ w,
                                                const float *__restrict__ bias, const int64_t *__restrict__ labels,
                                                float *__restrict__ logits, float *__restrict__ dlogits,
                                                float *__restrict__ loss_ps, int n_img, int C, int K, float sign) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float lg[];  // [K]
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float *x = pooled + (size_t)b * C;
@@ -940,10 +962,12 @@ __global__ void __launch_bounds__(128) k_fc_ce(const float *__restrict__ pooled,
 }
 void launch_fc_ce(const float *pooled, const float *w, const float *b, const int64_t *labels, float *logits,
                   float *dlogits, float *loss_per_sample, int n_img, int C, int K, float sign, cudaStream_t st) {
-  { k_fc_ce<<<n_img, 128, K * sizeof(float), st>>>(pooled, w, b, labels, logits, dlogits, loss_per_sample, n_img, C, K,
+  { ::salun::launch_pdl(k_fc_ce, dim3(n_img), dim3(128), K * sizeof(float), st, pooled, w, b, labels, logits, dlogits, loss_per_sample, n_img, C, K,
                                                   sign); ++::salun::g_launch_count; }
 }
 __global__ void k_loss_sum(const float *__restrict__ l, int n, float sign, float *__restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[32];
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) s += l[i];
@@ -957,11 +981,13 @@ __global__ void k_loss_sum(const float *__restrict__ l, int n, float sign, float
   }
 }
 void launch_loss_sum(const float *loss_per_sample, int n_img, float sign, float *loss_out, cudaStream_t st) {
-  { k_loss_sum<<<1, 256, 0, st>>>(loss_per_sample, n_img, sign, loss_out); ++::salun::g_launch_count; }
+  { ::salun::launch_pdl(k_loss_sum, dim3(1), dim3(256), 0, st, loss_per_sample, n_img, sign, loss_out); ++::salun::g_launch_count; }
 }
 
 __global__ void k_fc_bwd_w(const float *__restrict__ pooled, const float *__restrict__ dl, float *__restrict__ dw,
                            float *__restrict__ db, int n_img, int C, int K) {
+  pdl_trigger();
+  pdl_wait();
   // grid (K, C/64), block (64 channels, 8 batch lanes): fixed summation order -> deterministic
   __shared__ float sh[8][64];
   const int k = blockIdx.x, c = blockIdx.y * 64 + threadIdx.x;
@@ -990,6 +1016,8 @@ __global__ void k_fc_bwd_w(const float *__restrict__ pooled, const float *__rest
 }
 __global__ void k_fc_bwd_x(const float *__restrict__ dl, const float *__restrict__ w, __nv_bfloat16 *__restrict__ dact,
                            int n_img, int C, int K, int pix) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_img * C) return;
   const int b = i / C, c = i - b * C;
@@ -1000,8 +1028,8 @@ __global__ void k_fc_bwd_x(const float *__restrict__ dl, const float *__restrict
 }
 void launch_fc_bwd(const float *pooled, const float *dlogits, const float *w, float *dw, float *db,
                    __nv_bfloat16 *dact_flat, int n_img, int C, int K, int pix, cudaStream_t st) {
-  { k_fc_bwd_w<<<dim3(K, (C + 63) / 64), dim3(64, 8), 0, st>>>(pooled, dlogits, dw, db, n_img, C, K); ++::salun::g_launch_count; }
-  { k_fc_bwd_x<<<(n_img * C + 255) / 256, 256, 0, st>>>(dlogits, w, dact_flat, n_img, C, K, pix); ++::salun::g_launch_count; }
+  { ::salun::launch_pdl(k_fc_bwd_w, dim3(dim3(K, (C + 63) / 64)), dim3(dim3(64, 8)), 0, st, pooled, dlogits, dw, db, n_img, C, K); ++::salun::g_launch_count; }
+  { ::salun::launch_pdl(k_fc_bwd_x, dim3((n_img * C + 255) / 256), dim3(256), 0, st, dlogits, w, dact_flat, n_img, C, K, pix); ++::salun::g_launch_count; }
 }
 
 }  // namespace salun

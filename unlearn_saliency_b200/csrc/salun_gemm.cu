@@ -283,6 +283,7 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   constexpr uint32_t kABytes = kBM * kBK * 2;
   constexpr uint32_t kBBytes = BN * kBK * 2;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
@@ -315,6 +316,7 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above is global-memory free (barriers, tensor memory, descriptor prefetch)
 
   const bool dbg_on = a.dbg != nullptr;
   const long long t_begin = dbg_on ? clock64() : 0;
@@ -692,6 +694,7 @@ k_conv_rw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   constexpr int kStages = kCinBlocks == 1 ? 6 : 3;
   constexpr uint32_t kSlab = 64 * 128;                    // one [64 out-ch][64 in-ch] weight slab
   constexpr uint32_t kWBytes = 9 * kCinBlocks * kSlab;
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t w_base = smem_u32(smem);
@@ -726,6 +729,7 @@ k_conv_rw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   const bool dbg_on = a.dbg != nullptr;
   const long long t_begin = dbg_on ? clock64() : 0;
@@ -1177,7 +1181,7 @@ static int launch_conv_gemm_p_t(const CUtensorMap &tmA, const CUtensorMap &tmB, 
   if (grid > num_sms) grid = num_sms;
   ConvGemmArgs aa = a;
   aa.dbg = g_dbg;
-  { k_conv_gemm_p<BN, S><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, aa, m_tiles, n_tiles); ++::salun::g_launch_count; }
+  { SALUN_CUDA_OK(::salun::launch_pdl(k_conv_gemm_p<BN, S>, dim3(grid), dim3(kGemmThreads), smem, st, tmA, tmB, aa, m_tiles, n_tiles)); ++::salun::g_launch_count; }
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;
 }
@@ -1280,7 +1284,7 @@ static int launch_conv_rw_t(const CUtensorMap &tmA, const CUtensorMap &tmB, cons
   prof_open(0, 2.0 * a.M * a.N * 9.0 * kCB * 64.0, st);
   ConvRwArgs aa = a;
   aa.dbg = g_dbg;
-  { k_conv_rw<kW, kCB><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, aa); ++::salun::g_launch_count; }
+  { SALUN_CUDA_OK(::salun::launch_pdl(k_conv_rw<kW, kCB>, dim3(grid), dim3(kGemmThreads), smem, st, tmA, tmB, aa)); ++::salun::g_launch_count; }
   prof_close(st);
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;

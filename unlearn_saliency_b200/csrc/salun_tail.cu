@@ -7,6 +7,7 @@
 // persistent grids of (#SMs x 8) CTAs x 256 threads, no shared-memory staging (no reuse).
 // Floating point uses explicit __fmul_rn/__fadd_rn so the sequence of roundings equals
 // oracle/salun_oracle.c (built with -ffp-contract=off) and results compare bit-exactly.
+#include <stdlib.h>
 #include <math.h>
 #include <stdarg.h>
 
@@ -15,6 +16,14 @@
 namespace salun {
 
 long long g_launch_count = 0;
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SALUN_PDL");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
 static thread_local char g_err[512] = "";
 char *err_buf() { return g_err; }
 void set_error(const char *fmt, ...) {
