@@ -250,6 +250,68 @@ int salun_resnet_forward_backward(salun_resnet *net, const float *x, const int64
 /* eval-mode inference (trainer/val.py:6-72 validate): logits only */
 int salun_resnet_forward(salun_resnet *net, const float *x, int n, float *logits_dev, void *stream);
 
+
+/* ---------------------------------------------------------------------------------------
+ * Class-conditional DDPM U-Net forward + backward engine.
+ * replaces  model(x_t, t.float(), c, mode=..., ...)  and  loss.backward()  of
+ *           DDPM/runners/diffusion.py:974-983  (generate_mask: cond + null pass, eval mode)
+ *           DDPM/runners/diffusion.py:533-580  (saliency_unlearn: remain / forget / pseudo-label passes, train mode)
+ *           DDPM/functions/losses.py:21-37     (the model call inside noise_estimation_loss_conditional)
+ * for the architecture of DDPM/models/diffusion.py:195-413 (Conditional_Model) with the keys of
+ * DDPM/configs/cifar10_saliency_unlearn.yml:14-27.  bf16 tensor-core operands and activations, fp32 accumulation,
+ * GroupNorm statistics, embeddings, master weights and gradients.
+ *
+ * Arena layout (caller-owned device buffers, fp32): tensors back to back in model.named_parameters() order
+ * (null_classes_emb, temb.dense.*, classes_emb.weight, cemb.dense.*, conv_in, down.*, mid.*, up.0 ... up.L-1, norm_out,
+ * conv_out); every conv weight is stored [Cout][kh][kw][Cin] (the reference's [Cout][Cin][kh][kw] permuted (0,2,3,1)),
+ * everything else as in PyTorch.
+ *
+ * GroupNorm does not couple samples, so the caller may run several of the reference's model calls as ONE batch
+ * (e.g. remain + forget mini-batches, or the conditional + null passes of classifier-free guidance via drop[]) and
+ * hand back per-sample dL/d(eps).
+ * ------------------------------------------------------------------------------------- */
+typedef struct salun_unet salun_unet;
+typedef struct salun_unet_cfg {
+  int ch;             /* model.ch (128: the reference's ResnetBlock hard-codes cemb_channels = 512 = 4 * 128) */
+  int n_levels;       /* len(model.ch_mult) */
+  int ch_mult[8];     /* model.ch_mult */
+  int num_res_blocks; /* model.num_res_blocks */
+  int n_attn_res;     /* len(model.attn_resolutions) */
+  int attn_res[8];    /* model.attn_resolutions (<= 16) */
+  int image_size;     /* data.image_size: power of two, smallest level >= 4x4 */
+  int in_channels;    /* 3 */
+  int out_ch;         /* 3 */
+  int n_classes;      /* data.n_classes */
+  int max_batch;      /* largest batch a call will pass */
+  float dropout;      /* model.dropout; applied when train != 0 (counter-based generator, see salun_unet_forward) */
+} salun_unet_cfg;
+
+int64_t salun_unet_param_count(const salun_unet_cfg *cfg);
+int salun_unet_create(salun_ctx *ctx, const salun_unet_cfg *cfg, float *params, float *grads, salun_unet **out);
+int salun_unet_destroy(salun_unet *net);
+
+/* eps = model._forward(x, t, c) for n samples.
+ *   x    : fp32 NCHW [n][3][S][S] (x_t)          t : fp32 [n] (the reference passes t.float())       c : int64 [n]
+ *   drop : optional uint8 [n]; 1 = the class embedding of that sample is replaced by null_classes_emb
+ *          (diffusion.py:372-376; the caller draws the cond_drop_prob decisions, or passes all-ones for the null pass
+ *          of _forward_with_cond_scale :340-355).  NULL = keep every class embedding.
+ *   train: != 0 applies dropout(cfg.dropout) after norm2 + swish of every ResnetBlock with a counter-based generator
+ *          keyed by `seed` (the mask is regenerated, not stored, in the backward pass).  It is a different stream of
+ *          random numbers than torch's Philox: parity runs use dropout 0.
+ *   save_for_backward: != 0 keeps the activations for salun_unet_backward (a later forward overwrites them).
+ *   eps_out : fp32 NCHW [n][3][S][S]. */
+int salun_unet_forward(salun_unet *net, const float *x, const float *t, const int64_t *c, const uint8_t *drop, int n,
+                       int train, uint64_t seed, int save_for_backward, float *eps_out, void *stream);
+/* grads (=|+=) d loss / d params for the last saved forward, given d_eps = d loss / d eps_out (fp32 NCHW [n][3][S][S]).
+ * accumulate == 0 overwrites the gradient arena (the zero_grad() of the reference loop is implied). */
+int salun_unet_backward(salun_unet *net, const float *d_eps, int accumulate, void *stream);
+
+/* bring-up / parity-test accessors: the tape's activation tensors, exported as fp32 NCHW [n][C][H][H]
+ * (which = 0: value, 1: gradient of the last backward). */
+int salun_unet_num_tensors(const salun_unet *net);
+int salun_unet_tensor_info(const salun_unet *net, int idx, char *name_buf, int name_cap, int *C, int *H);
+int salun_unet_export_tensor(salun_unet *net, int idx, int which, float *out_nchw, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -867,6 +867,7 @@ __global__ void __launch_bounds__(256) k_prep_w_all(const WPrepEntry *__restrict
   const int tiles_ci = (cin + 31) / 32, tiles_co = (e.cout + 31) / 32;
   const int ntiles = taps * tiles_ci * tiles_co;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int ldo = e.ldo ? e.ldo : e.cout;
   for (int tIdx = blockIdx.x; tIdx < ntiles; tIdx += gridDim.x) {
     const int t = tIdx / (tiles_ci * tiles_co);
     const int r = tIdx - t * tiles_ci * tiles_co;
@@ -881,7 +882,7 @@ __global__ void __launch_bounds__(256) k_prep_w_all(const WPrepEntry *__restrict
     for (int j = 0; j < 4; ++j) {  // write out[ci][taps-1-t][co]: co contiguous
       const int ci = ci0 + ty + 8 * j, co = co0 + tx;
       if (ci < cin && co < e.cout)
-        e.w_dgrad[((size_t)ci * taps + (taps - 1 - t)) * e.cout + co] = __float2bfloat16(tile[tx][ty + 8 * j]);
+        e.w_dgrad[((size_t)ci * taps + (taps - 1 - t)) * ldo + co] = __float2bfloat16(tile[tx][ty + 8 * j]);
     }
     __syncthreads();
   }

@@ -60,6 +60,7 @@ struct WPrepEntry {
   __nv_bfloat16 *w_dgrad;  // dgrad operand or nullptr
   int cout, cin, kc, kcp;
   int dgrad_mode;          // 0: none, 1: stride-1 flipped [ci][tap'][co], 2: transposed [kc][co]
+  int ldo;                 // row stride (in co) of the dgrad operand; 0 = cout (conv_out of the U-Net pads 3 -> 64)
 };
 void launch_prep_w_all(const WPrepEntry *table_dev, int n_convs, const float *params, int need_dgrad, cudaStream_t st);
 

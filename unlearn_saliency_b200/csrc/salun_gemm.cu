@@ -336,6 +336,7 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           y0 = (pix0 - n0 * hw) / a.W;
         }
         int cb = 0, kx = 0, ky = 0;
+        const int b_row0 = n_tile * BN + (a.batch_rows_a ? (m_tile * kBM / a.batch_rows_a) * a.batch_rows_b : 0);
         for (int kb = 0; kb < a.num_k_blocks; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
@@ -348,7 +349,7 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             else
               tma_load_2d(sa, &tmA, full0 + 8 * s, kb * kBK, m_tile * kBM);
           } else {
-            tma_load_2d(sb, &tmB, full0 + 8 * s, kb * kBK, n_tile * BN);
+            tma_load_2d(sb, &tmB, full0 + 8 * s, kb * kBK, b_row0);
           }
           if (++cb == a.cin_blocks) {
             cb = 0;
@@ -407,6 +408,8 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const bool row_ok = row < a.M;
       const int stat_row = (m_tile * 4 + q);
       const size_t fuse_pad = (a.f1.act && row_ok) ? pad_row_off(row, a.fH, a.fW, a.N) : 0;
+      const size_t out_row = !row_ok ? 0 : (a.out_pad ? pad_row_off(row, a.fH, a.fW, a.ld_out) : (size_t)row * a.ld_out);
+      const float *rb_row = (a.rowbias && row_ok) ? a.rowbias + (size_t)(row >> a.rb_shift) * a.rb_ld : nullptr;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
@@ -429,8 +432,28 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               a.stat_sq[(size_t)stat_row * a.N + col0 + lane] = s2;
             }
           }
+          if (a.bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4 *>(a.bias + col0) + j);
+              r[4 * j + 0] = __float_as_uint(__uint_as_float(r[4 * j + 0]) + b4.x);
+              r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + b4.y);
+              r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + b4.z);
+              r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + b4.w);
+            }
+          }
+          if (rb_row) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4 *>(rb_row + col0) + j);
+              r[4 * j + 0] = __float_as_uint(__uint_as_float(r[4 * j + 0]) + b4.x);
+              r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + b4.y);
+              r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + b4.z);
+              r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + b4.w);
+            }
+          }
           if (row_ok && a.addend) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(a.addend + (size_t)row * a.ld_out + col0);
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.addend + out_row + col0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint4 v = src[j];
@@ -449,7 +472,7 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           }
           if (row_ok) {
             if (a.out_bf16) {
-              uint4 *dst = reinterpret_cast<uint4 *>(a.out_bf16 + (size_t)row * a.ld_out + col0);
+              uint4 *dst = reinterpret_cast<uint4 *>(a.out_bf16 + out_row + col0);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 uint4 v;
@@ -1254,6 +1277,11 @@ int launch_conv_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvG
     }
     prof_close(st);
     return rc;
+  }
+  if (a.bias || a.rowbias || a.out_pad || a.batch_rows_a) {
+    set_error("launch_conv_gemm: bias / rowbias / out_pad / batched operands need the persistent kernel (SALUN_GEMM_PERSIST=1)");
+    prof_close(st);
+    return SALUN_ERR_UNSUPPORTED;
   }
   switch (bn) {
     case 64: rc = launch_conv_gemm_t<64, 4>(tmA, tmB, a, st); break;

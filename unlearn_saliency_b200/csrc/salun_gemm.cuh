@@ -36,7 +36,15 @@ struct ConvGemmArgs {
   const __nv_bfloat16 *addend;  // optional [M][ld_out]: D += addend before the store (residual-gradient merge)
   long long *dbg;               // optional per-CTA role timing [gridDim][8] (bring-up / profiling only)
   BnBwdFuse f1, f2;             // up to two consumer BatchNorms of the produced gradient (bn2 + projection-shortcut BN)
-  int fH, fW;                   // image size of the output pixels (padded-offset arithmetic of f1/f2.act)
+  int fH, fW;                   // image size of the output pixels (padded-offset arithmetic of f1/f2.act and of out_pad)
+  // ---- U-Net path (persistent kernel only) ----
+  const float *bias;            // optional [N] fp32: D += bias[col]            (conv bias, DDPM/models/diffusion.py:104-119)
+  const float *rowbias;         // optional fp32 [rows >> rb_shift][rb_ld]: D += rowbias[(row >> rb_shift) * rb_ld + col]
+  int rb_shift, rb_ld;          //   (the per-sample temb/cemb projection added after conv1, diffusion.py:131-132)
+  int out_pad;                  // 1: rows of out_bf16 / addend are the pixels of a halo-padded NHWC tensor
+                                //    [n][fH+2][fW+2][ld_out] (row m -> interior pixel), 0: flat [M][ld_out]
+  int batch_rows_a, batch_rows_b;  // batched GEMM (one B matrix per group of batch_rows_a rows of A): the B tile of
+                                   // output tile (m, n) starts at row (m*128 / batch_rows_a) * batch_rows_b + n*BN.  0 = off
 };
 
 // dW[co][b*64 + j] += sum_p dY[p][co] * X_b[p][j]   (both operands MN-major: pixels are the K dimension)

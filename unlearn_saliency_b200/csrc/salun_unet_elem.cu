@@ -1,0 +1,831 @@
+// salun_unet_elem.cu -- HBM-bound kernels of the DDPM U-Net path (see salun_unet_elem.cuh).  bf16 storage, 8 channels
+// (16 bytes) per thread, fp32 math, fp64 where a reduction feeds a variance.  Every kernel is deterministic (fixed
+// reduction order, no atomics).
+#include "salun_unet_elem.cuh"
+
+#include <math.h>
+
+#include "salun_common.cuh"
+
+namespace salun {
+
+typedef __nv_bfloat16 bf16;
+
+namespace {
+
+constexpr int kT = 256;
+
+__device__ __forceinline__ void u_ld8(const bf16 *p, float (&f)[8]) {
+  const uint4 v = *reinterpret_cast<const uint4 *>(p);
+  const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void u_st8(bf16 *p, const float (&f)[8]) {
+  uint4 v;
+  __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<uint4 *>(p) = v;
+}
+// element offset of pixel p (0 .. H*H-1) of image n, channel 0
+__device__ __forceinline__ size_t pix_off(int n, int p, int H, int C, int flat) {
+  if (flat) return ((size_t)n * H * H + p) * C;
+  const int y = p / H, x = p - y * H;
+  return (((size_t)n * (H + 2) + y + 1) * (H + 2) + x + 1) * C;
+}
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+// dropout decision of element e (flat index (n*HW + p)*C + c) -- the same function in forward and backward
+__device__ __forceinline__ float drop_scale(uint32_t seed, uint32_t e, uint32_t thr, float inv_keep) {
+  return hash32(e ^ seed) >= thr ? inv_keep : 0.f;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// sums over the row lanes of a (vecs x rl) thread block: acc[k][8] per thread -> partial[k][C] of this (n, slice)
+template <int K>
+__device__ __forceinline__ void slice_reduce_store(float (&acc)[K][8], int v, int r, int rl, bool active, int C,
+                                                   float *__restrict__ dst /* [K][C] */) {
+  __shared__ float red[K * 2048];
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[(k * rl + r) * C + v * 8 + i] = acc[k][i];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < K * C; j += kT) {
+    const int k = j / C, c = j - k * C;
+    float s = 0.f;
+    for (int q = 0; q < rl; ++q) s += red[(k * rl + q) * C + c];
+    dst[j] = s;
+  }
+}
+
+}  // namespace
+
+int unet_slices(int H) {
+  int s = H * H / 64;
+  if (s < 1) s = 1;
+  if (s > 16) s = 16;
+  return s;
+}
+
+// =================================================================================================================
+// GroupNorm forward
+// =================================================================================================================
+__global__ void __launch_bounds__(kT) k_gn_stats(const bf16 *__restrict__ x, float *__restrict__ partial, int H, int C,
+                                                 int S) {
+  const int n = blockIdx.y, s = blockIdx.x;
+  const int vecs = C >> 3, rl = kT / vecs;
+  const int v = threadIdx.x % vecs, r = threadIdx.x / vecs;
+  const bool active = r < rl;
+  const int rps = H * H / S;
+  float acc[2][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
+  if (active) {
+    for (int p = s * rps + r; p < (s + 1) * rps; p += rl) {
+      float f[8];
+      u_ld8(x + pix_off(n, p, H, C, 0) + v * 8, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[0][i] += f[i];
+        acc[1][i] += f[i] * f[i];
+      }
+    }
+  }
+  slice_reduce_store<2>(acc, v, r, rl, active, C, partial + ((size_t)n * S + s) * 2 * C);
+}
+__global__ void __launch_bounds__(32) k_gn_fwd_finalize(const float *__restrict__ partial, float *__restrict__ stats,
+                                                        int C, int S, float count, float eps) {
+  const int n = blockIdx.x, g = threadIdx.x;
+  const int cpg = C / kGnGroups;
+  double s1 = 0.0, s2 = 0.0;
+  for (int s = 0; s < S; ++s) {
+    const float *p = partial + ((size_t)n * S + s) * 2 * C;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      s1 += (double)p[c];
+      s2 += (double)p[C + c];
+    }
+  }
+  const double mean = s1 / count;
+  double var = s2 / count - mean * mean;  // biased variance, like torch.nn.GroupNorm
+  if (var < 0.0) var = 0.0;
+  stats[((size_t)n * kGnGroups + g) * 2 + 0] = (float)mean;
+  stats[((size_t)n * kGnGroups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+void launch_gn_stats(const bf16 *x_pad, float *partial, float *stats, int n, int H, int C, float eps, cudaStream_t st) {
+  const int S = unet_slices(H);
+  k_gn_stats<<<dim3(S, n), kT, 0, st>>>(x_pad, partial, H, C, S);
+  k_gn_fwd_finalize<<<n, 32, 0, st>>>(partial, stats, C, S, (float)(C / kGnGroups) * H * H, eps);
+  g_launch_count += 2;
+}
+
+__global__ void __launch_bounds__(kT) k_gn_apply(const bf16 *__restrict__ x, const float *__restrict__ stats,
+                                                 const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                 bf16 *__restrict__ out, int out_flat, int swish, uint32_t drop_thr,
+                                                 float inv_keep, uint32_t seed, int H, int C, int S) {
+  const int n = blockIdx.y, s = blockIdx.x;
+  const int vecs = C >> 3, rl = kT / vecs;
+  const int v = threadIdx.x % vecs, r = threadIdx.x / vecs;
+  if (r >= rl) return;
+  const int cpg = C / kGnGroups, rps = H * H / S, c0 = v * 8;
+  float a[8], b[8];  // y = a*x + b
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int g = (c0 + i) / cpg;
+    const float mean = stats[((size_t)n * kGnGroups + g) * 2], rstd = stats[((size_t)n * kGnGroups + g) * 2 + 1];
+    a[i] = gamma[c0 + i] * rstd;
+    b[i] = beta[c0 + i] - mean * a[i];
+  }
+  for (int p = s * rps + r; p < (s + 1) * rps; p += rl) {
+    float f[8];
+    u_ld8(x + pix_off(n, p, H, C, 0) + c0, f);
+    const uint32_t e0 = (uint32_t)(((size_t)n * H * H + p) * C + c0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float y = a[i] * f[i] + b[i];
+      if (swish) y = y * sigmoidf_(y);
+      if (drop_thr) y *= drop_scale(seed, e0 + i, drop_thr, inv_keep);
+      f[i] = y;
+    }
+    u_st8(out + pix_off(n, p, H, C, out_flat) + c0, f);
+  }
+}
+static inline uint32_t drop_threshold(float p) {
+  if (p <= 0.f) return 0u;
+  double t = (double)p * 4294967296.0;
+  if (t > 4294967295.0) t = 4294967295.0;
+  return (uint32_t)t;
+}
+void launch_gn_apply(const bf16 *x_pad, const float *stats, const float *gamma, const float *beta, bf16 *out,
+                     int out_flat, int swish, float drop_p, uint32_t drop_seed, int n, int H, int C, cudaStream_t st) {
+  const int S = unet_slices(H);
+  k_gn_apply<<<dim3(S, n), kT, 0, st>>>(x_pad, stats, gamma, beta, out, out_flat, swish, drop_threshold(drop_p),
+                                        drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f, drop_seed, H, C, S);
+  ++g_launch_count;
+}
+
+// =================================================================================================================
+// GroupNorm backward
+// =================================================================================================================
+// dyh and xhat of 8 channels of one pixel
+struct GnCh {
+  float mean[8], rstd[8], gam[8], bet[8];
+};
+__device__ __forceinline__ void gn_load_ch(GnCh &ch, const float *stats, const float *gamma, const float *beta, int n,
+                                           int c0, int cpg) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int g = (c0 + i) / cpg;
+    ch.mean[i] = stats[((size_t)n * kGnGroups + g) * 2];
+    ch.rstd[i] = stats[((size_t)n * kGnGroups + g) * 2 + 1];
+    ch.gam[i] = gamma[c0 + i];
+    ch.bet[i] = beta[c0 + i];
+  }
+}
+__device__ __forceinline__ void gn_dyh(const GnCh &ch, const float (&xf)[8], const float (&df)[8], int swish,
+                                       uint32_t drop_thr, float inv_keep, uint32_t seed, uint32_t e0, float (&xhat)[8],
+                                       float (&dyh)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    xhat[i] = (xf[i] - ch.mean[i]) * ch.rstd[i];
+    float d = df[i];
+    if (drop_thr) d *= drop_scale(seed, e0 + i, drop_thr, inv_keep);
+    if (swish) {
+      const float y = ch.gam[i] * xhat[i] + ch.bet[i];
+      const float sg = sigmoidf_(y);
+      d *= sg * (1.f + y * (1.f - sg));
+    }
+    dyh[i] = d;
+  }
+}
+__global__ void __launch_bounds__(kT) k_gn_bwd_reduce(const bf16 *__restrict__ dout, const bf16 *__restrict__ x,
+                                                      const float *__restrict__ stats, const float *__restrict__ gamma,
+                                                      const float *__restrict__ beta, int swish, uint32_t drop_thr,
+                                                      float inv_keep, uint32_t seed, float *__restrict__ partial, int H,
+                                                      int C, int S) {
+  const int n = blockIdx.y, s = blockIdx.x;
+  const int vecs = C >> 3, rl = kT / vecs;
+  const int v = threadIdx.x % vecs, r = threadIdx.x / vecs;
+  const bool active = r < rl;
+  const int cpg = C / kGnGroups, rps = H * H / S, c0 = v * 8;
+  float acc[2][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
+  if (active) {
+    GnCh ch;
+    gn_load_ch(ch, stats, gamma, beta, n, c0, cpg);
+    for (int p = s * rps + r; p < (s + 1) * rps; p += rl) {
+      float xf[8], df[8], xhat[8], dyh[8];
+      u_ld8(x + pix_off(n, p, H, C, 0) + c0, xf);
+      u_ld8(dout + pix_off(n, p, H, C, 1) + c0, df);
+      gn_dyh(ch, xf, df, swish, drop_thr, inv_keep, seed, (uint32_t)(((size_t)n * H * H + p) * C + c0), xhat, dyh);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[0][i] += dyh[i];
+        acc[1][i] += dyh[i] * xhat[i];
+      }
+    }
+  }
+  slice_reduce_store<2>(acc, v, r, rl, active, C, partial + ((size_t)n * S + s) * 2 * C);
+}
+// per (sample, group): coef = (sum_c gamma_c S1[c], sum_c gamma_c S2[c]) / count
+__global__ void __launch_bounds__(32) k_gn_bwd_group(const float *__restrict__ partial, const float *__restrict__ gamma,
+                                                     float *__restrict__ coef, int C, int S, float inv_count) {
+  const int n = blockIdx.x, g = threadIdx.x;
+  const int cpg = C / kGnGroups;
+  float a = 0.f, b = 0.f;
+  for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int s = 0; s < S; ++s) {
+      const float *p = partial + ((size_t)n * S + s) * 2 * C;
+      s1 += p[c];
+      s2 += p[C + c];
+    }
+    a += gamma[c] * s1;
+    b += gamma[c] * s2;
+  }
+  coef[((size_t)n * kGnGroups + g) * 2 + 0] = a * inv_count;
+  coef[((size_t)n * kGnGroups + g) * 2 + 1] = b * inv_count;
+}
+// out_k[c] = sum over rows of partial[row][k][c], rows = n*S; K planes; up to two destinations for plane 0
+__global__ void __launch_bounds__(256) k_sum_rows(const float *__restrict__ partial, int rows, int K, int C,
+                                                  float *__restrict__ d0, float *__restrict__ d0b,
+                                                  float *__restrict__ d1) {
+  __shared__ float red[2][8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < C) {
+    for (int i = ty; i < rows; i += 8) {
+      s0 += partial[(size_t)i * K * C + c];
+      if (K > 1) s1 += partial[(size_t)i * K * C + C + c];
+    }
+  }
+  red[0][ty][tx] = s0;
+  red[1][ty][tx] = s1;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      a += red[0][q][tx];
+      b += red[1][q][tx];
+    }
+    if (d0) d0[c] = a;
+    if (d0b) d0b[c] = a;
+    if (d1 && K > 1) d1[c] = b;
+  }
+}
+__global__ void __launch_bounds__(kT) k_gn_bwd_apply(const bf16 *__restrict__ dout, const bf16 *__restrict__ x,
+                                                     const float *__restrict__ stats, const float *__restrict__ gamma,
+                                                     const float *__restrict__ beta, const float *__restrict__ coef,
+                                                     int swish, uint32_t drop_thr, float inv_keep, uint32_t seed,
+                                                     bf16 *__restrict__ dx, int accumulate, int H, int C, int S) {
+  const int n = blockIdx.y, s = blockIdx.x;
+  const int vecs = C >> 3, rl = kT / vecs;
+  const int v = threadIdx.x % vecs, r = threadIdx.x / vecs;
+  if (r >= rl) return;
+  const int cpg = C / kGnGroups, rps = H * H / S, c0 = v * 8;
+  GnCh ch;
+  gn_load_ch(ch, stats, gamma, beta, n, c0, cpg);
+  float ca[8], cb[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int g = (c0 + i) / cpg;
+    ca[i] = coef[((size_t)n * kGnGroups + g) * 2];
+    cb[i] = coef[((size_t)n * kGnGroups + g) * 2 + 1];
+  }
+  for (int p = s * rps + r; p < (s + 1) * rps; p += rl) {
+    float xf[8], df[8], xhat[8], dyh[8];
+    const size_t po = pix_off(n, p, H, C, 0) + c0;
+    u_ld8(x + po, xf);
+    u_ld8(dout + pix_off(n, p, H, C, 1) + c0, df);
+    gn_dyh(ch, xf, df, swish, drop_thr, inv_keep, seed, (uint32_t)(((size_t)n * H * H + p) * C + c0), xhat, dyh);
+    float o[8];
+    if (accumulate) {
+      u_ld8(dx + po, o);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] += ch.rstd[i] * (ch.gam[i] * dyh[i] - ca[i] - xhat[i] * cb[i]);
+    u_st8(dx + po, o);
+  }
+}
+void launch_gn_backward(const bf16 *dout_flat, const bf16 *x_pad, const float *stats, const float *gamma,
+                        const float *beta, int swish, float drop_p, uint32_t drop_seed, float *partial, float *coef,
+                        float *dgamma, float *dbeta, bf16 *dx_pad, int accumulate, int n, int H, int C,
+                        cudaStream_t st) {
+  const int S = unet_slices(H);
+  const uint32_t thr = drop_threshold(drop_p);
+  const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  k_gn_bwd_reduce<<<dim3(S, n), kT, 0, st>>>(dout_flat, x_pad, stats, gamma, beta, swish, thr, inv_keep, drop_seed,
+                                             partial, H, C, S);
+  k_gn_bwd_group<<<n, 32, 0, st>>>(partial, gamma, coef, C, S, 1.f / ((float)(C / kGnGroups) * H * H));
+  k_sum_rows<<<(C + 31) / 32, 256, 0, st>>>(partial, n * S, 2, C, dbeta, nullptr, dgamma);
+  k_gn_bwd_apply<<<dim3(S, n), kT, 0, st>>>(dout_flat, x_pad, stats, gamma, beta, coef, swish, thr, inv_keep, drop_seed,
+                                            dx_pad, accumulate, H, C, S);
+  g_launch_count += 4;
+}
+
+// =================================================================================================================
+// bias gradients
+// =================================================================================================================
+__global__ void __launch_bounds__(kT) k_colsum(const bf16 *__restrict__ dy, int flat, float *__restrict__ partial, int H,
+                                               int C, int S) {
+  const int n = blockIdx.y, s = blockIdx.x;
+  const int vecs = C >> 3, rl = kT / vecs;
+  const int v = threadIdx.x % vecs, r = threadIdx.x / vecs;
+  const bool active = r < rl;
+  const int rps = H * H / S;
+  float acc[1][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[0][i] = 0.f;
+  if (active) {
+    for (int p = s * rps + r; p < (s + 1) * rps; p += rl) {
+      float f[8];
+      u_ld8(dy + pix_off(n, p, H, C, flat) + v * 8, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[0][i] += f[i];
+    }
+  }
+  slice_reduce_store<1>(acc, v, r, rl, active, C, partial + ((size_t)n * S + s) * C);
+}
+__global__ void k_rowsum_slices(const float *__restrict__ partial, float *__restrict__ rowsum, int ld, int col0, int C,
+                                int S) {
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+    for (int s = 0; s < S; ++s) a += partial[((size_t)n * S + s) * C + c];
+    rowsum[(size_t)n * ld + col0 + c] = a;
+  }
+}
+void launch_bias_grad(const bf16 *dy, int dy_flat, float *partial, float *bias_grad_a, float *bias_grad_b, float *rowsum,
+                      int rowsum_ld, int rowsum_col0, int n, int H, int C, cudaStream_t st) {
+  const int S = unet_slices(H);
+  k_colsum<<<dim3(S, n), kT, 0, st>>>(dy, dy_flat, partial, H, C, S);
+  k_sum_rows<<<(C + 31) / 32, 256, 0, st>>>(partial, n * S, 1, C, bias_grad_a, bias_grad_b, nullptr);
+  g_launch_count += 2;
+  if (rowsum) {
+    k_rowsum_slices<<<n, 256, 0, st>>>(partial, rowsum, rowsum_ld, rowsum_col0, C, S);
+    ++g_launch_count;
+  }
+}
+
+// =================================================================================================================
+// copies
+// =================================================================================================================
+static inline int grid_for(long long total) {
+  long long g = (total + kT - 1) / kT;
+  if (g > 148 * 8) g = 148 * 8;
+  return (int)(g < 1 ? 1 : g);
+}
+// i -> (pixel m in n*H*H, vector v of `vecs`)
+__global__ void __launch_bounds__(kT) k_concat(const bf16 *__restrict__ a, int Ca, const bf16 *__restrict__ b, int Cb,
+                                               bf16 *__restrict__ out, long long total, int H) {
+  const int C = Ca + Cb, vecs = C >> 3, hw = H * H;
+  for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+    const int v = (int)(i % vecs);
+    const int m = (int)(i / vecs);
+    const int n = m / hw, p = m - n * hw;
+    const int c = v * 8;
+    const uint4 val = c < Ca ? *reinterpret_cast<const uint4 *>(a + pix_off(n, p, H, Ca, 0) + c)
+                             : *reinterpret_cast<const uint4 *>(b + pix_off(n, p, H, Cb, 0) + (c - Ca));
+    *reinterpret_cast<uint4 *>(out + pix_off(n, p, H, C, 0) + c) = val;
+  }
+}
+void launch_concat(const bf16 *a_pad, int Ca, const bf16 *b_pad, int Cb, bf16 *out_pad, int n, int H, cudaStream_t st) {
+  const long long total = (long long)n * H * H * ((Ca + Cb) >> 3);
+  k_concat<<<grid_for(total), kT, 0, st>>>(a_pad, Ca, b_pad, Cb, out_pad, total, H);
+  ++g_launch_count;
+}
+__global__ void __launch_bounds__(kT) k_split(const bf16 *__restrict__ dcat, bf16 *__restrict__ da, int Ca, int acc_a,
+                                              bf16 *__restrict__ db, int Cb, int acc_b, long long total, int H) {
+  const int C = Ca + Cb, vecs = C >> 3, hw = H * H;
+  for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+    const int v = (int)(i % vecs);
+    const int m = (int)(i / vecs);
+    const int n = m / hw, p = m - n * hw;
+    const int c = v * 8;
+    float f[8];
+    u_ld8(dcat + pix_off(n, p, H, C, 0) + c, f);
+    bf16 *dst = c < Ca ? da + pix_off(n, p, H, Ca, 0) + c : db + pix_off(n, p, H, Cb, 0) + (c - Ca);
+    if (c < Ca ? acc_a : acc_b) {
+      float o[8];
+      u_ld8(dst, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += o[j];
+    }
+    u_st8(dst, f);
+  }
+}
+void launch_split(const bf16 *dcat_pad, bf16 *da_pad, int Ca, int acc_a, bf16 *db_pad, int Cb, int acc_b, int n, int H,
+                  cudaStream_t st) {
+  const long long total = (long long)n * H * H * ((Ca + Cb) >> 3);
+  k_split<<<grid_for(total), kT, 0, st>>>(dcat_pad, da_pad, Ca, acc_a, db_pad, Cb, acc_b, total, H);
+  ++g_launch_count;
+}
+__global__ void __launch_bounds__(kT) k_add_into(const bf16 *__restrict__ src, bf16 *__restrict__ dst, int accumulate,
+                                                 long long nvec) {
+  for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < nvec; i += (long long)gridDim.x * kT) {
+    if (!accumulate) {
+      reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(src)[i];
+    } else {
+      float a[8], b[8];
+      u_ld8(src + i * 8, a);
+      u_ld8(dst + i * 8, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += b[j];
+      u_st8(dst + i * 8, a);
+    }
+  }
+}
+void launch_add_into(const bf16 *src, bf16 *dst, int accumulate, long long count, cudaStream_t st) {
+  k_add_into<<<grid_for(count >> 3), kT, 0, st>>>(src, dst, accumulate, count >> 3);
+  ++g_launch_count;
+}
+// out side 2H
+__global__ void __launch_bounds__(kT) k_upsample2(const bf16 *__restrict__ in, bf16 *__restrict__ out, long long total,
+                                                  int H, int C) {
+  const int vecs = C >> 3, Ho = 2 * H, hwo = Ho * Ho;
+  for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+    const int v = (int)(i % vecs);
+    const int m = (int)(i / vecs);
+    const int n = m / hwo, p = m - n * hwo;
+    const int y = p / Ho, x = p - y * Ho;
+    const uint4 val = *reinterpret_cast<const uint4 *>(in + pix_off(n, (y >> 1) * H + (x >> 1), H, C, 0) + v * 8);
+    *reinterpret_cast<uint4 *>(out + pix_off(n, p, Ho, C, 0) + v * 8) = val;
+  }
+}
+void launch_upsample2(const bf16 *in_pad, bf16 *out_pad, int n, int H, int C, cudaStream_t st) {
+  const long long total = (long long)n * 4 * H * H * (C >> 3);
+  k_upsample2<<<grid_for(total), kT, 0, st>>>(in_pad, out_pad, total, H, C);
+  ++g_launch_count;
+}
+__global__ void __launch_bounds__(kT) k_upsample2_bwd(const bf16 *__restrict__ dout, bf16 *__restrict__ din,
+                                                      int accumulate, long long total, int H, int C) {
+  const int vecs = C >> 3, Ho = 2 * H, hw = H * H;
+  for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+    const int v = (int)(i % vecs);
+    const int m = (int)(i / vecs);
+    const int n = m / hw, p = m - n * hw;
+    const int y = p / H, x = p - y * H;
+    float s[8];
+    bf16 *dst = din + pix_off(n, p, H, C, 0) + v * 8;
+    if (accumulate) {
+      u_ld8(dst, s);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] = 0.f;
+    }
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        float f[8];
+        u_ld8(dout + pix_off(n, (2 * y + dy) * Ho + 2 * x + dx, Ho, C, 0) + v * 8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += f[j];
+      }
+    u_st8(dst, s);
+  }
+}
+void launch_upsample2_bwd(const bf16 *dout_pad, bf16 *din_pad, int accumulate, int n, int H, int C, cudaStream_t st) {
+  const long long total = (long long)n * H * H * (C >> 3);
+  k_upsample2_bwd<<<grid_for(total), kT, 0, st>>>(dout_pad, din_pad, accumulate, total, H, C);
+  ++g_launch_count;
+}
+// Downsample: out(oy, ox) = sum_{ky,kx} w[ky][kx] . in(2oy + ky, 2ox + kx), in(H, .) = in(., H) = 0: padded coordinate
+// (2oy + ky + 1, 2ox + kx + 1), the last row / column falls into the zero halo.
+__global__ void __launch_bounds__(kT) k_down_im2col(const bf16 *__restrict__ in, bf16 *__restrict__ col, long long total,
+                                                    int H, int C) {
+  const int vecs = C >> 3, Ho = H / 2, hwo = Ho * Ho, Hp = H + 2;
+  for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+    const int v = (int)(i % vecs);
+    long long t = i / vecs;
+    const int tap = (int)(t % 9);
+    const int mo = (int)(t / 9);
+    const int n = mo / hwo, p = mo - n * hwo;
+    const int oy = p / Ho, ox = p - oy * Ho;
+    const int ky = tap / 3, kx = tap - ky * 3;
+    const int py = 2 * oy + ky + 1, px = 2 * ox + kx + 1;
+    const uint4 val = *reinterpret_cast<const uint4 *>(in + (((size_t)n * Hp + py) * Hp + px) * C + v * 8);
+    *reinterpret_cast<uint4 *>(col + ((size_t)mo * 9 + tap) * C + v * 8) = val;
+  }
+}
+void launch_down_im2col(const bf16 *in_pad, bf16 *col, int n, int H, int C, cudaStream_t st) {
+  const long long total = (long long)n * (H / 2) * (H / 2) * 9 * (C >> 3);
+  k_down_im2col<<<grid_for(total), kT, 0, st>>>(in_pad, col, total, H, C);
+  ++g_launch_count;
+}
+// gather form: input pixel (y, x) receives dcol[(oy, ox)][tap (ky, kx)] for every 2oy + ky == y, 2ox + kx == x
+__global__ void __launch_bounds__(kT) k_down_col2im(const bf16 *__restrict__ dcol, bf16 *__restrict__ din,
+                                                    int accumulate, long long total, int H, int C) {
+  const int vecs = C >> 3, Ho = H / 2, hw = H * H;
+  for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+    const int v = (int)(i % vecs);
+    const int m = (int)(i / vecs);
+    const int n = m / hw, p = m - n * hw;
+    const int y = p / H, x = p - y * H;
+    float s[8];
+    bf16 *dst = din + pix_off(n, p, H, C, 0) + v * 8;
+    if (accumulate) {
+      u_ld8(dst, s);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] = 0.f;
+    }
+    for (int ky = 0; ky < 3; ++ky) {
+      const int ty = y - ky;
+      if (ty < 0 || (ty & 1)) continue;
+      const int oy = ty >> 1;
+      if (oy >= Ho) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int tx = x - kx;
+        if (tx < 0 || (tx & 1)) continue;
+        const int ox = tx >> 1;
+        if (ox >= Ho) continue;
+        float f[8];
+        u_ld8(dcol + (((size_t)n * Ho * Ho + oy * Ho + ox) * 9 + ky * 3 + kx) * C + v * 8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += f[j];
+      }
+    }
+    u_st8(dst, s);
+  }
+}
+void launch_down_col2im(const bf16 *dcol, bf16 *din_pad, int accumulate, int n, int H, int C, cudaStream_t st) {
+  const long long total = (long long)n * H * H * (C >> 3);
+  k_down_col2im<<<grid_for(total), kT, 0, st>>>(dcol, din_pad, accumulate, total, H, C);
+  ++g_launch_count;
+}
+
+__global__ void __launch_bounds__(kT) k_eps_out(const float *__restrict__ y, const float *__restrict__ bias3,
+                                                float *__restrict__ eps, int total, int hw) {
+  const int i = blockIdx.x * kT + threadIdx.x;  // over n*3*hw, output order
+  if (i >= total) return;
+  const int p = i % hw, c = (i / hw) % 3, n = i / (3 * hw);
+  eps[i] = y[((size_t)n * hw + p) * 64 + c] + bias3[c];
+}
+void launch_eps_out(const float *y, const float *bias3, float *eps_nchw, int n, int H, cudaStream_t st) {
+  const int total = n * 3 * H * H;
+  k_eps_out<<<(total + kT - 1) / kT, kT, 0, st>>>(y, bias3, eps_nchw, total, H * H);
+  ++g_launch_count;
+}
+__global__ void __launch_bounds__(kT) k_eps_in(const float *__restrict__ deps, bf16 *__restrict__ dy, int total, int H) {
+  const int m = blockIdx.x * kT + threadIdx.x;  // over n*hw pixels
+  if (m >= total) return;
+  const int hw = H * H, n = m / hw, p = m - n * hw;
+  bf16 *dst = dy + pix_off(n, p, H, 64, 0);
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = 0.f;
+  for (int c = 0; c < 3; ++c) f[c] = deps[((size_t)n * 3 + c) * hw + p];
+  u_st8(dst, f);
+}
+__global__ void __launch_bounds__(256) k_eps_bias_grad(const float *__restrict__ deps, float *__restrict__ dbias3, int n,
+                                                       int hw) {
+  __shared__ float red[256];
+  const int c = blockIdx.x;
+  float s = 0.f;
+  for (int i = 0; i < n; ++i)
+    for (int p = threadIdx.x; p < hw; p += 256) s += deps[((size_t)i * 3 + c) * hw + p];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) dbias3[c] = red[0];
+}
+void launch_eps_in(const float *deps_nchw, bf16 *dy_pad, float *dbias3, int n, int H, cudaStream_t st) {
+  const int total = n * H * H;
+  k_eps_in<<<(total + kT - 1) / kT, kT, 0, st>>>(deps_nchw, dy_pad, total, H);
+  k_eps_bias_grad<<<3, 256, 0, st>>>(deps_nchw, dbias3, n, H * H);
+  g_launch_count += 2;
+}
+
+// =================================================================================================================
+// attention: softmax rows (one warp per row), batched transposes
+// =================================================================================================================
+__global__ void __launch_bounds__(256) k_softmax(const float *__restrict__ S, bf16 *__restrict__ P, int M, int Te, int T,
+                                                 float scale) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const int blk0 = ((row % Te) / T) * T;  // first key column of this row's sample inside its group
+  const float *s = S + (size_t)row * Te;
+  float v[8];
+  const int per = Te / 32;  // 4 or 8
+  float mx = -INFINITY;
+  for (int i = 0; i < per; ++i) {
+    const int j = lane + 32 * i;
+    const bool ok = j >= blk0 && j < blk0 + T;
+    v[i] = ok ? s[j] * scale : -INFINITY;
+    mx = fmaxf(mx, v[i]);
+  }
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int i = 0; i < per; ++i) {
+    v[i] = v[i] == -INFINITY ? 0.f : __expf(v[i] - mx);
+    sum += v[i];
+  }
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.f / sum;
+  for (int i = 0; i < per; ++i) P[(size_t)row * Te + lane + 32 * i] = __float2bfloat16(v[i] * inv);
+}
+void launch_softmax(const float *S, bf16 *P, int M, int Te, int T, float scale, cudaStream_t st) {
+  k_softmax<<<(M + 7) / 8, 256, 0, st>>>(S, P, M, Te, T, scale);
+  ++g_launch_count;
+}
+__global__ void __launch_bounds__(256) k_softmax_bwd(const float *__restrict__ dP, const bf16 *__restrict__ P,
+                                                     bf16 *__restrict__ dS, int M, int Te, float scale) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const int per = Te / 32;
+  float p[8], d[8], dot = 0.f;
+  for (int i = 0; i < per; ++i) {
+    const size_t j = (size_t)row * Te + lane + 32 * i;
+    p[i] = __bfloat162float(P[j]);
+    d[i] = dP[j];
+    dot += p[i] * d[i];
+  }
+  for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  for (int i = 0; i < per; ++i)
+    dS[(size_t)row * Te + lane + 32 * i] = __float2bfloat16(scale * p[i] * (d[i] - dot));
+}
+void launch_softmax_bwd(const float *dP, const bf16 *P, bf16 *dS, int M, int Te, float scale, cudaStream_t st) {
+  k_softmax_bwd<<<(M + 7) / 8, 256, 0, st>>>(dP, P, dS, M, Te, scale);
+  ++g_launch_count;
+}
+__global__ void __launch_bounds__(256) k_transpose(const bf16 *__restrict__ in, int ld_in, bf16 *__restrict__ out, int R,
+                                                   int Cc) {
+  __shared__ bf16 tile[32][34];
+  const int g = blockIdx.z, c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const bf16 *src = in + (size_t)g * R * ld_in;
+  bf16 *dst = out + (size_t)g * Cc * R;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) tile[ty + 8 * j][tx] = src[(size_t)(r0 + ty + 8 * j) * ld_in + c0 + tx];
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) dst[(size_t)(c0 + ty + 8 * j) * R + r0 + tx] = tile[tx][ty + 8 * j];
+}
+void launch_transpose(const bf16 *in, int ld_in, bf16 *out, int R, int Cc, int G, cudaStream_t st) {
+  k_transpose<<<dim3(Cc / 32, R / 32, G), 256, 0, st>>>(in, ld_in, out, R, Cc);
+  ++g_launch_count;
+}
+
+// =================================================================================================================
+// embedding MLPs
+// =================================================================================================================
+__global__ void k_emb_inputs(const float *__restrict__ t, const int64_t *__restrict__ c, const uint8_t *__restrict__ drop,
+                             const float *__restrict__ class_emb, const float *__restrict__ null_emb,
+                             float *__restrict__ sincos, float *__restrict__ ce, int n, int ch) {
+  const int i = blockIdx.x, d = threadIdx.x;
+  if (d >= ch) return;
+  const int half = ch / 2;
+  const float k = -(float)(log(10000.0) / (double)(half - 1));
+  const int j = d < half ? d : d - half;
+  const float ang = t[i] * expf((float)j * k);
+  sincos[(size_t)i * ch + d] = d < half ? sinf(ang) : cosf(ang);
+  const bool dr = drop && drop[i];
+  ce[(size_t)i * ch + d] = dr ? null_emb[d] : class_emb[(size_t)c[i] * ch + d];
+}
+void launch_emb_inputs(const float *t, const int64_t *c, const uint8_t *drop, const float *class_emb,
+                       const float *null_emb, float *sincos, float *ce, int n, int ch, cudaStream_t st) {
+  k_emb_inputs<<<n, ch, 0, st>>>(t, c, drop, class_emb, null_emb, sincos, ce, n, ch);
+  ++g_launch_count;
+}
+// 64 x 64 tile, 16-deep k steps, 4 x 4 outputs per thread
+__global__ void __launch_bounds__(256) k_sgemm(const float *__restrict__ A, long long sai, long long sak,
+                                               const float *__restrict__ B, long long sbk, long long sbj,
+                                               float *__restrict__ C, int ldc, int M, int N, int K,
+                                               const float *__restrict__ bias, int accumulate) {
+  __shared__ float As[16][65], Bs[16][65];
+  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = threadIdx.x + 256 * q;
+      // A tile: consecutive threads walk the dimension that is contiguous in memory
+      int ai, ak;
+      if (sak == 1) { ak = e & 15; ai = e >> 4; } else { ai = e & 63; ak = e >> 6; }
+      As[ak][ai] = (i0 + ai < M && k0 + ak < K) ? A[(long long)(i0 + ai) * sai + (long long)(k0 + ak) * sak] : 0.f;
+      int bj, bk;
+      if (sbk == 1) { bk = e & 15; bj = e >> 4; } else { bj = e & 63; bk = e >> 6; }
+      Bs[bk][bj] = (j0 + bj < N && k0 + bk < K) ? B[(long long)(k0 + bk) * sbk + (long long)(j0 + bj) * sbj] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        a[q] = As[k][ty * 4 + q];
+        b[q] = Bs[k][tx * 4 + q];
+      }
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[p][q] += a[p] * b[q];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int i = i0 + ty * 4 + p;
+    if (i >= M) continue;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = j0 + tx * 4 + q;
+      if (j >= N) continue;
+      float v = acc[p][q] + (bias ? bias[j] : 0.f);
+      if (accumulate) v += C[(size_t)i * ldc + j];
+      C[(size_t)i * ldc + j] = v;
+    }
+  }
+}
+void launch_sgemm(const float *A, long long sai, long long sak, const float *B, long long sbk, long long sbj, float *C,
+                  int ldc, int M, int N, int K, const float *bias, int accumulate, cudaStream_t st) {
+  k_sgemm<<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, st>>>(A, sai, sak, B, sbk, sbj, C, ldc, M, N, K, bias,
+                                                             accumulate);
+  ++g_launch_count;
+}
+__global__ void k_swish_f32(const float *__restrict__ in, float *__restrict__ out, long long count) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) {
+    const float x = in[i];
+    out[i] = x / (1.f + expf(-x));
+  }
+}
+void launch_swish_f32(const float *in, float *out, long long count, cudaStream_t st) {
+  k_swish_f32<<<(int)((count + 255) / 256), 256, 0, st>>>(in, out, count);
+  ++g_launch_count;
+}
+__global__ void k_dswish_f32(const float *__restrict__ dy, const float *__restrict__ pre, float *__restrict__ out,
+                             long long count) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) {
+    const float x = pre[i];
+    const float sg = 1.f / (1.f + expf(-x));
+    out[i] = dy[i] * sg * (1.f + x * (1.f - sg));
+  }
+}
+void launch_dswish_f32(const float *dy, const float *pre, float *out, long long count, cudaStream_t st) {
+  k_dswish_f32<<<(int)((count + 255) / 256), 256, 0, st>>>(dy, pre, out, count);
+  ++g_launch_count;
+}
+__global__ void k_colsum_f32(const float *__restrict__ a, int ld, int rows, int cols, float *__restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cols) return;
+  float s = 0.f;
+  for (int i = 0; i < rows; ++i) s += a[(size_t)i * ld + j];
+  out[j] = s;
+}
+void launch_colsum_f32(const float *a, int ld, int rows, int cols, float *out, cudaStream_t st) {
+  k_colsum_f32<<<(cols + 127) / 128, 128, 0, st>>>(a, ld, rows, cols, out);
+  ++g_launch_count;
+}
+__global__ void k_emb_scatter(const float *__restrict__ dce, const int64_t *__restrict__ c,
+                              const uint8_t *__restrict__ drop, float *__restrict__ d_class_emb,
+                              float *__restrict__ d_null, int n, int ch, int n_classes) {
+  const int k = blockIdx.x, d = threadIdx.x;  // k == n_classes: the null embedding
+  if (d >= ch) return;
+  float s = 0.f;
+  for (int i = 0; i < n; ++i) {
+    const bool dr = drop && drop[i];
+    const bool mine = k == n_classes ? dr : (!dr && (int)c[i] == k);
+    if (mine) s += dce[(size_t)i * ch + d];
+  }
+  if (k == n_classes)
+    d_null[d] = s;
+  else
+    d_class_emb[(size_t)k * ch + d] = s;
+}
+void launch_emb_scatter(const float *dce, const int64_t *c, const uint8_t *drop, float *d_class_emb, float *d_null, int n,
+                        int ch, int n_classes, cudaStream_t st) {
+  k_emb_scatter<<<n_classes + 1, ch, 0, st>>>(dce, c, drop, d_class_emb, d_null, n, ch, n_classes);
+  ++g_launch_count;
+}
+
+}  // namespace salun

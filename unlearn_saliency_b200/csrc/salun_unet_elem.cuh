@@ -1,0 +1,88 @@
+// salun_unet_elem.cuh -- launchers of the HBM-bound kernels of the DDPM U-Net path (salun_unet.cu): GroupNorm + swish
+// (+ dropout) forward / backward, per-sample column reductions (bias and temb-projection gradients), skip concat /
+// split, nearest upsample, strided-conv patches, softmax, batched transposes, the timestep / class embedding MLPs.
+// Replaces the ATen elementwise chain of DDPM/models/diffusion.py:38-192,357-413 and its autograd backward.
+//
+// Activation layouts (bf16, square power-of-two images of side H):
+//   padded ("P"): [n][H+2][H+2][C], zero halo, written once -- what the 4-D-TMA convolution kernels read
+//   flat   ("F"): [n*H*H][C]
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace salun {
+
+constexpr int kGnGroups = 32;  // Normalize() = GroupNorm(32, C, eps 1e-6)   diffusion.py:43-46
+
+// slices of one image's H*H pixels handled by separate CTAs in the per-sample kernels
+int unet_slices(int H);
+
+// ---- GroupNorm forward: partial[n][S][2][C] (sum x, sum x^2) -> stats[n][32][2] (mean, rstd) -> apply ----
+void launch_gn_stats(const __nv_bfloat16 *x_pad, float *partial, float *stats, int n, int H, int C, float eps,
+                     cudaStream_t st);
+// out = dropout(act(gamma * (x - mean) * rstd + beta)); act = swish or identity; out padded (out_flat = 0) or flat
+void launch_gn_apply(const __nv_bfloat16 *x_pad, const float *stats, const float *gamma, const float *beta,
+                     __nv_bfloat16 *out, int out_flat, int swish, float drop_p, uint32_t drop_seed, int n, int H, int C,
+                     cudaStream_t st);
+// ---- GroupNorm backward.  dout: gradient w.r.t. the GN(+swish+dropout) output, FLAT [n*H*H][C] ----
+//   partial[n][S][2][C] = per-sample sums over pixels of dyh and dyh * xhat        (dyh = dout * act'(yh) * dropmask)
+//   dgamma[c] = sum_n,pix dyh*xhat ; dbeta[c] = sum dyh ; coef[n][32][2] = (sum_c gamma dyh, sum_c gamma dyh xhat) / count
+//   dx = rstd * (gamma*dyh - coefA - xhat*coefB), written padded; accumulate != 0: added to what dx already holds
+void launch_gn_backward(const __nv_bfloat16 *dout_flat, const __nv_bfloat16 *x_pad, const float *stats,
+                        const float *gamma, const float *beta, int swish, float drop_p, uint32_t drop_seed,
+                        float *partial, float *coef, float *dgamma, float *dbeta, __nv_bfloat16 *dx_pad, int accumulate,
+                        int n, int H, int C, cudaStream_t st);
+
+// ---- bias gradients: per-sample column sums of dY (padded or flat), then reductions ----
+//   partial[n][S][C]; bias_grad_a / bias_grad_b [C] (either may be NULL) = sum over samples and pixels;
+//   rowsum (optional) [n][rowsum_ld] at column rowsum_col0: per-sample sums (gradient of the temb/cemb projection output)
+void launch_bias_grad(const __nv_bfloat16 *dy, int dy_flat, float *partial, float *bias_grad_a, float *bias_grad_b,
+                      float *rowsum, int rowsum_ld, int rowsum_col0, int n, int H, int C, cudaStream_t st);
+
+// ---- copies on padded tensors ----
+void launch_concat(const __nv_bfloat16 *a_pad, int Ca, const __nv_bfloat16 *b_pad, int Cb, __nv_bfloat16 *out_pad, int n,
+                   int H, cudaStream_t st);
+// da (=|+=) dcat[..., :Ca] ; db (=|+=) dcat[..., Ca:]
+void launch_split(const __nv_bfloat16 *dcat_pad, __nv_bfloat16 *da_pad, int Ca, int acc_a, __nv_bfloat16 *db_pad, int Cb,
+                  int acc_b, int n, int H, cudaStream_t st);
+// dst (=|+=) src over `count` bf16 elements (count % 8 == 0)
+void launch_add_into(const __nv_bfloat16 *src, __nv_bfloat16 *dst, int accumulate, long long count, cudaStream_t st);
+// nearest x2 (F.interpolate(scale_factor=2, mode="nearest"), diffusion.py:59): in side H -> out side 2H
+void launch_upsample2(const __nv_bfloat16 *in_pad, __nv_bfloat16 *out_pad, int n, int H, int C, cudaStream_t st);
+void launch_upsample2_bwd(const __nv_bfloat16 *dout_pad, __nv_bfloat16 *din_pad, int accumulate, int n, int H, int C,
+                          cudaStream_t st);
+// Downsample (diffusion.py:75-79): pad (0,1,0,1) then 3x3 / stride 2 / no padding.  col[n*Ho*Ho][9*C], tap-major
+void launch_down_im2col(const __nv_bfloat16 *in_pad, __nv_bfloat16 *col, int n, int H, int C, cudaStream_t st);
+void launch_down_col2im(const __nv_bfloat16 *dcol, __nv_bfloat16 *din_pad, int accumulate, int n, int H, int C,
+                        cudaStream_t st);
+// eps[n][3][H][H] fp32 = y[m][0..2] + bias   (y: fp32 [n*H*H][64] GEMM output of conv_out padded to 64 channels)
+void launch_eps_out(const float *y, const float *bias3, float *eps_nchw, int n, int H, cudaStream_t st);
+// dy_pad[n][H+2][H+2][64] bf16 (channels 0..2) = deps[n][3][H][H]; dbias3 = sum over n, pixels
+void launch_eps_in(const float *deps_nchw, __nv_bfloat16 *dy_pad, float *dbias3, int n, int H, cudaStream_t st);
+
+// ---- attention (diffusion.py:167-192): rows of S fp32 [M][Te] -> P bf16; block-diagonal mask of block T inside Te ----
+void launch_softmax(const float *S, __nv_bfloat16 *P, int M, int Te, int T, float scale, cudaStream_t st);
+// dS = scale * P * (dP - sum_j dP*P)
+void launch_softmax_bwd(const float *dP, const __nv_bfloat16 *P, __nv_bfloat16 *dS, int M, int Te, float scale,
+                        cudaStream_t st);
+// out[g][c][r] = in[g][r][c]; in rows have stride ld_in, out rows stride R; G groups of R rows; R, Cc multiples of 32
+void launch_transpose(const __nv_bfloat16 *in, int ld_in, __nv_bfloat16 *out, int R, int Cc, int G, cudaStream_t st);
+
+// ---- embedding MLPs (fp32, CUDA cores; tiny) ----
+// sincos[n][ch] (get_timestep_embedding, diffusion.py:17-35) and ce[n][ch] = drop[n] ? null_emb : class_emb[c[n]]
+void launch_emb_inputs(const float *t, const int64_t *c, const uint8_t *drop, const float *class_emb,
+                       const float *null_emb, float *sincos, float *ce, int n, int ch, cudaStream_t st);
+// C[i][j] (=|+=) sum_k A[i*sai + k*sak] * B[k*sbk + j*sbj] (+ bias[j])
+void launch_sgemm(const float *A, long long sai, long long sak, const float *B, long long sbk, long long sbj, float *C,
+                  int ldc, int M, int N, int K, const float *bias, int accumulate, cudaStream_t st);
+void launch_swish_f32(const float *in, float *out, long long count, cudaStream_t st);
+// out = dy * swish'(pre)
+void launch_dswish_f32(const float *dy, const float *pre, float *out, long long count, cudaStream_t st);
+// out[j] = sum_i a[i*ld + j]
+void launch_colsum_f32(const float *a, int ld, int rows, int cols, float *out, cudaStream_t st);
+// gradient of the embedding lookup: d_class_emb[k][:] = sum_{i: c[i]==k, !drop[i]} dce[i][:] ; d_null = sum_{drop[i]} dce[i]
+void launch_emb_scatter(const float *dce, const int64_t *c, const uint8_t *drop, float *d_class_emb, float *d_null,
+                        int n, int ch, int n_classes, cudaStream_t st);
+
+}  // namespace salun
