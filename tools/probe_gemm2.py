@@ -27,6 +27,9 @@ def timeit(fn, iters=20):
 
 shapes = [(16384, 256, 2304), (4096, 512, 4608), (65536, 128, 1152), (8192, 8192, 8192), (16384, 1024, 1024),
           (200704, 256, 64), (12544, 512, 1024), (3136, 2048, 512)]
+if len(sys.argv) > 1 and sys.argv[1] == "unet":  # conv GEMM shapes of the DDPM U-Net at batch 256 (M = n*H*H, N = Cout, K = 9*Cin)
+    shapes = [(262144, 128, 1152), (262144, 128, 3456), (262144, 128, 2304), (65536, 256, 2304), (65536, 256, 4608),
+              (65536, 256, 3456), (16384, 256, 4608), (4096, 256, 4608), (262144, 384, 1152), (65536, 512, 2304)]
 for M, N, K in shapes:
     A = torch.randn(M, K, device="cuda").bfloat16()
     B = torch.randn(N, K, device="cuda").bfloat16()

@@ -1111,6 +1111,24 @@ int make_tmap_2d_bf16(CUtensorMap *m, const void *base, uint64_t rows, uint64_t 
   return SALUN_OK;
 }
 
+int make_tmap_2d_bf16_ld(CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                         uint32_t box_cols) {
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  SALUN_ENCODE_OR_FAIL();
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstr, box,
+                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(2d rows=%llu cols=%llu ld=%llu box=%ux%u) failed: %d", (unsigned long long)rows,
+              (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols, (int)r);
+    return SALUN_ERR_CUDA;
+  }
+  return SALUN_OK;
+}
+
 int make_tmap_4d_bf16(CUtensorMap *m, const void *base, uint64_t C, uint64_t Wp, uint64_t Hp, uint64_t N,
                       TmapBox4 bx) {
   cuuint64_t gdim[4] = {C, Wp, Hp, N};
@@ -1265,7 +1283,19 @@ static bool gemm_persistent() {
   return v == 1;
 }
 
+static bool gemm_log() {  // SALUN_GEMM_LOG=1: one stderr line per tensor-core launch (shape), to pair with an ncu launch list
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SALUN_GEMM_LOG");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 int launch_conv_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvGemmArgs &a, int bn, cudaStream_t st) {
+  if (gemm_log())
+    fprintf(stderr, "GEMMLOG M=%d N=%d K=%d mode=%d bn=%d H=%d batched=%d\n", a.M, a.N, a.num_k_blocks * 64, a.mode_a, bn, a.H,
+            a.batch_rows_a);
   prof_open(0, 2.0 * a.M * a.N * (double)a.num_k_blocks * 64.0, st);
   int rc;
   if (gemm_persistent()) {
@@ -1370,6 +1400,8 @@ int launch_wgrad(const CUtensorMap &tmA, const CUtensorMap &tmB, const WgradArgs
     attr_set = true;
   }
   dim3 grid(co_tiles, col_groups, splits);
+  if (gemm_log())
+    fprintf(stderr, "WGLOG pixels=%d Cout=%d Kc=%d grid=%d,%d,%d\n", a.kb_total * 64, a.Cout, a.kvalid, co_tiles, col_groups, splits);
   prof_open(1, 2.0 * (double)a.kb_total * 64.0 * a.Cout * (double)a.kvalid, st);
   WgradArgs aa = a;
   aa.dbg = g_dbg;

@@ -89,6 +89,9 @@ struct TmapBox4 {
 
 int make_tmap_2d_bf16(CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows,
                       uint32_t box_cols);
+// same with a row stride of `ld` elements (ld >= cols, ld * 2 bytes a multiple of 16); columns >= cols read as zero
+int make_tmap_2d_bf16_ld(CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                         uint32_t box_cols);
 int make_tmap_4d_bf16(CUtensorMap *m, const void *base, uint64_t C, uint64_t Wp, uint64_t Hp, uint64_t N,
                       TmapBox4 box);
 

@@ -90,6 +90,8 @@ struct UAttnMaps {
 struct UPlan {
   std::vector<UConvMaps> conv;
   std::vector<UAttnMaps> attn;
+  CUtensorMap e_a, wcat_b, drb_a, wcatT_b, drbt_a, et_b;  // projection GEMMs (forward, dE, dW)
+  int bn_rb, bn_de, bn_dw;
 };
 
 }  // namespace salun
@@ -113,6 +115,11 @@ struct salun_unet {
   int emb;      // 4 * ch
   int ld_rb;    // sum of the ResnetBlock output widths
   float *sincos, *ce, *pre_t, *h_t, *pre_c, *h_c, *cat, *E, *RB, *dRB, *dE, *dcat, *dh, *dpre, *dce;
+  // all temb_cemb_proj Linears as one tensor-core GEMM (operands staged per step)
+  bf16 *wcat, *wcatT, *E_bf, *Et_bf, *dRB_bf, *dRBt_bf;
+  float *bcat, *dWcat, *persample;
+  long long *row_w, *row_b;
+  int nb32;
   float *t_dev;
   int64_t *c_dev;
   uint8_t *drop_dev;
@@ -475,6 +482,19 @@ static int build_plan(salun_unet *net, int n, UPlan **out) {
     TRY(make_tmap_2d_bf16(&m.ds, net->dS, M, A.Te, 128, 64));               // A of dQ = dS Kt^T
     (void)m.vt128;
   }
+  {
+    const int E8 = net->emb + 512, R = net->ld_rb;
+    plan.bn_rb = u_pick_bn(R, n);
+    plan.bn_de = u_pick_bn(E8, n);
+    plan.bn_dw = u_pick_bn(E8, R);
+    TRY(make_tmap_2d_bf16(&plan.e_a, net->E_bf, n, E8, 128, 64));
+    TRY(make_tmap_2d_bf16(&plan.wcat_b, net->wcat, R, E8, plan.bn_rb, 64));
+    TRY(make_tmap_2d_bf16(&plan.drb_a, net->dRB_bf, n, R, 128, 64));
+    TRY(make_tmap_2d_bf16(&plan.wcatT_b, net->wcatT, E8, R, plan.bn_de, 64));
+    // K = the batch: columns >= n are zero-filled by TMA (the buffers keep stale rows of larger batches)
+    TRY(make_tmap_2d_bf16_ld(&plan.drbt_a, net->dRBt_bf, R, n, net->nb32, 128, 64));
+    TRY(make_tmap_2d_bf16_ld(&plan.et_b, net->Et_bf, E8, n, net->nb32, plan.bn_dw, 64));
+  }
   auto res = net->plans.emplace(n, std::move(plan));
   *out = &res.first->second;
   return SALUN_OK;
@@ -538,10 +558,11 @@ static int conv_forward(salun_unet *net, const UConv &L, const UConvMaps &m, int
 }
 
 static int gemm_plain(const CUtensorMap &A, const CUtensorMap &B, int M, int N, int K, bf16 *out_bf16, float *out_f32,
-                      int ld_out, int batch_a, int batch_b, int bn, cudaStream_t st) {
+                      int ld_out, int batch_a, int batch_b, int bn, cudaStream_t st, const float *bias = nullptr) {
   ConvGemmArgs a{};
   a.mode_a = 0;
-  a.num_k_blocks = K / 64;
+  a.num_k_blocks = (K + 63) / 64;
+  a.bias = bias;
   a.M = M;
   a.N = N;
   a.out_bf16 = out_bf16;
@@ -564,7 +585,7 @@ static int attn_forward(salun_unet *net, const UAttn &A, const UAttnMaps &m, int
   return SALUN_OK;
 }
 
-static int emb_forward(salun_unet *net, int n, cudaStream_t st) {
+static int emb_forward(salun_unet *net, const UPlan &plan, int n, bool save, cudaStream_t st) {
   const int ch = net->cfg.ch, E4 = net->emb, E8 = net->emb + 512;
   const float *P = net->params;
   launch_emb_inputs(net->t_dev, net->c_dev, net->have_drop ? net->drop_dev : nullptr, P + net->cew, P + net->null_off,
@@ -576,8 +597,11 @@ static int emb_forward(salun_unet *net, int n, cudaStream_t st) {
   launch_swish_f32(net->pre_c, net->h_c, (long long)n * E4, st);
   launch_sgemm(net->h_c, E4, 1, P + net->c1w, 1, E4, net->cat + E4, E8, n, E4, E4, P + net->c1b, 0, st);
   launch_swish_f32(net->cat, net->E, (long long)n * E8, st);
-  for (const RbParams &p : net->rbs)
-    launch_sgemm(net->E, E8, 1, P + p.pw, 1, E8, net->RB + p.rb_col, net->ld_rb, n, p.cout, E8, P + p.pb, 0, st);
+  // RB[n][ld_rb] = E . Wcat^T + bcat : the temb_cemb_proj Linear of every ResnetBlock (diffusion.py:131-132) in one GEMM
+  launch_f32_to_bf16(net->E, E8, net->E_bf, E8, n, E8, st);
+  launch_gather_proj(P, net->row_w, net->row_b, net->wcat, net->bcat, net->ld_rb, E8, st);
+  if (save) launch_transpose(net->wcat, E8, net->wcatT, net->ld_rb, E8, 1, st);
+  TRY(gemm_plain(plan.e_a, plan.wcat_b, n, net->ld_rb, E8, nullptr, net->RB, net->ld_rb, 0, 0, plan.bn_rb, st, net->bcat));
   return SALUN_OK;
 }
 
@@ -593,7 +617,7 @@ static int forward_impl(salun_unet *net, const float *x, int n, int train, bool 
   UPlan *plan;
   TRY(build_plan(net, n, &plan));
   TRY(prep_weights(net, save, st));
-  TRY(emb_forward(net, n, st));
+  TRY(emb_forward(net, *plan, n, save, st));
   const float drop_p = train ? net->cfg.dropout : 0.f;
   net->drop_p = drop_p;
   for (const UOp &op : net->ops) {
@@ -689,7 +713,7 @@ static int conv_backward(salun_unet *net, int ci, const UConvMaps &m, int n, con
     launch_eps_in(d_eps, L.dy64, gdst + L.b_off, n, L.H, st);
   } else {
     UTensor &o = net->ts[L.out];
-    launch_bias_grad(o.g, o.gflat ? 1 : 0, net->bias_partial, gdst + L.b_off, L.pb_off >= 0 ? gdst + L.pb_off : nullptr,
+    launch_bias_grad(o.g, o.gflat ? 1 : 0, net->bias_partial, net->persample, gdst + L.b_off, L.pb_off >= 0 ? gdst + L.pb_off : nullptr,
                      L.rb_col >= 0 ? net->dRB : nullptr, net->ld_rb, L.rb_col, n, L.H, L.cout, st);
     if (L.addend >= 0) {
       UTensor &ad = net->ts[L.addend];
@@ -749,17 +773,17 @@ static int attn_backward(salun_unet *net, const UAttn &A, const UAttnMaps &m, in
   return SALUN_OK;
 }
 
-static int emb_backward(salun_unet *net, int n, float *gdst, cudaStream_t st) {
+static int emb_backward(salun_unet *net, const UPlan &plan, int n, float *gdst, cudaStream_t st) {
   const int ch = net->cfg.ch, E4 = net->emb, E8 = net->emb + 512;
   const float *P = net->params;
-  bool first = true;
-  for (const RbParams &p : net->rbs) {
-    // dE += dRB_i . Wp_i ; dWp_i = dRB_i^T . E
-    launch_sgemm(net->dRB + p.rb_col, net->ld_rb, 1, P + p.pw, E8, 1, net->dE, E8, n, E8, p.cout, nullptr, first ? 0 : 1,
-                 st);
-    launch_sgemm(net->dRB + p.rb_col, 1, net->ld_rb, net->E, E8, 1, gdst + p.pw, E8, p.cout, E8, n, nullptr, 0, st);
-    first = false;
-  }
+  // dE = dRB . Wcat ; dWcat = dRB^T . E  (two tensor-core GEMMs over all ResnetBlocks), rows scattered to the arena
+  const int R = net->ld_rb;
+  launch_f32_to_bf16(net->dRB, R, net->dRB_bf, R, n, R, st);
+  launch_transpose(net->dRB_bf, R, net->dRBt_bf, net->nb32, R, 1, st);
+  launch_transpose(net->E_bf, E8, net->Et_bf, net->nb32, E8, 1, st);
+  TRY(gemm_plain(plan.drb_a, plan.wcatT_b, n, E8, R, nullptr, net->dE, E8, 0, 0, plan.bn_de, st));
+  TRY(gemm_plain(plan.drbt_a, plan.et_b, R, E8, n, nullptr, net->dWcat, E8, 0, 0, plan.bn_dw, st));
+  launch_scatter_rows(net->dWcat, net->row_w, gdst, R, E8, st);
   launch_dswish_f32(net->dE, net->cat, net->dcat, (long long)n * E8, st);
   for (int br = 0; br < 2; ++br) {  // 0: temb, 1: cemb
     const float *dy = net->dcat + br * E4;
@@ -807,7 +831,7 @@ static int backward_impl(salun_unet *net, const float *d_eps, int accumulate, cu
         UTensor &in = net->ts[g.in];
         const UTensor &out = net->ts[g.out];
         launch_gn_backward(out.g, in.v, g.stats, net->params + g.g_off, net->params + g.b_off, g.swish,
-                           g.dropout ? net->drop_p : 0.f, gn_seed(net, g), net->gn_partial, net->gn_coef,
+                           g.dropout ? net->drop_p : 0.f, gn_seed(net, g), net->gn_partial, net->persample, net->gn_coef,
                            gdst + g.g_off, gdst + g.b_off, in.g, take_live(in), n, g.H, g.C, st);
         break;
       }
@@ -829,7 +853,7 @@ static int backward_impl(salun_unet *net, const float *d_eps, int accumulate, cu
         break;
     }
   }
-  TRY(emb_backward(net, n, gdst, st));
+  TRY(emb_backward(net, *plan, n, gdst, st));
   SALUN_CUDA_OK(cudaEventRecord(net->ev_join, net->side));
   SALUN_CUDA_OK(cudaStreamWaitEvent(st, net->ev_join, 0));
   for (size_t i = 0; i < net->convs.size(); ++i) {
@@ -988,6 +1012,33 @@ int salun_unet_create(salun_ctx *ctx, const salun_unet_cfg *cfg, float *params, 
     A(dmalloc(net, &net->dce, nb * ch));
     A(dmalloc(net, &net->RB, (size_t)nb * net->ld_rb));
     A(dmalloc(net, &net->dRB, (size_t)nb * net->ld_rb));
+    {
+      const size_t R = net->ld_rb;
+      net->nb32 = (nb + 31) / 32 * 32;
+      A(dmalloc(net, &net->wcat, R * E8));
+      A(dmalloc(net, &net->wcatT, R * E8));
+      A(dmalloc(net, &net->bcat, R));
+      A(dmalloc(net, &net->dWcat, R * E8));
+      A(dmalloc(net, &net->E_bf, (size_t)net->nb32 * E8));
+      A(dmalloc(net, &net->Et_bf, (size_t)net->nb32 * E8));
+      A(dmalloc(net, &net->dRB_bf, (size_t)net->nb32 * R));
+      A(dmalloc(net, &net->dRBt_bf, (size_t)net->nb32 * R));
+      A(dmalloc(net, &net->persample, (size_t)nb * 2 * 1024));
+      std::vector<long long> rw(R), rbv(R);
+      for (const RbParams &p : net->rbs)
+        for (int co = 0; co < p.cout; ++co) {
+          rw[p.rb_col + co] = p.pw + (long long)co * E8;
+          rbv[p.rb_col + co] = p.pb + co;
+        }
+      A(dmalloc(net, &net->row_w, R, false));
+      A(dmalloc(net, &net->row_b, R, false));
+      if (cudaMemcpy(net->row_w, rw.data(), R * sizeof(long long), cudaMemcpyHostToDevice) != cudaSuccess ||
+          cudaMemcpy(net->row_b, rbv.data(), R * sizeof(long long), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("cudaMemcpy(projection row tables) failed");
+        salun_unet_destroy(net);
+        return SALUN_ERR_CUDA;
+      }
+    }
     A(dmalloc(net, &net->t_dev, (size_t)nb));
     A(dmalloc(net, &net->c_dev, (size_t)nb));
     A(dmalloc(net, &net->drop_dev, (size_t)nb));

@@ -14,9 +14,21 @@ typedef __nv_bfloat16 bf16;
 namespace {
 
 constexpr int kT = 256;
+constexpr int kU = 4;   // rows in flight per thread in the per-sample streaming kernels (memory-level parallelism)
+constexpr int kUb = 2;  // ... in the register-heavy GroupNorm backward kernels
 
 __device__ __forceinline__ void u_ld8(const bf16 *p, float (&f)[8]) {
   const uint4 v = *reinterpret_cast<const uint4 *>(p);
+  const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 u_ldraw(const bf16 *p) { return *reinterpret_cast<const uint4 *>(p); }
+__device__ __forceinline__ void u_cvt8(const uint4 &v, float (&f)[8]) {
   const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -35,7 +47,8 @@ __device__ __forceinline__ void u_st8(bf16 *p, const float (&f)[8]) {
 // element offset of pixel p (0 .. H*H-1) of image n, channel 0
 __device__ __forceinline__ size_t pix_off(int n, int p, int H, int C, int flat) {
   if (flat) return ((size_t)n * H * H + p) * C;
-  const int y = p / H, x = p - y * H;
+  const int lh = 31 - __clz(H);  // H is a power of two
+  const int y = p >> lh, x = p & (H - 1);
   return (((size_t)n * (H + 2) + y + 1) * (H + 2) + x + 1) * C;
 }
 __device__ __forceinline__ uint32_t hash32(uint32_t x) {
@@ -46,11 +59,23 @@ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
   x ^= x >> 16;
   return x;
 }
-// dropout decision of element e (flat index (n*HW + p)*C + c) -- the same function in forward and backward
-__device__ __forceinline__ float drop_scale(uint32_t seed, uint32_t e, uint32_t thr, float inv_keep) {
-  return hash32(e ^ seed) >= thr ? inv_keep : 0.f;
+// dropout multipliers of the 8 elements starting at flat index e0 = (n*HW + p)*C + c0 (a multiple of 8): four hashes,
+// one 16-bit uniform per element, keep iff uniform >= thr16 = round(p * 65536).  The same function in forward and backward.
+__device__ __forceinline__ void drop8(uint32_t seed, uint32_t e0, uint32_t thr16, float inv_keep, float (&m)[8]) {
+  uint32_t h = hash32(e0 ^ seed);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    m[2 * j] = (h & 0xffffu) >= thr16 ? inv_keep : 0.f;
+    m[2 * j + 1] = (h >> 16) >= thr16 ? inv_keep : 0.f;
+    h = hash32(h + 0x9E3779B9u);
+  }
 }
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+// sigmoid through one MUFU op (tanh.approx, rel. error ~2^-11: below the bf16 rounding of everything it feeds)
+__device__ __forceinline__ float sigmoidf_(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(0.5f, t, 0.5f);
+}
 
 // sums over the row lanes of a (vecs x rl) thread block: acc[k][8] per thread -> partial[k][C] of this (n, slice)
 template <int K>
@@ -80,6 +105,14 @@ int unet_slices(int H) {
   if (s > 16) s = 16;
   return s;
 }
+// Slices actually launched for a batch of n: CTAs of 64 pixels are dominated by their fixed cost (launch, block
+// reduction) -- measured 2 TB/s at n = 256 -- so use the fewest slices that still give ~4 CTAs per SM.
+static int slices_for(int H, int n) {
+  const int smax = unet_slices(H);
+  int s = 1;
+  while (s < smax && (long long)n * s < 592) s *= 2;
+  return s;
+}
 
 // =================================================================================================================
 // GroupNorm forward
@@ -95,13 +128,22 @@ __global__ void __launch_bounds__(kT) k_gn_stats(const bf16 *__restrict__ x, flo
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
   if (active) {
-    for (int p = s * rps + r; p < (s + 1) * rps; p += rl) {
-      float f[8];
-      u_ld8(x + pix_off(n, p, H, C, 0) + v * 8, f);
+    const int end = (s + 1) * rps;
+    for (int p = s * rps + r; p < end; p += rl * kU) {
+      uint4 raw[kU];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        acc[0][i] += f[i];
-        acc[1][i] += f[i] * f[i];
+      for (int u = 0; u < kU; ++u)
+        if (p + u * rl < end) raw[u] = u_ldraw(x + pix_off(n, p + u * rl, H, C, 0) + v * 8);
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        if (p + u * rl >= end) continue;
+        float f[8];
+        u_cvt8(raw[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[0][i] += f[i];
+          acc[1][i] += f[i] * f[i];
+        }
       }
     }
   }
@@ -126,7 +168,7 @@ __global__ void __launch_bounds__(32) k_gn_fwd_finalize(const float *__restrict_
   stats[((size_t)n * kGnGroups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
 }
 void launch_gn_stats(const bf16 *x_pad, float *partial, float *stats, int n, int H, int C, float eps, cudaStream_t st) {
-  const int S = unet_slices(H);
+  const int S = slices_for(H, n);
   k_gn_stats<<<dim3(S, n), kT, 0, st>>>(x_pad, partial, H, C, S);
   k_gn_fwd_finalize<<<n, 32, 0, st>>>(partial, stats, C, S, (float)(C / kGnGroups) * H * H, eps);
   g_launch_count += 2;
@@ -149,29 +191,44 @@ __global__ void __launch_bounds__(kT) k_gn_apply(const bf16 *__restrict__ x, con
     a[i] = gamma[c0 + i] * rstd;
     b[i] = beta[c0 + i] - mean * a[i];
   }
-  for (int p = s * rps + r; p < (s + 1) * rps; p += rl) {
-    float f[8];
-    u_ld8(x + pix_off(n, p, H, C, 0) + c0, f);
-    const uint32_t e0 = (uint32_t)(((size_t)n * H * H + p) * C + c0);
+  const int end = (s + 1) * rps;
+  for (int p0 = s * rps + r; p0 < end; p0 += rl * kU) {
+    uint4 raw[kU];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float y = a[i] * f[i] + b[i];
-      if (swish) y = y * sigmoidf_(y);
-      if (drop_thr) y *= drop_scale(seed, e0 + i, drop_thr, inv_keep);
-      f[i] = y;
+    for (int u = 0; u < kU; ++u)
+      if (p0 + u * rl < end) raw[u] = u_ldraw(x + pix_off(n, p0 + u * rl, H, C, 0) + c0);
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int p = p0 + u * rl;
+      if (p >= end) continue;
+      float f[8];
+      u_cvt8(raw[u], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float y = fmaf(a[i], f[i], b[i]);
+        if (swish) y = y * sigmoidf_(y);
+        f[i] = y;
+      }
+      if (drop_thr) {
+        float m[8];
+        drop8(seed, (uint32_t)(((size_t)n * H * H + p) * C + c0), drop_thr, inv_keep, m);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] *= m[i];
+      }
+      u_st8(out + pix_off(n, p, H, C, out_flat) + c0, f);
     }
-    u_st8(out + pix_off(n, p, H, C, out_flat) + c0, f);
   }
 }
 static inline uint32_t drop_threshold(float p) {
   if (p <= 0.f) return 0u;
-  double t = (double)p * 4294967296.0;
-  if (t > 4294967295.0) t = 4294967295.0;
+  double t = (double)p * 65536.0 + 0.5;
+  if (t > 65535.0) t = 65535.0;
+  if (t < 1.0) t = 1.0;
   return (uint32_t)t;
 }
 void launch_gn_apply(const bf16 *x_pad, const float *stats, const float *gamma, const float *beta, bf16 *out,
                      int out_flat, int swish, float drop_p, uint32_t drop_seed, int n, int H, int C, cudaStream_t st) {
-  const int S = unet_slices(H);
+  const int S = slices_for(H, n);
   k_gn_apply<<<dim3(S, n), kT, 0, st>>>(x_pad, stats, gamma, beta, out, out_flat, swish, drop_threshold(drop_p),
                                         drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f, drop_seed, H, C, S);
   ++g_launch_count;
@@ -198,20 +255,24 @@ __device__ __forceinline__ void gn_load_ch(GnCh &ch, const float *stats, const f
 __device__ __forceinline__ void gn_dyh(const GnCh &ch, const float (&xf)[8], const float (&df)[8], int swish,
                                        uint32_t drop_thr, float inv_keep, uint32_t seed, uint32_t e0, float (&xhat)[8],
                                        float (&dyh)[8]) {
+  float m[8];
+  if (drop_thr) drop8(seed, e0, drop_thr, inv_keep, m);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     xhat[i] = (xf[i] - ch.mean[i]) * ch.rstd[i];
     float d = df[i];
-    if (drop_thr) d *= drop_scale(seed, e0 + i, drop_thr, inv_keep);
+    if (drop_thr) d *= m[i];
     if (swish) {
-      const float y = ch.gam[i] * xhat[i] + ch.bet[i];
+      const float y = fmaf(ch.gam[i], xhat[i], ch.bet[i]);
       const float sg = sigmoidf_(y);
-      d *= sg * (1.f + y * (1.f - sg));
+      d *= sg * fmaf(y, 1.f - sg, 1.f);
     }
     dyh[i] = d;
   }
 }
-__global__ void __launch_bounds__(kT) k_gn_bwd_reduce(const bf16 *__restrict__ dout, const bf16 *__restrict__ x,
+// reduces S1 = sum dyh, S2 = sum dyh * xhat and OVERWRITES dout with dyh (the apply pass then needs neither the
+// activation derivative nor the dropout mask again)
+__global__ void __launch_bounds__(kT) k_gn_bwd_reduce(bf16 *__restrict__ dout, const bf16 *__restrict__ x,
                                                       const float *__restrict__ stats, const float *__restrict__ gamma,
                                                       const float *__restrict__ beta, int swish, uint32_t drop_thr,
                                                       float inv_keep, uint32_t seed, float *__restrict__ partial, int H,
@@ -227,51 +288,78 @@ __global__ void __launch_bounds__(kT) k_gn_bwd_reduce(const bf16 *__restrict__ d
   if (active) {
     GnCh ch;
     gn_load_ch(ch, stats, gamma, beta, n, c0, cpg);
-    for (int p = s * rps + r; p < (s + 1) * rps; p += rl) {
-      float xf[8], df[8], xhat[8], dyh[8];
-      u_ld8(x + pix_off(n, p, H, C, 0) + c0, xf);
-      u_ld8(dout + pix_off(n, p, H, C, 1) + c0, df);
-      gn_dyh(ch, xf, df, swish, drop_thr, inv_keep, seed, (uint32_t)(((size_t)n * H * H + p) * C + c0), xhat, dyh);
+    const int end = (s + 1) * rps;
+    for (int p0 = s * rps + r; p0 < end; p0 += rl * kUb) {
+      uint4 rx[kUb], rd[kUb];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        acc[0][i] += dyh[i];
-        acc[1][i] += dyh[i] * xhat[i];
+      for (int u = 0; u < kUb; ++u)
+        if (p0 + u * rl < end) {
+          rx[u] = u_ldraw(x + pix_off(n, p0 + u * rl, H, C, 0) + c0);
+          rd[u] = u_ldraw(dout + pix_off(n, p0 + u * rl, H, C, 1) + c0);
+        }
+#pragma unroll
+      for (int u = 0; u < kUb; ++u) {
+        const int p = p0 + u * rl;
+        if (p >= end) continue;
+        float xf[8], df[8], xhat[8], dyh[8];
+        u_cvt8(rx[u], xf);
+        u_cvt8(rd[u], df);
+        gn_dyh(ch, xf, df, swish, drop_thr, inv_keep, seed, (uint32_t)(((size_t)n * H * H + p) * C + c0), xhat, dyh);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[0][i] += dyh[i];
+          acc[1][i] = fmaf(dyh[i], xhat[i], acc[1][i]);
+        }
+        if (swish || drop_thr) u_st8(dout + pix_off(n, p, H, C, 1) + c0, dyh);
       }
     }
   }
   slice_reduce_store<2>(acc, v, r, rl, active, C, partial + ((size_t)n * S + s) * 2 * C);
 }
-// per (sample, group): coef = (sum_c gamma_c S1[c], sum_c gamma_c S2[c]) / count
-__global__ void __launch_bounds__(32) k_gn_bwd_group(const float *__restrict__ partial, const float *__restrict__ gamma,
-                                                     float *__restrict__ coef, int C, int S, float inv_count) {
-  const int n = blockIdx.x, g = threadIdx.x;
+// per sample: slice sums -> persample[n][2][C] (S1, S2 per channel), and per group
+// coef = (sum_c gamma_c S1[c], sum_c gamma_c S2[c]) / count
+__global__ void __launch_bounds__(512) k_gn_bwd_group(const float *__restrict__ partial, const float *__restrict__ gamma,
+                                                      float *__restrict__ coef, float *__restrict__ persample, int C,
+                                                      int S, float inv_count) {
+  __shared__ float g1[512], g2[512];
+  const int n = blockIdx.x, c = threadIdx.x;
   const int cpg = C / kGnGroups;
-  float a = 0.f, b = 0.f;
-  for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+  if (c < C) {
     float s1 = 0.f, s2 = 0.f;
     for (int s = 0; s < S; ++s) {
       const float *p = partial + ((size_t)n * S + s) * 2 * C;
       s1 += p[c];
       s2 += p[C + c];
     }
-    a += gamma[c] * s1;
-    b += gamma[c] * s2;
+    persample[((size_t)n * 2 + 0) * C + c] = s1;
+    persample[((size_t)n * 2 + 1) * C + c] = s2;
+    g1[c] = gamma[c] * s1;
+    g2[c] = gamma[c] * s2;
   }
-  coef[((size_t)n * kGnGroups + g) * 2 + 0] = a * inv_count;
-  coef[((size_t)n * kGnGroups + g) * 2 + 1] = b * inv_count;
+  __syncthreads();
+  if (c < kGnGroups) {
+    float a = 0.f, b = 0.f;
+    for (int j = c * cpg; j < (c + 1) * cpg; ++j) {
+      a += g1[j];
+      b += g2[j];
+    }
+    coef[((size_t)n * kGnGroups + c) * 2 + 0] = a * inv_count;
+    coef[((size_t)n * kGnGroups + c) * 2 + 1] = b * inv_count;
+  }
 }
-// out_k[c] = sum over rows of partial[row][k][c], rows = n*S; K planes; up to two destinations for plane 0
-__global__ void __launch_bounds__(256) k_sum_rows(const float *__restrict__ partial, int rows, int K, int C,
-                                                  float *__restrict__ d0, float *__restrict__ d0b,
-                                                  float *__restrict__ d1) {
-  __shared__ float red[2][8][32];
+// d_k[c] = sum over rows of src[row * ld + k * C + c]; K (<= 2) planes; up to two destinations for plane 0.
+// 32 channels x 32 row lanes per block, fixed reduction order.
+__global__ void __launch_bounds__(1024) k_sum_rows(const float *__restrict__ src, long long ld, int rows, int K, int C,
+                                                   float *__restrict__ d0, float *__restrict__ d0b,
+                                                   float *__restrict__ d1) {
+  __shared__ float red[2][32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
   float s0 = 0.f, s1 = 0.f;
   if (c < C) {
-    for (int i = ty; i < rows; i += 8) {
-      s0 += partial[(size_t)i * K * C + c];
-      if (K > 1) s1 += partial[(size_t)i * K * C + C + c];
+    for (int i = ty; i < rows; i += 32) {
+      s0 += src[(size_t)i * ld + c];
+      if (K > 1) s1 += src[(size_t)i * ld + C + c];
     }
   }
   red[0][ty][tx] = s0;
@@ -280,7 +368,7 @@ __global__ void __launch_bounds__(256) k_sum_rows(const float *__restrict__ part
   if (ty == 0 && c < C) {
     float a = 0.f, b = 0.f;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < 32; ++q) {
       a += red[0][q][tx];
       b += red[1][q][tx];
     }
@@ -289,56 +377,63 @@ __global__ void __launch_bounds__(256) k_sum_rows(const float *__restrict__ part
     if (d1 && K > 1) d1[c] = b;
   }
 }
-__global__ void __launch_bounds__(kT) k_gn_bwd_apply(const bf16 *__restrict__ dout, const bf16 *__restrict__ x,
+__global__ void __launch_bounds__(kT) k_gn_bwd_apply(const bf16 *__restrict__ dyh_flat, const bf16 *__restrict__ x,
                                                      const float *__restrict__ stats, const float *__restrict__ gamma,
-                                                     const float *__restrict__ beta, const float *__restrict__ coef,
-                                                     int swish, uint32_t drop_thr, float inv_keep, uint32_t seed,
-                                                     bf16 *__restrict__ dx, int accumulate, int H, int C, int S) {
+                                                     const float *__restrict__ coef, bf16 *__restrict__ dx,
+                                                     int accumulate, int H, int C, int S) {
   const int n = blockIdx.y, s = blockIdx.x;
   const int vecs = C >> 3, rl = kT / vecs;
   const int v = threadIdx.x % vecs, r = threadIdx.x / vecs;
   if (r >= rl) return;
   const int cpg = C / kGnGroups, rps = H * H / S, c0 = v * 8;
-  GnCh ch;
-  gn_load_ch(ch, stats, gamma, beta, n, c0, cpg);
-  float ca[8], cb[8];
+  // dx = rstd*gamma*dyh - rstd*cb*xhat - rstd*ca  with xhat = (x - mean)*rstd:  dx = k1*dyh + k2*x + k3
+  float k1[8], k2[8], k3[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int g = (c0 + i) / cpg;
-    ca[i] = coef[((size_t)n * kGnGroups + g) * 2];
-    cb[i] = coef[((size_t)n * kGnGroups + g) * 2 + 1];
+    const float mean = stats[((size_t)n * kGnGroups + g) * 2], rstd = stats[((size_t)n * kGnGroups + g) * 2 + 1];
+    const float ca = coef[((size_t)n * kGnGroups + g) * 2], cb = coef[((size_t)n * kGnGroups + g) * 2 + 1];
+    k1[i] = rstd * gamma[c0 + i];
+    k2[i] = -rstd * rstd * cb;
+    k3[i] = rstd * (rstd * cb * mean - ca);
   }
-  for (int p = s * rps + r; p < (s + 1) * rps; p += rl) {
-    float xf[8], df[8], xhat[8], dyh[8];
-    const size_t po = pix_off(n, p, H, C, 0) + c0;
-    u_ld8(x + po, xf);
-    u_ld8(dout + pix_off(n, p, H, C, 1) + c0, df);
-    gn_dyh(ch, xf, df, swish, drop_thr, inv_keep, seed, (uint32_t)(((size_t)n * H * H + p) * C + c0), xhat, dyh);
-    float o[8];
-    if (accumulate) {
-      u_ld8(dx + po, o);
-    } else {
+  const int end = (s + 1) * rps;
+  for (int p0 = s * rps + r; p0 < end; p0 += rl * kU) {
+    uint4 rx[kU], rd[kU], ro[kU];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = 0.f;
+    for (int u = 0; u < kU; ++u)
+      if (p0 + u * rl < end) {
+        const size_t po = pix_off(n, p0 + u * rl, H, C, 0) + c0;
+        rx[u] = u_ldraw(x + po);
+        rd[u] = u_ldraw(dyh_flat + pix_off(n, p0 + u * rl, H, C, 1) + c0);
+        ro[u] = accumulate ? u_ldraw(dx + po) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int p = p0 + u * rl;
+      if (p >= end) continue;
+      float xf[8], df[8], o[8];
+      u_cvt8(rx[u], xf);
+      u_cvt8(rd[u], df);
+      u_cvt8(ro[u], o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] += fmaf(k1[i], df[i], fmaf(k2[i], xf[i], k3[i]));
+      u_st8(dx + pix_off(n, p, H, C, 0) + c0, o);
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] += ch.rstd[i] * (ch.gam[i] * dyh[i] - ca[i] - xhat[i] * cb[i]);
-    u_st8(dx + po, o);
   }
 }
-void launch_gn_backward(const bf16 *dout_flat, const bf16 *x_pad, const float *stats, const float *gamma,
-                        const float *beta, int swish, float drop_p, uint32_t drop_seed, float *partial, float *coef,
-                        float *dgamma, float *dbeta, bf16 *dx_pad, int accumulate, int n, int H, int C,
+void launch_gn_backward(bf16 *dout_flat, const bf16 *x_pad, const float *stats, const float *gamma,
+                        const float *beta, int swish, float drop_p, uint32_t drop_seed, float *partial, float *persample,
+                        float *coef, float *dgamma, float *dbeta, bf16 *dx_pad, int accumulate, int n, int H, int C,
                         cudaStream_t st) {
-  const int S = unet_slices(H);
+  const int S = slices_for(H, n);
   const uint32_t thr = drop_threshold(drop_p);
   const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   k_gn_bwd_reduce<<<dim3(S, n), kT, 0, st>>>(dout_flat, x_pad, stats, gamma, beta, swish, thr, inv_keep, drop_seed,
                                              partial, H, C, S);
-  k_gn_bwd_group<<<n, 32, 0, st>>>(partial, gamma, coef, C, S, 1.f / ((float)(C / kGnGroups) * H * H));
-  k_sum_rows<<<(C + 31) / 32, 256, 0, st>>>(partial, n * S, 2, C, dbeta, nullptr, dgamma);
-  k_gn_bwd_apply<<<dim3(S, n), kT, 0, st>>>(dout_flat, x_pad, stats, gamma, beta, coef, swish, thr, inv_keep, drop_seed,
-                                            dx_pad, accumulate, H, C, S);
+  k_gn_bwd_group<<<n, 512, 0, st>>>(partial, gamma, coef, persample, C, S, 1.f / ((float)(C / kGnGroups) * H * H));
+  k_sum_rows<<<(C + 31) / 32, 1024, 0, st>>>(persample, 2LL * C, n, 2, C, dbeta, nullptr, dgamma);
+  k_gn_bwd_apply<<<dim3(S, n), kT, 0, st>>>(dout_flat, x_pad, stats, gamma, coef, dx_pad, accumulate, H, C, S);
   g_launch_count += 4;
 }
 
@@ -356,11 +451,20 @@ __global__ void __launch_bounds__(kT) k_colsum(const bf16 *__restrict__ dy, int 
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[0][i] = 0.f;
   if (active) {
-    for (int p = s * rps + r; p < (s + 1) * rps; p += rl) {
-      float f[8];
-      u_ld8(dy + pix_off(n, p, H, C, flat) + v * 8, f);
+    const int end = (s + 1) * rps;
+    for (int p = s * rps + r; p < end; p += rl * kU) {
+      uint4 raw[kU];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[0][i] += f[i];
+      for (int u = 0; u < kU; ++u)
+        if (p + u * rl < end) raw[u] = u_ldraw(dy + pix_off(n, p + u * rl, H, C, flat) + v * 8);
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        if (p + u * rl >= end) continue;
+        float f[8];
+        u_cvt8(raw[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[0][i] += f[i];
+      }
     }
   }
   slice_reduce_store<1>(acc, v, r, rl, active, C, partial + ((size_t)n * S + s) * C);
@@ -374,16 +478,17 @@ __global__ void k_rowsum_slices(const float *__restrict__ partial, float *__rest
     rowsum[(size_t)n * ld + col0 + c] = a;
   }
 }
-void launch_bias_grad(const bf16 *dy, int dy_flat, float *partial, float *bias_grad_a, float *bias_grad_b, float *rowsum,
-                      int rowsum_ld, int rowsum_col0, int n, int H, int C, cudaStream_t st) {
-  const int S = unet_slices(H);
+void launch_bias_grad(const bf16 *dy, int dy_flat, float *partial, float *persample, float *bias_grad_a,
+                      float *bias_grad_b, float *rowsum, int rowsum_ld, int rowsum_col0, int n, int H, int C,
+                      cudaStream_t st) {
+  const int S = slices_for(H, n);
   k_colsum<<<dim3(S, n), kT, 0, st>>>(dy, dy_flat, partial, H, C, S);
-  k_sum_rows<<<(C + 31) / 32, 256, 0, st>>>(partial, n * S, 1, C, bias_grad_a, bias_grad_b, nullptr);
-  g_launch_count += 2;
-  if (rowsum) {
-    k_rowsum_slices<<<n, 256, 0, st>>>(partial, rowsum, rowsum_ld, rowsum_col0, C, S);
-    ++g_launch_count;
-  }
+  // per-sample sums go either into the caller's rowsum matrix (gradient of the temb/cemb projection) or into scratch
+  float *ps = rowsum ? rowsum + rowsum_col0 : persample;
+  const int ld = rowsum ? rowsum_ld : C;
+  k_rowsum_slices<<<n, 256, 0, st>>>(partial, ps, ld, 0, C, S);
+  k_sum_rows<<<(C + 31) / 32, 1024, 0, st>>>(ps, ld, n, 1, C, bias_grad_a, bias_grad_b, nullptr);
+  g_launch_count += 3;
 }
 
 // =================================================================================================================
@@ -825,6 +930,60 @@ __global__ void k_emb_scatter(const float *__restrict__ dce, const int64_t *__re
 void launch_emb_scatter(const float *dce, const int64_t *c, const uint8_t *drop, float *d_class_emb, float *d_null, int n,
                         int ch, int n_classes, cudaStream_t st) {
   k_emb_scatter<<<n_classes + 1, ch, 0, st>>>(dce, c, drop, d_class_emb, d_null, n, ch, n_classes);
+  ++g_launch_count;
+}
+
+
+// ---- temb/cemb projection of all ResnetBlocks as ONE tensor-core GEMM: operand staging ----
+// Wcat[r][k] = bf16(params[row_w[r] + k]) ; bcat[r] = params[row_b[r]]   (r walks the blocks' output channels)
+__global__ void __launch_bounds__(256) k_gather_proj(const float *__restrict__ params, const long long *__restrict__ row_w,
+                                                     const long long *__restrict__ row_b, bf16 *__restrict__ wcat,
+                                                     float *__restrict__ bcat, int K) {
+  const int r = blockIdx.x;
+  const float *src = params + row_w[r];
+  for (int k = threadIdx.x * 4; k < K; k += 256 * 4) {
+    const float4 v = *reinterpret_cast<const float4 *>(src + k);
+    uint2 o;
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    o.x = *reinterpret_cast<uint32_t *>(&a);
+    o.y = *reinterpret_cast<uint32_t *>(&b);
+    *reinterpret_cast<uint2 *>(wcat + (size_t)r * K + k) = o;
+  }
+  if (threadIdx.x == 0) bcat[r] = params[row_b[r]];
+}
+void launch_gather_proj(const float *params, const long long *row_w, const long long *row_b, bf16 *wcat, float *bcat,
+                        int rows, int K, cudaStream_t st) {
+  k_gather_proj<<<rows, 256, 0, st>>>(params, row_w, row_b, wcat, bcat, K);
+  ++g_launch_count;
+}
+// dst[row_w[r] + k] = src[r][k]
+__global__ void __launch_bounds__(256) k_scatter_rows(const float *__restrict__ src, const long long *__restrict__ row_w,
+                                                      float *__restrict__ dst, int K) {
+  const int r = blockIdx.x;
+  float *d = dst + row_w[r];
+  for (int k = threadIdx.x * 4; k < K; k += 256 * 4)
+    *reinterpret_cast<float4 *>(d + k) = *reinterpret_cast<const float4 *>(src + (size_t)r * K + k);
+}
+void launch_scatter_rows(const float *src, const long long *row_w, float *dst, int rows, int K, cudaStream_t st) {
+  k_scatter_rows<<<rows, 256, 0, st>>>(src, row_w, dst, K);
+  ++g_launch_count;
+}
+// out[i*ld_out + j] = bf16(in[i*ld_in + j]), cols % 4 == 0
+__global__ void __launch_bounds__(256) k_f32_to_bf16(const float *__restrict__ in, int ld_in, bf16 *__restrict__ out,
+                                                     int ld_out, int rows, int cols) {
+  const int c4 = cols >> 2;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < (long long)rows * c4; i += (long long)gridDim.x * 256) {
+    const int r = (int)(i / c4), j = (int)(i % c4) * 4;
+    const float4 v = *reinterpret_cast<const float4 *>(in + (size_t)r * ld_in + j);
+    uint2 o;
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    o.x = *reinterpret_cast<uint32_t *>(&a);
+    o.y = *reinterpret_cast<uint32_t *>(&b);
+    *reinterpret_cast<uint2 *>(out + (size_t)r * ld_out + j) = o;
+  }
+}
+void launch_f32_to_bf16(const float *in, int ld_in, bf16 *out, int ld_out, int rows, int cols, cudaStream_t st) {
+  k_f32_to_bf16<<<grid_for((long long)rows * (cols >> 2)), 256, 0, st>>>(in, ld_in, out, ld_out, rows, cols);
   ++g_launch_count;
 }
 

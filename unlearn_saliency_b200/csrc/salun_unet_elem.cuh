@@ -26,19 +26,22 @@ void launch_gn_apply(const __nv_bfloat16 *x_pad, const float *stats, const float
                      __nv_bfloat16 *out, int out_flat, int swish, float drop_p, uint32_t drop_seed, int n, int H, int C,
                      cudaStream_t st);
 // ---- GroupNorm backward.  dout: gradient w.r.t. the GN(+swish+dropout) output, FLAT [n*H*H][C] ----
-//   partial[n][S][2][C] = per-sample sums over pixels of dyh and dyh * xhat        (dyh = dout * act'(yh) * dropmask)
+//   partial[n][S][2][C] = per-sample, per-slice sums over pixels of dyh and dyh * xhat (dyh = dout * act'(yh) * dropmask)
+//   persample[n][2][C]  = the same summed over the slices (scratch)
 //   dgamma[c] = sum_n,pix dyh*xhat ; dbeta[c] = sum dyh ; coef[n][32][2] = (sum_c gamma dyh, sum_c gamma dyh xhat) / count
 //   dx = rstd * (gamma*dyh - coefA - xhat*coefB), written padded; accumulate != 0: added to what dx already holds
-void launch_gn_backward(const __nv_bfloat16 *dout_flat, const __nv_bfloat16 *x_pad, const float *stats,
+//   dout_flat is OVERWRITTEN with dyh (it has no other consumer)
+void launch_gn_backward(__nv_bfloat16 *dout_flat, const __nv_bfloat16 *x_pad, const float *stats,
                         const float *gamma, const float *beta, int swish, float drop_p, uint32_t drop_seed,
-                        float *partial, float *coef, float *dgamma, float *dbeta, __nv_bfloat16 *dx_pad, int accumulate,
-                        int n, int H, int C, cudaStream_t st);
+                        float *partial, float *persample, float *coef, float *dgamma, float *dbeta,
+                        __nv_bfloat16 *dx_pad, int accumulate, int n, int H, int C, cudaStream_t st);
 
 // ---- bias gradients: per-sample column sums of dY (padded or flat), then reductions ----
-//   partial[n][S][C]; bias_grad_a / bias_grad_b [C] (either may be NULL) = sum over samples and pixels;
+//   partial[n][S][C], persample[n][C] (scratch); bias_grad_a / bias_grad_b [C] (either may be NULL) = sum over samples and pixels;
 //   rowsum (optional) [n][rowsum_ld] at column rowsum_col0: per-sample sums (gradient of the temb/cemb projection output)
-void launch_bias_grad(const __nv_bfloat16 *dy, int dy_flat, float *partial, float *bias_grad_a, float *bias_grad_b,
-                      float *rowsum, int rowsum_ld, int rowsum_col0, int n, int H, int C, cudaStream_t st);
+void launch_bias_grad(const __nv_bfloat16 *dy, int dy_flat, float *partial, float *persample, float *bias_grad_a,
+                      float *bias_grad_b, float *rowsum, int rowsum_ld, int rowsum_col0, int n, int H, int C,
+                      cudaStream_t st);
 
 // ---- copies on padded tensors ----
 void launch_concat(const __nv_bfloat16 *a_pad, int Ca, const __nv_bfloat16 *b_pad, int Cb, __nv_bfloat16 *out_pad, int n,
@@ -84,5 +87,15 @@ void launch_colsum_f32(const float *a, int ld, int rows, int cols, float *out, c
 // gradient of the embedding lookup: d_class_emb[k][:] = sum_{i: c[i]==k, !drop[i]} dce[i][:] ; d_null = sum_{drop[i]} dce[i]
 void launch_emb_scatter(const float *dce, const int64_t *c, const uint8_t *drop, float *d_class_emb, float *d_null,
                         int n, int ch, int n_classes, cudaStream_t st);
+
+
+// ---- the temb/cemb projections of all ResnetBlocks as one tensor-core GEMM: operand staging ----
+// wcat[r][k] = bf16(params[row_w[r] + k]), bcat[r] = params[row_b[r]]  for r < rows, k < K (K % 4 == 0)
+void launch_gather_proj(const float *params, const long long *row_w, const long long *row_b, __nv_bfloat16 *wcat,
+                        float *bcat, int rows, int K, cudaStream_t st);
+// dst[row_w[r] + k] = src[r][k]
+void launch_scatter_rows(const float *src, const long long *row_w, float *dst, int rows, int K, cudaStream_t st);
+// out[i*ld_out + j] = bf16(in[i*ld_in + j]); cols % 4 == 0, 16-byte aligned rows
+void launch_f32_to_bf16(const float *in, int ld_in, __nv_bfloat16 *out, int ld_out, int rows, int cols, cudaStream_t st);
 
 }  // namespace salun

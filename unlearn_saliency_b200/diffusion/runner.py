@@ -5,9 +5,12 @@
   antithetic_t                runners/diffusion.py:527-531, 966-970
   DDPMUnlearner.generate_mask_batch / .finish_mask      :959-1039
   DDPMUnlearner.saliency_unlearn_step                   :519-593
-The model forward/backward is PyTorch; clip_grad_norm_, the mask multiply (the reference re-uploads the 309 MB int64
-mask every step, :589-592), Adam, the saliency accumulation (the reference copies every gradient to the CPU every
-batch, :992-996) and the top-k (two CPU argsorts of 38.6 M keys, :1006-1037) run in libsalun.so on flat arenas.
+DDPMEngineUnlearner runs the U-Net forward / backward on the sm_100a engine (diffusion/engine.py, salun_unet_*): the
+model calls of one iteration are concatenated into one batch (GroupNorm does not couple samples).  DDPMUnlearner is the
+same loop around a torch.nn.Module (any architecture the engine does not serve).  In both, clip_grad_norm_, the mask
+multiply (the reference re-uploads the 309 MB int64 mask every step, :589-592), Adam, the saliency accumulation (the
+reference copies every gradient to the CPU every batch, :992-996) and the top-k (two CPU argsorts of 38.6 M keys,
+:1006-1037) run in libsalun.so on flat arenas.
 """
 from __future__ import annotations
 
@@ -141,5 +144,147 @@ class DDPMUnlearner:
         os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
         sd = {"module." + k: v for k, v in self.model.state_dict().items()}
         optim = {"exp_avg": self.flat.dict_from_flat(self.opt.exp_avg), "exp_avg_sq": self.flat.dict_from_flat(self.opt.exp_avg_sq),
+                 "step": self.opt.step_count}
+        torch.save([sd, optim, step], path)
+
+
+class DDPMEngineUnlearner:
+    """UNetEngine + fused tail: the loop bodies of Diffusion.generate_mask / Diffusion.saliency_unlearn with every model
+    call on the sm_100a engine.  `mask`: the dict torch.load(mask_path) gives (CPU int64, ``module.`` keys); None = no mask.
+
+    Data parallel (torch.distributed initialised, world W): each rank runs its shard of the two mini-batches with
+    dL/d(eps) pre-scaled by 1/W, ONE all-reduce(sum) of the flat gradient arena gives the DDP-averaged gradient, and
+    every rank applies the identical clip + mask + Adam (clip uses the global norm)."""
+
+    def __init__(self, engine, betas, lr=1e-4, beta1=0.9, eps=1e-8, weight_decay=0.0, grad_clip=1.0,
+                 mask: Optional[Dict[str, torch.Tensor]] = None):
+        self.engine = engine
+        self.device = engine.device
+        self.betas = torch.as_tensor(betas).float().to(self.device)
+        self.num_timesteps = self.betas.shape[0]
+        self.opt = FlatMaskedAdam(engine, lr=lr, betas=(beta1, 0.999), eps=eps, weight_decay=weight_decay, mask=mask,
+                                  max_norm=grad_clip)
+        self.saliency = FlatSaliency(engine, max_norm=grad_clip)
+        self._step = 0
+
+    @staticmethod
+    def _world():
+        import torch.distributed as dist
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def _all_reduce_grads(self):
+        if self._world() > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.engine.grads)
+
+    def _drop(self, rng, key, n, p):
+        if key in rng:
+            return rng[key].to(self.device).to(torch.uint8)
+        if p <= 0:
+            return None
+        return (torch.rand(n, device=self.device) < p).to(torch.uint8)   # keep_mask = uniform < 1 - p  (diffusion.py:8-14)
+
+    # ---- runners/diffusion.py:959-996 -------------------------------------------------------------------------
+    def generate_mask_batch(self, x, c, cond_scale: float = 2.0, t=None, e=None):
+        """x in [0,1]; eval mode; the conditional and the null pass of _forward_with_cond_scale run as one batch of 2n."""
+        eng, dev = self.engine, self.device
+        x = 2 * x.to(dev).float() - 1.0
+        c = c.to(dev)
+        n = x.shape[0]
+        e = torch.randn_like(x) if e is None else e.to(dev)
+        t = antithetic_t(n, self.num_timesteps, dev) if t is None else t.to(dev)
+        xt = q_sample(x, t, e, self.betas).contiguous()
+        tf = t.float()
+        s = float(cond_scale)
+        if s == 0:
+            out = eng.forward(xt, tf, c, drop=None, save=True, train=False)
+            d_out = (-2.0 / n) * (e - out)
+            loss = (e - out).square().sum(dim=(1, 2, 3)).mean(dim=0)
+            eng.backward(d_out.contiguous())
+        elif 2 * n <= eng.max_batch:
+            drop = torch.cat([torch.zeros(n, dtype=torch.uint8, device=dev), torch.ones(n, dtype=torch.uint8, device=dev)])
+            eps2 = eng.forward(torch.cat([xt, xt]), torch.cat([tf, tf]), torch.cat([c, c]), drop=drop, save=True, train=False)
+            out = (1 + s) * eps2[:n] - s * eps2[n:]
+            loss = (e - out).square().sum(dim=(1, 2, 3)).mean(dim=0)
+            d_out = (-2.0 / n) * (e - out)
+            eng.backward(torch.cat([(1 + s) * d_out, -s * d_out]).contiguous())
+        else:
+            ones, zeros = torch.ones(n, dtype=torch.uint8, device=dev), torch.zeros(n, dtype=torch.uint8, device=dev)
+            null = eng.forward(xt, tf, c, drop=ones, save=False, train=False)
+            cond = eng.forward(xt, tf, c, drop=zeros, save=True, train=False)
+            out = (1 + s) * cond - s * null
+            loss = (e - out).square().sum(dim=(1, 2, 3)).mean(dim=0)
+            d_out = (-2.0 / n) * (e - out)
+            eng.backward(((1 + s) * d_out).contiguous())
+            eng.forward(xt, tf, c, drop=ones, save=True, train=False)
+            eng.backward((-s * d_out).contiguous(), accumulate=True)
+        self.saliency.accumulate()  # clip to norm 1 (per batch, :985-990) then gradients += grad (:992-996)
+        return loss.detach()
+
+    def finish_mask(self, path: Optional[str] = None, ratio: float = 0.5, key_prefix: str = "module."):
+        self.saliency.all_reduce()
+        if path is None:
+            return self.saliency.mask(ratio, key_prefix=key_prefix)
+        return self.saliency.save(path, ratio, key_prefix=key_prefix)
+
+    # ---- runners/diffusion.py:519-593 -------------------------------------------------------------------------
+    def saliency_unlearn_step(self, remain_x, remain_c, forget_x, forget_c, alpha: float = 1e-3, method: str = "rl",
+                              n_classes: int = 10, rng: Optional[dict] = None, train: bool = True):
+        """One iteration.  `rng` may carry externally drawn (t_r, e_r, t_f, e_f, drop_r, drop_f, drop_p) for parity runs;
+        dropout inside the network uses the engine's counter-based generator (seeded per step)."""
+        rng = rng or {}
+        eng, dev = self.engine, self.device
+        W = self._world()
+        p_drop = eng.cond_drop_prob
+        xr, cr = 2 * remain_x.to(dev).float() - 1.0, remain_c.to(dev)
+        nr = xr.shape[0]
+        e_r = rng["e_r"].to(dev) if "e_r" in rng else torch.randn_like(xr)
+        t_r = rng["t_r"].to(dev) if "t_r" in rng else antithetic_t(nr, self.num_timesteps, dev)
+        xf, cf = 2 * forget_x.to(dev).float() - 1.0, forget_c.to(dev)
+        nf = xf.shape[0]
+        e_f = rng["e_f"].to(dev) if "e_f" in rng else torch.randn_like(xf)
+        t_f = rng["t_f"].to(dev) if "t_f" in rng else antithetic_t(nf, self.num_timesteps, dev)
+        xt_r = q_sample(xr, t_r, e_r, self.betas)                                                  # losses.py:31-32
+        xt_f = q_sample(xf, t_f, e_f, self.betas)                                                  # :558-559
+        drop_r, drop_f = self._drop(rng, "drop_r", nr, p_drop), self._drop(rng, "drop_f", nf, p_drop)
+        self._step += 1
+        seed = int(rng.get("seed", self._step)) * 2
+        pseudo = None
+        if method == "rl":
+            drop_p = self._drop(rng, "drop_p", nf, p_drop)
+            pseudo = eng.forward(xt_f.contiguous(), t_f.float(), (cf + 1) % n_classes, drop=drop_p, save=False,
+                                 train=train, seed=seed + 1)                                       # :561-569 (no grad)
+        elif method != "ga":
+            raise NotImplementedError(method)
+        if drop_r is None and drop_f is None:
+            drop = None
+        else:
+            z = lambda k: torch.zeros(k, dtype=torch.uint8, device=dev)
+            drop = torch.cat([drop_r if drop_r is not None else z(nr), drop_f if drop_f is not None else z(nf)])
+        eps = eng.forward(torch.cat([xt_r, xt_f]).contiguous(), torch.cat([t_r, t_f]).float(), torch.cat([cr, cf]),
+                          drop=drop, save=True, train=train, seed=seed)
+        out_r, out_f = eps[:nr], eps[nr:]
+        remain_loss = (e_r - out_r).square().sum(dim=(1, 2, 3)).mean(dim=0)                        # :533-536
+        d_r = (-2.0 * alpha / nr) * (e_r - out_r)
+        if method == "ga":
+            forget_loss = -(e_f - out_f).square().sum(dim=(1, 2, 3)).mean(dim=0)                   # :552-555
+            d_f = (2.0 / nf) * (e_f - out_f)
+        else:
+            forget_loss = torch.nn.functional.mse_loss(out_f, pseudo)                              # :570
+            d_f = (2.0 / out_f.numel()) * (out_f - pseudo)
+        loss = forget_loss + alpha * remain_loss                                                   # :572
+        d = torch.cat([d_r, d_f])
+        if W > 1:
+            d = d / W
+        eng.backward(d.contiguous())                                                               # :579-580
+        self._all_reduce_grads()
+        self.opt.step()   # clip_grad_norm_(1.0) BEFORE the mask, grad *= mask, Adam -- one fused pass (:582-593)
+        return loss.detach()
+
+    def save_checkpoint(self, path: str, step: int):
+        """states = [model_sd, optim_sd, step] like :598-610"""
+        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+        sd = self.engine.state_dict(prefix="module.")
+        optim = {"exp_avg": self.engine.dict_from_flat(self.opt.exp_avg), "exp_avg_sq": self.engine.dict_from_flat(self.opt.exp_avg_sq),
                  "step": self.opt.step_count}
         torch.save([sd, optim, step], path)

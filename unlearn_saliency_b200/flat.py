@@ -139,9 +139,14 @@ class FlatSaliency:
 
     def mask(self, ratio: float = 0.5, cpu: bool = True, key_prefix: str = ""):
         """{name: int64 0/1 tensor} in the reference format (CPU tensors for DDPM/SD, runners/diffusion.py:995,1039)."""
-        # compact the arena (drop alignment padding) so that k = int(N * ratio) counts real parameters only
-        pieces = [self.acc[self.flat.offsets[n]: self.flat.offsets[n] + math.prod(s)] for n, s in self.flat.shapes.items()]
-        dense = torch.cat(pieces).contiguous()
+        if getattr(self.flat, "native_layout", False):
+            # engine arena (conv weights OHWI, no padding) -> the reference's flat order, so that ties at the threshold
+            # resolve in the same element order as torch.cat([g.flatten() ...]) (runners/diffusion.py:1006-1008)
+            dense = self.flat.from_native_flat(self.acc).contiguous()
+        else:
+            # compact the arena (drop alignment padding) so that k = int(N * ratio) counts real parameters only
+            pieces = [self.acc[self.flat.offsets[n]: self.flat.offsets[n] + math.prod(s)] for n, s in self.flat.shapes.items()]
+            dense = torch.cat(pieces).contiguous()
         k = topk_count(dense.numel(), ratio)
         m64, _, info = self.ctx.topk_mask(dense, k, want_bits=False, want_info=True)
         out, off = OrderedDict(), 0
