@@ -14,7 +14,7 @@ for row in csv.DictReader(lines):
     v = float(row["Metric Value"].replace(",", ""))
     v = v / 1000.0 if row["Metric Unit"] in ("ns", "nsecond") else v
     name = row["Kernel Name"]
-    if "k_conv_gemm_p" in name and gi < len(gem):
+    if ("k_conv_gemm_p" in name or "k_gemm2" in name) and gi < len(gem):
         key = ("gemm", gem[gi]); gi += 1
     elif "k_wgrad" in name and "reduce" not in name:
         if wi >= len(wg):

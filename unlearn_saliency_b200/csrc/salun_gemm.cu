@@ -571,6 +571,8 @@ k_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
           y0 = (m0 - n0 * hw) / a.W;
         }
         int cb = 0, kx = 0, ky = 0;
+        const int b_row0 = n_tile * BN + (int)rank * (BN / 2) +
+                           (a.batch_rows_a ? (m_pair * 256 / a.batch_rows_a) * a.batch_rows_b : 0);
         for (int kb = 0; kb < a.num_k_blocks; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
@@ -583,7 +585,7 @@ k_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
             else
               tma2_load_2d(sa, &tmA, full0 + 8 * s, kb * kBK, m0);
           } else {
-            tma2_load_2d(sb, &tmB, full0 + 8 * s, kb * kBK, n_tile * BN + (int)rank * (BN / 2));
+            tma2_load_2d(sb, &tmB, full0 + 8 * s, kb * kBK, b_row0);
           }
           if (++cb == a.cin_blocks) {
             cb = 0;
@@ -630,6 +632,8 @@ k_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
       const int row = m_pair * 256 + (int)rank * 128 + q * 32 + lane;
       const bool row_ok = row < a.M;
       const int stat_row = (m_pair * 2 + (int)rank) * 4 + q;
+      const size_t out_row = !row_ok ? 0 : (a.out_pad ? pad_row_off(row, a.fH, a.fW, a.ld_out) : (size_t)row * a.ld_out);
+      const float *rb_row = (a.rowbias && row_ok) ? a.rowbias + (size_t)(row >> a.rb_shift) * a.rb_ld : nullptr;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
@@ -652,8 +656,28 @@ k_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
               a.stat_sq[(size_t)stat_row * a.N + col0 + lane] = s2;
             }
           }
+          if (a.bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4 *>(a.bias + col0) + j);
+              r[4 * j + 0] = __float_as_uint(__uint_as_float(r[4 * j + 0]) + b4.x);
+              r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + b4.y);
+              r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + b4.z);
+              r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + b4.w);
+            }
+          }
+          if (rb_row) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4 *>(rb_row + col0) + j);
+              r[4 * j + 0] = __float_as_uint(__uint_as_float(r[4 * j + 0]) + b4.x);
+              r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + b4.y);
+              r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + b4.z);
+              r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + b4.w);
+            }
+          }
           if (row_ok && a.addend) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(a.addend + (size_t)row * a.ld_out + col0);
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.addend + out_row + col0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint4 v = src[j];
@@ -668,7 +692,7 @@ k_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
           }
           if (row_ok) {
             if (a.out_bf16) {
-              uint4 *dst = reinterpret_cast<uint4 *>(a.out_bf16 + (size_t)row * a.ld_out + col0);
+              uint4 *dst = reinterpret_cast<uint4 *>(a.out_bf16 + out_row + col0);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 uint4 v;
@@ -1296,6 +1320,7 @@ int launch_conv_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvG
   if (gemm_log())
     fprintf(stderr, "GEMMLOG M=%d N=%d K=%d mode=%d bn=%d H=%d batched=%d\n", a.M, a.N, a.num_k_blocks * 64, a.mode_a, bn, a.H,
             a.batch_rows_a);
+  if (a.pair) return launch_gemm2(tmA, tmB, a, bn, st);  // the caller encoded tmB with bn/2 box rows
   prof_open(0, 2.0 * a.M * a.N * (double)a.num_k_blocks * 64.0, st);
   int rc;
   if (gemm_persistent()) {

@@ -45,6 +45,8 @@ struct ConvGemmArgs {
                                 //    [n][fH+2][fW+2][ld_out] (row m -> interior pixel), 0: flat [M][ld_out]
   int batch_rows_a, batch_rows_b;  // batched GEMM (one B matrix per group of batch_rows_a rows of A): the B tile of
                                    // output tile (m, n) starts at row (m*128 / batch_rows_a) * batch_rows_b + n*BN.  0 = off
+  int pair;                        // 1: launch_conv_gemm routes to the CTA-pair kernel (k_gemm2, 256 x bn tiles): tmB must
+                                   // have been encoded with bn/2 box rows; bn in {128, 256}; batch_rows_a % 256 == 0
 };
 
 // dW[co][b*64 + j] += sum_p dY[p][co] * X_b[p][j]   (both operands MN-major: pixels are the K dimension)

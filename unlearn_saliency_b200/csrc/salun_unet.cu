@@ -55,11 +55,13 @@ struct UConv {
   bf16 *dy64;                      // CK_OUT: padded 64-channel dY
   float *wg_ws;
   int wg_splits_max;
+  float *bias_partial;             // [rows][cout_p] per-sample, per-slice column sums of dY (CK_OUT: [nb][3])
 };
 struct UGn {
   int in, out, C, H, swish, dropout;
   int64_t g_off, b_off;
-  float *stats;  // [nb][32][2]
+  float *stats;      // [nb][32][2]
+  float *persample;  // [nb][2][C] backward: per-sample sums of dyh, dyh*xhat
   uint32_t id;
 };
 struct UAttn {
@@ -82,6 +84,7 @@ struct UOp {
 };
 struct UConvMaps {
   CUtensorMap fwdA, fwdB, dgA, dgB, wgA, wgB;
+  int pair_fwd, pair_dg;  // forward / dgrad GEMM through the CTA-pair kernel (fwdB / dgB encoded with bn/2 box rows)
 };
 struct UAttnMaps {
   CUtensorMap q, k, v, vt128, p, xt_b, tt_a, og, ds;  // see build_plan
@@ -92,6 +95,8 @@ struct UPlan {
   std::vector<UAttnMaps> attn;
   CUtensorMap e_a, wcat_b, drb_a, wcatT_b, drbt_a, et_b;  // projection GEMMs (forward, dE, dW)
   int bn_rb, bn_de, bn_dw;
+  SumEntry *sum_table;  // device: the cross-sample sums of one backward pass (GroupNorm dgamma/dbeta, conv biases)
+  int n_sums;
 };
 
 }  // namespace salun
@@ -117,7 +122,7 @@ struct salun_unet {
   float *sincos, *ce, *pre_t, *h_t, *pre_c, *h_c, *cat, *E, *RB, *dRB, *dE, *dcat, *dh, *dpre, *dce;
   // all temb_cemb_proj Linears as one tensor-core GEMM (operands staged per step)
   bf16 *wcat, *wcatT, *E_bf, *Et_bf, *dRB_bf, *dRBt_bf;
-  float *bcat, *dWcat, *persample;
+  float *bcat, *dWcat;
   long long *row_w, *row_b;
   int nb32;
   float *t_dev;
@@ -125,7 +130,7 @@ struct salun_unet {
   uint8_t *drop_dev;
   bool have_drop;
   // scratch
-  float *gn_partial, *gn_coef, *bias_partial, *S_f32;
+  float *gn_partial, *gn_coef, *S_f32;
   bf16 *xt1, *xt2, *tt, *dS;
   WPrepEntry *wprep_table;
   WgReduceEntry *wgred_table, *wgred_host;
@@ -156,6 +161,18 @@ static int ilog2(int v) {
 static int u_pick_bn(int N, int64_t M) {
   if (N % 256 == 0 && ((M + 127) / 128) * (N / 256) >= 96) return 256;
   return N % 128 == 0 ? 128 : 64;
+}
+// CTA pairs (cta_group::2) halve the B-operand bytes each SM pulls through its L2 port -- the measured bound of the
+// 128 x bn tiles -- and are used when a GEMM still gives every pair at least two 256-row tiles.  SALUN_UNET_PAIR=0: off, 2: always.
+static bool use_pair(int64_t M, int N, int bn) {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("SALUN_UNET_PAIR");
+    on = e ? atoi(e) : 1;
+  }
+  if (!on || bn < 128) return false;
+  if (on == 2) return true;  // tests: force the pair kernel on small shapes too
+  return ((M + 255) / 256) * ((N + bn - 1) / bn) >= 148;
 }
 static bool has_res(const salun_unet_cfg &c, int res) {
   for (int i = 0; i < c.n_attn_res; ++i)
@@ -440,7 +457,9 @@ static int build_plan(salun_unet *net, int n, UPlan **out) {
     UConvMaps &m = plan.conv[i];
     const int64_t M = (int64_t)n * L.H * L.H;
     const int bn = u_pick_bn(L.cout_p, M);
-    TRY(make_tmap_2d_bf16(&m.fwdB, L.w_fwd, L.cout_p, L.kcp, bn, 64));
+    m.pair_fwd = use_pair(M, L.cout_p, bn) ? 1 : 0;
+    m.pair_dg = 0;
+    TRY(make_tmap_2d_bf16(&m.fwdB, L.w_fwd, L.cout_p, L.kcp, m.pair_fwd ? bn / 2 : bn, 64));
     if (L.kind == CK_S1 || L.kind == CK_OUT) {
       const UTensor &in = net->ts[L.in];
       TRY(map_act(&m.fwdA, in.v, in.vflat, L.cin, L.H, n, 128, 128));
@@ -450,7 +469,8 @@ static int build_plan(salun_unet *net, int n, UPlan **out) {
       TRY(map_act(&m.dgA, dy, dyflat, L.cout_p, L.H, n, 128, 128));
       TRY(map_act(&m.wgA, dy, dyflat, L.cout_p, L.H, n, 64, 64));
       const int bnd = u_pick_bn(L.cin, M);
-      TRY(make_tmap_2d_bf16(&m.dgB, L.w_dgrad, L.cin, (uint64_t)L.ks * L.ks * L.cout_p, bnd, 64));
+      m.pair_dg = use_pair(M, L.cin, bnd) ? 1 : 0;
+      TRY(make_tmap_2d_bf16(&m.dgB, L.w_dgrad, L.cin, (uint64_t)L.ks * L.ks * L.cout_p, m.pair_dg ? bnd / 2 : bnd, 64));
     } else {
       // conv_in / downsample: explicit patch matrix col[M][kcp]
       TRY(make_tmap_2d_bf16(&m.fwdA, L.col, M, L.kcp, 128, 64));
@@ -494,6 +514,25 @@ static int build_plan(salun_unet *net, int n, UPlan **out) {
     // K = the batch: columns >= n are zero-filled by TMA (the buffers keep stale rows of larger batches)
     TRY(make_tmap_2d_bf16_ld(&plan.drbt_a, net->dRBt_bf, R, n, net->nb32, 128, 64));
     TRY(make_tmap_2d_bf16_ld(&plan.et_b, net->Et_bf, E8, n, net->nb32, plan.bn_dw, 64));
+  }
+  {
+    std::vector<SumEntry> tab;
+    for (const UGn &g : net->gns) tab.push_back(SumEntry{g.persample, 2LL * g.C, n, 2, g.C, g.b_off, -1, g.g_off});
+    for (const UConv &L : net->convs) {
+      if (L.kind == CK_OUT) {
+        tab.push_back(SumEntry{L.bias_partial, 3, n, 1, 3, L.b_off, -1, -1});
+      } else if (L.rb_col >= 0) {  // per-sample sums live in dRB (they are also the projection's output gradient)
+        tab.push_back(SumEntry{net->dRB + L.rb_col, net->ld_rb, n, 1, L.cout, L.b_off, L.pb_off, -1});
+      } else {
+        tab.push_back(SumEntry{L.bias_partial, L.cout, n * unet_slices_for(L.H, n), 1, L.cout, L.b_off, -1, -1});
+      }
+    }
+    plan.n_sums = (int)tab.size();
+    void *q = nullptr;
+    SALUN_CUDA_OK(cudaMalloc(&q, tab.size() * sizeof(SumEntry)));
+    net->allocs.push_back(q);
+    plan.sum_table = (SumEntry *)q;
+    SALUN_CUDA_OK(cudaMemcpy(q, tab.data(), tab.size() * sizeof(SumEntry), cudaMemcpyHostToDevice));
   }
   auto res = net->plans.emplace(n, std::move(plan));
   *out = &res.first->second;
@@ -552,6 +591,7 @@ static int conv_forward(salun_unet *net, const UConv &L, const UConvMaps &m, int
     }
     if (L.addend >= 0) a.addend = net->ts[L.addend].v;  // same layout / width as the output
   }
+  a.pair = m.pair_fwd;
   TRY(launch_conv_gemm(m.fwdA, m.fwdB, a, u_pick_bn(L.cout_p, M), st));
   if (L.kind == CK_OUT) launch_eps_out(L.yf, net->params + L.b_off, eps_out, n, L.H, st);
   return SALUN_OK;
@@ -628,9 +668,8 @@ static int forward_impl(salun_unet *net, const float *x, int n, int train, bool 
       case OP_GN: {
         const UGn &g = net->gns[op.idx];
         const UTensor &in = net->ts[g.in], &out = net->ts[g.out];
-        launch_gn_stats(in.v, net->gn_partial, g.stats, n, g.H, g.C, 1e-6f, st);
-        launch_gn_apply(in.v, g.stats, net->params + g.g_off, net->params + g.b_off, out.v, out.vflat ? 1 : 0, g.swish,
-                        g.dropout ? drop_p : 0.f, gn_seed(net, g), n, g.H, g.C, st);
+        launch_gn_forward(in.v, net->gn_partial, g.stats, net->params + g.g_off, net->params + g.b_off, out.v,
+                          out.vflat ? 1 : 0, g.swish, g.dropout ? drop_p : 0.f, gn_seed(net, g), n, g.H, g.C, 1e-6f, st);
         break;
       }
       case OP_CONCAT: {
@@ -705,16 +744,15 @@ static int wgrad_conv(salun_unet *net, int ci, const UConvMaps &m, int n, cudaSt
   return launch_wgrad(m.wgA, m.wgB, a, co_tiles, groups, splits, net->side);
 }
 
-static int conv_backward(salun_unet *net, int ci, const UConvMaps &m, int n, const float *d_eps, float *gdst,
-                         cudaStream_t st) {
+static int conv_backward(salun_unet *net, int ci, const UConvMaps &m, int n, const float *d_eps, cudaStream_t st) {
   const UConv &L = net->convs[ci];
   const int M = n * L.H * L.H;
   if (L.kind == CK_OUT) {
-    launch_eps_in(d_eps, L.dy64, gdst + L.b_off, n, L.H, st);
+    launch_eps_in(d_eps, L.dy64, L.bias_partial, n, L.H, st);
   } else {
     UTensor &o = net->ts[L.out];
-    launch_bias_grad(o.g, o.gflat ? 1 : 0, net->bias_partial, net->persample, gdst + L.b_off, L.pb_off >= 0 ? gdst + L.pb_off : nullptr,
-                     L.rb_col >= 0 ? net->dRB : nullptr, net->ld_rb, L.rb_col, n, L.H, L.cout, st);
+    launch_bias_partial(o.g, o.gflat ? 1 : 0, L.bias_partial, L.rb_col >= 0 ? net->dRB : nullptr, net->ld_rb, L.rb_col, n,
+                        L.H, L.cout, st);
     if (L.addend >= 0) {
       UTensor &ad = net->ts[L.addend];
       launch_add_into(o.g, ad.g, take_live(ad), (long long)tensor_elems(net, ad, ad.gflat) / net->nb * n, st);
@@ -736,6 +774,7 @@ static int conv_backward(salun_unet *net, int ci, const UConvMaps &m, int n, con
     a.ld_out = L.cin;
     a.out_pad = in.gflat ? 0 : 1;
     if (take_live(in)) a.addend = in.g;
+    a.pair = m.pair_dg;
     TRY(launch_conv_gemm(m.dgA, m.dgB, a, u_pick_bn(L.cin, M), st));
   } else if (L.kind == CK_DOWN) {
     UTensor &in = net->ts[L.in];
@@ -824,15 +863,15 @@ static int backward_impl(salun_unet *net, const float *d_eps, int accumulate, cu
     const UOp &op = net->ops[oi];
     switch (op.type) {
       case OP_CONV:
-        TRY(conv_backward(net, op.idx, plan->conv[op.idx], n, d_eps, gdst, st));
+        TRY(conv_backward(net, op.idx, plan->conv[op.idx], n, d_eps, st));
         break;
       case OP_GN: {
         const UGn &g = net->gns[op.idx];
         UTensor &in = net->ts[g.in];
         const UTensor &out = net->ts[g.out];
         launch_gn_backward(out.g, in.v, g.stats, net->params + g.g_off, net->params + g.b_off, g.swish,
-                           g.dropout ? net->drop_p : 0.f, gn_seed(net, g), net->gn_partial, net->persample, net->gn_coef,
-                           gdst + g.g_off, gdst + g.b_off, in.g, take_live(in), n, g.H, g.C, st);
+                           g.dropout ? net->drop_p : 0.f, gn_seed(net, g), net->gn_partial, g.persample, in.g,
+                           take_live(in), n, g.H, g.C, st);
         break;
       }
       case OP_CONCAT: {
@@ -853,6 +892,7 @@ static int backward_impl(salun_unet *net, const float *d_eps, int accumulate, cu
         break;
     }
   }
+  launch_sum_rows_table(plan->sum_table, plan->n_sums, gdst, st);
   TRY(emb_backward(net, *plan, n, gdst, st));
   SALUN_CUDA_OK(cudaEventRecord(net->ev_join, net->side));
   SALUN_CUDA_OK(cudaStreamWaitEvent(st, net->ev_join, 0));
@@ -950,13 +990,14 @@ int salun_unet_create(salun_ctx *ctx, const salun_unet_cfg *cfg, float *params, 
   }
   const int nb = (cfg->max_batch + 7) / 8 * 8;
   net->nb = nb;
-  size_t max_part = 1, max_bias_part = 1, max_S = 1, max_xt = 1, max_tt = 1;
+  size_t max_part = 1, max_S = 1, max_xt = 1, max_tt = 1;
   for (UTensor &t : net->ts) {
     A(dmalloc(net, &t.v, tensor_elems(net, t, t.vflat)));
     if (t.need_g) A(dmalloc(net, &t.g, tensor_elems(net, t, t.gflat)));
   }
   for (UGn &g : net->gns) {
     A(dmalloc(net, &g.stats, (size_t)nb * kGnGroups * 2));
+    A(dmalloc(net, &g.persample, (size_t)nb * 2 * g.C));
     const size_t part = (size_t)nb * unet_slices(g.H) * 2 * g.C;
     if (part > max_part) max_part = part;
   }
@@ -975,8 +1016,14 @@ int salun_unet_create(salun_ctx *ctx, const salun_unet_cfg *cfg, float *params, 
     L.wg_splits_max = ctx->num_sms / tiles;
     if (L.wg_splits_max < 1) L.wg_splits_max = 1;
     A(dmalloc(net, &L.wg_ws, (size_t)L.wg_splits_max * L.cout * L.kc, false));
-    const size_t bp = (size_t)nb * unet_slices(L.H) * L.cout_p;
-    if (bp > max_bias_part) max_bias_part = bp;
+    {
+      size_t rows = 0;  // the largest n * slices_for(H, n) over n <= nb
+      for (int b = 1; b <= nb; ++b) {
+        const size_t r_ = (size_t)b * unet_slices_for(L.H, b);
+        if (r_ > rows) rows = r_;
+      }
+      A(dmalloc(net, &L.bias_partial, rows * L.cout_p));
+    }
   }
   for (UAttn &At : net->attns) {
     const size_t Mp = (size_t)nb * At.T;  // a multiple of Te (nb % 8 == 0)
@@ -988,7 +1035,6 @@ int salun_unet_create(salun_ctx *ctx, const salun_unet_cfg *cfg, float *params, 
   }
   A(dmalloc(net, &net->gn_partial, max_part));
   A(dmalloc(net, &net->gn_coef, (size_t)nb * kGnGroups * 2));
-  A(dmalloc(net, &net->bias_partial, max_bias_part));
   A(dmalloc(net, &net->S_f32, max_S));
   A(dmalloc(net, &net->dS, max_S));
   A(dmalloc(net, &net->xt1, max_xt));
@@ -1023,7 +1069,6 @@ int salun_unet_create(salun_ctx *ctx, const salun_unet_cfg *cfg, float *params, 
       A(dmalloc(net, &net->Et_bf, (size_t)net->nb32 * E8));
       A(dmalloc(net, &net->dRB_bf, (size_t)net->nb32 * R));
       A(dmalloc(net, &net->dRBt_bf, (size_t)net->nb32 * R));
-      A(dmalloc(net, &net->persample, (size_t)nb * 2 * 1024));
       std::vector<long long> rw(R), rbv(R);
       for (const RbParams &p : net->rbs)
         for (int co = 0; co < p.cout; ++co) {

@@ -149,36 +149,47 @@ __global__ void __launch_bounds__(kT) k_gn_stats(const bf16 *__restrict__ x, flo
   }
   slice_reduce_store<2>(acc, v, r, rl, active, C, partial + ((size_t)n * S + s) * 2 * C);
 }
-__global__ void __launch_bounds__(32) k_gn_fwd_finalize(const float *__restrict__ partial, float *__restrict__ stats,
-                                                        int C, int S, float count, float eps) {
-  const int n = blockIdx.x, g = threadIdx.x;
+// group statistics of sample n from the slice partials [S][2][C] (every CTA of the sample redoes this tiny reduction
+// instead of a separate finalize launch); fp64 for the variance
+__device__ __forceinline__ void gn_group_stats(const float *__restrict__ partial_n, int C, int S, float count, float eps,
+                                               float (*sh_stat)[2], float *sh_a, float *sh_b) {
   const int cpg = C / kGnGroups;
-  double s1 = 0.0, s2 = 0.0;
-  for (int s = 0; s < S; ++s) {
-    const float *p = partial + ((size_t)n * S + s) * 2 * C;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-      s1 += (double)p[c];
-      s2 += (double)p[C + c];
+  for (int c = threadIdx.x; c < C; c += kT) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int q = 0; q < S; ++q) {
+      s1 += partial_n[(size_t)q * 2 * C + c];
+      s2 += partial_n[(size_t)q * 2 * C + C + c];
     }
+    sh_a[c] = s1;
+    sh_b[c] = s2;
   }
-  const double mean = s1 / count;
-  double var = s2 / count - mean * mean;  // biased variance, like torch.nn.GroupNorm
-  if (var < 0.0) var = 0.0;
-  stats[((size_t)n * kGnGroups + g) * 2 + 0] = (float)mean;
-  stats[((size_t)n * kGnGroups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  __syncthreads();
+  if (threadIdx.x < kGnGroups) {
+    double a = 0.0, b = 0.0;
+    for (int j = threadIdx.x * cpg; j < (threadIdx.x + 1) * cpg; ++j) {
+      a += (double)sh_a[j];
+      b += (double)sh_b[j];
+    }
+    const double mean = a / count;
+    double var = b / count - mean * mean;  // biased variance, like torch.nn.GroupNorm
+    if (var < 0.0) var = 0.0;
+    sh_stat[threadIdx.x][0] = (float)mean;
+    sh_stat[threadIdx.x][1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
 }
-void launch_gn_stats(const bf16 *x_pad, float *partial, float *stats, int n, int H, int C, float eps, cudaStream_t st) {
-  const int S = slices_for(H, n);
-  k_gn_stats<<<dim3(S, n), kT, 0, st>>>(x_pad, partial, H, C, S);
-  k_gn_fwd_finalize<<<n, 32, 0, st>>>(partial, stats, C, S, (float)(C / kGnGroups) * H * H, eps);
-  g_launch_count += 2;
-}
-
-__global__ void __launch_bounds__(kT) k_gn_apply(const bf16 *__restrict__ x, const float *__restrict__ stats,
-                                                 const float *__restrict__ gamma, const float *__restrict__ beta,
-                                                 bf16 *__restrict__ out, int out_flat, int swish, uint32_t drop_thr,
-                                                 float inv_keep, uint32_t seed, int H, int C, int S) {
+__global__ void __launch_bounds__(kT) k_gn_apply(const bf16 *__restrict__ x, const float *__restrict__ partial,
+                                                 float *__restrict__ stats, const float *__restrict__ gamma,
+                                                 const float *__restrict__ beta, bf16 *__restrict__ out, int out_flat,
+                                                 int swish, uint32_t drop_thr, float inv_keep, uint32_t seed, int H,
+                                                 int C, int S, float count, float eps) {
+  __shared__ float sh_stat[kGnGroups][2], sh_a[512], sh_b[512];
   const int n = blockIdx.y, s = blockIdx.x;
+  gn_group_stats(partial + (size_t)n * S * 2 * C, C, S, count, eps, sh_stat, sh_a, sh_b);
+  if (s == 0 && threadIdx.x < kGnGroups) {  // kept for the backward pass
+    stats[((size_t)n * kGnGroups + threadIdx.x) * 2 + 0] = sh_stat[threadIdx.x][0];
+    stats[((size_t)n * kGnGroups + threadIdx.x) * 2 + 1] = sh_stat[threadIdx.x][1];
+  }
   const int vecs = C >> 3, rl = kT / vecs;
   const int v = threadIdx.x % vecs, r = threadIdx.x / vecs;
   if (r >= rl) return;
@@ -187,7 +198,7 @@ __global__ void __launch_bounds__(kT) k_gn_apply(const bf16 *__restrict__ x, con
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int g = (c0 + i) / cpg;
-    const float mean = stats[((size_t)n * kGnGroups + g) * 2], rstd = stats[((size_t)n * kGnGroups + g) * 2 + 1];
+    const float mean = sh_stat[g][0], rstd = sh_stat[g][1];
     a[i] = gamma[c0 + i] * rstd;
     b[i] = beta[c0 + i] - mean * a[i];
   }
@@ -226,12 +237,15 @@ static inline uint32_t drop_threshold(float p) {
   if (t < 1.0) t = 1.0;
   return (uint32_t)t;
 }
-void launch_gn_apply(const bf16 *x_pad, const float *stats, const float *gamma, const float *beta, bf16 *out,
-                     int out_flat, int swish, float drop_p, uint32_t drop_seed, int n, int H, int C, cudaStream_t st) {
+void launch_gn_forward(const bf16 *x_pad, float *partial, float *stats, const float *gamma, const float *beta, bf16 *out,
+                       int out_flat, int swish, float drop_p, uint32_t drop_seed, int n, int H, int C, float eps,
+                       cudaStream_t st) {
   const int S = slices_for(H, n);
-  k_gn_apply<<<dim3(S, n), kT, 0, st>>>(x_pad, stats, gamma, beta, out, out_flat, swish, drop_threshold(drop_p),
-                                        drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f, drop_seed, H, C, S);
-  ++g_launch_count;
+  k_gn_stats<<<dim3(S, n), kT, 0, st>>>(x_pad, partial, H, C, S);
+  k_gn_apply<<<dim3(S, n), kT, 0, st>>>(x_pad, partial, stats, gamma, beta, out, out_flat, swish, drop_threshold(drop_p),
+                                        drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f, drop_seed, H, C, S,
+                                        (float)(C / kGnGroups) * H * H, eps);
+  g_launch_count += 2;
 }
 
 // =================================================================================================================
@@ -318,81 +332,54 @@ __global__ void __launch_bounds__(kT) k_gn_bwd_reduce(bf16 *__restrict__ dout, c
 }
 // per sample: slice sums -> persample[n][2][C] (S1, S2 per channel), and per group
 // coef = (sum_c gamma_c S1[c], sum_c gamma_c S2[c]) / count
-__global__ void __launch_bounds__(512) k_gn_bwd_group(const float *__restrict__ partial, const float *__restrict__ gamma,
-                                                      float *__restrict__ coef, float *__restrict__ persample, int C,
-                                                      int S, float inv_count) {
-  __shared__ float g1[512], g2[512];
-  const int n = blockIdx.x, c = threadIdx.x;
-  const int cpg = C / kGnGroups;
-  if (c < C) {
-    float s1 = 0.f, s2 = 0.f;
-    for (int s = 0; s < S; ++s) {
-      const float *p = partial + ((size_t)n * S + s) * 2 * C;
-      s1 += p[c];
-      s2 += p[C + c];
-    }
-    persample[((size_t)n * 2 + 0) * C + c] = s1;
-    persample[((size_t)n * 2 + 1) * C + c] = s2;
-    g1[c] = gamma[c] * s1;
-    g2[c] = gamma[c] * s2;
-  }
-  __syncthreads();
-  if (c < kGnGroups) {
-    float a = 0.f, b = 0.f;
-    for (int j = c * cpg; j < (c + 1) * cpg; ++j) {
-      a += g1[j];
-      b += g2[j];
-    }
-    coef[((size_t)n * kGnGroups + c) * 2 + 0] = a * inv_count;
-    coef[((size_t)n * kGnGroups + c) * 2 + 1] = b * inv_count;
-  }
-}
-// d_k[c] = sum over rows of src[row * ld + k * C + c]; K (<= 2) planes; up to two destinations for plane 0.
-// 32 channels x 32 row lanes per block, fixed reduction order.
-__global__ void __launch_bounds__(1024) k_sum_rows(const float *__restrict__ src, long long ld, int rows, int K, int C,
-                                                   float *__restrict__ d0, float *__restrict__ d0b,
-                                                   float *__restrict__ d1) {
-  __shared__ float red[2][32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + tx;
-  float s0 = 0.f, s1 = 0.f;
-  if (c < C) {
-    for (int i = ty; i < rows; i += 32) {
-      s0 += src[(size_t)i * ld + c];
-      if (K > 1) s1 += src[(size_t)i * ld + C + c];
-    }
-  }
-  red[0][ty][tx] = s0;
-  red[1][ty][tx] = s1;
-  __syncthreads();
-  if (ty == 0 && c < C) {
-    float a = 0.f, b = 0.f;
-#pragma unroll
-    for (int q = 0; q < 32; ++q) {
-      a += red[0][q][tx];
-      b += red[1][q][tx];
-    }
-    if (d0) d0[c] = a;
-    if (d0b) d0b[c] = a;
-    if (d1 && K > 1) d1[c] = b;
-  }
-}
 __global__ void __launch_bounds__(kT) k_gn_bwd_apply(const bf16 *__restrict__ dyh_flat, const bf16 *__restrict__ x,
                                                      const float *__restrict__ stats, const float *__restrict__ gamma,
-                                                     const float *__restrict__ coef, bf16 *__restrict__ dx,
-                                                     int accumulate, int H, int C, int S) {
+                                                     const float *__restrict__ partial, float *__restrict__ persample,
+                                                     bf16 *__restrict__ dx, int accumulate, int H, int C, int S,
+                                                     float inv_count) {
+  __shared__ float sh_coef[kGnGroups][2], sh_a[512], sh_b[512];
   const int n = blockIdx.y, s = blockIdx.x;
+  const int cpg = C / kGnGroups;
+  {
+    // per-channel sums over the slices (S1 = sum dyh, S2 = sum dyh*xhat) -> persample (summed over samples later for
+    // dbeta / dgamma) and the per-group coefficients (sum_c gamma S1, sum_c gamma S2) / count
+    const float *pn = partial + (size_t)n * S * 2 * C;
+    for (int c = threadIdx.x; c < C; c += kT) {
+      float s1 = 0.f, s2 = 0.f;
+      for (int q = 0; q < S; ++q) {
+        s1 += pn[(size_t)q * 2 * C + c];
+        s2 += pn[(size_t)q * 2 * C + C + c];
+      }
+      if (s == 0) {
+        persample[((size_t)n * 2 + 0) * C + c] = s1;
+        persample[((size_t)n * 2 + 1) * C + c] = s2;
+      }
+      sh_a[c] = gamma[c] * s1;
+      sh_b[c] = gamma[c] * s2;
+    }
+    __syncthreads();
+    if (threadIdx.x < kGnGroups) {
+      float a = 0.f, b = 0.f;
+      for (int j = threadIdx.x * cpg; j < (threadIdx.x + 1) * cpg; ++j) {
+        a += sh_a[j];
+        b += sh_b[j];
+      }
+      sh_coef[threadIdx.x][0] = a * inv_count;
+      sh_coef[threadIdx.x][1] = b * inv_count;
+    }
+    __syncthreads();
+  }
   const int vecs = C >> 3, rl = kT / vecs;
   const int v = threadIdx.x % vecs, r = threadIdx.x / vecs;
   if (r >= rl) return;
-  const int cpg = C / kGnGroups, rps = H * H / S, c0 = v * 8;
+  const int rps = H * H / S, c0 = v * 8;
   // dx = rstd*gamma*dyh - rstd*cb*xhat - rstd*ca  with xhat = (x - mean)*rstd:  dx = k1*dyh + k2*x + k3
   float k1[8], k2[8], k3[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int g = (c0 + i) / cpg;
     const float mean = stats[((size_t)n * kGnGroups + g) * 2], rstd = stats[((size_t)n * kGnGroups + g) * 2 + 1];
-    const float ca = coef[((size_t)n * kGnGroups + g) * 2], cb = coef[((size_t)n * kGnGroups + g) * 2 + 1];
+    const float ca = sh_coef[g][0], cb = sh_coef[g][1];
     k1[i] = rstd * gamma[c0 + i];
     k2[i] = -rstd * rstd * cb;
     k3[i] = rstd * (rstd * cb * mean - ca);
@@ -422,19 +409,52 @@ __global__ void __launch_bounds__(kT) k_gn_bwd_apply(const bf16 *__restrict__ dy
     }
   }
 }
-void launch_gn_backward(bf16 *dout_flat, const bf16 *x_pad, const float *stats, const float *gamma,
-                        const float *beta, int swish, float drop_p, uint32_t drop_seed, float *partial, float *persample,
-                        float *coef, float *dgamma, float *dbeta, bf16 *dx_pad, int accumulate, int n, int H, int C,
-                        cudaStream_t st) {
+void launch_gn_backward(bf16 *dout_flat, const bf16 *x_pad, const float *stats, const float *gamma, const float *beta,
+                        int swish, float drop_p, uint32_t drop_seed, float *partial, float *persample, bf16 *dx_pad,
+                        int accumulate, int n, int H, int C, cudaStream_t st) {
   const int S = slices_for(H, n);
   const uint32_t thr = drop_threshold(drop_p);
   const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   k_gn_bwd_reduce<<<dim3(S, n), kT, 0, st>>>(dout_flat, x_pad, stats, gamma, beta, swish, thr, inv_keep, drop_seed,
                                              partial, H, C, S);
-  k_gn_bwd_group<<<n, 512, 0, st>>>(partial, gamma, coef, persample, C, S, 1.f / ((float)(C / kGnGroups) * H * H));
-  k_sum_rows<<<(C + 31) / 32, 1024, 0, st>>>(persample, 2LL * C, n, 2, C, dbeta, nullptr, dgamma);
-  k_gn_bwd_apply<<<dim3(S, n), kT, 0, st>>>(dout_flat, x_pad, stats, gamma, coef, dx_pad, accumulate, H, C, S);
-  g_launch_count += 4;
+  k_gn_bwd_apply<<<dim3(S, n), kT, 0, st>>>(dout_flat, x_pad, stats, gamma, partial, persample, dx_pad, accumulate, H, C,
+                                            S, 1.f / ((float)(C / kGnGroups) * H * H));
+  g_launch_count += 2;
+}
+
+// cross-sample sums of the whole backward pass in ONE launch: entry e sums rows of src into the gradient arena
+__global__ void __launch_bounds__(1024) k_sum_rows_table(const SumEntry *__restrict__ tab, float *__restrict__ gbase) {
+  __shared__ float red[2][32][33];
+  const SumEntry e = tab[blockIdx.y];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if ((int)blockIdx.x * 32 >= e.C) return;
+  const int c = blockIdx.x * 32 + tx;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < e.C) {
+    for (int i = ty; i < e.rows; i += 32) {
+      s0 += e.src[(size_t)i * e.ld + c];
+      if (e.K > 1) s1 += e.src[(size_t)i * e.ld + e.C + c];
+    }
+  }
+  red[0][ty][tx] = s0;
+  red[1][ty][tx] = s1;
+  __syncthreads();
+  if (ty == 0 && c < e.C) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      a += red[0][q][tx];
+      b += red[1][q][tx];
+    }
+    if (e.d0 >= 0) gbase[e.d0 + c] = a;
+    if (e.d0b >= 0) gbase[e.d0b + c] = a;
+    if (e.d1 >= 0 && e.K > 1) gbase[e.d1 + c] = b;
+  }
+}
+void launch_sum_rows_table(const SumEntry *table_dev, int n_entries, float *grad_base, cudaStream_t st) {
+  if (n_entries <= 0) return;
+  k_sum_rows_table<<<dim3(16, n_entries), 1024, 0, st>>>(table_dev, grad_base);
+  ++g_launch_count;
 }
 
 // =================================================================================================================
@@ -478,18 +498,18 @@ __global__ void k_rowsum_slices(const float *__restrict__ partial, float *__rest
     rowsum[(size_t)n * ld + col0 + c] = a;
   }
 }
-void launch_bias_grad(const bf16 *dy, int dy_flat, float *partial, float *persample, float *bias_grad_a,
-                      float *bias_grad_b, float *rowsum, int rowsum_ld, int rowsum_col0, int n, int H, int C,
-                      cudaStream_t st) {
+int launch_bias_partial(const bf16 *dy, int dy_flat, float *partial, float *rowsum, int rowsum_ld, int rowsum_col0, int n,
+                        int H, int C, cudaStream_t st) {
   const int S = slices_for(H, n);
   k_colsum<<<dim3(S, n), kT, 0, st>>>(dy, dy_flat, partial, H, C, S);
-  // per-sample sums go either into the caller's rowsum matrix (gradient of the temb/cemb projection) or into scratch
-  float *ps = rowsum ? rowsum + rowsum_col0 : persample;
-  const int ld = rowsum ? rowsum_ld : C;
-  k_rowsum_slices<<<n, 256, 0, st>>>(partial, ps, ld, 0, C, S);
-  k_sum_rows<<<(C + 31) / 32, 1024, 0, st>>>(ps, ld, n, 1, C, bias_grad_a, bias_grad_b, nullptr);
-  g_launch_count += 3;
+  ++g_launch_count;
+  if (rowsum) {
+    k_rowsum_slices<<<n, 256, 0, st>>>(partial, rowsum, rowsum_ld, rowsum_col0, C, S);
+    ++g_launch_count;
+  }
+  return n * S;
 }
+int unet_slices_for(int H, int n) { return slices_for(H, n); }
 
 // =================================================================================================================
 // copies
@@ -702,25 +722,24 @@ __global__ void __launch_bounds__(kT) k_eps_in(const float *__restrict__ deps, b
   for (int c = 0; c < 3; ++c) f[c] = deps[((size_t)n * 3 + c) * hw + p];
   u_st8(dst, f);
 }
-__global__ void __launch_bounds__(256) k_eps_bias_grad(const float *__restrict__ deps, float *__restrict__ dbias3, int n,
-                                                       int hw) {
+__global__ void __launch_bounds__(256) k_eps_bias_partial(const float *__restrict__ deps, float *__restrict__ partial,
+                                                          int hw) {
   __shared__ float red[256];
-  const int c = blockIdx.x;
+  const int c = blockIdx.x, i = blockIdx.y;
   float s = 0.f;
-  for (int i = 0; i < n; ++i)
-    for (int p = threadIdx.x; p < hw; p += 256) s += deps[((size_t)i * 3 + c) * hw + p];
+  for (int p = threadIdx.x; p < hw; p += 256) s += deps[((size_t)i * 3 + c) * hw + p];
   red[threadIdx.x] = s;
   __syncthreads();
   for (int o = 128; o; o >>= 1) {
     if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) dbias3[c] = red[0];
+  if (threadIdx.x == 0) partial[(size_t)i * 3 + c] = red[0];
 }
-void launch_eps_in(const float *deps_nchw, bf16 *dy_pad, float *dbias3, int n, int H, cudaStream_t st) {
+void launch_eps_in(const float *deps_nchw, bf16 *dy_pad, float *dbias_partial, int n, int H, cudaStream_t st) {
   const int total = n * H * H;
   k_eps_in<<<(total + kT - 1) / kT, kT, 0, st>>>(deps_nchw, dy_pad, total, H);
-  k_eps_bias_grad<<<3, 256, 0, st>>>(deps_nchw, dbias3, n, H * H);
+  k_eps_bias_partial<<<dim3(3, n), 256, 0, st>>>(deps_nchw, dbias_partial, H * H);
   g_launch_count += 2;
 }
 

@@ -18,30 +18,35 @@ constexpr int kGnGroups = 32;  // Normalize() = GroupNorm(32, C, eps 1e-6)   dif
 // slices of one image's H*H pixels handled by separate CTAs in the per-sample kernels
 int unet_slices(int H);
 
-// ---- GroupNorm forward: partial[n][S][2][C] (sum x, sum x^2) -> stats[n][32][2] (mean, rstd) -> apply ----
-void launch_gn_stats(const __nv_bfloat16 *x_pad, float *partial, float *stats, int n, int H, int C, float eps,
-                     cudaStream_t st);
-// out = dropout(act(gamma * (x - mean) * rstd + beta)); act = swish or identity; out padded (out_flat = 0) or flat
-void launch_gn_apply(const __nv_bfloat16 *x_pad, const float *stats, const float *gamma, const float *beta,
-                     __nv_bfloat16 *out, int out_flat, int swish, float drop_p, uint32_t drop_seed, int n, int H, int C,
-                     cudaStream_t st);
+// ---- GroupNorm forward: partial[n][S][2][C] (sum x, sum x^2 per slice) -> stats[n][32][2] (mean, rstd; kept for the
+// backward pass) -> out = dropout(act(gamma * (x - mean) * rstd + beta)); act = swish or identity; out padded or flat ----
+void launch_gn_forward(const __nv_bfloat16 *x_pad, float *partial, float *stats, const float *gamma, const float *beta,
+                       __nv_bfloat16 *out, int out_flat, int swish, float drop_p, uint32_t drop_seed, int n, int H, int C,
+                       float eps, cudaStream_t st);
 // ---- GroupNorm backward.  dout: gradient w.r.t. the GN(+swish+dropout) output, FLAT [n*H*H][C] ----
 //   partial[n][S][2][C] = per-sample, per-slice sums over pixels of dyh and dyh * xhat (dyh = dout * act'(yh) * dropmask)
-//   persample[n][2][C]  = the same summed over the slices (scratch)
-//   dgamma[c] = sum_n,pix dyh*xhat ; dbeta[c] = sum dyh ; coef[n][32][2] = (sum_c gamma dyh, sum_c gamma dyh xhat) / count
+//   persample[n][2][C]  = the same summed over the slices; the caller sums it over n into dbeta / dgamma (SumEntry)
 //   dx = rstd * (gamma*dyh - coefA - xhat*coefB), written padded; accumulate != 0: added to what dx already holds
 //   dout_flat is OVERWRITTEN with dyh (it has no other consumer)
-void launch_gn_backward(__nv_bfloat16 *dout_flat, const __nv_bfloat16 *x_pad, const float *stats,
-                        const float *gamma, const float *beta, int swish, float drop_p, uint32_t drop_seed,
-                        float *partial, float *persample, float *coef, float *dgamma, float *dbeta,
+void launch_gn_backward(__nv_bfloat16 *dout_flat, const __nv_bfloat16 *x_pad, const float *stats, const float *gamma,
+                        const float *beta, int swish, float drop_p, uint32_t drop_seed, float *partial, float *persample,
                         __nv_bfloat16 *dx_pad, int accumulate, int n, int H, int C, cudaStream_t st);
 
-// ---- bias gradients: per-sample column sums of dY (padded or flat), then reductions ----
-//   partial[n][S][C], persample[n][C] (scratch); bias_grad_a / bias_grad_b [C] (either may be NULL) = sum over samples and pixels;
+// ---- cross-sample sums, all in one launch at the end of the backward pass ----
+//   gbase[d0 + c] (and gbase[d0b + c]) = sum_rows src[row*ld + c];  K == 2: gbase[d1 + c] = sum_rows src[row*ld + C + c]
+struct SumEntry {
+  const float *src;
+  long long ld;
+  int rows, K, C;
+  long long d0, d0b, d1;  // offsets into the gradient arena, -1 = unused
+};
+void launch_sum_rows_table(const SumEntry *table_dev, int n_entries, float *grad_base, cudaStream_t st);
+
+// ---- bias gradients: per-sample, per-slice column sums of dY (padded or flat): partial[n][S][C]; returns n*S.
 //   rowsum (optional) [n][rowsum_ld] at column rowsum_col0: per-sample sums (gradient of the temb/cemb projection output)
-void launch_bias_grad(const __nv_bfloat16 *dy, int dy_flat, float *partial, float *persample, float *bias_grad_a,
-                      float *bias_grad_b, float *rowsum, int rowsum_ld, int rowsum_col0, int n, int H, int C,
-                      cudaStream_t st);
+int launch_bias_partial(const __nv_bfloat16 *dy, int dy_flat, float *partial, float *rowsum, int rowsum_ld,
+                        int rowsum_col0, int n, int H, int C, cudaStream_t st);
+int unet_slices_for(int H, int n);  // slices launched for a batch of n (<= unet_slices(H))
 
 // ---- copies on padded tensors ----
 void launch_concat(const __nv_bfloat16 *a_pad, int Ca, const __nv_bfloat16 *b_pad, int Cb, __nv_bfloat16 *out_pad, int n,
@@ -61,8 +66,8 @@ void launch_down_col2im(const __nv_bfloat16 *dcol, __nv_bfloat16 *din_pad, int a
                         cudaStream_t st);
 // eps[n][3][H][H] fp32 = y[m][0..2] + bias   (y: fp32 [n*H*H][64] GEMM output of conv_out padded to 64 channels)
 void launch_eps_out(const float *y, const float *bias3, float *eps_nchw, int n, int H, cudaStream_t st);
-// dy_pad[n][H+2][H+2][64] bf16 (channels 0..2) = deps[n][3][H][H]; dbias3 = sum over n, pixels
-void launch_eps_in(const float *deps_nchw, __nv_bfloat16 *dy_pad, float *dbias3, int n, int H, cudaStream_t st);
+// dy_pad[n][H+2][H+2][64] bf16 (channels 0..2) = deps[n][3][H][H]; dbias_partial[n][3] = per-sample sums over pixels
+void launch_eps_in(const float *deps_nchw, __nv_bfloat16 *dy_pad, float *dbias_partial, int n, int H, cudaStream_t st);
 
 // ---- attention (diffusion.py:167-192): rows of S fp32 [M][Te] -> P bf16; block-diagonal mask of block T inside Te ----
 void launch_softmax(const float *S, __nv_bfloat16 *P, int M, int Te, int T, float scale, cudaStream_t st);
