@@ -101,6 +101,125 @@ def oracle_cpu_steps_per_sec(batch, steps, warmup=0):
     return sum(times) / len(times), torch.get_num_threads()
 
 
+def oracle_cpu_ddpm_sec_per_it(sample, steps=2, warmup=1):
+    """The reference's CPU path for one DDPM saliency_unlearn iteration (oracle/ddpm.py: the statements of
+    runners/diffusion.py:519-593 around the pinned U-Net restatement, torch fp32, all host threads) on `sample` remain +
+    `sample` forget images.  Returns (seconds per iteration at that size, threads)."""
+    import torch
+    from oracle import ddpm as OD
+    from unlearn_saliency_b200.diffusion.runner import get_beta_schedule
+    from unlearn_saliency_b200.diffusion.unet import ConditionalUNet, cifar10_config
+    torch.set_num_threads(os.cpu_count())
+    torch.manual_seed(0)
+    model = ConditionalUNet(cifar10_config())
+    g = torch.Generator().manual_seed(1)
+    mask = {k: (torch.rand(p.shape, generator=g) < 0.5).to(torch.int64) for k, p in model.named_parameters()}
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    betas = torch.from_numpy(get_beta_schedule("linear", beta_start=1e-4, beta_end=0.02, num_diffusion_timesteps=1000)).float()
+    n, S = sample, 32
+    times = []
+    for s in range(warmup + steps):
+        r = dict(x_r=torch.rand(n, 3, S, S, generator=g), c_r=torch.randint(1, 10, (n,), generator=g),
+                 x_f=torch.rand(n, 3, S, S, generator=g), c_f=torch.zeros(n, dtype=torch.long),
+                 t_r=torch.randint(0, 1000, (n,), generator=g), e_r=torch.randn(n, 3, S, S, generator=g),
+                 t_f=torch.randint(0, 1000, (n,), generator=g), e_f=torch.randn(n, 3, S, S, generator=g),
+                 drop_r=torch.rand(n, generator=g) < 0.1, drop_f=torch.rand(n, generator=g) < 0.1,
+                 drop_p=torch.rand(n, generator=g) < 0.1)
+        t0 = time.perf_counter()
+        OD.saliency_unlearn_step(model, opt, mask, r, betas, alpha=1e-3, method="rl")
+        if s >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), torch.get_num_threads()
+
+
+DDPM_BATCH = 128
+DDPM_IT_TFLOP = 7 * DDPM_BATCH * 12.449e-3  # SURVEY.md section 8d: 7 forward-equivalents x 128 images x 12.449 GFLOP
+
+
+def bench_ddpm(args, dev, rank, world, L, timed, tf_peak, peak_src):
+    """Second headline workload (BASELINE.json configs[2]): one DDPM saliency_unlearn iteration (runners/diffusion.py:519-593)
+    on the cifar10 U-Net, 128 remain + 128 forget images per GPU, method rl, dropout 0.1, 50% mask, clip 1.0, Adam.
+    Weak scaling like the ResNet line; N > 1 adds one NCCL all-reduce of the 154 MB gradient arena per iteration."""
+    import ctypes as C
+    import torch
+    from unlearn_saliency_b200.diffusion.engine import UNetEngine
+    from unlearn_saliency_b200.diffusion.runner import DDPMEngineUnlearner, get_beta_schedule
+    from unlearn_saliency_b200.diffusion.unet import cifar10_config
+    cfg = cifar10_config()
+    eng = UNetEngine(cfg, max_batch=2 * DDPM_BATCH, device=dev)
+    g = torch.Generator(device="cpu").manual_seed(0)  # same random-init weights on every rank
+    sd = {}
+    for k, shp in eng.shapes.items():
+        if "norm" in k:
+            sd[k] = torch.ones(shp) if k.endswith("weight") else torch.zeros(shp)
+        elif len(shp) >= 2:
+            fan_in = 1
+            for d in shp[1:]:
+                fan_in *= d
+            sd[k] = (torch.rand(shp, generator=g) * 2 - 1) / fan_in ** 0.5
+        else:
+            sd[k] = (torch.rand(shp, generator=g) * 2 - 1) * 0.05
+    eng.load_state_dict(sd)
+    mask_native = (torch.rand(eng.n, generator=g) < 0.5).to(torch.int64).to(dev)
+    betas = torch.from_numpy(get_beta_schedule("linear", beta_start=1e-4, beta_end=0.02, num_diffusion_timesteps=1000)).float()
+    un = DDPMEngineUnlearner(eng, betas, lr=1e-4, grad_clip=1.0)
+    un.opt.mask_bits = eng.ctx.pack_mask(mask_native)
+    gen = torch.Generator(device="cpu").manual_seed(200 + rank)
+    B = DDPM_BATCH
+    host = [(torch.rand(B, 3, 32, 32, generator=gen).pin_memory(), torch.randint(1, 10, (B,), generator=gen).pin_memory(),
+             torch.rand(B, 3, 32, 32, generator=gen).pin_memory(), torch.zeros(B, dtype=torch.long).pin_memory())
+            for _ in range(4)]
+    resident = [tuple(t.to(dev) for t in h) for h in host]
+
+    def it_resident(i):
+        xr, cr, xf, cf = resident[i % 4]
+        un.saliency_unlearn_step(xr, cr, xf, cf, alpha=1e-3, method="rl")
+
+    last = [0.0]
+
+    def it_e2e(i):
+        xr, cr, xf, cf = host[i % 4]  # pinned host tensors: the step copies them to the device (H2D inside the timed region)
+        last[0] = float(un.saliency_unlearn_step(xr, cr, xf, cf, alpha=1e-3, method="rl").item())  # D2H of the loss
+
+    steps = max(1, min(args.steps, args.ddpm_steps))
+    for i in range(3):
+        it_resident(i)
+    l0 = L.salun_launch_count()
+    ms = timed(it_resident, steps) / steps
+    launches = L.salun_launch_count() - l0
+    for i in range(3):
+        it_e2e(i)
+    ms_e2e = timed(it_e2e, steps) / steps
+    roof = None
+    if rank == 0:
+        L.salun_profile_begin()
+        for i in range(min(steps, 3)):
+            it_resident(i)
+        pm, pc, pf = (C.c_double * 2)(), (C.c_int64 * 2)(), (C.c_double * 2)()
+        L.salun_profile_end(pm, pc, pf)
+        k = min(steps, 3)
+        ach = [pf[c] / (pm[c] * 1e-3) / 1e12 if pm[c] > 0 else 0.0 for c in range(2)]
+        roof = {"bound": "tensor", "kernel": "k_conv_gemm_p / k_gemm2 (conv forward + dgrad, attention and projection GEMMs)",
+                "achieved": ach[0], "peak": tf_peak, "unit": "TFLOP/s", "frac": ach[0] / tf_peak, "traffic": None,
+                "peak_source": peak_src, "avg_launch_us": pm[0] * 1e3 / max(1, pc[0]), "launches_per_it": pc[0] / k,
+                "share_of_it": pm[0] / k / ms,
+                "other": {"kernel": "k_wgrad (side stream)", "achieved": ach[1], "share_of_it": pm[1] / k / ms}}
+    h2d = 2 * (B * 3 * 32 * 32 * 4 + B * 8)
+    res = {"metric": "DDPM saliency_unlearn iterations/sec (cifar10 U-Net 32x32, 128 remain + 128 forget images per GPU, rl)",
+           "value": world * 1000.0 / ms, "unit": "iterations/s", "n_gpus": world, "steps": steps, "ms_per_it": ms,
+           "tflops_per_gpu": DDPM_IT_TFLOP / ms * 1e3, "dtype": "bf16", "scaling": "weak",
+           "config": {"workload": "DDPM U-Net CIFAR-10 32x32 saliency_unlearn iteration (runners/diffusion.py:519-593), "
+                                  "method rl, alpha 1e-3, dropout 0.1, cond_drop 0.1, mask ratio 0.5, clip 1.0, Adam 1e-4",
+                      "per_gpu_batch": [B, B], "params": eng.n,
+                      "collective": "NCCL all-reduce of the flat gradient (before the clip)" if world > 1 else "none"},
+           "gpu_launches": int(launches), "launches_per_it": launches / steps,
+           "e2e": {"value": world * 1000.0 / ms_e2e, "unit": "iterations/s", "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": 4, "ms_per_it": ms_e2e},
+           "roofline": roof, "final_loss": last[0]}
+    eng.close()
+    return res
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -120,6 +239,15 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_ddpm:
+        sn = int(os.environ.get("SALUN_REF_DDPM_BATCH", "2"))
+        dsec, dthreads = oracle_cpu_ddpm_sec_per_it(sn, steps=2, warmup=1)
+        dval = 1.0 / (dsec * DDPM_BATCH / sn)
+        line["ddpm"] = {"metric": "DDPM saliency_unlearn iterations/sec (cifar10 U-Net 32x32, 128 remain + 128 forget images, rl)",
+                        "value": dval, "unit": "iterations/s", "dtype": "f32",
+                        "cpu_baseline": {"value": dval, "unit": "iterations/s", "cores": dthreads, "kind": "port",
+                                         "sample": f"2 iterations of {sn}+{sn} images after 1 warm-up (oracle/ddpm.py, torch fp32 CPU), "
+                                                   f"scaled x{DDPM_BATCH // sn} to 128+128 images"}}
     print(json.dumps(line), flush=True)
 
 
@@ -130,6 +258,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ddpm", action="store_true", help="skip the second workload (DDPM U-Net iteration)")
+    ap.add_argument("--ddpm-steps", type=int, default=20)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -281,6 +411,22 @@ def main():
         cpu = {"value": 1.0 / (sec * BATCH / sb), "unit": "steps/s", "cores": threads, "kind": "port",
                "sample": f"4 RL steps of {sb} images after 1 warm-up (oracle/classification.py, torch fp32), scaled x{BATCH // sb}"}
 
+    ddpm = None
+    if not args.no_ddpm:
+        try:
+            eng.close()
+            del opt
+            torch.cuda.empty_cache()
+            ddpm = bench_ddpm(args, dev, rank, world, L, timed, tf_peak, peak_src)
+            if rank == 0 and world == 1 and not args.no_cpu_baseline:
+                sn = int(os.environ.get("SALUN_REF_DDPM_BATCH", "2"))
+                dsec, dthreads = oracle_cpu_ddpm_sec_per_it(sn, steps=1, warmup=1)
+                ddpm["cpu_baseline"] = {"value": 1.0 / (dsec * DDPM_BATCH / sn), "unit": "iterations/s", "cores": dthreads,
+                                        "kind": "port", "sample": f"1 iteration of {sn}+{sn} images after 1 warm-up "
+                                        f"(oracle/ddpm.py, torch fp32), scaled x{DDPM_BATCH // sn}"}
+        except Exception as e:  # the headline line must still be printed
+            ddpm = {"error": repr(e)}
+            print(f"[bench] DDPM workload failed: {e!r}", file=sys.stderr)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
@@ -297,6 +443,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e},
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "final_loss": final_loss,
+            "ddpm": ddpm,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

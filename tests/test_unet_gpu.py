@@ -228,40 +228,22 @@ def _draw(seed, n, size):
 
 @pytest.mark.parametrize("method", ["rl", "ga"])
 def test_engine_saliency_unlearn_step_matches_reference_statements(salun_ctx, method):
-    from unlearn_saliency_b200.diffusion.runner import DDPMEngineUnlearner, eps_loss, get_beta_schedule, q_sample
+    """DDPMEngineUnlearner.saliency_unlearn_step vs oracle/ddpm.py (the reference's statements, stock PyTorch fp32)"""
+    from oracle import ddpm as OD
+    from unlearn_saliency_b200.diffusion.runner import DDPMEngineUnlearner, get_beta_schedule
     cfg = small_config()
     ref = _torch_model(cfg)
     eng = _engine(cfg, ref, salun_ctx)
     betas = torch.from_numpy(get_beta_schedule("linear", beta_start=1e-4, beta_end=0.02, num_diffusion_timesteps=1000)).float()
     g = torch.Generator().manual_seed(3)
-    mask = {"module." + k: (torch.rand(p.shape, generator=g) < 0.5).to(torch.int64) for k, p in ref.named_parameters()}
-    un = DDPMEngineUnlearner(eng, betas, lr=1e-4, grad_clip=1.0, mask=mask)
+    mask = {k: (torch.rand(p.shape, generator=g) < 0.5).to(torch.int64) for k, p in ref.named_parameters()}
+    un = DDPMEngineUnlearner(eng, betas, lr=1e-4, grad_clip=1.0, mask={"module." + k: v for k, v in mask.items()})
     opt = torch.optim.Adam(ref.parameters(), lr=1e-4, weight_decay=0.0, betas=(0.9, 0.999), amsgrad=False, eps=1e-8)
-    bd = betas.cuda()
     p0 = {k: p.detach().clone() for k, p in ref.named_parameters()}
-    n, S = 4, cfg.data.image_size
-    r = _draw(10, n, S)
+    r = _draw(10, 4, cfg.data.image_size)
     loss_mine = un.saliency_unlearn_step(r["x_r"], r["c_r"], r["x_f"], r["c_f"], alpha=1e-3, method=method,
                                          rng={k: r[k] for k in ("t_r", "e_r", "t_f", "e_f", "drop_r", "drop_f", "drop_p")})
-    # the reference's statements (runners/diffusion.py:523-593) with stock PyTorch (dropout is 0 in this config)
-    ref.train()
-    xr, xf = 2 * r["x_r"].cuda() - 1, 2 * r["x_f"].cuda() - 1
-    remain = eps_loss(ref, xr, r["t_r"].cuda(), r["c_r"].cuda(), r["e_r"].cuda(), bd, drop_mask=r["drop_r"].cuda())
-    if method == "ga":
-        forget = -eps_loss(ref, xf, r["t_f"].cuda(), r["c_f"].cuda(), r["e_f"].cuda(), bd, drop_mask=r["drop_f"].cuda())
-    else:
-        xt = q_sample(xf, r["t_f"].cuda(), r["e_f"].cuda(), bd)
-        out = ref(xt, r["t_f"].cuda().float(), r["c_f"].cuda(), mode="train", drop_mask=r["drop_f"].cuda())
-        pseudo = ref(xt, r["t_f"].cuda().float(), (r["c_f"].cuda() + 1) % 10, mode="train", drop_mask=r["drop_p"].cuda()).detach()
-        forget = torch.nn.functional.mse_loss(out, pseudo)
-    loss = forget + 1e-3 * remain
-    opt.zero_grad()
-    loss.backward()
-    gref = {k: p.grad.detach().clone() for k, p in ref.named_parameters()}
-    norm_ref = torch.nn.utils.clip_grad_norm_(ref.parameters(), 1.0)
-    for k, p in ref.named_parameters():
-        p.grad *= mask["module." + k].to(p.device)
-    opt.step()
+    loss, norm_ref, gref = OD.saliency_unlearn_step(ref, opt, mask, r, betas.cuda(), alpha=1e-3, method=method)
     assert abs(float(loss_mine) - float(loss)) <= 0.02 * abs(float(loss)) + 1e-5, (float(loss_mine), float(loss))
     assert abs(float(un.opt.grad_norm()) - float(norm_ref)) <= 0.03 * float(norm_ref)   # the clip used the same norm
     _assert_grads_close(eng.grad_dict(), gref)
@@ -269,7 +251,7 @@ def test_engine_saliency_unlearn_step_matches_reference_statements(salun_ctx, me
     mine = eng.state_dict()
     agree = tot = 0
     for k, p in ref.named_parameters():
-        m = mask["module." + k].cuda().bool()
+        m = mask[k].cuda().bool()
         assert torch.equal(mine[k][~m], p0[k][~m]), k
         big = m & (gref[k].abs() > 0.1 * gref[k].abs().mean())     # skip near-zero gradients (their sign is rounding noise)
         agree += int((torch.sign(mine[k] - p0[k])[big] == torch.sign(p.detach() - p0[k])[big]).sum())
@@ -279,30 +261,22 @@ def test_engine_saliency_unlearn_step_matches_reference_statements(salun_ctx, me
 
 
 def test_engine_generate_mask_matches_reference_statements(salun_ctx, tmp_path):
-    from unlearn_saliency_b200.diffusion.runner import DDPMEngineUnlearner, get_beta_schedule, q_sample
+    """DDPMEngineUnlearner.generate_mask_batch / finish_mask vs oracle/ddpm.py + the argsort definition of the mask"""
+    from oracle import ddpm as OD
+    from unlearn_saliency_b200.diffusion.runner import DDPMEngineUnlearner, get_beta_schedule
     cfg = small_config()
     ref = _torch_model(cfg)
     eng = _engine(cfg, ref, salun_ctx, max_batch=8)
     betas = torch.from_numpy(get_beta_schedule("linear", beta_start=1e-4, beta_end=0.02, num_diffusion_timesteps=1000)).float()
     un = DDPMEngineUnlearner(eng, betas)
-    bd = betas.cuda()
-    grads = {k: 0 for k, _ in ref.named_parameters()}
-    ref.eval()
-    S = cfg.data.image_size
+    grads = {}
     for b, n in enumerate((4, 6)):   # 2n = 8 fits max_batch (one batched call), 2n = 12 does not (three-pass path)
-        r = _draw(30 + b, n, S)
+        r = _draw(30 + b, n, cfg.data.image_size)
         loss_mine = un.generate_mask_batch(r["x_f"], r["c_f"], cond_scale=2.0, t=r["t_f"], e=r["e_f"])
-        x = 2 * r["x_f"].cuda() - 1
-        xt = q_sample(x, r["t_f"].cuda(), r["e_f"].cuda(), bd)
-        out = ref(xt, r["t_f"].cuda().float(), r["c_f"].cuda(), cond_scale=2.0, mode="test")
-        loss = (r["e_f"].cuda() - out).square().sum(dim=(1, 2, 3)).mean(dim=0)       # :980
+        loss = OD.generate_mask_batch(ref, r["x_f"].cuda(), r["c_f"].cuda(), r["t_f"].cuda(), r["e_f"].cuda(), betas.cuda(),
+                                      grads, cond_scale=2.0)
         assert abs(float(loss_mine) - float(loss)) <= 0.03 * float(loss)
-        ref.zero_grad()
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(ref.parameters(), 1.0)                          # :985-990
-        for k, p in ref.named_parameters():
-            if p.grad is not None:
-                grads[k] = grads[k] + p.grad.data.cpu()                                # :992-996
+    grads = {k: grads[k] for k, _ in ref.named_parameters()}
     path = str(tmp_path / "mask" / "0" / "with_0.5.pt")
     un.finish_mask(path, 0.5)
     m = torch.load(path)
