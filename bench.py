@@ -324,7 +324,23 @@ def main():
     dev_x = [t.to(dev) for t in host_x]
     dev_y = [t.to(dev) for t in host_y]
 
+    # The ~175 dependent launches of a step are launch-latency bound: capture the step once into a CUDA graph
+    # (engine.GraphedStep) and replay it.  N > 1 stays eager (the fused DP kernel synchronises ranks through peer flags).
+    graph, graph_launches = None, 0
+    if world == 1 and os.environ.get("SALUN_GRAPH", "1") != "0":
+        try:
+            from unlearn_saliency_b200.engine import GraphedStep
+            c0 = L.salun_launch_count()
+            graph = GraphedStep(eng, opt, BATCH)
+            graph_launches = (L.salun_launch_count() - c0) // 3  # two warm-up steps + the captured one
+        except Exception as e:
+            print(f"[bench] CUDA graph capture unavailable ({e!r}); eager launches", file=sys.stderr)
+            graph = None
+
     def step_resident(i):
+        if graph is not None:
+            graph(dev_x[i % n_pool], dev_y[i % n_pool])
+            return
         eng.forward_backward(dev_x[i % n_pool], dev_y[i % n_pool])
         if world > 1 and not fused_dp:
             dist.all_reduce(eng.grads)
@@ -332,6 +348,8 @@ def main():
         opt.step()  # fused_dp: reduce-scatter + masked SGD + all-gather in one kernel over NVLink peer memory
 
     def step_e2e(i):
+        if graph is not None:  # H2D copies into the graph's static buffers, replay, D2H read of the loss
+            return float(graph(host_x[i % n_pool], host_y[i % n_pool]).item())
         x = host_x[i % n_pool].to(dev, non_blocking=True)
         y = host_y[i % n_pool].to(dev, non_blocking=True)
         loss, _ = eng.forward_backward(x, y)
@@ -369,6 +387,8 @@ def main():
     launches0 = L.salun_launch_count()
     ms_total = timed(step_resident, args.steps)
     launches = L.salun_launch_count() - launches0
+    if graph is not None:
+        launches = graph_launches * args.steps  # graph replays do not pass through the library's launch counter
     clocks = sampler.stop() if sampler else None
     ms_step = ms_total / args.steps
     value = world * 1000.0 / ms_step
@@ -438,6 +458,7 @@ def main():
                        "collective": ("fused reduce-scatter + masked SGD + all-gather kernel over NVLink peer memory"
                                       if fused_dp else ("NCCL all-reduce of the flat gradient" if world > 1 else "none")),
                        "optimizer": "SGD lr 0.013 momentum 0.9 wd 5e-4 (fused masked step)",
+                       "cuda_graph": graph is not None,
                        "l2": "step working set (~2 GB activations + 134 MB optimizer state) exceeds the 126 MB L2"},
             "tflops_per_gpu": STEP_GFLOP / ms_step, "gpu_launches": int(launches), "launches_per_step": launches / args.steps,
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

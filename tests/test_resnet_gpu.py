@@ -245,3 +245,37 @@ def test_resnet50_forward_backward(salun_ctx, imagenet, size, n):
     sd = eng.state_dict()
     assert set(sd.keys()) == set(OC.state_dict_of(params, buffers).keys())
     eng.close()
+
+
+def test_graphed_step_equals_eager_step(salun_ctx):
+    """engine.GraphedStep (CUDA graph of forward_backward + MaskedSGD.step) is bit-identical to the eager calls, and the
+    capture leaves the model state untouched."""
+    from unlearn_saliency_b200.engine import GraphedStep, MaskedSGD, ResNetEngine
+    params, buffers = OC.synth_state(10, seed=0)
+    sd = OC.state_dict_of(params, buffers)
+    g = torch.Generator().manual_seed(5)
+    n = 32
+    xs = [torch.rand(n, 3, 32, 32, generator=g).cuda() for _ in range(3)]
+    ys = [torch.randint(0, 10, (n,), generator=g).cuda() for _ in range(3)]
+    res = []
+    for graphed in (False, True):
+        eng = ResNetEngine("resnet18", 10, 32, max_batch=n, ctx=salun_ctx)
+        eng.load_state_dict(sd)
+        bits = eng.ctx.pack_mask((torch.rand(eng.n_params, generator=torch.Generator().manual_seed(6)) < 0.5).to(torch.int64).cuda())
+        opt = MaskedSGD(eng, 0.013, 0.9, 5e-4, mask_bits=bits)
+        eng.train()
+        p_before = eng.params.clone()
+        step = GraphedStep(eng, opt, n) if graphed else None
+        assert torch.equal(eng.params, p_before)          # capture + warm-up restored the snapshot
+        losses = []
+        for x, y in zip(xs, ys):
+            if graphed:
+                losses.append(float(step(x, y)))
+            else:
+                loss, _ = eng.forward_backward(x, y)
+                opt.step()
+                losses.append(float(loss))
+        torch.cuda.synchronize()
+        res.append((eng.params.clone(), eng.running_mean.clone(), losses))
+        eng.close()
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and res[0][2] == res[1][2]

@@ -298,3 +298,46 @@ def test_engine_generate_mask_matches_reference_statements(salun_ctx, tmp_path):
     ref_mask = OT.topk_mask_argsort(flat_ref.abs().numpy(), k)
     assert (mine_mask != ref_mask).mean() < 0.05, (mine_mask != ref_mask).mean()
     eng.close()
+
+
+def test_diffusion_runner_mirror_end_to_end(salun_ctx, tmp_path, monkeypatch):
+    """Diffusion(args, config).generate_mask() / .saliency_unlearn() (DDPM/train.py:150-155) on synthetic loaders:
+    reads <ckpt_folder>/ckpts/ckpt.pth, writes results/cifar10/mask/<label>/with_0.5.pt and <ckpt_dir>/ckpt.pth in the
+    reference's formats; masked-out weights stay at their checkpoint values."""
+    from torch.utils.data import DataLoader, TensorDataset
+    from unlearn_saliency_b200.diffusion.runner import Diffusion
+    from unlearn_saliency_b200.diffusion.unet import ConditionalUNet
+    cfg = tiny_config()
+    cfg.training = SimpleNamespace(batch_size=4, n_iters=3, snapshot_freq=3, log_freq=1)
+    cfg.optim = SimpleNamespace(weight_decay=0.0, optimizer="Adam", lr=1e-4, beta1=0.9, amsgrad=False, eps=1e-8, grad_clip=1.0)
+    cfg.ckpt_dir = str(tmp_path / "out")
+    model = ConditionalUNet(cfg)
+    sd0 = {"module." + k: v.clone() for k, v in model.state_dict().items()}
+    (tmp_path / "ck" / "ckpts").mkdir(parents=True)
+    torch.save([sd0, {}, 0], str(tmp_path / "ck" / "ckpts" / "ckpt.pth"))
+    g = torch.Generator().manual_seed(0)
+    S = cfg.data.image_size
+    remain = DataLoader(TensorDataset(torch.rand(12, 3, S, S, generator=g), torch.randint(1, 10, (12,), generator=g)), batch_size=4)
+    forget = DataLoader(TensorDataset(torch.rand(8, 3, S, S, generator=g), torch.zeros(8, dtype=torch.long)), batch_size=4)
+    monkeypatch.chdir(tmp_path)
+    args = SimpleNamespace(ckpt_folder=str(tmp_path / "ck"), label_to_forget=0, cond_scale=2.0, mask_path=None, alpha=1e-3,
+                           method="rl", seed=1234)
+    runner = Diffusion(args, cfg, loaders=(remain, forget))
+    runner.generate_mask()
+    mpath = tmp_path / "results" / "cifar10" / "mask" / "0" / "with_0.5.pt"
+    mask = torch.load(str(mpath))
+    assert list(mask.keys()) == list(sd0.keys())
+    n_tot = sum(v.numel() for v in mask.values())
+    assert sum(int(v.sum()) for v in mask.values()) == int(n_tot * 0.5)
+    assert all(v.dtype == torch.int64 and v.device.type == "cpu" for v in mask.values())
+    args.mask_path = str(mpath)
+    loss = runner.saliency_unlearn()
+    assert loss is not None and np.isfinite(loss)
+    states = torch.load(str(tmp_path / "out" / "ckpt.pth"))
+    assert len(states) == 3 and states[2] == 2 and list(states[0].keys()) == list(sd0.keys())
+    moved = 0
+    for k, v in states[0].items():
+        m = mask[k].bool()
+        assert torch.equal(v.cpu()[~m], sd0[k][~m]), k
+        moved += int((v.cpu()[m] != sd0[k][m]).sum())
+    assert moved > 0.9 * int(n_tot * 0.5)

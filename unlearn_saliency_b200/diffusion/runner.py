@@ -288,3 +288,117 @@ class DDPMEngineUnlearner:
         optim = {"exp_avg": self.engine.dict_from_flat(self.opt.exp_avg), "exp_avg_sq": self.engine.dict_from_flat(self.opt.exp_avg_sq),
                  "step": self.opt.step_count}
         torch.save([sd, optim, step], path)
+
+
+def get_forget_dataset(args, config, label_to_drop):
+    """(remain_loader, forget_loader) like DDPM/datasets/__init__.py:120-177: CIFAR-10 train split, Resize +
+    RandomHorizontalFlip (config.data.random_flip) + ToTensor, split by label.  The data must already be under
+    config.data.path (this mirror never downloads)."""
+    from torch.utils.data import DataLoader
+    from torchvision import transforms
+    from torchvision.datasets import CIFAR10
+    tf = [transforms.Resize(config.data.image_size)]
+    if getattr(config.data, "random_flip", True):
+        tf.append(transforms.RandomHorizontalFlip(p=0.5))
+    tf.append(transforms.ToTensor())
+    if config.data.dataset != "CIFAR10":
+        raise NotImplementedError(f"dataset {config.data.dataset!r}: the SalUn DDPM configs served here use CIFAR10")
+    dataset = CIFAR10(config.data.path, train=True, download=False, transform=transforms.Compose(tf))
+    remain = [d for d in dataset if d[1] != label_to_drop]
+    forget = [d for d in dataset if d[1] == label_to_drop]
+    bs, nw = config.training.batch_size, getattr(config.data, "num_workers", 0)
+    return (DataLoader(remain, batch_size=bs, shuffle=True, num_workers=nw),
+            DataLoader(forget, batch_size=bs, shuffle=True, num_workers=nw))
+
+
+def _cycle(loader):
+    while True:
+        for batch in loader:
+            yield batch
+
+
+class Diffusion:
+    """Mirror of the reference runner ``Diffusion(args, config)`` for the two SalUn modes that DDPM/train.py:150-155
+    dispatches to: ``generate_mask()`` (runners/diffusion.py:947-1039) and ``saliency_unlearn()`` (:485-620).
+
+    Same args (ckpt_folder, label_to_forget, cond_scale, mask_path, alpha, method, seed), same config keys
+    (data.*, model.*, diffusion.*, training.{batch_size,n_iters,snapshot_freq,log_freq}, optim.*), same files: the
+    checkpoint ``<ckpt_folder>/ckpts/ckpt.pth`` ([model_sd with ``module.`` keys, ...]) is read, the mask is written to
+    ``results/cifar10/mask/<label>/with_0.5.pt`` (CPU int64 dict, ``module.`` keys) and snapshots go to
+    ``<config.ckpt_dir>/ckpt.pth`` as [model_sd, optim_sd, step].  The U-Net runs on the sm_100a engine; sampling /
+    FID (sample_visualization, :598-619) is outside the hot path and is left to the reference's own sampler on the
+    saved checkpoint (``on_snapshot`` is called with (step, state_dict) for callers who want it inline).
+
+    ``loaders=(remain_loader, forget_loader)`` overrides get_forget_dataset (tests, synthetic data)."""
+
+    def __init__(self, args, config, device=None, loaders=None, on_snapshot=None):
+        self.args, self.config = args, config
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        d = config.diffusion
+        self.betas = torch.from_numpy(get_beta_schedule(d.beta_schedule, beta_start=d.beta_start, beta_end=d.beta_end,
+                                                        num_diffusion_timesteps=d.num_diffusion_timesteps)).float()
+        self.num_timesteps = self.betas.shape[0]
+        self.loaders, self.on_snapshot = loaders, on_snapshot
+
+    def _loaders(self):
+        if self.loaders is not None:
+            return self.loaders
+        return get_forget_dataset(self.args, self.config, self.args.label_to_forget)
+
+    def _engine(self, max_batch):
+        from .engine import UNetEngine
+        eng = UNetEngine(self.config, max_batch=max_batch, device=self.device)
+        path = os.path.join(self.args.ckpt_folder, "ckpts/ckpt.pth")
+        states = torch.load(path, map_location="cpu")
+        eng.load_state_dict(states[0], strict=True)           # DataParallel keys: the ``module.`` prefix is stripped
+        return eng
+
+    def generate_mask(self, threshold_list=(0.5,)):
+        args, config = self.args, self.config
+        _, forget_loader = self._loaders()
+        eng = self._engine(2 * config.training.batch_size)     # conditional + null pass as one batch
+        o = config.optim
+        un = DDPMEngineUnlearner(eng, self.betas, lr=o.lr, beta1=o.beta1, eps=o.eps, weight_decay=o.weight_decay,
+                                 grad_clip=o.grad_clip)
+        if getattr(args, "seed", None) is not None:
+            torch.manual_seed(args.seed)
+        for x, forget_c in forget_loader:
+            un.generate_mask_batch(x, forget_c, cond_scale=args.cond_scale)
+        mask_path = os.path.join("results/cifar10/mask", str(args.label_to_forget))     # :1003
+        infos = {}
+        for i in threshold_list:
+            infos[i] = un.finish_mask(os.path.join(mask_path, f"with_{str(i)}.pt"), ratio=i)
+        eng.close()
+        return infos
+
+    def saliency_unlearn(self):
+        args, config = self.args, self.config
+        remain_loader, forget_loader = self._loaders()
+        remain_iter, forget_iter = _cycle(remain_loader), _cycle(forget_loader)
+        mask = torch.load(args.mask_path) if getattr(args, "mask_path", None) else None   # :493-496
+        eng = self._engine(2 * config.training.batch_size)      # remain + forget mini-batch as one batch
+        o = config.optim
+        un = DDPMEngineUnlearner(eng, self.betas, lr=o.lr, beta1=o.beta1, eps=o.eps, weight_decay=o.weight_decay,
+                                 grad_clip=o.grad_clip, mask=mask)
+        if getattr(config.model, "ema", False):
+            raise NotImplementedError("model.ema=True: the SalUn unlearning config sets ema False (cifar10_saliency_unlearn.yml:23)")
+        if getattr(args, "seed", None) is not None:
+            torch.manual_seed(args.seed)
+        import logging
+        import time
+        start = time.time()
+        loss = None
+        for step in range(config.training.n_iters):
+            remain_x, remain_c = next(remain_iter)
+            forget_x, forget_c = next(forget_iter)
+            loss = un.saliency_unlearn_step(remain_x, remain_c, forget_x, forget_c, alpha=args.alpha, method=args.method,
+                                            n_classes=config.data.n_classes)
+            if (step + 1) % config.training.log_freq == 0:
+                logging.info(f"step: {step}, loss: {loss.item()}, time: {time.time() - start}")
+                start = time.time()
+            if (step + 1) % config.training.snapshot_freq == 0:
+                un.save_checkpoint(os.path.join(config.ckpt_dir, "ckpt.pth"), step)
+                if self.on_snapshot is not None:
+                    self.on_snapshot(step, eng.state_dict(prefix="module."))
+        eng.close()
+        return None if loss is None else float(loss)
