@@ -417,21 +417,6 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         tc_wait_ld();
         const int col0 = n_tile * BN + c * 32;
         if (col0 < a.N) {
-          if (a.stat_sum) {
-            float v[32], w[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = row_ok ? __uint_as_float(r[j]) : 0.f;
-              v[j] = x;
-              w[j] = x * x;
-            }
-            float s1 = warp_transpose_reduce(v, lane);
-            float s2 = warp_transpose_reduce(w, lane);
-            if (col0 + lane < a.N) {
-              a.stat_sum[(size_t)stat_row * a.N + col0 + lane] = s1;
-              a.stat_sq[(size_t)stat_row * a.N + col0 + lane] = s2;
-            }
-          }
           if (a.bias) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -464,6 +449,21 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 r[8 * j + 2 * i] = __float_as_uint(__uint_as_float(r[8 * j + 2 * i]) + t.x);
                 r[8 * j + 2 * i + 1] = __float_as_uint(__uint_as_float(r[8 * j + 2 * i + 1]) + t.y);
               }
+            }
+          }
+          if (a.stat_sum) {  // column partials of the FINAL value (after bias / projection / residual)
+            float v[32], w[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = row_ok ? __uint_as_float(r[j]) : 0.f;
+              v[j] = x;
+              w[j] = x * x;
+            }
+            float s1 = warp_transpose_reduce(v, lane);
+            float s2 = warp_transpose_reduce(w, lane);
+            if (col0 + lane < a.N) {
+              a.stat_sum[(size_t)stat_row * a.N + col0 + lane] = s1;
+              a.stat_sq[(size_t)stat_row * a.N + col0 + lane] = s2;
             }
           }
           if (a.f1.act) {
@@ -641,21 +641,6 @@ k_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
         tc_wait_ld();
         const int col0 = n_tile * BN + c * 32;
         if (col0 < a.N) {
-          if (a.stat_sum) {
-            float v[32], w[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = row_ok ? __uint_as_float(r[j]) : 0.f;
-              v[j] = x;
-              w[j] = x * x;
-            }
-            float s1 = warp_transpose_reduce(v, lane);
-            float s2 = warp_transpose_reduce(w, lane);
-            if (col0 + lane < a.N) {
-              a.stat_sum[(size_t)stat_row * a.N + col0 + lane] = s1;
-              a.stat_sq[(size_t)stat_row * a.N + col0 + lane] = s2;
-            }
-          }
           if (a.bias) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -688,6 +673,21 @@ k_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                 r[8 * j + 2 * i] = __float_as_uint(__uint_as_float(r[8 * j + 2 * i]) + t.x);
                 r[8 * j + 2 * i + 1] = __float_as_uint(__uint_as_float(r[8 * j + 2 * i + 1]) + t.y);
               }
+            }
+          }
+          if (a.stat_sum) {
+            float v[32], w[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = row_ok ? __uint_as_float(r[j]) : 0.f;
+              v[j] = x;
+              w[j] = x * x;
+            }
+            float s1 = warp_transpose_reduce(v, lane);
+            float s2 = warp_transpose_reduce(w, lane);
+            if (col0 + lane < a.N) {
+              a.stat_sum[(size_t)stat_row * a.N + col0 + lane] = s1;
+              a.stat_sq[(size_t)stat_row * a.N + col0 + lane] = s2;
             }
           }
           if (row_ok) {

@@ -43,6 +43,8 @@ struct UTensor {
   bool need_g;
   bf16 *v, *g;
   bool g_live;         // backward: the gradient buffer already holds a contribution
+  bool want_stats;     // a GroupNorm reads this tensor (directly or through a concat): its producer's GEMM epilogue
+  float *st_sum, *st_sq;  // emits the per-(32-row group) column sums [nb*H*H/32][C] the GroupNorm statistics need
 };
 enum ConvKind { CK_S1 = 0, CK_IN = 1, CK_DOWN = 2, CK_OUT = 3 };
 struct UConv {
@@ -417,6 +419,21 @@ static int build_arch(salun_unet *net) {
   const int an = B.add_tensor("norm_out", c_last, S, false, true);
   B.add_gn(h, an, c_last, S, 1, 0, no_w, no_b);
   B.add_conv(CK_OUT, c_last, 3, 3, S, co_w, co_b, an, -1);
+  // GroupNorm statistics out of the producers' epilogues: walk the tape backwards so that a concat that feeds a
+  // GroupNorm marks its two sources (32-row groups must not straddle samples: H*H >= 32)
+  {
+    const char *e = getenv("SALUN_UNET_EPILOGUE_STATS");
+    const bool on = e ? atoi(e) != 0 : true;
+    for (int oi = (int)net->ops.size() - 1; on && oi >= 0; --oi) {
+      const UOp &op = net->ops[oi];
+      if (op.type == OP_GN) {
+        UTensor &t = net->ts[net->gns[op.idx].in];
+        if (t.H * t.H >= 32) t.want_stats = true;
+      } else if (op.type == OP_CONCAT && net->ts[op.c].want_stats) {
+        net->ts[op.a].want_stats = net->ts[op.b].want_stats = true;
+      }
+    }
+  }
   return SALUN_OK;
 }
 
@@ -590,6 +607,10 @@ static int conv_forward(salun_unet *net, const UConv &L, const UConvMaps &m, int
       a.rb_shift = ilog2(L.H * L.H);
     }
     if (L.addend >= 0) a.addend = net->ts[L.addend].v;  // same layout / width as the output
+    if (o.want_stats) {
+      a.stat_sum = o.st_sum;
+      a.stat_sq = o.st_sq;
+    }
   }
   a.pair = m.pair_fwd;
   TRY(launch_conv_gemm(m.fwdA, m.fwdB, a, u_pick_bn(L.cout_p, M), st));
@@ -668,13 +689,17 @@ static int forward_impl(salun_unet *net, const float *x, int n, int train, bool 
       case OP_GN: {
         const UGn &g = net->gns[op.idx];
         const UTensor &in = net->ts[g.in], &out = net->ts[g.out];
-        launch_gn_forward(in.v, net->gn_partial, g.stats, net->params + g.g_off, net->params + g.b_off, out.v,
+        launch_gn_forward(in.v, in.want_stats ? in.st_sum : nullptr, in.st_sq, net->gn_partial, g.stats,
+                          net->params + g.g_off, net->params + g.b_off, out.v,
                           out.vflat ? 1 : 0, g.swish, g.dropout ? drop_p : 0.f, gn_seed(net, g), n, g.H, g.C, 1e-6f, st);
         break;
       }
       case OP_CONCAT: {
         const UTensor &a = net->ts[op.a], &b = net->ts[op.b], &o = net->ts[op.c];
         launch_concat(a.v, a.C, b.v, b.C, o.v, n, o.H, st);
+        if (o.want_stats)
+          launch_concat_stats(a.st_sum, a.st_sq, a.C, b.st_sum, b.st_sq, b.C, o.st_sum, o.st_sq,
+                              (long long)n * o.H * o.H / 32, st);
         break;
       }
       case OP_UP: {
@@ -994,6 +1019,11 @@ int salun_unet_create(salun_ctx *ctx, const salun_unet_cfg *cfg, float *params, 
   for (UTensor &t : net->ts) {
     A(dmalloc(net, &t.v, tensor_elems(net, t, t.vflat)));
     if (t.need_g) A(dmalloc(net, &t.g, tensor_elems(net, t, t.gflat)));
+    if (t.want_stats) {
+      const size_t rows = ((size_t)nb * t.H * t.H + 127) / 128 * 4;
+      A(dmalloc(net, &t.st_sum, rows * t.C));
+      A(dmalloc(net, &t.st_sq, rows * t.C));
+    }
   }
   for (UGn &g : net->gns) {
     A(dmalloc(net, &g.stats, (size_t)nb * kGnGroups * 2));

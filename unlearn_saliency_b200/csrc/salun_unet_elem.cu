@@ -149,16 +149,18 @@ __global__ void __launch_bounds__(kT) k_gn_stats(const bf16 *__restrict__ x, flo
   }
   slice_reduce_store<2>(acc, v, r, rl, active, C, partial + ((size_t)n * S + s) * 2 * C);
 }
-// group statistics of sample n from the slice partials [S][2][C] (every CTA of the sample redoes this tiny reduction
-// instead of a separate finalize launch); fp64 for the variance
-__device__ __forceinline__ void gn_group_stats(const float *__restrict__ partial_n, int C, int S, float count, float eps,
-                                               float (*sh_stat)[2], float *sh_a, float *sh_b) {
+// group statistics of one sample from R rows of per-channel partial sums (sum x at psum[q*ld + c], sum x^2 at
+// psq[q*ld + c]): the slice partials of k_gn_stats, or the per-(32-row group) column partials a producing GEMM's epilogue
+// wrote.  Every CTA of the sample redoes this tiny reduction instead of a separate finalize launch; fp64 for the variance.
+__device__ __forceinline__ void gn_group_stats(const float *__restrict__ psum, const float *__restrict__ psq, long long ld,
+                                               int R, int C, float count, float eps, float (*sh_stat)[2], float *sh_a,
+                                               float *sh_b) {
   const int cpg = C / kGnGroups;
   for (int c = threadIdx.x; c < C; c += kT) {
     float s1 = 0.f, s2 = 0.f;
-    for (int q = 0; q < S; ++q) {
-      s1 += partial_n[(size_t)q * 2 * C + c];
-      s2 += partial_n[(size_t)q * 2 * C + C + c];
+    for (int q = 0; q < R; ++q) {
+      s1 += psum[(size_t)q * ld + c];
+      s2 += psq[(size_t)q * ld + c];
     }
     sh_a[c] = s1;
     sh_b[c] = s2;
@@ -178,14 +180,15 @@ __device__ __forceinline__ void gn_group_stats(const float *__restrict__ partial
   }
   __syncthreads();
 }
-__global__ void __launch_bounds__(kT) k_gn_apply(const bf16 *__restrict__ x, const float *__restrict__ partial,
+__global__ void __launch_bounds__(kT) k_gn_apply(const bf16 *__restrict__ x, const float *__restrict__ psum,
+                                                 const float *__restrict__ psq, long long pld, int R,
                                                  float *__restrict__ stats, const float *__restrict__ gamma,
                                                  const float *__restrict__ beta, bf16 *__restrict__ out, int out_flat,
                                                  int swish, uint32_t drop_thr, float inv_keep, uint32_t seed, int H,
                                                  int C, int S, float count, float eps) {
   __shared__ float sh_stat[kGnGroups][2], sh_a[512], sh_b[512];
   const int n = blockIdx.y, s = blockIdx.x;
-  gn_group_stats(partial + (size_t)n * S * 2 * C, C, S, count, eps, sh_stat, sh_a, sh_b);
+  gn_group_stats(psum + (size_t)n * R * pld, psq + (size_t)n * R * pld, pld, R, C, count, eps, sh_stat, sh_a, sh_b);
   if (s == 0 && threadIdx.x < kGnGroups) {  // kept for the backward pass
     stats[((size_t)n * kGnGroups + threadIdx.x) * 2 + 0] = sh_stat[threadIdx.x][0];
     stats[((size_t)n * kGnGroups + threadIdx.x) * 2 + 1] = sh_stat[threadIdx.x][1];
@@ -237,15 +240,50 @@ static inline uint32_t drop_threshold(float p) {
   if (t < 1.0) t = 1.0;
   return (uint32_t)t;
 }
-void launch_gn_forward(const bf16 *x_pad, float *partial, float *stats, const float *gamma, const float *beta, bf16 *out,
-                       int out_flat, int swish, float drop_p, uint32_t drop_seed, int n, int H, int C, float eps,
-                       cudaStream_t st) {
+void launch_gn_forward(const bf16 *x_pad, const float *ep_sum, const float *ep_sq, float *partial, float *stats,
+                       const float *gamma, const float *beta, bf16 *out, int out_flat, int swish, float drop_p,
+                       uint32_t drop_seed, int n, int H, int C, float eps, cudaStream_t st) {
   const int S = slices_for(H, n);
-  k_gn_stats<<<dim3(S, n), kT, 0, st>>>(x_pad, partial, H, C, S);
-  k_gn_apply<<<dim3(S, n), kT, 0, st>>>(x_pad, partial, stats, gamma, beta, out, out_flat, swish, drop_threshold(drop_p),
-                                        drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f, drop_seed, H, C, S,
-                                        (float)(C / kGnGroups) * H * H, eps);
-  g_launch_count += 2;
+  const float *psum, *psq;
+  long long pld;
+  int R;
+  if (ep_sum) {  // the producer's GEMM epilogue already reduced 32-row groups: H*H/32 partial rows per sample
+    psum = ep_sum;
+    psq = ep_sq;
+    pld = C;
+    R = H * H / 32;
+  } else {
+    k_gn_stats<<<dim3(S, n), kT, 0, st>>>(x_pad, partial, H, C, S);
+    ++g_launch_count;
+    psum = partial;
+    psq = partial + C;
+    pld = 2LL * C;
+    R = S;
+  }
+  k_gn_apply<<<dim3(S, n), kT, 0, st>>>(x_pad, psum, psq, pld, R, stats, gamma, beta, out, out_flat, swish,
+                                        drop_threshold(drop_p), drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f, drop_seed, H, C,
+                                        S, (float)(C / kGnGroups) * H * H, eps);
+  ++g_launch_count;
+}
+// cat_stat[r][0:Ca] = a_stat[r][:], cat_stat[r][Ca:] = b_stat[r][:]  (both planes) for r < rows
+__global__ void k_concat_stats(const float *__restrict__ a1, const float *__restrict__ a2, int Ca,
+                               const float *__restrict__ b1, const float *__restrict__ b2, int Cb, float *__restrict__ o1,
+                               float *__restrict__ o2, long long total) {
+  const int C = Ca + Cb;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C;
+    const int c = (int)(i - r * C);
+    o1[i] = c < Ca ? a1[r * Ca + c] : b1[r * Cb + (c - Ca)];
+    o2[i] = c < Ca ? a2[r * Ca + c] : b2[r * Cb + (c - Ca)];
+  }
+}
+void launch_concat_stats(const float *a_sum, const float *a_sq, int Ca, const float *b_sum, const float *b_sq, int Cb,
+                         float *o_sum, float *o_sq, long long rows, cudaStream_t st) {
+  const long long total = rows * (Ca + Cb);
+  long long g = (total + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  k_concat_stats<<<(int)g, 256, 0, st>>>(a_sum, a_sq, Ca, b_sum, b_sq, Cb, o_sum, o_sq, total);
+  ++g_launch_count;
 }
 
 // =================================================================================================================

@@ -20,9 +20,14 @@ int unet_slices(int H);
 
 // ---- GroupNorm forward: partial[n][S][2][C] (sum x, sum x^2 per slice) -> stats[n][32][2] (mean, rstd; kept for the
 // backward pass) -> out = dropout(act(gamma * (x - mean) * rstd + beta)); act = swish or identity; out padded or flat ----
-void launch_gn_forward(const __nv_bfloat16 *x_pad, float *partial, float *stats, const float *gamma, const float *beta,
-                       __nv_bfloat16 *out, int out_flat, int swish, float drop_p, uint32_t drop_seed, int n, int H, int C,
-                       float eps, cudaStream_t st);
+// ep_sum / ep_sq (optional): per-(32-row group) column partials [n*H*H/32][C] of x that the producing GEMM's epilogue
+// wrote (ConvGemmArgs::stat_sum / stat_sq) -- the statistics pass over x is then skipped.
+void launch_gn_forward(const __nv_bfloat16 *x_pad, const float *ep_sum, const float *ep_sq, float *partial, float *stats,
+                       const float *gamma, const float *beta, __nv_bfloat16 *out, int out_flat, int swish, float drop_p,
+                       uint32_t drop_seed, int n, int H, int C, float eps, cudaStream_t st);
+// epilogue partials of a skip concatenation: row r of the result = [row r of a | row r of b]
+void launch_concat_stats(const float *a_sum, const float *a_sq, int Ca, const float *b_sum, const float *b_sq, int Cb,
+                         float *o_sum, float *o_sq, long long rows, cudaStream_t st);
 // ---- GroupNorm backward.  dout: gradient w.r.t. the GN(+swish+dropout) output, FLAT [n*H*H][C] ----
 //   partial[n][S][2][C] = per-sample, per-slice sums over pixels of dyh and dyh * xhat (dyh = dout * act'(yh) * dropmask)
 //   persample[n][2][C]  = the same summed over the slices; the caller sums it over n into dbeta / dgamma (SumEntry)
