@@ -191,12 +191,13 @@ def bench_ddpm(args, dev, rank, world, L, timed, tf_peak, peak_src):
         it_e2e(i)
     ms_e2e = timed(it_e2e, steps) / steps
     roof = None
+    # instrumented replay on EVERY rank (the iteration contains the gradient all-reduce); rank 0 reports
+    L.salun_profile_begin()
+    for i in range(min(steps, 3)):
+        it_resident(i)
+    pm, pc, pf = (C.c_double * 2)(), (C.c_int64 * 2)(), (C.c_double * 2)()
+    L.salun_profile_end(pm, pc, pf)
     if rank == 0:
-        L.salun_profile_begin()
-        for i in range(min(steps, 3)):
-            it_resident(i)
-        pm, pc, pf = (C.c_double * 2)(), (C.c_int64 * 2)(), (C.c_double * 2)()
-        L.salun_profile_end(pm, pc, pf)
         k = min(steps, 3)
         ach = [pf[c] / (pm[c] * 1e-3) / 1e12 if pm[c] > 0 else 0.0 for c in range(2)]
         roof = {"bound": "tensor", "kernel": "k_conv_gemm_p / k_gemm2 (conv forward + dgrad, attention and projection GEMMs)",
@@ -279,7 +280,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a mismatched collective must fail within minutes, not after the default 10-minute watchdog
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     L = _lib.lib()
 
     fused_dp = world > 1 and os.environ.get("SALUN_FUSED_DP", "1") != "0"
