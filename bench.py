@@ -146,7 +146,13 @@ def bench_ddpm(args, dev, rank, world, L, timed, tf_peak, peak_src):
     from unlearn_saliency_b200.diffusion.runner import DDPMEngineUnlearner, get_beta_schedule
     from unlearn_saliency_b200.diffusion.unet import cifar10_config
     cfg = cifar10_config()
-    eng = UNetEngine(cfg, max_batch=2 * DDPM_BATCH, device=dev)
+    fused_dp = world > 1 and os.environ.get("SALUN_FUSED_DP", "1") != "0"
+    try:
+        eng = UNetEngine(cfg, max_batch=2 * DDPM_BATCH, device=dev, symmetric=fused_dp)
+    except Exception as e:  # symmetric memory unavailable: NCCL all-reduce + local clip / mask / Adam (same arithmetic)
+        print(f"[bench] symmetric memory unavailable for the DDPM arenas ({e!r}); using NCCL all-reduce", file=sys.stderr)
+        fused_dp = False
+        eng = UNetEngine(cfg, max_batch=2 * DDPM_BATCH, device=dev)
     g = torch.Generator(device="cpu").manual_seed(0)  # same random-init weights on every rank
     sd = {}
     for k, shp in eng.shapes.items():
@@ -212,7 +218,10 @@ def bench_ddpm(args, dev, rank, world, L, timed, tf_peak, peak_src):
            "config": {"workload": "DDPM U-Net CIFAR-10 32x32 saliency_unlearn iteration (runners/diffusion.py:519-593), "
                                   "method rl, alpha 1e-3, dropout 0.1, cond_drop 0.1, mask ratio 0.5, clip 1.0, Adam 1e-4",
                       "per_gpu_batch": [B, B], "params": eng.n,
-                      "collective": "NCCL all-reduce of the flat gradient (before the clip)" if world > 1 else "none"},
+                      "collective": ("none" if world == 1 else
+                                     "fused reduce-scatter + global-norm clip + mask + Adam + all-gather over NVLink peer memory "
+                                     "(two kernels around one barrier, optimizer state sharded)" if un.fused_dp else
+                                     "NCCL all-reduce of the flat gradient (before the clip)")},
            "gpu_launches": int(launches), "launches_per_it": launches / steps,
            "e2e": {"value": world * 1000.0 / ms_e2e, "unit": "iterations/s", "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": 4, "ms_per_it": ms_e2e},

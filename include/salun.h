@@ -142,6 +142,27 @@ int salun_dp_masked_sgd_step(salun_ctx *ctx, float *const *param_peers_host, con
                              float *v_shard, const uint32_t *mask_bits, int64_t n, int rank, int world, float lr,
                              float momentum, float wd, void *stream);
 
+/* Data-parallel form of clip + mask + Adam (DDPM/runners/diffusion.py:582-593 under DDP-averaged gradients), two
+ * kernels over NVLink peer memory around ONE cross-rank barrier, instead of all-reduce + grad_sumsq + clip_coef +
+ * masked_adam_step.  The clip needs the norm of the AVERAGED gradient before masking, so:
+ *   salun_dp_grad_reduce_sumsq : g_shard[i - lo] = (sum_r grad_peers[r][i]) / world for the shard [lo, hi) =
+ *                                salun_dp_shard(n, rank, world) (peer loads, fixed order); norm_slot[0] = sum g_shard^2
+ *                                (double).  norm_slot must live in memory every peer can read (symmetric memory).
+ *   -- cross-rank barrier on the stream (all norm slots written) --
+ *   salun_dp_masked_adam_step  : coef = min(1, max_norm / (sqrt(sum_r *norm_peers[r]) + 1e-6)) (max_norm <= 0: no clip);
+ *                                Adam exactly as salun_masked_adam_step on p[lo:hi) with g_shard and the shard-sized
+ *                                moments m1_shard / m2_shard (zero-initialised); the new weights are stored into
+ *                                param_peers[r] for every r (peer stores).  coef_norm_dev (optional, 2 floats): the clip
+ *                                coefficient and the pre-clip global gradient norm.
+ *   -- cross-rank barrier (all weights delivered) --
+ * Optimizer state exists only for the owned shard (1/world of the arena per GPU). */
+int salun_dp_grad_reduce_sumsq(salun_ctx *ctx, const float *const *grad_peers_host, float *g_shard, double *norm_slot,
+                               int64_t n, int rank, int world, void *stream);
+int salun_dp_masked_adam_step(salun_ctx *ctx, float *const *param_peers_host, const double *const *norm_peers_host,
+                              const float *g_shard, float *m1_shard, float *m2_shard, const uint32_t *mask_bits, int64_t n,
+                              int rank, int world, float lr, float beta1, float beta2, float eps, float wd, int64_t step,
+                              float max_norm, float *coef_norm_dev, void *stream);
+
 /* sumsq_dev[0] = sum_i g[i]^2 in double (deterministic two-stage reduction).
  * replaces the norm inside clip_grad_norm_   DDPM/runners/diffusion.py:582-587,985-990 */
 int salun_grad_sumsq(salun_ctx *ctx, const float *g, int64_t n, double *sumsq_dev, void *stream);

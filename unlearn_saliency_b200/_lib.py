@@ -55,6 +55,9 @@ _SIGNATURES = {
     "salun_masked_sgd_step": [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _P],
     "salun_dp_shard": [_I64, C.c_int, C.c_int, C.POINTER(_I64), C.POINTER(_I64)],
     "salun_dp_masked_sgd_step": [_P, C.POINTER(_P), C.POINTER(_P), _P, _P, _I64, C.c_int, C.c_int, _F, _F, _F, _P],
+    "salun_dp_grad_reduce_sumsq": [_P, C.POINTER(_P), _P, _P, _I64, C.c_int, C.c_int, _P],
+    "salun_dp_masked_adam_step": [_P, C.POINTER(_P), C.POINTER(_P), _P, _P, _P, _P, _I64, C.c_int, C.c_int, _F, _F, _F, _F,
+                                  _F, _I64, _F, _P, _P],
     "salun_grad_sumsq": [_P, _P, _I64, _P, _P],
     "salun_clip_coef": [_P, _P, _F, _P, _P],
     "salun_masked_adam_step": [_P, _P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I64, _P, _P],

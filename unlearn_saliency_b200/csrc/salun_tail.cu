@@ -515,6 +515,75 @@ __global__ void __launch_bounds__(kThreads) k_masked_adam(float *__restrict__ p,
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// data-parallel clip + mask + Adam over NVLink peer memory (ZeRO-1 style, SURVEY.md section 7.3 option (a)):
+//   phase 1 (k_dp_reduce_sumsq): g_shard = sum_r grad_r[lo:hi] (peer loads, rank order) ; per-CTA partials of sum g_shard^2
+//   phase 2 (k_dp_masked_adam) : total = sum_r norm_slot_r (every rank's shard norm, peer loads, rank order) ->
+//                                clip coefficient -> mask (.) Adam on the shard -> new weights stored into every replica
+// ------------------------------------------------------------------------------------------
+struct PeerG {
+  const float *g[kMaxPeers];
+};
+__global__ void __launch_bounds__(kThreads) k_dp_reduce_sumsq(PeerG peers, int world, float *__restrict__ g_shard,
+                                                              int64_t lo, int64_t hi, float inv_world,
+                                                              double *__restrict__ partials) {
+  __shared__ double sh[kThreads / 32];
+  double s = 0.0;
+  int64_t stride = (int64_t)gridDim.x * kThreads * 4;
+  for (int64_t i = lo + ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4; i < hi; i += stride) {
+    float4 gg = load4(peers.g[0], i, hi, 0.f);
+    for (int r = 1; r < world; ++r) {
+      const float4 t = load4(peers.g[r], i, hi, 0.f);
+      gg.x = __fadd_rn(gg.x, t.x); gg.y = __fadd_rn(gg.y, t.y); gg.z = __fadd_rn(gg.z, t.z); gg.w = __fadd_rn(gg.w, t.w);
+    }
+    gg.x = __fmul_rn(gg.x, inv_world); gg.y = __fmul_rn(gg.y, inv_world);
+    gg.z = __fmul_rn(gg.z, inv_world); gg.w = __fmul_rn(gg.w, inv_world);
+    store4(g_shard, i - lo, hi - lo, gg);
+    s += (double)gg.x * gg.x + (double)gg.y * gg.y + (double)gg.z * gg.z + (double)gg.w * gg.w;
+  }
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) t += sh[w];
+    partials[blockIdx.x] = t;
+  }
+}
+struct PeerAdam {
+  float *p[kMaxPeers];
+  const double *norm[kMaxPeers];  // every rank's slot holding its shard's sum of squares
+};
+__global__ void __launch_bounds__(kThreads) k_dp_masked_adam(PeerAdam peers, int world, const float *__restrict__ g_shard,
+                                                             float *__restrict__ m1, float *__restrict__ m2,
+                                                             const uint32_t *__restrict__ bits, int64_t lo, int64_t hi,
+                                                             AdamK k, float max_norm, float *__restrict__ coef_out) {
+  float coef = 1.0f;
+  if (max_norm > 0.f) {  // the same scalar arithmetic on every thread of every rank: identical replicas
+    double tot = 0.0;
+    for (int r = 0; r < world; ++r) tot += *peers.norm[r];
+    const float c = __fdiv_rn(max_norm, __fadd_rn((float)sqrt(tot), 1e-6f));
+    coef = c > 1.0f ? 1.0f : c;
+    if (coef_out && blockIdx.x == 0 && threadIdx.x == 0) {
+      coef_out[0] = coef;
+      coef_out[1] = (float)sqrt(tot);
+    }
+  }
+  int64_t stride = (int64_t)gridDim.x * kThreads * 4;
+  for (int64_t i = lo + ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4; i < hi; i += stride) {
+    const uint32_t nib = mask_nibble(bits, i);
+    float4 pp = load4(peers.p[0], i, hi, 0.f), gg = load4(g_shard, i - lo, hi - lo, 0.f);
+    float4 aa = load4(m1, i - lo, hi - lo, 0.f), bb = load4(m2, i - lo, hi - lo, 0.f);
+    adam1(pp.x, gg.x, aa.x, bb.x, nib & 1u, coef, k);
+    adam1(pp.y, gg.y, aa.y, bb.y, nib & 2u, coef, k);
+    adam1(pp.z, gg.z, aa.z, bb.z, nib & 4u, coef, k);
+    adam1(pp.w, gg.w, aa.w, bb.w, nib & 8u, coef, k);
+    store4(m1, i - lo, hi - lo, aa);
+    store4(m2, i - lo, hi - lo, bb);
+    for (int r = 0; r < world; ++r) store4(peers.p[r], i, hi, pp);
+  }
+}
+
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace salun
@@ -765,6 +834,65 @@ int salun_dp_masked_sgd_step(salun_ctx *ctx, float *const *param_peers_host, con
   SALUN_REQUIRE(aligned16(v_shard), "v_shard must be 16-byte aligned");
   k_dp_masked_sgd<<<grid_for(ctx, (hi - lo + 3) / 4), kThreads, 0, st>>>(pp, world, v_shard, mask_bits, lo, hi, lr,
                                                                           momentum, wd, 1.0f / (float)world);
+  ++::salun::g_launch_count;
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+
+int salun_dp_grad_reduce_sumsq(salun_ctx *ctx, const float *const *grad_peers_host, float *g_shard, double *norm_slot,
+                               int64_t n, int rank, int world, void *stream) {
+  SALUN_ENTER(ctx);
+  SALUN_REQUIRE(grad_peers_host && g_shard && norm_slot, "NULL argument");
+  SALUN_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "world must be 1..8");
+  int64_t lo, hi;
+  salun_dp_shard(n, rank, world, &lo, &hi);
+  PeerG pg;
+  for (int r = 0; r < world; ++r) {
+    SALUN_REQUIRE(grad_peers_host[r] && aligned16(grad_peers_host[r]), "peer gradient arenas must be non-NULL and 16-byte aligned");
+    pg.g[r] = grad_peers_host[r];  // summed in rank order on every rank
+  }
+  SALUN_REQUIRE(aligned16(g_shard), "g_shard must be 16-byte aligned");
+  int grid = hi > lo ? grid_for(ctx, (hi - lo + 3) / 4) : 1;
+  k_dp_reduce_sumsq<<<grid, kThreads, 0, st>>>(pg, world, g_shard, lo, hi > lo ? hi : lo, 1.0f / (float)world,
+                                               ctx->partials);
+  k_sumsq_final<<<1, 256, 0, st>>>(ctx->partials, grid, norm_slot);
+  ::salun::g_launch_count += 2;
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+
+int salun_dp_masked_adam_step(salun_ctx *ctx, float *const *param_peers_host, const double *const *norm_peers_host,
+                              const float *g_shard, float *m1_shard, float *m2_shard, const uint32_t *mask_bits, int64_t n,
+                              int rank, int world, float lr, float beta1, float beta2, float eps, float wd, int64_t step,
+                              float max_norm, float *coef_norm_dev, void *stream) {
+  SALUN_ENTER(ctx);
+  SALUN_REQUIRE(param_peers_host && norm_peers_host && g_shard && m1_shard && m2_shard, "NULL argument");
+  SALUN_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "world must be 1..8");
+  SALUN_REQUIRE(step >= 1, "step < 1");
+  int64_t lo, hi;
+  salun_dp_shard(n, rank, world, &lo, &hi);
+  if (hi <= lo) return SALUN_OK;
+  PeerAdam pa;
+  for (int r = 0; r < world; ++r) {
+    const int src = (rank + r) % world;  // local replica first: it is the one whose weights are read
+    SALUN_REQUIRE(param_peers_host[src] && aligned16(param_peers_host[src]), "peer parameter arenas must be non-NULL and 16-byte aligned");
+    pa.p[r] = param_peers_host[src];
+    SALUN_REQUIRE(norm_peers_host[r], "NULL peer norm slot");
+    pa.norm[r] = norm_peers_host[r];  // rank order
+  }
+  SALUN_REQUIRE(aligned16(g_shard) && aligned16(m1_shard) && aligned16(m2_shard), "shard buffers must be 16-byte aligned");
+  AdamK k;
+  double bc1 = 1.0 - pow((double)beta1, (double)step);
+  double bc2 = 1.0 - pow((double)beta2, (double)step);
+  k.lr_step = (float)((double)lr / bc1);
+  k.bc2_sqrt = (float)sqrt(bc2);
+  k.b2 = beta2;
+  k.one_m_b1 = (float)(1.0 - (double)beta1);
+  k.one_m_b2 = (float)(1.0 - (double)beta2);
+  k.eps = eps;
+  k.wd = wd;
+  k_dp_masked_adam<<<grid_for(ctx, (hi - lo + 3) / 4), kThreads, 0, st>>>(pa, world, g_shard, m1_shard, m2_shard, mask_bits,
+                                                                           lo, hi, k, max_norm, coef_norm_dev);
   ++::salun::g_launch_count;
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;

@@ -59,7 +59,10 @@ class UNetEngine:
 
     native_layout = True  # conv weights are stored OHWI in the arena (flat.FlatSaliency converts before the top-k)
 
-    def __init__(self, config, max_batch: int = 256, device=None, ctx: Optional[SalunContext] = None):
+    def __init__(self, config, max_batch: int = 256, device=None, ctx: Optional[SalunContext] = None,
+                 symmetric: bool = False):
+        """symmetric=True allocates the parameter / gradient arenas as torch symmetric memory (NVLink peer-mapped), which
+        DistMaskedAdam needs for its fused reduce-scatter + clip + mask + Adam + all-gather kernels."""
         m, d = config.model, config.data
         if not m.resamp_with_conv:
             raise NotImplementedError("resamp_with_conv=False is not used by the SalUn configs")
@@ -86,8 +89,16 @@ class UNetEngine:
             self.offsets[k] = off
             off += math.prod(s)
         dev = self.device
-        self.params = torch.zeros(self.n, device=dev)
-        self.grads = torch.zeros(self.n, device=dev)
+        self.symmetric = bool(symmetric)
+        if symmetric:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.params = symm_mem.empty(self.n, dtype=torch.float32, device=dev)
+            self.grads = symm_mem.empty(self.n, dtype=torch.float32, device=dev)
+            self.params.zero_()
+            self.grads.zero_()
+        else:
+            self.params = torch.zeros(self.n, device=dev)
+            self.grads = torch.zeros(self.n, device=dev)
         h = C.c_void_p()
         check(self._lib.salun_unet_create(self.ctx.handle, C.byref(self.cfg), _ptr(self.params), _ptr(self.grads),
                                           C.byref(h)), "salun_unet_create")
@@ -231,3 +242,82 @@ class UNetEngine:
         out = torch.empty(n, cc, hh, hh, device=self.device)
         check(self._lib.salun_unet_export_tensor(self._h, i, 1 if grad else 0, _ptr(out), _stream(self.device)), "export")
         return out
+
+
+class DistMaskedAdam:
+    """Data-parallel clip + mask + Adam (runners/diffusion.py:582-593 under DDP-averaged gradients) as two kernels over
+    NVLink peer memory (salun_dp_grad_reduce_sumsq -> barrier -> salun_dp_masked_adam_step): each rank sums its 1/W shard
+    of every peer's gradient arena, the W shard norms give the global pre-clip norm, the shard is updated (Adam moments
+    exist only for the shard: ZeRO-1) and the new weights are stored into every replica.  Replaces NCCL all-reduce +
+    grad_sumsq + clip_coef + masked_adam_step.  The engine must have been created with symmetric=True."""
+
+    def __init__(self, engine: UNetEngine, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, mask=None,
+                 max_norm: Optional[float] = None, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        if not engine.symmetric:
+            raise ValueError("DistMaskedAdam needs UNetEngine(symmetric=True)")
+        self.flat = self.engine = engine
+        self.ctx = engine.ctx
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.lr, self.betas, self.eps, self.wd, self.max_norm = lr, betas, eps, weight_decay, max_norm
+        self.step_count = 0
+        self.mask_bits = None
+        if mask is not None:
+            self.mask_bits = self.ctx.pack_mask(engine.flat_from_dict(mask, dtype=torch.int64).contiguous())
+        lib = engine._lib
+        lo, hi = C.c_int64(), C.c_int64()
+        check(lib.salun_dp_shard(engine.n, self.rank, self.world, C.byref(lo), C.byref(hi)), "salun_dp_shard")
+        self.lo, self.hi = lo.value, hi.value
+        m = max(4, self.hi - self.lo)
+        dev = engine.device
+        self.g_shard = torch.zeros(m, device=dev)
+        self.exp_avg = torch.zeros(m, device=dev)        # shard only
+        self.exp_avg_sq = torch.zeros(m, device=dev)
+        self._norm = symm_mem.empty(2, dtype=torch.float64, device=dev)   # slot 0: this rank's shard sum of squares
+        self._norm.zero_()
+        self._coef_norm = torch.zeros(2, device=dev)
+        self._hp = symm_mem.rendezvous(engine.params, self.group)
+        self._hg = symm_mem.rendezvous(engine.grads, self.group)
+        self._hn = symm_mem.rendezvous(self._norm, self.group)
+        W = self.world
+        self._pp = (C.c_void_p * W)(*[int(p) for p in self._hp.buffer_ptrs])
+        self._gp = (C.c_void_p * W)(*[int(p) for p in self._hg.buffer_ptrs])
+        self._np = (C.c_void_p * W)(*[int(p) for p in self._hn.buffer_ptrs])
+
+    def zero_grad(self):
+        pass
+
+    def grad_norm(self) -> torch.Tensor:
+        """pre-clip global norm of the averaged gradient (device scalar), as returned by clip_grad_norm_"""
+        return self._coef_norm[1]
+
+    def gather_state(self):
+        """(exp_avg, exp_avg_sq) as full arena-layout tensors on every rank (checkpoints): all-gather of the shards"""
+        import torch.distributed as dist
+        per = (self.engine.n + self.world - 1) // self.world
+        per = (per + 127) // 128 * 128
+        outs = []
+        for sh in (self.exp_avg, self.exp_avg_sq):
+            pad = torch.zeros(per, device=sh.device)
+            pad[: self.hi - self.lo] = sh[: self.hi - self.lo]
+            full = torch.empty(per * self.world, device=sh.device)
+            dist.all_gather_into_tensor(full, pad, group=self.group)
+            outs.append(full[: self.engine.n].contiguous())
+        return tuple(outs)
+
+    def step(self):
+        self.step_count += 1
+        eng, lib, st = self.engine, self.engine._lib, _stream(self.engine.device)
+        self._hg.barrier(channel=0)      # every rank's backward has written its gradient arena
+        check(lib.salun_dp_grad_reduce_sumsq(self.ctx.handle, self._gp, _ptr(self.g_shard), _ptr(self._norm), eng.n,
+                                             self.rank, self.world, st), "salun_dp_grad_reduce_sumsq")
+        self._hn.barrier(channel=1)      # every rank's shard norm is visible
+        check(lib.salun_dp_masked_adam_step(self.ctx.handle, self._pp, self._np, _ptr(self.g_shard), _ptr(self.exp_avg),
+                                            _ptr(self.exp_avg_sq), _ptr(self.mask_bits), eng.n, self.rank, self.world,
+                                            float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
+                                            float(self.wd), self.step_count,
+                                            float(self.max_norm) if self.max_norm is not None else -1.0,
+                                            _ptr(self._coef_norm), st), "salun_dp_masked_adam_step")
+        self._hp.barrier(channel=2)      # every rank's shard of the new weights has landed in every replica

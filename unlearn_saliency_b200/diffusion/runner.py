@@ -162,8 +162,14 @@ class DDPMEngineUnlearner:
         self.device = engine.device
         self.betas = torch.as_tensor(betas).float().to(self.device)
         self.num_timesteps = self.betas.shape[0]
-        self.opt = FlatMaskedAdam(engine, lr=lr, betas=(beta1, 0.999), eps=eps, weight_decay=weight_decay, mask=mask,
-                                  max_norm=grad_clip)
+        self.fused_dp = bool(getattr(engine, "symmetric", False)) and self._world() > 1
+        if self.fused_dp:   # reduce-scatter + global clip + mask + Adam + all-gather over NVLink peer memory
+            from .engine import DistMaskedAdam
+            self.opt = DistMaskedAdam(engine, lr=lr, betas=(beta1, 0.999), eps=eps, weight_decay=weight_decay, mask=mask,
+                                      max_norm=grad_clip)
+        else:
+            self.opt = FlatMaskedAdam(engine, lr=lr, betas=(beta1, 0.999), eps=eps, weight_decay=weight_decay, mask=mask,
+                                      max_norm=grad_clip)
         self.saliency = FlatSaliency(engine, max_norm=grad_clip)
         self._step = 0
 
@@ -274,10 +280,11 @@ class DDPMEngineUnlearner:
             d_f = (2.0 / out_f.numel()) * (out_f - pseudo)
         loss = forget_loss + alpha * remain_loss                                                   # :572
         d = torch.cat([d_r, d_f])
-        if W > 1:
-            d = d / W
+        if W > 1 and not self.fused_dp:
+            d = d / W          # the fused DP step averages inside its reduce kernel
         eng.backward(d.contiguous())                                                               # :579-580
-        self._all_reduce_grads()
+        if not self.fused_dp:
+            self._all_reduce_grads()
         self.opt.step()   # clip_grad_norm_(1.0) BEFORE the mask, grad *= mask, Adam -- one fused pass (:582-593)
         return loss.detach()
 
@@ -285,7 +292,8 @@ class DDPMEngineUnlearner:
         """states = [model_sd, optim_sd, step] like :598-610"""
         os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
         sd = self.engine.state_dict(prefix="module.")
-        optim = {"exp_avg": self.engine.dict_from_flat(self.opt.exp_avg), "exp_avg_sq": self.engine.dict_from_flat(self.opt.exp_avg_sq),
+        m1, m2 = self.opt.gather_state() if self.fused_dp else (self.opt.exp_avg, self.opt.exp_avg_sq)
+        optim = {"exp_avg": self.engine.dict_from_flat(m1), "exp_avg_sq": self.engine.dict_from_flat(m2),
                  "step": self.opt.step_count}
         torch.save([sd, optim, step], path)
 
