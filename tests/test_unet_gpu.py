@@ -341,3 +341,78 @@ def test_diffusion_runner_mirror_end_to_end(salun_ctx, tmp_path, monkeypatch):
         assert torch.equal(v.cpu()[~m], sd0[k][~m]), k
         moved += int((v.cpu()[m] != sd0[k][m]).sum())
     assert moved > 0.9 * int(n_tot * 0.5)
+
+
+def mid_config():
+    """three levels (32x32 -> 16x16 -> 8x8), two ResnetBlocks per level, attention with 256 tokens at 16x16: every kernel
+    variant of the cifar10 config (1024-pixel images, stride-2 down / nearest up at two scales, 384-wide concat at 32x32)"""
+    c = small_config()
+    c.model.ch_mult, c.model.attn_resolutions, c.model.num_res_blocks = [1, 2, 2], [16], 2
+    c.data.image_size = 32
+    return c
+
+
+@pytest.mark.parametrize("n", [1, 3, 16])
+def test_engine_batch_edges(salun_ctx, n):
+    """one image, an odd batch and the full allocated batch through the same engine instance's plan cache"""
+    cfg = mid_config()
+    model = _torch_model(cfg)
+    model.eval()
+    eng = _engine(cfg, model, salun_ctx, max_batch=16).eval()
+    for nn_ in (n, max(1, n - 1), n):     # growing / shrinking batches must not see stale rows of earlier ones
+        x, t, c, drop, d_eps = _batch(cfg, nn_, 20 + nn_)
+        model.zero_grad()
+        eps_ref = model(x, t.float(), c, mode="train", drop_mask=drop)
+        (eps_ref * d_eps).sum().backward()
+        gref = {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in model.named_parameters()}
+        eps = eng.forward(x, t.float(), c, drop=drop, save=True)
+        assert rel(eps, eps_ref) < 0.02, (nn_, rel(eps, eps_ref))
+        eng.backward(d_eps)
+        _assert_grads_close(eng.grad_dict(), gref, whole_tol=0.05, per_tol=0.12)
+    eng.close()
+
+
+def test_engine_rejects_unserved_configs(salun_ctx):
+    from unlearn_saliency_b200.diffusion.engine import UNetEngine
+    for mutate in (lambda c: setattr(c.model, "ch", 64), lambda c: setattr(c.model, "attn_resolutions", [32]),
+                   lambda c: setattr(c.data, "image_size", 24)):
+        cfg = mid_config()
+        mutate(cfg)
+        with pytest.raises(RuntimeError):
+            UNetEngine(cfg, max_batch=4, ctx=salun_ctx)
+    eng = UNetEngine(tiny_config(), max_batch=4, ctx=salun_ctx)
+    x = torch.zeros(5, 3, 8, 8, device="cuda")
+    with pytest.raises(ValueError):
+        eng.forward(x, torch.zeros(5, device="cuda"), torch.zeros(5, dtype=torch.long, device="cuda"))   # batch > max_batch
+    with pytest.raises(ValueError):
+        eng.forward(x[:2].double(), torch.zeros(2, device="cuda"), torch.zeros(2, dtype=torch.long, device="cuda"))
+    eng.close()
+
+
+def test_cli_mirror_of_train_py(salun_ctx, tmp_path, monkeypatch):
+    """python -m unlearn_saliency_b200.diffusion.cli: the flags / YAML keys / directories of DDPM/train.py on synthetic data"""
+    import yaml
+    from unlearn_saliency_b200.diffusion import cli
+    from unlearn_saliency_b200.diffusion.unet import ConditionalUNet
+    monkeypatch.chdir(tmp_path)
+    cfg = dict(data=dict(dataset="CIFAR10", image_size=8, channels=3, random_flip=True, num_workers=0, n_classes=10, path="./data"),
+               model=dict(type="simple", in_channels=3, out_ch=3, ch=128, ch_mult=[1, 1], num_res_blocks=1, attn_resolutions=[4],
+                          dropout=0.1, ema=False, resamp_with_conv=True, cond_drop_prob=0.1),
+               diffusion=dict(beta_schedule="linear", beta_start=1e-4, beta_end=0.02, num_diffusion_timesteps=1000),
+               training=dict(batch_size=4, n_iters=2, snapshot_freq=2, log_freq=1),
+               optim=dict(weight_decay=0.0, optimizer="Adam", lr=1e-4, beta1=0.9, amsgrad=False, eps=1e-8, grad_clip=1.0))
+    (tmp_path / "configs").mkdir()
+    (tmp_path / "configs" / "tiny.yml").write_text(yaml.safe_dump(cfg))
+    model = ConditionalUNet(cli.dict2namespace(cfg))
+    (tmp_path / "ck" / "ckpts").mkdir(parents=True)
+    torch.save([{"module." + k: v for k, v in model.state_dict().items()}, {}, 0], str(tmp_path / "ck" / "ckpts" / "ckpt.pth"))
+    assert cli.main(["--config", "tiny.yml", "--ckpt_folder", "ck", "--label_to_forget", "3", "--mode", "generate_mask",
+                     "--synthetic", "8"]) == 0
+    mpath = tmp_path / "results" / "cifar10" / "mask" / "3" / "with_0.5.pt"
+    assert mpath.exists()
+    assert cli.main(["--config", "tiny.yml", "--ckpt_folder", "ck", "--label_to_forget", "3", "--mode", "saliency_unlearn",
+                     "--mask_path", str(mpath), "--alpha", "0.001", "--method", "rl", "--synthetic", "8"]) == 0
+    runs = list((tmp_path / "results" / "cifar10" / "forget" / "rl").glob("0.001_full/*/ckpts/ckpt.pth"))
+    assert len(runs) == 1
+    states = torch.load(str(runs[0]))
+    assert states[2] == 1 and all(k.startswith("module.") for k in states[0])
