@@ -25,6 +25,11 @@ namespace salun {
 using namespace sm100;
 
 constexpr int kGemmThreads = 192;
+// k_conv_gemm_p: 8 epilogue warps (two per TMEM lane quarter, alternating 32-column chunks).  The epilogue is a latency
+// chain per warp (tcgen05.ld -> wait -> adds -> 4 row-scattered 16-byte stores); with short K (the 1x1 convolutions and
+// attention products of the U-Net, K = 256) it is the slow side of the kernel: role timing showed the MMA issuer waiting on
+// the accumulator hand-back for 43 % of its life with 4 epilogue warps (profiles/README.md section 5).
+constexpr int kGemmPThreads = 320;
 constexpr int kBM = 128;
 constexpr int kBK = 64;  // bf16 elements per k-block = one 128-byte swizzle row
 
@@ -277,7 +282,7 @@ k_conv_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // stem and of the stride-2 dgrad spent most of their time in that setup).
 // =================================================================================================
 template <int BN, int kStages>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmPThreads, 1)
 k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvGemmArgs a,
               int m_tiles, int n_tiles) {
   constexpr uint32_t kABytes = kBM * kBK * 2;
@@ -304,7 +309,7 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull0 + 8 * i, 1);
-      mbar_init(tempty0 + 8 * i, 4);
+      mbar_init(tempty0 + 8 * i, 8);
     }
     fence_barrier_init();
   }
@@ -396,7 +401,9 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
     }
   } else {
-    const int q = warp & 3;
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2; // warps 2..5 take the even 32-column chunks, warps 6..9 the odd ones
+    uint8_t *stg = smem + kStages * kStageBytes + 256 + (warp - 2) * 4096;  // this warp's 4 KB store-transpose buffer
     long long w_tfull = 0;
     uint32_t ti = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
@@ -411,7 +418,7 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const size_t out_row = !row_ok ? 0 : (a.out_pad ? pad_row_off(row, a.fH, a.fW, a.ld_out) : (size_t)row * a.ld_out);
       const float *rb_row = (a.rowbias && row_ok) ? a.rowbias + (size_t)(row >> a.rb_shift) * a.rb_ld : nullptr;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         uint32_t r[32];
         tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, r);
         tc_wait_ld();
@@ -470,24 +477,45 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             bn_bwd_fuse_chunk(a.f1, r, row_ok, fuse_pad, (size_t)row * a.N, col0, a.N, stat_row, lane);
             if (a.f2.act) bn_bwd_fuse_chunk(a.f2, r, row_ok, fuse_pad, (size_t)row * a.N, col0, a.N, stat_row, lane);
           }
-          if (row_ok) {
-            if (a.out_bf16) {
-              uint4 *dst = reinterpret_cast<uint4 *>(a.out_bf16 + out_row + col0);
+          // Stores go through a per-warp shared-memory transpose: straight out of the TMEM layout (lane = row) a warp
+          // store touches 32 different rows with 16 bytes each (32 LSU wavefronts per instruction -- the measured bound
+          // of the short-K GEMMs); transposed, one instruction writes 8 rows x 64 B (bf16) / 4 rows x 128 B (fp32).
+          if (a.out_bf16) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 v;
-                v.x = pack_bf16x2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]));
-                v.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
-                v.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
-                v.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
-                dst[j] = v;
-              }
+            for (int j = 0; j < 4; ++j) {
+              uint4 v;
+              v.x = pack_bf16x2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]));
+              v.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+              v.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+              v.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+              *reinterpret_cast<uint4 *>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = v;
             }
-            if (a.out_f32) {
-              uint4 *dst = reinterpret_cast<uint4 *>(a.out_f32 + (size_t)row * a.ld_out + col0);
+            __syncwarp();
 #pragma unroll
-              for (int j = 0; j < 8; ++j) dst[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            for (int jj = 0; jj < 4; ++jj) {
+              const int rl = 8 * jj + (lane >> 2), unit = lane & 3;
+              const uint4 v = *reinterpret_cast<const uint4 *>(stg + rl * 64 + ((unit ^ ((rl >> 1) & 3)) << 4));
+              const unsigned long long orow = __shfl_sync(0xffffffffu, (unsigned long long)out_row, rl);
+              const int ok = __shfl_sync(0xffffffffu, row_ok ? 1 : 0, rl);
+              if (ok) *reinterpret_cast<uint4 *>(a.out_bf16 + orow + col0 + unit * 8) = v;
             }
+            __syncwarp();
+          }
+          if (a.out_f32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4 *>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            __syncwarp();
+            const int row_base = m_tile * kBM + q * 32;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const int rl = 4 * jj + (lane >> 3), unit = lane & 7;
+              const uint4 v = *reinterpret_cast<const uint4 *>(stg + rl * 128 + ((unit ^ (rl & 7)) << 4));
+              if (row_base + rl < a.M)
+                *reinterpret_cast<uint4 *>(a.out_f32 + (size_t)(row_base + rl) * a.ld_out + col0 + unit * 4) = v;
+            }
+            __syncwarp();
           }
         }
         __syncwarp();
@@ -495,7 +523,7 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       tc_fence_before();
       if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
     }
-    if (dbg_on && q == 0 && lane == 0) {
+    if (dbg_on && warp == 4 && lane == 0) {
       a.dbg[blockIdx.x * 8 + 5] = w_tfull;
       a.dbg[blockIdx.x * 8 + 6] = clock64() - t_begin;
     }
@@ -1231,7 +1259,7 @@ static int launch_conv_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, co
 
 template <int BN, int S>
 static int launch_conv_gemm_p_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvGemmArgs &a, cudaStream_t st) {
-  constexpr size_t smem = (size_t)S * (kBM * kBK * 2 + BN * kBK * 2) + 1024 + 256;
+  constexpr size_t smem = (size_t)S * (kBM * kBK * 2 + BN * kBK * 2) + 1024 + 256 + 8 * 4096;  // + store-transpose buffers
   static bool attr_set = false;
   static int num_sms = 0;
   if (!attr_set) {
@@ -1246,7 +1274,7 @@ static int launch_conv_gemm_p_t(const CUtensorMap &tmA, const CUtensorMap &tmB, 
   if (grid > num_sms) grid = num_sms;
   ConvGemmArgs aa = a;
   aa.dbg = g_dbg;
-  { SALUN_CUDA_OK(::salun::launch_pdl(k_conv_gemm_p<BN, S>, dim3(grid), dim3(kGemmThreads), smem, st, tmA, tmB, aa, m_tiles, n_tiles)); ++::salun::g_launch_count; }
+  { SALUN_CUDA_OK(::salun::launch_pdl(k_conv_gemm_p<BN, S>, dim3(grid), dim3(kGemmPThreads), smem, st, tmA, tmB, aa, m_tiles, n_tiles)); ++::salun::g_launch_count; }
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;
 }
