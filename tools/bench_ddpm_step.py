@@ -78,6 +78,16 @@ def main():
     res["fwd_ms_256"] = timeit(lambda: eng.forward(x2, t2, c2, save=True, train=True, seed=1))
     res["fwd_bwd_ms_256"] = timeit(lambda: (eng.forward(x2, t2, c2, save=True, train=True, seed=1), eng.backward(d2)))
     res["tail_ms"] = timeit(un.opt.step)
+    # mask generation (runners/diffusion.py:959-1039): one forget batch of 128 = conditional + null pass as a batch of 256,
+    # backward, clip, accumulate; then |.| + global top-k over 38.6 M saliencies and the int64 mask dict
+    res["maskgen_batch_ms_128"] = timeit(lambda: un.generate_mask_batch(xf_d, cf_d, cond_scale=2.0))
+    import time
+    torch.cuda.synchronize()
+    t0 = time.time()
+    m, info = un.finish_mask(None, 0.5)
+    torch.cuda.synchronize()
+    res["maskgen_select_and_export_ms"] = (time.time() - t0) * 1e3
+    res["maskgen_ones"] = int(sum(int(v.sum()) for v in m.values()))
     if "--no-ref" not in sys.argv:
         opt = torch.optim.Adam(ref.parameters(), lr=1e-4)
         bd = betas.cuda()

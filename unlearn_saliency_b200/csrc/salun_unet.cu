@@ -89,7 +89,7 @@ struct UConvMaps {
   int pair_fwd, pair_dg;  // forward / dgrad GEMM through the CTA-pair kernel (fwdB / dgB encoded with bn/2 box rows)
 };
 struct UAttnMaps {
-  CUtensorMap q, k, v, vt128, p, xt_b, tt_a, og, ds;  // see build_plan
+  CUtensorMap q, k, v, p, xt_b, tt_a, og, ds;  // see build_plan
   int bn_s, bn_o;
 };
 struct UPlan {
@@ -132,8 +132,8 @@ struct salun_unet {
   uint8_t *drop_dev;
   bool have_drop;
   // scratch
-  float *gn_partial, *gn_coef, *S_f32;
-  bf16 *xt1, *xt2, *tt, *dS;
+  float *gn_partial, *S_f32;
+  bf16 *xt1, *tt, *dS;
   WPrepEntry *wprep_table;
   WgReduceEntry *wgred_table, *wgred_host;
   std::vector<int> wg_splits;
@@ -517,7 +517,6 @@ static int build_plan(salun_unet *net, int n, UPlan **out) {
     TRY(make_tmap_2d_bf16(&m.tt_a, net->tt, G * A.Te, A.Te, 128, 64));      // A = a [Te][Te] transpose (Pt, dSt)
     TRY(make_tmap_2d_bf16(&m.og, net->ts[A.o].g, M, A.C, 128, 64));         // A of dP
     TRY(make_tmap_2d_bf16(&m.ds, net->dS, M, A.Te, 128, 64));               // A of dQ = dS Kt^T
-    (void)m.vt128;
   }
   {
     const int E8 = net->emb + 512, R = net->ld_rb;
@@ -1064,12 +1063,10 @@ int salun_unet_create(salun_ctx *ctx, const salun_unet_cfg *cfg, float *params, 
     if (G * At.Te * At.Te > max_tt) max_tt = G * At.Te * At.Te;
   }
   A(dmalloc(net, &net->gn_partial, max_part));
-  A(dmalloc(net, &net->gn_coef, (size_t)nb * kGnGroups * 2));
   A(dmalloc(net, &net->S_f32, max_S));
   A(dmalloc(net, &net->dS, max_S));
   A(dmalloc(net, &net->xt1, max_xt));
   A(dmalloc(net, &net->tt, max_tt));
-  net->xt2 = nullptr;
   A(dmalloc(net, &net->gscratch, (size_t)net->n_params));
   {
     const size_t ch = cfg->ch, E4 = net->emb, E8 = net->emb + 512;
