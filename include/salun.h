@@ -327,6 +327,21 @@ int salun_unet_forward(salun_unet *net, const float *x, const float *t, const in
  * accumulate == 0 overwrites the gradient arena (the zero_grad() of the reference loop is implied). */
 int salun_unet_backward(salun_unet *net, const float *d_eps, int accumulate, void *stream);
 
+/* x_t = x0 * sqrt_abar[t] + e * sqrt_1m_abar[t], x0 = rescale ? 2 * x01 - 1 : x01          (n samples of chw floats)
+ * replaces  data_transform (DDPM/datasets/__init__.py:241-255) and the q-sample of DDPM/functions/losses.py:31-32 /
+ *           runners/diffusion.py:558-559, :971-973.  sqrt_abar / sqrt_1m_abar: device tables over the T timesteps
+ *           ((1 - betas).cumprod(0).sqrt() and (1 - cumprod).sqrt(), fp32).  Same rounding sequence as the torch
+ *           statements: bit-identical. */
+int salun_ddpm_q_sample(salun_ctx *ctx, const float *x01, const float *e, const int64_t *t, const float *sqrt_abar,
+                        const float *sqrt_1m_abar, int rescale, int n, int chw, float *x_t, void *stream);
+/* The eps-prediction losses of an iteration and their gradient w.r.t. eps in one pass:
+ *   sumsq_ps[i] = sum_chw (eps[i] - target[i])^2 ;  d_eps[i] = 2 * w[i] * (eps[i] - target[i]) ;  loss = sum_i w[i] * sumsq_ps[i]
+ * replaces  noise_estimation_loss_conditional (losses.py:33-37: target = e, w = alpha / n for the remain batch, -1 / n for
+ *           method ga), MSELoss(pseudo, output) (runners/diffusion.py:570: target = pseudo, w = 1 / (n * chw)), their sum
+ *           (:572) and the first step of loss.backward() (:579-580).  w: device fp32 [n] per-sample weights. */
+int salun_ddpm_eps_loss_grad(salun_ctx *ctx, const float *eps, const float *target, const float *w, int n, int chw,
+                             float *d_eps, float *sumsq_ps, float *loss_dev, void *stream);
+
 /* bring-up / parity-test accessors: the tape's activation tensors, exported as fp32 NCHW [n][C][H][H]
  * (which = 0: value, 1: gradient of the last backward). */
 int salun_unet_num_tensors(const salun_unet *net);

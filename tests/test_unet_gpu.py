@@ -416,3 +416,42 @@ def test_cli_mirror_of_train_py(salun_ctx, tmp_path, monkeypatch):
     assert len(runs) == 1
     states = torch.load(str(runs[0]))
     assert states[2] == 1 and all(k.startswith("module.") for k in states[0])
+
+
+def test_q_sample_and_loss_kernels_match_torch(salun_ctx):
+    """salun_ddpm_q_sample is bit-identical to the reference statements (2x - 1, x0 sqrt(abar) + e sqrt(1 - abar));
+    salun_ddpm_eps_loss_grad equals autograd on forget_loss + alpha * remain_loss (runners/diffusion.py:533-580)."""
+    from oracle import ddpm as OD
+    from unlearn_saliency_b200.diffusion.engine import DDPMLoss
+    from unlearn_saliency_b200.diffusion.runner import get_beta_schedule
+    betas = torch.from_numpy(get_beta_schedule("linear", beta_start=1e-4, beta_end=0.02, num_diffusion_timesteps=1000)).float()
+    L = DDPMLoss(betas, salun_ctx)
+    g = torch.Generator().manual_seed(2)
+    for n in (1, 7, 128):
+        x01 = torch.rand(n, 3, 32, 32, generator=g).cuda()
+        e = torch.randn(n, 3, 32, 32, generator=g).cuda()
+        t = torch.randint(0, 1000, (n,), generator=g).cuda()
+        ref = OD.q_sample(2 * x01 - 1.0, t, e, betas.cuda())
+        assert torch.equal(L.q_sample(x01, e, t, rescale=True), ref)
+        assert torch.equal(L.q_sample(x01, e, t, rescale=False), OD.q_sample(x01, t, e, betas.cuda()))
+    nr, nf, alpha = 5, 3, 1e-3
+    for method in ("rl", "ga"):
+        eps = torch.randn(nr + nf, 3, 16, 16, generator=g).cuda().requires_grad_(True)
+        e = torch.randn(nr + nf, 3, 16, 16, generator=g).cuda()
+        pseudo = torch.randn(nf, 3, 16, 16, generator=g).cuda()
+        remain = (e[:nr] - eps[:nr]).square().sum(dim=(1, 2, 3)).mean(dim=0)
+        if method == "rl":
+            forget = torch.nn.functional.mse_loss(eps[nr:], pseudo)
+            target = torch.cat([e[:nr], pseudo])
+            wf = 1.0 / (nf * 3 * 16 * 16)
+        else:
+            forget = -(e[nr:] - eps[nr:]).square().sum(dim=(1, 2, 3)).mean(dim=0)
+            target = e
+            wf = -1.0 / nf
+        loss_ref = forget + alpha * remain
+        loss_ref.backward()
+        w = torch.cat([torch.full((nr,), alpha / nr), torch.full((nf,), wf)]).cuda()
+        loss, d, ss = L.loss_grad(eps.detach(), target, w)
+        torch.testing.assert_close(loss[0], loss_ref.detach(), rtol=2e-5, atol=1e-7)
+        torch.testing.assert_close(d, eps.grad, rtol=1e-5, atol=1e-9)
+        torch.testing.assert_close(ss, (eps.detach() - target).square().sum(dim=(1, 2, 3)), rtol=1e-5, atol=1e-6)

@@ -1171,6 +1171,27 @@ int salun_unet_backward(salun_unet *net, const float *d_eps, int accumulate, voi
   return backward_impl(net, d_eps, accumulate, (cudaStream_t)stream);
 }
 
+int salun_ddpm_q_sample(salun_ctx *ctx, const float *x01, const float *e, const int64_t *t, const float *sqrt_abar,
+                        const float *sqrt_1m_abar, int rescale, int n, int chw, float *x_t, void *stream) {
+  SALUN_REQUIRE(ctx && x01 && e && t && sqrt_abar && sqrt_1m_abar && x_t, "NULL argument");
+  SALUN_REQUIRE(n >= 0 && chw > 0, "bad sizes");
+  if (n == 0) return SALUN_OK;
+  SALUN_CUDA_OK(cudaSetDevice(ctx->device));
+  launch_q_sample(x01, e, t, sqrt_abar, sqrt_1m_abar, rescale, n, chw, x_t, (cudaStream_t)stream);
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+
+int salun_ddpm_eps_loss_grad(salun_ctx *ctx, const float *eps, const float *target, const float *w, int n, int chw,
+                             float *d_eps, float *sumsq_ps, float *loss_dev, void *stream) {
+  SALUN_REQUIRE(ctx && eps && target && w && d_eps && sumsq_ps && loss_dev, "NULL argument");
+  SALUN_REQUIRE(n > 0 && chw > 0, "bad sizes");
+  SALUN_CUDA_OK(cudaSetDevice(ctx->device));
+  launch_eps_loss_grad(eps, target, w, n, chw, d_eps, sumsq_ps, loss_dev, (cudaStream_t)stream);
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+
 int salun_unet_num_tensors(const salun_unet *net) { return net ? (int)net->ts.size() : -1; }
 
 int salun_unet_tensor_info(const salun_unet *net, int idx, char *name_buf, int name_cap, int *C, int *H) {

@@ -1044,4 +1044,63 @@ void launch_f32_to_bf16(const float *in, int ld_in, bf16 *out, int ld_out, int r
   ++g_launch_count;
 }
 
+
+// =================================================================================================================
+// q-sample and the eps-prediction losses (DDPM/functions/losses.py:21-37, runners/diffusion.py:533-572)
+// =================================================================================================================
+// x_t = x0 * sqrt(abar_t) + e * sqrt(1 - abar_t), x0 = 2 * x01 - 1 when rescale (data_transform): the same fp32 operation
+// sequence as torch (separately rounded multiplies and adds, no contraction) -> bit-identical to the reference statements
+__global__ void __launch_bounds__(256) k_q_sample(const float *__restrict__ x01, const float *__restrict__ e,
+                                                  const int64_t *__restrict__ t, const float *__restrict__ sa,
+                                                  const float *__restrict__ sb, int rescale, long long total, int chw,
+                                                  float *__restrict__ xt) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int n = (int)(i / chw);
+    const int tt = (int)t[n];
+    float x0 = x01[i];
+    if (rescale) x0 = __fadd_rn(__fmul_rn(2.0f, x0), -1.0f);
+    xt[i] = __fadd_rn(__fmul_rn(x0, sa[tt]), __fmul_rn(e[i], sb[tt]));
+  }
+}
+void launch_q_sample(const float *x01, const float *e, const int64_t *t, const float *sqrt_abar, const float *sqrt_1m_abar,
+                     int rescale, int n, int chw, float *xt, cudaStream_t st) {
+  const long long total = (long long)n * chw;
+  k_q_sample<<<grid_for(total), 256, 0, st>>>(x01, e, t, sqrt_abar, sqrt_1m_abar, rescale, total, chw, xt);
+  ++g_launch_count;
+}
+// per sample: ss[n] = sum_chw (eps - target)^2 ; d_eps = 2 * w[n] * (eps - target)
+__global__ void __launch_bounds__(256) k_eps_loss_grad(const float *__restrict__ eps, const float *__restrict__ target,
+                                                       const float *__restrict__ w, int chw, float *__restrict__ d_eps,
+                                                       float *__restrict__ ss) {
+  __shared__ float red[256];
+  const int n = blockIdx.x;
+  const float w2 = 2.0f * w[n];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < chw; i += 256) {
+    const float d = eps[(size_t)n * chw + i] - target[(size_t)n * chw + i];
+    s = fmaf(d, d, s);
+    d_eps[(size_t)n * chw + i] = w2 * d;
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) ss[n] = red[0];
+}
+// loss = sum_n w[n] * ss[n]   (one warp, fixed order)
+__global__ void k_weighted_sum(const float *__restrict__ w, const float *__restrict__ ss, int n, float *__restrict__ out) {
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 32) s = fmaf(w[i], ss[i], s);
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (threadIdx.x == 0) *out = s;
+}
+void launch_eps_loss_grad(const float *eps, const float *target, const float *w, int n, int chw, float *d_eps, float *ss,
+                          float *loss, cudaStream_t st) {
+  k_eps_loss_grad<<<n, 256, 0, st>>>(eps, target, w, chw, d_eps, ss);
+  k_weighted_sum<<<1, 32, 0, st>>>(w, ss, n, loss);
+  g_launch_count += 2;
+}
+
 }  // namespace salun

@@ -108,4 +108,12 @@ void launch_scatter_rows(const float *src, const long long *row_w, float *dst, i
 // out[i*ld_out + j] = bf16(in[i*ld_in + j]); cols % 4 == 0, 16-byte aligned rows
 void launch_f32_to_bf16(const float *in, int ld_in, __nv_bfloat16 *out, int ld_out, int rows, int cols, cudaStream_t st);
 
+
+// ---- q-sample and eps-prediction losses (functions/losses.py:21-37, runners/diffusion.py:533-572) ----
+void launch_q_sample(const float *x01, const float *e, const int64_t *t, const float *sqrt_abar, const float *sqrt_1m_abar,
+                     int rescale, int n, int chw, float *xt, cudaStream_t st);
+// ss[n] = sum_chw (eps - target)^2 ; d_eps = 2 w[n] (eps - target) ; loss = sum_n w[n] ss[n]
+void launch_eps_loss_grad(const float *eps, const float *target, const float *w, int n, int chw, float *d_eps, float *ss,
+                          float *loss, cudaStream_t st);
+
 }  // namespace salun

@@ -43,7 +43,49 @@ _lib.register_signatures({
     "salun_unet_num_tensors": [_P],
     "salun_unet_tensor_info": [_P, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "salun_unet_export_tensor": [_P, C.c_int, C.c_int, _P, _P],
+    "salun_ddpm_q_sample": [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P],
+    "salun_ddpm_eps_loss_grad": [_P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P],
 }, {"salun_unet_param_count": C.c_int64})
+
+
+class DDPMLoss:
+    """q-sample and the eps-prediction losses + dL/d(eps) of one iteration on the sm_100a kernels
+    (salun_ddpm_q_sample, salun_ddpm_eps_loss_grad): functions/losses.py:21-37, runners/diffusion.py:533-580."""
+
+    def __init__(self, betas: torch.Tensor, ctx: SalunContext):
+        self.ctx, self._lib = ctx, _lib.lib()
+        dev = ctx.device
+        abar = (1 - betas.float().to(dev)).cumprod(dim=0)       # the reference's own fp32 statements (losses.py:31)
+        self.sqrt_abar = abar.sqrt().contiguous()
+        self.sqrt_1m_abar = (1.0 - abar).sqrt().contiguous()
+        self.device = dev
+
+    def q_sample(self, x01: torch.Tensor, e: torch.Tensor, t: torch.Tensor, rescale: bool = True) -> torch.Tensor:
+        x01, e, t = x01.contiguous(), e.contiguous(), t.contiguous()
+        if not (x01.is_cuda and x01.dtype == torch.float32 and e.dtype == torch.float32 and t.dtype == torch.int64
+                and e.shape == x01.shape and t.numel() == x01.shape[0]):
+            raise ValueError("q_sample: x01 / e must be CUDA fp32 of the same shape, t CUDA int64 [n]")
+        out = torch.empty_like(x01)
+        n = x01.shape[0]
+        check(self._lib.salun_ddpm_q_sample(self.ctx.handle, _ptr(x01), _ptr(e), _ptr(t), _ptr(self.sqrt_abar),
+                                            _ptr(self.sqrt_1m_abar), 1 if rescale else 0, n, x01.numel() // max(n, 1),
+                                            _ptr(out), _stream(self.device)), "salun_ddpm_q_sample")
+        return out
+
+    def loss_grad(self, eps: torch.Tensor, target: torch.Tensor, w: torch.Tensor):
+        """returns (loss [1], d_eps like eps, per-sample sum of squares [n])"""
+        eps, target, w = eps.contiguous(), target.contiguous(), w.contiguous()
+        n = eps.shape[0]
+        if not (eps.is_cuda and eps.dtype == torch.float32 and target.shape == eps.shape and target.dtype == torch.float32
+                and w.dtype == torch.float32 and w.numel() == n):
+            raise ValueError("loss_grad: eps / target must be CUDA fp32 of the same shape, w CUDA fp32 [n]")
+        d = torch.empty_like(eps)
+        ss = torch.empty(n, device=eps.device)
+        loss = torch.empty(1, device=eps.device)
+        check(self._lib.salun_ddpm_eps_loss_grad(self.ctx.handle, _ptr(eps), _ptr(target), _ptr(w), n, eps.numel() // n,
+                                                 _ptr(d), _ptr(ss), _ptr(loss), _stream(self.device)),
+              "salun_ddpm_eps_loss_grad")
+        return loss, d, ss
 
 
 def unet_param_table(config) -> "OrderedDict[str, tuple]":

@@ -172,6 +172,19 @@ class DDPMEngineUnlearner:
                                       max_norm=grad_clip)
         self.saliency = FlatSaliency(engine, max_norm=grad_clip)
         self._step = 0
+        from .engine import DDPMLoss
+        self.loss_k = DDPMLoss(self.betas, engine.ctx)   # q-sample, eps losses and dL/d(eps) as kernels
+        self._w_cache = {}
+
+    def _weights(self, nr, nf, alpha, method, chw, scale):
+        """per-sample loss weights: loss = sum_i w_i * sum_chw (eps_i - target_i)^2  (losses.py:33-37, diffusion.py:552-572)"""
+        key = (nr, nf, float(alpha), method, chw, float(scale))
+        w = self._w_cache.get(key)
+        if w is None:
+            wf = 1.0 / (nf * chw) if method == "rl" else -1.0 / nf
+            w = torch.cat([torch.full((nr,), alpha / nr), torch.full((nf,), wf)]).mul_(scale).to(self.device)
+            self._w_cache[key] = w
+        return w
 
     @staticmethod
     def _world():
@@ -194,12 +207,12 @@ class DDPMEngineUnlearner:
     def generate_mask_batch(self, x, c, cond_scale: float = 2.0, t=None, e=None):
         """x in [0,1]; eval mode; the conditional and the null pass of _forward_with_cond_scale run as one batch of 2n."""
         eng, dev = self.engine, self.device
-        x = 2 * x.to(dev).float() - 1.0
+        x = x.to(dev).float()
         c = c.to(dev)
         n = x.shape[0]
         e = torch.randn_like(x) if e is None else e.to(dev)
         t = antithetic_t(n, self.num_timesteps, dev) if t is None else t.to(dev)
-        xt = q_sample(x, t, e, self.betas).contiguous()
+        xt = self.loss_k.q_sample(x, e, t, rescale=True)     # data_transform (2x - 1) + q-sample, one kernel
         tf = t.float()
         s = float(cond_scale)
         if s == 0:
@@ -242,51 +255,43 @@ class DDPMEngineUnlearner:
         eng, dev = self.engine, self.device
         W = self._world()
         p_drop = eng.cond_drop_prob
-        xr, cr = 2 * remain_x.to(dev).float() - 1.0, remain_c.to(dev)
-        nr = xr.shape[0]
-        e_r = rng["e_r"].to(dev) if "e_r" in rng else torch.randn_like(xr)
-        t_r = rng["t_r"].to(dev) if "t_r" in rng else antithetic_t(nr, self.num_timesteps, dev)
-        xf, cf = 2 * forget_x.to(dev).float() - 1.0, forget_c.to(dev)
-        nf = xf.shape[0]
-        e_f = rng["e_f"].to(dev) if "e_f" in rng else torch.randn_like(xf)
-        t_f = rng["t_f"].to(dev) if "t_f" in rng else antithetic_t(nf, self.num_timesteps, dev)
-        xt_r = q_sample(xr, t_r, e_r, self.betas)                                                  # losses.py:31-32
-        xt_f = q_sample(xf, t_f, e_f, self.betas)                                                  # :558-559
+        x01 = torch.cat([remain_x.to(dev, non_blocking=True).float(), forget_x.to(dev, non_blocking=True).float()])
+        cr, cf = remain_c.to(dev, non_blocking=True), forget_c.to(dev, non_blocking=True)
+        nr, nf = remain_x.shape[0], forget_x.shape[0]
+        e = torch.cat([rng["e_r"].to(dev), rng["e_f"].to(dev)]) if "e_r" in rng else torch.randn_like(x01)
+        t = (torch.cat([rng["t_r"].to(dev), rng["t_f"].to(dev)]) if "t_r" in rng else
+             torch.cat([antithetic_t(nr, self.num_timesteps, dev), antithetic_t(nf, self.num_timesteps, dev)]))
+        xt = self.loss_k.q_sample(x01, e, t, rescale=True)          # data_transform + q-sample (losses.py:31-32, :558-559)
+        tf = t.float()
         drop_r, drop_f = self._drop(rng, "drop_r", nr, p_drop), self._drop(rng, "drop_f", nf, p_drop)
         self._step += 1
         seed = int(rng.get("seed", self._step)) * 2
-        pseudo = None
         if method == "rl":
             drop_p = self._drop(rng, "drop_p", nf, p_drop)
-            pseudo = eng.forward(xt_f.contiguous(), t_f.float(), (cf + 1) % n_classes, drop=drop_p, save=False,
+            pseudo = eng.forward(xt[nr:], tf[nr:], (cf + 1) % n_classes, drop=drop_p, save=False,
                                  train=train, seed=seed + 1)                                       # :561-569 (no grad)
-        elif method != "ga":
+            target = torch.cat([e[:nr], pseudo])
+        elif method == "ga":
+            target = e
+        else:
             raise NotImplementedError(method)
         if drop_r is None and drop_f is None:
             drop = None
         else:
             z = lambda k: torch.zeros(k, dtype=torch.uint8, device=dev)
             drop = torch.cat([drop_r if drop_r is not None else z(nr), drop_f if drop_f is not None else z(nf)])
-        eps = eng.forward(torch.cat([xt_r, xt_f]).contiguous(), torch.cat([t_r, t_f]).float(), torch.cat([cr, cf]),
-                          drop=drop, save=True, train=train, seed=seed)
-        out_r, out_f = eps[:nr], eps[nr:]
-        remain_loss = (e_r - out_r).square().sum(dim=(1, 2, 3)).mean(dim=0)                        # :533-536
-        d_r = (-2.0 * alpha / nr) * (e_r - out_r)
-        if method == "ga":
-            forget_loss = -(e_f - out_f).square().sum(dim=(1, 2, 3)).mean(dim=0)                   # :552-555
-            d_f = (2.0 / nf) * (e_f - out_f)
-        else:
-            forget_loss = torch.nn.functional.mse_loss(out_f, pseudo)                              # :570
-            d_f = (2.0 / out_f.numel()) * (out_f - pseudo)
-        loss = forget_loss + alpha * remain_loss                                                   # :572
-        d = torch.cat([d_r, d_f])
-        if W > 1 and not self.fused_dp:
-            d = d / W          # the fused DP step averages inside its reduce kernel
-        eng.backward(d.contiguous())                                                               # :579-580
+        eps = eng.forward(xt, tf, torch.cat([cr, cf]), drop=drop, save=True, train=train, seed=seed)
+        # loss = forget_loss + alpha * remain_loss (:533-572) and dL/d(eps), one kernel; the NCCL path averages the
+        # gradient by pre-scaling dL/d(eps) with 1/W (the fused DP step averages inside its reduce kernel)
+        scale = 1.0 / W if (W > 1 and not self.fused_dp) else 1.0
+        loss, d, _ = self.loss_k.loss_grad(eps, target, self._weights(nr, nf, alpha, method, eps[0].numel(), scale))
+        if scale != 1.0:
+            loss = loss * W
+        eng.backward(d)                                                                            # :579-580
         if not self.fused_dp:
             self._all_reduce_grads()
         self.opt.step()   # clip_grad_norm_(1.0) BEFORE the mask, grad *= mask, Adam -- one fused pass (:582-593)
-        return loss.detach()
+        return loss[0]
 
     def save_checkpoint(self, path: str, step: int):
         """states = [model_sd, optim_sd, step] like :598-610"""
