@@ -116,3 +116,95 @@ def test_dp_matches_single_process():
         torch.testing.assert_close(acc_r, acc, rtol=1e-5, atol=1e-6)       # one all-reduce(sum) of the accumulator
         torch.testing.assert_close(params_r, eng2.params, rtol=1e-5, atol=1e-6)  # sharded batch == global-batch mean grad
     assert torch.equal(res[0][2], res[1][2])  # replicas stay bit-identical
+
+
+def test_dp_shard_tiles_the_arena():
+    """salun_dp_shard (host-only): the shards of the fused DP kernels tile [0, n) exactly, in whole mask words / vectors"""
+    import ctypes as C
+    from unlearn_saliency_b200 import _lib
+    lib = _lib.lib()
+    for n in (0, 1, 127, 128, 129, 11173962, 38632323):
+        for world in (1, 2, 3, 4, 8):
+            prev = 0
+            for rank in range(world):
+                lo, hi = C.c_int64(), C.c_int64()
+                assert lib.salun_dp_shard(n, rank, world, C.byref(lo), C.byref(hi)) == 0
+                assert lo.value == prev and lo.value <= hi.value <= n
+                assert lo.value % 128 == 0 or lo.value == n
+                prev = hi.value
+            assert prev == n
+    lo, hi = C.c_int64(), C.c_int64()
+    assert lib.salun_dp_shard(10, 2, 2, C.byref(lo), C.byref(hi)) != 0      # rank out of range
+
+
+def _adam_worker(rank, world, port, q):
+    """The exchange DistMaskedAdam's two kernels implement (salun_dp_grad_reduce_sumsq -> barrier ->
+    salun_dp_masked_adam_step), restated with gloo collectives on the CPU: reduce the owned shard of the averaged gradient,
+    exchange the shard norms, clip with the GLOBAL norm, mask, Adam on the shard with shard-sized moments, all-gather."""
+    import ctypes as C
+    from unlearn_saliency_b200 import _lib
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = _lib.lib()
+    n = 1000
+    g0 = torch.Generator().manual_seed(0)
+    p = torch.randn(n, generator=g0)
+    mask = (torch.rand(n, generator=g0) < 0.5).float()
+    lo, hi = C.c_int64(), C.c_int64()
+    lib.salun_dp_shard(n, rank, world, C.byref(lo), C.byref(hi))
+    lo, hi = lo.value, hi.value
+    m1, m2 = torch.zeros(hi - lo), torch.zeros(hi - lo)
+    for step in range(1, 4):
+        grad = torch.randn(n, generator=torch.Generator().manual_seed(100 * step + rank)) * (0.2 if step == 2 else 0.01)
+        grads = [torch.empty(n) for _ in range(world)]
+        dist.all_gather(grads, grad)                      # stands in for the peer-mapped gradient arenas
+        gs = sum(g_[lo:hi] for g_ in grads) / world       # phase 1: owned shard of the averaged gradient ...
+        norms = [torch.empty(1, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(norms, gs.double().square().sum().reshape(1))   # ... and its sum of squares, visible to all
+        total = float(torch.stack(norms).sum().sqrt())    # phase 2: global pre-clip norm
+        coef = min(1.0, 1.0 / (total + 1e-6))
+        gi = gs * coef * mask[lo:hi]
+        m1 = m1 + (gi - m1) * (1 - 0.9)
+        m2 = 0.999 * m2 + (1 - 0.999) * gi * gi
+        denom = m2.sqrt() / (1 - 0.999 ** step) ** 0.5 + 1e-8
+        new = p[lo:hi] - 1e-3 / (1 - 0.9 ** step) * m1 / denom
+        per = (n + world - 1) // world
+        per = (per + 127) // 128 * 128
+        pad = torch.zeros(per)
+        pad[: hi - lo] = new
+        allp = [torch.empty(per) for _ in range(world)]
+        dist.all_gather(allp, pad)                        # the new weights land in every replica
+        p = torch.cat(allp)[:n].clone()
+    q.put((rank, p))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dp_clip_mask_adam_exchange_matches_single_process():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_adam_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    # single process: the reference's statements on the DDP-averaged gradient (runners/diffusion.py:582-593)
+    n = 1000
+    g0 = torch.Generator().manual_seed(0)
+    p = torch.nn.Parameter(torch.randn(n, generator=g0))
+    mask = (torch.rand(n, generator=g0) < 0.5).float()
+    opt = torch.optim.Adam([p], lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    for step in range(1, 4):
+        gr = [torch.randn(n, generator=torch.Generator().manual_seed(100 * step + r)) * (0.2 if step == 2 else 0.01)
+              for r in range(world)]
+        p.grad = sum(gr) / world
+        torch.nn.utils.clip_grad_norm_([p], 1.0)
+        p.grad *= mask
+        opt.step()
+    for rank, pr_ in res:
+        torch.testing.assert_close(pr_, p.detach(), rtol=1e-5, atol=1e-7)
+    assert torch.equal(res[0][1], res[1][1])
