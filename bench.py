@@ -207,7 +207,10 @@ def bench_ddpm(args, dev, rank, world, L, timed, tf_peak, peak_src):
         k = min(steps, 3)
         ach = [pf[c] / (pm[c] * 1e-3) / 1e12 if pm[c] > 0 else 0.0 for c in range(2)]
         roof = {"bound": "tensor", "kernel": "k_conv_gemm_p / k_gemm2 (conv forward + dgrad, attention and projection GEMMs)",
-                "achieved": ach[0], "peak": tf_peak, "unit": "TFLOP/s", "frac": ach[0] / tf_peak, "traffic": None,
+                "achieved": ach[0], "peak": tf_peak, "unit": "TFLOP/s", "frac": ach[0] / tf_peak,
+                # one launch of the 128->128 3x3 convolution at 32x32, batch 256 (profiles/r1_ncu_full_unet_conv128.csv):
+                # 76.1 MB read = the padded activation once, 23.6 MB written before the kernel retired (output 67 MB)
+                "traffic": 99716352, "traffic_unit": "bytes per launch (ncu --set full, profiles/r1_ncu_full_unet_conv128.csv)",
                 "peak_source": peak_src, "avg_launch_us": pm[0] * 1e3 / max(1, pc[0]), "launches_per_it": pc[0] / k,
                 "share_of_it": pm[0] / k / ms,
                 "other": {"kernel": "k_wgrad (side stream)", "achieved": ach[1], "share_of_it": pm[1] / k / ms}}
@@ -428,7 +431,11 @@ def main():
         dom = 0 if ms[0] >= ms[1] else 1
         roof = {
             "bound": "tensor", "kernel": ["k_conv_gemm (conv forward + dgrad)", "k_wgrad"][dom],
-            "achieved": ach[dom], "peak": tf_peak, "unit": "TFLOP/s", "frac": ach[dom] / tf_peak, "traffic": None,
+            "achieved": ach[dom], "peak": tf_peak, "unit": "TFLOP/s", "frac": ach[dom] / tf_peak,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the category's largest kernel (k_conv_rw<32,1>,
+            # the 64->64 3x3 convolution at 32x32, batch 256) from profiles/r1_ncu_full_rw.csv: 38.0 MB read = the padded
+            # activation once (no re-reads) + 1.3 MB written before the kernel retired
+            "traffic": 39258624, "traffic_unit": "bytes per launch (ncu --set full, profiles/r1_ncu_full_rw.csv)",
             "peak_source": peak_src,
             "how": f"CUDA events around every launch of the kernel, {prof_steps} instrumented steps replayed after the timed region",
             "avg_launch_us": ms[dom] * 1e3 / max(1, cnt[dom]), "launches_per_step": cnt[dom] / prof_steps,
