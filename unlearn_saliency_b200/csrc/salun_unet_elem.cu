@@ -872,54 +872,46 @@ void launch_emb_inputs(const float *t, const int64_t *c, const uint8_t *drop, co
   k_emb_inputs<<<n, ch, 0, st>>>(t, c, drop, class_emb, null_emb, sincos, ce, n, ch);
   ++g_launch_count;
 }
-// 64 x 64 tile, 16-deep k steps, 4 x 4 outputs per thread
+// 32 x 32 tile, 32-deep k steps, 2 x 2 outputs per thread: the embedding MLPs are 256 x 512 x 512 and smaller, so small
+// tiles are what fills the SMs (128 CTAs instead of 32 for the 64 x 64 version, which took 41 us per launch)
 __global__ void __launch_bounds__(256) k_sgemm(const float *__restrict__ A, long long sai, long long sak,
                                                const float *__restrict__ B, long long sbk, long long sbj,
                                                float *__restrict__ C, int ldc, int M, int N, int K,
                                                const float *__restrict__ bias, int accumulate) {
-  __shared__ float As[16][65], Bs[16][65];
-  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  __shared__ float As[32][33], Bs[32][33];
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float acc[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += 16) {
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int k0 = 0; k0 < K; k0 += 32) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int e = threadIdx.x + 256 * q;
-      // A tile: consecutive threads walk the dimension that is contiguous in memory
+      // consecutive threads walk the dimension that is contiguous in memory
       int ai, ak;
-      if (sak == 1) { ak = e & 15; ai = e >> 4; } else { ai = e & 63; ak = e >> 6; }
+      if (sak == 1) { ak = e & 31; ai = e >> 5; } else { ai = e & 31; ak = e >> 5; }
       As[ak][ai] = (i0 + ai < M && k0 + ak < K) ? A[(long long)(i0 + ai) * sai + (long long)(k0 + ak) * sak] : 0.f;
       int bj, bk;
-      if (sbk == 1) { bk = e & 15; bj = e >> 4; } else { bj = e & 63; bk = e >> 6; }
+      if (sbk == 1) { bk = e & 31; bj = e >> 5; } else { bj = e & 31; bk = e >> 5; }
       Bs[bk][bj] = (j0 + bj < N && k0 + bk < K) ? B[(long long)(k0 + bk) * sbk + (long long)(j0 + bj) * sbj] : 0.f;
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      float a[4], b[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        a[q] = As[k][ty * 4 + q];
-        b[q] = Bs[k][tx * 4 + q];
-      }
-#pragma unroll
-      for (int p = 0; p < 4; ++p)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc[p][q] += a[p] * b[q];
+    for (int k = 0; k < 32; ++k) {
+      const float a0 = As[k][ty * 2], a1 = As[k][ty * 2 + 1], b0 = Bs[k][tx * 2], b1 = Bs[k][tx * 2 + 1];
+      acc[0][0] = fmaf(a0, b0, acc[0][0]);
+      acc[0][1] = fmaf(a0, b1, acc[0][1]);
+      acc[1][0] = fmaf(a1, b0, acc[1][0]);
+      acc[1][1] = fmaf(a1, b1, acc[1][1]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    const int i = i0 + ty * 4 + p;
+  for (int p = 0; p < 2; ++p) {
+    const int i = i0 + ty * 2 + p;
     if (i >= M) continue;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int j = j0 + tx * 4 + q;
+    for (int q = 0; q < 2; ++q) {
+      const int j = j0 + tx * 2 + q;
       if (j >= N) continue;
       float v = acc[p][q] + (bias ? bias[j] : 0.f);
       if (accumulate) v += C[(size_t)i * ldc + j];
@@ -929,7 +921,7 @@ __global__ void __launch_bounds__(256) k_sgemm(const float *__restrict__ A, long
 }
 void launch_sgemm(const float *A, long long sai, long long sak, const float *B, long long sbk, long long sbj, float *C,
                   int ldc, int M, int N, int K, const float *bias, int accumulate, cudaStream_t st) {
-  k_sgemm<<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, st>>>(A, sai, sak, B, sbk, sbj, C, ldc, M, N, K, bias,
+  k_sgemm<<<dim3((N + 31) / 32, (M + 31) / 32), 256, 0, st>>>(A, sai, sak, B, sbk, sbj, C, ldc, M, N, K, bias,
                                                              accumulate);
   ++g_launch_count;
 }
