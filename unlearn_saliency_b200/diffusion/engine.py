@@ -102,9 +102,13 @@ class UNetEngine:
     native_layout = True  # conv weights are stored OHWI in the arena (flat.FlatSaliency converts before the top-k)
 
     def __init__(self, config, max_batch: int = 256, device=None, ctx: Optional[SalunContext] = None,
-                 symmetric: bool = False):
+                 symmetric: bool = False, share_with: Optional["UNetEngine"] = None):
         """symmetric=True allocates the parameter / gradient arenas as torch symmetric memory (NVLink peer-mapped), which
-        DistMaskedAdam needs for its fused reduce-scatter + clip + mask + Adam + all-gather kernels."""
+        DistMaskedAdam needs for its fused reduce-scatter + clip + mask + Adam + all-gather kernels.
+        share_with=<engine> builds a second set of activation buffers over the SAME parameter arena (a forward-only
+        replica, e.g. for running the no-grad pseudo-label pass on another stream next to the main pass)."""
+        if share_with is not None:
+            ctx = share_with.ctx if ctx is None else ctx
         m, d = config.model, config.data
         if not m.resamp_with_conv:
             raise NotImplementedError("resamp_with_conv=False is not used by the SalUn configs")
@@ -132,7 +136,11 @@ class UNetEngine:
             off += math.prod(s)
         dev = self.device
         self.symmetric = bool(symmetric)
-        if symmetric:
+        if share_with is not None:
+            if share_with.n != self.n:
+                raise ValueError("share_with: the two engines must have the same architecture")
+            self.params, self.grads, self.symmetric = share_with.params, share_with.grads, share_with.symmetric
+        elif symmetric:
             import torch.distributed._symmetric_memory as symm_mem
             self.params = symm_mem.empty(self.n, dtype=torch.float32, device=dev)
             self.grads = symm_mem.empty(self.n, dtype=torch.float32, device=dev)

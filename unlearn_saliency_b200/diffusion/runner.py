@@ -175,6 +175,32 @@ class DDPMEngineUnlearner:
         from .engine import DDPMLoss
         self.loss_k = DDPMLoss(self.betas, engine.ctx)   # q-sample, eps losses and dL/d(eps) as kernels
         self._w_cache = {}
+        # The no-grad pseudo-label pass (:561-569) is independent of the main forward until the loss: a forward-only
+        # replica of the engine (same parameter arena, own activations) runs it on a second stream so that its HBM-bound
+        # kernels overlap the main pass' tensor-core kernels and vice versa.  SALUN_DDPM_OVERLAP=0 keeps one stream.
+        self._pseudo_engine, self._pseudo_stream = None, None
+        self._overlap = os.environ.get("SALUN_DDPM_OVERLAP", "1") != "0"
+
+    def _pseudo_forward(self, xt_f, tf_f, c_p, drop_p, train, seed):
+        eng = self.engine
+        if not self._overlap:
+            return eng.forward(xt_f, tf_f, c_p, drop=drop_p, save=False, train=train, seed=seed)
+        if self._pseudo_engine is None or self._pseudo_engine.max_batch < xt_f.shape[0]:
+            from .engine import UNetEngine
+            self._pseudo_engine = UNetEngine(eng.config, max_batch=max(xt_f.shape[0], 8), share_with=eng)
+            self._pseudo_stream = torch.cuda.Stream(self.device)
+        cur = torch.cuda.current_stream(self.device)
+        self._pseudo_stream.wait_stream(cur)            # x_t, t, labels are ready
+        with torch.cuda.stream(self._pseudo_stream):
+            pseudo = self._pseudo_engine.forward(xt_f, tf_f, c_p, drop=drop_p, save=False, train=train, seed=seed)
+        for tns in (xt_f, tf_f, c_p, drop_p, pseudo):
+            if tns is not None:
+                tns.record_stream(self._pseudo_stream)
+        return pseudo
+
+    def _pseudo_join(self):
+        if self._overlap and self._pseudo_stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._pseudo_stream)
 
     def _weights(self, nr, nf, alpha, method, chw, scale):
         """per-sample loss weights: loss = sum_i w_i * sum_chw (eps_i - target_i)^2  (losses.py:33-37, diffusion.py:552-572)"""
@@ -266,14 +292,11 @@ class DDPMEngineUnlearner:
         drop_r, drop_f = self._drop(rng, "drop_r", nr, p_drop), self._drop(rng, "drop_f", nf, p_drop)
         self._step += 1
         seed = int(rng.get("seed", self._step)) * 2
+        pseudo = None
         if method == "rl":
             drop_p = self._drop(rng, "drop_p", nf, p_drop)
-            pseudo = eng.forward(xt[nr:], tf[nr:], (cf + 1) % n_classes, drop=drop_p, save=False,
-                                 train=train, seed=seed + 1)                                       # :561-569 (no grad)
-            target = torch.cat([e[:nr], pseudo])
-        elif method == "ga":
-            target = e
-        else:
+            pseudo = self._pseudo_forward(xt[nr:], tf[nr:], (cf + 1) % n_classes, drop_p, train, seed + 1)   # :561-569 (no grad)
+        elif method != "ga":
             raise NotImplementedError(method)
         if drop_r is None and drop_f is None:
             drop = None
@@ -281,6 +304,11 @@ class DDPMEngineUnlearner:
             z = lambda k: torch.zeros(k, dtype=torch.uint8, device=dev)
             drop = torch.cat([drop_r if drop_r is not None else z(nr), drop_f if drop_f is not None else z(nf)])
         eps = eng.forward(xt, tf, torch.cat([cr, cf]), drop=drop, save=True, train=train, seed=seed)
+        if pseudo is not None:
+            self._pseudo_join()
+            target = torch.cat([e[:nr], pseudo])
+        else:
+            target = e
         # loss = forget_loss + alpha * remain_loss (:533-572) and dL/d(eps), one kernel; the NCCL path averages the
         # gradient by pre-scaling dL/d(eps) with 1/W (the fused DP step averages inside its reduce kernel)
         scale = 1.0 / W if (W > 1 and not self.fused_dp) else 1.0
