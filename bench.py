@@ -198,11 +198,15 @@ def bench_ddpm(args, dev, rank, world, L, timed, tf_peak, peak_src):
     ms_e2e = timed(it_e2e, steps) / steps
     roof = None
     # instrumented replay on EVERY rank (the iteration contains the gradient all-reduce); rank 0 reports
+    # (single stream for the replay: with the pseudo-label pass overlapped on a second stream the per-launch events would
+    # also time the other stream's kernels)
+    un._overlap = False
     L.salun_profile_begin()
     for i in range(min(steps, 3)):
         it_resident(i)
     pm, pc, pf = (C.c_double * 2)(), (C.c_int64 * 2)(), (C.c_double * 2)()
     L.salun_profile_end(pm, pc, pf)
+    un._overlap = True
     if rank == 0:
         k = min(steps, 3)
         ach = [pf[c] / (pm[c] * 1e-3) / 1e12 if pm[c] > 0 else 0.0 for c in range(2)]
@@ -211,6 +215,8 @@ def bench_ddpm(args, dev, rank, world, L, timed, tf_peak, peak_src):
                 # one launch of the 128->128 3x3 convolution at 32x32, batch 256 (profiles/r1_ncu_full_unet_conv128.csv):
                 # 76.1 MB read = the padded activation once, 23.6 MB written before the kernel retired (output 67 MB)
                 "traffic": 99716352, "traffic_unit": "bytes per launch (ncu --set full, profiles/r1_ncu_full_unet_conv128.csv)",
+                "how": "CUDA events around every launch of the kernel category, 3 instrumented single-stream iterations "
+                       "replayed after the timed region",
                 "peak_source": peak_src, "avg_launch_us": pm[0] * 1e3 / max(1, pc[0]), "launches_per_it": pc[0] / k,
                 "share_of_it": pm[0] / k / ms,
                 "other": {"kernel": "k_wgrad (side stream)", "achieved": ach[1], "share_of_it": pm[1] / k / ms}}
@@ -221,6 +227,7 @@ def bench_ddpm(args, dev, rank, world, L, timed, tf_peak, peak_src):
            "config": {"workload": "DDPM U-Net CIFAR-10 32x32 saliency_unlearn iteration (runners/diffusion.py:519-593), "
                                   "method rl, alpha 1e-3, dropout 0.1, cond_drop 0.1, mask ratio 0.5, clip 1.0, Adam 1e-4",
                       "per_gpu_batch": [B, B], "params": eng.n,
+                      "streams": "pseudo-label pass on a second stream (forward-only engine replica), wgrad on a side stream",
                       "collective": ("none" if world == 1 else
                                      "fused reduce-scatter + global-norm clip + mask + Adam + all-gather over NVLink peer memory "
                                      "(two kernels around one barrier, optimizer state sharded)" if un.fused_dp else
