@@ -30,6 +30,33 @@ def tiny_config():
     )
 
 
+def small_config():
+    """two levels with a channel change: nin_shortcut (128 -> 256), a 384-wide skip concatenation whose GroupNorm groups
+    straddle the concat boundary, strided-conv down / nearest up sampling, attention with 64 tokens"""
+    return SimpleNamespace(
+        model=SimpleNamespace(type="conditional", in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2], num_res_blocks=1,
+                              attn_resolutions=[8], dropout=0.0, resamp_with_conv=True, cond_drop_prob=0.1),
+        data=SimpleNamespace(image_size=16, channels=3, n_classes=10),
+        diffusion=SimpleNamespace(beta_schedule="linear", beta_start=1e-4, beta_end=0.02, num_diffusion_timesteps=1000),
+    )
+
+
+def default_init_weights(model, seed=0):
+    """PyTorch-default-scale weights (uniform +-1/sqrt(fan_in)) from a seeded formula, norms 1 +- 0.1, biases +-0.05:
+    keeps activations O(1) through the deeper config (synth_weights' 0.1 * randn grows them by ~3x per conv)"""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, v in model.state_dict().items():
+        if "norm" in k and k.endswith("weight"):
+            sd[k] = 1.0 + 0.1 * torch.randn(v.shape, generator=g)
+        elif k.endswith("bias") or v.dim() == 1:
+            sd[k] = 0.05 * torch.randn(v.shape, generator=g)
+        else:
+            fan_in = v[0].numel()
+            sd[k] = (torch.rand(v.shape, generator=g) * 2 - 1) / fan_in ** 0.5
+    return sd
+
+
 def synth_weights(model, seed=0):
     g = torch.Generator().manual_seed(seed)
     sd = {}
@@ -87,6 +114,33 @@ def main():
     out["numel_full"] = np.int64(sum(p.numel() for p in full.parameters()))
     np.savez_compressed(os.path.join(HERE, "ddpm_tiny.npz"), **out)
     print("ddpm_tiny.npz loss", out["loss"], "keys", len(out["keys_tiny"]), len(out["keys_full"]), out["numel_full"])
+    main_small(Conditional_Model, noise_estimation_loss_conditional, betas)
+
+
+def main_small(Conditional_Model, noise_estimation_loss_conditional, betas):
+    """ddpm_small.npz: the channel-changing config (small_config) -- eps in "train" mode with externally chosen
+    class-dropout decisions reproduced through cond_drop_prob in {0, 1} per half, the eps loss, every parameter's gradient
+    norm and sampled gradient entries, from the UNMODIFIED reference model."""
+    cfg = small_config()
+    model = Conditional_Model(cfg)
+    model.load_state_dict(default_init_weights(model))
+    model.eval()
+    x0, e, t, c = inputs(seed=2, n=4, size=16)
+    a = (1 - betas).cumprod(dim=0).index_select(0, t).view(-1, 1, 1, 1)
+    xt = x0 * a.sqrt() + e * (1.0 - a).sqrt()
+    out = {}
+    out["eps_cond"] = model(xt, t.float(), c, mode="train", cond_drop_prob=0.0).detach().numpy()
+    out["eps_null"] = model(xt, t.float(), c, mode="train", cond_drop_prob=1.0).detach().numpy()
+    model.zero_grad()
+    loss = noise_estimation_loss_conditional(model, x0, t, c, e, betas, cond_drop_prob=0.0)
+    loss.backward()
+    out["loss"] = np.float32(loss.item())
+    grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in model.parameters()]
+    out["gnorm"] = np.array([g.norm().item() for g in grads])
+    out["gsample"] = np.concatenate([g.flatten()[sample_idx(g.numel())].numpy() for g in grads])
+    out["keys"] = np.array([n for n, _ in model.named_parameters()])
+    np.savez_compressed(os.path.join(HERE, "ddpm_small.npz"), **out)
+    print("ddpm_small.npz loss", out["loss"], "keys", len(out["keys"]), "max |eps|", np.abs(out["eps_cond"]).max())
 
 
 if __name__ == "__main__":

@@ -47,3 +47,30 @@ def test_unet_forward_loss_backward_equal_reference():
     np.testing.assert_allclose(np.array([g.norm().item() for g in grads]), z["gnorm"], rtol=1e-3, atol=1e-6)
     gs = np.concatenate([g.flatten()[sample_idx(g.numel())].numpy() for g in grads])
     np.testing.assert_allclose(gs, z["gsample"], rtol=1e-2, atol=1e-4)
+
+
+def test_unet_channel_changing_config_equals_reference():
+    """tests/golden/ddpm_small.npz (made from the UNMODIFIED reference): nin_shortcut, the 384-wide skip concatenation whose
+    GroupNorm groups straddle the concat boundary, strided down / nearest up sampling, attention with 64 tokens"""
+    from tests.golden.make_golden_ddpm import default_init_weights, small_config
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ddpm_small.npz"))
+    model = ConditionalUNet(small_config())
+    assert [n for n, _ in model.named_parameters()] == list(z["keys"])
+    model.load_state_dict(default_init_weights(model))
+    model.eval()
+    x0, e, t, c = inputs(seed=2, n=4, size=16)
+    betas = torch.from_numpy(get_beta_schedule("linear", beta_start=1e-4, beta_end=0.02, num_diffusion_timesteps=1000)).float()
+    xt = q_sample(x0, t, e, betas)
+    np.testing.assert_allclose(model(xt, t.float(), c, mode="train", cond_drop_prob=0.0).detach().numpy(), z["eps_cond"],
+                               rtol=1e-4, atol=1e-5)
+    drop = torch.ones(4, dtype=torch.bool)
+    np.testing.assert_allclose(model(xt, t.float(), c, mode="train", drop_mask=drop).detach().numpy(), z["eps_null"],
+                               rtol=1e-4, atol=1e-5)
+    model.zero_grad()
+    loss = eps_loss(model, x0, t, c, e, betas, cond_drop_prob=0.0)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), z["loss"], rtol=1e-5)
+    grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in model.parameters()]
+    np.testing.assert_allclose(np.array([g.norm().item() for g in grads]), z["gnorm"], rtol=1e-3, atol=1e-6)
+    gs = np.concatenate([g.flatten()[sample_idx(g.numel())].numpy() for g in grads])
+    np.testing.assert_allclose(gs, z["gsample"], rtol=1e-2, atol=1e-5)

@@ -455,3 +455,36 @@ def test_q_sample_and_loss_kernels_match_torch(salun_ctx):
         torch.testing.assert_close(loss[0], loss_ref.detach(), rtol=2e-5, atol=1e-7)
         torch.testing.assert_close(d, eps.grad, rtol=1e-5, atol=1e-9)
         torch.testing.assert_close(ss, (eps.detach() - target).square().sum(dim=(1, 2, 3)), rtol=1e-5, atol=1e-6)
+
+
+def test_engine_matches_reference_golden_channel_changing_config(salun_ctx):
+    """tests/golden/ddpm_small.npz -- outputs of the UNMODIFIED reference on the config with nin_shortcut, the 384-wide
+    skip concat, down / up sampling and 64-token attention -- against the engine directly"""
+    from tests.golden.make_golden_ddpm import default_init_weights, small_config as golden_small
+    from unlearn_saliency_b200.diffusion.engine import DDPMLoss, UNetEngine
+    from unlearn_saliency_b200.diffusion.runner import get_beta_schedule
+    from unlearn_saliency_b200.diffusion.unet import ConditionalUNet
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ddpm_small.npz"))
+    cfg = golden_small()
+    eng = UNetEngine(cfg, max_batch=8, ctx=salun_ctx).eval()
+    assert eng.names == list(z["keys"])
+    eng.load_state_dict(default_init_weights(ConditionalUNet(cfg)))
+    x0, e, t, c = inputs(seed=2, n=4, size=16)
+    betas = torch.from_numpy(get_beta_schedule("linear", beta_start=1e-4, beta_end=0.02, num_diffusion_timesteps=1000)).float()
+    L = DDPMLoss(betas, salun_ctx)
+    xt = L.q_sample(x0.cuda(), e.cuda(), t.cuda(), rescale=False)
+    n = 4
+    tf, cc = t.float().cuda(), c.cuda()
+    zeros, ones = torch.zeros(n, dtype=torch.uint8, device="cuda"), torch.ones(n, dtype=torch.uint8, device="cuda")
+    eps2 = eng.forward(torch.cat([xt, xt]), torch.cat([tf, tf]), torch.cat([cc, cc]), drop=torch.cat([zeros, ones]))
+    assert rel(eps2[:n], torch.from_numpy(z["eps_cond"]).cuda()) < 0.02
+    assert rel(eps2[n:], torch.from_numpy(z["eps_null"]).cuda()) < 0.02
+    eps = eng.forward(xt, tf, cc, drop=zeros, save=True)
+    loss, d, _ = L.loss_grad(eps, e.cuda(), torch.full((n,), 1.0 / n, device="cuda"))
+    assert abs(float(loss) - float(z["loss"])) < 0.02 * float(z["loss"])
+    eng.backward(d)
+    gn = np.array([float(g.norm()) for g in eng.grad_dict().values()])
+    ref_gn = z["gnorm"]
+    big = ref_gn > 1e-3 * ref_gn.max()
+    assert np.all(np.abs(gn[big] - ref_gn[big]) <= 0.08 * ref_gn[big]), np.abs(gn[big] / ref_gn[big] - 1).max()
+    eng.close()
