@@ -313,6 +313,7 @@ int salun_unet_destroy(salun_unet *net);
 
 /* eps = model._forward(x, t, c) for n samples.
  *   x    : fp32 NCHW [n][3][S][S] (x_t)          t : fp32 [n] (the reference passes t.float())       c : int64 [n]
+ *          (labels in [0, n_classes); out-of-range labels are clamped instead of reading outside the embedding table)
  *   drop : optional uint8 [n]; 1 = the class embedding of that sample is replaced by null_classes_emb
  *          (diffusion.py:372-376; the caller draws the cond_drop_prob decisions, or passes all-ones for the null pass
  *          of _forward_with_cond_scale :340-355).  NULL = keep every class embedding.
@@ -330,10 +331,11 @@ int salun_unet_backward(salun_unet *net, const float *d_eps, int accumulate, voi
 /* x_t = x0 * sqrt_abar[t] + e * sqrt_1m_abar[t], x0 = rescale ? 2 * x01 - 1 : x01          (n samples of chw floats)
  * replaces  data_transform (DDPM/datasets/__init__.py:241-255) and the q-sample of DDPM/functions/losses.py:31-32 /
  *           runners/diffusion.py:558-559, :971-973.  sqrt_abar / sqrt_1m_abar: device tables over the T timesteps
- *           ((1 - betas).cumprod(0).sqrt() and (1 - cumprod).sqrt(), fp32).  Same rounding sequence as the torch
- *           statements: bit-identical. */
+ *           ((1 - betas).cumprod(0).sqrt() and (1 - cumprod).sqrt(), fp32; num_timesteps entries, t is clamped into
+ *           them).  Same rounding sequence as the torch statements: bit-identical. */
 int salun_ddpm_q_sample(salun_ctx *ctx, const float *x01, const float *e, const int64_t *t, const float *sqrt_abar,
-                        const float *sqrt_1m_abar, int rescale, int n, int chw, float *x_t, void *stream);
+                        const float *sqrt_1m_abar, int num_timesteps, int rescale, int n, int chw, float *x_t,
+                        void *stream);
 /* The eps-prediction losses of an iteration and their gradient w.r.t. eps in one pass:
  *   sumsq_ps[i] = sum_chw (eps[i] - target[i])^2 ;  d_eps[i] = 2 * w[i] * (eps[i] - target[i]) ;  loss = sum_i w[i] * sumsq_ps[i]
  * replaces  noise_estimation_loss_conditional (losses.py:33-37: target = e, w = alpha / n for the remain batch, -1 / n for

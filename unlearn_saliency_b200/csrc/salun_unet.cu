@@ -649,7 +649,7 @@ static int emb_forward(salun_unet *net, const UPlan &plan, int n, bool save, cud
   const int ch = net->cfg.ch, E4 = net->emb, E8 = net->emb + 512;
   const float *P = net->params;
   launch_emb_inputs(net->t_dev, net->c_dev, net->have_drop ? net->drop_dev : nullptr, P + net->cew, P + net->null_off,
-                    net->sincos, net->ce, n, ch, st);
+                    net->sincos, net->ce, n, ch, net->cfg.n_classes, st);
   launch_sgemm(net->sincos, ch, 1, P + net->t0w, 1, ch, net->pre_t, E4, n, E4, ch, P + net->t0b, 0, st);
   launch_swish_f32(net->pre_t, net->h_t, (long long)n * E4, st);
   launch_sgemm(net->h_t, E4, 1, P + net->t1w, 1, E4, net->cat, E8, n, E4, E4, P + net->t1b, 0, st);
@@ -1172,12 +1172,13 @@ int salun_unet_backward(salun_unet *net, const float *d_eps, int accumulate, voi
 }
 
 int salun_ddpm_q_sample(salun_ctx *ctx, const float *x01, const float *e, const int64_t *t, const float *sqrt_abar,
-                        const float *sqrt_1m_abar, int rescale, int n, int chw, float *x_t, void *stream) {
+                        const float *sqrt_1m_abar, int num_timesteps, int rescale, int n, int chw, float *x_t,
+                        void *stream) {
   SALUN_REQUIRE(ctx && x01 && e && t && sqrt_abar && sqrt_1m_abar && x_t, "NULL argument");
-  SALUN_REQUIRE(n >= 0 && chw > 0, "bad sizes");
+  SALUN_REQUIRE(n >= 0 && chw > 0 && num_timesteps > 0, "bad sizes");
   if (n == 0) return SALUN_OK;
   SALUN_CUDA_OK(cudaSetDevice(ctx->device));
-  launch_q_sample(x01, e, t, sqrt_abar, sqrt_1m_abar, rescale, n, chw, x_t, (cudaStream_t)stream);
+  launch_q_sample(x01, e, t, sqrt_abar, sqrt_1m_abar, num_timesteps, rescale, n, chw, x_t, (cudaStream_t)stream);
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;
 }

@@ -856,7 +856,7 @@ void launch_transpose(const bf16 *in, int ld_in, bf16 *out, int R, int Cc, int G
 // =================================================================================================================
 __global__ void k_emb_inputs(const float *__restrict__ t, const int64_t *__restrict__ c, const uint8_t *__restrict__ drop,
                              const float *__restrict__ class_emb, const float *__restrict__ null_emb,
-                             float *__restrict__ sincos, float *__restrict__ ce, int n, int ch) {
+                             float *__restrict__ sincos, float *__restrict__ ce, int n, int ch, int n_classes) {
   const int i = blockIdx.x, d = threadIdx.x;
   if (d >= ch) return;
   const int half = ch / 2;
@@ -865,11 +865,13 @@ __global__ void k_emb_inputs(const float *__restrict__ t, const int64_t *__restr
   const float ang = t[i] * expf((float)j * k);
   sincos[(size_t)i * ch + d] = d < half ? sinf(ang) : cosf(ang);
   const bool dr = drop && drop[i];
-  ce[(size_t)i * ch + d] = dr ? null_emb[d] : class_emb[(size_t)c[i] * ch + d];
+  long long ci = c[i];  // an out-of-range label must not read outside the embedding table
+  ci = ci < 0 ? 0 : (ci >= n_classes ? n_classes - 1 : ci);
+  ce[(size_t)i * ch + d] = dr ? null_emb[d] : class_emb[(size_t)ci * ch + d];
 }
 void launch_emb_inputs(const float *t, const int64_t *c, const uint8_t *drop, const float *class_emb,
-                       const float *null_emb, float *sincos, float *ce, int n, int ch, cudaStream_t st) {
-  k_emb_inputs<<<n, ch, 0, st>>>(t, c, drop, class_emb, null_emb, sincos, ce, n, ch);
+                       const float *null_emb, float *sincos, float *ce, int n, int ch, int n_classes, cudaStream_t st) {
+  k_emb_inputs<<<n, ch, 0, st>>>(t, c, drop, class_emb, null_emb, sincos, ce, n, ch, n_classes);
   ++g_launch_count;
 }
 // 32 x 32 tile, 32-deep k steps, 2 x 2 outputs per thread: the embedding MLPs are 256 x 512 x 512 and smaller, so small
@@ -1044,20 +1046,21 @@ void launch_f32_to_bf16(const float *in, int ld_in, bf16 *out, int ld_out, int r
 // sequence as torch (separately rounded multiplies and adds, no contraction) -> bit-identical to the reference statements
 __global__ void __launch_bounds__(256) k_q_sample(const float *__restrict__ x01, const float *__restrict__ e,
                                                   const int64_t *__restrict__ t, const float *__restrict__ sa,
-                                                  const float *__restrict__ sb, int rescale, long long total, int chw,
-                                                  float *__restrict__ xt) {
+                                                  const float *__restrict__ sb, int num_t, int rescale, long long total,
+                                                  int chw, float *__restrict__ xt) {
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const int n = (int)(i / chw);
-    const int tt = (int)t[n];
+    long long tl = t[n];  // an out-of-range timestep must not read outside the schedule tables
+    const int tt = (int)(tl < 0 ? 0 : (tl >= num_t ? num_t - 1 : tl));
     float x0 = x01[i];
     if (rescale) x0 = __fadd_rn(__fmul_rn(2.0f, x0), -1.0f);
     xt[i] = __fadd_rn(__fmul_rn(x0, sa[tt]), __fmul_rn(e[i], sb[tt]));
   }
 }
 void launch_q_sample(const float *x01, const float *e, const int64_t *t, const float *sqrt_abar, const float *sqrt_1m_abar,
-                     int rescale, int n, int chw, float *xt, cudaStream_t st) {
+                     int num_t, int rescale, int n, int chw, float *xt, cudaStream_t st) {
   const long long total = (long long)n * chw;
-  k_q_sample<<<grid_for(total), 256, 0, st>>>(x01, e, t, sqrt_abar, sqrt_1m_abar, rescale, total, chw, xt);
+  k_q_sample<<<grid_for(total), 256, 0, st>>>(x01, e, t, sqrt_abar, sqrt_1m_abar, num_t, rescale, total, chw, xt);
   ++g_launch_count;
 }
 // per sample: ss[n] = sum_chw (eps - target)^2 ; d_eps = 2 * w[n] * (eps - target)

@@ -85,7 +85,7 @@ void launch_transpose(const __nv_bfloat16 *in, int ld_in, __nv_bfloat16 *out, in
 // ---- embedding MLPs (fp32, CUDA cores; tiny) ----
 // sincos[n][ch] (get_timestep_embedding, diffusion.py:17-35) and ce[n][ch] = drop[n] ? null_emb : class_emb[c[n]]
 void launch_emb_inputs(const float *t, const int64_t *c, const uint8_t *drop, const float *class_emb,
-                       const float *null_emb, float *sincos, float *ce, int n, int ch, cudaStream_t st);
+                       const float *null_emb, float *sincos, float *ce, int n, int ch, int n_classes, cudaStream_t st);
 // C[i][j] (=|+=) sum_k A[i*sai + k*sak] * B[k*sbk + j*sbj] (+ bias[j])
 void launch_sgemm(const float *A, long long sai, long long sak, const float *B, long long sbk, long long sbj, float *C,
                   int ldc, int M, int N, int K, const float *bias, int accumulate, cudaStream_t st);
@@ -111,7 +111,7 @@ void launch_f32_to_bf16(const float *in, int ld_in, __nv_bfloat16 *out, int ld_o
 
 // ---- q-sample and eps-prediction losses (functions/losses.py:21-37, runners/diffusion.py:533-572) ----
 void launch_q_sample(const float *x01, const float *e, const int64_t *t, const float *sqrt_abar, const float *sqrt_1m_abar,
-                     int rescale, int n, int chw, float *xt, cudaStream_t st);
+                     int num_t, int rescale, int n, int chw, float *xt, cudaStream_t st);
 // ss[n] = sum_chw (eps - target)^2 ; d_eps = 2 w[n] (eps - target) ; loss = sum_n w[n] ss[n]
 void launch_eps_loss_grad(const float *eps, const float *target, const float *w, int n, int chw, float *d_eps, float *ss,
                           float *loss, cudaStream_t st);

@@ -43,7 +43,7 @@ _lib.register_signatures({
     "salun_unet_num_tensors": [_P],
     "salun_unet_tensor_info": [_P, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "salun_unet_export_tensor": [_P, C.c_int, C.c_int, _P, _P],
-    "salun_ddpm_q_sample": [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P],
+    "salun_ddpm_q_sample": [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P],
     "salun_ddpm_eps_loss_grad": [_P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P],
 }, {"salun_unet_param_count": C.c_int64})
 
@@ -68,7 +68,8 @@ class DDPMLoss:
         out = torch.empty_like(x01)
         n = x01.shape[0]
         check(self._lib.salun_ddpm_q_sample(self.ctx.handle, _ptr(x01), _ptr(e), _ptr(t), _ptr(self.sqrt_abar),
-                                            _ptr(self.sqrt_1m_abar), 1 if rescale else 0, n, x01.numel() // max(n, 1),
+                                            _ptr(self.sqrt_1m_abar), int(self.sqrt_abar.numel()), 1 if rescale else 0, n,
+                                            x01.numel() // max(n, 1),
                                             _ptr(out), _stream(self.device)), "salun_ddpm_q_sample")
         return out
 
