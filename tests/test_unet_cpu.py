@@ -85,3 +85,90 @@ def test_sd_train_method_selection():
     assert sel("selflayer") == ["input_blocks.4.1.transformer_blocks.0.attn1.to_q.weight",
                                 "input_blocks.7.1.transformer_blocks.0.attn1.to_v.weight"]
     assert sel("nonsense") == []
+
+
+class _FakeSaliency:
+    def __init__(self):
+        self.reduced, self.saved = 0, []
+
+    def all_reduce(self):
+        self.reduced += 1
+
+    def save(self, path, ratio, key_prefix=""):
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        open(path, "wb").write(b"mask")
+        self.saved.append((path, ratio, key_prefix))
+        return "info"
+
+    def mask(self, ratio, key_prefix=""):
+        return {}, "info"
+
+
+class _FakeUnlearner:
+    """stands in for DDPMEngineUnlearner: records the control flow of the Diffusion mirror (no GPU)"""
+    instances = []
+
+    def __init__(self, eng, betas, **kw):
+        self.kw, self.batches, self.steps, self.ckpts = kw, [], [], []
+        self.saliency, self.fused_dp = _FakeSaliency(), False
+        _FakeUnlearner.instances.append(self)
+
+    def generate_mask_batch(self, x, c, cond_scale=2.0):
+        self.batches.append(int(x[0, 0, 0, 0] * 1000))
+
+    def saliency_unlearn_step(self, rx, rc, fx, fc, alpha, method, n_classes):
+        import torch
+        self.steps.append((tuple(rx.shape), tuple(fx.shape), alpha, method, n_classes))
+        return torch.tensor(0.5)
+
+    def save_checkpoint(self, path, step, write=True):
+        self.ckpts.append((path, step, write))
+
+
+def _fake_runner(monkeypatch, tmp_path, rank_world):
+    import torch
+    from types import SimpleNamespace
+    from torch.utils.data import DataLoader, TensorDataset
+    from unlearn_saliency_b200.diffusion import runner
+    _FakeUnlearner.instances.clear()
+    monkeypatch.setattr(runner, "DDPMEngineUnlearner", _FakeUnlearner)
+    monkeypatch.setattr(runner, "_rank_world", lambda: rank_world)
+    monkeypatch.setattr(runner.Diffusion, "_engine", lambda self, mb: SimpleNamespace(close=lambda: None,
+                                                                                       state_dict=lambda prefix="": {}))
+    monkeypatch.chdir(tmp_path)
+    cfg = tiny_config()
+    cfg.training = SimpleNamespace(batch_size=2, n_iters=5, snapshot_freq=2, log_freq=1)
+    cfg.optim = SimpleNamespace(weight_decay=0.0, lr=1e-4, beta1=0.9, eps=1e-8, grad_clip=1.0)
+    cfg.ckpt_dir = str(tmp_path / "ckpts")
+    x = torch.arange(6).float().view(6, 1, 1, 1).expand(6, 3, 8, 8) / 1000.0     # batch i starts with image 2i
+    forget = DataLoader(TensorDataset(x, torch.zeros(6, dtype=torch.long)), batch_size=2)
+    remain = DataLoader(TensorDataset(x, torch.ones(6, dtype=torch.long)), batch_size=2)
+    args = SimpleNamespace(ckpt_folder="ck", label_to_forget=4, cond_scale=2.0, mask_path=None, alpha=1e-3, method="rl", seed=7)
+    return runner.Diffusion(args, cfg, device="cpu", loaders=(remain, forget)), cfg
+
+
+def test_diffusion_mirror_control_flow_single_process(monkeypatch, tmp_path):
+    r, cfg = _fake_runner(monkeypatch, tmp_path, (0, 1))
+    r.generate_mask()
+    un = _FakeUnlearner.instances[-1]
+    assert un.batches == [0, 2, 4] and un.saliency.reduced == 1          # every forget batch, one all-reduce
+    assert un.saliency.saved == [(os.path.join("results/cifar10/mask", "4", "with_0.5.pt"), 0.5, "module.")]
+    assert r.saliency_unlearn() == 0.5
+    un = _FakeUnlearner.instances[-1]
+    assert len(un.steps) == 5 and un.steps[0] == ((2, 3, 8, 8), (2, 3, 8, 8), 1e-3, "rl", 10)
+    assert un.ckpts == [(os.path.join(cfg.ckpt_dir, "ckpt.pth"), 1, True), (os.path.join(cfg.ckpt_dir, "ckpt.pth"), 3, True)]
+    assert un.kw["grad_clip"] == 1.0 and un.kw["lr"] == 1e-4 and un.kw["mask"] is None
+
+
+def test_diffusion_mirror_control_flow_rank1_of_2(monkeypatch, tmp_path):
+    """data parallel: whole forget batches are dealt round-robin, every rank joins the all-reduce and the checkpoint
+    gather, only rank 0 writes files"""
+    import torch.distributed as dist
+    monkeypatch.setattr(dist, "barrier", lambda *a, **k: None)
+    r, cfg = _fake_runner(monkeypatch, tmp_path, (1, 2))
+    r.generate_mask()
+    un = _FakeUnlearner.instances[-1]
+    assert un.batches == [2] and un.saliency.reduced == 1 and un.saliency.saved == []
+    r.saliency_unlearn()
+    un = _FakeUnlearner.instances[-1]
+    assert [c[2] for c in un.ckpts] == [False, False] and len(un.steps) == 5

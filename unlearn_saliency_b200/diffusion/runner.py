@@ -321,11 +321,14 @@ class DDPMEngineUnlearner:
         self.opt.step()   # clip_grad_norm_(1.0) BEFORE the mask, grad *= mask, Adam -- one fused pass (:582-593)
         return loss[0]
 
-    def save_checkpoint(self, path: str, step: int):
-        """states = [model_sd, optim_sd, step] like :598-610"""
+    def save_checkpoint(self, path: str, step: int, write: bool = True):
+        """states = [model_sd, optim_sd, step] like :598-610.  Data parallel: call on every rank (the fused DP step keeps
+        only a shard of the Adam moments per rank; they are all-gathered here) with write=True on one of them."""
+        m1, m2 = self.opt.gather_state() if self.fused_dp else (self.opt.exp_avg, self.opt.exp_avg_sq)
+        if not write:
+            return
         os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
         sd = self.engine.state_dict(prefix="module.")
-        m1, m2 = self.opt.gather_state() if self.fused_dp else (self.opt.exp_avg, self.opt.exp_avg_sq)
         optim = {"exp_avg": self.engine.dict_from_flat(m1), "exp_avg_sq": self.engine.dict_from_flat(m2),
                  "step": self.opt.step_count}
         torch.save([sd, optim, step], path)
@@ -350,6 +353,13 @@ def get_forget_dataset(args, config, label_to_drop):
     bs, nw = config.training.batch_size, getattr(config.data, "num_workers", 0)
     return (DataLoader(remain, batch_size=bs, shuffle=True, num_workers=nw),
             DataLoader(forget, batch_size=bs, shuffle=True, num_workers=nw))
+
+
+def _rank_world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
 
 
 def _cycle(loader):
@@ -402,13 +412,22 @@ class Diffusion:
         un = DDPMEngineUnlearner(eng, self.betas, lr=o.lr, beta1=o.beta1, eps=o.eps, weight_decay=o.weight_decay,
                                  grad_clip=o.grad_clip)
         if getattr(args, "seed", None) is not None:
-            torch.manual_seed(args.seed)
-        for x, forget_c in forget_loader:
+            torch.manual_seed(args.seed)      # the same loader order on every rank
+        rank, world = _rank_world()
+        for i, (x, forget_c) in enumerate(forget_loader):
+            # data parallel: whole batches are dealt round-robin, so the per-batch clip (:985-990)
+            # sees exactly the batches of the single-process run; ONE all-reduce of the accumulator follows
+            if i % world != rank:
+                continue
             un.generate_mask_batch(x, forget_c, cond_scale=args.cond_scale)
         mask_path = os.path.join("results/cifar10/mask", str(args.label_to_forget))     # :1003
         infos = {}
+        un.saliency.all_reduce()
         for i in threshold_list:
-            infos[i] = un.finish_mask(os.path.join(mask_path, f"with_{str(i)}.pt"), ratio=i)
+            path = os.path.join(mask_path, f"with_{str(i)}.pt") if rank == 0 else None   # rank 0 writes the file
+            infos[i] = un.saliency.save(path, i, key_prefix="module.") if path else un.saliency.mask(i, key_prefix="module.")[1]
+        if world > 1:
+            torch.distributed.barrier()
         eng.close()
         return infos
 
@@ -423,8 +442,9 @@ class Diffusion:
                                  grad_clip=o.grad_clip, mask=mask)
         if getattr(config.model, "ema", False):
             raise NotImplementedError("model.ema=True: the SalUn unlearning config sets ema False (cifar10_saliency_unlearn.yml:23)")
+        rank, world = _rank_world()
         if getattr(args, "seed", None) is not None:
-            torch.manual_seed(args.seed)
+            torch.manual_seed(args.seed + rank)   # data parallel: every rank draws its own mini-batches / noise
         import logging
         import time
         start = time.time()
@@ -438,8 +458,9 @@ class Diffusion:
                 logging.info(f"step: {step}, loss: {loss.item()}, time: {time.time() - start}")
                 start = time.time()
             if (step + 1) % config.training.snapshot_freq == 0:
-                un.save_checkpoint(os.path.join(config.ckpt_dir, "ckpt.pth"), step)
-                if self.on_snapshot is not None:
+                # every rank calls (the sharded Adam moments are all-gathered); rank 0 writes the file
+                un.save_checkpoint(os.path.join(config.ckpt_dir, "ckpt.pth"), step, write=(rank == 0))
+                if self.on_snapshot is not None and rank == 0:
                     self.on_snapshot(step, eng.state_dict(prefix="module."))
         eng.close()
         return None if loss is None else float(loss)
