@@ -167,6 +167,11 @@ int salun_dp_masked_adam_step(salun_ctx *ctx, float *const *param_peers_host, co
  * replaces the norm inside clip_grad_norm_   DDPM/runners/diffusion.py:582-587,985-990 */
 int salun_grad_sumsq(salun_ctx *ctx, const float *g, int64_t n, double *sumsq_dev, void *stream);
 
+/* g[i] += alpha * sign(p[i]);  l1_dev[0] = sum_i |p[i]| in double: the gradient and the value of the FT_l1 penalty
+ * alpha * torch.linalg.norm(cat(params), ord=1).
+ * replaces l1_regularization + its autograd   Classification/unlearn/FT.py:13-17,133-134 */
+int salun_l1_penalty_grad(salun_ctx *ctx, const float *p, float *g, int64_t n, float alpha, double *l1_dev, void *stream);
+
 /* coef_dev[0] = min(1, max_norm / (sqrt(sumsq_dev[0]) + 1e-6))   (torch clip_grad_norm_) */
 int salun_clip_coef(salun_ctx *ctx, const double *sumsq_dev, float max_norm, float *coef_dev,
                     void *stream);

@@ -246,9 +246,13 @@ class MaskedSGD:
             self.p[k] = newp
 
 
-def unlearn_step(p, b, opt: MaskedSGD, x, y, sign: float = 1.0, emulate_bf16: bool = False):
-    """one loop body of RL/GA/FT: train-mode forward, backward, mask, SGD, restore. Returns (loss, logits)."""
+def unlearn_step(p, b, opt: MaskedSGD, x, y, sign: float = 1.0, emulate_bf16: bool = False, l1_alpha: float = 0.0):
+    """one loop body of RL/GA/FT: train-mode forward, backward, mask, SGD, restore. Returns (loss, logits).
+    l1_alpha: FT_l1's  loss += alpha * ||theta||_1  (FT.py:13-17,133-134)  =>  grad += alpha * sign(theta) before the mask."""
     loss, out, g = loss_and_grads(p, b, x, y, train=True, sign=sign, emulate_bf16=emulate_bf16)
+    if l1_alpha:
+        g = OrderedDict((k, g[k] + l1_alpha * torch.sign(p[k])) for k in p)
+        loss = loss + l1_alpha * sum(t.abs().sum() for t in p.values())
     opt.step(g)
     return loss, out
 

@@ -229,3 +229,20 @@ void oracle_apply_mask(float *g, const uint32_t *mask_bits, int64_t n) {
     if (!m) g[i] = g[i] * 0.0f;
   }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * FT_l1 penalty.  Classification/unlearn/FT.py:13-17  l1_regularization = ||cat(params)||_1 ;
+ * :133-134  loss += current_alpha * l1_regularization(model)  =>  autograd adds
+ * alpha * sign(theta) (sign(0) = 0) to every gradient BEFORE the mask multiply (:138-139).
+ * Returns sum |theta| (double accumulation; the CUDA path's sum differs only in association).
+ * ------------------------------------------------------------------------------------------ */
+double oracle_l1_penalty_grad(const float *p, float *g, int64_t n, float alpha) {
+  double s = 0.0;
+  for (int64_t i = 0; i < n; ++i) {
+    const float v = p[i];
+    s += (double)fabsf(v);
+    const float sg = v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f);
+    g[i] = g[i] + alpha * sg;
+  }
+  return s;
+}

@@ -111,3 +111,12 @@ def masked_adam_step(p, g, m1, m2, bits, lr, b1, b2, eps, wd, step, clip):
 def apply_mask(g, bits):
     assert g.dtype == np.float32 and g.flags.c_contiguous
     lib().oracle_apply_mask(_p(g), _p(bits), C.c_int64(g.size))
+
+
+def l1_penalty_grad(p: np.ndarray, g: np.ndarray, alpha: float) -> float:
+    """g += alpha * sign(p) in place; returns sum |p| (FT.py:13-17,133-134)."""
+    assert g.dtype == np.float32 and g.flags.c_contiguous
+    pp, ppp = _f32(p)
+    l = lib()
+    l.oracle_l1_penalty_grad.restype = C.c_double
+    return float(l.oracle_l1_penalty_grad(ppp, _p(g), C.c_int64(g.size), C.c_float(alpha)))

@@ -2,7 +2,7 @@
 (same arithmetic up to the summation order inside the norm), replicas bit-identical; then one DDPM iteration through
 DDPMEngineUnlearner on a symmetric engine vs the NCCL path."""
 import datetime, os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch, torch.distributed as dist
 from types import SimpleNamespace
 from unlearn_saliency_b200.diffusion.engine import DistMaskedAdam, UNetEngine

@@ -1,7 +1,7 @@
 """torchrun -N 2: the fused peer-memory DP step against NCCL all-reduce + local masked SGD (same arithmetic up to the
 summation order of the all-reduce), replicas bit-identical."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 os.environ["NCCL_DEBUG"] = "WARN"
 import torch, torch.distributed as dist
 from unlearn_saliency_b200.engine import DistMaskedSGD, MaskedSGD, ResNetEngine

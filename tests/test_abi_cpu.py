@@ -18,13 +18,26 @@ def declared_symbols():
     return names
 
 
-def test_library_exports_every_declared_symbol():
-    lib = _lib.lib()
+import pytest
+
+
+@pytest.mark.parametrize("precision", ["bf16", "split"])
+def test_library_exports_every_declared_symbol(precision):
+    """both builds (libsalun.so, libsalun_split.so: csrc/Makefile) export the whole C ABI"""
+    lib = _lib.lib(precision)
     decl = declared_symbols()
     assert len(decl) >= 15
     for name in sorted(decl):
-        assert hasattr(lib, name), f"{name} declared in include/ but not exported by libsalun.so"
+        assert hasattr(lib, name), f"{name} declared in include/ but not exported by {_lib.LIB_PATHS[precision]}"
     assert lib.salun_version() >= 1000
+
+
+def test_the_two_builds_keep_their_own_kernels():
+    """RTLD_LOCAL + -Bsymbolic: the same symbol resolves to a different address in each library"""
+    a, b = _lib.lib("bf16"), _lib.lib("split")
+    pa = ctypes.cast(a.salun_resnet_forward_backward, ctypes.c_void_p).value
+    pb = ctypes.cast(b.salun_resnet_forward_backward, ctypes.c_void_p).value
+    assert pa != pb
 
 
 def test_bound_symbols_are_declared():

@@ -116,9 +116,11 @@ class _FakeUnlearner:
     def generate_mask_batch(self, x, c, cond_scale=2.0):
         self.batches.append(int(x[0, 0, 0, 0] * 1000))
 
-    def saliency_unlearn_step(self, rx, rc, fx, fc, alpha, method, n_classes):
+    def saliency_unlearn_step(self, rx, rc, fx, fc, alpha, method, n_classes, global_counts=None):
         import torch
         self.steps.append((tuple(rx.shape), tuple(fx.shape), alpha, method, n_classes))
+        self.counts = getattr(self, "counts", []) + [global_counts]
+        self.first = getattr(self, "first", []) + [int(rx[0, 0, 0, 0] * 1000)]
         return torch.tensor(0.5)
 
     def save_checkpoint(self, path, step, write=True):
@@ -172,3 +174,7 @@ def test_diffusion_mirror_control_flow_rank1_of_2(monkeypatch, tmp_path):
     r.saliency_unlearn()
     un = _FakeUnlearner.instances[-1]
     assert [c[2] for c in un.ckpts] == [False, False] and len(un.steps) == 5
+    # ONE global mini-batch of 2 + 2 per iteration, scattered: rank 1 gets the second sample of each (nn.DataParallel
+    # semantics, runners/diffusion.py:505), and the loss means are taken over the global counts
+    assert un.steps[0][:2] == ((1, 3, 8, 8), (1, 3, 8, 8)) and un.counts[0] == (2, 2)
+    assert un.first[:3] == [1, 3, 5]

@@ -1,0 +1,69 @@
+"""The drop-in entry points get_unlearn_method("GA" | "FT" | "FT_l1" | "RL") on the sm_100a engine against weights
+produced by the UNMODIFIED reference (tests/golden/resnet18_gaft.npz, make_golden_gaft.py): same loaders, same 0.5 mask,
+same hyper-parameters.  Masked-out coordinates must be bit-identical to theta0; the update of the masked-in coordinates
+is compared with the reference's update (tolerance per precision mode: see PRECISION_TOL)."""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import classification as OC
+from tests.test_oracle_gaft_cpu import G, gaft_inputs, golden_mask, sample_idx
+
+pytestmark = pytest.mark.gpu
+
+# relative L2 error of the sampled UPDATE (theta - theta0 on mask=1 coordinates) vs the reference's fp32 update, and cosine
+PRECISION_TOL = {"bf16": (0.35, 0.93), "split": (2e-3, 0.99999)}
+
+
+def _args(name, **kw):
+    a = SimpleNamespace(unlearn_lr=0.013, momentum=0.9, weight_decay=5e-4, dataset="cifar10", num_classes=10, warmup=0,
+                        print_freq=1000, unlearn_epochs=1, decreasing_lr="91,136", rewind_epoch=0, imagenet_arch=False,
+                        unlearn=name, batch_size=16, no_l1_epochs=0, alpha=0.0, arch="resnet18", input_size=32, lr=0.1)
+    for k, v in kw.items():
+        setattr(a, k, v)
+    return a
+
+
+def _loaders(k):
+    x, y, xr, yr = gaft_inputs()
+    mk = lambda a, b: torch.utils.data.DataLoader(torch.utils.data.TensorDataset(a[:k], b[:k]), batch_size=16, shuffle=False)
+    return {"forget": mk(x, y), "retain": mk(xr, yr)}
+
+
+@pytest.mark.parametrize("precision", ["bf16", "split"])
+@pytest.mark.parametrize("name,kw", [("GA", {}), ("FT", {}), ("FT_l1", dict(alpha=5e-4, unlearn_epochs=2, no_l1_epochs=0))])
+def test_method_matches_reference_weights(salun_ctx, name, kw, precision):
+    from unlearn_saliency_b200 import _lib
+    from unlearn_saliency_b200.classification.unlearn import get_unlearn_method
+    from unlearn_saliency_b200.engine import ResNetEngine
+    if precision not in _lib.available_precisions():
+        pytest.skip(f"precision {precision} not built")
+    z = np.load(os.path.join(G, "resnet18_gaft.npz"))
+    mask = golden_mask()
+    params, buffers = OC.synth_state(10, seed=0)
+    eng = ResNetEngine("resnet18", 10, 32, max_batch=16, precision=precision)
+    eng.load_state_dict(OC.state_dict_of(params, buffers))
+    get_unlearn_method(name)(_loaders(16), eng, torch.nn.CrossEntropyLoss(), _args(name, **kw),
+                             {k: v.cuda() for k, v in mask.items()})
+    torch.cuda.synchronize()
+    got, ref, p0, msk = [], z[f"{name}_1_psample"], [], []
+    for k, t in params.items():
+        idx = sample_idx(t.numel())
+        e = eng.get_param(k).cpu()
+        assert torch.equal(e[mask[k] == 0], t[mask[k] == 0]), k        # restore is exact (RL.py:17-34)
+        got.append(e.flatten()[idx].numpy())
+        p0.append(t.flatten()[idx].numpy())
+        msk.append(mask[k].flatten()[idx].numpy())
+    got, p0, msk = np.concatenate(got), np.concatenate(p0), np.concatenate(msk).astype(bool)
+    du, dr = (got - p0)[msk], (ref - p0)[msk]
+    rel = float(np.linalg.norm(du - dr) / np.linalg.norm(dr))
+    cos = float(du @ dr / (np.linalg.norm(du) * np.linalg.norm(dr)))
+    print(f"{name} [{precision}]: update rel err {rel:.3e}, cos {cos:.6f}")
+    tol_rel, tol_cos = PRECISION_TOL[precision]
+    assert rel <= tol_rel and cos >= tol_cos, (name, precision, rel, cos)
+    np.testing.assert_allclose(eng.running_mean[:64].cpu().numpy(), z[f"{name}_1_rm_bn1"], rtol=2e-2 if precision == "bf16" else 1e-3,
+                               atol=2e-3 if precision == "bf16" else 5e-5)
+    eng.close()

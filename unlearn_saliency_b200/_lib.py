@@ -10,8 +10,15 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libsalun.so")
+# Two builds of the same sources and the same C ABI (csrc/Makefile):
+#   "bf16"  : activations / tensor-core operands stored as bf16 (the fast path)
+#   "split" : every activation element is a (hi, lo) bf16 pair (16 significand bits) and every product runs as
+#             hi*hi + hi*lo + lo*hi + lo*lo on the tensor cores: fp32-class results for the precision-critical
+#             passes (saliency-mask generation), DESIGN.md section 4
+LIB_PATHS = {"bf16": LIB_PATH, "split": os.path.join(_HERE, "csrc", "libsalun_split.so")}
 
 _lib = None
+_libs: dict = {}
 
 
 class salun_resnet_cfg(C.Structure):
@@ -59,6 +66,7 @@ _SIGNATURES = {
     "salun_dp_masked_adam_step": [_P, C.POINTER(_P), C.POINTER(_P), _P, _P, _P, _P, _I64, C.c_int, C.c_int, _F, _F, _F, _F,
                                   _F, _I64, _F, _P, _P],
     "salun_grad_sumsq": [_P, _P, _I64, _P, _P],
+    "salun_l1_penalty_grad": [_P, _P, _P, _I64, _F, _P, _P],
     "salun_clip_coef": [_P, _P, _F, _P, _P],
     "salun_masked_adam_step": [_P, _P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I64, _P, _P],
     # tcgen05 GEMM / convolution entry points (salun_gemm.cu)
@@ -92,8 +100,8 @@ def register_signatures(sigs: dict, restypes: dict | None = None):
     _EXTRA_SIGNATURES.update(sigs)
     if restypes:
         _RESTYPES.update(restypes)
-    if _lib is not None:
-        _bind(_lib, sigs)
+    for l in _libs.values():
+        _bind(l, sigs)
 
 
 def _bind(lib, sigs):
@@ -103,22 +111,39 @@ def _bind(lib, sigs):
         fn.restype = _RESTYPES.get(name, C.c_int)
 
 
-def lib():
+def available_precisions():
+    """precision modes whose library has been built"""
+    return [k for k, p in LIB_PATHS.items() if os.path.exists(p)]
+
+
+def lib(precision: str = "bf16"):
+    """The library of one precision mode.  The two builds export the same symbols: they are loaded RTLD_LOCAL (and
+    linked -Bsymbolic), so each keeps its own kernels; context handles (plain device workspaces) are interchangeable."""
     global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
+    l = _libs.get(precision)
+    if l is None:
+        if precision not in LIB_PATHS:
+            raise ValueError(f"unknown precision {precision!r} (known: {sorted(LIB_PATHS)})")
+        path = LIB_PATHS[precision]
+        if not os.path.exists(path):
             raise RuntimeError(
-                f"libsalun.so not found at {LIB_PATH}: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"{os.path.basename(path)} not found at {path}: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(or `make -C unlearn_saliency_b200/csrc`). There is no CPU / PyTorch fallback."
             )
-        l = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        l = C.CDLL(path, mode=C.RTLD_LOCAL)
         _bind(l, _SIGNATURES)
         _bind(l, _EXTRA_SIGNATURES)
-        _lib = l
-    return _lib
+        _libs[precision] = l
+        if precision == "bf16":
+            _lib = l
+    return l
 
 
-def check(rc: int, what: str = ""):
+def check(rc: int, what: str = "", lib_=None):
     if rc != 0:
-        msg = lib().salun_last_error()
-        raise RuntimeError(f"libsalun {what} failed (status {rc}): {msg.decode() if msg else '?'}")
+        msgs = []
+        for l in ([lib_] if lib_ is not None else list(_libs.values())):
+            m = l.salun_last_error()
+            if m:
+                msgs.append(m.decode())
+        raise RuntimeError(f"libsalun {what} failed (status {rc}): {' | '.join(msgs) if msgs else '?'}")

@@ -26,9 +26,10 @@ def as_engine(model, args=None, max_batch=None, symmetric: bool = False) -> ResN
     num_classes = sd["fc.weight"].shape[0]
     mean = tuple(float(v) for v in sd.get("normalize.mean", torch.tensor(CIFAR_MEAN)).flatten())
     std = tuple(float(v) for v in sd.get("normalize.std", torch.tensor(CIFAR_STD)).flatten())
-    image = int(getattr(args, "input_size", 32) or 32)
+    imagenet = bool(getattr(args, "imagenet_arch", False))       # models/ResNet.py:224-230 stem (resnet50/101/152)
+    image = int(getattr(args, "input_size", None) or (224 if imagenet else 32))
     mb = int(max_batch or getattr(args, "batch_size", 256) or 256)
-    eng = ResNetEngine(arch, num_classes, image, max_batch=mb, mean=mean, std=std, symmetric=symmetric)
+    eng = ResNetEngine(arch, num_classes, image, max_batch=mb, mean=mean, std=std, symmetric=symmetric, imagenet=imagenet)
     eng.load_state_dict(sd)
     eng.train(model.training)
     eng._source_module = model  # written back by sync_to_module()

@@ -1,5 +1,5 @@
 """mirror of Classification/unlearn/__init__.py:22-61 for the methods on the SalUn hot path."""
-from .FT import FT
+from .FT import FT, FT_l1
 from .GA import GA
 from .RL import RL
 from .impl import iterative_unlearn  # noqa: F401
@@ -19,4 +19,6 @@ def get_unlearn_method(name):
         return GA
     if name == "FT":
         return FT
-    raise NotImplementedError(f"Unlearn method {name} is not on the sm_100a hot path (served: raw, RL, GA, FT)")
+    if name == "FT_l1":
+        return FT_l1
+    raise NotImplementedError(f"Unlearn method {name} is not on the sm_100a hot path (served: raw, RL, GA, FT, FT_l1)")

@@ -5,6 +5,7 @@ import time
 
 from ...engine import DistMaskedSGD, MaskedSGD
 from ..common import as_engine, check_criterion, dist_info, sync_to_module
+from .steps import sync_bn_buffers
 
 
 def _lr_at(base_lr, epoch, milestones, gamma=0.1):
@@ -17,8 +18,6 @@ def _iterative_unlearn_impl(unlearn_iter_func):
         check_criterion(criterion)
         if getattr(args, "rewind_epoch", 0) != 0:
             raise NotImplementedError("weight rewinding (impl.py:58-67, 98-101) is outside the SalUn hot path")
-        if getattr(args, "imagenet_arch", False):
-            raise NotImplementedError("imagenet_arch branches are not served by the CIFAR-stem engine")
         decreasing_lr = list(map(int, args.decreasing_lr.split(",")))
         _, world = dist_info()
         engine = as_engine(model, args, symmetric=world > 1)
@@ -37,6 +36,7 @@ def _iterative_unlearn_impl(unlearn_iter_func):
             print("Epoch #{}, Learning rate: {}".format(epoch, optimizer.param_groups[0]["lr"]))
             train_acc = unlearn_iter_func(data_loaders, engine, criterion, optimizer, epoch, args, mask, **kwargs)
             print("one epoch duration:{}".format(time.time() - start_time))
+        sync_bn_buffers(engine)
         sync_to_module(engine)
         return train_acc
 

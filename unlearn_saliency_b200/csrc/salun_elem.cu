@@ -14,33 +14,6 @@ namespace salun {
 constexpr int kET = 256;
 constexpr int kRedY = 32;  // row lanes of the (32 x kRedY)-thread column-reduction blocks
 
-__device__ __forceinline__ void ld8(const __nv_bfloat16 *p, float (&f)[8]) {
-  uint4 v = *reinterpret_cast<const uint4 *>(p);
-  const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
-}
-__device__ __forceinline__ uint4 ldraw(const __nv_bfloat16 *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
-__device__ __forceinline__ void cvt8(const uint4 &v, float (&f)[8]) {
-  const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
-}
-__device__ __forceinline__ void st8(__nv_bfloat16 *p, const float (&f)[8]) {
-  uint4 v;
-  __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&v);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-  *reinterpret_cast<uint4 *>(p) = v;
-}
 __device__ __forceinline__ size_t pad_off(int m, int H, int W, int C) {
   const int hw = H * W;
   const int n = m / hw, r = m - n * hw;
@@ -133,8 +106,8 @@ __device__ __forceinline__ void bn_prologue(const BnFwd &p, float *sc, float *sh
 }
 
 template <int kU, int kMinB>
-__global__ void __launch_bounds__(kET, kMinB) k_bn_apply(BnFwd a, BnFwd b, int has_b, const __nv_bfloat16 *__restrict__ resid,
-                                                  __nv_bfloat16 *__restrict__ out, uint8_t *__restrict__ rmask, int M,
+__global__ void __launch_bounds__(kET, kMinB) k_bn_apply(BnFwd a, BnFwd b, int has_b, const act_t *__restrict__ resid,
+                                                  act_t *__restrict__ out, uint8_t *__restrict__ rmask, int M,
                                                   int H, int W, int C, int relu, int train, float eps, float momentum) {
   pdl_trigger();
   pdl_wait();
@@ -149,7 +122,7 @@ __global__ void __launch_bounds__(kET, kMinB) k_bn_apply(BnFwd a, BnFwd b, int h
   // SM with ~32 KB in flight, below what HBM3e latency x bandwidth needs (profiles/README.md section 3)
   const int stride = gridDim.x * rpb;
   for (int m0 = blockIdx.x * rpb + rl; m0 < M; m0 += kU * stride) {
-    uint4 ra[kU], rb[kU], rr[kU];
+    avec ra[kU], rb[kU], rr[kU];
     size_t po[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
@@ -209,7 +182,7 @@ static inline int elem_grid(int M, int C, int blocks_per_sm = 8) {
   if (g > 148 * blocks_per_sm) g = 148 * blocks_per_sm;  // = resident blocks: one full wave, no ragged second wave
   return (int)(g < 1 ? 1 : g);
 }
-void launch_bn_apply(const BnFwd &a, const BnFwd *b, const __nv_bfloat16 *resid_padded, __nv_bfloat16 *out_padded,
+void launch_bn_apply(const BnFwd &a, const BnFwd *b, const act_t *resid_padded, act_t *out_padded,
                      uint8_t *relu_mask_out, int n_img, int H, int W, int C, int relu, int train, float eps,
                      float momentum, cudaStream_t st) {
   const int M = n_img * H * W;
@@ -235,9 +208,9 @@ void launch_bn_apply(const BnFwd &a, const BnFwd *b, const __nv_bfloat16 *resid_
 // BN backward
 // ------------------------------------------------------------------------------------------------
 template <int kU>
-__global__ void __launch_bounds__(kET, 2) k_bn_bwd_reduce(const __nv_bfloat16 *__restrict__ dout,
+__global__ void __launch_bounds__(kET, 2) k_bn_bwd_reduce(const act_t *__restrict__ dout,
                                                        const uint8_t *__restrict__ rmask,
-                                                       const __nv_bfloat16 *__restrict__ y,
+                                                       const act_t *__restrict__ y,
                                                        const float *__restrict__ mean, const float *__restrict__ invstd,
                                                        float *__restrict__ partials, int M, int H, int W, int C) {
   pdl_trigger();
@@ -255,7 +228,7 @@ __global__ void __launch_bounds__(kET, 2) k_bn_bwd_reduce(const __nv_bfloat16 *_
   // kU independent loads per trip; rows are still accumulated in ascending order (same sums as kU = 1)
   const int stride = gridDim.x * rpb;
   for (int m0 = blockIdx.x * rpb + rl; m0 < M; m0 += kU * stride) {
-    uint4 rd[kU], ry[kU];
+    avec rd[kU], ry[kU];
     uint32_t rbits[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
@@ -303,7 +276,7 @@ static inline int bwd_rows(int M, int C) {
   int g = (M + rpb - 1) / rpb;
   return g < kBwdPartialRows ? (g < 1 ? 1 : g) : kBwdPartialRows;
 }
-void launch_bn_bwd_reduce(const __nv_bfloat16 *dout, const uint8_t *relu_mask, const __nv_bfloat16 *y,
+void launch_bn_bwd_reduce(const act_t *dout, const uint8_t *relu_mask, const act_t *y,
                           const float *saved_mean, const float *saved_invstd, float *partials, int n_img, int H, int W,
                           int C, cudaStream_t st) {
   const int M = n_img * H * W;
@@ -368,12 +341,12 @@ void launch_bn_bwd_finalize(const float *partials, int rows, int C, const float 
 }
 
 template <int kU, int kMinB>
-__global__ void __launch_bounds__(kET, kMinB) k_bn_bwd_apply(const __nv_bfloat16 *__restrict__ dout,
+__global__ void __launch_bounds__(kET, kMinB) k_bn_bwd_apply(const act_t *__restrict__ dout,
                                                       const uint8_t *__restrict__ rmask,
-                                                      const __nv_bfloat16 *__restrict__ y,
+                                                      const act_t *__restrict__ y,
                                                       const float *__restrict__ mean, const float *__restrict__ invstd,
-                                                      const float *__restrict__ coef, __nv_bfloat16 *__restrict__ dy,
-                                                      int dy_padded, __nv_bfloat16 *__restrict__ dz_flat, int M, int H,
+                                                      const float *__restrict__ coef, act_t *__restrict__ dy,
+                                                      int dy_padded, act_t *__restrict__ dz_flat, int M, int H,
                                                       int W, int C) {
   pdl_trigger();
   pdl_wait();
@@ -390,7 +363,7 @@ __global__ void __launch_bounds__(kET, kMinB) k_bn_bwd_apply(const __nv_bfloat16
   }
   const int stride = gridDim.x * rpb;
   for (int m0 = blockIdx.x * rpb + rl; m0 < M; m0 += kU * stride) {
-    uint4 rd[kU], ry[kU];
+    avec rd[kU], ry[kU];
     uint32_t rbits[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
@@ -417,9 +390,9 @@ __global__ void __launch_bounds__(kET, kMinB) k_bn_bwd_apply(const __nv_bfloat16
     }
   }
 }
-void launch_bn_bwd_apply(const __nv_bfloat16 *dout, const uint8_t *relu_mask, const __nv_bfloat16 *y,
-                         const float *saved_mean, const float *saved_invstd, const float *coef, __nv_bfloat16 *dy,
-                         int dy_padded, __nv_bfloat16 *dz_flat, int n_img, int H, int W, int C, cudaStream_t st) {
+void launch_bn_bwd_apply(const act_t *dout, const uint8_t *relu_mask, const act_t *y,
+                         const float *saved_mean, const float *saved_invstd, const float *coef, act_t *dy,
+                         int dy_padded, act_t *dz_flat, int n_img, int H, int W, int C, cudaStream_t st) {
   const int M = n_img * H * W;
 #define SALUN_BN_BWD_APPLY(U, B)                                                                              \
   ::salun::launch_pdl(k_bn_bwd_apply<U, B>, dim3(elem_grid(M, C, B)), dim3(kET), 0, st, dout, relu_mask, y, saved_mean, saved_invstd, coef, dy, \
@@ -440,7 +413,7 @@ void launch_bn_bwd_apply(const __nv_bfloat16 *dout, const uint8_t *relu_mask, co
 // ------------------------------------------------------------------------------------------------
 // stem / stride-2 patch kernels
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kET) k_stem_im2col(const float *__restrict__ x, __nv_bfloat16 *__restrict__ col, int M,
+__global__ void __launch_bounds__(kET) k_stem_im2col(const float *__restrict__ x, act_t *__restrict__ col, int M,
                                                      int H, int W, float m0, float m1, float m2, float i0, float i1,
                                                      float i2) {
   pdl_trigger();
@@ -466,7 +439,7 @@ __global__ void __launch_bounds__(kET) k_stem_im2col(const float *__restrict__ x
         v[(ky * 3 + kx) * 3 + c] = t;
       }
     }
-  __nv_bfloat16 *dst = col + (size_t)m * 64;
+  act_t *dst = col + (size_t)m * 64;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     float f[8];
@@ -475,14 +448,14 @@ __global__ void __launch_bounds__(kET) k_stem_im2col(const float *__restrict__ x
     st8(dst + 8 * j, f);
   }
 }
-void launch_stem_im2col(const float *x, __nv_bfloat16 *col, int n_img, int H, int W, const float *mean3,
+void launch_stem_im2col(const float *x, act_t *col, int n_img, int H, int W, const float *mean3,
                         const float *inv_std3, cudaStream_t st) {
   const int M = n_img * H * W;
   { ::salun::launch_pdl(k_stem_im2col, dim3((M + kET - 1) / kET), dim3(kET), 0, st, x, col, M, H, W, mean3[0], mean3[1], mean3[2], inv_std3[0],
                                                      inv_std3[1], inv_std3[2]); ++::salun::g_launch_count; }
 }
 
-__global__ void __launch_bounds__(kET) k_im2col_s2(const __nv_bfloat16 *__restrict__ in, __nv_bfloat16 *__restrict__ col,
+__global__ void __launch_bounds__(kET) k_im2col_s2(const act_t *__restrict__ in, act_t *__restrict__ col,
                                                    long long total, int Hin, int Win, int C, int ks) {
   pdl_trigger();
   pdl_wait();
@@ -496,12 +469,11 @@ __global__ void __launch_bounds__(kET) k_im2col_s2(const __nv_bfloat16 *__restri
     const int ky = tap / ks, kx = tap - ky * ks;
     const int off = ks == 3 ? 0 : 1;  // padded coordinates of input pixel (2oy+ky-pad, 2ox+kx-pad)
     const int py = 2 * oy + ky + off, px = 2 * ox + kx + off;
-    const uint4 v =
-        *reinterpret_cast<const uint4 *>(in + ((size_t)(n * (Hin + 2) + py) * (Win + 2) + px) * C + cg * 8);
-    *reinterpret_cast<uint4 *>(col + ((size_t)mo * taps + tap) * C + cg * 8) = v;
+    const avec v = ldvec(in + ((size_t)(n * (Hin + 2) + py) * (Win + 2) + px) * C + cg * 8);
+    stvec(col + ((size_t)mo * taps + tap) * C + cg * 8, v);
   }
 }
-void launch_im2col_s2(const __nv_bfloat16 *in_padded, __nv_bfloat16 *col, int n_img, int Hin, int Win, int C, int ks,
+void launch_im2col_s2(const act_t *in_padded, act_t *col, int n_img, int Hin, int Win, int C, int ks,
                       cudaStream_t st) {
   const long long total = (long long)n_img * (Hin / 2) * (Win / 2) * ks * ks * (C >> 3);
   long long g = (total + kET - 1) / kET;
@@ -509,9 +481,9 @@ void launch_im2col_s2(const __nv_bfloat16 *in_padded, __nv_bfloat16 *col, int n_
   { ::salun::launch_pdl(k_im2col_s2, dim3((int)g), dim3(kET), 0, st, in_padded, col, total, Hin, Win, C, ks); ++::salun::g_launch_count; }
 }
 
-__global__ void __launch_bounds__(kET) k_col2im_s2(const __nv_bfloat16 *__restrict__ dcol3,
-                                                   const __nv_bfloat16 *__restrict__ dcol1,
-                                                   __nv_bfloat16 *__restrict__ dx, long long total, int Hin, int Win,
+__global__ void __launch_bounds__(kET) k_col2im_s2(const act_t *__restrict__ dcol3,
+                                                   const act_t *__restrict__ dcol1,
+                                                   act_t *__restrict__ dx, long long total, int Hin, int Win,
                                                    int C) {
   pdl_trigger();
   pdl_wait();
@@ -548,7 +520,7 @@ __global__ void __launch_bounds__(kET) k_col2im_s2(const __nv_bfloat16 *__restri
     st8(dx + (size_t)m * C + cg * 8, acc);
   }
 }
-void launch_col2im_s2(const __nv_bfloat16 *dcol3, const __nv_bfloat16 *dcol1, __nv_bfloat16 *dx, int n_img, int Hin,
+void launch_col2im_s2(const act_t *dcol3, const act_t *dcol1, act_t *dx, int n_img, int Hin,
                       int Win, int C, cudaStream_t st) {
   const long long total = (long long)n_img * Hin * Win * (C >> 3);
   long long g = (total + kET - 1) / kET;
@@ -559,7 +531,7 @@ void launch_col2im_s2(const __nv_bfloat16 *dcol3, const __nv_bfloat16 *dcol1, __
 // ------------------------------------------------------------------------------------------------
 // generic flat-activation kernels (Bottleneck / ImageNet-stem nets: any H, W, stride, padding)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kET) k_im2col_flat(const __nv_bfloat16 *__restrict__ in, __nv_bfloat16 *__restrict__ col,
+__global__ void __launch_bounds__(kET) k_im2col_flat(const act_t *__restrict__ in, act_t *__restrict__ col,
                                                      long long total, int Hin, int Win, int C, int ks, int stride, int pad,
                                                      int Hout, int Wout) {
   const int cgs = C >> 3, taps = ks * ks;
@@ -571,13 +543,12 @@ __global__ void __launch_bounds__(kET) k_im2col_flat(const __nv_bfloat16 *__rest
     const int n = mo / (Hout * Wout), r = mo - n * Hout * Wout, oy = r / Wout, ox = r - oy * Wout;
     const int ky = tap / ks, kx = tap - ky * ks;
     const int y = oy * stride + ky - pad, x = ox * stride + kx - pad;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (y >= 0 && y < Hin && x >= 0 && x < Win)
-      v = *reinterpret_cast<const uint4 *>(in + ((size_t)(n * Hin + y) * Win + x) * C + cg * 8);
-    *reinterpret_cast<uint4 *>(col + ((size_t)mo * taps + tap) * C + cg * 8) = v;
+    avec v = avec_zero();
+    if (y >= 0 && y < Hin && x >= 0 && x < Win) v = ldvec(in + ((size_t)(n * Hin + y) * Win + x) * C + cg * 8);
+    stvec(col + ((size_t)mo * taps + tap) * C + cg * 8, v);
   }
 }
-void launch_im2col_flat(const __nv_bfloat16 *in_flat, __nv_bfloat16 *col, int n_img, int Hin, int Win, int C, int ks,
+void launch_im2col_flat(const act_t *in_flat, act_t *col, int n_img, int Hin, int Win, int C, int ks,
                         int stride, int pad, int Hout, int Wout, cudaStream_t st) {
   const long long total = (long long)n_img * Hout * Wout * ks * ks * (C >> 3);
   long long g = (total + kET - 1) / kET;
@@ -585,7 +556,7 @@ void launch_im2col_flat(const __nv_bfloat16 *in_flat, __nv_bfloat16 *col, int n_
   { k_im2col_flat<<<(int)g, kET, 0, st>>>(in_flat, col, total, Hin, Win, C, ks, stride, pad, Hout, Wout); ++::salun::g_launch_count; }
 }
 
-__global__ void __launch_bounds__(kET) k_stem_im2col_generic(const float *__restrict__ x, __nv_bfloat16 *__restrict__ col,
+__global__ void __launch_bounds__(kET) k_stem_im2col_generic(const float *__restrict__ x, act_t *__restrict__ col,
                                                              long long total, int Hin, int Win, int ks, int stride,
                                                              int pad, int Hout, int Wout, int kcp, float m0, float m1,
                                                              float m2, float i0, float i1, float i2) {
@@ -614,7 +585,7 @@ __global__ void __launch_bounds__(kET) k_stem_im2col_generic(const float *__rest
     st8(col + (size_t)mo * kcp + gidx * 8, f);
   }
 }
-void launch_stem_im2col_generic(const float *x, __nv_bfloat16 *col, int n_img, int Hin, int Win, int ks, int stride,
+void launch_stem_im2col_generic(const float *x, act_t *col, int n_img, int Hin, int Win, int ks, int stride,
                                 int pad, int Hout, int Wout, int kcp, const float *mean3, const float *inv_std3,
                                 cudaStream_t st) {
   const long long total = (long long)n_img * Hout * Wout * (kcp >> 3);
@@ -624,9 +595,9 @@ void launch_stem_im2col_generic(const float *x, __nv_bfloat16 *col, int n_img, i
                                                   mean3[1], mean3[2], inv_std3[0], inv_std3[1], inv_std3[2]); ++::salun::g_launch_count; }
 }
 
-__global__ void __launch_bounds__(kET) k_col2im_flat(const __nv_bfloat16 *__restrict__ dcol,
-                                                     const __nv_bfloat16 *__restrict__ addend,
-                                                     __nv_bfloat16 *__restrict__ dx, long long total, int Hin, int Win,
+__global__ void __launch_bounds__(kET) k_col2im_flat(const act_t *__restrict__ dcol,
+                                                     const act_t *__restrict__ addend,
+                                                     act_t *__restrict__ dx, long long total, int Hin, int Win,
                                                      int C, int ks, int stride, int pad, int Hout, int Wout) {
   const int cgs = C >> 3, taps = ks * ks;
   for (long long i = (long long)blockIdx.x * kET + threadIdx.x; i < total; i += (long long)gridDim.x * kET) {
@@ -657,7 +628,7 @@ __global__ void __launch_bounds__(kET) k_col2im_flat(const __nv_bfloat16 *__rest
     st8(dx + (size_t)m * C + cg * 8, acc);
   }
 }
-void launch_col2im_flat(const __nv_bfloat16 *dcol, const __nv_bfloat16 *addend, __nv_bfloat16 *dx, int n_img, int Hin,
+void launch_col2im_flat(const act_t *dcol, const act_t *addend, act_t *dx, int n_img, int Hin,
                         int Win, int C, int ks, int stride, int pad, int Hout, int Wout, cudaStream_t st) {
   const long long total = (long long)n_img * Hin * Win * (C >> 3);
   long long g = (total + kET - 1) / kET;
@@ -665,8 +636,8 @@ void launch_col2im_flat(const __nv_bfloat16 *dcol, const __nv_bfloat16 *addend, 
   { k_col2im_flat<<<(int)g, kET, 0, st>>>(dcol, addend, dx, total, Hin, Win, C, ks, stride, pad, Hout, Wout); ++::salun::g_launch_count; }
 }
 
-__global__ void __launch_bounds__(kET) k_bn_apply_flat(BnFwd a, BnFwd b, int has_b, const __nv_bfloat16 *__restrict__ resid,
-                                                       __nv_bfloat16 *__restrict__ out, uint8_t *__restrict__ rmask, int M,
+__global__ void __launch_bounds__(kET) k_bn_apply_flat(BnFwd a, BnFwd b, int has_b, const act_t *__restrict__ resid,
+                                                       act_t *__restrict__ out, uint8_t *__restrict__ rmask, int M,
                                                        int C, int relu, int train, float eps, float momentum) {
   extern __shared__ float smf[];
   float *sc_a = smf, *sh_a = smf + C, *sc_b = smf + 2 * C, *sh_b = smf + 3 * C;
@@ -706,7 +677,7 @@ __global__ void __launch_bounds__(kET) k_bn_apply_flat(BnFwd a, BnFwd b, int has
     }
   }
 }
-void launch_bn_apply_flat(const BnFwd &a, const BnFwd *b, const __nv_bfloat16 *resid_flat, __nv_bfloat16 *out_flat,
+void launch_bn_apply_flat(const BnFwd &a, const BnFwd *b, const act_t *resid_flat, act_t *out_flat,
                           uint8_t *relu_mask_out, int M, int C, int relu, int train, float eps, float momentum,
                           cudaStream_t st) {
   BnFwd bb = b ? *b : a;
@@ -714,7 +685,7 @@ void launch_bn_apply_flat(const BnFwd &a, const BnFwd *b, const __nv_bfloat16 *r
                                                                        relu_mask_out, M, C, relu, train, eps, momentum); ++::salun::g_launch_count; }
 }
 
-__global__ void __launch_bounds__(kET) k_maxpool_fwd(const __nv_bfloat16 *__restrict__ in, __nv_bfloat16 *__restrict__ out,
+__global__ void __launch_bounds__(kET) k_maxpool_fwd(const act_t *__restrict__ in, act_t *__restrict__ out,
                                                      uint8_t *__restrict__ argmax, long long total, int Hin, int Win,
                                                      int C) {
   const int Ho = (Hin + 2 - 3) / 2 + 1, Wo = (Win + 2 - 3) / 2 + 1, cgs = C >> 3;
@@ -752,7 +723,7 @@ __global__ void __launch_bounds__(kET) k_maxpool_fwd(const __nv_bfloat16 *__rest
     *reinterpret_cast<uint2 *>(argmax + (size_t)mo * C + cg * 8) = packed;
   }
 }
-void launch_maxpool_fwd(const __nv_bfloat16 *in_flat, __nv_bfloat16 *out_flat, uint8_t *argmax, int n_img, int Hin,
+void launch_maxpool_fwd(const act_t *in_flat, act_t *out_flat, uint8_t *argmax, int n_img, int Hin,
                         int Win, int C, cudaStream_t st) {
   const int Ho = (Hin + 2 - 3) / 2 + 1, Wo = (Win + 2 - 3) / 2 + 1;
   const long long total = (long long)n_img * Ho * Wo * (C >> 3);
@@ -760,8 +731,8 @@ void launch_maxpool_fwd(const __nv_bfloat16 *in_flat, __nv_bfloat16 *out_flat, u
   if (g > 148 * 16) g = 148 * 16;
   { k_maxpool_fwd<<<(int)g, kET, 0, st>>>(in_flat, out_flat, argmax, total, Hin, Win, C); ++::salun::g_launch_count; }
 }
-__global__ void __launch_bounds__(kET) k_maxpool_bwd(const __nv_bfloat16 *__restrict__ dout,
-                                                     const uint8_t *__restrict__ argmax, __nv_bfloat16 *__restrict__ dx,
+__global__ void __launch_bounds__(kET) k_maxpool_bwd(const act_t *__restrict__ dout,
+                                                     const uint8_t *__restrict__ argmax, act_t *__restrict__ dx,
                                                      long long total, int Hin, int Win, int C) {
   const int Ho = (Hin + 2 - 3) / 2 + 1, Wo = (Win + 2 - 3) / 2 + 1, cgs = C >> 3;
   for (long long i = (long long)blockIdx.x * kET + threadIdx.x; i < total; i += (long long)gridDim.x * kET) {
@@ -792,57 +763,28 @@ __global__ void __launch_bounds__(kET) k_maxpool_bwd(const __nv_bfloat16 *__rest
     st8(dx + (size_t)m * C + cg * 8, acc);
   }
 }
-void launch_maxpool_bwd(const __nv_bfloat16 *dout_flat, const uint8_t *argmax, __nv_bfloat16 *dx_flat, int n_img, int Hin,
+void launch_maxpool_bwd(const act_t *dout_flat, const uint8_t *argmax, act_t *dx_flat, int n_img, int Hin,
                         int Win, int C, cudaStream_t st) {
   const long long total = (long long)n_img * Hin * Win * (C >> 3);
   long long g = (total + kET - 1) / kET;
   if (g > 148 * 16) g = 148 * 16;
   { k_maxpool_bwd<<<(int)g, kET, 0, st>>>(dout_flat, argmax, dx_flat, total, Hin, Win, C); ++::salun::g_launch_count; }
 }
-__global__ void k_avgpool_flat(const __nv_bfloat16 *__restrict__ act, float *__restrict__ pooled, int n_img, int pix, int C) {
+__global__ void k_avgpool_flat(const act_t *__restrict__ act, float *__restrict__ pooled, int n_img, int pix, int C) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_img * C) return;
   const int n = i / C, c = i - n * C;
   float s = 0.f;
-  for (int p = 0; p < pix; ++p) s += __bfloat162float(act[((size_t)n * pix + p) * C + c]);
+  for (int p = 0; p < pix; ++p) s += act_to_float(act[((size_t)n * pix + p) * C + c]);
   pooled[i] = s / (float)pix;
 }
-void launch_avgpool_flat(const __nv_bfloat16 *act_flat, float *pooled, int n_img, int pix, int C, cudaStream_t st) {
+void launch_avgpool_flat(const act_t *act_flat, float *pooled, int n_img, int pix, int C, cudaStream_t st) {
   { k_avgpool_flat<<<(n_img * C + 255) / 256, 256, 0, st>>>(act_flat, pooled, n_img, pix, C); ++::salun::g_launch_count; }
 }
 
 // ------------------------------------------------------------------------------------------------
 // weight re-layout (fp32 master, native [Cout][tap][Cin]) -> bf16 GEMM operands
 // ------------------------------------------------------------------------------------------------
-__global__ void k_prep_w_fwd(const float *__restrict__ w, __nv_bfloat16 *__restrict__ out, int Cout, int kc, int kcp) {
-  const long long total = (long long)Cout * kcp;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int co = (int)(i / kcp), j = (int)(i - (long long)co * kcp);
-    out[i] = __float2bfloat16(j < kc ? w[(size_t)co * kc + j] : 0.f);
-  }
-}
-__global__ void k_prep_w_dgrad_s1(const float *__restrict__ w, __nv_bfloat16 *__restrict__ out, int Cout, int Cin,
-                                  int taps) {
-  // out[ci][(taps-1-t)*Cout + co] = w[(co*taps + t)*Cin + ci]; threads walk the OUTPUT (coalesced writes)
-  const long long total = (long long)Cout * Cin * taps;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int co = (int)(i % Cout);
-    long long r = i / Cout;
-    const int tf = (int)(r % taps);
-    const int ci = (int)(r / taps);
-    const int t = taps - 1 - tf;
-    out[i] = __float2bfloat16(w[((size_t)co * taps + t) * Cin + ci]);
-  }
-}
-__global__ void k_prep_w_transpose(const float *__restrict__ w, __nv_bfloat16 *__restrict__ out, int Cout, int kc) {
-  // out[j][co] = w[co][j]
-  const long long total = (long long)Cout * kc;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int co = (int)(i % Cout);
-    const int j = (int)(i / Cout);
-    out[i] = __float2bfloat16(w[(size_t)co * kc + j]);
-  }
-}
 // all convolutions of the network in ONE launch: blockIdx.y walks the table.
 //   forward operand : plain cast (+ zero padding of the stem's 27 -> 64 columns), coalesced both ways
 //   dgrad operand   : out[ci][taps-1-t][co] = w[co][t][ci]  (stride-1: flipped taps)   or   out[j][co] = w[co][j]
@@ -858,8 +800,8 @@ __global__ void __launch_bounds__(256) k_prep_w_all(const WPrepEntry *__restrict
   // forward operand: one output row per block iteration, threads along the row (no integer division per element)
   for (int co = blockIdx.x; co < e.cout; co += gridDim.x) {
     const float *__restrict__ src = w + (size_t)co * e.kc;
-    __nv_bfloat16 *__restrict__ dst = e.w_fwd + (size_t)co * e.kcp;
-    for (int j = threadIdx.x; j < e.kcp; j += blockDim.x) dst[j] = __float2bfloat16(j < e.kc ? src[j] : 0.f);
+    wop_t *__restrict__ dst = e.w_fwd + (size_t)co * e.kcp * kWopK;
+    for (int j = threadIdx.x; j < e.kcp; j += blockDim.x) wop_store(dst, j, e.kcp, j < e.kc ? src[j] : 0.f);
   }
   if (!need_dgrad || e.dgrad_mode == 0) return;
   const int taps = e.dgrad_mode == 1 ? e.kc / e.cin : 1;
@@ -882,7 +824,7 @@ __global__ void __launch_bounds__(256) k_prep_w_all(const WPrepEntry *__restrict
     for (int j = 0; j < 4; ++j) {  // write out[ci][taps-1-t][co]: co contiguous
       const int ci = ci0 + ty + 8 * j, co = co0 + tx;
       if (ci < cin && co < e.cout)
-        e.w_dgrad[((size_t)ci * taps + (taps - 1 - t)) * ldo + co] = __float2bfloat16(tile[tx][ty + 8 * j]);
+        wop_store(e.w_dgrad + (size_t)ci * taps * ldo * kWopK, (taps - 1 - t) * ldo + co, taps * ldo, tile[tx][ty + 8 * j]);
     }
     __syncthreads();
   }
@@ -891,25 +833,10 @@ void launch_prep_w_all(const WPrepEntry *table_dev, int n_convs, const float *pa
   { ::salun::launch_pdl(k_prep_w_all, dim3(dim3(592, n_convs)), dim3(256), 0, st, table_dev, params, need_dgrad); ++::salun::g_launch_count; }
 }
 
-static inline int flat_grid(long long total) {
-  long long g = (total + 255) / 256;
-  if (g > 148 * 4) g = 148 * 4;  // = resident blocks (launch bounds (kET, 4)): one full wave, no ragged second wave
-  return (int)(g < 1 ? 1 : g);
-}
-void launch_prep_w_fwd(const float *w, __nv_bfloat16 *out, int Cout, int kc, int kc_padded, cudaStream_t st) {
-  { k_prep_w_fwd<<<flat_grid((long long)Cout * kc_padded), 256, 0, st>>>(w, out, Cout, kc, kc_padded); ++::salun::g_launch_count; }
-}
-void launch_prep_w_dgrad_s1(const float *w, __nv_bfloat16 *out, int Cout, int Cin, int taps, cudaStream_t st) {
-  { k_prep_w_dgrad_s1<<<flat_grid((long long)Cout * Cin * taps), 256, 0, st>>>(w, out, Cout, Cin, taps); ++::salun::g_launch_count; }
-}
-void launch_prep_w_transpose(const float *w, __nv_bfloat16 *out, int Cout, int kc, cudaStream_t st) {
-  { k_prep_w_transpose<<<flat_grid((long long)Cout * kc), 256, 0, st>>>(w, out, Cout, kc); ++::salun::g_launch_count; }
-}
-
 // ------------------------------------------------------------------------------------------------
 // head: global average pool, FC, cross-entropy (mean over the batch), and their backward
 // ------------------------------------------------------------------------------------------------
-__global__ void k_avgpool(const __nv_bfloat16 *__restrict__ act, float *__restrict__ pooled, int n_img, int H, int W,
+__global__ void k_avgpool(const act_t *__restrict__ act, float *__restrict__ pooled, int n_img, int H, int W,
                           int C) {
   pdl_trigger();
   pdl_wait();
@@ -918,10 +845,10 @@ __global__ void k_avgpool(const __nv_bfloat16 *__restrict__ act, float *__restri
   const int n = i / C, c = i - n * C;
   float s = 0.f;
   for (int y = 0; y < H; ++y)
-    for (int x = 0; x < W; ++x) s += __bfloat162float(act[((size_t)(n * (H + 2) + y + 1) * (W + 2) + x + 1) * C + c]);
+    for (int x = 0; x < W; ++x) s += act_to_float(act[((size_t)(n * (H + 2) + y + 1) * (W + 2) + x + 1) * C + c]);
   pooled[i] = s / (float)(H * W);
 }
-void launch_avgpool(const __nv_bfloat16 *act_padded, float *pooled, int n_img, int H, int W, int C, cudaStream_t st) {
+void launch_avgpool(const act_t *act_padded, float *pooled, int n_img, int H, int W, int C, cudaStream_t st) {
   { ::salun::launch_pdl(k_avgpool, dim3((n_img * C + 255) / 256), dim3(256), 0, st, act_padded, pooled, n_img, H, W, C); ++::salun::g_launch_count; }
 }
 
@@ -1015,7 +942,7 @@ __global__ void k_fc_bwd_w(const float *__restrict__ pooled, const float *__rest
     db[k] = t;
   }
 }
-__global__ void k_fc_bwd_x(const float *__restrict__ dl, const float *__restrict__ w, __nv_bfloat16 *__restrict__ dact,
+__global__ void k_fc_bwd_x(const float *__restrict__ dl, const float *__restrict__ w, act_t *__restrict__ dact,
                            int n_img, int C, int K, int pix) {
   pdl_trigger();
   pdl_wait();
@@ -1024,11 +951,11 @@ __global__ void k_fc_bwd_x(const float *__restrict__ dl, const float *__restrict
   const int b = i / C, c = i - b * C;
   float s = 0.f;
   for (int k = 0; k < K; ++k) s += dl[(size_t)b * K + k] * w[(size_t)k * C + c];
-  const __nv_bfloat16 v = __float2bfloat16(s / (float)pix);
+  const act_t v = act_from_float(s / (float)pix);
   for (int p = 0; p < pix; ++p) dact[((size_t)b * pix + p) * C + c] = v;
 }
 void launch_fc_bwd(const float *pooled, const float *dlogits, const float *w, float *dw, float *db,
-                   __nv_bfloat16 *dact_flat, int n_img, int C, int K, int pix, cudaStream_t st) {
+                   act_t *dact_flat, int n_img, int C, int K, int pix, cudaStream_t st) {
   { ::salun::launch_pdl(k_fc_bwd_w, dim3(dim3(K, (C + 63) / 64)), dim3(dim3(64, 8)), 0, st, pooled, dlogits, dw, db, n_img, C, K); ++::salun::g_launch_count; }
   { ::salun::launch_pdl(k_fc_bwd_x, dim3((n_img * C + 255) / 256), dim3(256), 0, st, dlogits, w, dact_flat, n_img, C, K, pix); ++::salun::g_launch_count; }
 }

@@ -73,6 +73,55 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
   return v[0];
 }
 
+// r[0..31] (fp32 accumulators of 32 consecutive columns) += 32 consecutive activation elements at src
+__device__ __forceinline__ void epi_add_act32(uint32_t (&r)[32], const act_t *src) {
+#ifdef SALUN_SPLIT
+  const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint4 v = s4[j];
+    r[4 * j + 0] = __float_as_uint(__uint_as_float(r[4 * j + 0]) + act_unpack_pair(v.x));
+    r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + act_unpack_pair(v.y));
+    r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + act_unpack_pair(v.z));
+    r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + act_unpack_pair(v.w));
+  }
+#else
+  const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 v = s4[j];
+    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __bfloat1622float2(h[i]);
+      r[8 * j + 2 * i] = __float_as_uint(__uint_as_float(r[8 * j + 2 * i]) + t.x);
+      r[8 * j + 2 * i + 1] = __float_as_uint(__uint_as_float(r[8 * j + 2 * i + 1]) + t.y);
+    }
+  }
+#endif
+}
+// 32 consecutive activation elements at dst <- r[0..31] (row-per-lane store straight out of the TMEM layout)
+__device__ __forceinline__ void epi_store_act32(act_t *dst, const uint32_t (&r)[32]) {
+  uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+#ifdef SALUN_SPLIT
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    d4[j] = make_uint4(act_pack_pair(__uint_as_float(r[4 * j])), act_pack_pair(__uint_as_float(r[4 * j + 1])),
+                       act_pack_pair(__uint_as_float(r[4 * j + 2])), act_pack_pair(__uint_as_float(r[4 * j + 3])));
+#else
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 v;
+    v.x = pack_bf16x2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]));
+    v.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+    v.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+    v.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+    d4[j] = v;
+  }
+#endif
+}
+
+#ifndef SALUN_SPLIT
 // BN-backward partial sums of one 32-column chunk held in r[] (fp32 dX of row `row`): see BnBwdFuse.
 __device__ __forceinline__ void bn_bwd_fuse_chunk(const BnBwdFuse &f, const uint32_t (&r)[32], bool row_ok,
                                                   size_t pad_off_elems, size_t flat_off_elems, int col0, int N,
@@ -114,6 +163,10 @@ __device__ __forceinline__ void bn_bwd_fuse_chunk(const BnBwdFuse &f, const uint
   f.partials[((size_t)stat_row * 2 + 0) * N + col0 + lane] = s1;
   f.partials[((size_t)stat_row * 2 + 1) * N + col0 + lane] = s2;
 }
+#else
+__device__ __forceinline__ void bn_bwd_fuse_chunk(const BnBwdFuse &, const uint32_t (&)[32], bool, size_t, size_t, int, int,
+                                                  int, int) {}  // the fused BatchNorm-backward partials are a bf16-build option
+#endif
 __device__ __forceinline__ size_t pad_row_off(int m, int H, int W, int C) {
   const int hw = H * W;
   const int n = m / hw, rr = m - n * hw;
@@ -121,6 +174,7 @@ __device__ __forceinline__ size_t pad_row_off(int m, int H, int W, int C) {
   return ((size_t)(n * (H + 2) + y + 1) * (W + 2) + x + 1) * C;
 }
 
+#ifndef SALUN_SPLIT
 // =================================================================================================
 // conv / plain GEMM, K-major operands
 // =================================================================================================
@@ -275,6 +329,8 @@ k_conv_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 1) tmem_dealloc(tmem_base, BN);
 }
 
+#endif  // !SALUN_SPLIT
+
 // =================================================================================================
 // k_conv_gemm_p: PERSISTENT variant of k_conv_gemm.  One CTA per SM walks output tiles (n fastest, so that CTAs
 // running concurrently share the A tile in L2); two TMEM accumulators let the epilogue of tile i run under the MMAs of
@@ -342,7 +398,8 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         }
         int cb = 0, kx = 0, ky = 0;
         const int b_row0 = n_tile * BN + (a.batch_rows_a ? (m_tile * kBM / a.batch_rows_a) * a.batch_rows_b : 0);
-        for (int kb = 0; kb < a.num_k_blocks; ++kb, ++it) {
+        for (int kb = 0, ka = 0; kb < a.num_k_blocks; ++kb, ++ka, ++it) {
+          if (kb == a.k_wrap) ka = cb = kx = ky = 0;  // split build: second pass over the same activation tile
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait_t(empty0 + 8 * s, ph ^ 1, w_empty, dbg_on);
@@ -352,7 +409,7 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             if (a.mode_a == 1)
               tma_load_4d(sa, &tmA, full0 + 8 * s, cb * kBK, a.tap_x0 + kx, a.tap_y0 + y0 + ky, n0);
             else
-              tma_load_2d(sa, &tmA, full0 + 8 * s, kb * kBK, m_tile * kBM);
+              tma_load_2d(sa, &tmA, full0 + 8 * s, ka * kBK, m_tile * kBM);
           } else {
             tma_load_2d(sb, &tmB, full0 + 8 * s, kb * kBK, b_row0);
           }
@@ -444,20 +501,7 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + b4.w);
             }
           }
-          if (row_ok && a.addend) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(a.addend + out_row + col0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 v = src[j];
-              const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 t = __bfloat1622float2(h[i]);
-                r[8 * j + 2 * i] = __float_as_uint(__uint_as_float(r[8 * j + 2 * i]) + t.x);
-                r[8 * j + 2 * i + 1] = __float_as_uint(__uint_as_float(r[8 * j + 2 * i + 1]) + t.y);
-              }
-            }
-          }
+          if (row_ok && a.addend) epi_add_act32(r, a.addend + out_row + col0);
           if (a.stat_sum) {  // column partials of the FINAL value (after bias / projection / residual)
             float v[32], w[32];
 #pragma unroll
@@ -480,6 +524,25 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           // Stores go through a per-warp shared-memory transpose: straight out of the TMEM layout (lane = row) a warp
           // store touches 32 different rows with 16 bytes each (32 LSU wavefronts per instruction -- the measured bound
           // of the short-K GEMMs); transposed, one instruction writes 8 rows x 64 B (bf16) / 4 rows x 128 B (fp32).
+#ifdef SALUN_SPLIT
+          if (a.out_bf16) {  // (hi, lo) pairs are 4 bytes per element: the fp32 staging geometry, 4 rows x 128 B per store
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4 *>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_uint4(act_pack_pair(__uint_as_float(r[4 * j])), act_pack_pair(__uint_as_float(r[4 * j + 1])),
+                             act_pack_pair(__uint_as_float(r[4 * j + 2])), act_pack_pair(__uint_as_float(r[4 * j + 3])));
+            __syncwarp();
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const int rl = 4 * jj + (lane >> 3), unit = lane & 7;
+              const uint4 v = *reinterpret_cast<const uint4 *>(stg + rl * 128 + ((unit ^ (rl & 7)) << 4));
+              const unsigned long long orow = __shfl_sync(0xffffffffu, (unsigned long long)out_row, rl);
+              const int ok = __shfl_sync(0xffffffffu, row_ok ? 1 : 0, rl);
+              if (ok) *reinterpret_cast<uint4 *>(a.out_bf16 + orow + col0 + unit * 4) = v;
+            }
+            __syncwarp();
+          }
+#else
           if (a.out_bf16) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -501,6 +564,7 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             }
             __syncwarp();
           }
+#endif
           if (a.out_f32) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -601,7 +665,8 @@ k_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
         int cb = 0, kx = 0, ky = 0;
         const int b_row0 = n_tile * BN + (int)rank * (BN / 2) +
                            (a.batch_rows_a ? (m_pair * 256 / a.batch_rows_a) * a.batch_rows_b : 0);
-        for (int kb = 0; kb < a.num_k_blocks; ++kb, ++it) {
+        for (int kb = 0, ka = 0; kb < a.num_k_blocks; ++kb, ++ka, ++it) {
+          if (kb == a.k_wrap) ka = cb = kx = ky = 0;  // split build: second pass over the same activation tile
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(empty0 + 8 * s, ph ^ 1);
@@ -611,7 +676,7 @@ k_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
             if (a.mode_a == 1)
               tma2_load_4d(sa, &tmA, full0 + 8 * s, cb * kBK, a.tap_x0 + kx, a.tap_y0 + y0 + ky, n0);
             else
-              tma2_load_2d(sa, &tmA, full0 + 8 * s, kb * kBK, m0);
+              tma2_load_2d(sa, &tmA, full0 + 8 * s, ka * kBK, m0);
           } else {
             tma2_load_2d(sb, &tmB, full0 + 8 * s, kb * kBK, b_row0);
           }
@@ -689,20 +754,7 @@ k_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
               r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + b4.w);
             }
           }
-          if (row_ok && a.addend) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(a.addend + out_row + col0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 v = src[j];
-              const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 t = __bfloat1622float2(h[i]);
-                r[8 * j + 2 * i] = __float_as_uint(__uint_as_float(r[8 * j + 2 * i]) + t.x);
-                r[8 * j + 2 * i + 1] = __float_as_uint(__uint_as_float(r[8 * j + 2 * i + 1]) + t.y);
-              }
-            }
-          }
+          if (row_ok && a.addend) epi_add_act32(r, a.addend + out_row + col0);
           if (a.stat_sum) {
             float v[32], w[32];
 #pragma unroll
@@ -719,18 +771,7 @@ k_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
             }
           }
           if (row_ok) {
-            if (a.out_bf16) {
-              uint4 *dst = reinterpret_cast<uint4 *>(a.out_bf16 + out_row + col0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 v;
-                v.x = pack_bf16x2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]));
-                v.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
-                v.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
-                v.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
-                dst[j] = v;
-              }
-            }
+            if (a.out_bf16) epi_store_act32(a.out_bf16 + out_row + col0, r);
             if (a.out_f32) {
               uint4 *dst = reinterpret_cast<uint4 *>(a.out_f32 + (size_t)row * a.ld_out + col0);
 #pragma unroll
@@ -749,6 +790,7 @@ k_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
   if (warp == 1) tmem2_dealloc(tmem_base, kTmemCols);
 }
 
+#ifndef SALUN_SPLIT
 // =================================================================================================
 // k_conv_rw: persistent stride-1 3x3 convolution with the weight slice RESIDENT in shared memory.
 //
@@ -947,6 +989,8 @@ k_conv_rw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 128);
 }
+
+#endif  // !SALUN_SPLIT
 
 // =================================================================================================
 // wgrad: MN-major operands (pixel dimension is K)
@@ -1243,6 +1287,7 @@ static void prof_close(cudaStream_t st) {
   cudaEventRecord(g_recs.back().b, st);
 }
 
+#ifndef SALUN_SPLIT
 template <int BN, int S>
 static int launch_conv_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvGemmArgs &a, cudaStream_t st) {
   constexpr size_t smem = (size_t)S * (kBM * kBK * 2 + BN * kBK * 2) + 1024 + 256;
@@ -1256,6 +1301,8 @@ static int launch_conv_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, co
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;
 }
+
+#endif
 
 template <int BN, int S>
 static int launch_conv_gemm_p_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvGemmArgs &a, cudaStream_t st) {
@@ -1313,9 +1360,24 @@ static int launch_gemm2_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const 
   return SALUN_OK;
 }
 
+// The runtimes describe a GEMM in activation / weight ELEMENTS (K / 64 k-blocks, Cin / 64 blocks per tap).  In the split
+// build every activation element is two bf16 operand elements and the weight operand holds [dup(hi) | dup(lo)]: twice
+// the k-blocks per pass, two passes, the A operand rewinding at the start of the second (salun_act.cuh).
+static ConvGemmArgs operand_units(const ConvGemmArgs &a) {
+  ConvGemmArgs aa = a;
+  aa.k_wrap = 0;
+  if (kSplit) {
+    aa.k_wrap = a.num_k_blocks * 2;
+    aa.num_k_blocks = a.num_k_blocks * 4;
+    aa.cin_blocks = a.cin_blocks * 2;
+  }
+  return aa;
+}
+
 // CTA-pair GEMM: B tensor map must have box rows BN/2.  bn in {128, 256}.
-int launch_gemm2(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvGemmArgs &a, int bn, cudaStream_t st) {
-  prof_open(0, 2.0 * a.M * a.N * (double)a.num_k_blocks * 64.0, st);
+static int launch_gemm2_units(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvGemmArgs &a, double flops, int bn,
+                              cudaStream_t st) {
+  prof_open(0, flops, st);
   int rc;
   switch (bn) {
     case 128: rc = launch_gemm2_t<128, 8>(tmA, tmB, a, st); break;
@@ -1325,6 +1387,9 @@ int launch_gemm2(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvGemmA
   prof_close(st);
   return rc;
 }
+int launch_gemm2(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvGemmArgs &a, int bn, cudaStream_t st) {
+  return launch_gemm2_units(tmA, tmB, operand_units(a), 2.0 * a.M * a.N * (double)a.num_k_blocks * 64.0, bn, st);
+}
 
 static bool gemm_persistent() {
   static int v = -1;
@@ -1332,7 +1397,7 @@ static bool gemm_persistent() {
     const char *e = getenv("SALUN_GEMM_PERSIST");
     v = (e && e[0] == '0') ? 0 : 1;
   }
-  return v == 1;
+  return v == 1 || kSplit;
 }
 
 static bool gemm_log() {  // SALUN_GEMM_LOG=1: one stderr line per tensor-core launch (shape), to pair with an ncu launch list
@@ -1344,12 +1409,14 @@ static bool gemm_log() {  // SALUN_GEMM_LOG=1: one stderr line per tensor-core l
   return v == 1;
 }
 
-int launch_conv_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvGemmArgs &a, int bn, cudaStream_t st) {
+int launch_conv_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvGemmArgs &a0, int bn, cudaStream_t st) {
   if (gemm_log())
-    fprintf(stderr, "GEMMLOG M=%d N=%d K=%d mode=%d bn=%d H=%d batched=%d\n", a.M, a.N, a.num_k_blocks * 64, a.mode_a, bn, a.H,
-            a.batch_rows_a);
-  if (a.pair) return launch_gemm2(tmA, tmB, a, bn, st);  // the caller encoded tmB with bn/2 box rows
-  prof_open(0, 2.0 * a.M * a.N * (double)a.num_k_blocks * 64.0, st);
+    fprintf(stderr, "GEMMLOG M=%d N=%d K=%d mode=%d bn=%d H=%d batched=%d\n", a0.M, a0.N, a0.num_k_blocks * 64, a0.mode_a, bn, a0.H,
+            a0.batch_rows_a);
+  const double flops = 2.0 * a0.M * a0.N * (double)a0.num_k_blocks * 64.0;  // algorithmic (one product per element pair)
+  const ConvGemmArgs a = operand_units(a0);
+  if (a.pair) return launch_gemm2_units(tmA, tmB, a, flops, bn, st);  // the caller encoded tmB with bn/2 box rows
+  prof_open(0, flops, st);
   int rc;
   if (gemm_persistent()) {
     switch (bn) {
@@ -1361,6 +1428,7 @@ int launch_conv_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvG
     prof_close(st);
     return rc;
   }
+#ifndef SALUN_SPLIT
   if (a.bias || a.rowbias || a.out_pad || a.batch_rows_a) {
     set_error("launch_conv_gemm: bias / rowbias / out_pad / batched operands need the persistent kernel (SALUN_GEMM_PERSIST=1)");
     prof_close(st);
@@ -1372,10 +1440,14 @@ int launch_conv_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvG
     case 256: rc = launch_conv_gemm_t<256, 4>(tmA, tmB, a, st); break;
     default: set_error("launch_conv_gemm: unsupported BN=%d", bn); rc = SALUN_ERR_INVALID;
   }
+#else
+  rc = SALUN_ERR_UNSUPPORTED;
+#endif
   prof_close(st);
   return rc;
 }
 
+#ifndef SALUN_SPLIT
 template <int kW, int kCB>
 static int launch_conv_rw_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvRwArgs &a, int num_sms,
                             cudaStream_t st) {
@@ -1413,7 +1485,15 @@ int launch_conv_rw(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvRwA
   set_error("launch_conv_rw: unsupported W=%d cin_blocks=%d", a.W, a.cin_blocks);
   return SALUN_ERR_UNSUPPORTED;
 }
+#else
+bool conv_rw_supported(int, int, int) { return false; }  // resident-weight kernel: bf16 build only
+int launch_conv_rw(const CUtensorMap &, const CUtensorMap &, const ConvRwArgs &, int, cudaStream_t) {
+  set_error("launch_conv_rw: not available in the split-precision build");
+  return SALUN_ERR_UNSUPPORTED;
+}
+#endif
 
+#ifndef SALUN_SPLIT
 __global__ void __launch_bounds__(256) k_wgrad_reduce(const WgReduceEntry *__restrict__ tab, float *__restrict__ grads) {
   const WgReduceEntry e = tab[blockIdx.y];
   float *__restrict__ dst = grads + e.dst_off;
@@ -1433,8 +1513,30 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const WgReduceEntry *__res
     dst[i] = acc;
   }
 }
+#else
+// split build: slab s holds D'[2 cout][2 kc], the four partial products (dY_hi | dY_lo) x (X_hi | X_lo) of every weight:
+// dW[co][j] = sum_s  D'[2co][2j] + D'[2co][2j+1] + D'[2co+1][2j] + D'[2co+1][2j+1]   (fixed order: deterministic)
+__global__ void __launch_bounds__(256) k_wgrad_reduce(const WgReduceEntry *__restrict__ tab, float *__restrict__ grads) {
+  const WgReduceEntry e = tab[blockIdx.y];
+  float *__restrict__ dst = grads + e.dst_off;
+  const long long slab = 4 * e.count;
+  const int kc = e.kc;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < e.count; i += (long long)gridDim.x * blockDim.x) {
+    const long long co = i / kc;
+    const int j = (int)(i - co * kc);
+    const float *__restrict__ p0 = e.ws + (size_t)(2 * co) * (2 * kc) + 2 * j;
+    float acc = 0.f;
+    for (int s = 0; s < e.splits; ++s) {
+      const float2 r0 = *reinterpret_cast<const float2 *>(p0 + (size_t)s * slab);
+      const float2 r1 = *reinterpret_cast<const float2 *>(p0 + (size_t)s * slab + 2 * kc);
+      acc += (r0.x + r0.y) + (r1.x + r1.y);
+    }
+    dst[i] = acc;
+  }
+}
+#endif
 void launch_wgrad_reduce(const WgReduceEntry *table_dev, int n_entries, float *grads, cudaStream_t st) {
-  { k_wgrad_reduce<<<dim3(64, n_entries), 256, 0, st>>>(table_dev, grads); ++::salun::g_launch_count; }
+  { k_wgrad_reduce<<<dim3(kSplit ? 256 : 64, n_entries), 256, 0, st>>>(table_dev, grads); ++::salun::g_launch_count; }
 }
 
 int wgrad_pick_blocks(int total_blocks) {
@@ -1444,7 +1546,18 @@ int wgrad_pick_blocks(int total_blocks) {
   return 1;
 }
 
-int launch_wgrad(const CUtensorMap &tmA, const CUtensorMap &tmB, const WgradArgs &a, int co_tiles, int col_groups,
+WgradGeom wgrad_geometry(int cout, int kcp) {
+  WgradGeom g;
+  g.total_blocks = kcp * kActK / 64;
+  g.n_blocks = wgrad_pick_blocks(g.total_blocks);
+  g.co_tiles = (cout * kActK + 127) / 128;
+  g.groups = g.total_blocks / g.n_blocks;
+  return g;
+}
+
+// `a0` in weight / activation ELEMENTS (Cout, ldw, kvalid, cin_blocks = Cin / 64, split_stride = cout * kc); total_blocks,
+// n_blocks and the grid (co_tiles, col_groups) from wgrad_geometry().  The split build widens rows and columns by two.
+int launch_wgrad(const CUtensorMap &tmA, const CUtensorMap &tmB, const WgradArgs &a0, int co_tiles, int col_groups,
                  int splits, cudaStream_t st) {
   constexpr size_t smem = (size_t)kWgStages * 6 * kWgBlockBytes + 1024 + 256;
   static bool attr_set = false;
@@ -1452,11 +1565,18 @@ int launch_wgrad(const CUtensorMap &tmA, const CUtensorMap &tmB, const WgradArgs
     SALUN_CUDA_OK(cudaFuncSetAttribute(k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
+  WgradArgs aa = a0;
+  if (kSplit) {
+    aa.Cout = a0.Cout * 2;
+    aa.ldw = a0.ldw * 2;
+    aa.kvalid = a0.kvalid * 2;
+    aa.cin_blocks = a0.cin_blocks * 2;
+    aa.split_stride = a0.split_stride * 4;
+  }
   dim3 grid(co_tiles, col_groups, splits);
   if (gemm_log())
-    fprintf(stderr, "WGLOG pixels=%d Cout=%d Kc=%d grid=%d,%d,%d\n", a.kb_total * 64, a.Cout, a.kvalid, co_tiles, col_groups, splits);
-  prof_open(1, 2.0 * (double)a.kb_total * 64.0 * a.Cout * (double)a.kvalid, st);
-  WgradArgs aa = a;
+    fprintf(stderr, "WGLOG pixels=%d Cout=%d Kc=%d grid=%d,%d,%d\n", a0.kb_total * 64, a0.Cout, a0.kvalid, co_tiles, col_groups, splits);
+  prof_open(1, 2.0 * (double)a0.kb_total * 64.0 * a0.Cout * (double)a0.kvalid, st);
   aa.dbg = g_dbg;
   { k_wgrad<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, aa); ++::salun::g_launch_count; }
   prof_close(st);
@@ -1512,6 +1632,10 @@ int salun_profile_end(double *ms_by_cat, int64_t *launches_by_cat, double *flops
 // D[M][N] (fp32 and/or bf16) = A[M][K] . B[N][K]^T, bf16 row-major operands, K % 64 == 0, N % 64 == 0
 int salun_gemm_bf16_tn(salun_ctx *ctx, const void *A, const void *B, float *out_f32, void *out_bf16, int64_t M,
                        int64_t N, int64_t K, void *stream) {
+#ifdef SALUN_SPLIT
+  set_error("salun_gemm_bf16_tn: raw-bf16 entry point, served by libsalun.so (this is the split-precision build)");
+  return SALUN_ERR_UNSUPPORTED;
+#else
   SALUN_REQUIRE(ctx && A && B && (out_f32 || out_bf16), "NULL argument");
   SALUN_REQUIRE(M > 0 && N > 0 && K > 0 && K % 64 == 0 && N % 64 == 0, "need K % 64 == 0 and N % 64 == 0");
   SALUN_CUDA_OK(cudaSetDevice(ctx->device));
@@ -1525,15 +1649,20 @@ int salun_gemm_bf16_tn(salun_ctx *ctx, const void *A, const void *B, float *out_
   a.num_k_blocks = (int)(K / 64);
   a.M = (int)M;
   a.N = (int)N;
-  a.out_bf16 = (__nv_bfloat16 *)out_bf16;
+  a.out_bf16 = (act_t *)out_bf16;
   a.out_f32 = out_f32;
   a.ld_out = (int)N;
   return launch_conv_gemm(tmA, tmB, a, bn, (cudaStream_t)stream);
+#endif
 }
 
 // CTA-pair (cta_group::2) variant of salun_gemm_bf16_tn: N % 128 == 0.
 int salun_gemm2_bf16_tn(salun_ctx *ctx, const void *A, const void *B, float *out_f32, void *out_bf16, int64_t M,
                         int64_t N, int64_t K, void *stream) {
+#ifdef SALUN_SPLIT
+  set_error("salun_gemm2_bf16_tn: raw-bf16 entry point, served by libsalun.so (this is the split-precision build)");
+  return SALUN_ERR_UNSUPPORTED;
+#else
   SALUN_REQUIRE(ctx && A && B && (out_f32 || out_bf16), "NULL argument");
   SALUN_REQUIRE(M > 0 && N > 0 && K > 0 && K % 64 == 0 && N % 128 == 0, "need K % 64 == 0 and N % 128 == 0");
   SALUN_CUDA_OK(cudaSetDevice(ctx->device));
@@ -1548,10 +1677,11 @@ int salun_gemm2_bf16_tn(salun_ctx *ctx, const void *A, const void *B, float *out
   a.cin_blocks = 1 << 30;
   a.M = (int)M;
   a.N = (int)N;
-  a.out_bf16 = (__nv_bfloat16 *)out_bf16;
+  a.out_bf16 = (act_t *)out_bf16;
   a.out_f32 = out_f32;
   a.ld_out = (int)N;
   return launch_gemm2(tmA, tmB, a, bn, (cudaStream_t)stream);
+#endif
 }
 
 // Y[batch*H*W][Cout] = conv(X, Wk) for a stride-1 kh x kw convolution (3x3/pad 1 or 1x1/pad 0).
@@ -1561,6 +1691,10 @@ int salun_gemm2_bf16_tn(salun_ctx *ctx, const void *A, const void *B, float *out
 // replaces F.conv2d forward (cuDNN) behind Classification/models/ResNet.py:111-119.
 int salun_conv_fwd_bf16(salun_ctx *ctx, const void *xpad, const void *wk, void *y_bf16, float *y_f32, float *stat_sum,
                         float *stat_sq, int batch, int H, int W, int Cin, int Cout, int ksize, void *stream) {
+#ifdef SALUN_SPLIT
+  set_error("salun_conv_fwd_bf16: raw-bf16 entry point, served by libsalun.so (this is the split-precision build)");
+  return SALUN_ERR_UNSUPPORTED;
+#else
   SALUN_REQUIRE(ctx && xpad && wk && (y_bf16 || y_f32), "NULL argument");
   SALUN_REQUIRE(ksize == 3 || ksize == 1, "ksize must be 1 or 3");
   SALUN_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "Cin and Cout must be multiples of 64");
@@ -1583,18 +1717,23 @@ int salun_conv_fwd_bf16(salun_ctx *ctx, const void *xpad, const void *wk, void *
   a.W = W;
   a.M = batch * H * W;
   a.N = Cout;
-  a.out_bf16 = (__nv_bfloat16 *)y_bf16;
+  a.out_bf16 = (act_t *)y_bf16;
   a.out_f32 = y_f32;
   a.ld_out = Cout;
   a.stat_sum = stat_sum;
   a.stat_sq = stat_sq;
   return launch_conv_gemm(tmA, tmB, a, bn, (cudaStream_t)stream);
+#endif
 }
 
 // Same contract as salun_conv_fwd_bf16 (3x3 only) through the persistent resident-weight kernel k_conv_rw;
 // W (= H) in {16, 32}, Cin in {64, 128}.
 int salun_conv_rw_fwd_bf16(salun_ctx *ctx, const void *xpad, const void *wk, void *y_bf16, float *stat_sum,
                            float *stat_sq, int batch, int H, int W, int Cin, int Cout, void *stream) {
+#ifdef SALUN_SPLIT
+  set_error("salun_conv_rw_fwd_bf16: raw-bf16 entry point, served by libsalun.so (this is the split-precision build)");
+  return SALUN_ERR_UNSUPPORTED;
+#else
   SALUN_REQUIRE(ctx && xpad && wk && y_bf16, "NULL argument");
   SALUN_REQUIRE(H == W && conv_rw_supported(W, Cin, Cout), "shape not served by k_conv_rw");
   SALUN_CUDA_OK(cudaSetDevice(ctx->device));
@@ -1610,11 +1749,12 @@ int salun_conv_rw_fwd_bf16(salun_ctx *ctx, const void *xpad, const void *wk, voi
   r.M = batch * H * W;
   r.num_tiles = (r.M + 127) / 128;
   r.N = Cout;
-  r.out_bf16 = (__nv_bfloat16 *)y_bf16;
+  r.out_bf16 = (act_t *)y_bf16;
   r.ld_out = Cout;
   r.stat_sum = stat_sum;
   r.stat_sq = stat_sq;
   return launch_conv_rw(tmA, tmB, r, ctx->num_sms, (cudaStream_t)stream);
+#endif
 }
 
 // dW[Cout][kh*kw*Cin] (fp32, tap-major) += sum over pixels dY[p][Cout]^T . X_tap[p][Cin]
@@ -1622,6 +1762,10 @@ int salun_conv_rw_fwd_bf16(salun_ctx *ctx, const void *xpad, const void *wk, voi
 // replaces the cuDNN wgrad inside loss.backward() (Classification/unlearn/RL.py:132).
 int salun_conv_wgrad_bf16(salun_ctx *ctx, const void *dy, const void *xpad, float *dw, int batch, int H, int W, int Cin,
                           int Cout, int ksize, int splits, int swap_lbo_sbo, void *stream) {
+#ifdef SALUN_SPLIT
+  set_error("salun_conv_wgrad_bf16: raw-bf16 entry point, served by libsalun.so (this is the split-precision build)");
+  return SALUN_ERR_UNSUPPORTED;
+#else
   SALUN_REQUIRE(ctx && dy && xpad && dw, "NULL argument");
   SALUN_REQUIRE(ksize == 3 || ksize == 1, "ksize must be 1 or 3");
   SALUN_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "Cin and Cout must be multiples of 64");
@@ -1658,6 +1802,7 @@ int salun_conv_wgrad_bf16(salun_ctx *ctx, const void *dy, const void *xpad, floa
   a.kb_per_split = (a.kb_total + splits - 1) / splits;
   splits = (a.kb_total + a.kb_per_split - 1) / a.kb_per_split;
   return launch_wgrad(tmA, tmB, a, co_tiles, groups, splits, (cudaStream_t)stream);
+#endif
 }
 
 }  // extern "C"

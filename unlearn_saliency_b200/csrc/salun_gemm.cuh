@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include "salun_act.cuh"
 #include "salun_common.cuh"
 
 namespace salun {
@@ -12,8 +13,8 @@ namespace salun {
 // dZ = dX * (act > 0), xhat = (y - mean) * invstd : they are reduced here from the fp32 accumulators (per (tile, warp)
 // column partials, same layout as the forward statistics) instead of in a separate pass over dX, act and y.
 struct BnBwdFuse {
-  const __nv_bfloat16 *act;   // halo-padded activation (ReLU mask), nullptr = fusion off
-  const __nv_bfloat16 *y;     // raw conv output [M][N] feeding that BN
+  const act_t *act;           // halo-padded activation (ReLU mask), nullptr = fusion off (bf16 build only)
+  const act_t *y;             // raw conv output [M][N] feeding that BN
   const float *mean, *invstd; // saved statistics of that BN
   float *partials;            // [tiles*4][2][N]
 };
@@ -23,17 +24,19 @@ struct BnBwdFuse {
 // halo-padded NHWC activation through a 4-D tensor map (implicit GEMM: k-block = (tap, 64 channels)).
 struct ConvGemmArgs {
   int mode_a;        // 0: A is [M][K] row-major; 1: A is padded NHWC [batch][H+2][W+2][C], taps walk it
-  int num_k_blocks;  // K / 64
+  int num_k_blocks;  // K / 64 (K in activation elements; launch_conv_gemm rescales for the split build)
+  int k_wrap;        // set by launch_conv_gemm.  > 0: the A operand restarts at k-block 0 when the k loop reaches this
+                     // block (split build: pass 2 multiplies the same activation tile with the lo half of the weights)
   int cin_blocks;    // mode 1: 64-channel blocks per tap
   int kw;            // mode 1: taps per kernel row (3 for 3x3, 1 for 1x1)
   int tap_y0, tap_x0;  // mode 1: padded coordinate of tap (0,0) for output pixel (0,0): 0 for 3x3/pad1, 1 for 1x1/pad0
   int H, W;          // mode 1: output spatial size (== input spatial size, stride 1)
   int M, N;          // valid rows / columns of D
-  __nv_bfloat16 *out_bf16;  // [M][ld_out] or nullptr
+  act_t *out_bf16;          // activation-typed output [M][ld_out] or nullptr (bf16, or (hi, lo) pairs in the split build)
   float *out_f32;           // [M][ld_out] or nullptr
   int ld_out;
   float *stat_sum, *stat_sq;  // per-(m tile, warp) column partial sums [gridDim.x * 4][N], or nullptr
-  const __nv_bfloat16 *addend;  // optional [M][ld_out]: D += addend before the store (residual-gradient merge)
+  const act_t *addend;          // optional [M][ld_out]: D += addend before the store (residual-gradient merge)
   long long *dbg;               // optional per-CTA role timing [gridDim][8] (bring-up / profiling only)
   BnBwdFuse f1, f2;             // up to two consumer BatchNorms of the produced gradient (bn2 + projection-shortcut BN)
   int fH, fW;                   // image size of the output pixels (padded-offset arithmetic of f1/f2.act and of out_pad)
@@ -77,10 +80,10 @@ struct ConvRwArgs {
   int cin_blocks;       // Cin / 64
   int num_tiles;        // ceil(M / 128)
   int M, N;             // valid rows / columns (N = Cout)
-  __nv_bfloat16 *out_bf16;
+  act_t *out_bf16;
   int ld_out;
   float *stat_sum, *stat_sq;
-  const __nv_bfloat16 *addend;
+  const act_t *addend;
   long long *dbg;
   BnBwdFuse f1, f2;
 };
@@ -91,11 +94,25 @@ struct TmapBox4 {
 
 int make_tmap_2d_bf16(CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows,
                       uint32_t box_cols);
+// Typed forms used by the runtimes (sizes in ACTIVATION / WEIGHT elements; the split build widens them):
+//   act : an activation matrix [rows][cols]              -> bf16 [rows][cols * kActK], 64-wide boxes
+//   wop : a prepared weight operand [rows][K] (K padded)  -> bf16 [rows][K * kWopK]
+static inline int make_tmap_2d_act(CUtensorMap *m, const act_t *base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  return make_tmap_2d_bf16(m, base, rows, cols * kActK, box_rows, 64);
+}
+static inline int make_tmap_2d_wop(CUtensorMap *m, const wop_t *base, uint64_t rows, uint64_t K, uint32_t box_rows) {
+  return make_tmap_2d_bf16(m, base, rows, K * kWopK, box_rows, 64);
+}
 // same with a row stride of `ld` elements (ld >= cols, ld * 2 bytes a multiple of 16); columns >= cols read as zero
 int make_tmap_2d_bf16_ld(CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                          uint32_t box_cols);
 int make_tmap_4d_bf16(CUtensorMap *m, const void *base, uint64_t C, uint64_t Wp, uint64_t Hp, uint64_t N,
                       TmapBox4 box);
+static inline int make_tmap_4d_act(CUtensorMap *m, const act_t *base, uint64_t C, uint64_t Wp, uint64_t Hp, uint64_t N,
+                                   TmapBox4 box) {
+  return make_tmap_4d_bf16(m, base, C * kActK, Wp, Hp, N, box);
+}
+
 
 // box decomposition of `pixels` consecutive output pixels of an H x W image batch (power-of-two sizes)
 int conv_box(int H, int W, int pixels, TmapBox4 *box);
@@ -106,12 +123,20 @@ int launch_wgrad(const CUtensorMap &tmA, const CUtensorMap &tmB, const WgradArgs
 // CTA-pair (cta_group::2) GEMM, 256 x bn tiles; tmB must be encoded with bn/2 box rows
 int launch_gemm2(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvGemmArgs &a, int bn, cudaStream_t st);
 int wgrad_pick_blocks(int total_blocks);
+// Tile decomposition of one weight-gradient GEMM dW[cout][kcp] (sizes in weight elements, kcp % 64 == 0); the split
+// build computes the 2 x 2 partial products of every (co, k) pair: twice the rows and columns, and a 4x workspace.
+struct WgradGeom {
+  int co_tiles, groups, n_blocks, total_blocks;
+};
+WgradGeom wgrad_geometry(int cout, int kcp);
+static inline size_t wgrad_ws_elems(int cout, int kc) { return (size_t)cout * kc * kActK * kActK; }
 // dst[off + i] = sum_s ws[s*count + i], one table entry per convolution, ONE launch for the whole network
 struct WgReduceEntry {
   const float *ws;
   long long dst_off;
-  long long count;
+  long long count;     // cout * kc weight elements
   int splits;
+  int kc;              // row length of the weight (split build: the workspace row is 2 * kc wide)
 };
 void launch_wgrad_reduce(const WgReduceEntry *table_dev, int n_entries, float *grads, cudaStream_t st);
 bool conv_rw_supported(int W, int cin, int cout);

@@ -25,8 +25,6 @@
 
 namespace salun {
 
-typedef __nv_bfloat16 bf16;
-
 struct ConvL {
   int cin, cout, ks, stride, hin, hout;
   bool stem;
@@ -34,7 +32,8 @@ struct ConvL {
   int64_t w_off, g_off, b_off;  // arena offsets: weight, BN gamma, BN beta
   int rs_off;            // offset into the running-stat arenas
   int in_act;            // index of the padded input activation (-1: network input)
-  bf16 *w_fwd, *w_dgrad, *col, *y, *dy, *dcol;
+  wop_t *w_fwd, *w_dgrad;
+  act_t *col, *y, *dy, *dcol;
   float *stat_sum, *stat_sq, *saved_mean, *saved_invstd, *coef, *bwd_partials;
   float *wg_ws;          // split-K workspace of the weight gradient: [wg_splits_max][cout][kc]
   int wg_splits_max;
@@ -43,9 +42,9 @@ struct ConvL {
 };
 struct Act {
   int C, H;
-  bf16 *p;       // padded [n][H+2][H+2][C]
-  bf16 *dout;    // gradient w.r.t. this activation, flat [n*H*H][C]
-  bf16 *dz;      // dout * (act > 0), flat (identity-shortcut blocks only)
+  act_t *p;      // padded [n][H+2][H+2][C]
+  act_t *dout;   // gradient w.r.t. this activation, flat [n*H*H][C]
+  act_t *dz;     // dout * (act > 0), flat (identity-shortcut blocks only)
   uint8_t *rmask;  // 1-bit ReLU mask of this activation, [n*H*H][C/8] (read by the BatchNorm backward instead of p)
 };
 struct Block {
@@ -205,40 +204,40 @@ static int build_plan(salun_resnet *net, int n, std::vector<ConvMaps> **out) {
     m.rw_fwd = m.rw_dgrad = false;
     const int64_t Mout = (int64_t)n * L.hout * L.hout;
     const int bn = pick_bn(L.cout, Mout);
-    TRY(make_tmap_2d_bf16(&m.fwdB, L.w_fwd, L.cout, L.kcp, bn, 64));
+    TRY(make_tmap_2d_wop(&m.fwdB, L.w_fwd, L.cout, L.kcp, bn));
     TmapBox4 bx128, bx64;
     if (L.dy_padded) {
       // stride-1 3x3: forward A and wgrad B read the padded input activation, dgrad A / wgrad A the padded dY
       const Act &in = net->acts[L.in_act];
       TRY(conv_box(L.hin, L.hin, 128, &bx128));
       TRY(conv_box(L.hin, L.hin, 64, &bx64));
-      TRY(make_tmap_4d_bf16(&m.fwdA, in.p, L.cin, L.hin + 2, L.hin + 2, n, bx128));
-      TRY(make_tmap_4d_bf16(&m.dgA, L.dy, L.cout, L.hout + 2, L.hout + 2, n, bx128));
+      TRY(make_tmap_4d_act(&m.fwdA, in.p, L.cin, L.hin + 2, L.hin + 2, n, bx128));
+      TRY(make_tmap_4d_act(&m.dgA, L.dy, L.cout, L.hout + 2, L.hout + 2, n, bx128));
       const int bnd = pick_bn(L.cin, Mout);
-      TRY(make_tmap_2d_bf16(&m.dgB, L.w_dgrad, L.cin, (uint64_t)L.ks * L.ks * L.cout, bnd, 64));
-      TRY(make_tmap_4d_bf16(&m.wgA, L.dy, L.cout, L.hout + 2, L.hout + 2, n, bx64));
-      TRY(make_tmap_4d_bf16(&m.wgB, in.p, L.cin, L.hin + 2, L.hin + 2, n, bx64));
+      TRY(make_tmap_2d_wop(&m.dgB, L.w_dgrad, L.cin, (uint64_t)L.ks * L.ks * L.cout, bnd));
+      TRY(make_tmap_4d_act(&m.wgA, L.dy, L.cout, L.hout + 2, L.hout + 2, n, bx64));
+      TRY(make_tmap_4d_act(&m.wgB, in.p, L.cin, L.hin + 2, L.hin + 2, n, bx64));
       m.rw_fwd = net->use_conv_rw && (net->use_conv_rw == 1 || L.hin == 32) && L.ks == 3 && conv_rw_supported(L.hin, L.cin, L.cout);
       m.rw_dgrad = net->use_conv_rw && (net->use_conv_rw == 1 || L.hout == 32) && L.ks == 3 && conv_rw_supported(L.hout, L.cout, L.cin);
       TmapBox4 bxr{64, L.hin, 128 / L.hin + 2, 1};
       if (m.rw_fwd) {
-        TRY(make_tmap_4d_bf16(&m.rwA, in.p, L.cin, L.hin + 2, L.hin + 2, n, bxr));
-        TRY(make_tmap_2d_bf16(&m.rwB, L.w_fwd, L.cout, L.kcp, 64, 64));
+        TRY(make_tmap_4d_act(&m.rwA, in.p, L.cin, L.hin + 2, L.hin + 2, n, bxr));
+        TRY(make_tmap_2d_wop(&m.rwB, L.w_fwd, L.cout, L.kcp, 64));
       }
       if (m.rw_dgrad) {
-        TRY(make_tmap_4d_bf16(&m.rwdA, L.dy, L.cout, L.hout + 2, L.hout + 2, n, bxr));
-        TRY(make_tmap_2d_bf16(&m.rwdB, L.w_dgrad, L.cin, (uint64_t)9 * L.cout, 64, 64));
+        TRY(make_tmap_4d_act(&m.rwdA, L.dy, L.cout, L.hout + 2, L.hout + 2, n, bxr));
+        TRY(make_tmap_2d_wop(&m.rwdB, L.w_dgrad, L.cin, (uint64_t)9 * L.cout, 64));
       }
     } else {
       // stem / stride-2: explicit patch matrix col[Mout][kcp]
-      TRY(make_tmap_2d_bf16(&m.fwdA, L.col, Mout, L.kcp, 128, 64));
-      TRY(make_tmap_2d_bf16(&m.wgA, L.dy, Mout, L.cout, 64, 64));
-      TRY(make_tmap_2d_bf16(&m.wgB, L.col, Mout, L.kcp, 64, 64));
+      TRY(make_tmap_2d_act(&m.fwdA, L.col, Mout, L.kcp, 128));
+      TRY(make_tmap_2d_act(&m.wgA, L.dy, Mout, L.cout, 64));
+      TRY(make_tmap_2d_act(&m.wgB, L.col, Mout, L.kcp, 64));
       if (!L.stem) {
         // dgrad: dcol[Mout][kc] = dY[Mout][Cout] . Wt[kc][Cout]^T
-        TRY(make_tmap_2d_bf16(&m.dgA, L.dy, Mout, L.cout, 128, 64));
+        TRY(make_tmap_2d_act(&m.dgA, L.dy, Mout, L.cout, 128));
         const int bnd = pick_bn(L.kc, Mout);
-        TRY(make_tmap_2d_bf16(&m.dgB, L.w_dgrad, L.kc, L.cout, bnd, 64));
+        TRY(make_tmap_2d_wop(&m.dgB, L.w_dgrad, L.kc, L.cout, bnd));
       }
     }
   }
@@ -319,12 +318,13 @@ static int wgrad_conv(salun_resnet *net, const ConvL &L, const ConvMaps &m, int 
   a.kw = L.ks;
   a.tap_y0 = a.tap_x0 = L.ks == 3 ? 0 : 1;
   a.H = a.W = L.hout;
-  a.total_blocks = L.kcp / 64;
-  a.n_blocks = wgrad_pick_blocks(a.total_blocks);
+  const WgradGeom geo = wgrad_geometry(L.cout, L.kcp);
+  a.total_blocks = geo.total_blocks;
+  a.n_blocks = geo.n_blocks;
   a.Cout = L.cout;
   a.ldw = L.kc;
   a.kvalid = L.kc;
-  const int co_tiles = (L.cout + 127) / 128, groups = a.total_blocks / a.n_blocks;
+  const int co_tiles = geo.co_tiles, groups = geo.groups;
   // one wave: as many pixel splits as fit on the SMs next to the (co tile, tap group) decomposition
   int splits = net->ctx->num_sms / (co_tiles * groups);
   if (splits < 1) splits = 1;
@@ -339,7 +339,7 @@ static int wgrad_conv(salun_resnet *net, const ConvL &L, const ConvMaps &m, int 
 }
 
 // BN backward of one conv's BatchNorm: dout (flat) [* relu mask of out_act] -> L.dy (+ dz)
-static void bn_backward(salun_resnet *net, const ConvL &L, const bf16 *dout, const uint8_t *relu_act, bf16 *dz, int n,
+static void bn_backward(salun_resnet *net, const ConvL &L, const act_t *dout, const uint8_t *relu_act, act_t *dz, int n,
                         int train, cudaStream_t st) {
   const int H = L.hout;
   const int ci = (int)(&L - net->convs.data());
@@ -561,6 +561,7 @@ static int backward_impl(salun_resnet *net, cudaStream_t st) {
     e.dst_off = L.w_off;
     e.count = (long long)L.cout * L.kc;
     e.splits = net->wg_splits_host[i];
+    e.kc = L.kc;
   }
   SALUN_CUDA_OK(cudaMemcpyAsync(net->wgred_table, net->wgred_host, net->convs.size() * sizeof(WgReduceEntry),
                                 cudaMemcpyHostToDevice, st));
@@ -653,7 +654,7 @@ int salun_resnet_create(salun_ctx *ctx, const salun_resnet_cfg *cfg, float *para
     // measured on B200 (profiles/README.md): the dgrad epilogues are already the slower side of their kernels, so
     // moving the BatchNorm-backward reduction into them costs more (-6% steps/s) than the 16 reduce launches it saves
     const char *e = getenv("SALUN_BN_BWD_FUSE");
-    net->use_bwd_fuse = e ? atoi(e) : 0;
+    net->use_bwd_fuse = (e && !kSplit) ? atoi(e) : 0;
   }
   {
     const char *e = getenv("SALUN_CONV_RW");
@@ -683,8 +684,8 @@ int salun_resnet_create(salun_ctx *ctx, const salun_resnet_cfg *cfg, float *para
   }
   for (ConvL &L : net->convs) {
     const size_t Mo = (size_t)nb * L.hout * L.hout;
-    A(dmalloc(net, &L.w_fwd, (size_t)L.cout * L.kcp, true));
-    if (!L.stem) A(dmalloc(net, &L.w_dgrad, (size_t)L.cout * L.kc, true));
+    A(dmalloc(net, &L.w_fwd, (size_t)L.cout * L.kcp * kWopK, true));
+    if (!L.stem) A(dmalloc(net, &L.w_dgrad, (size_t)L.cout * L.kc * kWopK, true));
     A(dmalloc(net, &L.y, Mo * L.cout, false));
     if (L.dy_padded) {
       A(dmalloc(net, &L.dy, (size_t)nb * (L.hout + 2) * (L.hout + 2) * L.cout, true));
@@ -706,11 +707,11 @@ int salun_resnet_create(salun_ctx *ctx, const salun_resnet_cfg *cfg, float *para
       A(dmalloc(net, &L.bwd_partials, prow * 2 * L.cout, true));
     }
     {
-      const int total_blocks = L.kcp / 64, nb_ = wgrad_pick_blocks(total_blocks);
-      const int tiles = ((L.cout + 127) / 128) * (total_blocks / nb_);
+      const WgradGeom geo = wgrad_geometry(L.cout, L.kcp);
+      const int tiles = geo.co_tiles * geo.groups;
       L.wg_splits_max = ctx->num_sms / tiles;
       if (L.wg_splits_max < 1) L.wg_splits_max = 1;
-      A(dmalloc(net, &L.wg_ws, (size_t)L.wg_splits_max * L.cout * L.kc, false));
+      A(dmalloc(net, &L.wg_ws, (size_t)L.wg_splits_max * wgrad_ws_elems(L.cout, L.kc), false));
     }
   }
   net->wg_splits_host.assign(net->convs.size(), 1);

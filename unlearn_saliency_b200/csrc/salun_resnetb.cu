@@ -19,7 +19,6 @@
 
 namespace salun {
 
-typedef __nv_bfloat16 bf16;
 
 struct FConv {
   int cin, cout, ks, stride, pad, hin, win, hout, wout;
@@ -28,14 +27,15 @@ struct FConv {
   int64_t w_off, g_off, b_off;
   int rs_off, in_act;
   bool direct;  // 1x1 / stride 1: the input activation IS the GEMM operand
-  bf16 *w_fwd, *w_dg, *y, *dy;
+  wop_t *w_fwd, *w_dg;
+  act_t *y, *dy;
   float *stat_sum, *stat_sq, *saved_mean, *saved_invstd, *coef, *bwd_partials, *wg_ws;
   double *slices;
   int wg_splits_max;
 };
 struct FAct {
   int C, H, W;
-  bf16 *p, *dout, *dz;
+  act_t *p, *dout, *dz;
   uint8_t *rmask;
 };
 struct FBlock {
@@ -59,7 +59,7 @@ struct FlatNet {
   int64_t fc_w_off, fc_b_off;
   int feat;
   float *pooled, *logits, *dlogits, *loss_ps;
-  bf16 *scratch_col, *scratch_dcol;
+  act_t *scratch_col, *scratch_dcol;
   WPrepEntry *wprep_table;
   WgReduceEntry *wgred_table, *wgred_host;
   std::vector<int> wg_splits;
@@ -163,7 +163,7 @@ static int fmalloc(FlatNet *net, T **p, size_t count, bool zero) {
   return SALUN_OK;
 }
 
-static const bf16 *conv_operand(FlatNet *net, const FConv &L) { return L.direct ? net->acts[L.in_act].p : net->scratch_col; }
+static const act_t *conv_operand(FlatNet *net, const FConv &L) { return L.direct ? net->acts[L.in_act].p : net->scratch_col; }
 
 static int fplan(FlatNet *net, int n, std::vector<FMaps> **out) {
   auto it = net->plans.find(n);
@@ -176,14 +176,14 @@ static int fplan(FlatNet *net, int n, std::vector<FMaps> **out) {
     const FConv &L = net->convs[i];
     FMaps &m = maps[i];
     const int64_t Mo = (int64_t)n * L.hout * L.wout;
-    const bf16 *A = conv_operand(net, L);
-    TRY(make_tmap_2d_bf16(&m.fwdA, A, Mo, L.kcp, 128, 64));
-    TRY(make_tmap_2d_bf16(&m.fwdB, L.w_fwd, L.cout, L.kcp, fpick_bn(L.cout, Mo), 64));
-    TRY(make_tmap_2d_bf16(&m.wgA, L.dy, Mo, L.cout, 64, 64));
-    TRY(make_tmap_2d_bf16(&m.wgB, A, Mo, L.kcp, 64, 64));
+    const act_t *A = conv_operand(net, L);
+    TRY(make_tmap_2d_act(&m.fwdA, A, Mo, L.kcp, 128));
+    TRY(make_tmap_2d_wop(&m.fwdB, L.w_fwd, L.cout, L.kcp, fpick_bn(L.cout, Mo)));
+    TRY(make_tmap_2d_act(&m.wgA, L.dy, Mo, L.cout, 64));
+    TRY(make_tmap_2d_act(&m.wgB, A, Mo, L.kcp, 64));
     if (!L.stem) {
-      TRY(make_tmap_2d_bf16(&m.dgA, L.dy, Mo, L.cout, 128, 64));
-      TRY(make_tmap_2d_bf16(&m.dgB, L.w_dg, L.kc, L.cout, fpick_bn(L.kc, Mo), 64));
+      TRY(make_tmap_2d_act(&m.dgA, L.dy, Mo, L.cout, 128));
+      TRY(make_tmap_2d_wop(&m.dgB, L.w_dg, L.kc, L.cout, fpick_bn(L.kc, Mo)));
     }
   }
   auto res = net->plans.emplace(n, std::move(maps));
@@ -243,7 +243,7 @@ static int fforward(FlatNet *net, const float *x, const int64_t *labels, int n, 
   TRY(fplan(net, n, &plan));
   launch_prep_w_all(net->wprep_table, (int)net->convs.size(), net->params, need_bwd ? 1 : 0, st);
   const salun_resnet_cfg &c = net->cfg;
-  auto apply = [&](const FConv &L, const BnFwd *second, const bf16 *resid, FAct &out, int relu) {
+  auto apply = [&](const FConv &L, const BnFwd *second, const act_t *resid, FAct &out, int relu) {
     BnFwd b = fbn_of(net, L);
     launch_bn_apply_flat(b, second, resid, out.p, need_bwd ? out.rmask : nullptr, n * L.hout * L.wout, L.cout, relu, train,
                          c.bn_eps, c.bn_momentum, st);
@@ -280,7 +280,7 @@ static int fforward(FlatNet *net, const float *x, const int64_t *labels, int n, 
   return SALUN_OK;
 }
 
-static void fbn_backward(FlatNet *net, const FConv &L, const bf16 *dout, const uint8_t *rmask, bf16 *dz, int n, int train,
+static void fbn_backward(FlatNet *net, const FConv &L, const act_t *dout, const uint8_t *rmask, act_t *dz, int n, int train,
                          cudaStream_t st) {
   const int M = n * L.hout * L.wout;
   // the reduce / apply kernels only use n*H*W as a row count when dY is flat: pass it as (n = M, H = W = 1)
@@ -301,12 +301,13 @@ static int fwgrad(FlatNet *net, int ci, const FMaps &m, const float *x, int n, c
   a.cin_blocks = 1;
   a.kw = 1;
   a.H = a.W = 1;
-  a.total_blocks = L.kcp / 64;
-  a.n_blocks = wgrad_pick_blocks(a.total_blocks);
+  const WgradGeom geo = wgrad_geometry(L.cout, L.kcp);
+  a.total_blocks = geo.total_blocks;
+  a.n_blocks = geo.n_blocks;
   a.Cout = L.cout;
   a.ldw = L.kc;
   a.kvalid = L.kc;
-  const int co_tiles = (L.cout + 127) / 128, groups = a.total_blocks / a.n_blocks;
+  const int co_tiles = geo.co_tiles, groups = geo.groups;
   int splits = net->ctx->num_sms / (co_tiles * groups);
   if (splits < 1) splits = 1;
   if (splits > L.wg_splits_max) splits = L.wg_splits_max;
@@ -320,7 +321,7 @@ static int fwgrad(FlatNet *net, int ci, const FMaps &m, const float *x, int n, c
 }
 
 // gradient w.r.t. the conv's input activation (+ addend), written to acts[L.in_act].dout
-static int fdgrad(FlatNet *net, int ci, const FMaps &m, const bf16 *addend, int n, cudaStream_t st) {
+static int fdgrad(FlatNet *net, int ci, const FMaps &m, const act_t *addend, int n, cudaStream_t st) {
   const FConv &L = net->convs[ci];
   const int Mo = n * L.hout * L.wout;
   FAct &in = net->acts[L.in_act];
@@ -386,6 +387,7 @@ static int fbackward(FlatNet *net, const float *x, cudaStream_t st) {
     e.dst_off = L.w_off;
     e.count = (long long)L.cout * L.kc;
     e.splits = net->wg_splits[i];
+    e.kc = L.kc;
   }
   SALUN_CUDA_OK(cudaMemcpyAsync(net->wgred_table, net->wgred_host, net->convs.size() * sizeof(WgReduceEntry),
                                 cudaMemcpyHostToDevice, st));
@@ -450,8 +452,8 @@ int flatnet_create(salun_ctx *ctx, const salun_resnet_cfg *cfg, float *params, f
   size_t col_max = 0, dcol_max = 0;
   for (FConv &L : net->convs) {
     const size_t Mo = (size_t)nb * L.hout * L.wout;
-    A(fmalloc(net, &L.w_fwd, (size_t)L.cout * L.kcp, true));
-    if (!L.stem) A(fmalloc(net, &L.w_dg, (size_t)L.cout * L.kc, true));
+    A(fmalloc(net, &L.w_fwd, (size_t)L.cout * L.kcp * kWopK, true));
+    if (!L.stem) A(fmalloc(net, &L.w_dg, (size_t)L.cout * L.kc * kWopK, true));
     A(fmalloc(net, &L.y, Mo * L.cout, false));
     A(fmalloc(net, &L.dy, Mo * L.cout, false));
     if (!L.direct) {
@@ -466,11 +468,11 @@ int flatnet_create(salun_ctx *ctx, const salun_resnet_cfg *cfg, float *params, f
     A(fmalloc(net, &L.saved_invstd, (size_t)L.cout, true));
     A(fmalloc(net, &L.coef, (size_t)3 * L.cout, true));
     A(fmalloc(net, &L.bwd_partials, (size_t)kBwdPartialRows * 2 * L.cout, true));
-    const int total_blocks = L.kcp / 64, nbk = wgrad_pick_blocks(total_blocks);
-    const int tiles = ((L.cout + 127) / 128) * (total_blocks / nbk);
+    const WgradGeom geo = wgrad_geometry(L.cout, L.kcp);
+    const int tiles = geo.co_tiles * geo.groups;
     L.wg_splits_max = ctx->num_sms / tiles;
     if (L.wg_splits_max < 1) L.wg_splits_max = 1;
-    A(fmalloc(net, &L.wg_ws, (size_t)L.wg_splits_max * L.cout * L.kc, false));
+    A(fmalloc(net, &L.wg_ws, (size_t)L.wg_splits_max * wgrad_ws_elems(L.cout, L.kc), false));
   }
   A(fmalloc(net, &net->scratch_col, col_max + 64, true));
   A(fmalloc(net, &net->scratch_dcol, dcol_max + 64, true));

@@ -459,6 +459,28 @@ __global__ void __launch_bounds__(kThreads) k_sumsq_partial(const float *__restr
     partials[blockIdx.x] = t;
   }
 }
+// FT_l1 (Classification/unlearn/FT.py:13-17,133-134): loss += alpha * ||theta||_1  =>  g += alpha * sign(theta); the
+// penalty value sum |theta| comes out of the same pass (double partials, fixed tree).  12 B/param.
+__global__ void __launch_bounds__(kThreads) k_l1_penalty_grad(const float *__restrict__ p, float *__restrict__ g, int64_t n,
+                                                              float alpha, double *__restrict__ partials) {
+  __shared__ double sh[kThreads / 32];
+  double s = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const float v = p[i];
+    s += (double)fabsf(v);
+    const float sg = v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f);   // torch.sign: 0 at 0 (the subgradient autograd uses)
+    g[i] = __fadd_rn(g[i], __fmul_rn(alpha, sg));
+  }
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) t += sh[w];
+    partials[blockIdx.x] = t;
+  }
+}
 __global__ void k_sumsq_final(const double *__restrict__ partials, int nparts, double *__restrict__ out) {
   __shared__ double sh[32];
   double s = 0.0;
@@ -909,6 +931,21 @@ int salun_grad_sumsq(salun_ctx *ctx, const float *g, int64_t n, double *sumsq_de
   const int grid = grid_for(ctx, (n + 3) / 4);
   { k_sumsq_partial<<<grid, kThreads, 0, st>>>(g, n, ctx->partials); ++::salun::g_launch_count; }
   { k_sumsq_final<<<1, 256, 0, st>>>(ctx->partials, grid, sumsq_dev); ++::salun::g_launch_count; }
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+
+int salun_l1_penalty_grad(salun_ctx *ctx, const float *p, float *g, int64_t n, float alpha, double *l1_dev, void *stream) {
+  SALUN_ENTER(ctx);
+  SALUN_REQUIRE(n >= 0 && l1_dev, "n < 0 or NULL output");
+  if (n == 0) {
+    SALUN_CUDA_OK(cudaMemsetAsync(l1_dev, 0, sizeof(double), st));
+    return SALUN_OK;
+  }
+  SALUN_REQUIRE(p && g, "NULL buffer");
+  const int grid = grid_for(ctx, n);
+  { k_l1_penalty_grad<<<grid, kThreads, 0, st>>>(p, g, n, alpha, ctx->partials); ++::salun::g_launch_count; }
+  { k_sumsq_final<<<1, 256, 0, st>>>(ctx->partials, grid, l1_dev); ++::salun::g_launch_count; }
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;
 }

@@ -34,7 +34,7 @@
 
 namespace salun {
 
-typedef __nv_bfloat16 bf16;
+typedef act_t bf16;  // activation element of this build (salun_act.cuh)
 
 struct UTensor {
   std::string name;
@@ -52,7 +52,8 @@ struct UConv {
   int64_t w_off, b_off, pb_off;    // pb_off: bias of the temb_cemb_proj Linear that shares this conv's bias gradient (-1: none)
   int in, out, addend, rb_col;     // tensor ids; rb_col: column of this block's projection in RB (-1: none)
   int kc, kcp, cout_p;
-  bf16 *w_fwd, *w_dgrad, *col, *dcol;
+  wop_t *w_fwd, *w_dgrad;
+  bf16 *col, *dcol;
   float *yf;                       // CK_OUT: fp32 [M][64] GEMM output
   bf16 *dy64;                      // CK_OUT: padded 64-channel dY
   float *wg_ws;
@@ -123,7 +124,8 @@ struct salun_unet {
   int ld_rb;    // sum of the ResnetBlock output widths
   float *sincos, *ce, *pre_t, *h_t, *pre_c, *h_c, *cat, *E, *RB, *dRB, *dE, *dcat, *dh, *dpre, *dce;
   // all temb_cemb_proj Linears as one tensor-core GEMM (operands staged per step)
-  bf16 *wcat, *wcatT, *E_bf, *Et_bf, *dRB_bf, *dRBt_bf;
+  bf16 *wcat_act, *E_bf, *dRB_bf, *dRBt_bf;   // activation-side (A) operands; wcat_act: the gathered weights
+  wop_t *wcat, *wcatT, *Et_bf;                // weight-side (B) operands (bf16 build: wcat aliases wcat_act)
   float *bcat, *dWcat;
   long long *row_w, *row_b;
   int nb32;
@@ -133,7 +135,8 @@ struct salun_unet {
   bool have_drop;
   // scratch
   float *gn_partial, *S_f32;
-  bf16 *xt1, *tt, *dS;
+  bf16 *tt, *dS;
+  wop_t *xt1, *wpk;   // B operands of the attention GEMMs: transposes, and (split build) the packed K / V matrix
   WPrepEntry *wprep_table;
   WgReduceEntry *wgred_table, *wgred_host;
   std::vector<int> wg_splits;
@@ -455,10 +458,10 @@ static size_t tensor_elems(const salun_unet *net, const UTensor &t, bool flat) {
 // tensor maps per batch size
 // ------------------------------------------------------------------------------------------------------------------
 static int map_act(CUtensorMap *m, const bf16 *base, bool flat, int C, int H, int n, int pixels, int box_rows_flat) {
-  if (flat) return make_tmap_2d_bf16(m, base, (uint64_t)n * H * H, C, box_rows_flat, 64);
+  if (flat) return make_tmap_2d_act(m, base, (uint64_t)n * H * H, C, box_rows_flat);
   TmapBox4 bx;
   TRY(conv_box(H, H, pixels, &bx));
-  return make_tmap_4d_bf16(m, base, C, H + 2, H + 2, n, bx);
+  return make_tmap_4d_act(m, base, C, H + 2, H + 2, n, bx);
 }
 static int build_plan(salun_unet *net, int n, UPlan **out) {
   auto it = net->plans.find(n);
@@ -476,7 +479,7 @@ static int build_plan(salun_unet *net, int n, UPlan **out) {
     const int bn = u_pick_bn(L.cout_p, M);
     m.pair_fwd = use_pair(M, L.cout_p, bn) ? 1 : 0;
     m.pair_dg = 0;
-    TRY(make_tmap_2d_bf16(&m.fwdB, L.w_fwd, L.cout_p, L.kcp, m.pair_fwd ? bn / 2 : bn, 64));
+    TRY(make_tmap_2d_wop(&m.fwdB, L.w_fwd, L.cout_p, L.kcp, m.pair_fwd ? bn / 2 : bn));
     if (L.kind == CK_S1 || L.kind == CK_OUT) {
       const UTensor &in = net->ts[L.in];
       TRY(map_act(&m.fwdA, in.v, in.vflat, L.cin, L.H, n, 128, 128));
@@ -487,17 +490,17 @@ static int build_plan(salun_unet *net, int n, UPlan **out) {
       TRY(map_act(&m.wgA, dy, dyflat, L.cout_p, L.H, n, 64, 64));
       const int bnd = u_pick_bn(L.cin, M);
       m.pair_dg = use_pair(M, L.cin, bnd) ? 1 : 0;
-      TRY(make_tmap_2d_bf16(&m.dgB, L.w_dgrad, L.cin, (uint64_t)L.ks * L.ks * L.cout_p, m.pair_dg ? bnd / 2 : bnd, 64));
+      TRY(make_tmap_2d_wop(&m.dgB, L.w_dgrad, L.cin, (uint64_t)L.ks * L.ks * L.cout_p, m.pair_dg ? bnd / 2 : bnd));
     } else {
       // conv_in / downsample: explicit patch matrix col[M][kcp]
-      TRY(make_tmap_2d_bf16(&m.fwdA, L.col, M, L.kcp, 128, 64));
-      TRY(make_tmap_2d_bf16(&m.wgB, L.col, M, L.kcp, 64, 64));
+      TRY(make_tmap_2d_act(&m.fwdA, L.col, M, L.kcp, 128));
+      TRY(make_tmap_2d_act(&m.wgB, L.col, M, L.kcp, 64));
       const UTensor &o = net->ts[L.out];
       TRY(map_act(&m.wgA, o.g, false, L.cout, L.H, n, 64, 64));
       if (L.kind == CK_DOWN) {
         TRY(map_act(&m.dgA, o.g, false, L.cout, L.H, n, 128, 128));
         const int bnd = u_pick_bn(L.kc, M);
-        TRY(make_tmap_2d_bf16(&m.dgB, L.w_dgrad, L.kc, L.cout, bnd, 64));
+        TRY(make_tmap_2d_wop(&m.dgB, L.w_dgrad, L.kc, L.cout, bnd));
       }
     }
   }
@@ -509,27 +512,35 @@ static int build_plan(salun_unet *net, int n, UPlan **out) {
     m.bn_s = u_pick_bn(A.Te, M);
     m.bn_o = u_pick_bn(A.C, M);
     // A operands (box 128 rows) and B operands (box bn rows) over the same matrices
-    TRY(make_tmap_2d_bf16(&m.q, net->ts[A.q].v, M, A.C, 128, 64));          // A of S = Q K^T
-    TRY(make_tmap_2d_bf16(&m.k, net->ts[A.k].v, G * A.Te, A.C, m.bn_s, 64));  // B of S
-    TRY(make_tmap_2d_bf16(&m.v, net->ts[A.v].v, G * A.Te, A.C, m.bn_s, 64));  // B of dP = dO V^T
-    TRY(make_tmap_2d_bf16(&m.p, A.P, M, A.Te, 128, 64));                    // A of O = P Vt^T
-    TRY(make_tmap_2d_bf16(&m.xt_b, net->xt1, G * A.C, A.Te, m.bn_o, 64));   // B = a [C][Te] transpose (Vt, dOt, Kt, Qt)
-    TRY(make_tmap_2d_bf16(&m.tt_a, net->tt, G * A.Te, A.Te, 128, 64));      // A = a [Te][Te] transpose (Pt, dSt)
-    TRY(make_tmap_2d_bf16(&m.og, net->ts[A.o].g, M, A.C, 128, 64));         // A of dP
-    TRY(make_tmap_2d_bf16(&m.ds, net->dS, M, A.Te, 128, 64));               // A of dQ = dS Kt^T
+    // B operands that are themselves activations (K, V): the bf16 build reads them in place, the split build reads the
+    // packed copy launch_pack_wop() leaves in net->wpk
+    const wop_t *kb = kSplit ? net->wpk : reinterpret_cast<const wop_t *>(net->ts[A.k].v);
+    const wop_t *vb = kSplit ? net->wpk : reinterpret_cast<const wop_t *>(net->ts[A.v].v);
+    TRY(make_tmap_2d_act(&m.q, net->ts[A.q].v, M, A.C, 128));           // A of S = Q K^T
+    TRY(make_tmap_2d_wop(&m.k, kb, G * A.Te, A.C, m.bn_s));             // B of S
+    TRY(make_tmap_2d_wop(&m.v, vb, G * A.Te, A.C, m.bn_s));             // B of dP = dO V^T
+    TRY(make_tmap_2d_act(&m.p, A.P, M, A.Te, 128));                     // A of O = P Vt^T
+    TRY(make_tmap_2d_wop(&m.xt_b, net->xt1, G * A.C, A.Te, m.bn_o));    // B = a [C][Te] transpose (Vt, dOt, Kt, Qt)
+    TRY(make_tmap_2d_act(&m.tt_a, net->tt, G * A.Te, A.Te, 128));       // A = a [Te][Te] transpose (Pt, dSt)
+    TRY(make_tmap_2d_act(&m.og, net->ts[A.o].g, M, A.C, 128));          // A of dP
+    TRY(make_tmap_2d_act(&m.ds, net->dS, M, A.Te, 128));                // A of dQ = dS Kt^T
   }
   {
     const int E8 = net->emb + 512, R = net->ld_rb;
     plan.bn_rb = u_pick_bn(R, n);
     plan.bn_de = u_pick_bn(E8, n);
     plan.bn_dw = u_pick_bn(E8, R);
-    TRY(make_tmap_2d_bf16(&plan.e_a, net->E_bf, n, E8, 128, 64));
-    TRY(make_tmap_2d_bf16(&plan.wcat_b, net->wcat, R, E8, plan.bn_rb, 64));
-    TRY(make_tmap_2d_bf16(&plan.drb_a, net->dRB_bf, n, R, 128, 64));
-    TRY(make_tmap_2d_bf16(&plan.wcatT_b, net->wcatT, E8, R, plan.bn_de, 64));
-    // K = the batch: columns >= n are zero-filled by TMA (the buffers keep stale rows of larger batches)
-    TRY(make_tmap_2d_bf16_ld(&plan.drbt_a, net->dRBt_bf, R, n, net->nb32, 128, 64));
-    TRY(make_tmap_2d_bf16_ld(&plan.et_b, net->Et_bf, E8, n, net->nb32, plan.bn_dw, 64));
+    TRY(make_tmap_2d_act(&plan.e_a, net->E_bf, n, E8, 128));
+    TRY(make_tmap_2d_wop(&plan.wcat_b, net->wcat, R, E8, plan.bn_rb));
+    TRY(make_tmap_2d_act(&plan.drb_a, net->dRB_bf, n, R, 128));
+    TRY(make_tmap_2d_wop(&plan.wcatT_b, net->wcatT, E8, R, plan.bn_de));
+    // K = the batch: columns >= n of the A operand are zero-filled by TMA (the buffers keep stale rows of larger batches).
+    // Split build: the B rows span the whole pitch ([dup(hi) | dup(lo)] of logical length nb32) and K runs over nb32.
+    TRY(make_tmap_2d_bf16_ld(&plan.drbt_a, net->dRBt_bf, R, (uint64_t)n * kActK, (uint64_t)net->nb32 * kActK, 128, 64));
+    if (kSplit)
+      TRY(make_tmap_2d_wop(&plan.et_b, net->Et_bf, E8, net->nb32, plan.bn_dw));
+    else
+      TRY(make_tmap_2d_bf16_ld(&plan.et_b, net->Et_bf, E8, n, net->nb32, plan.bn_dw, 64));
   }
   {
     std::vector<SumEntry> tab;
@@ -637,10 +648,11 @@ static int attn_forward(salun_unet *net, const UAttn &A, const UAttnMaps &m, int
   const int M = n * A.T, G = (M + A.Te - 1) / A.Te;
   const float scale = 1.f / sqrtf((float)A.C);
   // S = Q K^T (per group), fp32
+  launch_pack_wop(net->ts[A.k].v, net->wpk, (long long)G * A.Te, A.C, st);
   TRY(gemm_plain(m.q, m.k, M, A.Te, A.C, nullptr, net->S_f32, A.Te, A.Te, A.Te, m.bn_s, st));
   launch_softmax(net->S_f32, A.P, M, A.Te, A.T, scale, st);
   // O = P V : B operand = V^T per group
-  launch_transpose(net->ts[A.v].v, A.C, net->xt1, A.Te, A.C, G, st);
+  launch_transpose_wop(net->ts[A.v].v, A.C, net->xt1, A.Te, A.C, G, st);
   TRY(gemm_plain(m.p, m.xt_b, M, A.C, A.Te, net->ts[A.o].v, nullptr, A.C, A.Te, A.C, m.bn_o, st));
   return SALUN_OK;
 }
@@ -659,8 +671,9 @@ static int emb_forward(salun_unet *net, const UPlan &plan, int n, bool save, cud
   launch_swish_f32(net->cat, net->E, (long long)n * E8, st);
   // RB[n][ld_rb] = E . Wcat^T + bcat : the temb_cemb_proj Linear of every ResnetBlock (diffusion.py:131-132) in one GEMM
   launch_f32_to_bf16(net->E, E8, net->E_bf, E8, n, E8, st);
-  launch_gather_proj(P, net->row_w, net->row_b, net->wcat, net->bcat, net->ld_rb, E8, st);
-  if (save) launch_transpose(net->wcat, E8, net->wcatT, net->ld_rb, E8, 1, st);
+  launch_gather_proj(P, net->row_w, net->row_b, net->wcat_act, net->bcat, net->ld_rb, E8, st);
+  launch_pack_wop(net->wcat_act, net->wcat, net->ld_rb, E8, st);   // bf16 build: wcat aliases wcat_act, nothing to do
+  if (save) launch_transpose_wop(net->wcat_act, E8, net->wcatT, net->ld_rb, E8, 1, st);
   TRY(gemm_plain(plan.e_a, plan.wcat_b, n, net->ld_rb, E8, nullptr, net->RB, net->ld_rb, 0, 0, plan.bn_rb, st, net->bcat));
   return SALUN_OK;
 }
@@ -750,12 +763,13 @@ static int wgrad_conv(salun_unet *net, int ci, const UConvMaps &m, int n, cudaSt
   a.kw = (L.kind == CK_S1 || L.kind == CK_OUT) ? L.ks : 1;
   a.tap_y0 = a.tap_x0 = (a.kw == 3) ? 0 : 1;
   a.H = a.W = L.H;
-  a.total_blocks = L.kcp / 64;
-  a.n_blocks = wgrad_pick_blocks(a.total_blocks);
+  const WgradGeom geo = wgrad_geometry(L.cout, L.kcp);
+  a.total_blocks = geo.total_blocks;
+  a.n_blocks = geo.n_blocks;
   a.Cout = L.cout;
   a.ldw = L.kc;
   a.kvalid = L.kc;
-  const int co_tiles = (L.cout + 127) / 128, groups = a.total_blocks / a.n_blocks;
+  const int co_tiles = geo.co_tiles, groups = geo.groups;
   int splits = net->ctx->num_sms / (co_tiles * groups);
   if (splits < 1) splits = 1;
   if (splits > L.wg_splits_max) splits = L.wg_splits_max;
@@ -820,17 +834,18 @@ static int attn_backward(salun_unet *net, const UAttn &A, const UAttnMaps &m, in
   UTensor &q = net->ts[A.q], &k = net->ts[A.k], &v = net->ts[A.v], &o = net->ts[A.o];
   // dV[j][c] = sum_i P[i][j] dO[i][c] : A = P^T, B = dO^T
   launch_transpose(A.P, A.Te, net->tt, A.Te, A.Te, G, st);
-  launch_transpose(o.g, A.C, net->xt1, A.Te, A.C, G, st);
+  launch_transpose_wop(o.g, A.C, net->xt1, A.Te, A.C, G, st);
   TRY(gemm_plain(m.tt_a, m.xt_b, M, A.C, A.Te, v.g, nullptr, A.C, A.Te, A.C, m.bn_o, st));
   // dP = dO V^T (fp32), dS = scale * P * (dP - rowsum(dP * P))
+  launch_pack_wop(v.v, net->wpk, (long long)G * A.Te, A.C, st);
   TRY(gemm_plain(m.og, m.v, M, A.Te, A.C, nullptr, net->S_f32, A.Te, A.Te, A.Te, m.bn_s, st));
   launch_softmax_bwd(net->S_f32, A.P, net->dS, M, A.Te, scale, st);
   // dQ = dS K : B = K^T
-  launch_transpose(k.v, A.C, net->xt1, A.Te, A.C, G, st);
+  launch_transpose_wop(k.v, A.C, net->xt1, A.Te, A.C, G, st);
   TRY(gemm_plain(m.ds, m.xt_b, M, A.C, A.Te, q.g, nullptr, A.C, A.Te, A.C, m.bn_o, st));
   // dK[j][c] = sum_i dS[i][j] Q[i][c] : A = dS^T, B = Q^T
   launch_transpose(net->dS, A.Te, net->tt, A.Te, A.Te, G, st);
-  launch_transpose(q.v, A.C, net->xt1, A.Te, A.C, G, st);
+  launch_transpose_wop(q.v, A.C, net->xt1, A.Te, A.C, G, st);
   TRY(gemm_plain(m.tt_a, m.xt_b, M, A.C, A.Te, k.g, nullptr, A.C, A.Te, A.C, m.bn_o, st));
   q.g_live = k.g_live = v.g_live = true;
   return SALUN_OK;
@@ -843,9 +858,9 @@ static int emb_backward(salun_unet *net, const UPlan &plan, int n, float *gdst, 
   const int R = net->ld_rb;
   launch_f32_to_bf16(net->dRB, R, net->dRB_bf, R, n, R, st);
   launch_transpose(net->dRB_bf, R, net->dRBt_bf, net->nb32, R, 1, st);
-  launch_transpose(net->E_bf, E8, net->Et_bf, net->nb32, E8, 1, st);
+  launch_transpose_wop(net->E_bf, E8, net->Et_bf, net->nb32, E8, 1, st);
   TRY(gemm_plain(plan.drb_a, plan.wcatT_b, n, E8, R, nullptr, net->dE, E8, 0, 0, plan.bn_de, st));
-  TRY(gemm_plain(plan.drbt_a, plan.et_b, R, E8, n, nullptr, net->dWcat, E8, 0, 0, plan.bn_dw, st));
+  TRY(gemm_plain(plan.drbt_a, plan.et_b, R, E8, kSplit ? net->nb32 : n, nullptr, net->dWcat, E8, 0, 0, plan.bn_dw, st));
   launch_scatter_rows(net->dWcat, net->row_w, gdst, R, E8, st);
   launch_dswish_f32(net->dE, net->cat, net->dcat, (long long)n * E8, st);
   for (int br = 0; br < 2; ++br) {  // 0: temb, 1: cemb
@@ -927,6 +942,7 @@ static int backward_impl(salun_unet *net, const float *d_eps, int accumulate, cu
     e.dst_off = L.w_off;
     e.count = (long long)L.cout * L.kc;
     e.splits = net->wg_splits[i];
+    e.kc = L.kc;
   }
   SALUN_CUDA_OK(cudaMemcpyAsync(net->wgred_table, net->wgred_host, net->convs.size() * sizeof(WgReduceEntry),
                                 cudaMemcpyHostToDevice, st));
@@ -947,7 +963,7 @@ __global__ void k_export_nchw(const bf16 *__restrict__ src, int flat, float *__r
     const int b = (int)(i / ((long long)H * H * C));
     const size_t off = flat ? (((size_t)b * H + y) * H + x) * C + c
                             : (((size_t)b * (H + 2) + y + 1) * (H + 2) + x + 1) * C + c;
-    out[i] = __bfloat162float(src[off]);
+    out[i] = act_to_float(src[off]);
   }
 }
 
@@ -1014,7 +1030,7 @@ int salun_unet_create(salun_ctx *ctx, const salun_unet_cfg *cfg, float *params, 
   }
   const int nb = (cfg->max_batch + 7) / 8 * 8;
   net->nb = nb;
-  size_t max_part = 1, max_S = 1, max_xt = 1, max_tt = 1;
+  size_t max_part = 1, max_S = 1, max_xt = 1, max_tt = 1, max_pk = 1;
   for (UTensor &t : net->ts) {
     A(dmalloc(net, &t.v, tensor_elems(net, t, t.vflat)));
     if (t.need_g) A(dmalloc(net, &t.g, tensor_elems(net, t, t.gflat)));
@@ -1032,19 +1048,19 @@ int salun_unet_create(salun_ctx *ctx, const salun_unet_cfg *cfg, float *params, 
   }
   for (UConv &L : net->convs) {
     const size_t M = (size_t)nb * L.H * L.H;
-    A(dmalloc(net, &L.w_fwd, (size_t)L.cout_p * L.kcp));
-    if (L.kind != CK_IN) A(dmalloc(net, &L.w_dgrad, (size_t)L.cout_p * L.kc));
+    A(dmalloc(net, &L.w_fwd, (size_t)L.cout_p * L.kcp * kWopK));
+    if (L.kind != CK_IN) A(dmalloc(net, &L.w_dgrad, (size_t)L.cout_p * L.kc * kWopK));
     if (L.kind == CK_IN || L.kind == CK_DOWN) A(dmalloc(net, &L.col, M * L.kcp));
     if (L.kind == CK_DOWN) A(dmalloc(net, &L.dcol, M * L.kc));
     if (L.kind == CK_OUT) {
       A(dmalloc(net, &L.yf, M * 64));
       A(dmalloc(net, &L.dy64, (size_t)nb * (L.H + 2) * (L.H + 2) * 64));
     }
-    const int total_blocks = L.kcp / 64, nb_ = wgrad_pick_blocks(total_blocks);
-    const int tiles = ((L.cout + 127) / 128) * (total_blocks / nb_);
+    const WgradGeom geo = wgrad_geometry(L.cout, L.kcp);
+    const int tiles = geo.co_tiles * geo.groups;
     L.wg_splits_max = ctx->num_sms / tiles;
     if (L.wg_splits_max < 1) L.wg_splits_max = 1;
-    A(dmalloc(net, &L.wg_ws, (size_t)L.wg_splits_max * L.cout * L.kc, false));
+    A(dmalloc(net, &L.wg_ws, (size_t)L.wg_splits_max * wgrad_ws_elems(L.cout, L.kc), false));
     {
       size_t rows = 0;  // the largest n * slices_for(H, n) over n <= nb
       for (int b = 1; b <= nb; ++b) {
@@ -1061,11 +1077,13 @@ int salun_unet_create(salun_ctx *ctx, const salun_unet_cfg *cfg, float *params, 
     const size_t G = Mp / At.Te;
     if (G * At.C * At.Te > max_xt) max_xt = G * At.C * At.Te;
     if (G * At.Te * At.Te > max_tt) max_tt = G * At.Te * At.Te;
+    if (Mp * At.C > max_pk) max_pk = Mp * At.C;
   }
   A(dmalloc(net, &net->gn_partial, max_part));
   A(dmalloc(net, &net->S_f32, max_S));
   A(dmalloc(net, &net->dS, max_S));
-  A(dmalloc(net, &net->xt1, max_xt));
+  A(dmalloc(net, &net->xt1, max_xt * kWopK));
+  if (kSplit) A(dmalloc(net, &net->wpk, max_pk * kWopK));
   A(dmalloc(net, &net->tt, max_tt));
   A(dmalloc(net, &net->gscratch, (size_t)net->n_params));
   {
@@ -1087,13 +1105,17 @@ int salun_unet_create(salun_ctx *ctx, const salun_unet_cfg *cfg, float *params, 
     A(dmalloc(net, &net->dRB, (size_t)nb * net->ld_rb));
     {
       const size_t R = net->ld_rb;
-      net->nb32 = (nb + 31) / 32 * 32;
-      A(dmalloc(net, &net->wcat, R * E8));
-      A(dmalloc(net, &net->wcatT, R * E8));
+      net->nb32 = (nb + 63) / 64 * 64;   // K pitch of the batch-contracting projection GEMM (whole k-blocks)
+      A(dmalloc(net, &net->wcat_act, R * E8));
+      if (kSplit)
+        A(dmalloc(net, &net->wcat, R * E8 * kWopK));
+      else
+        net->wcat = reinterpret_cast<wop_t *>(net->wcat_act);
+      A(dmalloc(net, &net->wcatT, R * E8 * kWopK));
       A(dmalloc(net, &net->bcat, R));
       A(dmalloc(net, &net->dWcat, R * E8));
       A(dmalloc(net, &net->E_bf, (size_t)net->nb32 * E8));
-      A(dmalloc(net, &net->Et_bf, (size_t)net->nb32 * E8));
+      A(dmalloc(net, &net->Et_bf, (size_t)net->nb32 * E8 * kWopK));
       A(dmalloc(net, &net->dRB_bf, (size_t)net->nb32 * R));
       A(dmalloc(net, &net->dRBt_bf, (size_t)net->nb32 * R));
       std::vector<long long> rw(R), rbv(R);

@@ -9,7 +9,7 @@
 
 namespace salun {
 
-typedef __nv_bfloat16 bf16;
+typedef act_t bf16;  // activation element of this build (salun_act.cuh)
 
 namespace {
 
@@ -17,32 +17,20 @@ constexpr int kT = 256;
 constexpr int kU = 4;   // rows in flight per thread in the per-sample streaming kernels (memory-level parallelism)
 constexpr int kUb = 2;  // ... in the register-heavy GroupNorm backward kernels
 
-__device__ __forceinline__ void u_ld8(const bf16 *p, float (&f)[8]) {
-  const uint4 v = *reinterpret_cast<const uint4 *>(p);
-  const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 t = __bfloat1622float2(h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
-}
-__device__ __forceinline__ uint4 u_ldraw(const bf16 *p) { return *reinterpret_cast<const uint4 *>(p); }
-__device__ __forceinline__ void u_cvt8(const uint4 &v, float (&f)[8]) {
-  const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 t = __bfloat1622float2(h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
-}
-__device__ __forceinline__ void u_st8(bf16 *p, const float (&f)[8]) {
-  uint4 v;
-  __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&v);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-  *reinterpret_cast<uint4 *>(p) = v;
+__device__ __forceinline__ void u_ld8(const bf16 *p, float (&f)[8]) { ld8(p, f); }
+__device__ __forceinline__ avec u_ldraw(const bf16 *p) { return ldvec(p); }
+__device__ __forceinline__ void u_cvt8(const avec &v, float (&f)[8]) { cvt8(v, f); }
+__device__ __forceinline__ void u_st8(bf16 *p, const float (&f)[8]) { st8(p, f); }
+__device__ __forceinline__ void st4(bf16 *p, const float4 &v) {   // 4 activation elements, p 4-element aligned
+#ifdef SALUN_SPLIT
+  *reinterpret_cast<uint4 *>(p) = make_uint4(act_pack_pair(v.x), act_pack_pair(v.y), act_pack_pair(v.z), act_pack_pair(v.w));
+#else
+  uint2 o;
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  o.x = *reinterpret_cast<uint32_t *>(&a);
+  o.y = *reinterpret_cast<uint32_t *>(&b);
+  *reinterpret_cast<uint2 *>(p) = o;
+#endif
 }
 // element offset of pixel p (0 .. H*H-1) of image n, channel 0
 __device__ __forceinline__ size_t pix_off(int n, int p, int H, int C, int flat) {
@@ -72,6 +60,9 @@ __device__ __forceinline__ void drop8(uint32_t seed, uint32_t e0, uint32_t thr16
 }
 // sigmoid through one MUFU op (tanh.approx, rel. error ~2^-11: below the bf16 rounding of everything it feeds)
 __device__ __forceinline__ float sigmoidf_(float x) {
+#ifdef SALUN_SPLIT
+  return 1.f / (1.f + expf(-x));  // the split build carries 16+ significand bits: full-precision transcendental
+#endif
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
   return fmaf(0.5f, t, 0.5f);
@@ -130,7 +121,7 @@ __global__ void __launch_bounds__(kT) k_gn_stats(const bf16 *__restrict__ x, flo
   if (active) {
     const int end = (s + 1) * rps;
     for (int p = s * rps + r; p < end; p += rl * kU) {
-      uint4 raw[kU];
+      avec raw[kU];
 #pragma unroll
       for (int u = 0; u < kU; ++u)
         if (p + u * rl < end) raw[u] = u_ldraw(x + pix_off(n, p + u * rl, H, C, 0) + v * 8);
@@ -207,7 +198,7 @@ __global__ void __launch_bounds__(kT) k_gn_apply(const bf16 *__restrict__ x, con
   }
   const int end = (s + 1) * rps;
   for (int p0 = s * rps + r; p0 < end; p0 += rl * kU) {
-    uint4 raw[kU];
+    avec raw[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u)
       if (p0 + u * rl < end) raw[u] = u_ldraw(x + pix_off(n, p0 + u * rl, H, C, 0) + c0);
@@ -342,7 +333,7 @@ __global__ void __launch_bounds__(kT) k_gn_bwd_reduce(bf16 *__restrict__ dout, c
     gn_load_ch(ch, stats, gamma, beta, n, c0, cpg);
     const int end = (s + 1) * rps;
     for (int p0 = s * rps + r; p0 < end; p0 += rl * kUb) {
-      uint4 rx[kUb], rd[kUb];
+      avec rx[kUb], rd[kUb];
 #pragma unroll
       for (int u = 0; u < kUb; ++u)
         if (p0 + u * rl < end) {
@@ -424,14 +415,14 @@ __global__ void __launch_bounds__(kT) k_gn_bwd_apply(const bf16 *__restrict__ dy
   }
   const int end = (s + 1) * rps;
   for (int p0 = s * rps + r; p0 < end; p0 += rl * kU) {
-    uint4 rx[kU], rd[kU], ro[kU];
+    avec rx[kU], rd[kU], ro[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u)
       if (p0 + u * rl < end) {
         const size_t po = pix_off(n, p0 + u * rl, H, C, 0) + c0;
         rx[u] = u_ldraw(x + po);
         rd[u] = u_ldraw(dyh_flat + pix_off(n, p0 + u * rl, H, C, 1) + c0);
-        ro[u] = accumulate ? u_ldraw(dx + po) : make_uint4(0, 0, 0, 0);
+        ro[u] = accumulate ? u_ldraw(dx + po) : avec_zero();
       }
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
@@ -511,7 +502,7 @@ __global__ void __launch_bounds__(kT) k_colsum(const bf16 *__restrict__ dy, int 
   if (active) {
     const int end = (s + 1) * rps;
     for (int p = s * rps + r; p < end; p += rl * kU) {
-      uint4 raw[kU];
+      avec raw[kU];
 #pragma unroll
       for (int u = 0; u < kU; ++u)
         if (p + u * rl < end) raw[u] = u_ldraw(dy + pix_off(n, p + u * rl, H, C, flat) + v * 8);
@@ -566,9 +557,8 @@ __global__ void __launch_bounds__(kT) k_concat(const bf16 *__restrict__ a, int C
     const int m = (int)(i / vecs);
     const int n = m / hw, p = m - n * hw;
     const int c = v * 8;
-    const uint4 val = c < Ca ? *reinterpret_cast<const uint4 *>(a + pix_off(n, p, H, Ca, 0) + c)
-                             : *reinterpret_cast<const uint4 *>(b + pix_off(n, p, H, Cb, 0) + (c - Ca));
-    *reinterpret_cast<uint4 *>(out + pix_off(n, p, H, C, 0) + c) = val;
+    const avec val = c < Ca ? ldvec(a + pix_off(n, p, H, Ca, 0) + c) : ldvec(b + pix_off(n, p, H, Cb, 0) + (c - Ca));
+    stvec(out + pix_off(n, p, H, C, 0) + c, val);
   }
 }
 void launch_concat(const bf16 *a_pad, int Ca, const bf16 *b_pad, int Cb, bf16 *out_pad, int n, int H, cudaStream_t st) {
@@ -606,7 +596,7 @@ __global__ void __launch_bounds__(kT) k_add_into(const bf16 *__restrict__ src, b
                                                  long long nvec) {
   for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < nvec; i += (long long)gridDim.x * kT) {
     if (!accumulate) {
-      reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(src)[i];
+      stvec(dst + i * 8, ldvec(src + i * 8));
     } else {
       float a[8], b[8];
       u_ld8(src + i * 8, a);
@@ -630,8 +620,8 @@ __global__ void __launch_bounds__(kT) k_upsample2(const bf16 *__restrict__ in, b
     const int m = (int)(i / vecs);
     const int n = m / hwo, p = m - n * hwo;
     const int y = p / Ho, x = p - y * Ho;
-    const uint4 val = *reinterpret_cast<const uint4 *>(in + pix_off(n, (y >> 1) * H + (x >> 1), H, C, 0) + v * 8);
-    *reinterpret_cast<uint4 *>(out + pix_off(n, p, Ho, C, 0) + v * 8) = val;
+    const avec val = ldvec(in + pix_off(n, (y >> 1) * H + (x >> 1), H, C, 0) + v * 8);
+    stvec(out + pix_off(n, p, Ho, C, 0) + v * 8, val);
   }
 }
 void launch_upsample2(const bf16 *in_pad, bf16 *out_pad, int n, int H, int C, cudaStream_t st) {
@@ -686,8 +676,8 @@ __global__ void __launch_bounds__(kT) k_down_im2col(const bf16 *__restrict__ in,
     const int oy = p / Ho, ox = p - oy * Ho;
     const int ky = tap / 3, kx = tap - ky * 3;
     const int py = 2 * oy + ky + 1, px = 2 * ox + kx + 1;
-    const uint4 val = *reinterpret_cast<const uint4 *>(in + (((size_t)n * Hp + py) * Hp + px) * C + v * 8);
-    *reinterpret_cast<uint4 *>(col + ((size_t)mo * 9 + tap) * C + v * 8) = val;
+    const avec val = ldvec(in + (((size_t)n * Hp + py) * Hp + px) * C + v * 8);
+    stvec(col + ((size_t)mo * 9 + tap) * C + v * 8, val);
   }
 }
 void launch_down_im2col(const bf16 *in_pad, bf16 *col, int n, int H, int C, cudaStream_t st) {
@@ -802,12 +792,12 @@ __global__ void __launch_bounds__(256) k_softmax(const float *__restrict__ S, bf
   for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   float sum = 0.f;
   for (int i = 0; i < per; ++i) {
-    v[i] = v[i] == -INFINITY ? 0.f : __expf(v[i] - mx);
+    v[i] = v[i] == -INFINITY ? 0.f : (kSplit ? expf(v[i] - mx) : __expf(v[i] - mx));
     sum += v[i];
   }
   for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float inv = 1.f / sum;
-  for (int i = 0; i < per; ++i) P[(size_t)row * Te + lane + 32 * i] = __float2bfloat16(v[i] * inv);
+  for (int i = 0; i < per; ++i) P[(size_t)row * Te + lane + 32 * i] = act_from_float(v[i] * inv);
 }
 void launch_softmax(const float *S, bf16 *P, int M, int Te, int T, float scale, cudaStream_t st) {
   k_softmax<<<(M + 7) / 8, 256, 0, st>>>(S, P, M, Te, T, scale);
@@ -821,34 +811,70 @@ __global__ void __launch_bounds__(256) k_softmax_bwd(const float *__restrict__ d
   float p[8], d[8], dot = 0.f;
   for (int i = 0; i < per; ++i) {
     const size_t j = (size_t)row * Te + lane + 32 * i;
-    p[i] = __bfloat162float(P[j]);
+    p[i] = act_to_float(P[j]);
     d[i] = dP[j];
     dot += p[i] * d[i];
   }
   for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
   for (int i = 0; i < per; ++i)
-    dS[(size_t)row * Te + lane + 32 * i] = __float2bfloat16(scale * p[i] * (d[i] - dot));
+    dS[(size_t)row * Te + lane + 32 * i] = act_from_float(scale * p[i] * (d[i] - dot));
 }
 void launch_softmax_bwd(const float *dP, const bf16 *P, bf16 *dS, int M, int Te, float scale, cudaStream_t st) {
   k_softmax_bwd<<<(M + 7) / 8, 256, 0, st>>>(dP, P, dS, M, Te, scale);
   ++g_launch_count;
 }
-__global__ void __launch_bounds__(256) k_transpose(const bf16 *__restrict__ in, int ld_in, bf16 *__restrict__ out, int R,
+// kWop: the result is a prepared weight-side operand (rows of logical length R, salun_act.cuh) instead of an activation
+template <bool kWop>
+__global__ void __launch_bounds__(256) k_transpose(const bf16 *__restrict__ in, int ld_in, void *__restrict__ out, int R,
                                                    int Cc) {
-  __shared__ bf16 tile[32][34];
+  __shared__ float tile[32][33];
   const int g = blockIdx.z, c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const bf16 *src = in + (size_t)g * R * ld_in;
-  bf16 *dst = out + (size_t)g * Cc * R;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) tile[ty + 8 * j][tx] = src[(size_t)(r0 + ty + 8 * j) * ld_in + c0 + tx];
+  for (int j = 0; j < 4; ++j) tile[ty + 8 * j][tx] = act_to_float(src[(size_t)(r0 + ty + 8 * j) * ld_in + c0 + tx]);
   __syncthreads();
 #pragma unroll
-  for (int j = 0; j < 4; ++j) dst[(size_t)(c0 + ty + 8 * j) * R + r0 + tx] = tile[tx][ty + 8 * j];
+  for (int j = 0; j < 4; ++j) {
+    const size_t orow = (size_t)g * Cc + c0 + ty + 8 * j;
+    if (kWop)
+      wop_store(reinterpret_cast<wop_t *>(out) + orow * R * kWopK, r0 + tx, R, tile[tx][ty + 8 * j]);
+    else
+      reinterpret_cast<bf16 *>(out)[orow * R + r0 + tx] = act_from_float(tile[tx][ty + 8 * j]);
+  }
 }
 void launch_transpose(const bf16 *in, int ld_in, bf16 *out, int R, int Cc, int G, cudaStream_t st) {
-  k_transpose<<<dim3(Cc / 32, R / 32, G), 256, 0, st>>>(in, ld_in, out, R, Cc);
+  k_transpose<false><<<dim3(Cc / 32, R / 32, G), 256, 0, st>>>(in, ld_in, out, R, Cc);
   ++g_launch_count;
+}
+void launch_transpose_wop(const bf16 *in, int ld_in, wop_t *out, int R, int Cc, int G, cudaStream_t st) {
+  k_transpose<true><<<dim3(Cc / 32, R / 32, G), 256, 0, st>>>(in, ld_in, out, R, Cc);
+  ++g_launch_count;
+}
+#ifdef SALUN_SPLIT
+__global__ void __launch_bounds__(256) k_pack_wop(const bf16 *__restrict__ in, wop_t *__restrict__ out, long long total, int K) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long r = i / K;
+    const int k = (int)(i - r * K);
+    const bf16 v = in[i];   // the (hi, lo) pair is already split: no re-rounding
+    wop_t *row = out + (size_t)r * K * kWopK;
+    *reinterpret_cast<__nv_bfloat162 *>(row + 2 * k) = __nv_bfloat162(v.hi, v.hi);
+    *reinterpret_cast<__nv_bfloat162 *>(row + 2 * (size_t)K + 2 * k) = __nv_bfloat162(v.lo, v.lo);
+  }
+}
+#endif
+const wop_t *launch_pack_wop(const bf16 *in, wop_t *out, long long rows, int K, cudaStream_t st) {
+#ifdef SALUN_SPLIT
+  const long long total = rows * K;
+  long long g = (total + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  k_pack_wop<<<(int)g, 256, 0, st>>>(in, out, total, K);
+  ++g_launch_count;
+  return out;
+#else
+  (void)out; (void)rows; (void)K; (void)st;
+  return in;
+#endif
 }
 
 // =================================================================================================================
@@ -994,11 +1020,7 @@ __global__ void __launch_bounds__(256) k_gather_proj(const float *__restrict__ p
   const float *src = params + row_w[r];
   for (int k = threadIdx.x * 4; k < K; k += 256 * 4) {
     const float4 v = *reinterpret_cast<const float4 *>(src + k);
-    uint2 o;
-    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-    o.x = *reinterpret_cast<uint32_t *>(&a);
-    o.y = *reinterpret_cast<uint32_t *>(&b);
-    *reinterpret_cast<uint2 *>(wcat + (size_t)r * K + k) = o;
+    st4(wcat + (size_t)r * K + k, v);
   }
   if (threadIdx.x == 0) bcat[r] = params[row_b[r]];
 }
@@ -1026,11 +1048,7 @@ __global__ void __launch_bounds__(256) k_f32_to_bf16(const float *__restrict__ i
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < (long long)rows * c4; i += (long long)gridDim.x * 256) {
     const int r = (int)(i / c4), j = (int)(i % c4) * 4;
     const float4 v = *reinterpret_cast<const float4 *>(in + (size_t)r * ld_in + j);
-    uint2 o;
-    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-    o.x = *reinterpret_cast<uint32_t *>(&a);
-    o.y = *reinterpret_cast<uint32_t *>(&b);
-    *reinterpret_cast<uint2 *>(out + (size_t)r * ld_out + j) = o;
+    st4(out + (size_t)r * ld_out + j, v);
   }
 }
 void launch_f32_to_bf16(const float *in, int ld_in, bf16 *out, int ld_out, int rows, int cols, cudaStream_t st) {

@@ -103,20 +103,23 @@ class UNetEngine:
     native_layout = True  # conv weights are stored OHWI in the arena (flat.FlatSaliency converts before the top-k)
 
     def __init__(self, config, max_batch: int = 256, device=None, ctx: Optional[SalunContext] = None,
-                 symmetric: bool = False, share_with: Optional["UNetEngine"] = None):
+                 symmetric: bool = False, share_with: Optional["UNetEngine"] = None, precision: Optional[str] = None):
         """symmetric=True allocates the parameter / gradient arenas as torch symmetric memory (NVLink peer-mapped), which
         DistMaskedAdam needs for its fused reduce-scatter + clip + mask + Adam + all-gather kernels.
         share_with=<engine> builds a second set of activation buffers over the SAME parameter arena (a forward-only
-        replica, e.g. for running the no-grad pseudo-label pass on another stream next to the main pass)."""
+        replica, e.g. for running the no-grad pseudo-label pass on another stream next to the main pass).
+        precision: "bf16" (default) or "split" (bf16 hi/lo pairs, fp32-class products: the mask-generation mode)."""
         if share_with is not None:
             ctx = share_with.ctx if ctx is None else ctx
+            precision = share_with.precision if precision is None else precision
+        self.precision = precision or "bf16"
         m, d = config.model, config.data
         if not m.resamp_with_conv:
             raise NotImplementedError("resamp_with_conv=False is not used by the SalUn configs")
         self.config = config
         self.ctx = ctx if ctx is not None else SalunContext(device)
         self.device = self.ctx.device
-        self._lib = _lib.lib()
+        self._lib = _lib.lib(self.precision)
         self.max_batch = int(max_batch)
         mult, attn = list(m.ch_mult), list(m.attn_resolutions)
         self.cfg = salun_unet_cfg(m.ch, len(mult), (C.c_int * 8)(*mult), m.num_res_blocks, len(attn), (C.c_int * 8)(*attn),

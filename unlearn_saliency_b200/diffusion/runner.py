@@ -15,7 +15,7 @@ reference copies every gradient to the CPU every batch, :992-996) and the top-k 
 from __future__ import annotations
 
 import os
-from typing import Dict, Optional
+from typing import Dict, Optional, Tuple
 
 import numpy as np
 import torch
@@ -152,9 +152,12 @@ class DDPMEngineUnlearner:
     """UNetEngine + fused tail: the loop bodies of Diffusion.generate_mask / Diffusion.saliency_unlearn with every model
     call on the sm_100a engine.  `mask`: the dict torch.load(mask_path) gives (CPU int64, ``module.`` keys); None = no mask.
 
-    Data parallel (torch.distributed initialised, world W): each rank runs its shard of the two mini-batches with
-    dL/d(eps) pre-scaled by 1/W, ONE all-reduce(sum) of the flat gradient arena gives the DDP-averaged gradient, and
-    every rank applies the identical clip + mask + Adam (clip uses the global norm)."""
+    Data parallel (torch.distributed initialised, world W): each rank runs the samples it is handed with dL/d(eps)
+    pre-scaled by 1/W, ONE all-reduce(sum) of the flat gradient arena (or the fused peer-memory exchange) gives the
+    rank-averaged gradient, and every rank applies the identical clip + mask + Adam (clip uses the global norm,
+    SURVEY.md section 7.3).  ``Diffusion.saliency_unlearn`` hands every rank its contiguous SHARD of one global
+    mini-batch (what nn.DataParallel's scatter does, runners/diffusion.py:505) and passes ``global_counts`` so that the
+    averaged gradient is exactly the gradient of the global-batch loss, also for uneven shards."""
 
     def __init__(self, engine, betas, lr=1e-4, beta1=0.9, eps=1e-8, weight_decay=0.0, grad_clip=1.0,
                  mask: Optional[Dict[str, torch.Tensor]] = None):
@@ -202,13 +205,15 @@ class DDPMEngineUnlearner:
         if self._overlap and self._pseudo_stream is not None:
             torch.cuda.current_stream(self.device).wait_stream(self._pseudo_stream)
 
-    def _weights(self, nr, nf, alpha, method, chw, scale):
-        """per-sample loss weights: loss = sum_i w_i * sum_chw (eps_i - target_i)^2  (losses.py:33-37, diffusion.py:552-572)"""
-        key = (nr, nf, float(alpha), method, chw, float(scale))
+    def _weights(self, nr, nf, alpha, method, chw, scale, nr_w=None, nf_w=None):
+        """per-sample loss weights: loss = sum_i w_i * sum_chw (eps_i - target_i)^2  (losses.py:33-37, diffusion.py:552-572);
+        nr_w / nf_w: the divisor of the two batch means (the local counts unless the samples are a shard)."""
+        nr_w, nf_w = float(nr if nr_w is None else nr_w), float(nf if nf_w is None else nf_w)
+        key = (nr, nf, float(alpha), method, chw, float(scale), nr_w, nf_w)
         w = self._w_cache.get(key)
         if w is None:
-            wf = 1.0 / (nf * chw) if method == "rl" else -1.0 / nf
-            w = torch.cat([torch.full((nr,), alpha / nr), torch.full((nf,), wf)]).mul_(scale).to(self.device)
+            wf = 1.0 / (nf_w * chw) if method == "rl" else -1.0 / nf_w
+            w = torch.cat([torch.full((nr,), alpha / nr_w), torch.full((nf,), wf)]).mul_(scale).to(self.device)
             self._w_cache[key] = w
         return w
 
@@ -274,9 +279,12 @@ class DDPMEngineUnlearner:
 
     # ---- runners/diffusion.py:519-593 -------------------------------------------------------------------------
     def saliency_unlearn_step(self, remain_x, remain_c, forget_x, forget_c, alpha: float = 1e-3, method: str = "rl",
-                              n_classes: int = 10, rng: Optional[dict] = None, train: bool = True):
+                              n_classes: int = 10, rng: Optional[dict] = None, train: bool = True,
+                              global_counts: Optional[Tuple[int, int]] = None):
         """One iteration.  `rng` may carry externally drawn (t_r, e_r, t_f, e_f, drop_r, drop_f, drop_p) for parity runs;
-        dropout inside the network uses the engine's counter-based generator (seeded per step)."""
+        dropout inside the network uses the engine's counter-based generator (seeded per step).
+        `global_counts` = (remain, forget) sizes of the GLOBAL mini-batch this rank's samples are a shard of: the loss
+        means are then taken over the global batch (default: every rank's samples form its own mean)."""
         rng = rng or {}
         eng, dev = self.engine, self.device
         W = self._world()
@@ -312,7 +320,9 @@ class DDPMEngineUnlearner:
         # loss = forget_loss + alpha * remain_loss (:533-572) and dL/d(eps), one kernel; the NCCL path averages the
         # gradient by pre-scaling dL/d(eps) with 1/W (the fused DP step averages inside its reduce kernel)
         scale = 1.0 / W if (W > 1 and not self.fused_dp) else 1.0
-        loss, d, _ = self.loss_k.loss_grad(eps, target, self._weights(nr, nf, alpha, method, eps[0].numel(), scale))
+        # mean over the global batch: after the 1/W rank average a sample must weigh 1/n_global, i.e. W/n_global here
+        nr_w, nf_w = (nr, nf) if global_counts is None else (global_counts[0] / W, global_counts[1] / W)
+        loss, d, _ = self.loss_k.loss_grad(eps, target, self._weights(nr, nf, alpha, method, eps[0].numel(), scale, nr_w, nf_w))
         if scale != 1.0:
             loss = loss * W
         eng.backward(d)                                                                            # :579-580
@@ -360,6 +370,14 @@ def _rank_world():
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
     return 0, 1
+
+
+def shard_batch(x, c, rank, world):
+    """This rank's contiguous chunk of a global mini-batch (nn.DataParallel scatters contiguous chunks too; here the
+    chunk sizes differ by at most one, so no rank is empty while n >= W)."""
+    n = x.shape[0]
+    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+    return x[lo:hi], c[lo:hi]
 
 
 def _cycle(loader):
@@ -444,7 +462,12 @@ class Diffusion:
             raise NotImplementedError("model.ema=True: the SalUn unlearning config sets ema False (cifar10_saliency_unlearn.yml:23)")
         rank, world = _rank_world()
         if getattr(args, "seed", None) is not None:
-            torch.manual_seed(args.seed + rank)   # data parallel: every rank draws its own mini-batches / noise
+            # data parallel = nn.DataParallel semantics (runners/diffusion.py:505): ONE global mini-batch per iteration,
+            # scattered across the ranks.  The loaders (CPU generator) therefore run in lock-step on every rank; the
+            # noise / timestep / dropout draws (CUDA generator) are per rank.
+            torch.manual_seed(args.seed)
+            if world > 1 and self.device.type == "cuda":
+                torch.cuda.manual_seed(args.seed + rank)
         import logging
         import time
         start = time.time()
@@ -452,8 +475,15 @@ class Diffusion:
         for step in range(config.training.n_iters):
             remain_x, remain_c = next(remain_iter)
             forget_x, forget_c = next(forget_iter)
+            counts = None
+            if world > 1:
+                counts = (remain_x.shape[0], forget_x.shape[0])
+                (remain_x, remain_c), (forget_x, forget_c) = (shard_batch(remain_x, remain_c, rank, world),
+                                                              shard_batch(forget_x, forget_c, rank, world))
+                if min(counts) < world:   # a trailing partial batch too small to give every rank a sample: skipped by all
+                    continue
             loss = un.saliency_unlearn_step(remain_x, remain_c, forget_x, forget_c, alpha=args.alpha, method=args.method,
-                                            n_classes=config.data.n_classes)
+                                            n_classes=config.data.n_classes, global_counts=counts)
             if (step + 1) % config.training.log_freq == 0:
                 logging.info(f"step: {step}, loss: {loss.item()}, time: {time.time() - start}")
                 start = time.time()

@@ -92,9 +92,11 @@ class ResNetEngine:
 
     def __init__(self, arch: str = "resnet18", num_classes: int = 10, image_size: int = 32, max_batch: int = 256,
                  mean=CIFAR_MEAN, std=CIFAR_STD, device=None, ctx: Optional[SalunContext] = None,
-                 symmetric: bool = False, imagenet: bool = False):
+                 symmetric: bool = False, imagenet: bool = False, precision: str = "bf16"):
         """symmetric=True allocates the parameter / gradient arenas as torch symmetric memory (NVLink peer-mapped), which
-        DistMaskedSGD needs for its fused reduce-scatter + update + all-gather kernel."""
+        DistMaskedSGD needs for its fused reduce-scatter + update + all-gather kernel.
+        precision: "bf16" (activations and tensor-core operands in bf16) or "split" (bf16 hi/lo pairs, fp32-class
+        products; the mode the saliency-mask pass uses to reproduce the fp32 reference's index set)."""
         if arch not in _ARCH_DEPTH:
             raise ValueError(f"arch {arch!r} is not served by the sm_100a engine (supported: {sorted(_ARCH_DEPTH)})")
         self.arch, self.depth = arch, _ARCH_DEPTH[arch]
@@ -104,7 +106,8 @@ class ResNetEngine:
         self.num_classes, self.image_size, self.max_batch = num_classes, image_size, max_batch
         self.ctx = ctx if ctx is not None else SalunContext(device)
         self.device = self.ctx.device
-        self._lib = _lib.lib()
+        self.precision = precision
+        self._lib = _lib.lib(precision)
         self.mean, self.std = tuple(float(v) for v in mean), tuple(float(v) for v in std)
         self.cfg = _lib.salun_resnet_cfg(self.depth, num_classes, image_size, max_batch, (C.c_float * 3)(*self.mean),
                                          (C.c_float * 3)(*self.std), 1e-5, 0.1, 1 if imagenet else 0)

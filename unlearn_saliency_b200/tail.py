@@ -149,6 +149,15 @@ class SalunContext:
         check(self._lib.salun_grad_sumsq(self._h, _ptr(g), g.numel(), _ptr(out), _stream(self.device)), "salun_grad_sumsq")
         return out
 
+    def l1_penalty_grad(self, p: torch.Tensor, g: torch.Tensor, alpha: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """g += alpha * sign(p); returns sum |p| (float64 device scalar) -- FT.py:13-17,133-134."""
+        _req(p, torch.float32, "p")
+        _req(g, torch.float32, "g")
+        out = out if out is not None else torch.empty(1, dtype=torch.float64, device=g.device)
+        check(self._lib.salun_l1_penalty_grad(self._h, _ptr(p), _ptr(g), p.numel(), float(alpha), _ptr(out),
+                                              _stream(self.device)), "salun_l1_penalty_grad")
+        return out
+
     def clip_coef(self, sumsq: torch.Tensor, max_norm: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         out = out if out is not None else torch.empty(1, dtype=torch.float32, device=sumsq.device)
         check(self._lib.salun_clip_coef(self._h, _ptr(sumsq), float(max_norm), _ptr(out), _stream(self.device)), "salun_clip_coef")
