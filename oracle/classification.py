@@ -147,8 +147,8 @@ def resnet_forward(p: Dict[str, torch.Tensor], b: Dict[str, torch.Tensor], x: to
     reference of the op the kernels actually implement; the fp32 chain measures what bf16 storage costs."""
     rf = _RoundFwd.apply if emulate_bf16 else (lambda t: t)
     rb = _RoundBoth.apply if emulate_bf16 else (lambda t: t)
-    m = torch.tensor(mean, dtype=x.dtype)[None, :, None, None]
-    s = torch.tensor(std, dtype=x.dtype)[None, :, None, None]
+    m = torch.tensor(mean, dtype=x.dtype, device=x.device)[None, :, None, None]
+    s = torch.tensor(std, dtype=x.dtype, device=x.device)[None, :, None, None]
     if emulate_bf16:
         x = (x - m) * (1.0 / s)  # the engine multiplies by 1/std
     else:
@@ -322,8 +322,8 @@ def bottleneck_forward(p, b, x, train: bool, imagenet: bool = True, mean=CIFAR_M
     """ResNet._forward_impl (ResNet.py:303-322) with Bottleneck.forward (:157-177); emulate_bf16 as in resnet_forward."""
     rf = _RoundFwd.apply if emulate_bf16 else (lambda t: t)
     rb = _RoundBoth.apply if emulate_bf16 else (lambda t: t)
-    m = torch.tensor(mean, dtype=x.dtype)[None, :, None, None]
-    s = torch.tensor(std, dtype=x.dtype)[None, :, None, None]
+    m = torch.tensor(mean, dtype=x.dtype, device=x.device)[None, :, None, None]
+    s = torch.tensor(std, dtype=x.dtype, device=x.device)[None, :, None, None]
     x = (x - m) * (1.0 / s) if emulate_bf16 else x.sub(m).div(s)
     x = rf(x)
     w = lambda k: rf(p[k])

@@ -1,0 +1,129 @@
+"""The split-precision build (libsalun_split.so: activations as bf16 hi/lo pairs, four tensor-core partial products per
+multiply) against the fp32 oracle -- tight, per-tensor tolerances (the bf16 build's tolerance model
+in tests/test_resnet_gpu.py does not apply: there is no bf16 rounding left to model)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import classification as OC
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, r):
+    a, r = a.float().flatten().cpu(), r.float().flatten().cpu()
+    return float((a - r).norm() / (r.norm() + 1e-30))
+
+
+def _data(n, seed=11, size=32):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(n, 3, size, size, generator=g), torch.randint(0, 10, (n,), generator=g)
+
+
+@pytest.fixture(scope="module")
+def split_engine(salun_ctx):
+    from unlearn_saliency_b200 import _lib
+    from unlearn_saliency_b200.engine import ResNetEngine
+    if "split" not in _lib.available_precisions():
+        pytest.skip("libsalun_split.so not built")
+    eng = ResNetEngine("resnet18", 10, 32, max_batch=64, ctx=salun_ctx, precision="split")
+    yield eng
+    eng.close()
+
+
+@pytest.mark.parametrize("train,sign,n", [(False, -1.0, 32), (True, 1.0, 32), (True, 1.0, 13), (False, -1.0, 64)])
+def test_resnet18_split_forward_backward_vs_fp32_oracle(split_engine, train, sign, n):
+    eng = split_engine
+    params, buffers = OC.synth_state(10, seed=0)
+    eng.load_state_dict(OC.state_dict_of(params, buffers))
+    x, y = _data(n)
+    b = {k: v.clone() for k, v in buffers.items()}
+    lref, oref, gref = OC.loss_and_grads(params, b, x, y, train=train, sign=sign)
+    eng.train(train)
+    loss, logits = eng.forward_backward(x.cuda(), y.cuda(), loss_sign=sign, want_logits=True)
+    torch.cuda.synchronize()
+    assert _rel(logits, oref) < 2e-4, _rel(logits, oref)
+    assert abs(float(loss) - float(lref)) < 1e-4 * max(1.0, abs(float(lref)))
+    gd = eng.grad_dict()
+    worst = max(((_rel(gd[k], r), k) for k, r in gref.items()))
+    print("split build, worst per-tensor gradient error:", worst)
+    for k, r in gref.items():
+        assert _rel(gd[k], r) < 3e-3, (k, _rel(gd[k], r))      # fp32 reorder noise of the train-mode BN chain is ~1e-4..1e-3
+    whole = _rel(torch.cat([gd[k].flatten() for k in gref]), torch.cat([r.flatten() for r in gref.values()]))
+    assert whole < 1e-3, whole
+    if train:
+        sd = eng.state_dict()
+        np.testing.assert_allclose(sd["bn1.running_mean"].cpu().numpy(), b["bn1.running_mean"].numpy(), rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(sd["layer4.1.bn2.running_var"].cpu().numpy(), b["layer4.1.bn2.running_var"].numpy(),
+                                   rtol=1e-3, atol=1e-7)
+
+
+def test_resnet50_split_forward_backward(salun_ctx):
+    """Bottleneck runtime (flat activations, explicit patch matrices) in the split build"""
+    from unlearn_saliency_b200 import _lib
+    from unlearn_saliency_b200.engine import ResNetEngine
+    if "split" not in _lib.available_precisions():
+        pytest.skip("libsalun_split.so not built")
+    params, buffers = OC.synth_state_bottleneck(10, seed=0, depth=50, imagenet=True)
+    eng = ResNetEngine("resnet50", 10, 64, max_batch=8, ctx=salun_ctx, imagenet=True, precision="split")
+    eng.load_state_dict(OC.state_dict_of(params, buffers))
+    x, y = _data(4, seed=21, size=64)
+    for train, sign in ((False, -1.0), (True, 1.0)):
+        b = {k: v.clone() for k, v in buffers.items()}
+        lref, oref, gref = OC.bottleneck_loss_and_grads(params, b, x, y, train=train, sign=sign)
+        eng.train(train)
+        loss, logits = eng.forward_backward(x.cuda(), y.cuda(), loss_sign=sign, want_logits=True)
+        assert _rel(logits, oref) < 5e-4
+        gd = eng.grad_dict()
+        whole = _rel(torch.cat([gd[k].flatten() for k in gref]), torch.cat([r.flatten() for r in gref.values()]))
+        print("resnet50 split whole-gradient error", whole, "train" if train else "eval")
+        assert whole < 5e-3, whole
+    eng.close()
+
+
+def test_unet_split_matches_reference_golden(salun_ctx):
+    """DDPM U-Net engine, split build, against the reference-generated golden (tests/golden/ddpm_small.npz: channel
+    change, 384-wide concat, down / up sampling, 64-token attention) and the fp32 torch statements."""
+    import os
+    from oracle import ddpm as OD
+    from tests.golden.make_golden_ddpm import inputs, small_config, synth_weights
+    from unlearn_saliency_b200 import _lib
+    from unlearn_saliency_b200.diffusion.engine import UNetEngine
+    from unlearn_saliency_b200.diffusion.runner import get_beta_schedule
+    from unlearn_saliency_b200.diffusion.unet import ConditionalUNet
+    if "split" not in _lib.available_precisions():
+        pytest.skip("libsalun_split.so not built")
+    cfg = small_config()
+    ref = ConditionalUNet(cfg)
+    ref.load_state_dict(synth_weights(ref))
+    ref.eval()
+    x0, e, t, c = inputs(seed=2, n=6, size=cfg.data.image_size)
+    betas = torch.from_numpy(get_beta_schedule("linear", beta_start=1e-4, beta_end=0.02, num_diffusion_timesteps=1000)).float()
+    ref.zero_grad()
+    lref = OD.eps_loss(ref, x0, t, c, e, betas, cond_drop_prob=0.0)
+    lref.backward()
+    eng = UNetEngine(cfg, max_batch=8, ctx=salun_ctx, precision="split").eval()
+    eng.load_state_dict(ref.state_dict())
+    n = x0.shape[0]
+    xt = OD.q_sample(x0, t, e, betas).cuda().contiguous()
+    eps = eng.forward(xt, t.float().cuda(), c.cuda(), drop=torch.zeros(n, dtype=torch.uint8, device="cuda"), save=True)
+    with torch.no_grad():
+        eps_ref = ref(OD.q_sample(x0, t, e, betas), t.float(), c, mode="train", cond_drop_prob=0.0)
+    assert _rel(eps, eps_ref) < 3e-4, _rel(eps, eps_ref)
+    ed = e.cuda()
+    eng.backward(((-2.0 / n) * (ed - eps)).contiguous())
+    torch.cuda.synchronize()
+    gd = eng.grad_dict()
+    worst = (0.0, None)
+    for k, p in ref.named_parameters():
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        if float(g.norm()) < 1e-7:
+            continue
+        r = _rel(gd[k], g)
+        worst = max(worst, (r, k))
+    print("unet split worst per-tensor gradient error", worst)
+    mine = torch.cat([gd[k].reshape(-1).cpu() for k, _ in ref.named_parameters()])
+    want = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for _, p in ref.named_parameters()])
+    assert _rel(mine, want) < 2e-3, _rel(mine, want)
+    assert worst[0] < 2e-2, worst
+    eng.close()
