@@ -108,7 +108,7 @@ def oracle_cpu_ddpm_sec_per_it(sample, steps=2, warmup=1):
     import torch
     from oracle import ddpm as OD
     from unlearn_saliency_b200.diffusion.runner import get_beta_schedule
-    from unlearn_saliency_b200.diffusion.unet import ConditionalUNet, cifar10_config
+    from oracle.unet import ConditionalUNet, cifar10_config
     torch.set_num_threads(os.cpu_count())
     torch.manual_seed(0)
     model = ConditionalUNet(cifar10_config())
@@ -144,7 +144,7 @@ def bench_ddpm(args, dev, rank, world, L, timed, tf_peak, peak_src):
     import torch
     from unlearn_saliency_b200.diffusion.engine import UNetEngine
     from unlearn_saliency_b200.diffusion.runner import DDPMEngineUnlearner, get_beta_schedule
-    from unlearn_saliency_b200.diffusion.unet import cifar10_config
+    from unlearn_saliency_b200.diffusion.config import cifar10_config
     cfg = cifar10_config()
     fused_dp = world > 1 and os.environ.get("SALUN_FUSED_DP", "1") != "0"
     try:

@@ -1,4 +1,7 @@
-"""Class-conditional DDPM U-Net with the parameter names / registration order of the reference's
+"""TEST INFRASTRUCTURE (checker network; only tests/, __graft_entry__.smoke() and bench.py's CPU / torch baseline legs import
+it -- the product path runs the U-Net in libsalun, csrc/salun_unet.cu).
+
+Class-conditional DDPM U-Net with the parameter names / registration order of the reference's
 ``Conditional_Model`` (DDPM/models/diffusion.py:195-413), so reference checkpoints (``states[0]``, with or without the
 DataParallel ``module.`` prefix) load unchanged and masks keyed by ``named_parameters()`` line up (SURVEY.md A.3:
 334 tensors, 38 632 323 parameters for the cifar10 config, ``null_classes_emb`` first).
@@ -14,21 +17,12 @@ concatenation on the way up, GroupNorm -> swish -> conv_out.
 from __future__ import annotations
 
 import math
-from types import SimpleNamespace
-
 import torch
 import torch.nn.functional as F
 from torch import nn
 
 
-def cifar10_config(n_classes: int = 10, dropout: float = 0.1, cond_drop_prob: float = 0.1) -> SimpleNamespace:
-    """DDPM/configs/cifar10_saliency_unlearn.yml:1-57 (model / data / diffusion keys the network reads)"""
-    return SimpleNamespace(
-        model=SimpleNamespace(type="conditional", in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2, 2, 2], num_res_blocks=2,
-                              attn_resolutions=[16], dropout=dropout, resamp_with_conv=True, cond_drop_prob=cond_drop_prob),
-        data=SimpleNamespace(image_size=32, channels=3, n_classes=n_classes),
-        diffusion=SimpleNamespace(beta_schedule="linear", beta_start=1e-4, beta_end=0.02, num_diffusion_timesteps=1000),
-    )
+from unlearn_saliency_b200.diffusion.config import cifar10_config  # noqa: E402,F401  (re-exported for the tests)
 
 
 def swish(x):

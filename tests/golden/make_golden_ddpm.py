@@ -85,7 +85,7 @@ def main():
     from models.diffusion import Conditional_Model
     from functions.losses import noise_estimation_loss_conditional
     from runners.diffusion import get_beta_schedule
-    from unlearn_saliency_b200.diffusion.unet import cifar10_config
+    from unlearn_saliency_b200.diffusion.config import cifar10_config
 
     cfg = tiny_config()
     model = Conditional_Model(cfg)

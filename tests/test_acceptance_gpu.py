@@ -155,7 +155,7 @@ def test_ddpm_mask_jaccard_full_cifar10_unet(salun_ctx):
     from unlearn_saliency_b200 import _lib
     from unlearn_saliency_b200.diffusion.engine import UNetEngine
     from unlearn_saliency_b200.diffusion.runner import DDPMEngineUnlearner, antithetic_t, get_beta_schedule
-    from unlearn_saliency_b200.diffusion.unet import ConditionalUNet, cifar10_config
+    from oracle.unet import ConditionalUNet, cifar10_config
     cfg = cifar10_config()
     torch.manual_seed(0)
     model = ConditionalUNet(cfg).cuda().eval()

@@ -7,7 +7,7 @@ import torch
 
 from tests.golden.make_golden_ddpm import inputs, sample_idx, synth_weights, tiny_config
 from unlearn_saliency_b200.diffusion.runner import eps_loss, get_beta_schedule, q_sample
-from unlearn_saliency_b200.diffusion.unet import ConditionalUNet, cifar10_config
+from oracle.unet import ConditionalUNet, cifar10_config
 
 G = os.path.join(os.path.dirname(__file__), "golden", "ddpm_tiny.npz")
 

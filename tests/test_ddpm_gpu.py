@@ -17,7 +17,7 @@ torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def _models():
-    from unlearn_saliency_b200.diffusion.unet import ConditionalUNet
+    from oracle.unet import ConditionalUNet
     m = ConditionalUNet(tiny_config())
     m.load_state_dict(synth_weights(m))
     return m.cuda(), copy.deepcopy(m).cuda()
@@ -35,7 +35,8 @@ def _draw(seed, n=8, size=8):
 
 
 def test_saliency_unlearn_step_matches_reference_statements(salun_ctx):
-    from unlearn_saliency_b200.diffusion.runner import DDPMUnlearner, eps_loss, get_beta_schedule, q_sample
+    from tests.ddpm_torch_helper import DDPMUnlearner
+    from unlearn_saliency_b200.diffusion.runner import eps_loss, get_beta_schedule, q_sample
     mine, ref = _models()
     betas = torch.from_numpy(get_beta_schedule("linear", beta_start=1e-4, beta_end=0.02, num_diffusion_timesteps=1000)).float()
     g = torch.Generator().manual_seed(3)
@@ -79,7 +80,8 @@ def test_saliency_unlearn_step_matches_reference_statements(salun_ctx):
 
 
 def test_generate_mask_matches_reference_statements(salun_ctx, tmp_path):
-    from unlearn_saliency_b200.diffusion.runner import DDPMUnlearner, get_beta_schedule, q_sample
+    from tests.ddpm_torch_helper import DDPMUnlearner
+    from unlearn_saliency_b200.diffusion.runner import get_beta_schedule, q_sample
     mine, ref = _models()
     betas = torch.from_numpy(get_beta_schedule("linear", beta_start=1e-4, beta_end=0.02, num_diffusion_timesteps=1000)).float()
     un = DDPMUnlearner(mine, betas, ctx=salun_ctx)

@@ -7,7 +7,7 @@ import torch
 
 from oracle import ddpm as OD
 from tests.golden.make_golden_ddpm import inputs, sample_idx, synth_weights, tiny_config
-from unlearn_saliency_b200.diffusion.unet import ConditionalUNet
+from oracle.unet import ConditionalUNet
 
 G = os.path.join(os.path.dirname(__file__), "golden", "ddpm_tiny.npz")
 

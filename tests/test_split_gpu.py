@@ -90,7 +90,7 @@ def test_unet_split_matches_reference_golden(salun_ctx):
     from unlearn_saliency_b200 import _lib
     from unlearn_saliency_b200.diffusion.engine import UNetEngine
     from unlearn_saliency_b200.diffusion.runner import get_beta_schedule
-    from unlearn_saliency_b200.diffusion.unet import ConditionalUNet
+    from oracle.unet import ConditionalUNet
     if "split" not in _lib.available_precisions():
         pytest.skip("libsalun_split.so not built")
     cfg = small_config()

@@ -10,7 +10,7 @@ import yaml
 from tests.golden.make_golden_ddpm import tiny_config
 from unlearn_saliency_b200 import _lib
 from unlearn_saliency_b200.diffusion.engine import salun_unet_cfg, unet_param_table
-from unlearn_saliency_b200.diffusion.unet import cifar10_config
+from unlearn_saliency_b200.diffusion.config import cifar10_config
 
 G = os.path.join(os.path.dirname(__file__), "golden", "ddpm_tiny.npz")
 

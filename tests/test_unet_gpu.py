@@ -1,6 +1,6 @@
 """sm_100a DDPM U-Net engine (salun_unet_*, through the C ABI) against
   * the golden outputs of the UNMODIFIED reference Conditional_Model (tests/golden/ddpm_tiny.npz), and
-  * the PyTorch fp32 restatement (unlearn_saliency_b200/diffusion/unet.py, pinned to the reference on CPU by
+  * the PyTorch fp32 restatement (oracle/unet.py, pinned to the reference on CPU by
     tests/test_ddpm_cpu.py) run on the same GPU with TF32 off,
 and the DDPM SalUn loop bodies on the engine against the reference's statements (DDPM/runners/diffusion.py:519-593,
 959-1039) with stock PyTorch.
@@ -49,7 +49,7 @@ def rel(a, b):
 
 
 def _torch_model(cfg, seed=0):
-    from unlearn_saliency_b200.diffusion.unet import ConditionalUNet
+    from oracle.unet import ConditionalUNet
     torch.manual_seed(seed)
     m = ConditionalUNet(cfg).cuda()
     g = torch.Generator().manual_seed(seed + 1)
@@ -118,7 +118,7 @@ def test_engine_matches_reference_golden(salun_ctx):
     """outputs of the unmodified reference model (make_golden_ddpm.py) on its seeded weights / inputs"""
     from unlearn_saliency_b200.diffusion.engine import UNetEngine
     from unlearn_saliency_b200.diffusion.runner import q_sample
-    from unlearn_saliency_b200.diffusion.unet import ConditionalUNet
+    from oracle.unet import ConditionalUNet
     z = np.load(G)
     cfg = tiny_config()
     eng = UNetEngine(cfg, max_batch=16, ctx=salun_ctx).eval()
@@ -306,7 +306,7 @@ def test_diffusion_runner_mirror_end_to_end(salun_ctx, tmp_path, monkeypatch):
     reference's formats; masked-out weights stay at their checkpoint values."""
     from torch.utils.data import DataLoader, TensorDataset
     from unlearn_saliency_b200.diffusion.runner import Diffusion
-    from unlearn_saliency_b200.diffusion.unet import ConditionalUNet
+    from oracle.unet import ConditionalUNet
     cfg = tiny_config()
     cfg.training = SimpleNamespace(batch_size=4, n_iters=3, snapshot_freq=3, log_freq=1)
     cfg.optim = SimpleNamespace(weight_decay=0.0, optimizer="Adam", lr=1e-4, beta1=0.9, amsgrad=False, eps=1e-8, grad_clip=1.0)
@@ -393,7 +393,7 @@ def test_cli_mirror_of_train_py(salun_ctx, tmp_path, monkeypatch):
     """python -m unlearn_saliency_b200.diffusion.cli: the flags / YAML keys / directories of DDPM/train.py on synthetic data"""
     import yaml
     from unlearn_saliency_b200.diffusion import cli
-    from unlearn_saliency_b200.diffusion.unet import ConditionalUNet
+    from oracle.unet import ConditionalUNet
     monkeypatch.chdir(tmp_path)
     cfg = dict(data=dict(dataset="CIFAR10", image_size=8, channels=3, random_flip=True, num_workers=0, n_classes=10, path="./data"),
                model=dict(type="simple", in_channels=3, out_ch=3, ch=128, ch_mult=[1, 1], num_res_blocks=1, attn_resolutions=[4],
@@ -463,7 +463,7 @@ def test_engine_matches_reference_golden_channel_changing_config(salun_ctx):
     from tests.golden.make_golden_ddpm import default_init_weights, small_config as golden_small
     from unlearn_saliency_b200.diffusion.engine import DDPMLoss, UNetEngine
     from unlearn_saliency_b200.diffusion.runner import get_beta_schedule
-    from unlearn_saliency_b200.diffusion.unet import ConditionalUNet
+    from oracle.unet import ConditionalUNet
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ddpm_small.npz"))
     cfg = golden_small()
     eng = UNetEngine(cfg, max_batch=8, ctx=salun_ctx).eval()

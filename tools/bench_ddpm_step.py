@@ -16,7 +16,7 @@ import torch  # noqa: E402
 from unlearn_saliency_b200 import _lib  # noqa: E402
 from unlearn_saliency_b200.diffusion.engine import UNetEngine  # noqa: E402
 from unlearn_saliency_b200.diffusion.runner import DDPMEngineUnlearner, eps_loss, get_beta_schedule, q_sample  # noqa: E402
-from unlearn_saliency_b200.diffusion.unet import ConditionalUNet, cifar10_config  # noqa: E402
+from oracle.unet import ConditionalUNet, cifar10_config  # noqa: E402
 
 B = int(os.environ.get("DDPM_BATCH", "128"))
 args = [a for a in sys.argv[1:] if not a.startswith("--")]

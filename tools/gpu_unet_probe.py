@@ -1,5 +1,5 @@
 """Bring-up probe of the sm_100a DDPM U-Net engine: every tape tensor that has a module-level counterpart and every
-parameter gradient against the PyTorch fp32 restatement (unlearn_saliency_b200/diffusion/unet.py, itself pinned to the
+parameter gradient against the PyTorch fp32 restatement (oracle/unet.py, itself pinned to the
 reference by tests/test_ddpm_cpu.py) on the same GPU.  Prints relative errors; exit code 1 if anything is off.
 
     python tools/gpu_unet_probe.py [tiny|small|full] [n]
@@ -12,7 +12,7 @@ import torch
 
 sys.path.insert(0, ".")
 from unlearn_saliency_b200.diffusion.engine import UNetEngine  # noqa: E402
-from unlearn_saliency_b200.diffusion.unet import ConditionalUNet, cifar10_config  # noqa: E402
+from oracle.unet import ConditionalUNet, cifar10_config  # noqa: E402
 
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False

@@ -5,7 +5,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from unlearn_saliency_b200.diffusion.engine import UNetEngine
-from unlearn_saliency_b200.diffusion.unet import cifar10_config
+from unlearn_saliency_b200.diffusion.config import cifar10_config
 
 cfg = cifar10_config()
 B = 128

@@ -89,12 +89,7 @@ class DDPMLoss:
         return loss, d, ss
 
 
-def unet_param_table(config) -> "OrderedDict[str, tuple]":
-    """named_parameters() order and PyTorch shapes of Conditional_Model (DDPM/models/diffusion.py:195-338)."""
-    from .unet import ConditionalUNet
-    with torch.device("meta"):
-        m = ConditionalUNet(config)
-    return OrderedDict((n, tuple(p.shape)) for n, p in m.named_parameters())
+from .config import unet_param_table  # noqa: E402  (named_parameters() order and shapes, pure Python)
 
 
 class UNetEngine:
