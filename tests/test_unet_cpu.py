@@ -135,8 +135,8 @@ def _fake_runner(monkeypatch, tmp_path, rank_world):
     _FakeUnlearner.instances.clear()
     monkeypatch.setattr(runner, "DDPMEngineUnlearner", _FakeUnlearner)
     monkeypatch.setattr(runner, "_rank_world", lambda: rank_world)
-    monkeypatch.setattr(runner.Diffusion, "_engine", lambda self, mb: SimpleNamespace(close=lambda: None,
-                                                                                       state_dict=lambda prefix="": {}))
+    monkeypatch.setattr(runner.Diffusion, "_engine", lambda self, mb, precision="bf16": SimpleNamespace(
+        close=lambda: None, state_dict=lambda prefix="": {}, precision=precision))
     monkeypatch.chdir(tmp_path)
     cfg = tiny_config()
     cfg.training = SimpleNamespace(batch_size=2, n_iters=5, snapshot_freq=2, log_freq=1)

@@ -46,7 +46,10 @@ def build_parser():
     p.add_argument("--indexes_to_replace", type=list, default=None)
     p.add_argument("--alpha", default=0.2, type=float)
     p.add_argument("--mask_path", default=None, type=str, help="the path of saliency map")
+    p.add_argument("--no_l1_epochs", default=0, type=int, help="FT_l1: epochs without the l1 penalty at the end (FT.py:124)")
     # additions of this mirror (no counterpart in the reference)
+    p.add_argument("--precision", type=str, default=None, choices=["bf16", "split"],
+                   help="engine build: default split (fp32-class) for generate_mask, bf16 for the unlearning steps")
     p.add_argument("--synthetic", type=int, default=0, metavar="N",
                    help="use N synthetic CIFAR-shaped training images instead of the dataset on disk (offline runs)")
     return p

@@ -14,9 +14,10 @@ def check_criterion(criterion):
         raise ValueError("the sm_100a engine implements nn.CrossEntropyLoss() (mean reduction, no weights) only")
 
 
-def as_engine(model, args=None, max_batch=None, symmetric: bool = False) -> ResNetEngine:
+def as_engine(model, args=None, max_batch=None, symmetric: bool = False, precision: str = "bf16") -> ResNetEngine:
     """Accept the reference's nn.Module (models/ResNet.py) and move it onto the engine, or pass an engine through.
-    symmetric=True: allocate the arenas as NVLink peer-mapped symmetric memory (fused data-parallel step)."""
+    symmetric=True: allocate the arenas as NVLink peer-mapped symmetric memory (fused data-parallel step).
+    precision: engine build ("bf16" | "split"); args.precision, when set, overrides the caller's default."""
     if isinstance(model, ResNetEngine):
         return model
     if not isinstance(model, torch.nn.Module):
@@ -29,7 +30,9 @@ def as_engine(model, args=None, max_batch=None, symmetric: bool = False) -> ResN
     imagenet = bool(getattr(args, "imagenet_arch", False))       # models/ResNet.py:224-230 stem (resnet50/101/152)
     image = int(getattr(args, "input_size", None) or (224 if imagenet else 32))
     mb = int(max_batch or getattr(args, "batch_size", 256) or 256)
-    eng = ResNetEngine(arch, num_classes, image, max_batch=mb, mean=mean, std=std, symmetric=symmetric, imagenet=imagenet)
+    precision = getattr(args, "precision", None) or precision
+    eng = ResNetEngine(arch, num_classes, image, max_batch=mb, mean=mean, std=std, symmetric=symmetric, imagenet=imagenet,
+                       precision=precision)
     eng.load_state_dict(sd)
     eng.train(model.training)
     eng._source_module = model  # written back by sync_to_module()

@@ -50,7 +50,21 @@ def parse_args_and_config(argv=None):
     p.add_argument("--alpha", type=float, default=1.0)
     p.add_argument("--mask_path", type=str, default=None)
     p.add_argument("--method", type=str, default=None)
-    p.add_argument("--mask_ratio", type=float, default=0.5)
+    p.add_argument("--mask_ratio", type=float, default=0.5,
+                   help="accepted like the reference's flag, which generate_mask ignores too (threshold_list = [0.5], "
+                        "runners/diffusion.py:1006)")
+    # reference flags of the sampling / training modes: accepted so that the reference's command lines run unchanged
+    p.add_argument("--sample_type", type=str, default="generalized")
+    p.add_argument("--skip_type", type=str, default="uniform")
+    p.add_argument("--timesteps", type=int, default=1000)
+    p.add_argument("--eta", type=float, default=1.0)
+    p.add_argument("--sequence", action="store_true")
+    p.add_argument("--uc", type=bool, default=True)
+    p.add_argument("--negative_guidance", type=float, default=7.5)
+    p.add_argument("--sparse", type=bool, default=False)
+    # additions of this mirror
+    p.add_argument("--precision", type=str, default=None, choices=["bf16", "split"],
+                   help="engine build: default split (fp32-class) for generate_mask, bf16 for saliency_unlearn")
     p.add_argument("--synthetic", type=int, default=0, help="use N random images per split instead of CIFAR-10")
     args = p.parse_args(argv)
     cfg_dict, _ = _load_config(args.config)

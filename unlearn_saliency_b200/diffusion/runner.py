@@ -326,9 +326,10 @@ class Diffusion:
             return self.loaders
         return get_forget_dataset(self.args, self.config, self.args.label_to_forget)
 
-    def _engine(self, max_batch):
+    def _engine(self, max_batch, precision="bf16"):
         from .engine import UNetEngine
-        eng = UNetEngine(self.config, max_batch=max_batch, device=self.device)
+        precision = getattr(self.args, "precision", None) or precision
+        eng = UNetEngine(self.config, max_batch=max_batch, device=self.device, precision=precision)
         path = os.path.join(self.args.ckpt_folder, "ckpts/ckpt.pth")
         states = torch.load(path, map_location="cpu")
         eng.load_state_dict(states[0], strict=True)           # DataParallel keys: the ``module.`` prefix is stripped
@@ -337,7 +338,9 @@ class Diffusion:
     def generate_mask(self, threshold_list=(0.5,)):
         args, config = self.args, self.config
         _, forget_loader = self._loaders()
-        eng = self._engine(2 * config.training.batch_size)     # conditional + null pass as one batch
+        # the saliency pass decides an index set: it runs on the split-precision build (fp32-class products, DESIGN.md
+        # section 4) unless args.precision says otherwise; conditional + null pass as one batch
+        eng = self._engine(2 * config.training.batch_size, precision="split")
         o = config.optim
         un = DDPMEngineUnlearner(eng, self.betas, lr=o.lr, beta1=o.beta1, eps=o.eps, weight_decay=o.weight_decay,
                                  grad_clip=o.grad_clip)
