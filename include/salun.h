@@ -355,6 +355,28 @@ int salun_unet_num_tensors(const salun_unet *net);
 int salun_unet_tensor_info(const salun_unet *net, int idx, char *name_buf, int name_cap, int *C, int *H);
 int salun_unet_export_tensor(salun_unet *net, int idx, int which, float *out_nchw, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * The steps either side of the hot path, csrc/salun_data.cu
+ * --------------------------------------------------------------------------------------------------------------- */
+
+/* out_nchw[i] (fp32 [n][3][H][W] in [0,1]) = ToTensor(HorizontalFlip_{flip[i]}(Crop_{crop_xy[i]}(ZeroPad_{pad}(
+ * images_hwc[index[i]])))) from a uint8 [n_images][H][W][3] dataset resident in device memory.
+ *   index   int64 [n] or NULL (identity);  crop_xy int32 [n][2] = (left, top) of the crop window inside the padded image,
+ *   0 .. 2*pad, or NULL (centre = no crop);  flip uint8 [n] or NULL (no flip).  Bit-identical to the torchvision ops.
+ * replaces the DataLoader gather + RandomCrop(32, padding=4) + RandomHorizontalFlip + ToTensor
+ * Classification/dataset.py:549-555, main_forget.py:42-48 */
+int salun_augment_batch(salun_ctx *ctx, const uint8_t *images_hwc, int64_t n_images, const int64_t *index,
+                        const int32_t *crop_xy, const uint8_t *flip, int n, int H, int W, int pad, float *out_nchw,
+                        void *stream);
+
+/* One batch of logits [n][K]:  loss_sum_dev[0] += sum_i CE(logits_i, labels_i)  (double),  correct_dev[0] += #{argmax ==
+ * label},  probs (optional, [n][K]) = softmax(logits).  labels may be NULL when only probs are wanted.  Accumulators live
+ * on the device: a whole validation pass needs one read-back.
+ * replaces criterion + utils.accuracy + the two .item() per batch of  Classification/trainer/val.py:44-61  and
+ * F.softmax of  Classification/evaluation/SVC_MIA.py:44-46 */
+int salun_eval_logits(salun_ctx *ctx, const float *logits, const int64_t *labels, int n, int K, float *probs,
+                      double *loss_sum_dev, int64_t *correct_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,8 @@ _SIGNATURES = {
     "salun_grad_sumsq": [_P, _P, _I64, _P, _P],
     "salun_l1_penalty_grad": [_P, _P, _P, _I64, _F, _P, _P],
     "salun_clip_coef": [_P, _P, _F, _P, _P],
+    "salun_augment_batch": [_P, _P, _I64, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P],
+    "salun_eval_logits": [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P],
     "salun_masked_adam_step": [_P, _P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I64, _P, _P],
     # tcgen05 GEMM / convolution entry points (salun_gemm.cu)
     "salun_gemm_bf16_tn": [_P, _P, _P, _P, _P, _I64, _I64, _I64, _P],

@@ -48,6 +48,10 @@ def build_parser():
     p.add_argument("--mask_path", default=None, type=str, help="the path of saliency map")
     p.add_argument("--no_l1_epochs", default=0, type=int, help="FT_l1: epochs without the l1 penalty at the end (FT.py:124)")
     # additions of this mirror (no counterpart in the reference)
+    p.add_argument("--device_data", action="store_true",
+                   help="keep the dataset resident on the GPU as uint8 and run gather + RandomCrop(32,4) + flip + ToTensor as "
+                        "one kernel per batch (device_data.py) instead of the host DataLoader")
+    p.add_argument("--mia", action="store_true", help="also run the SVC membership-inference evaluation (main_forget.py:158-183)")
     p.add_argument("--precision", type=str, default=None, choices=["bf16", "split"],
                    help="engine build: default split (fp32-class) for generate_mask, bf16 for the unlearning steps")
     p.add_argument("--synthetic", type=int, default=0, metavar="N",

@@ -17,6 +17,7 @@ import torch
 from ..engine import ResNetEngine
 from . import arg_parser
 from .data import make_loaders
+from .evaluation import SVC_MIA, validate
 from .generate_mask import save_gradient_ratio
 from .unlearn import get_unlearn_method
 
@@ -34,15 +35,13 @@ def _engine_from_args(args) -> ResNetEngine:
     return eng
 
 
-@torch.no_grad()
-def validate(loader, engine) -> float:
-    """top-1 accuracy in percent (trainer/val.py:6-72) with the engine's eval-mode forward"""
-    correct = total = 0
-    for x, y in loader:
-        logits = engine.forward(x.to(engine.device, non_blocking=True).float().contiguous())
-        correct += int((logits.argmax(1).cpu() == y).sum())
-        total += y.numel()
-    return 100.0 * correct / max(1, total)
+def _first_n(loader, n, args):
+    """torch.utils.data.Subset(dataset, range(n)) + DataLoader(shuffle=False) (main_forget.py:168-171)"""
+    from .device_data import DeviceLoader
+    if isinstance(loader, DeviceLoader):
+        return DeviceLoader(loader.dataset, loader.indices[:n], batch_size=args.batch_size, shuffle=False, augment=False)
+    sub = torch.utils.data.Subset(loader.dataset, list(range(min(n, len(loader.dataset)))))
+    return torch.utils.data.DataLoader(sub, batch_size=args.batch_size, shuffle=False)
 
 
 def generate_mask_main(args):
@@ -68,9 +67,22 @@ def unlearn_main(args, with_mask: bool):
     method = get_unlearn_method(args.unlearn)
     method(loaders, engine, torch.nn.CrossEntropyLoss(), args, mask) if mask is not None else \
         method(loaders, engine, torch.nn.CrossEntropyLoss(), args)
-    evaluation_result = {"accuracy": {name: validate(ld, engine) for name, ld in loaders.items()}}
-    for name, acc in evaluation_result["accuracy"].items():
-        print(f"{name} acc: {acc:.3f}")
+    # main_forget.py:141-151: every loader in test mode (no augmentation), trainer/val.py validate on the engine's kernels
+    crit = torch.nn.CrossEntropyLoss()
+    eval_loaders = make_loaders(args, test_mode=True) if getattr(args, "device_data", False) else loaders
+    evaluation_result = {"accuracy": {}}
+    for name, ld in eval_loaders.items():
+        evaluation_result["accuracy"][name] = validate(ld, engine, crit, args)
+        print(f"{name} acc: {evaluation_result['accuracy'][name]}")
+    if getattr(args, "mia", False):
+        # main_forget.py:158-183 forget-efficacy MIA: shadow_train = the first len(test) retain samples, shadow_test = test,
+        # target_test = forget
+        test_len = len(eval_loaders["test"].dataset) if not getattr(args, "device_data", False) else eval_loaders["test"].indices.numel()
+        shadow_train = _first_n(eval_loaders["retain"], test_len, args)
+        evaluation_result["SVC_MIA_forget_efficacy"] = SVC_MIA(shadow_train=shadow_train, shadow_test=eval_loaders["test"],
+                                                                target_train=None, target_test=eval_loaders["forget"],
+                                                                model=engine)
+        print("SVC_MIA_forget_efficacy", evaluation_result["SVC_MIA_forget_efficacy"])
     state = {"state_dict": engine.state_dict(), "evaluation_result": evaluation_result}  # impl.py:21-30
     torch.save(state, os.path.join(args.save_dir, str(args.unlearn) + "checkpoint.pth.tar"))  # utils.py:44-52
     torch.save(evaluation_result, os.path.join(args.save_dir, str(args.unlearn) + "eval_result.pth.tar"))

@@ -92,12 +92,24 @@ def test_filter(y_test: torch.Tensor, args):
     return torch.arange(len(y_test))
 
 
-def make_loaders(args):
-    """OrderedDict(retain, forget, val, test) of DataLoaders like main_forget.py:110-116."""
+def make_loaders(args, test_mode: bool = False):
+    """OrderedDict(retain, forget, val, test) of loaders like main_forget.py:110-116.  args.device_data: DeviceLoaders over
+    uint8 datasets resident on the GPU (device_data.py) with the reference's train transform as a kernel; test_mode=True
+    turns shuffling and augmentation off (utils.dataset_convert_to_test, main_forget.py:143)."""
     xtr, ytr, xte, yte = load_train_test(args)
     s = split_indices(ytr, args)
     ti = test_filter(yte, args)
     torch.manual_seed(args.seed)  # utils.setup_seed just before the loaders are built (main_forget.py:38-48)
+    if getattr(args, "device_data", False):
+        from .device_data import DeviceDataset, DeviceLoader
+        dev = f"cuda:{int(getattr(args, 'gpu', 0))}"
+        tr = DeviceDataset.from_float_nchw(xtr, ytr, device=dev)
+        te = DeviceDataset.from_float_nchw(xte, yte, device=dev, ctx=tr.ctx)
+        aug = (not test_mode) and not getattr(args, "no_aug", False)
+        mk = lambda ds, idx, train: DeviceLoader(ds, idx, batch_size=args.batch_size, shuffle=train and not test_mode,
+                                                 augment=train and aug)
+        return OrderedDict(retain=mk(tr, s["retain"], True), forget=mk(tr, s["forget"], True), val=mk(tr, s["val"], False),
+                           test=mk(te, ti, False))
     mk = lambda x, y, shuffle: DataLoader(TensorDataset(x, y), batch_size=args.batch_size, shuffle=shuffle,
                                           pin_memory=True, num_workers=0)
     fi, ri, vi = (torch.from_numpy(s[k]) for k in ("forget", "retain", "val"))

@@ -55,6 +55,7 @@ struct ConvMaps {
   CUtensorMap fwdA, fwdB, dgA, dgB, wgA, wgB;
   CUtensorMap rwA, rwB, rwdA, rwdB;  // k_conv_rw (resident weights) forward / dgrad maps
   bool rw_fwd, rw_dgrad;
+  int pair_fwd, pair_dg;   // forward / dgrad through the CTA-pair kernel (fwdB / dgB encoded with bn/2 box rows)
 };
 
 }  // namespace salun
@@ -176,6 +177,19 @@ static int pick_bn(int N, int64_t M) {
   return N % 128 == 0 ? 128 : 64;
 }
 
+// CTA pairs (k_gemm2: 256 x bn tiles, each CTA pulls half of B) for the GEMMs that still give every pair a tile.
+// SALUN_RESNET_PAIR: 0 = off (default), 1 = when >= 74 pair-tiles, 2 = when >= 37
+static bool rn_use_pair(int64_t M, int N, int bn) {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("SALUN_RESNET_PAIR");
+    on = e ? atoi(e) : 0;
+  }
+  if (!on || bn < 128) return false;
+  const int64_t tiles = ((M + 255) / 256) * ((N + bn - 1) / bn);
+  return tiles >= (on == 2 ? 37 : 74);
+}
+
 template <typename T>
 static int dmalloc(salun_resnet *net, T **p, size_t count, bool zero) {
   void *q = nullptr;
@@ -204,7 +218,10 @@ static int build_plan(salun_resnet *net, int n, std::vector<ConvMaps> **out) {
     m.rw_fwd = m.rw_dgrad = false;
     const int64_t Mout = (int64_t)n * L.hout * L.hout;
     const int bn = pick_bn(L.cout, Mout);
-    TRY(make_tmap_2d_wop(&m.fwdB, L.w_fwd, L.cout, L.kcp, bn));
+    m.pair_fwd = m.pair_dg = 0;
+    const bool rw_f = L.dy_padded && net->use_conv_rw && (net->use_conv_rw == 1 || L.hin == 32) && L.ks == 3 && conv_rw_supported(L.hin, L.cin, L.cout);
+    if (!rw_f && rn_use_pair(Mout, L.cout, bn)) m.pair_fwd = 1;
+    TRY(make_tmap_2d_wop(&m.fwdB, L.w_fwd, L.cout, L.kcp, m.pair_fwd ? bn / 2 : bn));
     TmapBox4 bx128, bx64;
     if (L.dy_padded) {
       // stride-1 3x3: forward A and wgrad B read the padded input activation, dgrad A / wgrad A the padded dY
@@ -214,7 +231,9 @@ static int build_plan(salun_resnet *net, int n, std::vector<ConvMaps> **out) {
       TRY(make_tmap_4d_act(&m.fwdA, in.p, L.cin, L.hin + 2, L.hin + 2, n, bx128));
       TRY(make_tmap_4d_act(&m.dgA, L.dy, L.cout, L.hout + 2, L.hout + 2, n, bx128));
       const int bnd = pick_bn(L.cin, Mout);
-      TRY(make_tmap_2d_wop(&m.dgB, L.w_dgrad, L.cin, (uint64_t)L.ks * L.ks * L.cout, bnd));
+      const bool rw_d = net->use_conv_rw && (net->use_conv_rw == 1 || L.hout == 32) && L.ks == 3 && conv_rw_supported(L.hout, L.cout, L.cin);
+      if (!rw_d && !net->use_bwd_fuse && rn_use_pair(Mout, L.cin, bnd)) m.pair_dg = 1;
+      TRY(make_tmap_2d_wop(&m.dgB, L.w_dgrad, L.cin, (uint64_t)L.ks * L.ks * L.cout, m.pair_dg ? bnd / 2 : bnd));
       TRY(make_tmap_4d_act(&m.wgA, L.dy, L.cout, L.hout + 2, L.hout + 2, n, bx64));
       TRY(make_tmap_4d_act(&m.wgB, in.p, L.cin, L.hin + 2, L.hin + 2, n, bx64));
       m.rw_fwd = net->use_conv_rw && (net->use_conv_rw == 1 || L.hin == 32) && L.ks == 3 && conv_rw_supported(L.hin, L.cin, L.cout);
@@ -284,6 +303,7 @@ static int conv_forward(salun_resnet *net, const ConvL &L, const ConvMaps &m, in
     a.mode_a = 0;
     a.num_k_blocks = L.kcp / 64;
   }
+  a.pair = m.pair_fwd;
   TRY(launch_conv_gemm(m.fwdA, m.fwdB, a, bn, st));
   if (train) launch_bn_stats_reduce(L.stat_sum, L.stat_sq, (M + 127) / 128 * 4, L.cout, L.slices, st);
   return SALUN_OK;
@@ -463,6 +483,7 @@ static int backward_impl(salun_resnet *net, cudaStream_t st) {
       a.ld_out = L2.cin;
       a.fH = a.fW = L2.hout;
       fuse_for(B.c1, mid, &a.f1, (a.M + 127) / 128 * 4);
+      a.pair = (*plan)[B.c2].pair_dg;
       TRY(launch_conv_gemm((*plan)[B.c2].dgA, (*plan)[B.c2].dgB, a, pick_bn(L2.cin, a.M), st));
       TRY(wgrad_conv(net, L2, (*plan)[B.c2], n, st));
     }
@@ -513,6 +534,7 @@ static int backward_impl(salun_resnet *net, cudaStream_t st) {
           fuse_for(0, in, &a.f1, rows);
         }
       }
+      a.pair = (*plan)[B.c1].pair_dg;
       TRY(launch_conv_gemm((*plan)[B.c1].dgA, (*plan)[B.c1].dgB, a, pick_bn(L1.cin, a.M), st));
       if (!identity) {
         set_error("salun_resnet: stride-1 block with projection shortcut is not supported");
@@ -694,7 +716,7 @@ int salun_resnet_create(salun_ctx *ctx, const salun_resnet_cfg *cfg, float *para
       A(dmalloc(net, &L.col, Mo * L.kcp, true));
       if (!L.stem) A(dmalloc(net, &L.dcol, Mo * L.kc, false));
     }
-    const size_t rows = (Mo + 127) / 128 * 4;
+    const size_t rows = (Mo + 255) / 256 * 8;   // whole CTA pairs: the pair kernel's second CTA owns a (possibly empty) tile
     A(dmalloc(net, &L.stat_sum, rows * L.cout, true));
     A(dmalloc(net, &L.stat_sq, rows * L.cout, true));
     A(dmalloc(net, &L.slices, (size_t)kStatSlices * 2 * L.cout, true));
