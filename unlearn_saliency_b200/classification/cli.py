@@ -63,7 +63,7 @@ def unlearn_main(args, with_mask: bool):
     if with_mask:
         if not args.mask_path:
             raise SystemExit("main_random needs --mask_path (main_random.py:133-140 raises NameError without it)")
-        mask = torch.load(args.mask_path, map_location=engine.device)
+        mask = args.mask_path   # resolved by the engine: the packed side-car <mask_path>.bits when present, else the int64 dict
     method = get_unlearn_method(args.unlearn)
     method(loaders, engine, torch.nn.CrossEntropyLoss(), args, mask) if mask is not None else \
         method(loaders, engine, torch.nn.CrossEntropyLoss(), args)

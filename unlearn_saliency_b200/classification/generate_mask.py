@@ -17,6 +17,7 @@ import os
 
 import torch
 
+from ..io import default_saver, save_sidecar
 from ..tail import topk_count
 from .common import as_engine, check_criterion, dist_info
 
@@ -67,9 +68,13 @@ def save_gradient_ratio(data_loaders, model, criterion, args):
     flat = engine.from_native_flat(acc).contiguous()  # named_parameters order & PyTorch layout, as cat(flatten) :57
     os.makedirs(args.save_dir, exist_ok=True)
     infos = {}
+    saver = default_saver()   # the ten 89 MB files are pickled / written on a worker thread while the next select runs
     for r in THRESHOLD_LIST:
-        hard_dict, _, info = masks_for_ratio(engine, flat, r)
+        hard_dict, bits, info = masks_for_ratio(engine, flat, r)
         infos[r] = info
         if rank == 0:
-            torch.save(hard_dict, os.path.join(args.save_dir, "with_{}.pt".format(r)))  # :82
+            path = os.path.join(args.save_dir, "with_{}.pt".format(r))
+            saver.save(hard_dict, path, cuda_tensors=True)                  # :82 -- CUDA tensors, like the reference's file
+            save_sidecar(saver, path, bits, engine.table, ratio=r)          # 1 bit / parameter, same order and layout
+    saver.wait()
     return infos

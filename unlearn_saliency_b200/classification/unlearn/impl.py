@@ -21,7 +21,8 @@ def _iterative_unlearn_impl(unlearn_iter_func):
         decreasing_lr = list(map(int, args.decreasing_lr.split(",")))
         _, world = dist_info()
         engine = as_engine(model, args, symmetric=world > 1)
-        bits = engine.mask_bits_from_dict(mask) if mask else None  # `if mask:` RL.py:134
+        # `if mask:` RL.py:134.  A path (str) instead of the loaded dict lets the packed side-car be used (io.py)
+        bits = (engine.mask_bits_from_file(mask) if isinstance(mask, str) else engine.mask_bits_from_dict(mask)) if mask else None
         if world > 1 and engine.symmetric:
             # data parallel: gradient reduce-scatter + masked SGD + weight all-gather in ONE kernel over NVLink peer memory
             optimizer = DistMaskedSGD(engine, args.unlearn_lr, momentum=args.momentum, weight_decay=args.weight_decay,

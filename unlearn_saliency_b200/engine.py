@@ -295,6 +295,14 @@ class ResNetEngine:
         native = self.to_native({k: mask[k].to(torch.int64) for k in self.table})
         return self.ctx.pack_mask(native.contiguous())
 
+    def mask_bits_from_file(self, path: str) -> torch.Tensor:
+        """mask file of the reference (``with_<r>.pt``) or its packed side-car (``with_<r>.pt.bits``, io.py) -> packed bits
+        in arena layout.  The side-car is 64x smaller than the int64 dict and is preferred when present."""
+        from .io import load_mask
+        bits_torch_order = load_mask(path, self.table, self.ctx, self.device)
+        m64 = self.ctx.unpack_mask(bits_torch_order, self.n_params)
+        return self.ctx.pack_mask(self.to_native(m64).contiguous())
+
     def mask_dict_from_native_i64(self, flat_i64: torch.Tensor) -> "OrderedDict[str, torch.Tensor]":
         return self.from_native(flat_i64)
 

@@ -157,8 +157,13 @@ class FlatSaliency:
             off += c
         return out, info
 
-    def save(self, path: str, ratio: float = 0.5, **kw):
-        m, info = self.mask(ratio, **kw)
-        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
-        torch.save(m, path)
+    def save(self, path: str, ratio: float = 0.5, wait: bool = True, **kw):
+        """the reference's mask file (CPU int64 dict) written through the streaming saver (io.py); wait=False returns while
+        the file is still being written (call io.default_saver().wait() before reading it back)"""
+        from .io import default_saver
+        m, info = self.mask(ratio, cpu=False, **{k: v for k, v in kw.items() if k != "cpu"})
+        saver = default_saver()
+        saver.save(m, path)          # staged to pinned host memory on a side stream, pickled on a worker thread
+        if wait:
+            saver.wait()
         return info
