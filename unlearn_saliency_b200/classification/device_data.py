@@ -52,6 +52,8 @@ class DeviceDataset:
         n = int(index.numel())
         if out is None:
             out = torch.empty(n, 3, self.H, self.W, device=self.device)
+        if n == 0:
+            return out, self.targets[:0]
         if crop_xy is not None:
             crop_xy = crop_xy.to(self.device, torch.int32).contiguous()
         if flip is not None:
