@@ -32,10 +32,20 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-# keep stdout to the ONE JSON line: NCCL writes its banner / INFO lines to stdout unless NCCL_DEBUG_FILE says otherwise.
-# The debug level itself is left alone (the driver's rank check reads the INFO lines): they go to stderr.
-if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+# Keep stdout to the ONE JSON line.  NCCL (every rank) writes its version banner / INFO lines to stdout at whatever
+# NCCL_DEBUG level the environment sets; the level is left alone (the driver's rank check reads those lines) but the
+# process-level stdout (fd 1) is pointed at stderr, and the JSON line is written to a private duplicate of the real stdout.
+if not os.environ.get("NCCL_DEBUG_FILE"):
     os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+sys.stdout.flush()
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
 
 BATCH = 256
 FWD_GFLOP_PER_IMG = 1.1108  # SURVEY.md section 6 (torch.utils.flop_counter on the reference model)
@@ -183,7 +193,7 @@ def run_reference(args):
     if "ddpm" in cb:
         line["ddpm"] = {"metric": "DDPM saliency_unlearn iterations/sec (cifar10 U-Net 32x32, 128 remain + 128 forget images, rl)",
                         "value": cb["ddpm"]["value"], "unit": "iterations/s", "dtype": "f32", "cpu_baseline": cb["ddpm"]}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # =====================================================================================================================
@@ -219,7 +229,7 @@ def run_torch(args):
             "config": {"workload": "ResNet-18/CIFAR-10 SalUn RL masked unlearn step, batch 256, mask ratio 0.5 (stock PyTorch eager)"},
             "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": BATCH * 3 * 32 * 32 * 4 + BATCH * 8, "d2h_bytes_per_step": 4},
             "gpu_launches": 0, "torch_eager": t}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # =====================================================================================================================
@@ -682,7 +692,9 @@ def main():
         for nm in ("resnet18", "ddpm", "resnet18_weights"):
             a = load_json(f"profiles/r2_acceptance_{nm}.json")
             if a:
-                parity[nm] = {k: a[k] for k in ("jaccard", "rel_l2_saliency", "update_rel_l2", "update_cos") if k in a}
+                parity[nm] = {k: a[k] for k in ("rel_l2_saliency", "update_rel_l2", "update_cos") if k in a}
+                if "jaccard" in a:   # per build: the 50 % mask and the worst ratio of 0.1 .. 0.9
+                    parity[nm]["jaccard"] = {b: {"ratio_0.5": j["0.5"], "min_over_ratios": min(j.values())} for b, j in a["jaccard"].items()}
         line = {
             "metric": METRIC_STRONG if strong else METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
@@ -701,7 +713,7 @@ def main():
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "final_loss": final_loss,
             "ddpm": ddpm, "maskgen": maskgen, "modes": modes, "torch_eager": torch_eager, "parity": parity,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
