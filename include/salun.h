@@ -273,6 +273,18 @@ int salun_resnet_destroy(salun_resnet *net);
 int salun_resnet_forward_backward(salun_resnet *net, const float *x, const int64_t *labels, int n,
                                   int train, float loss_sign, float *loss_dev, float *logits_dev,
                                   void *stream);
+/* Sync-BN for a mini-batch sharded over ranks: train-mode BatchNorm statistics (sum x, sum x^2,
+ * pixel count) and the two batch means of the BatchNorm backward are exchanged through NVLink peer-mapped memory, so the
+ * sharded step computes the single-process step of the concatenated batch (nn.BatchNorm2d over the global batch:
+ * Classification/models/ResNet.py:111-119 under the reference's single-GPU loop).
+ *   peer_sums_host[r]  : rank r's arena of salun_resnet_syncbn_doubles(cfg) doubles (zero-initialised, peer-mapped)
+ *   peer_flags_host[r] : rank r's `world` 64-bit epoch flags (zero-initialised, peer-mapped)
+ * Every rank must enqueue the same sequence of forward_backward calls (each BatchNorm exchange is a cross-rank barrier
+ * of one CTA; a missing rank traps after ~10 s instead of hanging).  resnet18 / resnet34, world <= 8. */
+int64_t salun_resnet_syncbn_doubles(const salun_resnet_cfg *cfg);
+int salun_resnet_enable_syncbn(salun_resnet *net, double *const *peer_sums_host, unsigned long long *const *peer_flags_host,
+                               int rank, int world);
+
 /* eval-mode inference (trainer/val.py:6-72 validate): logits only */
 int salun_resnet_forward(salun_resnet *net, const float *x, int n, float *logits_dev, void *stream);
 

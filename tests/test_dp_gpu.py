@@ -43,6 +43,13 @@ def test_fused_dp_masked_sgd_two_ranks():
     assert "replicas identical: True" in out and "masked-out exact: True" in out
 
 
+def test_sync_bn_sharded_step_equals_full_batch_step():
+    """dp_syncbn_worker.py: sync-BN over NVLink peer memory -- a batch sharded over 2 ranks reproduces the single-process
+    step of the concatenated batch (weights, running statistics); per-shard statistics do not"""
+    out = _run("dp_syncbn_worker.py")
+    assert "replicas identical: True" in out
+
+
 def test_fused_dp_masked_adam_two_ranks():
     out = _run("dp_fused_adam_worker.py")
     assert "replicas identical: True" in out and "norms ok: True" in out

@@ -84,9 +84,11 @@ _SIGNATURES = {
     "salun_resnet_destroy": [_P],
     "salun_resnet_forward_backward": [_P, _P, _P, C.c_int, C.c_int, _F, _P, _P, _P],
     "salun_resnet_forward": [_P, _P, C.c_int, _P, _P],
+    "salun_resnet_syncbn_doubles": [_P],
+    "salun_resnet_enable_syncbn": [_P, C.POINTER(_P), C.POINTER(_P), C.c_int, C.c_int],
 }
 _RESTYPES = {"salun_last_error": C.c_char_p, "salun_launch_count": C.c_longlong, "salun_resnet_param_count": C.c_int64,
-             "salun_resnet_bn_channels": C.c_int64}
+             "salun_resnet_bn_channels": C.c_int64, "salun_resnet_syncbn_doubles": C.c_int64}
 
 
 def exported_symbols():

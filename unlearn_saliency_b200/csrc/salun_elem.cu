@@ -73,6 +73,7 @@ void launch_bn_stats_reduce(const float *stat_sum, const float *stat_sq, int row
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void bn_prologue(const BnFwd &p, float *sc, float *sh, int C, int train, double count,
                                             float eps, float momentum) {
+  if (train && p.count_dev) count = *p.count_dev;   // sync-BN: the global pixel count
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float mean, invstd;
     if (train) {
@@ -298,7 +299,7 @@ void launch_bn_bwd_reduce(const act_t *dout, const uint8_t *relu_mask, const act
 
 __global__ void k_bn_bwd_finalize(const float *__restrict__ partials, int rows, int C, const float *__restrict__ gamma,
                                   const float *__restrict__ invstd, float count, int train, float *__restrict__ dgamma,
-                                  float *__restrict__ dbeta, float *__restrict__ coef) {
+                                  float *__restrict__ dbeta, float *__restrict__ coef, double *__restrict__ xchg) {
   pdl_trigger();
   pdl_wait();
   __shared__ double sh[2][kRedY][32];
@@ -330,14 +331,72 @@ __global__ void k_bn_bwd_finalize(const float *__restrict__ partials, int rows, 
     coef[c] = gamma[c] * invstd[c];
     coef[C + c] = train ? (float)(a / (double)count) : 0.f;
     coef[2 * C + c] = train ? (float)(b / (double)count) : 0.f;
+    if (xchg) {   // sync-BN: the exchange kernel recomputes coef[C..3C) from the global sums
+      xchg[c] = a;
+      xchg[C + c] = b;
+    }
   }
 }
 void launch_bn_bwd_finalize(const float *partials, int rows, int C, const float *gamma, const float *saved_invstd,
-                            float count, int train, float *dgamma, float *dbeta, float *coef, cudaStream_t st) {
+                            float count, int train, float *dgamma, float *dbeta, float *coef, cudaStream_t st, double *xchg_out) {
   const int M = (int)count;
   dim3 grid((C + 31) / 32), block(32, kRedY);
   { ::salun::launch_pdl(k_bn_bwd_finalize, dim3(grid), dim3(block), 0, st, partials, rows > 0 ? rows : bwd_rows(M, C), C, gamma, saved_invstd, count, train, dgamma,
-                                            dbeta, coef); ++::salun::g_launch_count; }
+                                            dbeta, coef, xchg_out); ++::salun::g_launch_count; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sync-BN exchange over NVLink peer memory (see salun_elem.cuh)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(512) k_syncbn_exchange(SyncBnPeers p, unsigned long long epoch, int mode, int C,
+                                                         double *__restrict__ slices, double local_count,
+                                                         double *__restrict__ count_out, float *__restrict__ coef) {
+  double *mine = p.slot[p.rank];
+  if (mode == 0) {   // publish this rank's sums: the kStatSlices row slices collapse to one
+    for (int j = threadIdx.x; j < 2 * C; j += blockDim.x) {
+      double s = 0.0;
+      for (int i = 0; i < kStatSlices; ++i) s += slices[(size_t)i * 2 * C + j];
+      mine[j] = s;
+    }
+  }
+  if (threadIdx.x == 0) mine[2 * C] = local_count;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < p.world) {
+    st_release_sys(p.flags[threadIdx.x] + p.rank, epoch);          // "rank has published epoch" into every peer's memory
+    const unsigned long long *f = p.flags[p.rank] + threadIdx.x;   // wait until peer threadIdx.x has published it too
+    const long long t0 = clock64();
+    while (ld_acquire_sys(f) < epoch) {
+      if (clock64() - t0 > 20000000000LL) __trap();                // ~10 s: a missing rank must fail loudly, not hang
+    }
+  }
+  __syncthreads();
+  double cnt = 0.0;
+  for (int r = 0; r < p.world; ++r) cnt += p.slot[r][2 * C];
+  for (int j = threadIdx.x; j < 2 * C; j += blockDim.x) {
+    double s = 0.0;
+    for (int r = 0; r < p.world; ++r) s += p.slot[r][j];           // rank order: the same sum on every rank
+    if (mode == 0) {
+      slices[j] = s;
+      for (int i = 1; i < kStatSlices; ++i) slices[(size_t)i * 2 * C + j] = 0.0;
+    } else {
+      coef[C + j] = (float)(s / cnt);                                // coef[C + c] = mean dZ, coef[2C + c] = mean dZ * xhat
+    }
+  }
+  if (mode == 0 && threadIdx.x == 0) *count_out = cnt;
+}
+void launch_syncbn_exchange(const SyncBnPeers &p, unsigned long long epoch, int mode, int C, double *slices,
+                            double local_count, double *count_out, float *coef, cudaStream_t st) {
+  k_syncbn_exchange<<<1, 512, 0, st>>>(p, epoch, mode, C, slices, local_count, count_out, coef);
+  ++::salun::g_launch_count;
 }
 
 template <int kU, int kMinB>

@@ -19,6 +19,8 @@ struct BnFwd {            // one BatchNorm applied to a raw conv output y[M][C]
   const float *gamma, *beta;
   float *running_mean, *running_var;  // updated in train mode (momentum, unbiased var)
   float *saved_mean, *saved_invstd;   // written for the backward pass
+  const double *count_dev;            // optional: the element count of the statistics (sync-BN: the GLOBAL pixel count);
+                                      // nullptr = the M of this launch
 };
 
 // partial column sums written by the GEMM epilogue -> kStatSlices double slices
@@ -38,8 +40,25 @@ void launch_bn_bwd_reduce(const act_t *dout, const uint8_t *relu_mask, const act
                           int C, cudaStream_t st);
 // partials -> dgamma, dbeta (into the grad arena) and the per-channel coefficients k1, m1, m2 of the apply pass
 // rows > 0: number of partial rows (fused dgrad-epilogue partials); rows == 0: the rows launch_bn_bwd_reduce wrote
+// xchg_out (optional, sync-BN): the two sums in double, [2][C], for the cross-rank exchange that then owns coef[C..3C)
 void launch_bn_bwd_finalize(const float *partials, int rows, int C, const float *gamma, const float *saved_invstd,
-                            float count, int train, float *dgamma, float *dbeta, float *coef, cudaStream_t st);
+                            float count, int train, float *dgamma, float *dbeta, float *coef, cudaStream_t st,
+                            double *xchg_out = nullptr);
+
+// ---- sync-BN: statistics of a batch sharded over ranks, exchanged through NVLink peer memory ----
+// Every rank owns a symmetric slot [2][C] + 2 doubles per BatchNorm and direction.  One CTA: publish the local sums,
+// cross-rank barrier on per-peer epoch flags (release / acquire at system scope), sum the peers' slots in RANK order
+// (identical result everywhere).
+//   mode 0 (forward) : local = the kStatSlices slices of this rank (sum x, sum x^2) and its pixel count;
+//                      out   = slices[0] <- global sums, slices[1..] <- 0, count_out <- global count
+//   mode 1 (backward): local = xchg slot already written by launch_bn_bwd_finalize; out = coef[C..3C) <- global sums / count
+struct SyncBnPeers {
+  double *slot[8];                 // this BatchNorm's slot on every rank (slot[rank] is the local one)
+  unsigned long long *flags[8];    // flags[r][s]: epoch last published by rank s, in rank r's memory
+  int rank, world;
+};
+void launch_syncbn_exchange(const SyncBnPeers &p, unsigned long long epoch, int mode, int C, double *slices,
+                            double local_count, double *count_out, float *coef, cudaStream_t st);
 // dY = k1 * (dZ - m1 - xhat * m2); written padded (for the 4-D TMA consumers) or flat [M][C]; optionally dZ too
 void launch_bn_bwd_apply(const act_t *dout, const uint8_t *relu_mask, const act_t *y,
                          const float *saved_mean, const float *saved_invstd, const float *coef, act_t *dy,

@@ -91,6 +91,15 @@ struct salun_resnet {
   std::map<int, std::vector<ConvMaps>> plans;
   int last_n, last_train;
   bool fwd_done;
+  // sync-BN (salun_resnet_enable_syncbn): per-BatchNorm statistics slots in NVLink peer-mapped memory
+  bool syncbn;
+  double *sb_sums[8];                 // every rank's slot arena
+  unsigned long long *sb_flags[8];    // every rank's epoch flags [world]
+  int sb_rank, sb_world;
+  unsigned long long sb_epoch;
+  std::vector<int64_t> sb_off;        // per conv: offset of its forward slot; the backward slot sits sb_half further
+  int64_t sb_half;
+  double *sb_count;                   // device [n_convs]: global pixel count of each BatchNorm (written by the exchange)
 };
 
 namespace salun {
@@ -265,6 +274,23 @@ static int build_plan(salun_resnet *net, int n, std::vector<ConvMaps> **out) {
   return SALUN_OK;
 }
 
+static SyncBnPeers sb_peers(const salun_resnet *net, int ci, bool backward) {
+  SyncBnPeers p{};
+  p.rank = net->sb_rank;
+  p.world = net->sb_world;
+  for (int r = 0; r < net->sb_world; ++r) {
+    p.slot[r] = net->sb_sums[r] + net->sb_off[ci] + (backward ? net->sb_half : 0);
+    p.flags[r] = net->sb_flags[r];
+  }
+  return p;
+}
+// batch statistics of a sharded batch: sum the ranks' (sum x, sum x^2, count) before the BatchNorm apply reads them
+static void sync_stats(salun_resnet *net, const ConvL &L, int M, cudaStream_t st) {
+  if (!net->syncbn) return;
+  const int ci = (int)(&L - net->convs.data());
+  launch_syncbn_exchange(sb_peers(net, ci, false), ++net->sb_epoch, 0, L.cout, L.slices, (double)M, net->sb_count + ci, nullptr, st);
+}
+
 static int conv_forward(salun_resnet *net, const ConvL &L, const ConvMaps &m, int n, int train, cudaStream_t st) {
   const int M = n * L.hout * L.hout;
   ConvGemmArgs a{};
@@ -289,7 +315,10 @@ static int conv_forward(salun_resnet *net, const ConvL &L, const ConvMaps &m, in
     r.stat_sum = a.stat_sum;
     r.stat_sq = a.stat_sq;
     TRY(launch_conv_rw(m.rwA, m.rwB, r, net->ctx->num_sms, st));
-    if (train) launch_bn_stats_reduce(L.stat_sum, L.stat_sq, (M + 127) / 128 * 4, L.cout, L.slices, st);
+    if (train) {
+      launch_bn_stats_reduce(L.stat_sum, L.stat_sq, (M + 127) / 128 * 4, L.cout, L.slices, st);
+      sync_stats(net, L, M, st);
+    }
     return SALUN_OK;
   }
   if (L.dy_padded) {
@@ -305,12 +334,16 @@ static int conv_forward(salun_resnet *net, const ConvL &L, const ConvMaps &m, in
   }
   a.pair = m.pair_fwd;
   TRY(launch_conv_gemm(m.fwdA, m.fwdB, a, bn, st));
-  if (train) launch_bn_stats_reduce(L.stat_sum, L.stat_sq, (M + 127) / 128 * 4, L.cout, L.slices, st);
+  if (train) {
+    launch_bn_stats_reduce(L.stat_sum, L.stat_sq, (M + 127) / 128 * 4, L.cout, L.slices, st);
+    sync_stats(net, L, M, st);
+  }
   return SALUN_OK;
 }
 
 static BnFwd bn_of(salun_resnet *net, const ConvL &L) {
   BnFwd b;
+  b.count_dev = net->syncbn ? net->sb_count + (&L - net->convs.data()) : nullptr;
   b.y = L.y;
   b.slices = L.slices;
   b.gamma = net->params + L.g_off;
@@ -366,8 +399,14 @@ static void bn_backward(salun_resnet *net, const ConvL &L, const act_t *dout, co
   const int fused_rows = net->bwd_fused_rows[ci];  // > 0: the dgrad GEMM that produced `dout` already reduced dZ, dZ*xhat
   if (fused_rows == 0)
     launch_bn_bwd_reduce(dout, relu_act, L.y, L.saved_mean, L.saved_invstd, L.bwd_partials, n, H, H, L.cout, st);
+  const bool sync = net->syncbn && train;
+  SyncBnPeers sp{};
+  if (sync) sp = sb_peers(net, ci, true);
   launch_bn_bwd_finalize(L.bwd_partials, fused_rows, L.cout, net->params + L.g_off, L.saved_invstd, (float)(n * H * H),
-                         train, net->grads + L.g_off, net->grads + L.b_off, L.coef, st);
+                         train, net->grads + L.g_off, net->grads + L.b_off, L.coef, st, sync ? sp.slot[sp.rank] : nullptr);
+  // sync-BN: dgamma / dbeta stay this rank's sums (the data-parallel gradient average combines them); the batch means
+  // inside dX are over the GLOBAL batch
+  if (sync) launch_syncbn_exchange(sp, ++net->sb_epoch, 1, L.cout, nullptr, (double)(n * H * H), nullptr, L.coef, st);
   launch_bn_bwd_apply(dout, relu_act, L.y, L.saved_mean, L.saved_invstd, L.coef, L.dy, L.dy_padded ? 1 : 0, dz, n, H, H,
                       L.cout, st);
 }
@@ -656,6 +695,9 @@ int salun_resnet_create(salun_ctx *ctx, const salun_resnet_cfg *cfg, float *para
   net->rmean = running_mean;
   net->rvar = running_var;
   net->fwd_done = false;
+  net->syncbn = false;
+  net->sb_epoch = 0;
+  net->sb_count = nullptr;
   net->wgred_host = nullptr;
   net->side = nullptr;
   net->ev_fork = net->ev_join = nullptr;
@@ -771,6 +813,56 @@ int salun_resnet_create(salun_ctx *ctx, const salun_resnet_cfg *cfg, float *para
   A(dmalloc(net, &net->loss_ps, (size_t)nb, true));
 #undef A
   *out = net;
+  return SALUN_OK;
+}
+
+static int64_t syncbn_layout(const std::vector<ConvL> &convs, std::vector<int64_t> *off) {
+  int64_t o = 0;
+  for (const ConvL &L : convs) {
+    if (off) off->push_back(o);
+    o += 2 * (int64_t)L.cout + 2;
+  }
+  return o;  // one direction; the arena holds forward and backward slots: 2 * o doubles
+}
+
+int64_t salun_resnet_syncbn_doubles(const salun_resnet_cfg *cfg) {
+  if (!cfg || cfg->depth >= 50) return -1;
+  std::vector<ConvL> c;
+  std::vector<Act> a;
+  std::vector<Block> b;
+  int64_t n, fw, fb;
+  int nb, feat;
+  if (build_arch(*cfg, &c, &a, &b, &n, &nb, &fw, &fb, &feat)) return -1;
+  return 2 * syncbn_layout(c, nullptr);
+}
+
+int salun_resnet_enable_syncbn(salun_resnet *net, double *const *peer_sums_host, unsigned long long *const *peer_flags_host,
+                               int rank, int world) {
+  SALUN_REQUIRE(net && peer_sums_host && peer_flags_host, "NULL argument");
+  SALUN_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "rank / world out of range (<= 8 ranks)");
+  if (net->flat) {
+    set_error("salun_resnet_enable_syncbn: served for the BasicBlock runtime (resnet18 / 34)");
+    return SALUN_ERR_UNSUPPORTED;
+  }
+  SALUN_CUDA_OK(cudaSetDevice(net->ctx->device));
+  net->sb_off.clear();
+  net->sb_half = syncbn_layout(net->convs, &net->sb_off);
+  for (int r = 0; r < world; ++r) {
+    SALUN_REQUIRE(peer_sums_host[r] && peer_flags_host[r], "NULL peer buffer");
+    net->sb_sums[r] = peer_sums_host[r];
+    net->sb_flags[r] = peer_flags_host[r];
+  }
+  net->sb_rank = rank;
+  net->sb_world = world;
+  if (!net->sb_count) {
+    void *q = nullptr;
+    SALUN_CUDA_OK(cudaMalloc(&q, net->convs.size() * sizeof(double)));
+    SALUN_CUDA_OK(cudaMemset(q, 0, net->convs.size() * sizeof(double)));
+    net->allocs.push_back(q);
+    net->sb_count = (double *)q;
+  }
+  net->sb_epoch = 0;
+  net->syncbn = true;
   return SALUN_OK;
 }
 

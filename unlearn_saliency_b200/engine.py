@@ -150,6 +150,32 @@ class ResNetEngine:
         self._loss = torch.zeros(1, device=dev)
         self.training = True
 
+    def enable_sync_bn(self, group=None):
+        """Train-mode BatchNorm over the GLOBAL mini-batch when the batch is sharded across ranks (sync-BN): the per-BN
+        sums are exchanged through NVLink peer-mapped symmetric memory inside the step (salun_resnet_enable_syncbn), so a
+        data-parallel step computes what the reference's single-process step computes on the concatenated batch.
+        torch.distributed (NCCL) must be initialised; every rank calls this and then runs the same sequence of steps."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        n = int(self._lib.salun_resnet_syncbn_doubles(C.byref(self.cfg)))
+        if n <= 0:
+            raise RuntimeError("sync-BN is served for resnet18 / resnet34")
+        self._sb_sums = symm_mem.empty(n, dtype=torch.float64, device=self.device)
+        self._sb_flags = symm_mem.empty(max(world, 8), dtype=torch.int64, device=self.device)
+        self._sb_sums.zero_()
+        self._sb_flags.zero_()
+        self._sb_hs = symm_mem.rendezvous(self._sb_sums, group)
+        self._sb_hf = symm_mem.rendezvous(self._sb_flags, group)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group)                      # every rank's buffers are zeroed before anyone publishes an epoch
+        sums = (C.c_void_p * world)(*[int(p) for p in self._sb_hs.buffer_ptrs])
+        flags = (C.c_void_p * world)(*[int(p) for p in self._sb_hf.buffer_ptrs])
+        check(self._lib.salun_resnet_enable_syncbn(self._h, sums, flags, rank, world), "salun_resnet_enable_syncbn")
+        self.sync_bn = True
+        return self
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.salun_resnet_destroy(self._h)
