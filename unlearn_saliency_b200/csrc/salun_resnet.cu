@@ -342,7 +342,7 @@ static int conv_forward(salun_resnet *net, const ConvL &L, const ConvMaps &m, in
 }
 
 static BnFwd bn_of(salun_resnet *net, const ConvL &L) {
-  BnFwd b;
+  BnFwd b{};
   b.count_dev = net->syncbn ? net->sb_count + (&L - net->convs.data()) : nullptr;
   b.y = L.y;
   b.slices = L.slices;

@@ -225,7 +225,7 @@ static int fconv_forward(FlatNet *net, int ci, const FMaps &m, const float *x, i
 }
 
 static BnFwd fbn_of(FlatNet *net, const FConv &L) {
-  BnFwd b;
+  BnFwd b{};
   b.y = L.y;
   b.slices = L.slices;
   b.gamma = net->params + L.g_off;
