@@ -389,6 +389,16 @@ int salun_augment_batch(salun_ctx *ctx, const uint8_t *images_hwc, int64_t n_ima
 int salun_eval_logits(salun_ctx *ctx, const float *logits, const int64_t *labels, int n, int K, float *probs,
                       double *loss_sum_dev, int64_t *correct_dev, void *stream);
 
+/* One step of the class-conditional generalized (DDIM) sampler after the two U-Net passes of classifier-free guidance:
+ *   et = (1 + s) eps_cond - s eps_null ;  x0_t = (xt - et sqrt(1 - at)) / sqrt(at) ;
+ *   c1 = eta sqrt((1 - at/at_next)(1 - at_next)/(1 - at)) ;  c2 = sqrt((1 - at_next) - c1^2) ;
+ *   x_next = sqrt(at_next) x0_t + c1 noise + c2 et          (at, at_next: fp32 [n] = compute_alpha of t and next_t)
+ * eps_null NULL: no guidance (et = eps_cond); noise may be NULL when eta == 0; x0_out optional.
+ * replaces the update statements of generalized_steps_conditional   DDPM/functions/denoising.py:72-95 */
+int salun_ddim_step(salun_ctx *ctx, const float *eps_cond, const float *eps_null, const float *xt, const float *noise,
+                    const float *at, const float *at_next, float cond_scale, float eta, int n, int chw, float *x_next,
+                    float *x0_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,13 +84,22 @@ def test_resnet50_split_forward_backward(salun_ctx):
     for train, sign in ((False, -1.0), (True, 1.0)):
         b = {k: v.clone() for k, v in buffers.items()}
         lref, oref, gref = OC.bottleneck_loss_and_grads(params, b, x, y, train=train, sign=sign)
+        # yardstick: the same statements with torch's default TF32 convolutions on this GPU
+        torch.backends.cudnn.allow_tf32 = True
+        pc = {k: v.cuda() for k, v in params.items()}
+        bc = {k: v.clone().cuda() for k, v in buffers.items()}
+        _, otf, gtf = OC.bottleneck_loss_and_grads(pc, bc, x.cuda(), y.cuda(), train=train, sign=sign)
+        torch.backends.cudnn.allow_tf32 = False
+        flat_ref = torch.cat([r.flatten() for r in gref.values()])
+        whole_tf32 = _rel(torch.cat([t.flatten() for t in gtf.values()]), flat_ref)
         eng.train(train)
         loss, logits = eng.forward_backward(x.cuda(), y.cuda(), loss_sign=sign, want_logits=True)
-        assert _rel(logits, oref) < 2e-3, _rel(logits, oref)      # 53 layers; measured 9.5e-4
         gd = eng.grad_dict()
-        whole = _rel(torch.cat([gd[k].flatten() for k in gref]), torch.cat([r.flatten() for r in gref.values()]))
-        print("resnet50 split whole-gradient error", whole, "train" if train else "eval")
-        assert whole < (5e-2 if train else 1e-2), whole              # measured 4.0e-3 (eval); batch 4 train-mode BN is chaotic
+        whole = _rel(torch.cat([gd[k].flatten() for k in gref]), flat_ref)
+        print(f"resnet50 {'train' if train else 'eval'}: logits {_rel(logits, oref):.3e} (TF32 {_rel(otf, oref):.3e}); "
+              f"whole gradient {whole:.3e} (TF32 {whole_tf32:.3e})")
+        assert _rel(logits, oref) < max(2e-3, _rel(otf, oref)), _rel(logits, oref)
+        assert whole < whole_tf32, (whole, whole_tf32)            # closer to fp32 than the reference's own GPU arithmetic
     eng.close()
 
 

@@ -70,6 +70,7 @@ _SIGNATURES = {
     "salun_clip_coef": [_P, _P, _F, _P, _P],
     "salun_augment_batch": [_P, _P, _I64, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P],
     "salun_eval_logits": [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P],
+    "salun_ddim_step": [_P, _P, _P, _P, _P, _P, _P, _F, _F, C.c_int, C.c_int, _P, _P, _P],
     "salun_masked_adam_step": [_P, _P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I64, _P, _P],
     # tcgen05 GEMM / convolution entry points (salun_gemm.cu)
     "salun_gemm_bf16_tn": [_P, _P, _P, _P, _P, _I64, _I64, _I64, _P],

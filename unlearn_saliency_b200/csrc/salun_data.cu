@@ -116,3 +116,52 @@ int salun_eval_logits(salun_ctx *ctx, const float *logits, const int64_t *labels
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// One step of the conditional DDIM / generalized sampler (DDPM/functions/denoising.py:72-95) after the two U-Net passes:
+//   et      = (1 + s) * eps_cond - s * eps_null                      (classifier-free guidance, models/diffusion.py:340-355)
+//   x0_t    = (xt - et * sqrt(1 - at)) / sqrt(at)
+//   c1      = eta * sqrt((1 - at / at_next) * (1 - at_next) / (1 - at)) ;  c2 = sqrt((1 - at_next) - c1^2)
+//   xt_next = sqrt(at_next) * x0_t + c1 * noise + c2 * et
+// per-sample at / at_next (compute_alpha, :4-7); the same fp32 operation order as the torch statements.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace salun {
+__global__ void __launch_bounds__(256) k_ddim_step(const float *__restrict__ eps_cond, const float *__restrict__ eps_null,
+                                                   const float *__restrict__ xt, const float *__restrict__ noise,
+                                                   const float *__restrict__ at, const float *__restrict__ at_next, float s,
+                                                   float eta, long long total, int chw, float *__restrict__ x_next,
+                                                   float *__restrict__ x0_out) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int n = (int)(i / chw);
+    const float a = at[n], an = at_next[n];
+    float et = eps_cond[i];
+    if (eps_null) et = __fsub_rn(__fmul_rn(1.f + s, et), __fmul_rn(s, eps_null[i]));
+    const float x0 = __fdiv_rn(__fsub_rn(xt[i], __fmul_rn(et, sqrtf(1.f - a))), sqrtf(a));
+    const float c1 = eta * sqrtf(__fdiv_rn(__fmul_rn(1.f - __fdiv_rn(a, an), 1.f - an), 1.f - a));
+    const float c2 = sqrtf(__fsub_rn(1.f - an, __fmul_rn(c1, c1)));
+    float v = __fmul_rn(sqrtf(an), x0);
+    v = __fadd_rn(v, __fmul_rn(c1, noise ? noise[i] : 0.f));
+    v = __fadd_rn(v, __fmul_rn(c2, et));
+    x_next[i] = v;
+    if (x0_out) x0_out[i] = x0;
+  }
+}
+}  // namespace salun
+
+extern "C" int salun_ddim_step(salun_ctx *ctx, const float *eps_cond, const float *eps_null, const float *xt, const float *noise,
+                               const float *at, const float *at_next, float cond_scale, float eta, int n, int chw,
+                               float *x_next, float *x0_out, void *stream) {
+  SALUN_REQUIRE(ctx && eps_cond && xt && at && at_next && x_next, "NULL argument");
+  SALUN_REQUIRE(n >= 0 && chw > 0, "bad sizes");
+  SALUN_REQUIRE(eta == 0.f || noise, "eta != 0 needs the noise tensor");
+  if (n == 0) return SALUN_OK;
+  SALUN_CUDA_OK(cudaSetDevice(ctx->device));
+  const long long total = (long long)n * chw;
+  long long g = (total + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  salun::k_ddim_step<<<(int)g, 256, 0, (cudaStream_t)stream>>>(eps_cond, eps_null, xt, noise, at, at_next, cond_scale, eta, total,
+                                                               chw, x_next, x0_out);
+  ++salun::g_launch_count;
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
