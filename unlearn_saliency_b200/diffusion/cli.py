@@ -63,6 +63,8 @@ def parse_args_and_config(argv=None):
     p.add_argument("--negative_guidance", type=float, default=7.5)
     p.add_argument("--sparse", type=bool, default=False)
     # additions of this mirror
+    p.add_argument("--visualize", action="store_true",
+                   help="sample_visualization at every snapshot of saliency_unlearn, like the reference (runners/diffusion.py:611-619)")
     p.add_argument("--precision", type=str, default=None, choices=["bf16", "split"],
                    help="engine build: default split (fp32-class) for generate_mask, bf16 for saliency_unlearn")
     p.add_argument("--synthetic", type=int, default=0, help="use N random images per split instead of CIFAR-10")
@@ -117,8 +119,10 @@ def main(argv=None):
         runner.generate_mask()
     elif args.mode == "saliency_unlearn":
         runner.saliency_unlearn()
+    elif args.mode == "visualization":
+        runner.visualization()
     else:
-        raise SystemExit(f"mode {args.mode!r}: only generate_mask and saliency_unlearn run on the engine "
+        raise SystemExit(f"mode {args.mode!r}: generate_mask, saliency_unlearn and visualization run on the engine "
                          "(train / forget / retrain are the reference's own loops)")
     return 0
 

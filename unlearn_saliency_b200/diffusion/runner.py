@@ -364,6 +364,33 @@ class Diffusion:
         eng.close()
         return infos
 
+    def sample_visualization(self, eng, name, cond_scale):
+        """runners/diffusion.py:877-931: visualization_samples images (the same number per class) through the engine's
+        class-conditional sampler, saved as <log_dir>/sample-<name>.png.  Flags as in DDPM/train.py (--sample_type
+        generalized, --skip_type, --timesteps, --eta)."""
+        from .sampler import EngineSampler
+        args, config = self.args, self.config
+        total = int(config.training.visualization_samples)
+        bs = min(int(config.sampling.batch_size), eng.max_batch // 2)
+        was_training = eng.training
+        eng.eval()
+        sm = EngineSampler(eng, self.betas)
+        out_dir = getattr(config, "log_dir", None) or args.ckpt_folder
+        imgs = sm.sample_visualization(config.data.n_classes, total, bs, cond_scale, config.data.image_size,
+                                       config.data.channels, path=os.path.join(out_dir, f"sample-{name}.png"),
+                                       sample_type=getattr(args, "sample_type", "generalized"),
+                                       skip_type=getattr(args, "skip_type", "uniform"),
+                                       timesteps=int(getattr(args, "timesteps", 1000)), eta=float(getattr(args, "eta", 1.0)))
+        eng.train(was_training)
+        return imgs
+
+    def visualization(self):
+        """DDPM/train.py --mode visualization (runners/diffusion.py:635-668 `sample`): load the checkpoint, sample, save"""
+        eng = self._engine(2 * int(self.config.sampling.batch_size))
+        imgs = self.sample_visualization(eng, str(self.args.cond_scale), self.args.cond_scale)
+        eng.close()
+        return imgs
+
     def saliency_unlearn(self):
         args, config = self.args, self.config
         remain_loader, forget_loader = self._loaders()
@@ -407,5 +434,8 @@ class Diffusion:
                 un.save_checkpoint(os.path.join(config.ckpt_dir, "ckpt.pth"), step, write=(rank == 0))
                 if self.on_snapshot is not None and rank == 0:
                     self.on_snapshot(step, eng.state_dict(prefix="module."))
+                if rank == 0 and getattr(args, "visualize", False):
+                    # :611-619 sample_visualization(test_model, step, cond_scale) on the engine's forward kernels
+                    self.sample_visualization(eng, step, args.cond_scale)
         eng.close()
         return None if loss is None else float(loss)
