@@ -399,6 +399,64 @@ int salun_ddim_step(salun_ctx *ctx, const float *eps_cond, const float *eps_null
                     const float *at, const float *at_next, float cond_scale, float eta, int n, int chw, float *x_next,
                     float *x0_out, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Op-level entry points (csrc/salun_ops.cu): the tcgen05 convolution / GEMM and the elementwise kernels one layer at a
+ * time, plus the layers the Stable-Diffusion U-Net adds (LayerNorm, GEGLU, multi-head self / cross attention, cos|sin
+ * timestep embedding, GroupNorm of any width).  The SD U-Net forward (SD/ldm/modules/diffusionmodules/openaimodel.py:814-846)
+ * is composed from them by unlearn_saliency_b200/sd/engine.py and replayed from a CUDA graph.
+ * Activations ("act") are bf16 in libsalun.so and (hi, lo) bf16 pairs in libsalun_split.so: salun_act_bytes() per element.
+ * Layouts: padded NHWC [n][H+2][W+2][C] (zero halo, written once by the caller's memset) or flat [rows][C].
+ * --------------------------------------------------------------------------------------------------------------- */
+int salun_act_bytes(void);   /* 2 (bf16) or 4 (bf16 hi/lo pair) */
+int salun_wop_k(void);       /* bf16 elements a prepared weight operand spends per weight element: 1 or 4 */
+int salun_op_f32_to_act(salun_ctx *ctx, const float *src, int64_t ld_src, void *dst, int64_t ld_dst, int64_t rows, int64_t cols,
+                        void *stream);
+int salun_op_act_to_f32(salun_ctx *ctx, const void *src, int64_t ld_src, float *dst, int64_t ld_dst, int64_t rows, int64_t cols,
+                        void *stream);
+/* x fp32 NCHW [n][C][H][W] -> padded NHWC act with Cp >= C channels (the extra ones zero) and back */
+int salun_op_nchw_to_padded(salun_ctx *ctx, const float *x, void *out_pad, int n, int C, int Cp, int H, int W, void *stream);
+int salun_op_padded_to_nchw(salun_ctx *ctx, const void *in_pad, float *out, int n, int C, int H, int W, void *stream);
+/* out NCHW [n][C][H][W] = y[pixel][c] (+ bias[c]); y: fp32 rows of leading dimension ld >= C (a GEMM with padded N) */
+int salun_op_rows_to_nchw(salun_ctx *ctx, const float *y, int ld, const float *bias, float *out, int n, int C, int H, int W,
+                          void *stream);
+/* PyTorch weight (Conv2d OIHW fp32, or Linear [out][in] with ks = 1) -> tensor-core operand rows [cout_pad][ks*ks*cin_pad]
+ * (tap-major then channel, zero padded); salun_wop_k() * 2 bytes per element */
+int salun_op_prep_weight(salun_ctx *ctx, const float *w, void *wop, int cout, int cin, int ks, int cout_pad, int cin_pad,
+                         void *stream);
+/* Stride-1 convolution (ks 3 / pad 1 or ks 1) or Linear over token rows (in_flat, ks 1) with the epilogue fused:
+ *   out = conv(in, w) + bias[col] + rowbias[sample][col] + addend        (bias / rowbias / addend optional)
+ * in: padded act [n][H+2][W+2][cin] or flat [n*H*W][cin]; out: act flat or padded (out_pad) and / or fp32 flat (out_f32);
+ * addend has the layout of out.  cin, cout multiples of 64 (pad the operand).  rowbias: fp32 [n][rb_ld].
+ * replaces nn.Conv2d / nn.Linear + the adds of ResBlock._forward (openaimodel.py:268-288), CrossAttention.to_q / to_k / to_v
+ * / to_out, FeedForward (attention.py:37-66,168-192) */
+int salun_op_conv(salun_ctx *ctx, const void *in, int in_flat, const void *wop, const float *bias, const float *rowbias, int rb_ld,
+                  const void *addend, void *out, int out_pad, float *out_f32, int n, int H, int W, int cin, int cout, int ks,
+                  void *stream);
+/* Downsample: conv 3x3 / stride 2 / padding 1 (openaimodel.py:131-160).  col_scratch: act [n*(Hin/2)*(Win/2)][9*cin] */
+int salun_op_conv_s2(salun_ctx *ctx, const void *in_pad, void *col_scratch, const void *wop, const float *bias, void *out_padded,
+                     int n, int Hin, int Win, int cin, int cout, void *stream);
+/* GroupNorm(32, C, eps) (+ SiLU): padded in -> padded or flat out; stats_ws: fp32 [n][32][2]  (util.py:217-224 normalization) */
+int salun_op_groupnorm(salun_ctx *ctx, const void *in_pad, const float *gamma, const float *beta, float *stats_ws, void *out,
+                       int out_flat, int n, int H, int W, int C, float eps, int swish, void *stream);
+int salun_op_upsample2(salun_ctx *ctx, const void *in_pad, void *out_pad, int n, int H, int C, void *stream);
+int salun_op_concat(salun_ctx *ctx, const void *a_pad, int Ca, const void *b_pad, int Cb, void *out_pad, int n, int H, void *stream);
+/* out[n][N] = (silu_in ? silu(x) : x)[n][K] . w[N][K]^T + b  in fp32 (time_embed / emb_layers, openaimodel.py:556-560,222-229) */
+int salun_op_linear_f32(salun_ctx *ctx, const float *x, const float *w, const float *b, float *out, float *tmp, int n, int K, int N,
+                        int silu_in, void *stream);
+/* timestep_embedding(t, dim, max_period): [cos | sin]   (SD/ldm/modules/diffusionmodules/util.py:173-197) */
+int salun_sd_timestep_embedding(salun_ctx *ctx, const float *t, float *out, int n, int dim, float max_period, void *stream);
+/* nn.LayerNorm(C) over token rows (attention.py:221-223) */
+int salun_sd_layernorm(salun_ctx *ctx, const void *x, const float *gamma, const float *beta, void *out, int64_t rows, int C,
+                       float eps, void *stream);
+/* GEGLU: out[r][c] = proj[r][c] * gelu(proj[r][Ci + c])   (attention.py:37-44) */
+int salun_sd_geglu(salun_ctx *ctx, const void *proj, void *out, int64_t rows, int Ci, void *stream);
+/* Multi-head attention: out = merge_heads(softmax(q_h k_h^T / sqrt(d)) v_h); q [n*Tq][heads*d], k / v [n*Tk][heads*d] (act);
+ * two batched tcgen05 GEMMs per call over (sample, head) units, fp32 scores.  ws: salun_sd_attention_ws_bytes(...) bytes.
+ * replaces CrossAttention.forward after the projections   SD/ldm/modules/attention.py:177-191 */
+int64_t salun_sd_attention_ws_bytes(int n, int Tq, int Tk, int heads, int d);
+int salun_sd_attention(salun_ctx *ctx, void *ws, int64_t ws_bytes, const void *q, const void *k, const void *v, void *out, int n,
+                       int Tq, int Tk, int heads, int d, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,27 @@ _SIGNATURES = {
     "salun_clip_coef": [_P, _P, _F, _P, _P],
     "salun_augment_batch": [_P, _P, _I64, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P],
     "salun_eval_logits": [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P],
+    # op-level entry points (salun_ops.cu)
+    "salun_act_bytes": [],
+    "salun_wop_k": [],
+    "salun_op_f32_to_act": [_P, _P, _I64, _P, _I64, _I64, _I64, _P],
+    "salun_op_act_to_f32": [_P, _P, _I64, _P, _I64, _I64, _I64, _P],
+    "salun_op_nchw_to_padded": [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P],
+    "salun_op_padded_to_nchw": [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P],
+    "salun_op_rows_to_nchw": [_P, _P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P],
+    "salun_op_prep_weight": [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P],
+    "salun_op_conv": [_P, _P, C.c_int, _P, _P, _P, C.c_int, _P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                      C.c_int, _P],
+    "salun_op_conv_s2": [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P],
+    "salun_op_groupnorm": [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _F, C.c_int, _P],
+    "salun_op_upsample2": [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P],
+    "salun_op_concat": [_P, _P, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P],
+    "salun_op_linear_f32": [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P],
+    "salun_sd_timestep_embedding": [_P, _P, _P, C.c_int, C.c_int, _F, _P],
+    "salun_sd_layernorm": [_P, _P, _P, _P, _P, _I64, C.c_int, _F, _P],
+    "salun_sd_geglu": [_P, _P, _P, _I64, C.c_int, _P],
+    "salun_sd_attention_ws_bytes": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int],
+    "salun_sd_attention": [_P, _P, _I64, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P],
     "salun_ddim_step": [_P, _P, _P, _P, _P, _P, _P, _F, _F, C.c_int, C.c_int, _P, _P, _P],
     "salun_masked_adam_step": [_P, _P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I64, _P, _P],
     # tcgen05 GEMM / convolution entry points (salun_gemm.cu)
@@ -89,7 +110,8 @@ _SIGNATURES = {
     "salun_resnet_enable_syncbn": [_P, C.POINTER(_P), C.POINTER(_P), C.c_int, C.c_int],
 }
 _RESTYPES = {"salun_last_error": C.c_char_p, "salun_launch_count": C.c_longlong, "salun_resnet_param_count": C.c_int64,
-             "salun_resnet_bn_channels": C.c_int64, "salun_resnet_syncbn_doubles": C.c_int64}
+             "salun_resnet_bn_channels": C.c_int64, "salun_resnet_syncbn_doubles": C.c_int64,
+             "salun_sd_attention_ws_bytes": C.c_int64}
 
 
 def exported_symbols():

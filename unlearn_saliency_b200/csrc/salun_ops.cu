@@ -1,0 +1,638 @@
+// salun_ops.cu -- op-level C ABI over the tcgen05 GEMM / convolution kernels and the elementwise kernels, plus the layers the
+// Stable-Diffusion (LDM) U-Net adds to the DDPM one: LayerNorm, GEGLU, multi-head self / cross attention, the cos|sin timestep
+// embedding, GroupNorm at any width.  The SD U-Net forward (SD/ldm/modules/diffusionmodules/openaimodel.py:814-846 with
+// ResBlock :268-288, SpatialTransformer / BasicTransformerBlock / CrossAttention SD/ldm/modules/attention.py:168-303, GEGLU
+// :37-44, timestep_embedding util.py:173-197) is composed from these ops by the host mirror (unlearn_saliency_b200/sd/engine.py)
+// and replayed from a CUDA graph; the ops are also the unit the parity tests check one by one.
+//
+// Activations are act_t (bf16, or bf16 hi/lo pairs in the split build; salun_act.cuh): padded NHWC [n][H+2][W+2][C] with a zero
+// halo for 3x3 convolutions, flat [rows][C] for token matrices.  Weights are prepared once per load into tensor-core operand
+// layout (salun_op_prep_weight).  Every call enqueues on the caller's stream; nothing synchronises.
+#include <math.h>
+#include <stdlib.h>
+
+#include "salun_elem.cuh"
+#include "salun_gemm.cuh"
+#include "salun_unet_elem.cuh"
+
+namespace salun {
+
+static inline int grid1d(long long total, int threads = 256, int cap = 148 * 8) {
+  long long g = (total + threads - 1) / threads;
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
+}
+static int ilog2i(long long v) {
+  int s = 0;
+  while ((1LL << s) < v) ++s;
+  return s;
+}
+__device__ __forceinline__ size_t pad_off4(int n, int y, int x, int H, int W, int C) {
+  return (((size_t)n * (H + 2) + y + 1) * (W + 2) + x + 1) * C;
+}
+
+// ------------------------------------------------------------------------------------------------ conversions
+__global__ void k_f32_to_act(const float *__restrict__ src, long long ld_src, act_t *__restrict__ dst, long long ld_dst,
+                             long long rows, long long cols) {
+  const long long total = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols, c = i - r * cols;
+    dst[r * ld_dst + c] = act_from_float(src[r * ld_src + c]);
+  }
+}
+__global__ void k_act_to_f32(const act_t *__restrict__ src, long long ld_src, float *__restrict__ dst, long long ld_dst,
+                             long long rows, long long cols) {
+  const long long total = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols, c = i - r * cols;
+    dst[r * ld_dst + c] = act_to_float(src[r * ld_src + c]);
+  }
+}
+// x fp32 NCHW -> padded NHWC act with Cp >= C channels (extra channels zero); the halo is not touched (zeroed at allocation)
+__global__ void k_nchw_to_padded(const float *__restrict__ x, act_t *__restrict__ out, long long total, int C, int Cp, int H,
+                                 int W) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cp);
+    long long r = i / Cp;
+    const int xx = (int)(r % W);
+    r /= W;
+    const int y = (int)(r % H), n = (int)(r / H);
+    const float v = c < C ? x[(((size_t)n * C + c) * H + y) * W + xx] : 0.f;
+    out[pad_off4(n, y, xx, H, W, Cp) + c] = act_from_float(v);
+  }
+}
+__global__ void k_padded_to_nchw(const act_t *__restrict__ in, float *__restrict__ out, long long total, int C, int H, int W) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % W);
+    long long r = i / W;
+    const int y = (int)(r % H);
+    r /= H;
+    const int c = (int)(r % C), n = (int)(r / C);
+    out[i] = act_to_float(in[pad_off4(n, y, xx, H, W, C) + c]);
+  }
+}
+// out NCHW [n][C][H][W] = y[(n*H + yy)*W + xx][c] + bias[c]   (fp32 rows of a GEMM whose N was padded to ld)
+__global__ void k_rows_to_nchw(const float *__restrict__ y, int ld, const float *__restrict__ bias, float *__restrict__ out,
+                               long long total, int C, int H, int W) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % W);
+    long long r = i / W;
+    const int yy = (int)(r % H);
+    r /= H;
+    const int c = (int)(r % C), n = (int)(r / C);
+    out[i] = y[(((size_t)n * H + yy) * W + xx) * ld + c] + (bias ? bias[c] : 0.f);
+  }
+}
+// PyTorch conv weight OIHW fp32 (or Linear [out][in], ks = 1) -> operand rows [cout_pad][ks*ks*cin_pad] (tap-major, then
+// channel), zero padded, in the weight-operand layout of this build
+__global__ void k_prep_weight(const float *__restrict__ w, wop_t *__restrict__ out, int cout, int cin, int ks, int cout_pad,
+                              int cin_pad) {
+  const int taps = ks * ks, Kp = taps * cin_pad;
+  const long long total = (long long)cout_pad * Kp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i / Kp), j = (int)(i - (long long)co * Kp);
+    const int tap = j / cin_pad, ci = j - tap * cin_pad;
+    float v = 0.f;
+    if (co < cout && ci < cin) v = w[((size_t)co * cin + ci) * taps + tap];
+    wop_store(out + (size_t)co * Kp * kWopK, j, Kp, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm (any C % 8 == 0)
+__global__ void __launch_bounds__(256) k_gn2_stats(const act_t *__restrict__ x, float *__restrict__ stats, int H, int W, int C,
+                                                   float eps) {
+  __shared__ double sh[2][256];
+  const int g = blockIdx.x, n = blockIdx.y, cpg = C / 32;
+  const long long cnt = (long long)H * W * cpg;
+  double a = 0.0, b = 0.0;
+  for (long long i = threadIdx.x; i < cnt; i += 256) {
+    const int c = (int)(i % cpg);
+    const long long p = i / cpg;
+    const int xx = (int)(p % W), y = (int)(p / W);
+    const float v = act_to_float(x[pad_off4(n, y, xx, H, W, C) + g * cpg + c]);
+    a += v;
+    b += (double)v * v;
+  }
+  sh[0][threadIdx.x] = a;
+  sh[1][threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if (threadIdx.x < o) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double mean = sh[0][0] / (double)cnt;
+    double var = sh[1][0] / (double)cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[((size_t)n * 32 + g) * 2] = (float)mean;
+    stats[((size_t)n * 32 + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+__global__ void __launch_bounds__(256) k_gn2_apply(const act_t *__restrict__ x, const float *__restrict__ stats,
+                                                   const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                   act_t *__restrict__ out, int out_flat, int swish, long long total, int H,
+                                                   int W, int C) {
+  const int vecs = C >> 3, cpg = C / 32;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int v = (int)(i % vecs);
+    long long p = i / vecs;
+    const int xx = (int)(p % W);
+    p /= W;
+    const int y = (int)(p % H), n = (int)(p / H);
+    const int c0 = v * 8;
+    float f[8];
+    ld8(x + pad_off4(n, y, xx, H, W, C) + c0, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (c0 + j) / cpg;
+      const float mean = stats[((size_t)n * 32 + g) * 2], rstd = stats[((size_t)n * 32 + g) * 2 + 1];
+      float yv = (f[j] - mean) * rstd * gamma[c0 + j] + beta[c0 + j];
+      if (swish) yv = yv / (1.f + expf(-yv));
+      f[j] = yv;
+    }
+    const size_t o = out_flat ? (((size_t)n * H + y) * W + xx) * C + c0 : pad_off4(n, y, xx, H, W, C) + c0;
+    st8(out + o, f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm / GEGLU / embedding
+// one warp per token row, C <= 2048, C % 8 == 0 (nn.LayerNorm(dim), attention.py:221-223: biased variance, eps 1e-5)
+__global__ void __launch_bounds__(256) k_layernorm(const act_t *__restrict__ x, const float *__restrict__ gamma,
+                                                   const float *__restrict__ beta, act_t *__restrict__ out, long long rows, int C,
+                                                   float eps) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int vecs = C >> 3;
+  float f[8][8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int v = lane + 32 * k;
+    if (v < vecs) {
+      ld8(x + row * C + v * 8, f[k]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += f[k][j];
+    }
+  }
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int v = lane + 32 * k;
+    if (v < vecs) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = f[k][j] - mean;
+        q += d * d;
+      }
+    }
+  }
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)C + eps);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int v = lane + 32 * k;
+    if (v < vecs) {
+      float o8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o8[j] = (f[k][j] - mean) * rstd * gamma[v * 8 + j] + beta[v * 8 + j];
+      st8(out + row * C + v * 8, o8);
+    }
+  }
+}
+// out[r][c] = proj[r][c] * gelu(proj[r][Ci + c])   (GEGLU, attention.py:37-44; exact erf GELU like F.gelu)
+__global__ void __launch_bounds__(256) k_geglu(const act_t *__restrict__ proj, act_t *__restrict__ out, long long total, int Ci) {
+  const int vecs = Ci >> 3;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long r = i / vecs;
+    const int c0 = (int)(i - r * vecs) * 8;
+    float a[8], g[8];
+    ld8(proj + r * 2 * Ci + c0, a);
+    ld8(proj + r * 2 * Ci + Ci + c0, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] *= 0.5f * g[j] * (1.f + erff(g[j] * 0.70710678118654752f));
+    st8(out + r * Ci + c0, a);
+  }
+}
+// timestep_embedding (util.py:173-197): freqs = exp(-ln(max_period) * i / half), emb = [cos(t f) | sin(t f)] (+ 0 if dim is odd)
+__global__ void k_timestep_embedding(const float *__restrict__ t, float *__restrict__ out, int n, int dim, float max_period) {
+  const int half = dim / 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * dim; i += gridDim.x * blockDim.x) {
+    const int b = i / dim, j = i - b * dim;
+    float v = 0.f;
+    if (j < 2 * half) {
+      const int k = j < half ? j : j - half;
+      const float freq = expf(-logf(max_period) * (float)k / (float)half);
+      const float arg = t[b] * freq;
+      v = j < half ? cosf(arg) : sinf(arg);
+    }
+    out[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ multi-head attention
+// (sample, head) unit g = b * heads + h.  Q rows are padded to Tqp (multiple of 128), keys to Tkp (multiple of 128), the head
+// width to dp (multiple of 64): zero padding, masked in the softmax.
+__global__ void __launch_bounds__(256) k_heads_pack_q(const act_t *__restrict__ q, act_t *__restrict__ dst, long long total, int Tq,
+                                                      int Tqp, int C, int heads, int d, int dp) {
+  const int vecs = dp >> 3;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int v = (int)(i % vecs);
+    long long r = i / vecs;
+    const int t = (int)(r % Tqp);
+    const long long g = r / Tqp;
+    const int h = (int)(g % heads);
+    const long long b = g / heads;
+    avec val = avec_zero();
+    if (t < Tq && v * 8 < d) val = ldvec(q + (b * Tq + t) * C + h * d + v * 8);
+    stvec(dst + (g * Tqp + t) * dp + v * 8, val);
+  }
+}
+// K as the B operand of S = Q K^T: operand row (g * Tkp + j), logical length dp
+__global__ void __launch_bounds__(256) k_heads_pack_k(const act_t *__restrict__ k, wop_t *__restrict__ dst, long long total, int Tk,
+                                                      int Tkp, int C, int heads, int d, int dp) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int c = (int)(i % dp);
+    long long r = i / dp;
+    const int j = (int)(r % Tkp);
+    const long long g = r / Tkp;
+    const int h = (int)(g % heads);
+    const long long b = g / heads;
+    float v = 0.f;
+    if (j < Tk && c < d) v = act_to_float(k[(b * Tk + j) * C + h * d + c]);
+    wop_store(dst + (size_t)(g * Tkp + j) * dp * kWopK, c, dp, v);
+  }
+}
+// V^T as the B operand of O = P V: operand row (g * dp + c), logical length Tkp
+__global__ void __launch_bounds__(256) k_heads_pack_vt(const act_t *__restrict__ v, wop_t *__restrict__ dst, long long total, int Tk,
+                                                       int Tkp, int C, int heads, int d, int dp) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int j = (int)(i % Tkp);
+    long long r = i / Tkp;
+    const int c = (int)(r % dp);
+    const long long g = r / dp;
+    const int h = (int)(g % heads);
+    const long long b = g / heads;
+    float val = 0.f;
+    if (j < Tk && c < d) val = act_to_float(v[(b * Tk + j) * C + h * d + c]);
+    wop_store(dst + (size_t)(g * dp + c) * Tkp * kWopK, j, Tkp, val);
+  }
+}
+// P = softmax(scale * S) over the Tk valid keys; padded query rows and padded keys get 0.  One warp per row.
+__global__ void __launch_bounds__(256) k_softmax_rows(const float *__restrict__ S, act_t *__restrict__ P, long long rows, int Tq,
+                                                      int Tqp, int Tk, int Tkp, float scale) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float *s = S + row * Tkp;
+  act_t *p = P + row * Tkp;
+  if ((int)(row % Tqp) >= Tq) {
+    for (int j = lane; j < Tkp; j += 32) p[j] = act_from_float(0.f);
+    return;
+  }
+  float mx = -INFINITY;
+  for (int j = lane; j < Tk; j += 32) mx = fmaxf(mx, s[j] * scale);
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int j = lane; j < Tk; j += 32) sum += expf(s[j] * scale - mx);
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.f / sum;
+  for (int j = lane; j < Tkp; j += 32) p[j] = act_from_float(j < Tk ? expf(s[j] * scale - mx) * inv : 0.f);
+}
+__global__ void __launch_bounds__(256) k_heads_merge(const act_t *__restrict__ oh, act_t *__restrict__ out, long long total, int Tq,
+                                                     int Tqp, int C, int heads, int d, int dp) {
+  const int vecs = d >> 3;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int v = (int)(i % vecs);
+    long long r = i / vecs;
+    const int h = (int)(r % heads);
+    r /= heads;
+    const int t = (int)(r % Tq);
+    const long long b = r / Tq;
+    const long long g = b * heads + h;
+    stvec(out + (b * Tq + t) * C + h * d + v * 8, ldvec(oh + (g * Tqp + t) * dp + v * 8));
+  }
+}
+
+static int pick_bn_ops(int N, long long M) {
+  if (N % 256 == 0 && ((M + 127) / 128) * (N / 256) >= 96) return 256;
+  return N % 128 == 0 ? 128 : 64;
+}
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace salun
+
+using namespace salun;
+
+extern "C" {
+
+int salun_act_bytes(void) { return (int)sizeof(act_t); }
+int salun_wop_k(void) { return kWopK; }
+
+int salun_op_f32_to_act(salun_ctx *ctx, const float *src, int64_t ld_src, void *dst, int64_t ld_dst, int64_t rows, int64_t cols,
+                        void *stream) {
+  SALUN_REQUIRE(ctx && src && dst && rows >= 0 && cols >= 0, "bad argument");
+  if (rows * cols == 0) return SALUN_OK;
+  SALUN_CUDA_OK(cudaSetDevice(ctx->device));
+  k_f32_to_act<<<grid1d(rows * cols), 256, 0, (cudaStream_t)stream>>>(src, ld_src, (act_t *)dst, ld_dst, rows, cols);
+  ++g_launch_count;
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+int salun_op_act_to_f32(salun_ctx *ctx, const void *src, int64_t ld_src, float *dst, int64_t ld_dst, int64_t rows, int64_t cols,
+                        void *stream) {
+  SALUN_REQUIRE(ctx && src && dst && rows >= 0 && cols >= 0, "bad argument");
+  if (rows * cols == 0) return SALUN_OK;
+  SALUN_CUDA_OK(cudaSetDevice(ctx->device));
+  k_act_to_f32<<<grid1d(rows * cols), 256, 0, (cudaStream_t)stream>>>((const act_t *)src, ld_src, dst, ld_dst, rows, cols);
+  ++g_launch_count;
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+int salun_op_nchw_to_padded(salun_ctx *ctx, const float *x, void *out_pad, int n, int C, int Cp, int H, int W, void *stream) {
+  SALUN_REQUIRE(ctx && x && out_pad && n > 0 && C > 0 && Cp >= C && Cp % 8 == 0, "bad argument");
+  SALUN_CUDA_OK(cudaSetDevice(ctx->device));
+  const long long total = (long long)n * H * W * Cp;
+  k_nchw_to_padded<<<grid1d(total), 256, 0, (cudaStream_t)stream>>>(x, (act_t *)out_pad, total, C, Cp, H, W);
+  ++g_launch_count;
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+int salun_op_padded_to_nchw(salun_ctx *ctx, const void *in_pad, float *out, int n, int C, int H, int W, void *stream) {
+  SALUN_REQUIRE(ctx && in_pad && out && n > 0, "bad argument");
+  SALUN_CUDA_OK(cudaSetDevice(ctx->device));
+  const long long total = (long long)n * C * H * W;
+  k_padded_to_nchw<<<grid1d(total), 256, 0, (cudaStream_t)stream>>>((const act_t *)in_pad, out, total, C, H, W);
+  ++g_launch_count;
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+int salun_op_rows_to_nchw(salun_ctx *ctx, const float *y, int ld, const float *bias, float *out, int n, int C, int H, int W,
+                          void *stream) {
+  SALUN_REQUIRE(ctx && y && out && n > 0 && C > 0 && ld >= C, "bad argument");
+  SALUN_CUDA_OK(cudaSetDevice(ctx->device));
+  const long long total = (long long)n * C * H * W;
+  k_rows_to_nchw<<<grid1d(total), 256, 0, (cudaStream_t)stream>>>(y, ld, bias, out, total, C, H, W);
+  ++g_launch_count;
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+int salun_op_prep_weight(salun_ctx *ctx, const float *w, void *wop, int cout, int cin, int ks, int cout_pad, int cin_pad,
+                         void *stream) {
+  SALUN_REQUIRE(ctx && w && wop, "NULL argument");
+  SALUN_REQUIRE((ks == 1 || ks == 3) && cout_pad >= cout && cin_pad >= cin && cout_pad % 64 == 0 && (ks * ks * cin_pad) % 64 == 0,
+                "ks in {1,3}; cout_pad % 64 == 0; ks*ks*cin_pad % 64 == 0");
+  SALUN_CUDA_OK(cudaSetDevice(ctx->device));
+  k_prep_weight<<<grid1d((long long)cout_pad * ks * ks * cin_pad), 256, 0, (cudaStream_t)stream>>>(w, (wop_t *)wop, cout, cin, ks,
+                                                                                                cout_pad, cin_pad);
+  ++g_launch_count;
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+
+int salun_op_conv(salun_ctx *ctx, const void *in, int in_flat, const void *wop, const float *bias, const float *rowbias, int rb_ld,
+                  const void *addend, void *out, int out_pad, float *out_f32, int n, int H, int W, int cin, int cout, int ks,
+                  void *stream) {
+  SALUN_REQUIRE(ctx && in && wop && (out || out_f32), "NULL argument");
+  SALUN_REQUIRE(ks == 1 || ks == 3, "ks must be 1 or 3");
+  SALUN_REQUIRE(cin % 64 == 0 && cout % 64 == 0, "cin and cout must be multiples of 64 (pad the weight operand)");
+  SALUN_REQUIRE(!(in_flat && ks != 1), "a flat input is a token matrix: ks must be 1");
+  SALUN_REQUIRE(!(out_f32 && (out_pad || addend)), "the fp32 output is flat and takes no addend");
+  SALUN_CUDA_OK(cudaSetDevice(ctx->device));
+  const long long M = (long long)n * H * W;
+  const int bn = pick_bn_ops(cout, M);
+  CUtensorMap tmA, tmB;
+  int rc;
+  ConvGemmArgs a{};
+  if (in_flat) {
+    if ((rc = make_tmap_2d_act(&tmA, (const act_t *)in, (uint64_t)M, cin, 128))) return rc;
+    a.mode_a = 0;
+    a.num_k_blocks = cin / 64;
+  } else {
+    TmapBox4 bx;
+    if ((rc = conv_box(H, W, 128, &bx))) return rc;
+    if ((rc = make_tmap_4d_act(&tmA, (const act_t *)in, cin, W + 2, H + 2, n, bx))) return rc;
+    a.mode_a = 1;
+    a.cin_blocks = cin / 64;
+    a.num_k_blocks = ks * ks * a.cin_blocks;
+    a.kw = ks;
+    a.tap_y0 = a.tap_x0 = ks == 3 ? 0 : 1;
+    a.H = H;
+    a.W = W;
+  }
+  if ((rc = make_tmap_2d_wop(&tmB, (const wop_t *)wop, cout, (uint64_t)ks * ks * cin, bn))) return rc;
+  a.M = (int)M;
+  a.N = cout;
+  a.fH = H;
+  a.fW = W;
+  a.out_bf16 = (act_t *)out;
+  a.out_f32 = out_f32;
+  a.ld_out = cout;
+  a.out_pad = out_pad;
+  a.bias = bias;
+  a.addend = (const act_t *)addend;
+  if (rowbias) {
+    SALUN_REQUIRE(((long long)H * W & ((long long)H * W - 1)) == 0, "rowbias needs a power-of-two pixel count per sample");
+    a.rowbias = rowbias;
+    a.rb_ld = rb_ld;
+    a.rb_shift = ilog2i((long long)H * W);
+  }
+  return launch_conv_gemm(tmA, tmB, a, bn, (cudaStream_t)stream);
+}
+
+// Downsample (openaimodel.py:131-160: conv 3x3, stride 2, padding 1): patches of the padded input -> GEMM
+int salun_op_conv_s2(salun_ctx *ctx, const void *in_pad, void *col_scratch, const void *wop, const float *bias, void *out_padded,
+                     int n, int Hin, int Win, int cin, int cout, void *stream) {
+  SALUN_REQUIRE(ctx && in_pad && col_scratch && wop && out_padded, "NULL argument");
+  SALUN_REQUIRE(cin % 64 == 0 && cout % 64 == 0 && Hin % 2 == 0 && Win % 2 == 0, "cin, cout % 64 == 0; even image size");
+  SALUN_CUDA_OK(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  launch_im2col_s2((const act_t *)in_pad, (act_t *)col_scratch, n, Hin, Win, cin, 3, st);
+  const int Ho = Hin / 2, Wo = Win / 2;
+  const long long M = (long long)n * Ho * Wo;
+  const int bn = pick_bn_ops(cout, M);
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_tmap_2d_act(&tmA, (const act_t *)col_scratch, (uint64_t)M, 9 * (uint64_t)cin, 128))) return rc;
+  if ((rc = make_tmap_2d_wop(&tmB, (const wop_t *)wop, cout, 9 * (uint64_t)cin, bn))) return rc;
+  ConvGemmArgs a{};
+  a.mode_a = 0;
+  a.num_k_blocks = 9 * cin / 64;
+  a.M = (int)M;
+  a.N = cout;
+  a.fH = Ho;
+  a.fW = Wo;
+  a.out_bf16 = (act_t *)out_padded;
+  a.ld_out = cout;
+  a.out_pad = 1;
+  a.bias = bias;
+  return launch_conv_gemm(tmA, tmB, a, bn, st);
+}
+
+int salun_op_groupnorm(salun_ctx *ctx, const void *in_pad, const float *gamma, const float *beta, float *stats_ws, void *out,
+                       int out_flat, int n, int H, int W, int C, float eps, int swish, void *stream) {
+  SALUN_REQUIRE(ctx && in_pad && gamma && beta && stats_ws && out, "NULL argument");
+  SALUN_REQUIRE(C % 32 == 0 && C % 8 == 0 && n > 0, "C must be a multiple of 32");
+  SALUN_CUDA_OK(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  k_gn2_stats<<<dim3(32, n), 256, 0, st>>>((const act_t *)in_pad, stats_ws, H, W, C, eps);
+  const long long total = (long long)n * H * W * (C >> 3);
+  k_gn2_apply<<<grid1d(total, 256, 148 * 16), 256, 0, st>>>((const act_t *)in_pad, stats_ws, gamma, beta, (act_t *)out, out_flat, swish,
+                                                            total, H, W, C);
+  g_launch_count += 2;
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+
+int salun_op_upsample2(salun_ctx *ctx, const void *in_pad, void *out_pad, int n, int H, int C, void *stream) {
+  SALUN_REQUIRE(ctx && in_pad && out_pad && C % 8 == 0 && (H & (H - 1)) == 0, "square power-of-two images, C % 8 == 0");
+  SALUN_CUDA_OK(cudaSetDevice(ctx->device));
+  launch_upsample2((const act_t *)in_pad, (act_t *)out_pad, n, H, C, (cudaStream_t)stream);
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+int salun_op_concat(salun_ctx *ctx, const void *a_pad, int Ca, const void *b_pad, int Cb, void *out_pad, int n, int H, void *stream) {
+  SALUN_REQUIRE(ctx && a_pad && b_pad && out_pad && Ca % 8 == 0 && Cb % 8 == 0 && (H & (H - 1)) == 0, "bad argument");
+  SALUN_CUDA_OK(cudaSetDevice(ctx->device));
+  launch_concat((const act_t *)a_pad, Ca, (const act_t *)b_pad, Cb, (act_t *)out_pad, n, H, (cudaStream_t)stream);
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+// out[n][N] = act_in(x)[n][K] . w[N][K]^T + b   (fp32, CUDA cores: the embedding MLPs); silu_in: x <- x * sigmoid(x) first (tmp)
+int salun_op_linear_f32(salun_ctx *ctx, const float *x, const float *w, const float *b, float *out, float *tmp, int n, int K, int N,
+                        int silu_in, void *stream) {
+  SALUN_REQUIRE(ctx && x && w && out && (!silu_in || tmp), "NULL argument");
+  SALUN_CUDA_OK(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const float *src = x;
+  if (silu_in) {
+    launch_swish_f32(x, tmp, (long long)n * K, st);
+    src = tmp;
+  }
+  launch_sgemm(src, K, 1, w, 1, K, out, N, n, N, K, b, 0, st);
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+int salun_sd_timestep_embedding(salun_ctx *ctx, const float *t, float *out, int n, int dim, float max_period, void *stream) {
+  SALUN_REQUIRE(ctx && t && out && n > 0 && dim > 1, "bad argument");
+  SALUN_CUDA_OK(cudaSetDevice(ctx->device));
+  k_timestep_embedding<<<grid1d((long long)n * dim), 256, 0, (cudaStream_t)stream>>>(t, out, n, dim, max_period);
+  ++g_launch_count;
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+int salun_sd_layernorm(salun_ctx *ctx, const void *x, const float *gamma, const float *beta, void *out, int64_t rows, int C,
+                       float eps, void *stream) {
+  SALUN_REQUIRE(ctx && x && gamma && beta && out, "NULL argument");
+  SALUN_REQUIRE(C % 8 == 0 && C <= 2048, "C % 8 == 0 and C <= 2048");
+  if (rows == 0) return SALUN_OK;
+  SALUN_CUDA_OK(cudaSetDevice(ctx->device));
+  k_layernorm<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>((const act_t *)x, gamma, beta, (act_t *)out, rows, C, eps);
+  ++g_launch_count;
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+int salun_sd_geglu(salun_ctx *ctx, const void *proj, void *out, int64_t rows, int Ci, void *stream) {
+  SALUN_REQUIRE(ctx && proj && out && Ci % 8 == 0, "bad argument");
+  if (rows == 0) return SALUN_OK;
+  SALUN_CUDA_OK(cudaSetDevice(ctx->device));
+  const long long total = rows * (Ci >> 3);
+  k_geglu<<<grid1d(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>((const act_t *)proj, (act_t *)out, total, Ci);
+  ++g_launch_count;
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+
+// workspace carve-up of salun_sd_attention
+static void attn_sizes(int n, int Tq, int Tk, int heads, int d, int *Tqp, int *Tkp, int *dp, size_t off[6], size_t *total) {
+  *Tqp = (Tq + 127) / 128 * 128;
+  *Tkp = (Tk + 127) / 128 * 128;
+  *dp = (d + 63) / 64 * 64;
+  const size_t G = (size_t)n * heads;
+  size_t o = 0;
+  off[0] = o; o = align_up(o + G * *Tqp * *dp * sizeof(act_t), 1024);                 // Qh  (A operand)
+  off[1] = o; o = align_up(o + G * *Tkp * *dp * kWopK * sizeof(wop_t), 1024);         // Kh  (B operand of S)
+  off[2] = o; o = align_up(o + G * *dp * *Tkp * kWopK * sizeof(wop_t), 1024);         // Vt  (B operand of O)
+  off[3] = o; o = align_up(o + G * *Tqp * (size_t)*Tkp * sizeof(float), 1024);        // S   fp32
+  off[4] = o; o = align_up(o + G * *Tqp * (size_t)*Tkp * sizeof(act_t), 1024);        // P
+  off[5] = o; o = align_up(o + G * *Tqp * *dp * sizeof(act_t), 1024);                 // Oh
+  *total = o;
+}
+int64_t salun_sd_attention_ws_bytes(int n, int Tq, int Tk, int heads, int d) {
+  int a, b, c;
+  size_t off[6], total;
+  attn_sizes(n, Tq, Tk, heads, d, &a, &b, &c, off, &total);
+  return (int64_t)total;
+}
+// out[n*Tq][heads*d] = softmax(q_h k_h^T / sqrt(d)) v_h per (sample, head)   (CrossAttention.forward, attention.py:168-192;
+// q [n*Tq][C], k / v [n*Tk][C], C = heads * d; self-attention: k, v from the same tokens, Tk = Tq)
+int salun_sd_attention(salun_ctx *ctx, void *ws, int64_t ws_bytes, const void *q, const void *k, const void *v, void *out, int n,
+                       int Tq, int Tk, int heads, int d, void *stream) {
+  SALUN_REQUIRE(ctx && ws && q && k && v && out, "NULL argument");
+  SALUN_REQUIRE(n > 0 && Tq > 0 && Tk > 0 && heads > 0 && d > 0 && d % 8 == 0, "bad sizes (d % 8 == 0)");
+  int Tqp, Tkp, dp;
+  size_t off[6], total;
+  attn_sizes(n, Tq, Tk, heads, d, &Tqp, &Tkp, &dp, off, &total);
+  SALUN_REQUIRE((size_t)ws_bytes >= total, "workspace too small (salun_sd_attention_ws_bytes)");
+  SALUN_CUDA_OK(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = heads * d;
+  const long long G = (long long)n * heads;
+  char *w = (char *)ws;
+  act_t *Qh = (act_t *)(w + off[0]);
+  wop_t *Kh = (wop_t *)(w + off[1]), *Vt = (wop_t *)(w + off[2]);
+  float *S = (float *)(w + off[3]);
+  act_t *P = (act_t *)(w + off[4]), *Oh = (act_t *)(w + off[5]);
+  k_heads_pack_q<<<grid1d(G * Tqp * (dp >> 3), 256, 148 * 16), 256, 0, st>>>((const act_t *)q, Qh, G * Tqp * (dp >> 3), Tq, Tqp, C, heads, d, dp);
+  k_heads_pack_k<<<grid1d(G * Tkp * dp, 256, 148 * 16), 256, 0, st>>>((const act_t *)k, Kh, G * Tkp * dp, Tk, Tkp, C, heads, d, dp);
+  k_heads_pack_vt<<<grid1d(G * dp * Tkp, 256, 148 * 16), 256, 0, st>>>((const act_t *)v, Vt, G * dp * Tkp, Tk, Tkp, C, heads, d, dp);
+  g_launch_count += 3;
+  const long long M = G * Tqp;
+  int rc;
+  {  // S = Qh Kh^T per unit
+    const int bn = pick_bn_ops(Tkp, M);
+    CUtensorMap tmA, tmB;
+    if ((rc = make_tmap_2d_act(&tmA, Qh, (uint64_t)M, dp, 128))) return rc;
+    if ((rc = make_tmap_2d_wop(&tmB, Kh, (uint64_t)G * Tkp, dp, bn))) return rc;
+    ConvGemmArgs a{};
+    a.mode_a = 0;
+    a.num_k_blocks = dp / 64;
+    a.M = (int)M;
+    a.N = Tkp;
+    a.out_f32 = S;
+    a.ld_out = Tkp;
+    a.batch_rows_a = Tqp;
+    a.batch_rows_b = Tkp;
+    if ((rc = launch_conv_gemm(tmA, tmB, a, bn, st))) return rc;
+  }
+  k_softmax_rows<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(S, P, M, Tq, Tqp, Tk, Tkp, 1.f / sqrtf((float)d));
+  ++g_launch_count;
+  {  // Oh = P Vt^T per unit
+    const int bn = pick_bn_ops(dp, M);
+    CUtensorMap tmA, tmB;
+    if ((rc = make_tmap_2d_act(&tmA, P, (uint64_t)M, Tkp, 128))) return rc;
+    if ((rc = make_tmap_2d_wop(&tmB, Vt, (uint64_t)G * dp, Tkp, bn))) return rc;
+    ConvGemmArgs a{};
+    a.mode_a = 0;
+    a.num_k_blocks = Tkp / 64;
+    a.M = (int)M;
+    a.N = dp;
+    a.out_bf16 = Oh;
+    a.ld_out = dp;
+    a.batch_rows_a = Tqp;
+    a.batch_rows_b = dp;
+    if ((rc = launch_conv_gemm(tmA, tmB, a, bn, st))) return rc;
+  }
+  const long long tot = (long long)n * Tq * heads * (d >> 3);
+  k_heads_merge<<<grid1d(tot, 256, 148 * 16), 256, 0, st>>>(Oh, (act_t *)out, tot, Tq, Tqp, C, heads, d, dp);
+  ++g_launch_count;
+  SALUN_CUDA_OK(cudaGetLastError());
+  return SALUN_OK;
+}
+
+}  // extern "C"
