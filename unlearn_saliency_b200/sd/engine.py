@@ -183,11 +183,32 @@ class SDUNetEngine:
         self._programs.clear()
         return self
 
+    @torch.no_grad()
+    def update_parameters(self, sd: Dict[str, torch.Tensor]):
+        """In-place refresh after an optimizer step on the caller's module (ESD samples from the model it trains,
+        train-esd.py:262-283): same storage, so captured graphs stay valid; only the given keys are re-prepared."""
+        if not self.params:
+            return self.load_state_dict(sd)
+        touched = []
+        for k, v in sd.items():
+            k = k.split("model.diffusion_model.")[-1]
+            if k not in self.table:
+                raise KeyError(k)
+            self.params[k].copy_(v.detach().reshape(self.table[k]), non_blocking=True)
+            touched.append(k)
+        for k in touched:
+            if k in self._wops:
+                shp = self.table[k]
+                self._prep(k, shp[0], shp[1], shp[2] if len(shp) == 4 else 1)
+        return self
+
     def _prep(self, name: str, cout: int, cin: int, ks: int):
         """tensor-core operand of one Conv2d / Linear weight (zero padded to multiples of 64)"""
         cp, kp = _pad64(cout), _pad64(cin)
         w = self.params[name]
-        buf = torch.empty(cp * ks * ks * kp * self.wop_k, dtype=torch.bfloat16, device=self.device)
+        buf = self._wops.get(name)
+        if buf is None:
+            buf = torch.empty(cp * ks * ks * kp * self.wop_k, dtype=torch.bfloat16, device=self.device)
         check(self._lib.salun_op_prep_weight(self.ctx.handle, _ptr(w), _ptr(buf), cout, cin, ks, cp, kp, _stream(self.device)),
               "salun_op_prep_weight")
         self._wops[name] = buf
