@@ -435,7 +435,13 @@ int salun_op_conv(salun_ctx *ctx, const void *in, int in_flat, const void *wop, 
 /* Downsample: conv 3x3 / stride 2 / padding 1 (openaimodel.py:131-160).  col_scratch: act [n*(Hin/2)*(Win/2)][9*cin] */
 int salun_op_conv_s2(salun_ctx *ctx, const void *in_pad, void *col_scratch, const void *wop, const float *bias, void *out_padded,
                      int n, int Hin, int Win, int cin, int cout, void *stream);
-/* GroupNorm(32, C, eps) (+ SiLU): padded in -> padded or flat out; stats_ws: fp32 [n][32][2]  (util.py:217-224 normalization) */
+/* GroupNorm(32, C, eps) (+ SiLU): padded in -> padded or flat out (util.py:217-224 normalization).  stats_ws: scratch of
+ * salun_op_groupnorm_ws_floats(n) floats, 8-byte aligned (per-(sample, group, pixel-slice) fp64 partial sums) */
+int64_t salun_op_groupnorm_ws_floats(int n);
+/* Optional caller-owned scratch (16-byte aligned; 32 MiB covers SD v1.4 at batch 2) that lets salun_op_conv / salun_op_conv_s2
+ * split the k loop of small-M, deep-K GEMMs over several CTAs per output tile (fp32 partial tiles, fixed-order sum: results
+ * do not depend on the grid).  NULL / 0 = off.  One stream per context at a time while it is set. */
+int salun_op_set_scratch(salun_ctx *ctx, void *scratch, int64_t bytes);
 int salun_op_groupnorm(salun_ctx *ctx, const void *in_pad, const float *gamma, const float *beta, float *stats_ws, void *out,
                        int out_flat, int n, int H, int W, int C, float eps, int swish, void *stream);
 int salun_op_upsample2(salun_ctx *ctx, const void *in_pad, void *out_pad, int n, int H, int C, void *stream);

@@ -70,7 +70,7 @@ def _transformer(P, pre, x, context, heads, depth):
 
 def unet_forward(P, cfg, x, timesteps, context):
     mc, heads, depth = cfg["model_channels"], cfg["num_heads"], cfg.get("transformer_depth", 1)
-    emb = F.linear(timestep_embedding(timesteps, mc), P["time_embed.0.weight"], P["time_embed.0.bias"])
+    emb = F.linear(timestep_embedding(timesteps, mc).to(P["time_embed.0.weight"].dtype), P["time_embed.0.weight"], P["time_embed.0.bias"])
     emb = F.linear(F.silu(emb), P["time_embed.2.weight"], P["time_embed.2.bias"])
 
     def block(prefix, h):

@@ -121,7 +121,7 @@ def test_sd_ops_vs_torch(salun_ctx, precision):
     xp = o.empty(n * (H + 2) * (H + 2) * C)
     assert L.salun_op_nchw_to_padded(h, P(x.cuda()), P(xp), n, C, C, H, H, o.s()) == 0
     gam, bet = torch.randn(C, generator=g).cuda(), torch.randn(C, generator=g).cuda()
-    st = torch.zeros(n * 64, device="cuda")
+    st = torch.zeros(int(L.salun_op_groupnorm_ws_floats(n)), device="cuda")
     yp = o.empty(n * (H + 2) * (H + 2) * C)
     assert L.salun_op_groupnorm(h, P(xp), P(gam), P(bet), P(st), P(yp), 0, n, H, H, C, 1e-5, 1, o.s()) == 0
     back = torch.empty(n, C, H, H, device="cuda")
@@ -154,3 +154,85 @@ def salun_wop(L, h, P, w, cout, cin, ks, o):
     wk = torch.empty(cout * ks * ks * cin * L.salun_wop_k(), dtype=torch.bfloat16, device="cuda")
     assert L.salun_op_prep_weight(h, P(w.cuda().contiguous()), P(wk), cout, cin, ks, cout, cin, o.s()) == 0
     return wk
+
+
+@pytest.mark.parametrize("precision", ["split", "bf16"])
+def test_splitk_convolution_equals_unsplit(salun_ctx, precision):
+    """Small-M / deep-K convolutions (the 8x8 level of the U-Net at batch 2: 10 output tiles for 148 SMs) split the k loop
+    over several CTAs per tile when the context has a scratch; same result as the unsplit launch and as torch."""
+    import ctypes as C
+    from unlearn_saliency_b200 import _lib
+    if precision not in _lib.available_precisions():
+        pytest.skip("build missing")
+    o = Ops(salun_ctx, precision)
+    L, h, P = o.L, salun_ctx.handle, o.p
+    g = torch.Generator().manual_seed(3)
+    for (n, H, cin, cout, ks, flat) in [(2, 8, 1280, 1280, 3, False), (2, 8, 2560, 1280, 1, True), (1, 16, 640, 320, 3, False)]:
+        x = torch.randn(n, cin, H, H, generator=g)
+        w = torch.randn(cout, cin, ks, ks, generator=g) / (ks * ks * cin) ** 0.5
+        b, rb = torch.randn(cout, generator=g).cuda(), torch.randn(n, cout, generator=g).cuda()
+        res = torch.randn(n, cout, H, H, generator=g)
+        wk = salun_wop(L, h, P, w, cout, cin, ks, o)
+        rp = o.empty(n * (H + 2) ** 2 * cout)
+        L.salun_op_nchw_to_padded(h, P(res.cuda()), P(rp), n, cout, cout, H, H, o.s())
+        if flat:
+            xin = o.act(x.permute(0, 2, 3, 1).reshape(n * H * H, cin))
+        else:
+            xin = o.empty(n * (H + 2) ** 2 * cin)
+            L.salun_op_nchw_to_padded(h, P(x.cuda()), P(xin), n, cin, cin, H, H, o.s())
+        outs, launches = [], []
+        for scratch in (False, True):
+            if scratch:
+                salun_ctx._op_scratch = None
+                salun_ctx.ensure_op_scratch()
+            else:
+                assert L.salun_op_set_scratch(h, None, 0) == 0
+            yp = o.empty(n * (H + 2) ** 2 * cout)
+            yf = torch.zeros(n * H * H, cout, device="cuda")
+            l0 = L.salun_launch_count()
+            assert L.salun_op_conv(h, P(xin), int(flat), P(wk), P(b), P(rb), cout, P(rp), P(yp), 1, None, n, H, H, cin, cout, ks,
+                                   o.s()) == 0, L.salun_last_error()
+            assert L.salun_op_conv(h, P(xin), int(flat), P(wk), P(b), P(rb), cout, None, None, 0, P(yf), n, H, H, cin, cout, ks,
+                                   o.s()) == 0, L.salun_last_error()
+            launches.append(L.salun_launch_count() - l0)
+            back = torch.empty(n, cout, H, H, device="cuda")
+            L.salun_op_padded_to_nchw(h, P(yp), P(back), n, cout, H, H, o.s())
+            outs.append((back, yf.clone()))
+        ref32 = F.conv2d(x.cuda(), w.cuda(), b, padding=ks // 2) + rb[:, :, None, None]
+        ref = ref32 + res.cuda()
+        assert launches == [2, 4], launches                       # GEMM | GEMM + split-K epilogue, twice
+        for back, yf in outs:
+            assert _rel(back, ref) < TOL[precision] / 4
+            assert _rel(yf.view(n, H, H, cout).permute(0, 3, 1, 2), ref32) < (5e-3 if precision == "bf16" else 5e-4)  # split: fp32 accumulator truncation over 2880 MMAs
+        assert _rel(outs[1][1], outs[0][1]) < 1e-4                 # fp32 sums in a different order only
+
+
+@pytest.mark.parametrize("precision", ["split", "bf16"])
+def test_flash_attention_many_key_blocks(salun_ctx, precision):
+    """The fused attention kernel (head width <= 64) over several key blocks, with ragged token counts, padded keys in the
+    last block, and scores large enough that the running maximum moves between blocks; also against the unfused chain."""
+    import subprocess, sys
+    from unlearn_saliency_b200 import _lib
+    if precision not in _lib.available_precisions():
+        pytest.skip("build missing")
+    o = Ops(salun_ctx, precision)
+    L, h, P = o.L, salun_ctx.handle, o.p
+    g = torch.Generator().manual_seed(11)
+    tol = {"bf16": 2e-2, "split": 2e-4}[precision]
+    for (n, Tq, Tk, heads, d, qs) in ((1, 1024, 1024, 8, 40, 1.0), (2, 300, 200, 3, 24, 4.0), (1, 4096, 4096, 2, 40, 2.0),
+                                      (2, 129, 77, 8, 64, 1.0), (1, 128, 65, 1, 8, 6.0)):
+        Cc = heads * d
+        q, k, v = (torch.randn(n * T_, Cc, generator=g) for T_ in (Tq, Tk, Tk))
+        q = q * qs
+        nb = int(L.salun_sd_attention_ws_bytes(n, Tq, Tk, heads, d))
+        ws = torch.zeros(nb, dtype=torch.uint8, device="cuda")
+        out = o.empty(n * Tq * Cc)
+        assert L.salun_sd_attention(h, P(ws), nb, P(o.act(q)), P(o.act(k)), P(o.act(v)), P(out), n, Tq, Tk, heads, d, o.s()) == 0
+        torch.cuda.synchronize()
+        sp = lambda z, T_: z.cuda().double().view(n, T_, heads, d).permute(0, 2, 1, 3)
+        ref = torch.softmax(sp(q, Tq) @ sp(k, Tk).transpose(-1, -2) * d ** -0.5, dim=-1) @ sp(v, Tk)
+        ref = ref.permute(0, 2, 1, 3).reshape(n * Tq, Cc).float()
+        got = o.f32(out, n * Tq, Cc)
+        err = _rel(got, ref)
+        print(f"flash attention [{precision}] n={n} Tq={Tq} Tk={Tk} heads={heads} d={d} qscale={qs}: rel err {err:.3e}")
+        assert torch.isfinite(got).all() and err < tol, (n, Tq, Tk, heads, d, err)

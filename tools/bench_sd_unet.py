@@ -57,7 +57,6 @@ def main():
     P = None
     ref = None
     for precision in [p for p in ("bf16", "split") if p in _lib.available_precisions()]:
-        torch.cuda.reset_peak_memory_stats()
         t0 = time.time()
         eng = SDUNetEngine(cfg, latent_size=S, max_batch=n, context_len=L, device=dev, precision=precision)
         if P is None:
@@ -66,6 +65,8 @@ def main():
             torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
             with torch.no_grad():
                 ref = OS.unet_forward(P, cfg, x, t, ctx)
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats()
         eng.load_state_dict(P)
         eps = eng(x, t, ctx)
         torch.cuda.synchronize()

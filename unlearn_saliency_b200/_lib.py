@@ -90,6 +90,8 @@ _SIGNATURES = {
     "salun_sd_layernorm": [_P, _P, _P, _P, _P, _I64, C.c_int, _F, _P],
     "salun_sd_geglu": [_P, _P, _P, _I64, C.c_int, _P],
     "salun_sd_attention_ws_bytes": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int],
+    "salun_op_groupnorm_ws_floats": [C.c_int],
+    "salun_op_set_scratch": [_P, _P, _I64],
     "salun_sd_attention": [_P, _P, _I64, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P],
     "salun_ddim_step": [_P, _P, _P, _P, _P, _P, _P, _F, _F, C.c_int, C.c_int, _P, _P, _P],
     "salun_masked_adam_step": [_P, _P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I64, _P, _P],
@@ -111,7 +113,7 @@ _SIGNATURES = {
 }
 _RESTYPES = {"salun_last_error": C.c_char_p, "salun_launch_count": C.c_longlong, "salun_resnet_param_count": C.c_int64,
              "salun_resnet_bn_channels": C.c_int64, "salun_resnet_syncbn_doubles": C.c_int64,
-             "salun_sd_attention_ws_bytes": C.c_int64}
+             "salun_sd_attention_ws_bytes": C.c_int64, "salun_op_groupnorm_ws_floats": C.c_int64}
 
 
 def exported_symbols():

@@ -76,4 +76,7 @@ struct salun_ctx {
   double *partials;            // [kMaxPartials] reduction partials
   // pinned host mailbox for info read-back
   unsigned long long *mailbox_host;  // [8]
+  // caller-owned scratch of the op-level entry points (salun_op_set_scratch): split-K partial tiles of small-M GEMMs
+  float *op_scratch;
+  long long op_scratch_floats;
 };

@@ -353,8 +353,9 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kStages;
   const uint32_t tfull0 = empty0 + 8 * kStages, tempty0 = tfull0 + 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = m_tiles * n_tiles;
-  constexpr uint32_t kTmemCols = 2 * BN;
+  const int ksplit = a.ksplit > 1 ? a.ksplit : 1;
+  const int total_units = m_tiles * n_tiles * ksplit;  // (tile, k-slice) work units, k-slice fastest
+  constexpr uint32_t kTmemCols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);  // power of two >= two accumulators
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -388,7 +389,8 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       long long w_empty = 0;
       uint32_t it = 0;
       const int hw = a.H * a.W;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        const int tile = unit / ksplit, kz = unit - tile * ksplit;
         const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
         int n0 = 0, y0 = 0;
         if (a.mode_a == 1) {
@@ -396,10 +398,19 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           n0 = pix0 / hw;
           y0 = (pix0 - n0 * hw) / a.W;
         }
+        // k-blocks [kb0, kb1) of this unit (split-K: slice kz of ksplit; otherwise the whole loop)
+        const int kb0 = (int)((long long)a.num_k_blocks * kz / ksplit), kb1 = (int)((long long)a.num_k_blocks * (kz + 1) / ksplit);
+        int ka = (a.k_wrap > 0 && kb0 >= a.k_wrap) ? kb0 - a.k_wrap : kb0;
         int cb = 0, kx = 0, ky = 0;
+        if (a.mode_a == 1 && ka) {
+          cb = ka % a.cin_blocks;
+          const int tap = ka / a.cin_blocks;
+          ky = tap / a.kw;
+          kx = tap - ky * a.kw;
+        }
         const int b_row0 = n_tile * BN + (a.batch_rows_a ? (m_tile * kBM / a.batch_rows_a) * a.batch_rows_b : 0);
-        for (int kb = 0, ka = 0; kb < a.num_k_blocks; ++kb, ++ka, ++it) {
-          if (kb == a.k_wrap) ka = cb = kx = ky = 0;  // split build: second pass over the same activation tile
+        for (int kb = kb0; kb < kb1; ++kb, ++ka, ++it) {
+          if (kb == a.k_wrap && kb != kb0) ka = cb = kx = ky = 0;  // split build: second pass over the same activation tile
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait_t(empty0 + 8 * s, ph ^ 1, w_empty, dbg_on);
@@ -433,12 +444,14 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const uint32_t dhi = umma_desc_hi_sw128(1024), a_lo0 = umma_desc_lo(smem_base, 16);
       long long w_full = 0, w_tempty = 0;
       uint32_t it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++ti) {
         const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
         mbar_wait_t(tempty0 + 8 * acc, aph ^ 1, w_tempty, dbg_on);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < a.num_k_blocks; ++kb, ++it) {
+        const int kz = unit % ksplit;
+        const int kb0 = (int)((long long)a.num_k_blocks * kz / ksplit), kb1 = (int)((long long)a.num_k_blocks * (kz + 1) / ksplit);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait_t(full0 + 8 * s, ph, w_full, dbg_on);
@@ -446,7 +459,7 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           const uint32_t alo = a_lo0 + s * (kStageBytes >> 4), blo = alo + (kABytes >> 4);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k)
-            tc_mma_f16(d_tmem, umma_desc_pack(alo + 2 * k, dhi), umma_desc_pack(blo + 2 * k, dhi), idesc, (kb | k) != 0);
+            tc_mma_f16(d_tmem, umma_desc_pack(alo + 2 * k, dhi), umma_desc_pack(blo + 2 * k, dhi), idesc, ((kb - kb0) | k) != 0);
           tc_commit(empty0 + 8 * s);
         }
         tc_commit(tfull0 + 8 * acc);
@@ -463,8 +476,10 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     uint8_t *stg = smem + kStages * kStageBytes + 256 + (warp - 2) * 4096;  // this warp's 4 KB store-transpose buffer
     long long w_tfull = 0;
     uint32_t ti = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++ti) {
+      const int tile = unit / ksplit, kz = unit - tile * ksplit;
       const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
+      float *const out_f32 = a.out_f32 ? a.out_f32 + (size_t)kz * a.split_stride : nullptr;  // split-K: slab kz of the scratch
       const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
       mbar_wait_t(tfull0 + 8 * acc, aph, w_tfull, dbg_on);
       tc_fence_after();
@@ -534,11 +549,11 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             __syncwarp();
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
-              const int rl = 4 * jj + (lane >> 3), unit = lane & 7;
-              const uint4 v = *reinterpret_cast<const uint4 *>(stg + rl * 128 + ((unit ^ (rl & 7)) << 4));
+              const int rl = 4 * jj + (lane >> 3), u4 = lane & 7;
+              const uint4 v = *reinterpret_cast<const uint4 *>(stg + rl * 128 + ((u4 ^ (rl & 7)) << 4));
               const unsigned long long orow = __shfl_sync(0xffffffffu, (unsigned long long)out_row, rl);
               const int ok = __shfl_sync(0xffffffffu, row_ok ? 1 : 0, rl);
-              if (ok) *reinterpret_cast<uint4 *>(a.out_bf16 + orow + col0 + unit * 4) = v;
+              if (ok) *reinterpret_cast<uint4 *>(a.out_bf16 + orow + col0 + u4 * 4) = v;
             }
             __syncwarp();
           }
@@ -556,16 +571,16 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             __syncwarp();
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
-              const int rl = 8 * jj + (lane >> 2), unit = lane & 3;
-              const uint4 v = *reinterpret_cast<const uint4 *>(stg + rl * 64 + ((unit ^ ((rl >> 1) & 3)) << 4));
+              const int rl = 8 * jj + (lane >> 2), u4 = lane & 3;
+              const uint4 v = *reinterpret_cast<const uint4 *>(stg + rl * 64 + ((u4 ^ ((rl >> 1) & 3)) << 4));
               const unsigned long long orow = __shfl_sync(0xffffffffu, (unsigned long long)out_row, rl);
               const int ok = __shfl_sync(0xffffffffu, row_ok ? 1 : 0, rl);
-              if (ok) *reinterpret_cast<uint4 *>(a.out_bf16 + orow + col0 + unit * 8) = v;
+              if (ok) *reinterpret_cast<uint4 *>(a.out_bf16 + orow + col0 + u4 * 8) = v;
             }
             __syncwarp();
           }
 #endif
-          if (a.out_f32) {
+          if (out_f32) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               *reinterpret_cast<uint4 *>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
@@ -574,10 +589,10 @@ k_conv_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             const int row_base = m_tile * kBM + q * 32;
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
-              const int rl = 4 * jj + (lane >> 3), unit = lane & 7;
-              const uint4 v = *reinterpret_cast<const uint4 *>(stg + rl * 128 + ((unit ^ (rl & 7)) << 4));
+              const int rl = 4 * jj + (lane >> 3), u4 = lane & 7;
+              const uint4 v = *reinterpret_cast<const uint4 *>(stg + rl * 128 + ((u4 ^ (rl & 7)) << 4));
               if (row_base + rl < a.M)
-                *reinterpret_cast<uint4 *>(a.out_f32 + (size_t)(row_base + rl) * a.ld_out + col0 + unit * 4) = v;
+                *reinterpret_cast<uint4 *>(out_f32 + (size_t)(row_base + rl) * a.ld_out + col0 + u4 * 4) = v;
             }
             __syncwarp();
           }
@@ -1317,7 +1332,7 @@ static int launch_conv_gemm_p_t(const CUtensorMap &tmA, const CUtensorMap &tmB, 
     attr_set = true;
   }
   const int m_tiles = (a.M + kBM - 1) / kBM, n_tiles = (a.N + BN - 1) / BN;
-  int grid = m_tiles * n_tiles;
+  int grid = m_tiles * n_tiles * (a.ksplit > 1 ? a.ksplit : 1);
   if (grid > num_sms) grid = num_sms;
   ConvGemmArgs aa = a;
   aa.dbg = g_dbg;
@@ -1409,6 +1424,61 @@ static bool gemm_log() {  // SALUN_GEMM_LOG=1: one stderr line per tensor-core l
   return v == 1;
 }
 
+// Split-K epilogue: D[row][col] = sum_z part[z][row][col] (+ bias + rowbias + addend) -> activation-typed and / or fp32 output,
+// the same terms in the same order as the in-kernel epilogue of k_conv_gemm_p.  One thread per 8 columns of one row.
+__global__ void __launch_bounds__(256) k_splitk_epilogue(const float *__restrict__ part, int ksplit, long long split_stride, int ldp,
+                                                         const ConvGemmArgs a) {
+  const int vecs = (a.N + 7) >> 3;
+  const long long total = (long long)a.M * vecs;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int row = (int)(i / vecs), col0 = (int)(i - (long long)row * vecs) * 8;
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float *p = part + (size_t)row * ldp + col0;
+    for (int z = 0; z < ksplit; ++z, p += split_stride) {
+      const float4 u = *reinterpret_cast<const float4 *>(p), v = *reinterpret_cast<const float4 *>(p + 4);
+      f[0] += u.x; f[1] += u.y; f[2] += u.z; f[3] += u.w;
+      f[4] += v.x; f[5] += v.y; f[6] += v.z; f[7] += v.w;
+    }
+    if (a.bias) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += __ldg(a.bias + col0 + j);
+    }
+    if (a.rowbias) {
+      const float *rb = a.rowbias + (size_t)(row >> a.rb_shift) * a.rb_ld + col0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += __ldg(rb + j);
+    }
+    const size_t out_row = a.out_pad ? pad_row_off(row, a.fH, a.fW, a.ld_out) : (size_t)row * a.ld_out;
+    if (a.addend) {
+      float g[8];
+      ld8(a.addend + out_row + col0, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += g[j];
+    }
+    if (a.out_bf16) st8(a.out_bf16 + out_row + col0, f);
+    if (a.out_f32) {
+      float *o = a.out_f32 + (size_t)row * a.ld_out + col0;
+      *reinterpret_cast<float4 *>(o) = make_float4(f[0], f[1], f[2], f[3]);
+      *reinterpret_cast<float4 *>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    }
+  }
+}
+
+// k-slices per output tile for a launch of `tiles` tiles and `nkb` k-blocks (operand units): fill ~one wave of 148 CTAs,
+// keep >= 4 k-blocks per slice, stay inside the scratch.  1 = do not split.
+static int pick_ksplit(const ConvGemmArgs &a, int bn, int nkb) {
+  if (!a.splitk_ws || a.stat_sum || a.f1.act || a.f2.act || a.pair || (a.N & 7) || (a.ld_out & 7)) return 1;
+  const int m_tiles = (a.M + kBM - 1) / kBM, n_tiles = (a.N + bn - 1) / bn;
+  const long long tiles = (long long)m_tiles * n_tiles;
+  if (tiles > 74 || nkb < 8) return 1;
+  long long ks = 148 / tiles;
+  if (ks > nkb / 4) ks = nkb / 4;
+  if (ks > 32) ks = 32;
+  const long long slab = (long long)m_tiles * kBM * n_tiles * bn;
+  if (ks * slab > a.splitk_ws_floats) ks = a.splitk_ws_floats / slab;
+  return ks < 2 ? 1 : (int)ks;
+}
+
 int launch_conv_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvGemmArgs &a0, int bn, cudaStream_t st) {
   if (gemm_log())
     fprintf(stderr, "GEMMLOG M=%d N=%d K=%d mode=%d bn=%d H=%d batched=%d\n", a0.M, a0.N, a0.num_k_blocks * 64, a0.mode_a, bn, a0.H,
@@ -1419,11 +1489,33 @@ int launch_conv_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvG
   prof_open(0, flops, st);
   int rc;
   if (gemm_persistent()) {
+    const int ks = pick_ksplit(a, bn, a.num_k_blocks);
+    ConvGemmArgs g = a;
+    if (ks > 1) {  // partial tiles to the scratch, everything else of the epilogue in k_splitk_epilogue
+      const int m_tiles = (a.M + kBM - 1) / kBM, n_tiles = (a.N + bn - 1) / bn;
+      g.ksplit = ks;
+      g.split_stride = (long long)m_tiles * kBM * n_tiles * bn;
+      g.out_f32 = a.splitk_ws;
+      g.ld_out = n_tiles * bn;
+      g.out_bf16 = nullptr;
+      g.addend = nullptr;
+      g.bias = g.rowbias = nullptr;
+      g.out_pad = 0;
+    }
     switch (bn) {
-      case 64: rc = launch_conv_gemm_p_t<64, 8>(tmA, tmB, a, st); break;
-      case 128: rc = launch_conv_gemm_p_t<128, 6>(tmA, tmB, a, st); break;
-      case 256: rc = launch_conv_gemm_p_t<256, 4>(tmA, tmB, a, st); break;
+      case 64: rc = launch_conv_gemm_p_t<64, 8>(tmA, tmB, g, st); break;
+      case 128: rc = launch_conv_gemm_p_t<128, 6>(tmA, tmB, g, st); break;
+      case 160: rc = launch_conv_gemm_p_t<160, 5>(tmA, tmB, g, st); break;  // N = 320 (SD level 0): 2 column tiles, not 5 x 64
+      case 256: rc = launch_conv_gemm_p_t<256, 4>(tmA, tmB, g, st); break;
       default: set_error("launch_conv_gemm: unsupported BN=%d", bn); rc = SALUN_ERR_INVALID;
+    }
+    if (ks > 1 && rc == SALUN_OK) {
+      const long long total = (long long)a.M * ((a.N + 7) >> 3);
+      long long blocks = (total + 255) / 256;
+      if (blocks > 148 * 8) blocks = 148 * 8;
+      k_splitk_epilogue<<<(unsigned)blocks, 256, 0, st>>>(a.splitk_ws, ks, g.split_stride, g.ld_out, a);
+      ++::salun::g_launch_count;
+      if (cudaGetLastError() != cudaSuccess) rc = SALUN_ERR_CUDA;
     }
     prof_close(st);
     return rc;

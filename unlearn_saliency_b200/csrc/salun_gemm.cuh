@@ -48,6 +48,12 @@ struct ConvGemmArgs {
                                 //    [n][fH+2][fW+2][ld_out] (row m -> interior pixel), 0: flat [M][ld_out]
   int batch_rows_a, batch_rows_b;  // batched GEMM (one B matrix per group of batch_rows_a rows of A): the B tile of
                                    // output tile (m, n) starts at row (m*128 / batch_rows_a) * batch_rows_b + n*BN.  0 = off
+  float *splitk_ws;                // optional scratch: when the launch has too few output tiles to fill the GPU and K is
+  long long splitk_ws_floats;      //   deep, launch_conv_gemm splits the k loop over several CTAs per tile (fp32 partial tiles
+                                   //   in the scratch, then k_splitk_epilogue adds them in a fixed order and applies bias /
+                                   //   rowbias / addend / the output conversion).  Needs stat_sum == nullptr and no f1/f2.
+  int ksplit;                      // set by launch_conv_gemm (kernel side): k-slices per tile (0/1 = off) ...
+  long long split_stride;          //   ... and the float distance between the partial slabs in out_f32
   int pair;                        // 1: launch_conv_gemm routes to the CTA-pair kernel (k_gemm2, 256 x bn tiles): tmB must
                                    // have been encoded with bn/2 box rows; bn in {128, 256}; batch_rows_a % 256 == 0
 };
@@ -118,6 +124,10 @@ static inline int make_tmap_4d_act(CUtensorMap *m, const act_t *base, uint64_t C
 int conv_box(int H, int W, int pixels, TmapBox4 *box);
 
 int launch_conv_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvGemmArgs &a, int bn, cudaStream_t st);
+// fused attention forward for head widths <= 64 (salun_attn.cu); operands are the packed per-head buffers of salun_sd_attention
+bool flash_attn_supported(int d);
+int launch_flash_attn(const act_t *Qh, const wop_t *Kh, const wop_t *Vt, act_t *out, int n, int Tq, int Tqp, int Tk, int Tkp, int heads,
+                      int d, cudaStream_t st);
 int launch_wgrad(const CUtensorMap &tmA, const CUtensorMap &tmB, const WgradArgs &a, int co_tiles, int col_groups,
                  int splits, cudaStream_t st);
 // CTA-pair (cta_group::2) GEMM, 256 x bn tiles; tmB must be encoded with bn/2 box rows

@@ -99,43 +99,65 @@ __global__ void k_prep_weight(const float *__restrict__ w, wop_t *__restrict__ o
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm (any C % 8 == 0)
-__global__ void __launch_bounds__(256) k_gn2_stats(const act_t *__restrict__ x, float *__restrict__ stats, int H, int W, int C,
-                                                   float eps) {
-  __shared__ double sh[2][256];
-  const int g = blockIdx.x, n = blockIdx.y, cpg = C / 32;
-  const long long cnt = (long long)H * W * cpg;
-  double a = 0.0, b = 0.0;
+// Statistics in two steps so that batch 1-2 still fills the GPU: k_gn2_partial sums a 1/kGnSplits slice of the pixels of one
+// (sample, group) per CTA (32 * n * kGnSplits CTAs; fp32 per thread over a few dozen values, fp64 across threads) and stores
+// (sum, sum of squares) as doubles; k_gn2_apply folds the kGnSplits partials of every (sample, group) into mean / rstd in its
+// prologue (shared memory) and normalises.  Deterministic: fixed partition, fixed summation order, no atomics.
+constexpr int kGnSplits = 16;
+__global__ void __launch_bounds__(256) k_gn2_partial(const act_t *__restrict__ x, double *__restrict__ part, int H, int W, int C) {
+  __shared__ double sh[2][8];
+  const int g = blockIdx.x, n = blockIdx.y, z = blockIdx.z, cpg = C / 32;
+  const long long hw = (long long)H * W;
+  const long long p0 = hw * z / kGnSplits, p1 = hw * (z + 1) / kGnSplits;
+  const long long cnt = (p1 - p0) * cpg;
+  float a = 0.f, b = 0.f;
   for (long long i = threadIdx.x; i < cnt; i += 256) {
     const int c = (int)(i % cpg);
-    const long long p = i / cpg;
+    const long long p = p0 + i / cpg;
     const int xx = (int)(p % W), y = (int)(p / W);
     const float v = act_to_float(x[pad_off4(n, y, xx, H, W, C) + g * cpg + c]);
     a += v;
-    b += (double)v * v;
+    b = fmaf(v, v, b);
   }
-  sh[0][threadIdx.x] = a;
-  sh[1][threadIdx.x] = b;
+  double da = a, db = b;
+  for (int o = 16; o; o >>= 1) {
+    da += __shfl_xor_sync(0xffffffffu, da, o);
+    db += __shfl_xor_sync(0xffffffffu, db, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh[0][threadIdx.x >> 5] = da;
+    sh[1][threadIdx.x >> 5] = db;
+  }
   __syncthreads();
-  for (int o = 128; o; o >>= 1) {
-    if (threadIdx.x < o) {
-      sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
-      sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
-    }
-    __syncthreads();
-  }
   if (threadIdx.x == 0) {
-    const double mean = sh[0][0] / (double)cnt;
-    double var = sh[1][0] / (double)cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    stats[((size_t)n * 32 + g) * 2] = (float)mean;
-    stats[((size_t)n * 32 + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    double s0 = 0.0, s1 = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      s0 += sh[0][w];
+      s1 += sh[1][w];
+    }
+    part[(((size_t)n * 32 + g) * kGnSplits + z) * 2] = s0;
+    part[(((size_t)n * 32 + g) * kGnSplits + z) * 2 + 1] = s1;
   }
 }
-__global__ void __launch_bounds__(256) k_gn2_apply(const act_t *__restrict__ x, const float *__restrict__ stats,
+__global__ void __launch_bounds__(256) k_gn2_apply(const act_t *__restrict__ x, const double *__restrict__ part,
                                                    const float *__restrict__ gamma, const float *__restrict__ beta,
-                                                   act_t *__restrict__ out, int out_flat, int swish, long long total, int H,
-                                                   int W, int C) {
+                                                   act_t *__restrict__ out, int out_flat, int swish, long long total, int n_samples,
+                                                   int H, int W, int C, float eps) {
+  extern __shared__ float2 st[];  // [n_samples * 32] (mean, rstd)
   const int vecs = C >> 3, cpg = C / 32;
+  const double cnt = (double)H * W * cpg;
+  for (int u = threadIdx.x; u < n_samples * 32; u += 256) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int z = 0; z < kGnSplits; ++z) {
+      s0 += part[((size_t)u * kGnSplits + z) * 2];
+      s1 += part[((size_t)u * kGnSplits + z) * 2 + 1];
+    }
+    const double mean = s0 / cnt;
+    double var = s1 / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    st[u] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+  }
+  __syncthreads();
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const int v = (int)(i % vecs);
     long long p = i / vecs;
@@ -147,9 +169,8 @@ __global__ void __launch_bounds__(256) k_gn2_apply(const act_t *__restrict__ x, 
     ld8(x + pad_off4(n, y, xx, H, W, C) + c0, f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int g = (c0 + j) / cpg;
-      const float mean = stats[((size_t)n * 32 + g) * 2], rstd = stats[((size_t)n * 32 + g) * 2 + 1];
-      float yv = (f[j] - mean) * rstd * gamma[c0 + j] + beta[c0 + j];
+      const float2 mr = st[n * 32 + (c0 + j) / cpg];
+      float yv = (f[j] - mr.x) * mr.y * gamma[c0 + j] + beta[c0 + j];
       if (swish) yv = yv / (1.f + expf(-yv));
       f[j] = yv;
     }
@@ -232,6 +253,54 @@ __global__ void k_timestep_embedding(const float *__restrict__ t, float *__restr
       v = j < half ? cosf(arg) : sinf(arg);
     }
     out[i] = v;
+  }
+}
+
+// out[r][j] = sum_k f(x[r][k]) w[j][k] + b[j], f = SiLU or identity: the embedding MLPs (a handful of rows against a wide fp32
+// weight).  One warp per output feature streams its weight row once (float4, coalesced) for up to 8 rows of x at a time.
+__global__ void __launch_bounds__(256) k_linear_rows_f32(const float *__restrict__ x, const float *__restrict__ w,
+                                                         const float *__restrict__ b, float *__restrict__ out, int n, int K, int N,
+                                                         int silu_in) {
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (j >= N) return;
+  const float *wr = w + (size_t)j * K;
+  for (int r0 = 0; r0 < n; r0 += 8) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int nr = min(8, n - r0);
+    if ((K & 3) == 0) {
+      for (int k = lane * 4; k < K; k += 128) {
+        const float4 wv = __ldg(reinterpret_cast<const float4 *>(wr + k));
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          if (r < nr) {
+            float4 xv = __ldg(reinterpret_cast<const float4 *>(x + (size_t)(r0 + r) * K + k));
+            if (silu_in) {
+              xv.x = xv.x / (1.f + expf(-xv.x));
+              xv.y = xv.y / (1.f + expf(-xv.y));
+              xv.z = xv.z / (1.f + expf(-xv.z));
+              xv.w = xv.w / (1.f + expf(-xv.w));
+            }
+            acc[r] = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, fmaf(wv.z, xv.z, fmaf(wv.w, xv.w, acc[r]))));
+          }
+      }
+    } else {
+      for (int k = lane; k < K; k += 32) {
+        const float wv = __ldg(wr + k);
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          if (r < nr) {
+            float xv = __ldg(x + (size_t)(r0 + r) * K + k);
+            if (silu_in) xv = xv / (1.f + expf(-xv));
+            acc[r] = fmaf(wv, xv, acc[r]);
+          }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      float v = acc[r];
+      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && r < nr) out[(size_t)(r0 + r) * N + j] = v + (b ? b[j] : 0.f);
+    }
   }
 }
 
@@ -320,8 +389,16 @@ __global__ void __launch_bounds__(256) k_heads_merge(const act_t *__restrict__ o
 }
 
 static int pick_bn_ops(int N, long long M) {
+  static int forced = -1;  // SALUN_OPS_BN=64|128|160|256: A/B timing of the column-tile width
+  if (forced < 0) {
+    const char *e = getenv("SALUN_OPS_BN");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced) return forced;
   if (N % 256 == 0 && ((M + 127) / 128) * (N / 256) >= 96) return 256;
-  return N % 128 == 0 ? 128 : 64;
+  if (N % 128 == 0) return 128;
+  // N = 320, 960, ...: 160-wide tiles re-read the A tile from L2 N/160 times instead of N/64 times
+  return N % 160 == 0 ? 160 : 64;
 }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -442,6 +519,8 @@ int salun_op_conv(salun_ctx *ctx, const void *in, int in_flat, const void *wop, 
     a.rb_ld = rb_ld;
     a.rb_shift = ilog2i((long long)H * W);
   }
+  a.splitk_ws = ctx->op_scratch;
+  a.splitk_ws_floats = ctx->op_scratch_floats;
   return launch_conv_gemm(tmA, tmB, a, bn, (cudaStream_t)stream);
 }
 
@@ -471,19 +550,34 @@ int salun_op_conv_s2(salun_ctx *ctx, const void *in_pad, void *col_scratch, cons
   a.ld_out = cout;
   a.out_pad = 1;
   a.bias = bias;
+  a.splitk_ws = ctx->op_scratch;
+  a.splitk_ws_floats = ctx->op_scratch_floats;
   return launch_conv_gemm(tmA, tmB, a, bn, st);
 }
 
+// Caller-owned scratch for the split-K path of salun_op_conv / salun_op_conv_s2 (small-M, deep-K GEMMs: the 8x8 and 16x16
+// levels of the U-Net at batch 1-2 have 10-40 output tiles for 148 SMs).  NULL / 0 turns the path off.  The buffer must stay
+// valid, and ops of one context must not run concurrently on several streams, while it is set.
+int salun_op_set_scratch(salun_ctx *ctx, void *scratch, int64_t bytes) {
+  SALUN_REQUIRE(ctx && bytes >= 0 && (scratch || bytes == 0), "bad argument");
+  SALUN_REQUIRE(((uintptr_t)scratch & 15) == 0, "scratch must be 16-byte aligned");
+  ctx->op_scratch = (float *)scratch;
+  ctx->op_scratch_floats = bytes / 4;
+  return SALUN_OK;
+}
+int64_t salun_op_groupnorm_ws_floats(int n) { return (int64_t)n * 32 * kGnSplits * 4; }
 int salun_op_groupnorm(salun_ctx *ctx, const void *in_pad, const float *gamma, const float *beta, float *stats_ws, void *out,
                        int out_flat, int n, int H, int W, int C, float eps, int swish, void *stream) {
   SALUN_REQUIRE(ctx && in_pad && gamma && beta && stats_ws && out, "NULL argument");
-  SALUN_REQUIRE(C % 32 == 0 && C % 8 == 0 && n > 0, "C must be a multiple of 32");
+  SALUN_REQUIRE(C % 32 == 0 && C % 8 == 0 && n > 0 && n <= 1024, "C must be a multiple of 32, n <= 1024");
+  SALUN_REQUIRE(((uintptr_t)stats_ws & 7) == 0, "stats_ws must be 8-byte aligned");
   SALUN_CUDA_OK(cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
-  k_gn2_stats<<<dim3(32, n), 256, 0, st>>>((const act_t *)in_pad, stats_ws, H, W, C, eps);
+  double *part = reinterpret_cast<double *>(stats_ws);
+  k_gn2_partial<<<dim3(32, n, kGnSplits), 256, 0, st>>>((const act_t *)in_pad, part, H, W, C);
   const long long total = (long long)n * H * W * (C >> 3);
-  k_gn2_apply<<<grid1d(total, 256, 148 * 16), 256, 0, st>>>((const act_t *)in_pad, stats_ws, gamma, beta, (act_t *)out, out_flat, swish,
-                                                            total, H, W, C);
+  k_gn2_apply<<<grid1d(total, 256, 148 * 8), 256, (size_t)n * 32 * sizeof(float2), st>>>(
+      (const act_t *)in_pad, part, gamma, beta, (act_t *)out, out_flat, swish, total, n, H, W, C, eps);
   g_launch_count += 2;
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;
@@ -506,15 +600,12 @@ int salun_op_concat(salun_ctx *ctx, const void *a_pad, int Ca, const void *b_pad
 // out[n][N] = act_in(x)[n][K] . w[N][K]^T + b   (fp32, CUDA cores: the embedding MLPs); silu_in: x <- x * sigmoid(x) first (tmp)
 int salun_op_linear_f32(salun_ctx *ctx, const float *x, const float *w, const float *b, float *out, float *tmp, int n, int K, int N,
                         int silu_in, void *stream) {
-  SALUN_REQUIRE(ctx && x && w && out && (!silu_in || tmp), "NULL argument");
+  SALUN_REQUIRE(ctx && x && w && out, "NULL argument");
+  SALUN_REQUIRE(n > 0 && K > 0 && N > 0, "bad sizes");
+  (void)tmp;  // kept in the signature: SiLU is applied on the fly
   SALUN_CUDA_OK(cudaSetDevice(ctx->device));
-  cudaStream_t st = (cudaStream_t)stream;
-  const float *src = x;
-  if (silu_in) {
-    launch_swish_f32(x, tmp, (long long)n * K, st);
-    src = tmp;
-  }
-  launch_sgemm(src, K, 1, w, 1, K, out, N, n, N, K, b, 0, st);
+  k_linear_rows_f32<<<(N + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, w, b, out, n, K, N, silu_in);
+  ++g_launch_count;
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;
 }
@@ -548,6 +639,16 @@ int salun_sd_geglu(salun_ctx *ctx, const void *proj, void *out, int64_t rows, in
   return SALUN_OK;
 }
 
+// head widths <= 64 take the fused kernel (salun_attn.cu: S and P stay in tensor / shared memory); SALUN_FLASH_ATTN=0 forces the
+// unfused product - softmax - product chain (bring-up and A/B timing)
+static bool use_flash_attn(int d) {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SALUN_FLASH_ATTN");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1 && flash_attn_supported(d);
+}
 // workspace carve-up of salun_sd_attention
 static void attn_sizes(int n, int Tq, int Tk, int heads, int d, int *Tqp, int *Tkp, int *dp, size_t off[6], size_t *total) {
   *Tqp = (Tq + 127) / 128 * 128;
@@ -592,6 +693,7 @@ int salun_sd_attention(salun_ctx *ctx, void *ws, int64_t ws_bytes, const void *q
   k_heads_pack_k<<<grid1d(G * Tkp * dp, 256, 148 * 16), 256, 0, st>>>((const act_t *)k, Kh, G * Tkp * dp, Tk, Tkp, C, heads, d, dp);
   k_heads_pack_vt<<<grid1d(G * dp * Tkp, 256, 148 * 16), 256, 0, st>>>((const act_t *)v, Vt, G * dp * Tkp, Tk, Tkp, C, heads, d, dp);
   g_launch_count += 3;
+  if (use_flash_attn(d)) return launch_flash_attn(Qh, Kh, Vt, (act_t *)out, n, Tq, Tqp, Tk, Tkp, heads, d, st);
   const long long M = G * Tqp;
   int rc;
   {  // S = Qh Kh^T per unit

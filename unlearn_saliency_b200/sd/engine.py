@@ -155,6 +155,7 @@ class SDUNetEngine:
         self.act_bytes = int(self._lib.salun_act_bytes())
         self.wop_k = int(self._lib.salun_wop_k())
         self.use_graph = use_graph
+        self.ctx.ensure_op_scratch()
         mc, heads = self.cfg["model_channels"], self.cfg["num_heads"]
         if mc % 64 or self.cfg["context_dim"] % 64 or (mc // heads) % 8:
             raise ValueError("model_channels and context_dim must be multiples of 64, the head width a multiple of 8")
@@ -262,7 +263,7 @@ class SDUNetEngine:
             n, ted, ted, 1, what="time_embed.2")
         ctx_act = buf(self._flat(n * Lc, dc))
         run(L.salun_op_f32_to_act, h, _ptr(c_in), dc, _ptr(ctx_act), dc, n * Lc, dc, what="context")
-        stats = buf(torch.zeros(n * 64, device=dev))
+        stats = buf(torch.zeros(int(L.salun_op_groupnorm_ws_floats(n)), device=dev))
         attn_ws: Dict[tuple, torch.Tensor] = {}   # one attention workspace per (Tq, Tk, d) shape, shared by the layers
         out_ch = lambda layer: layer[2] if layer[0] == "attn" else layer[3]
 

@@ -66,6 +66,14 @@ class SalunContext:
     def handle(self):
         return self._h
 
+    def ensure_op_scratch(self, nbytes: int = 32 << 20):
+        """Context-owned scratch for the split-K path of the op-level convolutions (salun_op_set_scratch); allocated once and
+        kept for the life of the context because captured graphs hold its address."""
+        if getattr(self, "_op_scratch", None) is None:
+            self._op_scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            check(self._lib.salun_op_set_scratch(self._h, C.c_void_p(self._op_scratch.data_ptr()), nbytes), "salun_op_set_scratch")
+        return self._op_scratch
+
     # ---- (i) mask generation tail ------------------------------------------------------
     def saliency_accumulate(self, grads: Sequence[torch.Tensor], accum_flat: torch.Tensor,
                             scale: Optional[torch.Tensor] = None):
