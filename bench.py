@@ -426,6 +426,7 @@ def main():
     ap.add_argument("--no-maskgen", action="store_true")
     ap.add_argument("--no-modes", action="store_true", help="skip the split-precision rerun of both workloads")
     ap.add_argument("--no-torch", action="store_true", help="skip the stock-PyTorch eager denominator")
+    ap.add_argument("--no-sd", action="store_true", help="skip the Stable-Diffusion v1.4 U-Net forward / DDIM sub-line")
     ap.add_argument("--ddpm-steps", type=int, default=20)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -679,6 +680,19 @@ def main():
             torch_eager = {"error": repr(e)}
             print(f"[bench] torch eager arm failed: {e!r}", file=sys.stderr)
 
+    sd_unet = None
+    if single and not args.no_sd:
+        # the 859.5 M-parameter SD U-Net forward on the engine and one 50-step guided DDIM
+        # sample, beside the stock-PyTorch statement of the same network (tools/bench_sd_unet.py; random-init weights)
+        try:
+            torch.cuda.empty_cache()
+            from tools.bench_sd_unet import measure as sd_measure
+            sd_unet = sd_measure(dev, torch_fp32=False, iters=10)
+            torch.cuda.empty_cache()
+        except Exception as e:
+            sd_unet = {"error": repr(e)}
+            print(f"[bench] SD U-Net sub-line failed: {e!r}", file=sys.stderr)
+
     cpu = None
     if single and not args.no_cpu_baseline:
         cb = cpu_baselines(ddpm=bool(ddpm) and "error" not in (ddpm or {}))
@@ -712,6 +726,7 @@ def main():
                     "ms_per_step": ms_e2e},
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "final_loss": final_loss,
             "ddpm": ddpm, "maskgen": maskgen, "modes": modes, "torch_eager": torch_eager, "parity": parity,
+            "sd_unet": sd_unet,
         }
         emit(line)
     if world > 1:

@@ -103,6 +103,7 @@ class _TorchUNet(nn.Module):
     def __init__(self, P, cfg):
         super().__init__()
         self.cfg = cfg
+        self.num_heads = cfg["num_heads"]
         for k, v in P.items():
             m, parts = self, k.split(".")
             for p in parts[:-1]:
@@ -172,3 +173,25 @@ def test_esd_iteration_with_engine_sampler_and_frozen_engine(salun_ctx):
             assert torch.equal(q, P[n]), n
     # the second iteration sampled from the UPDATED weights on both sides: the engine refresh is on the path
     assert any(not torch.equal(q, P[n]) for n, q in mine.model.diffusion_model.named_parameters() if n in sel)
+
+
+def test_train_esd_on_engines_matches_torch_sampling(salun_ctx):
+    """train_esd(engine="split"): engines are built from the modules (config inferred from the parameter shapes), sampling
+    follows the trained weights; losses equal a run whose no-grad passes are the torch restatement."""
+    from unlearn_saliency_b200.sd import train_esd
+    c = CONFIGS["a"]
+    S, L, D = c["latent"], c["ctx_len"], c["cfg"]["context_dim"]
+    P = {k: v.cuda() for k, v in sd_synth_weights(__import__("unlearn_saliency_b200.sd.engine", fromlist=["x"]).sd_unet_param_table(c["cfg"]), seed=7).items()}
+    runs = []
+    for engine in ("split", None):
+        model, frozen = _LDM(P, c["cfg"], L, D).cuda(), _LDM(P, c["cfg"], L, D).cuda()
+        uncond = model.get_learned_conditioning([""])
+        torch_sample = lambda emb, s, code, t: OS.ddim_sample(model.apply_model, emb, uncond, code, 10, s, till_T=t)
+        torch.manual_seed(123)
+        with torch.random.fork_rng(devices=[0]):
+            torch.manual_seed(123)
+            runs.append(train_esd("Van Gogh", "xattn", 3.0, 1.0, 3, 1e-4, None, None, None, None, None, image_size=8 * S,
+                                  ddim_steps=10, models=(frozen, None, model, None), ctx=salun_ctx, engine=engine,
+                                  sample_fn=None if engine else torch_sample))
+    print("train_esd losses: engines", runs[0], "| torch sampling", runs[1])
+    assert all(abs(a - b) <= 3e-3 * abs(b) for a, b in zip(*runs)), runs

@@ -45,8 +45,8 @@ def timed(fn, iters, warmup=3):
     return a.elapsed_time(b) / iters
 
 
-def main():
-    dev = torch.device("cuda:0")
+def measure(dev=None, torch_fp32=True, iters=20):
+    dev = torch.device("cuda:0") if dev is None else dev
     cfg = sd_v1_config()
     n, S, L, D = 2, 64, 77, cfg["context_dim"]
     g = torch.Generator(device=dev).manual_seed(1)
@@ -72,7 +72,7 @@ def main():
         torch.cuda.synchronize()
         build_s = time.time() - t0
         rel = float((eps - ref).norm() / ref.norm())
-        ms = timed(lambda: eng(x, t, ctx), 20)
+        ms = timed(lambda: eng(x, t, ctx), iters)
         sampler = EngineDDIMSampler(eng)
         torch.cuda.synchronize()
         t1 = time.time()
@@ -86,7 +86,7 @@ def main():
         del eng, sampler
         torch.cuda.empty_cache()
     with torch.no_grad():
-        for name, tf32 in (("torch_fp32", False), ("torch_tf32", True)):
+        for name, tf32 in ((("torch_fp32", False),) if torch_fp32 else ()) + (("torch_tf32", True),):
             torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = tf32
             ms = timed(lambda: OS.unet_forward(P, cfg, x, t, ctx), 10)
             e = OS.unet_forward(P, cfg, x, t, ctx)
@@ -102,8 +102,10 @@ def main():
             out["torch_bf16"] = {"forward_ms": round(ms, 3), "rel_err_vs_fp32": float((bf().float() - ref).norm() / ref.norm())}
         except Exception as ex:          # dtype plumbing of the restatement, not a product path
             out["torch_bf16"] = {"error": str(ex)[:120]}
-    print(json.dumps(out))
+    best = min(out[k]["forward_ms"] for k in ("torch_tf32", "torch_bf16") if "forward_ms" in out.get(k, {}))
+    out["speedup_vs_best_torch_eager"] = {p: best / out[p]["forward_ms"] for p in ("bf16", "split") if p in out}
+    return out
 
 
 if __name__ == "__main__":
-    main()
+    print(json.dumps(measure()))

@@ -306,9 +306,9 @@ class Diffusion:
     (data.*, model.*, diffusion.*, training.{batch_size,n_iters,snapshot_freq,log_freq}, optim.*), same files: the
     checkpoint ``<ckpt_folder>/ckpts/ckpt.pth`` ([model_sd with ``module.`` keys, ...]) is read, the mask is written to
     ``results/cifar10/mask/<label>/with_0.5.pt`` (CPU int64 dict, ``module.`` keys) and snapshots go to
-    ``<config.ckpt_dir>/ckpt.pth`` as [model_sd, optim_sd, step].  The U-Net runs on the sm_100a engine; sampling /
-    FID (sample_visualization, :598-619) is outside the hot path and is left to the reference's own sampler on the
-    saved checkpoint (``on_snapshot`` is called with (step, state_dict) for callers who want it inline).
+    ``<config.ckpt_dir>/ckpt.pth`` as [model_sd, optim_sd, step].  The U-Net runs on the sm_100a engine, and so does the
+    DDIM sampling of ``sample_visualization`` / ``visualization`` (:598-619, diffusion/sampler.py); the FID network is
+    outside the path (``on_snapshot`` is called with (step, state_dict) for callers who score snapshots inline).
 
     ``loaders=(remain_loader, forget_loader)`` overrides get_forget_dataset (tests, synthetic data)."""
 

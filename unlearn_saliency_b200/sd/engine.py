@@ -139,6 +139,47 @@ def sd_unet_param_table(cfg: dict) -> "OrderedDict[str, tuple]":
     return _Arch(cfg).table
 
 
+def config_from_state_dict(sd: Dict[str, "torch.Tensor"], num_heads: int = 8) -> dict:
+    """unet_config.params of a UNetModel from its parameter names and shapes (keys may carry the LatentDiffusion prefix
+    `model.diffusion_model.`).  The head count is not visible in the shapes (to_q is C x C for any split): pass it, or use
+    config_from_module.  The result is checked against the full parameter table before it is returned."""
+    shp = {k.split("model.diffusion_model.")[-1]: tuple(v.shape) for k, v in sd.items()}
+    mc, cin = shp["input_blocks.0.0.weight"][:2]
+    mults, attn_res, nrb, ds, level_blocks, i = [], [], None, 1, 0, 1
+    depth, ctx_dim = 1, None
+    while f"input_blocks.{i}.0.in_layers.2.weight" in shp or f"input_blocks.{i}.0.op.weight" in shp:
+        if f"input_blocks.{i}.0.op.weight" in shp:
+            nrb = level_blocks if nrb is None else nrb
+            ds, level_blocks = ds * 2, 0
+        else:
+            mult = shp[f"input_blocks.{i}.0.in_layers.2.weight"][0] // mc
+            if level_blocks == 0:
+                mults.append(mult)
+            level_blocks += 1
+            if f"input_blocks.{i}.1.norm.weight" in shp:
+                if ds not in attn_res:
+                    attn_res.append(ds)
+                pre = f"input_blocks.{i}.1.transformer_blocks."
+                depth = max(depth, 1 + max(int(k[len(pre):].split(".")[0]) for k in shp if k.startswith(pre)))
+                ctx_dim = shp[pre + "0.attn2.to_k.weight"][1]
+        i += 1
+    nrb = level_blocks if nrb is None else nrb
+    if ctx_dim is None:
+        ctx_dim = shp["middle_block.1.transformer_blocks.0.attn2.to_k.weight"][1]
+    cfg = dict(in_channels=cin, out_channels=shp["out.2.weight"][0], model_channels=mc, attention_resolutions=attn_res,
+               num_res_blocks=nrb, channel_mult=mults, num_heads=num_heads, transformer_depth=depth, context_dim=ctx_dim)
+    table = sd_unet_param_table(cfg)
+    if set(table) != set(shp) or any(tuple(table[k]) != shp[k] for k in table):
+        bad = [k for k in table if shp.get(k) != tuple(table[k])][:3] + [k for k in shp if k not in table][:3]
+        raise ValueError(f"state dict is not a UNetModel this engine covers (use_spatial_transformer, conv_resample): {bad}")
+    return cfg
+
+
+def config_from_module(unet) -> dict:
+    """the same from a live UNetModel (openaimodel.py:466-560 keeps num_heads as an attribute)"""
+    return config_from_state_dict(dict(unet.named_parameters()), num_heads=int(getattr(unet, "num_heads", 8)))
+
+
 class SDUNetEngine:
     """eps = UNetModel(x, timesteps, context) without autograd, on libsalun's op-level entry points."""
 
@@ -201,6 +242,8 @@ class SDUNetEngine:
             if k in self._wops:
                 shp = self.table[k]
                 self._prep(k, shp[0], shp[1], shp[2] if len(shp) == 4 else 1)
+            elif ".emb_layers.1." in k:
+                self._stack_emb(k.split(".emb_layers.1.")[0])
         return self
 
     def _prep(self, name: str, cout: int, cin: int, ks: int):
@@ -219,6 +262,23 @@ class SDUNetEngine:
             if not k.endswith(".weight") or len(shp) < 2 or k.startswith("time_embed") or ".emb_layers." in k:
                 continue      # norms and the fp32 embedding MLPs keep their fp32 weights
             self._prep(k, shp[0], shp[1], shp[2] if len(shp) == 4 else 1)
+        # every ResBlock's emb_layers Linear reads the same SiLU(emb): one stacked [sum cout][time_embed_dim] weight, one launch
+        self._emb_off, off = {}, 0
+        for k, shp in self.table.items():
+            if k.endswith(".emb_layers.1.weight"):
+                self._emb_off[k[:-len(".emb_layers.1.weight")]] = (off, shp[0])
+                off += shp[0]
+        self._emb_total = off
+        if getattr(self, "_emb_w", None) is None:
+            self._emb_w = torch.empty(off, self.arch.time_embed_dim, device=self.device)
+            self._emb_b = torch.empty(off, device=self.device)
+        for pre, (o, c) in self._emb_off.items():
+            self._stack_emb(pre)
+
+    def _stack_emb(self, pre: str):
+        o, c = self._emb_off[pre]
+        self._emb_w[o:o + c].copy_(self.params[pre + ".emb_layers.1.weight"])
+        self._emb_b[o:o + c].copy_(self.params[pre + ".emb_layers.1.bias"])
 
     # ---- buffers -----------------------------------------------------------------------------------------------------
     def _act(self, elems: int) -> torch.Tensor:
@@ -261,6 +321,9 @@ class SDUNetEngine:
             mc, ted, 0, what="time_embed.0")
         run(L.salun_op_linear_f32, h, _ptr(temb1), _ptr(P["time_embed.2.weight"]), _ptr(P["time_embed.2.bias"]), _ptr(emb), _ptr(tmp),
             n, ted, ted, 1, what="time_embed.2")
+        emb_all = buf(torch.zeros(n, self._emb_total, device=dev))
+        run(L.salun_op_linear_f32, h, _ptr(emb), _ptr(self._emb_w), _ptr(self._emb_b), _ptr(emb_all), _ptr(tmp), n, ted,
+            self._emb_total, 1, what="emb_layers (all ResBlocks)")
         ctx_act = buf(self._flat(n * Lc, dc))
         run(L.salun_op_f32_to_act, h, _ptr(c_in), dc, _ptr(ctx_act), dc, n * Lc, dc, what="context")
         stats = buf(torch.zeros(int(L.salun_op_groupnorm_ws_floats(n)), device=dev))
@@ -273,7 +336,8 @@ class SDUNetEngine:
             if out_f32 is None:
                 out = buf(self._padded(n, H, cp) if out_pad else self._flat(n * H * H, cp))
             b = _ptr(P[name[:-len(".weight")] + ".bias"]) if bias and cout == cp else None
-            run(L.salun_op_conv, h, _ptr(x), 1 if in_flat else 0, _ptr(W[name]), b, _ptr(rowbias), cout if rowbias is not None else 0,
+            rb, rb_ld = (None, 0) if rowbias is None else rowbias      # (pointer, row stride in floats)
+            run(L.salun_op_conv, h, _ptr(x), 1 if in_flat else 0, _ptr(W[name]), b, rb, rb_ld,
                 _ptr(addend), _ptr(out), 1 if (out_pad and out_f32 is None) else 0, _ptr(out_f32), n, H, H, kp, cp, ks, what=name)
             return out
 
@@ -292,9 +356,7 @@ class SDUNetEngine:
 
         def resblock(x, pre, cin, cout, H):
             """ResBlock._forward (openaimodel.py:268-288), use_scale_shift_norm=False"""
-            eo = buf(torch.zeros(n, cout, device=dev))
-            run(L.salun_op_linear_f32, h, _ptr(emb), _ptr(P[pre + ".emb_layers.1.weight"]), _ptr(P[pre + ".emb_layers.1.bias"]), _ptr(eo),
-                _ptr(tmp), n, ted, cout, 1, what=pre + ".emb_layers")
+            eo = (C.c_void_p(emb_all.data_ptr() + 4 * self._emb_off[pre][0]), self._emb_total)   # this block's emb_layers columns
             a1 = groupnorm(x, pre + ".in_layers.0", cin, H, 1e-5, True)
             h1 = conv(a1, False, pre + ".in_layers.2.weight", cin, cout, 3, H, rowbias=eo)
             a2 = groupnorm(h1, pre + ".out_layers.0", cout, H, 1e-5, True)

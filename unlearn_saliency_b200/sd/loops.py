@@ -69,6 +69,7 @@ class SDTail:
         selected = set(select_parameters(names, train_method))
         if not selected:
             raise ValueError(f"train_method {train_method!r} selects no parameter")
+        self.trained = selected
         combined = None
         if mask is not None or len(selected) != len(names):
             combined = {}
@@ -118,25 +119,47 @@ def _reference_sd_stack(what: str):
         "checkpoints) is not importable here; pass the reference's own objects (models=..., loaders=..., sample_fn=...)")
 
 
+def engine_passes(model, model_orig, tail: "SDTail", precision: str, image_size: int = 512, ddim_steps: int = 50, ctx=None):
+    """The no-grad passes of ESD on the U-Net engine (sd/engine.py + sd/sampler.py): returns (frozen, sample_fn) where
+    `frozen.apply_model` serves e_0 / e_p of model_orig (train-esd.py:295-297) and sample_fn is quick_sample_till_t
+    (:281-283) sampling from `model`'s CURRENT weights -- the trained tensors are pushed into the engine before every call."""
+    from .engine import SDUNetEngine, config_from_module
+    from .sampler import EngineApplyModel, EngineDDIMSampler, make_quick_sample_till_t
+    unet, unet_orig = model.model.diffusion_model, model_orig.model.diffusion_model
+    uncond = model.get_learned_conditioning([""])
+    kw = dict(latent_size=image_size // 8, max_batch=2, context_len=int(uncond.shape[1]), ctx=ctx, precision=precision)
+    sampling = SDUNetEngine(config_from_module(unet), **kw).load_state_dict(dict(unet.named_parameters()))
+    frozen = SDUNetEngine(config_from_module(unet_orig), **kw).load_state_dict(dict(unet_orig.named_parameters()))
+    sampler = EngineDDIMSampler(sampling, alphas_cumprod=getattr(model, "alphas_cumprod", None))
+    sample_fn = make_quick_sample_till_t(sampler, uncond, image_size=image_size, ddim_steps=ddim_steps, module=unet,
+                                         train_keys=sorted(tail.trained))
+    return EngineApplyModel(frozen), sample_fn
+
+
 def train_esd(prompt, train_method, start_guidance, negative_guidance, iterations, lr, config_path, ckpt_path, mask_path,
               diffusers_config_path, devices, seperator=None, image_size=512, ddim_steps=50, *, models=None,
-              sample_fn=None, on_save=None, ctx=None):
-    """train-esd.py:129-343.  models = (model_orig, sampler_orig, model, sampler) from the reference's get_models()."""
+              sample_fn=None, on_save=None, ctx=None, engine: Optional[str] = None):
+    """train-esd.py:129-343.  models = (model_orig, sampler_orig, model, sampler) from the reference's get_models().
+    engine = "bf16" | "split": the DDIM partial sampling and the frozen model's two passes run on the U-Net engine
+    (engine_passes); otherwise sample_fn is the caller's quick_sample_till_t."""
     if prompt == "allartist":
         prompt = "Kelly Mckernan, Thomas Kinkade, Ajin Demi Human, Alena Aenami, Tyler Edlin, Kilian Eng"
     if prompt == "i2p":
         prompt = "hate, harassment, violence, suffering, humiliation, harm, suicide, sexual, nudity, bodily fluids, blood"
     words = [w.strip() for w in prompt.split(seperator)] if seperator is not None else [prompt]
-    if models is None or sample_fn is None:
+    if models is None or (sample_fn is None and engine is None):
         _reference_sd_stack("train_esd")
     model_orig, _sampler_orig, model, _sampler = models
     mask = torch.load(mask_path) if mask_path else None
     tail = SDTail(model, lr=lr, train_method=train_method, mask=mask, ctx=ctx)
+    frozen = model_orig
+    if engine is not None:
+        frozen, sample_fn = engine_passes(model, model_orig, tail, engine, image_size, ddim_steps, ctx=ctx)
     model.train()
     losses = []
     for i in range(iterations):
         word = random.sample(words, 1)[0]
-        loss = esd_iteration(model, model_orig, sample_fn, tail, word, start_guidance, negative_guidance, image_size,
+        loss = esd_iteration(model, frozen, sample_fn, tail, word, start_guidance, negative_guidance, image_size,
                              ddim_steps, devices)
         losses.append(float(loss))
         if on_save is not None and (i + 1) % 500 == 0 and i + 1 != iterations:
