@@ -204,18 +204,19 @@ def test_resnet34_forward_backward(salun_ctx):
     eng.close()
 
 
-@pytest.mark.parametrize("imagenet,size,n", [(True, 64, 6), (False, 32, 5)])
-def test_resnet50_forward_backward(salun_ctx, imagenet, size, n):
+@pytest.mark.parametrize("imagenet,size,n,classes", [(True, 64, 6, 10), (False, 32, 5, 10), (True, 64, 4, 200)])
+def test_resnet50_forward_backward(salun_ctx, imagenet, size, n, classes):
     """resnet50 (Bottleneck, ResNet.py:358) with the ImageNet stem (7x7/2 + max pool, BASELINE config 4 architecture) and
-    with the CIFAR stem: flat-activation runtime (csrc/salun_resnetb.cu), same tolerance model as resnet18."""
+    with the CIFAR stem: flat-activation runtime (csrc/salun_resnetb.cu), same tolerance model as resnet18.  200 classes x
+    2048 features takes the wide-head path (logits / dW / dpooled as fp32 GEMMs + k_ce_rows)."""
     from unlearn_saliency_b200.engine import ResNetEngine
-    eng = ResNetEngine("resnet50", 10, size, max_batch=8, ctx=salun_ctx, imagenet=imagenet)
-    params, buffers = OC.synth_state_bottleneck(10, seed=0, depth=50, imagenet=imagenet)
+    eng = ResNetEngine("resnet50", classes, size, max_batch=8, ctx=salun_ctx, imagenet=imagenet)
+    params, buffers = OC.synth_state_bottleneck(classes, seed=0, depth=50, imagenet=imagenet)
     assert list(params.keys()) == list(eng.table.keys()) and eng.n_params == sum(v.numel() for v in params.values())
     eng.load_state_dict(OC.state_dict_of(params, buffers))
     g = torch.Generator().manual_seed(21)
     x = torch.rand(n, 3, size, size, generator=g)
-    y = torch.randint(0, 10, (n,), generator=g)
+    y = torch.randint(0, classes, (n,), generator=g)
     for train, sign in ((False, -1.0), (True, 1.0)):
         b = {k: v.clone() for k, v in buffers.items()}
         loss_ref, logits_ref, g_ref = OC.bottleneck_loss_and_grads(params, b, x, y, train=train, sign=sign, imagenet=imagenet)

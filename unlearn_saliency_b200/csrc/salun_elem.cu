@@ -952,6 +952,48 @@ void launch_fc_ce(const float *pooled, const float *w, const float *b, const int
   { ::salun::launch_pdl(k_fc_ce, dim3(n_img), dim3(128), K * sizeof(float), st, pooled, w, b, labels, logits, dlogits, loss_per_sample, n_img, C, K,
                                                   sign); ++::salun::g_launch_count; }
 }
+// Wide classifier heads (ImageNet: 1000 x 2048): the logits come from an fp32 GEMM (launch_sgemm), this kernel does the
+// per-sample cross entropy and dL/dlogits of k_fc_ce on them.  One warp per sample, fixed summation order.
+__global__ void __launch_bounds__(256) k_ce_rows(const float *__restrict__ logits, const int64_t *__restrict__ labels,
+                                                 float *__restrict__ dlogits, float *__restrict__ loss_ps, int n_img, int K,
+                                                 float sign) {
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= n_img) return;
+  const float *lg = logits + (size_t)b * K;
+  float mx = -INFINITY;
+  for (int k = lane; k < K; k += 32) mx = fmaxf(mx, lg[k]);
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float se = 0.f;
+  for (int k = lane; k < K; k += 32) se += expf(lg[k] - mx);
+  for (int o = 16; o; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+  int y = (int)labels[b];
+  y = y < 0 ? 0 : (y >= K ? K - 1 : y);
+  if (lane == 0) loss_ps[b] = (logf(se) + mx) - lg[y];
+  const float inv = 1.f / se;
+  for (int k = lane; k < K; k += 32)
+    dlogits[(size_t)b * K + k] = sign * (expf(lg[k] - mx) * inv - (k == y ? 1.f : 0.f)) / (float)n_img;
+}
+void launch_ce_rows(const float *logits, const int64_t *labels, float *dlogits, float *loss_per_sample, int n_img, int K,
+                    float sign, cudaStream_t st) {
+  k_ce_rows<<<(n_img + 7) / 8, 256, 0, st>>>(logits, labels, dlogits, loss_per_sample, n_img, K, sign);
+  ++g_launch_count;
+}
+// gradient of the global average pool: dact[(b*pix + p)][c] = dpooled[b][c] / pix for every pixel p
+__global__ void k_pool_grad_bcast(const float *__restrict__ dpooled, act_t *__restrict__ dact, long long total, int C, int pix) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int c = (int)(i % C);
+    const long long b = i / ((long long)pix * C);
+    dact[i] = act_from_float(dpooled[b * C + c] / (float)pix);
+  }
+}
+void launch_pool_grad_bcast(const float *dpooled, act_t *dact_flat, int n_img, int C, int pix, cudaStream_t st) {
+  const long long total = (long long)n_img * pix * C;
+  long long g = (total + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  k_pool_grad_bcast<<<(int)g, 256, 0, st>>>(dpooled, dact_flat, total, C, pix);
+  ++g_launch_count;
+}
+
 __global__ void k_loss_sum(const float *__restrict__ l, int n, float sign, float *__restrict__ out) {
   pdl_trigger();
   pdl_wait();

@@ -112,6 +112,9 @@ void launch_avgpool(const act_t *act_padded, float *pooled, int n_img, int H, in
 void launch_fc_ce(const float *pooled, const float *w, const float *b, const int64_t *labels, float *logits,
                   float *dlogits, float *loss_per_sample, int n_img, int C, int K, float sign, cudaStream_t st);
 void launch_loss_sum(const float *loss_per_sample, int n_img, float sign, float *loss_out, cudaStream_t st);
+void launch_ce_rows(const float *logits, const int64_t *labels, float *dlogits, float *loss_per_sample, int n_img, int K,
+                    float sign, cudaStream_t st);
+void launch_pool_grad_bcast(const float *dpooled, act_t *dact_flat, int n_img, int C, int pix, cudaStream_t st);
 void launch_fc_bwd(const float *pooled, const float *dlogits, const float *w, float *dw, float *db,
                    act_t *dact_flat, int n_img, int C, int K, int pix, cudaStream_t st);
 

@@ -4,7 +4,7 @@
 // BASELINE.json config 4 (ResNet-50 / ImageNet shape).  Spatial sizes here are 56/28/14/7 (not powers of two), so this
 // path keeps activations FLAT ([n*H*W][C] bf16) and feeds the tcgen05 GEMM kernels in their plain 2-D mode:
 //   1x1 / stride 1 convs (2/3 of the layers, ~half of the FLOPs): A is the activation itself -- no copy at all;
-//   3x3, strided 1x1 and the stem: explicit bf16 patch matrix in a shared scratch buffer (re-built for the wgrad);
+//   3x3, strided 1x1 and the stem: explicit bf16 patch matrix, one buffer per conv (kept for the wgrad);
 //   dgrad of 1x1/s1: one GEMM straight into the input gradient (+ residual addend); others: dcol GEMM + col2im gather.
 // Everything else (BatchNorm kernels, 1-bit ReLU masks, split-K workspace + deterministic reduce, fused masked SGD)
 // is shared with the BasicBlock runtime (salun_resnet.cu).
@@ -16,6 +16,7 @@
 #include "salun_elem.cuh"
 #include "salun_gemm.cuh"
 #include "salun_resnetb.cuh"
+#include "salun_unet_elem.cuh"  // launch_sgemm, launch_colsum_f32
 
 namespace salun {
 
@@ -28,6 +29,8 @@ struct FConv {
   int rs_off, in_act;
   bool direct;  // 1x1 / stride 1: the input activation IS the GEMM operand
   wop_t *w_fwd, *w_dg;
+  act_t *col;  // own patch matrix [n*hout*wout][kcp] of a 3x3 / strided / stem conv: built in the forward pass, read again by
+               // the weight gradient (a shared scratch meant rebuilding all 20 of them per step: 7.6 ms of 40 at batch 256)
   act_t *y, *dy;
   float *stat_sum, *stat_sq, *saved_mean, *saved_invstd, *coef, *bwd_partials, *wg_ws;
   double *slices;
@@ -58,8 +61,8 @@ struct FlatNet {
   uint8_t *pool_argmax;
   int64_t fc_w_off, fc_b_off;
   int feat;
-  float *pooled, *logits, *dlogits, *loss_ps;
-  act_t *scratch_col, *scratch_dcol;
+  float *pooled, *logits, *dlogits, *loss_ps, *dpooled;
+  act_t *scratch_dcol;
   WPrepEntry *wprep_table;
   WgReduceEntry *wgred_table, *wgred_host;
   std::vector<int> wg_splits;
@@ -163,7 +166,7 @@ static int fmalloc(FlatNet *net, T **p, size_t count, bool zero) {
   return SALUN_OK;
 }
 
-static const act_t *conv_operand(FlatNet *net, const FConv &L) { return L.direct ? net->acts[L.in_act].p : net->scratch_col; }
+static const act_t *conv_operand(FlatNet *net, const FConv &L) { return L.direct ? net->acts[L.in_act].p : L.col; }
 
 static int fplan(FlatNet *net, int n, std::vector<FMaps> **out) {
   auto it = net->plans.find(n);
@@ -196,10 +199,10 @@ static void build_col(FlatNet *net, const FConv &L, const float *x, int n, cudaS
   const salun_resnet_cfg &c = net->cfg;
   if (L.stem) {
     const float inv_std[3] = {1.f / c.std[0], 1.f / c.std[1], 1.f / c.std[2]};
-    launch_stem_im2col_generic(x, net->scratch_col, n, L.hin, L.win, L.ks, L.stride, L.pad, L.hout, L.wout, L.kcp, c.mean,
+    launch_stem_im2col_generic(x, L.col, n, L.hin, L.win, L.ks, L.stride, L.pad, L.hout, L.wout, L.kcp, c.mean,
                                inv_std, st);
   } else {
-    launch_im2col_flat(net->acts[L.in_act].p, net->scratch_col, n, L.hin, L.win, L.cin, L.ks, L.stride, L.pad, L.hout,
+    launch_im2col_flat(net->acts[L.in_act].p, L.col, n, L.hin, L.win, L.cin, L.ks, L.stride, L.pad, L.hout,
                        L.wout, st);
   }
 }
@@ -223,6 +226,9 @@ static int fconv_forward(FlatNet *net, int ci, const FMaps &m, const float *x, i
   if (train) launch_bn_stats_reduce(L.stat_sum, L.stat_sq, (M + 127) / 128 * 4, L.cout, L.slices, st);
   return SALUN_OK;
 }
+
+// the one-CTA-per-sample head kernels re-read the whole weight per sample: fine for 10 x 2048, 2.7 ms for 1000 x 2048 at batch 256
+static bool wide_head(const FlatNet *net) { return (int64_t)net->cfg.num_classes * net->feat >= (1 << 18); }
 
 static BnFwd fbn_of(FlatNet *net, const FConv &L) {
   BnFwd b{};
@@ -270,8 +276,15 @@ static int fforward(FlatNet *net, const float *x, const int64_t *labels, int n, 
   }
   const FAct &last = net->acts[net->blocks.back().out_act];
   launch_avgpool_flat(last.p, net->pooled, n, last.H * last.W, last.C, st);
-  launch_fc_ce(net->pooled, net->params + net->fc_w_off, net->params + net->fc_b_off, labels,
-               logits_out ? logits_out : net->logits, net->dlogits, net->loss_ps, n, net->feat, c.num_classes, sign, st);
+  if (wide_head(net)) {  // logits[n][K] = pooled[n][C] . W[K][C]^T + b as an fp32 GEMM, then the per-sample cross entropy
+    float *lg = logits_out ? logits_out : net->logits;
+    launch_sgemm(net->pooled, net->feat, 1, net->params + net->fc_w_off, 1, net->feat, lg, c.num_classes, n, c.num_classes,
+                 net->feat, net->params + net->fc_b_off, 0, st);
+    if (labels) launch_ce_rows(lg, labels, net->dlogits, net->loss_ps, n, c.num_classes, sign, st);
+  } else {
+    launch_fc_ce(net->pooled, net->params + net->fc_w_off, net->params + net->fc_b_off, labels,
+                 logits_out ? logits_out : net->logits, net->dlogits, net->loss_ps, n, net->feat, c.num_classes, sign, st);
+  }
   if (labels && loss_dev) launch_loss_sum(net->loss_ps, n, sign, loss_dev, st);
   SALUN_CUDA_OK(cudaGetLastError());
   net->last_n = n;
@@ -293,7 +306,7 @@ static void fbn_backward(FlatNet *net, const FConv &L, const act_t *dout, const 
 static int fwgrad(FlatNet *net, int ci, const FMaps &m, const float *x, int n, cudaStream_t st) {
   const FConv &L = net->convs[ci];
   const int64_t M = (int64_t)n * L.hout * L.wout;
-  build_col(net, L, x, n, st);  // the patch matrix of the forward pass was overwritten by later layers: rebuild it
+  (void)x;  // the patch matrix of the forward pass is still in L.col
   WgradArgs a{};
   a.mode_a = 0;
   a.mode_b = 0;
@@ -351,8 +364,17 @@ static int fbackward(FlatNet *net, const float *x, cudaStream_t st) {
   std::vector<FMaps> *plan;
   TRY(fplan(net, n, &plan));
   const FAct &last = net->acts[net->blocks.back().out_act];
-  launch_fc_bwd(net->pooled, net->dlogits, net->params + net->fc_w_off, net->grads + net->fc_w_off,
-                net->grads + net->fc_b_off, last.dout, n, net->feat, net->cfg.num_classes, last.H * last.W, st);
+  if (wide_head(net)) {
+    const int K = net->cfg.num_classes, C = net->feat;
+    // dW[K][C] = dlogits^T . pooled ; db = column sums of dlogits ; dpooled[n][C] = dlogits . W   (fp32 GEMMs, fixed order)
+    launch_sgemm(net->dlogits, 1, K, net->pooled, C, 1, net->grads + net->fc_w_off, C, K, C, n, nullptr, 0, st);
+    launch_colsum_f32(net->dlogits, K, n, K, net->grads + net->fc_b_off, st);
+    launch_sgemm(net->dlogits, K, 1, net->params + net->fc_w_off, C, 1, net->dpooled, C, n, C, K, nullptr, 0, st);
+    launch_pool_grad_bcast(net->dpooled, last.dout, n, C, last.H * last.W, st);
+  } else {
+    launch_fc_bwd(net->pooled, net->dlogits, net->params + net->fc_w_off, net->grads + net->fc_w_off,
+                  net->grads + net->fc_b_off, last.dout, n, net->feat, net->cfg.num_classes, last.H * last.W, st);
+  }
   for (int bi = (int)net->blocks.size() - 1; bi >= 0; --bi) {
     const FBlock &B = net->blocks[bi];
     FAct &in = net->acts[B.in_act], &m1 = net->acts[B.mid1], &m2 = net->acts[B.mid2], &out = net->acts[B.out_act];
@@ -449,7 +471,7 @@ int flatnet_create(salun_ctx *ctx, const salun_resnet_cfg *cfg, float *params, f
     const FAct &p = net->acts[net->pool_act];
     A(fmalloc(net, &net->pool_argmax, (size_t)nb * p.H * p.W * p.C, true));
   }
-  size_t col_max = 0, dcol_max = 0;
+  size_t dcol_max = 0;
   for (FConv &L : net->convs) {
     const size_t Mo = (size_t)nb * L.hout * L.wout;
     A(fmalloc(net, &L.w_fwd, (size_t)L.cout * L.kcp * kWopK, true));
@@ -457,7 +479,7 @@ int flatnet_create(salun_ctx *ctx, const salun_resnet_cfg *cfg, float *params, f
     A(fmalloc(net, &L.y, Mo * L.cout, false));
     A(fmalloc(net, &L.dy, Mo * L.cout, false));
     if (!L.direct) {
-      if (Mo * L.kcp > col_max) col_max = Mo * L.kcp;
+      A(fmalloc(net, &L.col, Mo * L.kcp + 64, true));
       if (!L.stem && Mo * L.kc > dcol_max) dcol_max = Mo * L.kc;
     }
     const size_t rows = (Mo + 127) / 128 * 4;
@@ -474,7 +496,6 @@ int flatnet_create(salun_ctx *ctx, const salun_resnet_cfg *cfg, float *params, f
     if (L.wg_splits_max < 1) L.wg_splits_max = 1;
     A(fmalloc(net, &L.wg_ws, (size_t)L.wg_splits_max * wgrad_ws_elems(L.cout, L.kc), false));
   }
-  A(fmalloc(net, &net->scratch_col, col_max + 64, true));
   A(fmalloc(net, &net->scratch_dcol, dcol_max + 64, true));
   {
     std::vector<WPrepEntry> tab;
@@ -508,6 +529,7 @@ int flatnet_create(salun_ctx *ctx, const salun_resnet_cfg *cfg, float *params, f
   A(fmalloc(net, &net->logits, (size_t)nb * cfg->num_classes, true));
   A(fmalloc(net, &net->dlogits, (size_t)nb * cfg->num_classes, true));
   A(fmalloc(net, &net->loss_ps, (size_t)nb, true));
+  A(fmalloc(net, &net->dpooled, (size_t)nb * net->feat, true));
 #undef A
   *out = net;
   return SALUN_OK;
