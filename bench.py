@@ -512,7 +512,8 @@ def main():
 
     def graphed(engine, optimizer, batch, lib):
         """(GraphedStep | None, launches per replay): the ~175 dependent launches of a step are launch-latency bound"""
-        if world != 1 or os.environ.get("SALUN_GRAPH", "1") == "0":
+        # N > 1: only with the fused DP optimizer (its barriers and exchange kernel are captured); NCCL all-reduce stays eager
+        if (world != 1 and not fused_dp) or os.environ.get("SALUN_GRAPH", "1") == "0":
             return None, 0
         try:
             from unlearn_saliency_b200.engine import GraphedStep

@@ -43,6 +43,13 @@ def test_fused_dp_masked_sgd_two_ranks():
     assert "replicas identical: True" in out and "masked-out exact: True" in out
 
 
+def test_graphed_dp_step_equals_eager_two_ranks():
+    """dp_graph_worker.py: the whole data-parallel step, symmetric-memory barriers and the fused exchange kernel included,
+    replayed from a CUDA graph"""
+    out = _run("dp_graph_worker.py")
+    assert "graphed DP step equals eager: True" in out and "replicas identical: True" in out
+
+
 def test_sync_bn_sharded_step_equals_full_batch_step():
     """dp_syncbn_worker.py: sync-BN over NVLink peer memory -- a batch sharded over 2 ranks reproduces the single-process
     step of the concatenated batch (weights, running statistics); per-shard statistics do not"""

@@ -359,7 +359,9 @@ class GraphedStep:
     batch size and replayed: the ~175 dependent 3-35 us launches of a ResNet-18 step are launch-latency bound, and a graph
     replay removes the per-launch host cost and most of the inter-kernel gaps.  Inputs are copied into static buffers;
     the engine's wgrad side stream is captured through its fork / join events.  The two warm-up steps needed before
-    capture run on a snapshot: parameters, momentum and BatchNorm buffers are restored afterwards."""
+    capture run on a snapshot: parameters, momentum and BatchNorm buffers are restored afterwards.
+    With a DistMaskedSGD optimizer the two symmetric-memory barriers and the fused reduce-scatter + SGD + all-gather kernel
+    are part of the graph (every rank must construct and replay it the same number of times: the barriers pair up)."""
 
     def __init__(self, engine: "ResNetEngine", opt, batch: int, loss_sign: float = 1.0, train: Optional[bool] = None):
         self.engine, self.opt = engine, opt
@@ -369,6 +371,8 @@ class GraphedStep:
         self.train = engine.training if train is None else train
         snap = [t.clone() for t in (engine.params, engine.running_mean, engine.running_var)]
         mom = getattr(opt, "momentum_buffer", None)
+        if mom is None:
+            mom = getattr(opt, "momentum_shard", None)     # DistMaskedSGD: this rank's shard of the momentum
         mom_snap = mom.clone() if mom is not None else None
         nbt = engine.num_batches_tracked
         cur = torch.cuda.current_stream(dev)
