@@ -101,6 +101,15 @@ typedef struct salun_topk_info {
 int salun_topk_mask(salun_ctx *ctx, const float *accum, int64_t n, int64_t k, int64_t *mask_i64,
                     uint32_t *mask_bits, salun_topk_info *info_host, void *stream);
 
+/* The reference's sweep over threshold_list = [0.1 .. 1.0] (generate_mask.py:50-82) as ONE call: the three histogram passes,
+ * the tie count and the mask write read `accum` once for all n_ratios <= 16 ratios.  ks_host[r] = int(n * ratio_r);
+ * mask_i64_host / mask_bits_host: HOST arrays of n_ratios device pointers (either array, or single entries, may be NULL as
+ * long as every ratio has an output); infos_host: optional HOST array of n_ratios structs (synchronises `stream`).
+ * Output r is bit-identical to salun_topk_mask(accum, n, ks_host[r], ...). */
+int salun_topk_mask_multi(salun_ctx *ctx, const float *accum, int64_t n, const int64_t *ks_host, int n_ratios,
+                          int64_t *const *mask_i64_host, uint32_t *const *mask_bits_host, salun_topk_info *infos_host,
+                          void *stream);
+
 /* int64 {0,1} <-> packed bits (loading / saving the reference's on-disk mask) */
 int salun_pack_mask(salun_ctx *ctx, const int64_t *mask_i64, int64_t n, uint32_t *mask_bits,
                     void *stream);

@@ -88,6 +88,35 @@ def test_topk_ties_flat_order(salun_ctx):
     assert np.array_equal(m64.cpu().numpy(), O.topk_mask_argsort(small, 700))
 
 
+@pytest.mark.parametrize("n", [1, 37, 4097, 300000, 11173962])
+def test_topk_mask_multi_equals_single_and_oracle(salun_ctx, n):
+    """salun_topk_mask_multi (one sweep for the reference's whole threshold_list) against the C oracle and against the
+    single-ratio entry point: bit-identical masks, bits and info, including k = 0, k = n, huge tie classes and NaN / inf."""
+    rng = np.random.default_rng(n)
+    for kind in ("saliency", "ties"):
+        g = _saliency_like(rng, n) if kind == "saliency" else rng.integers(0, 4, n).astype(np.float32)
+        if n > 50 and kind == "saliency":
+            g[5], g[7], g[9] = np.nan, np.inf, -np.inf
+        ks = [int(n * r) for r in (0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0)] + [0, max(0, n - 5), 1]
+        d = _dev(g)
+        m64s, bitss, infos = salun_ctx.topk_mask_multi(d, ks, want_info=True)
+        for k, m64, bits, info in zip(ks, m64s, bitss, infos):
+            om, ob, thr, ngt, neq = O.topk_mask(np.abs(g), k)
+            assert np.array_equal(m64.cpu().numpy(), om), (n, kind, k)
+            assert np.array_equal(bits.cpu().numpy().view(np.uint32), ob), (n, kind, k)
+            if 0 < k < n:
+                assert (info.thr_key, info.n_greater, info.n_equal) == (thr, ngt, neq), (n, kind, k)
+                s64, sbits, sinfo = salun_ctx.topk_mask(d, k, want_info=True)
+                assert torch.equal(s64, m64) and torch.equal(sbits, bits)
+                assert (sinfo.thr_key, sinfo.thr_value, sinfo.n_greater, sinfo.n_equal) == \
+                       (info.thr_key, info.thr_value, info.n_greater, info.n_equal)
+    # bits only / int64 only
+    m64s, bitss, _ = salun_ctx.topk_mask_multi(d, ks[:3], want_i64=False)
+    assert m64s is None and len(bitss) == 3
+    with pytest.raises(ValueError):
+        salun_ctx.topk_mask_multi(d, list(range(17)))
+
+
 def test_pack_unpack(salun_ctx):
     rng = np.random.default_rng(3)
     for n in [1, 31, 32, 33, 100003]:

@@ -56,6 +56,8 @@ _SIGNATURES = {
     "salun_saliency_accumulate_flat": [_P, _P, _P, _I64, _P, _P],
     "salun_abs_inplace": [_P, _P, _I64, _P],
     "salun_topk_mask": [_P, _P, _I64, _I64, _P, _P, C.POINTER(salun_topk_info), _P],
+    "salun_topk_mask_multi": [_P, _P, _I64, C.POINTER(C.c_int64), C.c_int, C.POINTER(_P), C.POINTER(_P),
+                              C.POINTER(salun_topk_info), _P],
     "salun_pack_mask": [_P, _P, _I64, _P, _P],
     "salun_unpack_mask": [_P, _P, _I64, _P, _P],
     "salun_apply_mask": [_P, _P, _P, _I64, _P],

@@ -57,6 +57,24 @@ def masks_for_ratio(engine, absg_torch_order: torch.Tensor, ratio: float):
     return hard_dict, bits, info
 
 
+def masks_for_ratios(engine, absg_torch_order: torch.Tensor, ratios):
+    """generate_mask.py:50-80 for the whole threshold_list in ONE select sweep (salun_topk_mask_multi): the saliencies are
+    read once per radix pass for all ratios.  Returns [(hard_dict, packed bits, info)] in the order of `ratios`."""
+    n = absg_torch_order.numel()
+    m64s, bitss, infos = engine.ctx.topk_mask_multi(absg_torch_order, [topk_count(n, r) for r in ratios], want_info=True)
+    out = []
+    for m64, bits, info in zip(m64s, bitss, infos):
+        hard_dict, off = {}, 0
+        for name, shp in engine.table.items():
+            cnt = 1
+            for s in shp:
+                cnt *= s
+            hard_dict[name] = m64[off: off + cnt].reshape(shp)
+            off += cnt
+        out.append((hard_dict, bits, info))
+    return out
+
+
 def save_gradient_ratio(data_loaders, model, criterion, args):
     check_criterion(criterion)
     # the saliency pass decides an index set: it runs on the split-precision build (fp32-class products: 50 % mask
@@ -68,9 +86,8 @@ def save_gradient_ratio(data_loaders, model, criterion, args):
     flat = engine.from_native_flat(acc).contiguous()  # named_parameters order & PyTorch layout, as cat(flatten) :57
     os.makedirs(args.save_dir, exist_ok=True)
     infos = {}
-    saver = default_saver()   # the ten 89 MB files are pickled / written on a worker thread while the next select runs
-    for r in THRESHOLD_LIST:
-        hard_dict, bits, info = masks_for_ratio(engine, flat, r)
+    saver = default_saver()   # the ten 89 MB files are pickled / written on a worker thread
+    for r, (hard_dict, bits, info) in zip(THRESHOLD_LIST, masks_for_ratios(engine, flat, THRESHOLD_LIST)):
         infos[r] = info
         if rank == 0:
             path = os.path.join(args.save_dir, "with_{}.pt".format(r))

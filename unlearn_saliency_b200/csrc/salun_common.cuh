@@ -62,6 +62,7 @@ inline cudaError_t launch_pdl(void (*kernel)(Exp...), dim3 grid, dim3 block, siz
 extern long long g_launch_count;  // kernels launched by this library (bench.py reports it as gpu_launches)
 
 constexpr int kRadixBins = 2048;      // 11-bit digits: 3 passes over a 32-bit key
+constexpr int kMaxRatios = 16;        // ratios one salun_topk_mask_multi call can serve (the reference sweeps ten)
 constexpr int kMaxPartials = 148 * 8; // one partial per CTA of the persistent reduction grids
 
 }  // namespace salun
@@ -76,6 +77,11 @@ struct salun_ctx {
   double *partials;            // [kMaxPartials] reduction partials
   // pinned host mailbox for info read-back
   unsigned long long *mailbox_host;  // [8]
+  // multi-ratio select workspace (salun_topk_mask_multi), allocated on first use
+  unsigned long long *msel;          // [kMaxRatios][8]
+  unsigned int *mhist;               // [kMaxRatios][kRadixBins]
+  unsigned int *mties;               // [kMaxRatios][kMaxPartials + 1]
+  unsigned long long *mmailbox_host; // [kMaxRatios][8] pinned
   // caller-owned scratch of the op-level entry points (salun_op_set_scratch): split-K partial tiles of small-M GEMMs
   float *op_scratch;
   long long op_scratch_floats;

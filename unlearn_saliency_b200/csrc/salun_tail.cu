@@ -152,9 +152,8 @@ __global__ void __launch_bounds__(kThreads) k_radix_hist(const float *__restrict
 }
 
 // one warp: walk the histogram from the top digit, pick the digit holding rank `remaining`
-__global__ void k_radix_pick(unsigned int *__restrict__ hist, unsigned long long *__restrict__ sel, int pass,
-                             long long k) {
-  const int lane = threadIdx.x;
+__device__ __forceinline__ void radix_pick_warp(const unsigned int *__restrict__ hist, unsigned long long *__restrict__ sel,
+                                                int pass, long long k, int lane) {
   const int bins = pass_bins(pass);
   const int per = bins / 32;
   const unsigned long long remaining = sel[2], prefix_in = sel[0], pmask_in = sel[1];  // read before any lane writes
@@ -169,6 +168,7 @@ __global__ void k_radix_pick(unsigned int *__restrict__ hist, unsigned long long
   }
   unsigned long long excl = incl - mine;
   const bool owner = remaining > excl && remaining <= incl;
+  __syncwarp();
   if (owner) {
     unsigned long long r = remaining - excl;
     int d = top;
@@ -192,6 +192,11 @@ __global__ void k_radix_pick(unsigned int *__restrict__ hist, unsigned long long
     }
   }
   __syncwarp();
+}
+__global__ void k_radix_pick(unsigned int *__restrict__ hist, unsigned long long *__restrict__ sel, int pass,
+                             long long k) {
+  const int lane = threadIdx.x;
+  radix_pick_warp(hist, sel, pass, k, lane);
   for (int i = lane; i < kRadixBins; i += 32) hist[i] = 0;  // ready for the next pass
 }
 
@@ -321,6 +326,240 @@ __global__ void __launch_bounds__(kThreads) k_write_mask(const float *__restrict
       w |= __shfl_xor_sync(0xffffffffu, w, 2);
       w |= __shfl_xor_sync(0xffffffffu, w, 4);
       if ((lane & 7) == 0 && i < hi && i < n) mask_bits[i >> 5] = w;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Several ratios in one sweep (the reference's threshold_list = 0.1 .. 1.0, generate_mask.py:50-82): the three histogram
+// passes, the tie count and the mask write read the saliencies ONCE for all ratios instead of once per ratio, and the
+// ~10 launches per ratio become ~12 per call.  Same selection rule as salun_topk_mask, ratio by ratio (same threshold
+// key, same flat-order tie resolution): the outputs are bit-identical to R single calls.
+// ------------------------------------------------------------------------------------------
+struct MultiK {
+  long long k[kMaxRatios];
+  int mode[kMaxRatios];  // 0: select k of n, 1: all ones (k >= n), 2: all zeros (k == 0)
+  int R;
+};
+struct MultiOut {
+  long long *m64[kMaxRatios];
+  uint32_t *bits[kMaxRatios];
+  int vec64[kMaxRatios];
+};
+
+__global__ void k_msel_init(unsigned long long *msel, unsigned int *mhist, MultiK mk) {
+  const int t = threadIdx.x + blockIdx.x * blockDim.x, nt = gridDim.x * blockDim.x;
+  if (t < mk.R * 8) msel[t] = (t & 7) == 2 ? (unsigned long long)mk.k[t >> 3] : 0ull;
+  for (int i = t; i < kMaxRatios * kRadixBins; i += nt) mhist[i] = 0;
+}
+
+// PASS 0: one histogram of the top digit for everybody.  PASS 1 / 2: one histogram per ratio of the next digit of the
+// elements under that ratio's prefix; `which[top digit]` = bit set of the ratios whose prefix starts with that digit
+template <int PASS>
+__global__ void __launch_bounds__(kThreads) k_mhist(const float *__restrict__ a, int64_t n,
+                                                    const unsigned long long *__restrict__ msel,
+                                                    unsigned int *__restrict__ mhist, MultiK mk) {
+  extern __shared__ unsigned int msm[];
+  const int Rh = PASS == 0 ? 1 : mk.R;
+  unsigned int *sh = msm, *which = msm + Rh * kRadixBins, *pref = which + kRadixBins;
+  for (int i = threadIdx.x; i < Rh * kRadixBins; i += kThreads) sh[i] = 0;
+  if (PASS > 0) {
+    for (int i = threadIdx.x; i < kRadixBins; i += kThreads) which[i] = 0;
+    __syncthreads();
+    if (threadIdx.x < mk.R && mk.mode[threadIdx.x] == 0) {
+      const uint32_t p = (uint32_t)msel[threadIdx.x * 8];
+      pref[threadIdx.x] = p;
+      atomicOr(&which[p >> 21], 1u << threadIdx.x);
+    }
+  }
+  __syncthreads();
+  constexpr int shift = PASS == 0 ? 21 : (PASS == 1 ? 10 : 0);
+  constexpr uint32_t dmask = PASS == 2 ? 1023u : 2047u;
+  constexpr uint32_t pmask = PASS == 2 ? 0xFFFFFC00u : 0xFFE00000u;
+  const int64_t stride = (int64_t)gridDim.x * kThreads * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4; i < n; i += stride) {
+    const float4 v = load4(a, i, n, 0.f);
+    const uint32_t key[4] = {sal_key(v.x), sal_key(v.y), sal_key(v.z), sal_key(v.w)};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (i + j >= n) continue;
+      const uint32_t kk = key[j];
+      if (PASS == 0) {
+        atomicAdd(&sh[kk >> 21], 1u);
+      } else {
+        unsigned int m = which[kk >> 21];
+        while (m) {
+          const int r = __ffs(m) - 1;
+          m &= m - 1;
+          if (PASS == 1 || (kk & pmask) == pref[r]) atomicAdd(&sh[r * kRadixBins + ((kk >> shift) & dmask)], 1u);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Rh * kRadixBins; i += kThreads)
+    if (sh[i]) atomicAdd(&mhist[i], sh[i]);
+}
+
+// warp r picks for ratio r (pass 0 reads the shared histogram), then everybody clears the histograms for the next pass
+__global__ void k_mpick(unsigned int *__restrict__ mhist, unsigned long long *__restrict__ msel, int pass, MultiK mk) {
+  const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (r < mk.R && mk.mode[r] == 0)
+    radix_pick_warp(pass == 0 ? mhist : mhist + r * kRadixBins, msel + r * 8, pass, mk.k[r], lane);
+  __syncthreads();
+  for (int i = threadIdx.x; i < kMaxRatios * kRadixBins; i += blockDim.x) mhist[i] = 0;
+}
+
+__global__ void __launch_bounds__(kThreads) k_mtie_count(const float *__restrict__ a, int64_t n, int64_t chunk,
+                                                         const unsigned long long *__restrict__ msel,
+                                                         unsigned int *__restrict__ mties, MultiK mk) {
+  __shared__ unsigned int warp_cnt[kMaxRatios][kThreads / 32];
+  __shared__ uint32_t thr[kMaxRatios];
+  __shared__ int ordered[kMaxRatios];
+  if (threadIdx.x < kMaxRatios) {
+    const int r = threadIdx.x;
+    const bool on = r < mk.R && mk.mode[r] == 0 && msel[r * 8 + 7] != 0;
+    ordered[r] = on ? 1 : 0;
+    thr[r] = on ? (uint32_t)msel[r * 8 + 3] : 0u;
+  }
+  __syncthreads();
+  int any = 0;
+  for (int r = 0; r < mk.R; ++r) any |= ordered[r];
+  if (!any) return;  // uniform across the grid
+  unsigned int c[kMaxRatios];
+#pragma unroll
+  for (int r = 0; r < kMaxRatios; ++r) c[r] = 0;
+  const int64_t lo = (int64_t)blockIdx.x * chunk;
+  const int64_t hi = min(n, lo + chunk);
+  for (int64_t i = lo + (int64_t)threadIdx.x * 4; i < hi; i += kThreads * 4) {
+    const float4 v = load4(a, i, n, 0.f);
+    const uint32_t k0 = sal_key(v.x), k1 = sal_key(v.y), k2 = sal_key(v.z), k3 = sal_key(v.w);
+#pragma unroll
+    for (int r = 0; r < kMaxRatios; ++r)
+      if (r < mk.R && ordered[r]) {
+        const uint32_t t = thr[r];
+        c[r] += (k0 == t) + (i + 1 < n && k1 == t) + (i + 2 < n && k2 == t) + (i + 3 < n && k3 == t);
+      }
+  }
+#pragma unroll
+  for (int r = 0; r < kMaxRatios; ++r) {
+    unsigned int x = c[r];
+    for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) warp_cnt[r][threadIdx.x >> 5] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < mk.R) {
+    unsigned int t = 0;
+    for (int w = 0; w < kThreads / 32; ++w) t += warp_cnt[threadIdx.x][w];
+    mties[threadIdx.x * (kMaxPartials + 1) + blockIdx.x] = t;
+  }
+}
+
+__global__ void k_mtie_scan(unsigned int *__restrict__ mties, int nblocks, const unsigned long long *__restrict__ msel, MultiK mk) {
+  const int r = threadIdx.x;
+  if (r >= mk.R || mk.mode[r] != 0 || msel[r * 8 + 7] == 0) return;
+  unsigned int *bt = mties + r * (kMaxPartials + 1);
+  unsigned int run = 0;
+  for (int b = 0; b < nblocks; ++b) {
+    const unsigned int t = bt[b];
+    bt[b] = run;
+    run += t;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_mwrite(const float *__restrict__ a, int64_t n, int64_t chunk,
+                                                     const unsigned long long *__restrict__ msel,
+                                                     const unsigned int *__restrict__ mties, MultiK mk, MultiOut out) {
+  __shared__ unsigned int warp_tot[kThreads / 32];
+  __shared__ unsigned int iter_base[kMaxRatios];
+  __shared__ uint32_t thr[kMaxRatios];
+  __shared__ unsigned long long need[kMaxRatios];
+  __shared__ int ordered[kMaxRatios];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < kMaxRatios) {
+    const int r = threadIdx.x;
+    const bool sel = r < mk.R && mk.mode[r] == 0;
+    thr[r] = sel ? (uint32_t)msel[r * 8 + 3] : 0u;
+    need[r] = sel ? msel[r * 8 + 6] : 0ull;
+    ordered[r] = (sel && msel[r * 8 + 7] != 0) ? 1 : 0;
+    iter_base[r] = ordered[r] ? mties[r * (kMaxPartials + 1) + blockIdx.x] : 0u;
+  }
+  __syncthreads();
+  const int64_t lo = (int64_t)blockIdx.x * chunk;
+  const int64_t hi = min(n, lo + chunk);
+  for (int64_t base = lo; base < hi; base += kThreads * 4) {  // uniform trip count per block
+    const int64_t i = base + (int64_t)threadIdx.x * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < hi) v = load4(a, i, n, 0.f);
+    const uint32_t key[4] = {sal_key(v.x), sal_key(v.y), sal_key(v.z), sal_key(v.w)};
+    uint32_t validm = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) validm |= ((i + j < n && i < hi) ? 1u : 0u) << j;
+    for (int r = 0; r < mk.R; ++r) {
+      uint32_t sel_bits;
+      if (mk.mode[r] == 1) {
+        sel_bits = validm;
+      } else if (mk.mode[r] == 2) {
+        sel_bits = 0;
+      } else {
+        const uint32_t t = thr[r];
+        uint32_t gt = 0, eq = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool valid = (validm >> j) & 1u;
+          gt |= ((valid && key[j] > t) ? 1u : 0u) << j;
+          eq |= ((valid && key[j] == t) ? 1u : 0u) << j;
+        }
+        sel_bits = gt;
+        if (!ordered[r]) {
+          sel_bits |= eq;
+        } else {
+          unsigned int c = __popc(eq), incl = c;
+          for (int o = 1; o < 32; o <<= 1) {
+            unsigned int tt = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += tt;
+          }
+          if (lane == 31) warp_tot[warp] = incl;
+          __syncthreads();
+          unsigned int wbase = 0, total = 0;
+          for (int w = 0; w < kThreads / 32; ++w) {
+            const unsigned int tt = warp_tot[w];
+            if (w < warp) wbase += tt;
+            total += tt;
+          }
+          unsigned long long rank = (unsigned long long)iter_base[r] + wbase + (incl - c);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (eq & (1u << j)) {
+              if (rank < need[r]) sel_bits |= 1u << j;
+              ++rank;
+            }
+          __syncthreads();
+          if (threadIdx.x == 0) iter_base[r] += total;
+          __syncthreads();
+        }
+      }
+      long long *m64 = out.m64[r];
+      if (m64 && i < hi) {
+        const long long m0 = sel_bits & 1u, m1 = (sel_bits >> 1) & 1u, m2 = (sel_bits >> 2) & 1u, m3 = (sel_bits >> 3) & 1u;
+        if (out.vec64[r] && i + 3 < n) {
+          reinterpret_cast<longlong2 *>(m64 + i)[0] = make_longlong2(m0, m1);
+          reinterpret_cast<longlong2 *>(m64 + i)[1] = make_longlong2(m2, m3);
+        } else {
+          if (i < n) m64[i] = m0;
+          if (i + 1 < n) m64[i + 1] = m1;
+          if (i + 2 < n) m64[i + 2] = m2;
+          if (i + 3 < n) m64[i + 3] = m3;
+        }
+      }
+      uint32_t *mb = out.bits[r];
+      if (mb) {
+        uint32_t w = sel_bits << (4 * (lane & 7));
+        w |= __shfl_xor_sync(0xffffffffu, w, 1);
+        w |= __shfl_xor_sync(0xffffffffu, w, 2);
+        w |= __shfl_xor_sync(0xffffffffu, w, 4);
+        if ((lane & 7) == 0 && i < hi && i < n) mb[i >> 5] = w;
+      }
     }
   }
 }
@@ -655,6 +894,12 @@ int salun_ctx_destroy(salun_ctx *c) {
   cudaFree(c->block_ties);
   cudaFree(c->partials);
   cudaFreeHost(c->mailbox_host);
+  if (c->msel) {
+    cudaFree(c->msel);
+    cudaFree(c->mhist);
+    cudaFree(c->mties);
+    cudaFreeHost(c->mmailbox_host);
+  }
   delete c;
   return SALUN_OK;
 }
@@ -779,6 +1024,90 @@ int salun_topk_mask(salun_ctx *ctx, const float *accum, int64_t n, int64_t k, in
       memcpy(&info_host->thr_value, &vb, 4);
       info_host->n_greater = (int64_t)ctx->mailbox_host[4];
       info_host->n_equal = (int64_t)ctx->mailbox_host[5];
+    }
+  }
+  return SALUN_OK;
+}
+
+int salun_topk_mask_multi(salun_ctx *ctx, const float *accum, int64_t n, const int64_t *ks_host, int n_ratios,
+                          int64_t *const *mask_i64_host, uint32_t *const *mask_bits_host, salun_topk_info *infos_host,
+                          void *stream) {
+  SALUN_ENTER(ctx);
+  SALUN_REQUIRE(n >= 0 && n_ratios >= 0 && n_ratios <= kMaxRatios, "n < 0 or more than 16 ratios");
+  if (infos_host) memset(infos_host, 0, sizeof(salun_topk_info) * (size_t)n_ratios);
+  if (n == 0 || n_ratios == 0) return SALUN_OK;
+  SALUN_REQUIRE(ks_host && (mask_i64_host || mask_bits_host), "NULL argument");
+  SALUN_REQUIRE(accum && aligned16(accum), "accum must be non-NULL and 16-byte aligned");
+  if (!ctx->msel) {
+    SALUN_CUDA_OK(cudaMalloc(&ctx->msel, kMaxRatios * 8 * sizeof(unsigned long long)));
+    SALUN_CUDA_OK(cudaMalloc(&ctx->mhist, (size_t)kMaxRatios * kRadixBins * sizeof(unsigned int)));
+    SALUN_CUDA_OK(cudaMalloc(&ctx->mties, (size_t)kMaxRatios * (kMaxPartials + 1) * sizeof(unsigned int)));
+    SALUN_CUDA_OK(cudaMallocHost(&ctx->mmailbox_host, kMaxRatios * 8 * sizeof(unsigned long long)));
+  }
+  MultiK mk{};
+  MultiOut out{};
+  mk.R = n_ratios;
+  bool any_select = false;
+  for (int r = 0; r < n_ratios; ++r) {
+    SALUN_REQUIRE(ks_host[r] >= 0, "negative k");
+    mk.k[r] = ks_host[r];
+    mk.mode[r] = ks_host[r] == 0 ? 2 : (ks_host[r] >= n ? 1 : 0);
+    any_select |= mk.mode[r] == 0;
+    out.m64[r] = mask_i64_host ? (long long *)mask_i64_host[r] : nullptr;
+    out.bits[r] = mask_bits_host ? mask_bits_host[r] : nullptr;
+    out.vec64[r] = out.m64[r] && aligned16(out.m64[r]);
+    SALUN_REQUIRE(out.m64[r] || out.bits[r], "a ratio without an output");
+  }
+  const int grid = grid_for(ctx, (n + 3) / 4);
+  int64_t chunk = (n + grid - 1) / grid;
+  chunk = (chunk + 1023) / 1024 * 1024;
+  const int wgrid = (int)((n + chunk - 1) / chunk);
+  if (any_select) {
+    static bool attr_set = false;
+    const size_t smem_full = ((size_t)kMaxRatios * kRadixBins + kRadixBins + kMaxRatios) * sizeof(unsigned int);
+    if (!attr_set) {
+      SALUN_CUDA_OK(cudaFuncSetAttribute(k_mhist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_full));
+      SALUN_CUDA_OK(cudaFuncSetAttribute(k_mhist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_full));
+      attr_set = true;
+    }
+    const size_t smem0 = ((size_t)kRadixBins * 2 + kMaxRatios) * sizeof(unsigned int);
+    const size_t smemR = ((size_t)n_ratios * kRadixBins + kRadixBins + kMaxRatios) * sizeof(unsigned int);
+    k_msel_init<<<32, 256, 0, st>>>(ctx->msel, ctx->mhist, mk);
+    k_mhist<0><<<grid, kThreads, smem0, st>>>(accum, n, ctx->msel, ctx->mhist, mk);
+    k_mpick<<<1, kMaxRatios * 32, 0, st>>>(ctx->mhist, ctx->msel, 0, mk);
+    k_mhist<1><<<grid, kThreads, smemR, st>>>(accum, n, ctx->msel, ctx->mhist, mk);
+    k_mpick<<<1, kMaxRatios * 32, 0, st>>>(ctx->mhist, ctx->msel, 1, mk);
+    k_mhist<2><<<grid, kThreads, smemR, st>>>(accum, n, ctx->msel, ctx->mhist, mk);
+    k_mpick<<<1, kMaxRatios * 32, 0, st>>>(ctx->mhist, ctx->msel, 2, mk);
+    k_mtie_count<<<wgrid, kThreads, 0, st>>>(accum, n, chunk, ctx->msel, ctx->mties, mk);
+    k_mtie_scan<<<1, 32, 0, st>>>(ctx->mties, wgrid, ctx->msel, mk);
+    ::salun::g_launch_count += 9;
+  }
+  k_mwrite<<<wgrid, kThreads, 0, st>>>(accum, n, chunk, ctx->msel, ctx->mties, mk, out);
+  ++::salun::g_launch_count;
+  SALUN_CUDA_OK(cudaGetLastError());
+  if (infos_host) {
+    if (any_select)
+      SALUN_CUDA_OK(cudaMemcpyAsync(ctx->mmailbox_host, ctx->msel, (size_t)n_ratios * 8 * sizeof(unsigned long long),
+                                    cudaMemcpyDeviceToHost, st));
+    SALUN_CUDA_OK(cudaStreamSynchronize(st));
+    for (int r = 0; r < n_ratios; ++r) {
+      salun_topk_info &inf = infos_host[r];
+      if (mk.mode[r] == 2) {
+        inf.thr_key = 0xffffffffu;
+        inf.thr_value = INFINITY;
+      } else if (mk.mode[r] == 1) {
+        inf.thr_key = 0;
+        inf.thr_value = 0.f;
+        inf.n_greater = n;
+      } else {
+        const unsigned long long *m = ctx->mmailbox_host + r * 8;
+        inf.thr_key = (uint32_t)m[3];
+        uint32_t vb = inf.thr_key ? inf.thr_key - 1u : 0x7fc00000u;
+        memcpy(&inf.thr_value, &vb, 4);
+        inf.n_greater = (int64_t)m[4];
+        inf.n_equal = (int64_t)m[5];
+      }
     }
   }
   return SALUN_OK;

@@ -124,6 +124,25 @@ class SalunContext:
               "salun_topk_mask")
         return m64, bits, info
 
+    def topk_mask_multi(self, accum: torch.Tensor, ks: Sequence[int], want_i64: bool = True, want_bits: bool = True,
+                        want_info: bool = False):
+        """The reference's sweep over threshold_list (generate_mask.py:50-82) as one call: the saliencies are read once
+        per pass for ALL ratios.  Returns (list of mask_i64, list of mask_bits, list of info); entry r is bit-identical to
+        topk_mask(accum, ks[r])."""
+        _req(accum, torch.float32, "accum")
+        n, R = accum.numel(), len(ks)
+        if R > 16:
+            raise ValueError("at most 16 ratios per call")
+        m64 = [torch.empty(n, dtype=torch.int64, device=accum.device) for _ in range(R)] if want_i64 else None
+        bits = [torch.empty(mask_words(n), dtype=torch.int32, device=accum.device) for _ in range(R)] if want_bits else None
+        kk = (C.c_int64 * R)(*[int(k) for k in ks])
+        p64 = (C.c_void_p * R)(*[t.data_ptr() for t in m64]) if want_i64 else None
+        pb = (C.c_void_p * R)(*[t.data_ptr() for t in bits]) if want_bits else None
+        infos = (salun_topk_info * R)() if want_info else None
+        check(self._lib.salun_topk_mask_multi(self._h, _ptr(accum), n, kk, R, p64, pb, infos, _stream(self.device)),
+              "salun_topk_mask_multi")
+        return m64, bits, (list(infos) if infos is not None else None)
+
     def pack_mask(self, mask_i64: torch.Tensor) -> torch.Tensor:
         _req(mask_i64, torch.int64, "mask_i64")
         n = mask_i64.numel()
