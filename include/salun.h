@@ -471,6 +471,10 @@ int salun_sd_geglu(salun_ctx *ctx, const void *proj, void *out, int64_t rows, in
 int64_t salun_sd_attention_ws_bytes(int n, int Tq, int Tk, int heads, int d);
 int salun_sd_attention(salun_ctx *ctx, void *ws, int64_t ws_bytes, const void *q, const void *k, const void *v, void *out, int n,
                        int Tq, int Tk, int heads, int d, void *stream);
+/* the same with row strides (elements) for q, k, v: column slices of a fused q | k | v (self-attention) or k | v (cross-
+ * attention) projection output, so one GEMM serves the three / two Linears of attention.py:177-179 */
+int salun_sd_attention_ld(salun_ctx *ctx, void *ws, int64_t ws_bytes, const void *q, int ldq, const void *k, int ldk, const void *v,
+                          int ldv, void *out, int n, int Tq, int Tk, int heads, int d, void *stream);
 
 #ifdef __cplusplus
 }

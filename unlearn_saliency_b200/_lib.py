@@ -95,6 +95,8 @@ _SIGNATURES = {
     "salun_op_groupnorm_ws_floats": [C.c_int],
     "salun_op_set_scratch": [_P, _P, _I64],
     "salun_sd_attention": [_P, _P, _I64, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P],
+    "salun_sd_attention_ld": [_P, _P, _I64, _P, C.c_int, _P, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int,
+                              C.c_int, _P],
     "salun_ddim_step": [_P, _P, _P, _P, _P, _P, _P, _F, _F, C.c_int, C.c_int, _P, _P, _P],
     "salun_masked_adam_step": [_P, _P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I64, _P, _P],
     # tcgen05 GEMM / convolution entry points (salun_gemm.cu)

@@ -352,6 +352,53 @@ __global__ void __launch_bounds__(256) k_heads_pack_vt(const act_t *__restrict__
     wop_store(dst + (size_t)(g * dp + c) * Tkp * kWopK, j, Tkp, val);
   }
 }
+// The three packs above as ONE launch (blocks [0, gq) pack Q, [gq, gq + gk) pack K, the rest pack V^T), reading q / k / v with
+// their own row strides -- so q | k | v may be column slices of one fused projection output [rows][3C].
+__global__ void __launch_bounds__(256) k_heads_pack_all(const act_t *__restrict__ q, int ldq, const act_t *__restrict__ k, int ldk,
+                                                        const act_t *__restrict__ v, int ldv, act_t *__restrict__ Qh,
+                                                        wop_t *__restrict__ Kh, wop_t *__restrict__ Vt, int gq, int gk, long long totq,
+                                                        long long totk, long long totv, int Tq, int Tqp, int Tk, int Tkp, int heads,
+                                                        int d, int dp) {
+  if ((int)blockIdx.x < gq) {
+    const int vecs = dp >> 3;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < totq; i += (long long)gq * 256) {
+      const int vv = (int)(i % vecs);
+      long long r = i / vecs;
+      const int t = (int)(r % Tqp);
+      const long long g = r / Tqp;
+      const int h = (int)(g % heads);
+      const long long b = g / heads;
+      avec val = avec_zero();
+      if (t < Tq && vv * 8 < d) val = ldvec(q + (b * Tq + t) * ldq + h * d + vv * 8);
+      stvec(Qh + (g * Tqp + t) * dp + vv * 8, val);
+    }
+  } else if ((int)blockIdx.x < gq + gk) {
+    for (long long i = (long long)(blockIdx.x - gq) * 256 + threadIdx.x; i < totk; i += (long long)gk * 256) {
+      const int c = (int)(i % dp);
+      long long r = i / dp;
+      const int j = (int)(r % Tkp);
+      const long long g = r / Tkp;
+      const int h = (int)(g % heads);
+      const long long b = g / heads;
+      float val = 0.f;
+      if (j < Tk && c < d) val = act_to_float(k[(b * Tk + j) * ldk + h * d + c]);
+      wop_store(Kh + (size_t)(g * Tkp + j) * dp * kWopK, c, dp, val);
+    }
+  } else {
+    const int gv = gridDim.x - gq - gk;
+    for (long long i = (long long)(blockIdx.x - gq - gk) * 256 + threadIdx.x; i < totv; i += (long long)gv * 256) {
+      const int j = (int)(i % Tkp);
+      long long r = i / Tkp;
+      const int c = (int)(r % dp);
+      const long long g = r / dp;
+      const int h = (int)(g % heads);
+      const long long b = g / heads;
+      float val = 0.f;
+      if (j < Tk && c < d) val = act_to_float(v[(b * Tk + j) * ldv + h * d + c]);
+      wop_store(Vt + (size_t)(g * dp + c) * Tkp * kWopK, j, Tkp, val);
+    }
+  }
+}
 // P = softmax(scale * S) over the Tk valid keys; padded query rows and padded keys get 0.  One warp per row.
 __global__ void __launch_bounds__(256) k_softmax_rows(const float *__restrict__ S, act_t *__restrict__ P, long long rows, int Tq,
                                                       int Tqp, int Tk, int Tkp, float scale) {
@@ -674,8 +721,15 @@ int64_t salun_sd_attention_ws_bytes(int n, int Tq, int Tk, int heads, int d) {
 // q [n*Tq][C], k / v [n*Tk][C], C = heads * d; self-attention: k, v from the same tokens, Tk = Tq)
 int salun_sd_attention(salun_ctx *ctx, void *ws, int64_t ws_bytes, const void *q, const void *k, const void *v, void *out, int n,
                        int Tq, int Tk, int heads, int d, void *stream) {
+  return salun_sd_attention_ld(ctx, ws, ws_bytes, q, heads * d, k, heads * d, v, heads * d, out, n, Tq, Tk, heads, d, stream);
+}
+// the same with row strides (in elements) for q, k, v: column slices of a fused q | k | v (or k | v) projection output
+int salun_sd_attention_ld(salun_ctx *ctx, void *ws, int64_t ws_bytes, const void *q, int ldq, const void *k, int ldk, const void *v,
+                          int ldv, void *out, int n, int Tq, int Tk, int heads, int d, void *stream) {
   SALUN_REQUIRE(ctx && ws && q && k && v && out, "NULL argument");
   SALUN_REQUIRE(n > 0 && Tq > 0 && Tk > 0 && heads > 0 && d > 0 && d % 8 == 0, "bad sizes (d % 8 == 0)");
+  SALUN_REQUIRE(ldq >= heads * d && ldk >= heads * d && ldv >= heads * d && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0,
+                "row strides must cover heads * d and be multiples of 8");
   int Tqp, Tkp, dp;
   size_t off[6], total;
   attn_sizes(n, Tq, Tk, heads, d, &Tqp, &Tkp, &dp, off, &total);
@@ -689,10 +743,13 @@ int salun_sd_attention(salun_ctx *ctx, void *ws, int64_t ws_bytes, const void *q
   wop_t *Kh = (wop_t *)(w + off[1]), *Vt = (wop_t *)(w + off[2]);
   float *S = (float *)(w + off[3]);
   act_t *P = (act_t *)(w + off[4]), *Oh = (act_t *)(w + off[5]);
-  k_heads_pack_q<<<grid1d(G * Tqp * (dp >> 3), 256, 148 * 16), 256, 0, st>>>((const act_t *)q, Qh, G * Tqp * (dp >> 3), Tq, Tqp, C, heads, d, dp);
-  k_heads_pack_k<<<grid1d(G * Tkp * dp, 256, 148 * 16), 256, 0, st>>>((const act_t *)k, Kh, G * Tkp * dp, Tk, Tkp, C, heads, d, dp);
-  k_heads_pack_vt<<<grid1d(G * dp * Tkp, 256, 148 * 16), 256, 0, st>>>((const act_t *)v, Vt, G * dp * Tkp, Tk, Tkp, C, heads, d, dp);
-  g_launch_count += 3;
+  {
+    const long long totq = G * Tqp * (dp >> 3), totk = G * Tkp * dp, totv = G * dp * Tkp;
+    const int gq = grid1d(totq, 256, 148 * 4), gk = grid1d(totk, 256, 148 * 6), gv = grid1d(totv, 256, 148 * 6);
+    k_heads_pack_all<<<gq + gk + gv, 256, 0, st>>>((const act_t *)q, ldq, (const act_t *)k, ldk, (const act_t *)v, ldv, Qh, Kh, Vt, gq,
+                                                  gk, totq, totk, totv, Tq, Tqp, Tk, Tkp, heads, d, dp);
+    ++g_launch_count;
+  }
   if (use_flash_attn(d)) return launch_flash_attn(Qh, Kh, Vt, (act_t *)out, n, Tq, Tqp, Tk, Tkp, heads, d, st);
   const long long M = G * Tqp;
   int rc;

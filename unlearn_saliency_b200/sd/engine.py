@@ -258,6 +258,21 @@ class SDUNetEngine:
         self._wops[name] = buf
 
     def _prepare_weights(self):
+        # to_q | to_k | to_v of a self-attention (to_k | to_v of a cross-attention) read the same rows: their operands are
+        # slices of ONE stacked buffer, so the projections run as one GEMM with N = 3C (2C); _prep fills the slices in place
+        if not hasattr(self, "_stack"):
+            self._stack: Dict[str, tuple] = {}
+        for k, shp in self.table.items():
+            if k.endswith(".to_q.weight") and k[:-len(".to_q.weight")] not in self._stack:
+                pre = k[:-len(".to_q.weight")]
+                C_, kd = shp[0], self.table[pre + ".to_k.weight"][1]
+                names = [pre + ".to_q.weight", pre + ".to_k.weight", pre + ".to_v.weight"] if kd == C_ else \
+                        [pre + ".to_k.weight", pre + ".to_v.weight"]
+                per = C_ * _pad64(kd) * self.wop_k
+                stack = torch.empty(per * len(names), dtype=torch.bfloat16, device=self.device)
+                for i, nm in enumerate(names):
+                    self._wops[nm] = stack[i * per:(i + 1) * per]
+                self._stack[pre] = ("qkv" if kd == C_ else "kv", stack, per)
         for k, shp in self.table.items():
             if not k.endswith(".weight") or len(shp) < 2 or k.startswith("time_embed") or ".emb_layers." in k:
                 continue      # norms and the fp32 embedding MLPs keep their fp32 weights
@@ -341,12 +356,15 @@ class SDUNetEngine:
                 _ptr(addend), _ptr(out), 1 if (out_pad and out_f32 is None) else 0, _ptr(out_f32), n, H, H, kp, cp, ks, what=name)
             return out
 
-        def linear_rows(x, rows, name, cin, cout, bias=True, addend=None):
+        def linear_rows(x, rows, name, cin, cout, bias=True, addend=None, wop=None):
             out = buf(self._flat(rows, cout))
             b = _ptr(P[name[:-len(".weight")] + ".bias"]) if bias else None
-            run(L.salun_op_conv, h, _ptr(x), 1, _ptr(W[name]), b, None, 0, _ptr(addend), _ptr(out), 0, None, rows, 1, 1, cin, cout, 1,
-                what=name)
+            run(L.salun_op_conv, h, _ptr(x), 1, _ptr(W[name] if wop is None else wop), b, None, 0, _ptr(addend), _ptr(out), 0, None,
+                rows, 1, 1, cin, cout, 1, what=name)
             return out
+
+        def col_slice(t, col):     # pointer to column `col` of a flat activation matrix
+            return C.c_void_p(t.data_ptr() + col * self.act_bytes)
 
         def groupnorm(x, pre, C, H, eps, swish, out_flat=False):
             out = buf(self._flat(n * H * H, C) if out_flat else self._padded(n, H, C))
@@ -365,15 +383,20 @@ class SDUNetEngine:
 
         def attention(xq, rows_q, Tq, kv, Tk, pre, kd, C, d, addend):
             """CrossAttention.forward (attention.py:168-192): projections, per-head softmax(QK^T/sqrt(d)) V, to_out + residual"""
-            q = linear_rows(xq, rows_q, pre + ".to_q.weight", C, C, bias=False)
-            k = linear_rows(kv, n * Tk, pre + ".to_k.weight", kd, C, bias=False)
-            v = linear_rows(kv, n * Tk, pre + ".to_v.weight", kd, C, bias=False)
+            kind, stack, per = self._stack[pre]
+            if kind == "qkv" and kv is xq:      # self-attention: one GEMM for q | k | v
+                qkv = linear_rows(xq, rows_q, pre + ".to_q|k|v", C, 3 * C, bias=False, wop=stack)
+                qp, kp_, vp, ldq, ldkv = _ptr(qkv), col_slice(qkv, C), col_slice(qkv, 2 * C), 3 * C, 3 * C
+            else:                               # cross-attention: q from the tokens, k | v from the context in one GEMM
+                q = linear_rows(xq, rows_q, pre + ".to_q.weight", C, C, bias=False)
+                kvb = linear_rows(kv, n * Tk, pre + ".to_k|v", kd, 2 * C, bias=False, wop=stack if kind == "kv" else stack[per:])
+                qp, kp_, vp, ldq, ldkv = _ptr(q), _ptr(kvb), col_slice(kvb, C), C, 2 * C
             o = buf(self._flat(rows_q, C))
             nbytes = int(L.salun_sd_attention_ws_bytes(n, Tq, Tk, heads, d))
             if (Tq, Tk, d) not in attn_ws:
                 attn_ws[(Tq, Tk, d)] = buf(torch.zeros(nbytes, dtype=torch.uint8, device=dev))
             ws = attn_ws[(Tq, Tk, d)]
-            run(L.salun_sd_attention, h, _ptr(ws), nbytes, _ptr(q), _ptr(k), _ptr(v), _ptr(o), n, Tq, Tk, heads, d, what=pre)
+            run(L.salun_sd_attention_ld, h, _ptr(ws), nbytes, qp, ldq, kp_, ldkv, vp, ldkv, _ptr(o), n, Tq, Tk, heads, d, what=pre)
             return linear_rows(o, rows_q, pre + ".to_out.0.weight", C, C, addend=addend)
 
         def transformer(x, pre, C, d, H):
