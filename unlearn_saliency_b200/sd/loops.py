@@ -103,8 +103,11 @@ def esd_iteration(model, model_orig, sample_fn: Callable, tail: SDTail, word: st
     start_code = rng["start_code"] if "start_code" in rng else torch.randn((1, 4, image_size // 8, image_size // 8)).to(d0)
     with torch.no_grad():
         z = sample_fn(emb_p.to(d0), start_guidance, start_code, int(t_enc))
-        e_0 = model_orig.apply_model(z.to(d1), t_enc_ddpm.to(d1), emb_0.to(d1))
-        e_p = model_orig.apply_model(z.to(d1), t_enc_ddpm.to(d1), emb_p.to(d1))
+        if hasattr(model_orig, "apply_model_pair"):     # engine-backed frozen model: both conditionings in one pass
+            e_0, e_p = model_orig.apply_model_pair(z.to(d1), t_enc_ddpm.to(d1), emb_0.to(d1), emb_p.to(d1))
+        else:
+            e_0 = model_orig.apply_model(z.to(d1), t_enc_ddpm.to(d1), emb_0.to(d1))
+            e_p = model_orig.apply_model(z.to(d1), t_enc_ddpm.to(d1), emb_p.to(d1))
     e_n = model.apply_model(z.to(d0), t_enc_ddpm.to(d0), emb_n.to(d0))
     target = e_0.to(d0) - (negative_guidance * (e_p.to(d0) - e_0.to(d0)))
     loss = torch.nn.functional.mse_loss(e_n.to(d0), target)                     # :301-311

@@ -130,6 +130,16 @@ class EngineApplyModel:
     def apply_model(self, x_noisy, t, cond):
         return self.engine.forward(x_noisy.to(self.engine.device, torch.float32), t, cond.to(self.engine.device, torch.float32))
 
+    @torch.no_grad()
+    def apply_model_pair(self, x_noisy, t, cond_a, cond_b):
+        """eps for two conditionings of the SAME (x, t) as one batch of 2n (e_0 and e_p of train-esd.py:295-297)"""
+        n = x_noisy.shape[0]
+        dev = self.engine.device
+        x2 = torch.cat([x_noisy, x_noisy]).to(dev, torch.float32)
+        t2 = torch.cat([t, t]) if t.numel() == n else t.expand(2 * n)
+        eps = self.engine.forward(x2, t2, torch.cat([cond_a, cond_b]).to(dev, torch.float32))
+        return eps[:n], eps[n:]
+
     def eval(self):
         return self
 
