@@ -55,6 +55,17 @@ struct FaArgs {
   float c2;     // log2(e) / sqrt(d)
 };
 
+// tcgen05.wait::ld that also names the destination registers of the load it completes: the compiler must treat them as
+// written HERE, so it cannot read or move them between the (asynchronous) load and the wait when other work is interleaved
+__device__ __forceinline__ void tc_wait_ld_regs(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -171,75 +182,85 @@ k_flash_attn(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 #pragma unroll
     for (int i = 0; i < kFaDp; ++i) O[i] = 0.f;
     uint8_t *p_row = smem + (sP - smem_base) + row * 128;
+    constexpr int NC = BKV / 32;  // 32-column chunks of an S row: 4 | 2 (even: the two register buffers alternate statically)
+    uint32_t r[2][32];
     for (int j = 0; j < nblk; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int key0 = j * BKV;
-      float mx = m_run;
-#pragma unroll 1
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t r[32];
-        tc_ld_32x32b_x32(tmem_S + lane_off + c * 32, r);
-        tc_wait_ld();
+      // Tensor-memory loads are software pipelined (chunk c+1 is in flight while chunk c is consumed) and the max / sum
+      // run as four independent chains: with two softmax warps per scheduler nothing else hides those latencies.
+      // ---- pass 1: row maximum
+      float mx4[4] = {m_run, -INFINITY, -INFINITY, -INFINITY};
+      tc_ld_32x32b_x32(tmem_S + lane_off, r[0]);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        tc_wait_ld_regs(r[c & 1]);
+        tc_ld_32x32b_x32(tmem_S + lane_off + ((c + 1) % NC) * 32, r[(c + 1) & 1]);  // next chunk, or chunk 0 again for pass 2
+        const uint32_t(&x)[32] = r[c & 1];
         if (key0 + c * 32 + 32 <= a.Tk) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]) * a.c2);
+          for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(x[i]) * a.c2);
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (key0 + c * 32 + i < a.Tk) mx = fmaxf(mx, __uint_as_float(r[i]) * a.c2);
+            if (key0 + c * 32 + i < a.Tk) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(x[i]) * a.c2);
         }
       }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float alpha = ex2(m_run - mx);  // first block: exp2(-inf) = 0
-      float rowsum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t r[32];
-        tc_ld_32x32b_x32(tmem_S + lane_off + c * 32, r);
-        tc_wait_ld();
-        float p[32];
+      // ---- pass 2: P = exp2(S c - max), row sum, A operand of P V
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        tc_wait_ld_regs(r[c & 1]);
+        if (c + 1 < NC) tc_ld_32x32b_x32(tmem_S + lane_off + (c + 1) * 32, r[(c + 1) & 1]);
+        const uint32_t(&x)[32] = r[c & 1];
         const bool full = key0 + c * 32 + 32 <= a.Tk;
+        // eight scores at a time: exp2, row sum, pack, one 16-byte store of the A operand of P V (row `row`, operand columns
+        // [c*32*U, +32*U) -> 16-byte chunks of the 128B-swizzled [128][128 B] blocks); keeps the live registers low
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float v = ex2(fmaf(__uint_as_float(r[i]), a.c2, -mx));
-          if (!full && key0 + c * 32 + i >= a.Tk) v = 0.f;
-          p[i] = v;
-          rowsum += v;
-        }
-        // A operand of P V: row `row`, operand columns [c*32*U, +32*U) -> 16-byte chunks of the swizzled [128][128 B] blocks
-        if (U == 1) {
-          uint8_t *blk = p_row + (c >> 1) * Cfg::kQBlock;
+        for (int q8 = 0; q8 < 4; ++q8) {
+          float p[8];
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const int chunk = (c & 1) * 4 + q4;
-            *reinterpret_cast<uint4 *>(blk + ((chunk ^ (row & 7)) << 4)) =
-                make_uint4(pack_bf16x2(p[8 * q4], p[8 * q4 + 1]), pack_bf16x2(p[8 * q4 + 2], p[8 * q4 + 3]),
-                           pack_bf16x2(p[8 * q4 + 4], p[8 * q4 + 5]), pack_bf16x2(p[8 * q4 + 6], p[8 * q4 + 7]));
+          for (int i = 0; i < 8; ++i) {
+            float v = ex2(fmaf(__uint_as_float(x[q8 * 8 + i]), a.c2, -mx));
+            if (!full && key0 + c * 32 + q8 * 8 + i >= a.Tk) v = 0.f;
+            p[i] = v;
+            rs4[i & 3] += v;
           }
-        } else {
-          uint8_t *blk = p_row + c * Cfg::kQBlock;
-#pragma unroll
-          for (int chunk = 0; chunk < 8; ++chunk)
+          if (U == 1) {
+            uint8_t *blk = p_row + (c >> 1) * Cfg::kQBlock;
+            const int chunk = (c & 1) * 4 + q8;
             *reinterpret_cast<uint4 *>(blk + ((chunk ^ (row & 7)) << 4)) =
-                make_uint4(act_pack_pair(p[4 * chunk]), act_pack_pair(p[4 * chunk + 1]), act_pack_pair(p[4 * chunk + 2]),
-                           act_pack_pair(p[4 * chunk + 3]));
+                make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
+          } else {
+            uint8_t *blk = p_row + c * Cfg::kQBlock;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int chunk = q8 * 2 + hh;
+              *reinterpret_cast<uint4 *>(blk + ((chunk ^ (row & 7)) << 4)) =
+                  make_uint4(act_pack_pair(p[4 * hh]), act_pack_pair(p[4 * hh + 1]), act_pack_pair(p[4 * hh + 2]),
+                             act_pack_pair(p[4 * hh + 3]));
+            }
+          }
         }
       }
-      l_run = fmaf(l_run, alpha, rowsum);
+      l_run = fmaf(l_run, alpha, (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
       m_run = mx;
       tc_fence_before();
       fence_proxy_async();  // generic-proxy stores of P -> visible to the tensor core's async-proxy reads
       mbar_arrive(p_full);
       mbar_wait(o_full, j & 1);
       tc_fence_after();
+      tc_ld_32x32b_x32(tmem_O + lane_off, r[0]);
+      tc_wait_ld_regs(r[0]);
+      tc_ld_32x32b_x32(tmem_O + lane_off + 32, r[1]);
 #pragma unroll
-      for (int c = 0; c < kFaDp / 32; ++c) {
-        uint32_t r[32];
-        tc_ld_32x32b_x32(tmem_O + lane_off + c * 32, r);
-        tc_wait_ld();
+      for (int i = 0; i < 32; ++i) O[i] = fmaf(O[i], alpha, __uint_as_float(r[0][i]));
+      tc_wait_ld_regs(r[1]);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) O[c * 32 + i] = fmaf(O[c * 32 + i], alpha, __uint_as_float(r[i]));
-      }
+      for (int i = 0; i < 32; ++i) O[32 + i] = fmaf(O[32 + i], alpha, __uint_as_float(r[1][i]));
     }
     const int tq = m_tile * 128 + row;
     if (tq < a.Tq) {
