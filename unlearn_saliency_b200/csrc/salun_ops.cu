@@ -99,83 +99,154 @@ __global__ void k_prep_weight(const float *__restrict__ w, wop_t *__restrict__ o
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm (any C % 8 == 0)
-// Statistics in two steps so that batch 1-2 still fills the GPU: k_gn2_partial sums a 1/kGnSplits slice of the pixels of one
-// (sample, group) per CTA (32 * n * kGnSplits CTAs; fp32 per thread over a few dozen values, fp64 across threads) and stores
-// (sum, sum of squares) as doubles; k_gn2_apply folds the kGnSplits partials of every (sample, group) into mean / rstd in its
-// prologue (shared memory) and normalises.  Deterministic: fixed partition, fixed summation order, no atomics.
-constexpr int kGnSplits = 16;
-__global__ void __launch_bounds__(256) k_gn2_partial(const act_t *__restrict__ x, double *__restrict__ part, int H, int W, int C) {
-  __shared__ double sh[2][8];
-  const int g = blockIdx.x, n = blockIdx.y, z = blockIdx.z, cpg = C / 32;
-  const long long hw = (long long)H * W;
-  const long long p0 = hw * z / kGnSplits, p1 = hw * (z + 1) / kGnSplits;
-  const long long cnt = (p1 - p0) * cpg;
-  float a = 0.f, b = 0.f;
-  for (long long i = threadIdx.x; i < cnt; i += 256) {
-    const int c = (int)(i % cpg);
-    const long long p = p0 + i / cpg;
-    const int xx = (int)(p % W), y = (int)(p / W);
-    const float v = act_to_float(x[pad_off4(n, y, xx, H, W, C) + g * cpg + c]);
-    a += v;
-    b = fmaf(v, v, b);
-  }
-  double da = a, db = b;
-  for (int o = 16; o; o >>= 1) {
-    da += __shfl_xor_sync(0xffffffffu, da, o);
-    db += __shfl_xor_sync(0xffffffffu, db, o);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    sh[0][threadIdx.x >> 5] = da;
-    sh[1][threadIdx.x >> 5] = db;
+// Both kernels give every thread ONE fixed 8-channel vector (two for C > 2048) and walk pixels: 16-byte coalesced loads, one
+// 32-bit division per load (pixel -> row / column of the padded image) and nothing else in the loop.  (The first version
+// decoded (pixel, channel) per ELEMENT with 64-bit divisions and ran at 0.27 TB/s: profiles/r2_ncu_summary_sd.txt.)
+//   k_gn2_partial  grid (S, n): CTA z sums its 1/S slice of the pixels of sample n for all channels (fp32 per thread over a few
+//                  pixels, fp64 across threads and channels), writes (sum, sum of squares) per group as doubles
+//   k_gn2_apply    grid (X, n): prologue folds the S partials of the sample's 32 groups into mean / rstd and each thread
+//                  turns them into scale / shift of its own 8 channels (registers); then y = x * scale + shift (+ SiLU).
+// Deterministic: fixed partition, fixed summation order, no atomics.
+constexpr int kGnMaxSplits = 64;
+static inline int gn_splits(int HW) { return HW < kGnMaxSplits ? HW : kGnMaxSplits; }
+
+template <int VPT>
+__global__ void __launch_bounds__(256) k_gn2_partial(const act_t *__restrict__ x, double *__restrict__ part, int H, int W, int C,
+                                                     int S) {
+  extern __shared__ float gsm[];  // [R][C][2] per-row-lane channel sums
+  const int vecs = C >> 3, n = blockIdx.y, z = blockIdx.x, HW = H * W, cpg = C / 32;
+  const int R = VPT == 1 ? 256 / vecs : 1;
+  const int r = VPT == 1 ? threadIdx.x / vecs : 0, v = VPT == 1 ? threadIdx.x - r * vecs : threadIdx.x;
+  const int p0 = (int)((long long)HW * z / S), p1 = (int)((long long)HW * (z + 1) / S);
+  float a[VPT][8], b[VPT][8];
+#pragma unroll
+  for (int k = 0; k < VPT; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[k][j] = b[k][j] = 0.f;
+  if (r < R) {
+    constexpr int UN = VPT == 1 ? 4 : 2;  // pixels in flight per thread: the loads are issued before the first is consumed
+    for (int pb = p0 + r; pb < p1; pb += R * UN) {
+      avec q[UN][VPT];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int p = pb + u * R;
+        if (p < p1) {
+          const int y = p / W, xx = p - y * W;
+          const act_t *row = x + pad_off4(n, y, xx, H, W, C);
+#pragma unroll
+          for (int k = 0; k < VPT; ++k)
+            if (v + k * 256 < vecs) q[u][k] = ldvec(row + (v + k * 256) * 8);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        if (pb + u * R >= p1) break;
+#pragma unroll
+        for (int k = 0; k < VPT; ++k)
+          if (v + k * 256 < vecs) {
+            float f[8];
+            cvt8(q[u][k], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              a[k][j] += f[j];
+              b[k][j] = fmaf(f[j], f[j], b[k][j]);
+            }
+          }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const int vv = v + k * 256;
+      if (vv < vecs) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          gsm[((size_t)r * C + vv * 8 + j) * 2] = a[k][j];
+          gsm[((size_t)r * C + vv * 8 + j) * 2 + 1] = b[k][j];
+        }
+      }
+    }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {   // group g: its cpg channels x R row lanes, in a fixed order, in fp64
+    const int g = threadIdx.x;
     double s0 = 0.0, s1 = 0.0;
-    for (int w = 0; w < 8; ++w) {
-      s0 += sh[0][w];
-      s1 += sh[1][w];
-    }
-    part[(((size_t)n * 32 + g) * kGnSplits + z) * 2] = s0;
-    part[(((size_t)n * 32 + g) * kGnSplits + z) * 2 + 1] = s1;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c)
+      for (int q = 0; q < R; ++q) {
+        s0 += gsm[((size_t)q * C + c) * 2];
+        s1 += gsm[((size_t)q * C + c) * 2 + 1];
+      }
+    part[(((size_t)n * 32 + g) * S + z) * 2] = s0;
+    part[(((size_t)n * 32 + g) * S + z) * 2 + 1] = s1;
   }
 }
+
+template <int VPT>
 __global__ void __launch_bounds__(256) k_gn2_apply(const act_t *__restrict__ x, const double *__restrict__ part,
                                                    const float *__restrict__ gamma, const float *__restrict__ beta,
-                                                   act_t *__restrict__ out, int out_flat, int swish, long long total, int n_samples,
-                                                   int H, int W, int C, float eps) {
-  extern __shared__ float2 st[];  // [n_samples * 32] (mean, rstd)
-  const int vecs = C >> 3, cpg = C / 32;
-  const double cnt = (double)H * W * cpg;
-  for (int u = threadIdx.x; u < n_samples * 32; u += 256) {
+                                                   act_t *__restrict__ out, int out_flat, int swish, int H, int W, int C, int S,
+                                                   float eps) {
+  __shared__ float2 st[32];  // (mean, rstd) of the sample's groups
+  const int vecs = C >> 3, n = blockIdx.y, HW = H * W, cpg = C / 32;
+  {  // 8 lanes per group: each sums every 8th partial, then a fixed xor-tree over the 8 lanes (deterministic); a single
+     // thread per group walking 2 x 64 dependent L2 loads cost more than the normalisation itself
+    const int g = threadIdx.x >> 3, l = threadIdx.x & 7;
     double s0 = 0.0, s1 = 0.0;
-    for (int z = 0; z < kGnSplits; ++z) {
-      s0 += part[((size_t)u * kGnSplits + z) * 2];
-      s1 += part[((size_t)u * kGnSplits + z) * 2 + 1];
+    const double *pg = part + ((size_t)n * 32 + g) * S * 2;
+    for (int z = l; z < S; z += 8) {
+      s0 += pg[z * 2];
+      s1 += pg[z * 2 + 1];
     }
-    const double mean = s0 / cnt;
-    double var = s1 / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    st[u] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+    for (int o = 4; o; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if (l == 0) {
+      const double cnt = (double)HW * cpg, mean = s0 / cnt;
+      double var = s1 / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      st[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+    }
   }
   __syncthreads();
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const int v = (int)(i % vecs);
-    long long p = i / vecs;
-    const int xx = (int)(p % W);
-    p /= W;
-    const int y = (int)(p % H), n = (int)(p / H);
-    const int c0 = v * 8;
-    float f[8];
-    ld8(x + pad_off4(n, y, xx, H, W, C) + c0, f);
+  const int R = VPT == 1 ? 256 / vecs : 1;
+  const int r = VPT == 1 ? threadIdx.x / vecs : 0, v = VPT == 1 ? threadIdx.x - r * vecs : threadIdx.x;
+  if (r >= R) return;
+  float sc[VPT][8], sh[VPT][8];
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    const int vv = v + k * 256;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float2 mr = st[n * 32 + (c0 + j) / cpg];
-      float yv = (f[j] - mr.x) * mr.y * gamma[c0 + j] + beta[c0 + j];
-      if (swish) yv = yv / (1.f + expf(-yv));
-      f[j] = yv;
+      const int c = vv * 8 + j;
+      if (vv < vecs) {
+        const float2 mr = st[c / cpg];
+        sc[k][j] = mr.y * gamma[c];
+        sh[k][j] = beta[c] - mr.x * sc[k][j];
+      } else {
+        sc[k][j] = sh[k][j] = 0.f;
+      }
     }
-    const size_t o = out_flat ? (((size_t)n * H + y) * W + xx) * C + c0 : pad_off4(n, y, xx, H, W, C) + c0;
-    st8(out + o, f);
+  }
+  const int p0 = (int)((long long)HW * blockIdx.x / gridDim.x), p1 = (int)((long long)HW * (blockIdx.x + 1) / gridDim.x);
+  for (int p = p0 + r; p < p1; p += R) {
+    const int y = p / W, xx = p - y * W;
+    const size_t ip = pad_off4(n, y, xx, H, W, C);
+    const size_t op = out_flat ? ((size_t)n * HW + p) * C : ip;
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const int vv = v + k * 256;
+      if (vv < vecs) {
+        float f[8];
+        ld8(x + ip + vv * 8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float yv = fmaf(f[j], sc[k][j], sh[k][j]);
+          if (swish) yv = yv / (1.f + expf(-yv));
+          f[j] = yv;
+        }
+        st8(out + op + vv * 8, f);
+      }
+    }
   }
 }
 
@@ -612,19 +683,29 @@ int salun_op_set_scratch(salun_ctx *ctx, void *scratch, int64_t bytes) {
   ctx->op_scratch_floats = bytes / 4;
   return SALUN_OK;
 }
-int64_t salun_op_groupnorm_ws_floats(int n) { return (int64_t)n * 32 * kGnSplits * 4; }
+int64_t salun_op_groupnorm_ws_floats(int n) { return (int64_t)n * 32 * kGnMaxSplits * 4; }
 int salun_op_groupnorm(salun_ctx *ctx, const void *in_pad, const float *gamma, const float *beta, float *stats_ws, void *out,
                        int out_flat, int n, int H, int W, int C, float eps, int swish, void *stream) {
   SALUN_REQUIRE(ctx && in_pad && gamma && beta && stats_ws && out, "NULL argument");
-  SALUN_REQUIRE(C % 32 == 0 && C % 8 == 0 && n > 0 && n <= 1024, "C must be a multiple of 32, n <= 1024");
+  SALUN_REQUIRE(C % 32 == 0 && C % 8 == 0 && n > 0 && n <= 65535 && C <= 4096, "C must be a multiple of 32 (<= 4096)");
   SALUN_REQUIRE(((uintptr_t)stats_ws & 7) == 0, "stats_ws must be 8-byte aligned");
   SALUN_CUDA_OK(cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
   double *part = reinterpret_cast<double *>(stats_ws);
-  k_gn2_partial<<<dim3(32, n, kGnSplits), 256, 0, st>>>((const act_t *)in_pad, part, H, W, C);
-  const long long total = (long long)n * H * W * (C >> 3);
-  k_gn2_apply<<<grid1d(total, 256, 148 * 8), 256, (size_t)n * 32 * sizeof(float2), st>>>(
-      (const act_t *)in_pad, part, gamma, beta, (act_t *)out, out_flat, swish, total, n, H, W, C, eps);
+  const int HW = H * W, S = gn_splits(HW), vecs = C >> 3;
+  const int R = vecs <= 256 ? 256 / vecs : 1;
+  const size_t smem = (size_t)R * C * 2 * sizeof(float);
+  int gx = (HW + 2 * R - 1) / (2 * R);           // >= 2 pixels per row lane and CTA
+  const int cap = (148 * 6 + n - 1) / n;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  if (vecs <= 256) {
+    k_gn2_partial<1><<<dim3(S, n), 256, smem, st>>>((const act_t *)in_pad, part, H, W, C, S);
+    k_gn2_apply<1><<<dim3(gx, n), 256, 0, st>>>((const act_t *)in_pad, part, gamma, beta, (act_t *)out, out_flat, swish, H, W, C, S, eps);
+  } else {
+    k_gn2_partial<2><<<dim3(S, n), 256, smem, st>>>((const act_t *)in_pad, part, H, W, C, S);
+    k_gn2_apply<2><<<dim3(gx, n), 256, 0, st>>>((const act_t *)in_pad, part, gamma, beta, (act_t *)out, out_flat, swish, H, W, C, S, eps);
+  }
   g_launch_count += 2;
   SALUN_CUDA_OK(cudaGetLastError());
   return SALUN_OK;
