@@ -143,6 +143,31 @@ __device__ __forceinline__ void wop_store(wop_t *__restrict__ row, int j, int Kp
   row[j] = __float2bfloat16(w);
 #endif
 }
+// eight consecutive operand elements j0 .. j0+7 (j0 % 8 == 0, row 16-byte aligned): 16-byte stores
+__device__ __forceinline__ void wop_store8(wop_t *__restrict__ row, int j0, int Kp, const float (&f)[8]) {
+#ifdef SALUN_SPLIT
+  uint32_t hh[8], ll[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(f[i]);
+    const __nv_bfloat16 l = __float2bfloat16_rn(f[i] - __bfloat162float(h));
+    const uint32_t hb = __bfloat16_as_ushort(h), lb = __bfloat16_as_ushort(l);
+    hh[i] = hb | (hb << 16);
+    ll[i] = lb | (lb << 16);
+  }
+  uint4 *ph = reinterpret_cast<uint4 *>(row + 2 * (size_t)j0), *pl = reinterpret_cast<uint4 *>(row + 2 * (size_t)Kp + 2 * (size_t)j0);
+  ph[0] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+  ph[1] = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+  pl[0] = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+  pl[1] = make_uint4(ll[4], ll[5], ll[6], ll[7]);
+#else
+  (void)Kp;
+  __nv_bfloat162 h[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<uint4 *>(row + j0) = *reinterpret_cast<const uint4 *>(h);
+#endif
+}
 #endif  // __CUDACC__
 
 }  // namespace salun

@@ -378,53 +378,9 @@ __global__ void __launch_bounds__(256) k_linear_rows_f32(const float *__restrict
 // ------------------------------------------------------------------------------------------------ multi-head attention
 // (sample, head) unit g = b * heads + h.  Q rows are padded to Tqp (multiple of 128), keys to Tkp (multiple of 128), the head
 // width to dp (multiple of 64): zero padding, masked in the softmax.
-__global__ void __launch_bounds__(256) k_heads_pack_q(const act_t *__restrict__ q, act_t *__restrict__ dst, long long total, int Tq,
-                                                      int Tqp, int C, int heads, int d, int dp) {
-  const int vecs = dp >> 3;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const int v = (int)(i % vecs);
-    long long r = i / vecs;
-    const int t = (int)(r % Tqp);
-    const long long g = r / Tqp;
-    const int h = (int)(g % heads);
-    const long long b = g / heads;
-    avec val = avec_zero();
-    if (t < Tq && v * 8 < d) val = ldvec(q + (b * Tq + t) * C + h * d + v * 8);
-    stvec(dst + (g * Tqp + t) * dp + v * 8, val);
-  }
-}
-// K as the B operand of S = Q K^T: operand row (g * Tkp + j), logical length dp
-__global__ void __launch_bounds__(256) k_heads_pack_k(const act_t *__restrict__ k, wop_t *__restrict__ dst, long long total, int Tk,
-                                                      int Tkp, int C, int heads, int d, int dp) {
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const int c = (int)(i % dp);
-    long long r = i / dp;
-    const int j = (int)(r % Tkp);
-    const long long g = r / Tkp;
-    const int h = (int)(g % heads);
-    const long long b = g / heads;
-    float v = 0.f;
-    if (j < Tk && c < d) v = act_to_float(k[(b * Tk + j) * C + h * d + c]);
-    wop_store(dst + (size_t)(g * Tkp + j) * dp * kWopK, c, dp, v);
-  }
-}
-// V^T as the B operand of O = P V: operand row (g * dp + c), logical length Tkp
-__global__ void __launch_bounds__(256) k_heads_pack_vt(const act_t *__restrict__ v, wop_t *__restrict__ dst, long long total, int Tk,
-                                                       int Tkp, int C, int heads, int d, int dp) {
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const int j = (int)(i % Tkp);
-    long long r = i / Tkp;
-    const int c = (int)(r % dp);
-    const long long g = r / dp;
-    const int h = (int)(g % heads);
-    const long long b = g / heads;
-    float val = 0.f;
-    if (j < Tk && c < d) val = act_to_float(v[(b * Tk + j) * C + h * d + c]);
-    wop_store(dst + (size_t)(g * dp + c) * Tkp * kWopK, j, Tkp, val);
-  }
-}
-// The three packs above as ONE launch (blocks [0, gq) pack Q, [gq, gq + gk) pack K, the rest pack V^T), reading q / k / v with
-// their own row strides -- so q | k | v may be column slices of one fused projection output [rows][3C].
+// Head packs as ONE launch (blocks [0, gq) pack Q as the A operand, [gq, gq + gk) pack K as the B operand of S = Q K^T -- operand
+// row (g * Tkp + j), logical length dp --, the rest pack V^T as the B operand of O = P V -- operand row (g * dp + c), logical
+// length Tkp), reading q / k / v with their own row strides: they may be column slices of one fused projection output.
 __global__ void __launch_bounds__(256) k_heads_pack_all(const act_t *__restrict__ q, int ldq, const act_t *__restrict__ k, int ldk,
                                                         const act_t *__restrict__ v, int ldv, act_t *__restrict__ Qh,
                                                         wop_t *__restrict__ Kh, wop_t *__restrict__ Vt, int gq, int gk, long long totq,
@@ -444,29 +400,50 @@ __global__ void __launch_bounds__(256) k_heads_pack_all(const act_t *__restrict_
       stvec(Qh + (g * Tqp + t) * dp + vv * 8, val);
     }
   } else if ((int)blockIdx.x < gq + gk) {
+    // K: one 8-channel vector of one key per thread (totk counts vectors)
+    const int dv = dp >> 3;
     for (long long i = (long long)(blockIdx.x - gq) * 256 + threadIdx.x; i < totk; i += (long long)gk * 256) {
-      const int c = (int)(i % dp);
-      long long r = i / dp;
+      const int vv = (int)(i % dv);
+      long long r = i / dv;
       const int j = (int)(r % Tkp);
       const long long g = r / Tkp;
       const int h = (int)(g % heads);
       const long long b = g / heads;
-      float val = 0.f;
-      if (j < Tk && c < d) val = act_to_float(k[(b * Tk + j) * ldk + h * d + c]);
-      wop_store(Kh + (size_t)(g * Tkp + j) * dp * kWopK, c, dp, val);
+      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (j < Tk && vv * 8 < d) ld8(k + (b * Tk + j) * ldk + h * d + vv * 8, f);
+      wop_store8(Kh + (size_t)(g * Tkp + j) * dp * kWopK, vv * 8, dp, f);
     }
   } else {
-    const int gv = gridDim.x - gq - gk;
-    for (long long i = (long long)(blockIdx.x - gq - gk) * 256 + threadIdx.x; i < totv; i += (long long)gv * 256) {
-      const int j = (int)(i % Tkp);
-      long long r = i / Tkp;
-      const int c = (int)(r % dp);
-      const long long g = r / dp;
+    // V^T: 64 keys x 64 channels tiles through shared memory (coalesced reads along channels, 16-byte stores along keys);
+    // totv counts tiles
+    __shared__ float tile[64][65];
+    const int gv = gridDim.x - gq - gk, jt_n = Tkp >> 6, ct_n = dp >> 6;
+    for (long long t = blockIdx.x - gq - gk; t < totv; t += gv) {
+      const int ct = (int)(t % ct_n);
+      long long r = t / ct_n;
+      const int jt = (int)(r % jt_n);
+      const long long g = r / jt_n;
       const int h = (int)(g % heads);
       const long long b = g / heads;
-      float val = 0.f;
-      if (j < Tk && c < d) val = act_to_float(v[(b * Tk + j) * ldv + h * d + c]);
-      wop_store(Vt + (size_t)(g * dp + c) * Tkp * kWopK, j, Tkp, val);
+      __syncthreads();
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        const int idx = threadIdx.x + 256 * w, jj = idx >> 3, vv = idx & 7;
+        const int j = jt * 64 + jj, c0 = ct * 64 + vv * 8;
+        float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (j < Tk && c0 < d) ld8(v + (b * Tk + j) * ldv + h * d + c0, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) tile[jj][vv * 8 + e] = f[e];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        const int idx = threadIdx.x + 256 * w, cc = idx >> 3, jv = idx & 7;
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = tile[jv * 8 + e][cc];
+        wop_store8(Vt + (size_t)(g * dp + ct * 64 + cc) * Tkp * kWopK, jt * 64 + jv * 8, Tkp, f);
+      }
     }
   }
 }
@@ -825,8 +802,9 @@ int salun_sd_attention_ld(salun_ctx *ctx, void *ws, int64_t ws_bytes, const void
   float *S = (float *)(w + off[3]);
   act_t *P = (act_t *)(w + off[4]), *Oh = (act_t *)(w + off[5]);
   {
-    const long long totq = G * Tqp * (dp >> 3), totk = G * Tkp * dp, totv = G * dp * Tkp;
-    const int gq = grid1d(totq, 256, 148 * 4), gk = grid1d(totk, 256, 148 * 6), gv = grid1d(totv, 256, 148 * 6);
+    const long long totq = G * Tqp * (dp >> 3), totk = G * Tkp * (dp >> 3), totv = G * (Tkp >> 6) * (dp >> 6);  // vectors | vectors | tiles
+    const int gq = grid1d(totq, 256, 148 * 4), gk = grid1d(totk, 256, 148 * 4);
+    const int gv = (int)(totv < 148 * 4 ? totv : 148 * 4);
     k_heads_pack_all<<<gq + gk + gv, 256, 0, st>>>((const act_t *)q, ldq, (const act_t *)k, ldk, (const act_t *)v, ldv, Qh, Kh, Vt, gq,
                                                   gk, totq, totk, totv, Tq, Tqp, Tk, Tkp, heads, d, dp);
     ++g_launch_count;
