@@ -182,7 +182,7 @@ def run_reference(args):
     cb = cpu_baselines(ddpm=not args.no_ddpm, resnet_steps=max(1, min(args.steps, 3)))
     val = cb["resnet"]["value"]
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": METRIC_STRONG if (args.scaling == "strong" and args.gpus > 1) else METRIC, "value": val, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "ResNet-18/CIFAR-10 SalUn RL masked unlearn step, batch 256, mask ratio 0.5", "global_batch": BATCH},
